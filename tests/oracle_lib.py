@@ -1,0 +1,348 @@
+"""ctypes binding of the CPU oracle (oracle/libpslam_oracle.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py.  The product package
+(srrg2_proslam_b200/) never imports this module.
+"""
+import ctypes as C
+import pathlib
+import subprocess
+
+import numpy as np
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+ORACLE_DIR = ROOT / "oracle"
+GOLDEN = ROOT / "tests" / "golden"
+
+_lib = None
+
+
+def build():
+    subprocess.run(["make", "-C", str(ORACLE_DIR), "-s"], check=True)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        so = ORACLE_DIR / "libpslam_oracle.so"
+        if not so.exists():
+            build()
+        _lib = C.CDLL(str(so))
+        _lib.orc_pf_create.restype = C.c_void_p
+    return _lib
+
+
+def _p(a, t=None):
+    if a is None:
+        return None
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _img(img):
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    assert img.ndim == 2
+    return img
+
+
+def extract_cfg(threshold=10, nms=1, target=500, nh=3, nv=3):
+    return np.array([threshold, nms, target, nh, nv], dtype=np.float32)
+
+
+def load_gray(name):
+    import cv2
+    im = cv2.imread(str(GOLDEN / name), cv2.IMREAD_UNCHANGED)
+    assert im is not None, name
+    return im
+
+
+def fast_detect(img, thr, nms=True, mask=None, cap=200000):
+    img = _img(img)
+    xy = np.zeros((cap, 2), np.float32)
+    resp = np.zeros(cap, np.float32)
+    m = None if mask is None else _img(mask)
+    n = lib().orc_fast_detect(_p(img), img.shape[0], img.shape[1], img.shape[1], int(thr), int(nms),
+                              _p(m), cap, _p(xy), _p(resp))
+    assert n <= cap
+    return xy[:n].copy(), resp[:n].copy()
+
+
+def blur7(img):
+    img = _img(img)
+    out = np.zeros_like(img)
+    lib().orc_blur7(_p(img), img.shape[0], img.shape[1], img.shape[1], _p(out))
+    return out
+
+
+def detect_binned(img, cfg, cap=200000):
+    img = _img(img)
+    xy = np.zeros((cap, 2), np.float32)
+    resp = np.zeros(cap, np.float32)
+    n = lib().orc_detect_binned(_p(img), img.shape[0], img.shape[1], img.shape[1], _p(cfg), cap,
+                                _p(xy), _p(resp))
+    assert n <= cap
+    return xy[:n].copy(), resp[:n].copy()
+
+
+def extract_binned(img, cfg, mask=None, cap=100000):
+    """-> dict(xy [N,2] f32, response [N], intensity [N], desc [N,32] u8)"""
+    img = _img(img)
+    xy = np.zeros((cap, 2), np.float32)
+    resp = np.zeros(cap, np.float32)
+    inten = np.zeros(cap, np.float32)
+    desc = np.zeros((cap, 32), np.uint8)
+    m = None if mask is None else _img(mask)
+    n = lib().orc_extract_binned(_p(img), img.shape[0], img.shape[1], img.shape[1], _p(cfg), _p(m),
+                                 cap, _p(xy), _p(resp), _p(inten), _p(desc))
+    assert n <= cap
+    return dict(xy=xy[:n].copy(), response=resp[:n].copy(), intensity=inten[:n].copy(),
+                desc=desc[:n].copy())
+
+
+def bin_lut(rows, cols, nh, nv, target):
+    lut = np.zeros((rows, cols), np.int32)
+    q = C.c_int64(0)
+    lib().orc_bin_lut(rows, cols, nh, nv, target, _p(lut), C.byref(q))
+    return lut, q.value
+
+
+def std_sort(keys, descending=True):
+    """permutation libstdc++ std::sort produces for these keys (payload = original index)"""
+    keys = np.ascontiguousarray(keys, np.float32)
+    perm = np.arange(len(keys), dtype=np.int32)
+    fn = lib().orc_std_sort_desc if descending else lib().orc_std_sort_asc
+    fn(len(keys), _p(keys), _p(perm))
+    return perm
+
+
+def hamming_matrix(df, dm):
+    df = np.ascontiguousarray(df, np.uint8).reshape(-1, 32)
+    dm = np.ascontiguousarray(dm, np.uint8).reshape(-1, 32)
+    out = np.zeros((len(df), len(dm)), np.int32)
+    lib().orc_hamming_matrix(len(df), _p(df), len(dm), _p(dm), _p(out))
+    return out
+
+
+def bf_best2(df, dm, threads=1):
+    df = np.ascontiguousarray(df, np.uint8).reshape(-1, 32)
+    dm = np.ascontiguousarray(dm, np.uint8).reshape(-1, 32)
+    best = np.zeros(len(df), np.int32)
+    second = np.zeros(len(df), np.int32)
+    idx = np.zeros(len(df), np.int32)
+    lib().orc_bf_best2(len(df), _p(df), len(dm), _p(dm), int(threads), _p(best), _p(second), _p(idx))
+    return best, second, idx
+
+
+def _corr_out(cap):
+    return np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap, np.float32)
+
+
+def match_epipolar(xy_f, desc_f, xy_m, desc_m, max_dist=50.0, ratio=0.9, max_disp=100, thickness=0):
+    xy_f = np.ascontiguousarray(xy_f, np.float32).reshape(-1, 2)
+    xy_m = np.ascontiguousarray(xy_m, np.float32).reshape(-1, 2)
+    desc_f = np.ascontiguousarray(desc_f, np.uint8).reshape(-1, 32)
+    desc_m = np.ascontiguousarray(desc_m, np.uint8).reshape(-1, 32)
+    cap = max(len(xy_f), 1) * (2 * thickness + 1)
+    fi, mi, d = _corr_out(cap)
+    n = lib().orc_match_epipolar(len(xy_f), _p(xy_f), _p(desc_f), len(xy_m), _p(xy_m), _p(desc_m),
+                                 C.c_float(max_dist), C.c_float(ratio), int(max_disp),
+                                 int(thickness), cap, _p(fi), _p(mi), _p(d))
+    assert n <= cap
+    return fi[:n].copy(), mi[:n].copy(), d[:n].copy()
+
+
+def match_bruteforce(desc_f, desc_m, max_dist=50.0, ratio=0.9):
+    desc_f = np.ascontiguousarray(desc_f, np.uint8).reshape(-1, 32)
+    desc_m = np.ascontiguousarray(desc_m, np.uint8).reshape(-1, 32)
+    cap = max(min(len(desc_f), len(desc_m)), 1)
+    fi, mi, d = _corr_out(cap)
+    n = lib().orc_match_bruteforce(len(desc_f), _p(desc_f), len(desc_m), _p(desc_m),
+                                   C.c_float(max_dist), C.c_float(ratio), cap, _p(fi), _p(mi), _p(d))
+    assert n <= cap
+    return fi[:n].copy(), mi[:n].copy(), d[:n].copy()
+
+
+def stereo_adaptor(left, right, cfg, matcher="epipolar", max_dist=50.0, ratio=0.9, max_disp=100,
+                   thickness=0, cap=20000):
+    left, right = _img(left), _img(right)
+    mc = np.array([max_dist, ratio, max_disp, thickness], np.float32)
+    uvuv = np.zeros((cap, 4), np.float32)
+    inten = np.zeros(cap, np.float32)
+    desc = np.zeros((cap, 32), np.uint8)
+    nl, nr, nm = C.c_int(0), C.c_int(0), C.c_int(0)
+    n = lib().orc_stereo_adaptor(_p(left), _p(right), left.shape[0], left.shape[1], left.shape[1],
+                                 _p(cfg), 0 if matcher == "epipolar" else 1, _p(mc), cap, _p(uvuv),
+                                 _p(inten), _p(desc), C.byref(nl), C.byref(nr), C.byref(nm))
+    assert n <= cap
+    return dict(uvuv=uvuv[:n].copy(), intensity=inten[:n].copy(), desc=desc[:n].copy(),
+                n_left=nl.value, n_right=nr.value, n_matches=nm.value)
+
+
+def mono_depth_adaptor(img, depth, cfg, depth_scale=1.0, cap=20000):
+    img = _img(img)
+    is_float = depth.dtype == np.float32
+    depth = np.ascontiguousarray(depth, np.float32 if is_float else np.uint16)
+    uvd = np.zeros((cap, 3), np.float32)
+    inten = np.zeros(cap, np.float32)
+    desc = np.zeros((cap, 32), np.uint8)
+    nf = C.c_int(0)
+    n = lib().orc_mono_depth_adaptor(_p(img), img.shape[0], img.shape[1], img.shape[1], _p(depth),
+                                     int(is_float), depth.shape[1], C.c_float(depth_scale), _p(cfg),
+                                     cap, _p(uvd), _p(inten), _p(desc), C.byref(nf))
+    return dict(uvd=uvd[:n].copy(), intensity=inten[:n].copy(), desc=desc[:n].copy(),
+                n_features=nf.value)
+
+
+def triangulate(uvuv, K, b_x, min_disparity=1.0, infinity_depth=None):
+    uvuv = np.ascontiguousarray(uvuv, np.float32).reshape(-1, 4)
+    K = np.ascontiguousarray(K, np.float32).reshape(9)
+    if infinity_depth is None:
+        infinity_depth = float(np.sqrt(np.finfo(np.float32).max))
+    xyz = np.zeros((len(uvuv), 3), np.float32)
+    ninv = C.c_int(0)
+    lib().orc_triangulate(len(uvuv), _p(uvuv), _p(K), C.c_float(b_x), C.c_float(min_disparity),
+                          C.c_float(infinity_depth), _p(xyz), C.byref(ninv))
+    return xyz, ninv.value
+
+
+def project(xyz, pose12, K, rows, cols, rmin=0.1, rmax=1000.0):
+    xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+    pose12 = np.ascontiguousarray(pose12, np.float32).reshape(12)
+    K = np.ascontiguousarray(K, np.float32).reshape(9)
+    uvz = np.zeros((len(xyz), 3), np.float32)
+    idx = np.zeros(len(xyz), np.int32)
+    n = lib().orc_project(len(xyz), _p(xyz), _p(pose12), _p(K), rows, cols, C.c_float(rmin),
+                          C.c_float(rmax), _p(uvz), _p(idx))
+    return uvz[:n].copy(), idx[:n].copy()
+
+
+SHAPES = {"square": 0, "circle": 1, "rhombus": 2}
+
+
+class ProjectiveFinder:
+    """Stateful oracle of CorrespondenceFinderProjective{Square,Circle,Rhombus}."""
+
+    def __init__(self, K, rows, cols, shape="circle", max_desc_dist=50.0, ratio=0.9,
+                 min_matching_ratio=0.25, min_desc_dist=25.0, desc_step=5.0, max_radius=100,
+                 min_radius=10, radius_step=5, min_iterations=10, max_change_norm=1e-5,
+                 iters_per_projection=25, range_min=0.1, range_max=1000.0):
+        f = np.array([max_desc_dist, ratio, min_matching_ratio, min_desc_dist, desc_step, max_radius,
+                      min_radius, radius_step, min_iterations, max_change_norm, iters_per_projection,
+                      SHAPES[shape]], np.float32)
+        p = np.concatenate([np.asarray(K, np.float32).reshape(9),
+                            np.array([rows, cols, range_min, range_max], np.float32)])
+        self.h = C.c_void_p(lib().orc_pf_create(_p(f), _p(p)))
+        self.cap = 1
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_pf_destroy(self.h)
+            self.h = None
+
+    def set_fixed(self, coords, desc):
+        coords = np.ascontiguousarray(coords, np.float32)
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        self.cap = max(self.cap, len(coords) + 1)
+        lib().orc_pf_set_fixed(self.h, len(coords), _p(coords), coords.shape[1], _p(desc))
+
+    def set_moving(self, xyz, desc):
+        xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        self.ncap = len(xyz) + 1
+        lib().orc_pf_set_moving(self.h, len(xyz), _p(xyz), _p(desc))
+
+    def set_estimate(self, pose12):
+        pose12 = np.ascontiguousarray(pose12, np.float32).reshape(12)
+        lib().orc_pf_set_estimate(self.h, _p(pose12))
+
+    def get_estimate(self):
+        p = np.zeros(12, np.float32)
+        lib().orc_pf_get_estimate(self.h, _p(p))
+        return p
+
+    def set_radius(self, r):
+        lib().orc_pf_set_radius(self.h, int(r))
+
+    def set_descriptor_distance(self, d):
+        lib().orc_pf_set_descriptor_distance(self.h, C.c_float(d))
+
+    def compute(self):
+        fi, mi, d = _corr_out(self.cap)
+        n = lib().orc_pf_compute(self.h, self.cap, _p(fi), _p(mi), _p(d))
+        assert n <= self.cap
+        return fi[:n].copy(), mi[:n].copy(), d[:n].copy()
+
+    def state(self):
+        s = np.zeros(6, np.float32)
+        lib().orc_pf_state(self.h, _p(s))
+        return dict(radius=int(s[0]), descriptor_distance=float(s[1]), iteration=int(s[2]),
+                    converged=bool(s[3]), searches=int(s[4]), n_projected=int(s[5]))
+
+    def candidates(self):
+        out = np.zeros((self.ncap, 5), np.int32)
+        n = lib().orc_pf_candidates(self.h, self.ncap, _p(out))
+        return out[:n].copy()
+
+    def lattice(self):
+        out = np.zeros(self.cap, np.int32)
+        n = lib().orc_pf_lattice(self.h, self.cap, _p(out))
+        return out[:n].copy()
+
+
+FACTORS = {"stereo": 0, "depth": 1, "mono": 2}
+ROBUST = {"none": 0, "saturated": 1, "clamp": 2}
+
+
+def linearize_cfg(kind, K, cols, rows, baseline=(0, 0, 0), mean_disparity=0.0,
+                  robustifier="saturated", chi_threshold=25.0):
+    return np.concatenate([[FACTORS[kind]], np.asarray(K, np.float64).reshape(9), [cols, rows],
+                           np.asarray(baseline, np.float64), [mean_disparity, ROBUST[robustifier],
+                                                              chi_threshold]]).astype(np.float64)
+
+
+def linearize(lcfg, pose12, moving_xyz, fixed_meas, corr_fixed, corr_moving, info_diag, fp32=False):
+    pose12 = np.ascontiguousarray(pose12, np.float64).reshape(12)
+    moving_xyz = np.ascontiguousarray(moving_xyz, np.float64).reshape(-1, 3)
+    fixed_meas = np.ascontiguousarray(fixed_meas, np.float64)
+    cf = np.ascontiguousarray(corr_fixed, np.int32)
+    cm = np.ascontiguousarray(corr_moving, np.int32)
+    info = np.ascontiguousarray(info_diag, np.float64).reshape(-1, 3)
+    assert len(info) == len(fixed_meas)
+    H = np.zeros(36, np.float64)
+    b = np.zeros(6, np.float64)
+    st = np.zeros(4, np.float64)
+    fn = lib().orc_linearize_f32 if fp32 else lib().orc_linearize_f64
+    fn(_p(lcfg), _p(pose12), len(moving_xyz), _p(moving_xyz), len(fixed_meas), _p(fixed_meas),
+       fixed_meas.shape[1], len(cf), _p(cf), _p(cm), _p(info), _p(H), _p(b), _p(st))
+    return H.reshape(6, 6), b, dict(chi=st[0], inliers=int(st[1]), outliers=int(st[2]),
+                                    suppressed=int(st[3]))
+
+
+def gn_step(H, b, damping, pose12):
+    H = np.ascontiguousarray(H, np.float64).reshape(36)
+    b = np.ascontiguousarray(b, np.float64).reshape(6)
+    pose = np.ascontiguousarray(pose12, np.float64).reshape(12).copy()
+    dx = np.zeros(6, np.float64)
+    rc = lib().orc_gn_step_f64(_p(H), _p(b), C.c_double(damping), _p(pose), _p(dx))
+    return rc, pose, dx
+
+
+def t2tnq(pose12):
+    pose12 = np.ascontiguousarray(pose12, np.float64).reshape(12)
+    v = np.zeros(6, np.float64)
+    lib().orc_t2tnq_f64(_p(pose12), _p(v))
+    return v
+
+
+def pose_inverse(pose12):
+    pose12 = np.ascontiguousarray(pose12, np.float64).reshape(12)
+    o = np.zeros(12, np.float64)
+    lib().orc_pose_inverse_f64(_p(pose12), _p(o))
+    return o
+
+
+def pose_mul(a, b):
+    a = np.ascontiguousarray(a, np.float64).reshape(12)
+    b = np.ascontiguousarray(b, np.float64).reshape(12)
+    o = np.zeros(12, np.float64)
+    lib().orc_pose_mul_f64(_p(a), _p(b), _p(o))
+    return o
