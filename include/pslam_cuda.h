@@ -1,0 +1,226 @@
+/* =============================================================================
+ * pslam_cuda.h -- C ABI of the B200-native (sm_100a) srrg2_proslam frontend.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no
+ * torch / Eigen / OpenCV types.  Each entry point names the reference interface it
+ * replaces (paths relative to the reference root; `.../` abbreviates
+ * `srrg2_proslam/src/srrg2_proslam/`).  The host-side mirror of the srrg2 plugin
+ * classes (srrg2_proslam_b200/host/) and the Python test harness both call ONLY these
+ * functions.  There is no CPU fallback: every compute call needs a CUDA device and
+ * returns PSLAM_E_CUDA when none is usable.
+ *
+ * Conventions
+ *   - return value: 0 (PSLAM_OK) or a negative PSLAM_E_* code; functions that produce
+ *     a variable-length result return the element count (>= 0) instead.
+ *   - `*_dev` variants take DEVICE pointers (inputs already resident in HBM) and leave
+ *     their results on the device inside the context; the plain variants take HOST
+ *     pointers and do the host<->device copies themselves (these are the calls the
+ *     reference-side host code makes).
+ *   - descriptors are 256 bit, stored as 32 bytes (bit k of byte i = ORB pair 8i+k),
+ *     i.e. the row layout of the cv::Mat the reference keeps per point.
+ *   - poses are row-major 3x4 [R|t].  K is row-major 3x3.
+ * ========================================================================== */
+#ifndef PSLAM_CUDA_H
+#define PSLAM_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSLAM_OK 0
+#define PSLAM_E_INVALID (-1)  /* bad argument / configuration (reference: throw std::runtime_error) */
+#define PSLAM_E_CUDA (-2)     /* CUDA runtime error, see pslam_last_error() */
+#define PSLAM_E_CAPACITY (-3) /* a context limit (pslam_limits) was exceeded; nothing was truncated silently */
+#define PSLAM_E_NOT_SPD (-4)  /* linear system not positive definite */
+
+typedef struct pslam_ctx pslam_ctx;
+
+/* Context limits: size the device-resident buffers once (no allocation on the hot path). */
+typedef struct {
+  int max_images;        /* images per batch (a stereo pair is 2 images) */
+  int max_rows;          /* image height limit */
+  int max_cols;          /* image width limit */
+  int max_features;      /* selected features per image, <= 8192 */
+  int max_raw_per_bin;   /* FAST corners (after NMS) per detection region before selection */
+  int max_bins;          /* detection regions per image (nh * nv) */
+} pslam_limits;
+
+/* PARAMs of IntensityFeatureExtractorBinned_ (.../sensor_processing/feature_extractors/
+ * intensity_feature_extractor_base.h:24-58, intensity_feature_extractor_binned.h:17-27).
+ * detector_type is FAST and descriptor_type ORB-256 (the only pair the shipped configs use). */
+typedef struct {
+  float detector_threshold;
+  int enable_non_maximum_suppression;
+  int target_number_of_keypoints;
+  int number_of_detectors_horizontal;
+  int number_of_detectors_vertical;
+} pslam_extract_cfg;
+
+/* PARAMs of CorrespondenceFinderDescriptorBased{Bruteforce,Epipolar}
+ * (.../registration/correspondence_finders/correspondence_finder_descriptor_based_bruteforce.h:23-37,
+ *  correspondence_finder_descriptor_based_epipolar.h:24-34). */
+typedef struct {
+  float maximum_descriptor_distance;
+  float maximum_distance_ratio_to_second_best;
+  int maximum_disparity_pixels;
+  int epipolar_line_thickness_pixels;
+} pslam_match_cfg;
+
+/* ---- lifecycle ----------------------------------------------------------------- */
+int pslam_create(int device, const pslam_limits* limits, pslam_ctx** out);
+void pslam_destroy(pslam_ctx* ctx);
+const char* pslam_last_error(const pslam_ctx* ctx);
+const char* pslam_version(void);
+/* number of kernels this context has launched since creation (bench.py's gpu_launches) */
+long long pslam_launch_count(const pslam_ctx* ctx);
+/* the CUDA stream all of this context's kernels run on (cudaStream_t as void*) */
+void* pslam_stream(const pslam_ctx* ctx);
+int pslam_synchronize(pslam_ctx* ctx);
+
+/* ---- stage 1: detect + select + describe ---------------------------------------
+ * Replaces IntensityFeatureExtractorBinned_::compute(cv::Mat)
+ *   (.../feature_extractors/intensity_feature_extractor_base.cpp:55-85 calling
+ *    intensity_feature_extractor_binned.cpp:115-208 and base.cpp:45-53).
+ * Output order, coordinates, response, intensity and descriptor bytes are those of the
+ * reference; `mask` (rows x cols, non-zero = region of interest) mirrors
+ * setKeypointDetectionMask (base.h:128-132) and, as in the reference, disables binning.
+ * xy: 2 floats per feature; desc: 32 bytes per feature.  Returns the feature count. */
+int pslam_extract_binned(pslam_ctx* ctx, const uint8_t* image, int rows, int cols, int stride,
+                         const pslam_extract_cfg* cfg, const uint8_t* mask_or_null, int capacity,
+                         float* xy, float* response, float* intensity, uint8_t* desc);
+
+/* Batched, device-resident variant: `n_images` images of identical size, image i at
+ * d_images + i * image_pitch_bytes.  Results stay in the context's feature store
+ * (slot i <- image i) for the matchers; read them back with pslam_download_features. */
+int pslam_extract_binned_batch_dev(pslam_ctx* ctx, const uint8_t* d_images, int n_images, int rows,
+                                   int cols, int stride, long long image_pitch_bytes,
+                                   const pslam_extract_cfg* cfg);
+int pslam_download_features(pslam_ctx* ctx, int slot, int capacity, float* xy, float* response,
+                            float* intensity, uint8_t* desc);
+/* counts of all slots of the last batch (n ints) */
+int pslam_download_feature_counts(pslam_ctx* ctx, int n_images, int* counts);
+
+/* Intermediate products, exposed for stage-level parity tests:
+ * FAST+NMS keypoints in row-major order (cv::FastFeatureDetector::detect, called at
+ * intensity_feature_extractor_binned.cpp:141-146) and the ORB blur (cv::ORB::compute's
+ * 7x7 Gaussian, base.cpp:52). */
+int pslam_fast_detect(pslam_ctx* ctx, const uint8_t* image, int rows, int cols, int stride,
+                      int threshold, int nms, int capacity, float* xy, float* response);
+int pslam_blur7(pslam_ctx* ctx, const uint8_t* image, int rows, int cols, int stride, uint8_t* out);
+
+/* ---- stage 2a: stereo epipolar matching -----------------------------------------
+ * Replaces CorrespondenceFinderDescriptorBasedEpipolar::compute
+ *   (.../correspondence_finders/correspondence_finder_descriptor_based_epipolar_impl.cpp:44-219).
+ * fixed = left, moving = right.  Output order = the reference's scan order. */
+int pslam_match_epipolar(pslam_ctx* ctx, int n_fixed, const float* xy_fixed, const uint8_t* desc_fixed,
+                         int n_moving, const float* xy_moving, const uint8_t* desc_moving,
+                         const pslam_match_cfg* cfg, int capacity, int* fixed_idx, int* moving_idx,
+                         float* distance);
+
+/* ---- stage 1+2a fused per stereo pair: the measurement adaptor ------------------
+ * Replaces RawDataPreprocessorStereoProjective::compute
+ *   (.../sensor_processing/raw_data_preprocessor_stereo_projective.cpp:46-134):
+ * extract left and right, epipolar match, emit (uL,vL,uR,vR) + left descriptor/intensity,
+ * dropping negative disparities (:120-128).  Host buffers in and out. */
+int pslam_stereo_adaptor(pslam_ctx* ctx, const uint8_t* left, const uint8_t* right, int rows, int cols,
+                         int stride, const pslam_extract_cfg* ecfg, const pslam_match_cfg* mcfg,
+                         int capacity, float* uvuv, float* intensity, uint8_t* desc);
+
+/* Batched, device-resident: images 2p (left) and 2p+1 (right) of pair p.  Runs the whole
+ * frame-independent part of the frontend for n_pairs pairs; results stay on the device
+ * (stereo slots p) and can be fetched per pair.  Returns PSLAM_OK. */
+int pslam_stereo_frontend_batch_dev(pslam_ctx* ctx, const uint8_t* d_images, int n_pairs, int rows,
+                                    int cols, int stride, long long image_pitch_bytes,
+                                    const pslam_extract_cfg* ecfg, const pslam_match_cfg* mcfg);
+/* same, HOST images (pinned or pageable): copies inside the call */
+int pslam_stereo_frontend_batch(pslam_ctx* ctx, const uint8_t* h_images, int n_pairs, int rows,
+                                int cols, int stride, long long image_pitch_bytes,
+                                const pslam_extract_cfg* ecfg, const pslam_match_cfg* mcfg);
+int pslam_download_stereo_counts(pslam_ctx* ctx, int n_pairs, int* counts);
+/* per pair: 4 floats (uL,vL,uR,vR), left feature index, right feature index, distance */
+int pslam_download_stereo_points(pslam_ctx* ctx, int pair, int capacity, float* uvuv, int* left_idx,
+                                 int* right_idx, float* distance);
+
+/* ---- stage 2b: exhaustive Hamming matching --------------------------------------
+ * Replaces CorrespondenceFinderDescriptorBasedBruteforce::compute
+ *   (.../correspondence_finders/correspondence_finder_descriptor_based_bruteforce_impl.cpp:6-294).
+ * pslam_match_bruteforce returns the bijective, Lowe-checked correspondence set in the
+ * reference's output order.  pslam_bf_best2* is the raw sweep (per fixed row: smallest and
+ * second smallest distance and the argmin, first index wins ties); `second` is INT32_MAX
+ * and `best_idx` -1 where absent. */
+int pslam_match_bruteforce(pslam_ctx* ctx, int n_fixed, const uint8_t* desc_fixed, int n_moving,
+                           const uint8_t* desc_moving, const pslam_match_cfg* cfg, int capacity,
+                           int* fixed_idx, int* moving_idx, float* distance);
+int pslam_bf_best2(pslam_ctx* ctx, int n_fixed, const uint8_t* desc_fixed, int n_moving,
+                   const uint8_t* desc_moving, int32_t* best, int32_t* second, int32_t* best_idx);
+int pslam_bf_best2_dev(pslam_ctx* ctx, int n_fixed, const uint32_t* d_desc_fixed, int n_moving,
+                       const uint32_t* d_desc_moving, int32_t* d_best, int32_t* d_second,
+                       int32_t* d_best_idx);
+
+/* ---- stage 2c: projective window matching ---------------------------------------
+ * Replaces the device-worthy part of CorrespondenceFinderProjective{Square,Circle,Rhombus}:
+ * PointProjectorPinhole_::compute + _initializeDatabase + _findNearestNeighbors +
+ * _filterCorrespondences
+ *   (.../correspondence_finders/correspondence_finder_projective_base_impl.cpp:39-102,165-208,
+ *    ..._square_impl.cpp:7-118, ..._circle_impl.cpp:7-94, ..._rhombus_impl.cpp:7-93).
+ * The adaptive state machine (:104-293) stays in the host wrapper.  Output is in the order the
+ * reference's std::unordered_map iteration yields.  shape: 0 square, 1 circle, 2 rhombus. */
+typedef struct {
+  float K[9];
+  int canvas_rows, canvas_cols;
+  float range_min, range_max;
+  int shape;
+  int search_radius_pixels;
+  float descriptor_distance;                   /* current (adaptive) threshold */
+  float maximum_distance_ratio_to_second_best;
+} pslam_projective_cfg;
+
+/* setFixed (+ _initializeDatabase, cached until the next call) / setMoving / one search.  The
+ * reference rebuilds its lattice only when the fixed cloud changes (base_impl.cpp:109-134). */
+int pslam_projective_set_fixed(pslam_ctx* ctx, int n_fixed, const float* fixed_coords, int fixed_dim,
+                               const uint8_t* desc_fixed);
+int pslam_projective_set_moving(pslam_ctx* ctx, int n_moving, const float* moving_xyz,
+                                const uint8_t* desc_moving);
+int pslam_projective_match(pslam_ctx* ctx, int n_fixed, int n_moving, const float* local_map_in_sensor12,
+                           const pslam_projective_cfg* cfg, int capacity, int* fixed_idx,
+                           int* moving_idx, float* distance, int* n_projected);
+/* convenience: the three calls above in one */
+int pslam_match_projective(pslam_ctx* ctx, int n_fixed, const float* fixed_coords, int fixed_dim,
+                           const uint8_t* desc_fixed, int n_moving, const float* moving_xyz,
+                           const uint8_t* desc_moving, const float* local_map_in_sensor12,
+                           const pslam_projective_cfg* cfg, int capacity, int* fixed_idx,
+                           int* moving_idx, float* distance, int* n_projected);
+
+/* ---- stages 3+4: SE3 factor linearisation and H,b reduction ---------------------
+ * Replaces srrg2_solver FactorCorrespondenceDriven_::compute over
+ * SE3RectifiedStereoProjectiveErrorFactor / SE3ProjectiveDepthErrorFactor /
+ * SE3ProjectiveErrorFactor with RobustifierSaturated / Clamp, as wired by
+ * AlignerSliceProcessorProjective_::setupFactor
+ *   (.../registration/aligner_slice_processor_projective.cpp:27-112; factor use in
+ *    tests/test_aligners.cpp:586-638).  Arithmetic is fp64.
+ * kind: 0 stereo (fixed_dim 4), 1 depth (3), 2 mono (2).  robustifier: 0 none, 1 saturated, 2 clamp.
+ * info_diag: 3 doubles per FIXED point.  stats4 = {chi, inliers, outliers, suppressed}. */
+typedef struct {
+  int kind;
+  double K[9];
+  double image_cols, image_rows;
+  double baseline[3];
+  double mean_disparity; /* > 0 enables inverse-depth weighting */
+  int robustifier;
+  double chi_threshold;
+} pslam_linearize_cfg;
+
+int pslam_linearize_se3(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, const double* pose12,
+                        int n_moving, const double* moving_xyz, int n_fixed, const double* fixed_meas,
+                        int fixed_dim, int n_corr, const int* corr_fixed, const int* corr_moving,
+                        const double* info_diag, double* H36, double* b6, double* stats4);
+/* (H + damping I) dx = -b, pose <- pose * v2t(dx) on the device (one thread, fp64 Cholesky) */
+int pslam_gn_step(pslam_ctx* ctx, const double* H36, const double* b6, double damping, double* pose12,
+                  double* dx6);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSLAM_CUDA_H */

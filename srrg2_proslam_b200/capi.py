@@ -1,0 +1,317 @@
+"""ctypes binding of the C ABI (include/pslam_cuda.h) -- the Python harness used by tests/ and bench.py.
+
+This is plumbing, not the product: every compute call goes straight into libpslam_cuda.so (hand-written
+sm_100a kernels).  There is no fallback: if the library is missing or no CUDA device is usable the
+calls raise.
+"""
+import ctypes as C
+import pathlib
+
+import numpy as np
+
+PKG_DIR = pathlib.Path(__file__).resolve().parent
+LIB_PATH = PKG_DIR / "libpslam_cuda.so"
+
+PSLAM_OK, PSLAM_E_INVALID, PSLAM_E_CUDA, PSLAM_E_CAPACITY, PSLAM_E_NOT_SPD = 0, -1, -2, -3, -4
+
+
+class PslamError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"pslam error {code}: {msg}")
+        self.code = code
+
+
+class Limits(C.Structure):
+    _fields_ = [("max_images", C.c_int), ("max_rows", C.c_int), ("max_cols", C.c_int),
+                ("max_features", C.c_int), ("max_raw_per_bin", C.c_int), ("max_bins", C.c_int)]
+
+
+class ExtractCfg(C.Structure):
+    _fields_ = [("detector_threshold", C.c_float), ("enable_non_maximum_suppression", C.c_int),
+                ("target_number_of_keypoints", C.c_int), ("number_of_detectors_horizontal", C.c_int),
+                ("number_of_detectors_vertical", C.c_int)]
+
+
+class MatchCfg(C.Structure):
+    _fields_ = [("maximum_descriptor_distance", C.c_float),
+                ("maximum_distance_ratio_to_second_best", C.c_float),
+                ("maximum_disparity_pixels", C.c_int), ("epipolar_line_thickness_pixels", C.c_int)]
+
+
+class ProjectiveCfg(C.Structure):
+    _fields_ = [("K", C.c_float * 9), ("canvas_rows", C.c_int), ("canvas_cols", C.c_int),
+                ("range_min", C.c_float), ("range_max", C.c_float), ("shape", C.c_int),
+                ("search_radius_pixels", C.c_int), ("descriptor_distance", C.c_float),
+                ("maximum_distance_ratio_to_second_best", C.c_float)]
+
+
+class LinearizeCfg(C.Structure):
+    _fields_ = [("kind", C.c_int), ("K", C.c_double * 9), ("image_cols", C.c_double),
+                ("image_rows", C.c_double), ("baseline", C.c_double * 3), ("mean_disparity", C.c_double),
+                ("robustifier", C.c_int), ("chi_threshold", C.c_double)]
+
+
+class FrameCfg(C.Structure):
+    """pslam_frame_cfg: parameters of the batched projective + linearise stage"""
+    _fields_ = [("K", C.c_float * 9), ("baseline_x_pixels", C.c_float), ("range_min", C.c_float),
+                ("range_max", C.c_float), ("shape", C.c_int), ("search_radius_pixels", C.c_int),
+                ("descriptor_distance", C.c_float), ("maximum_distance_ratio_to_second_best", C.c_float),
+                ("info_diag", C.c_double * 3), ("robustifier", C.c_int), ("chi_threshold", C.c_double),
+                ("inverse_depth_weighting", C.c_int), ("minimum_disparity_pixels", C.c_float)]
+
+
+SHAPES = {"square": 0, "circle": 1, "rhombus": 2}
+FACTORS = {"stereo": 0, "depth": 1, "mono": 2}
+ROBUST = {"none": 0, "saturated": 1, "clamp": 2}
+
+_lib = None
+
+
+def lib():
+    """Load libpslam_cuda.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise RuntimeError(f"{LIB_PATH} is missing: build it with `make -C srrg2_proslam_b200/csrc` "
+                               "(or __graft_entry__.build()); there is no CPU fallback")
+        _lib = C.CDLL(str(LIB_PATH))
+        _lib.pslam_last_error.restype = C.c_char_p
+        _lib.pslam_version.restype = C.c_char_p
+        _lib.pslam_launch_count.restype = C.c_longlong
+        _lib.pslam_stream.restype = C.c_void_p
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def extract_cfg(threshold=10, nms=1, target=500, nh=3, nv=3):
+    return ExtractCfg(float(threshold), int(nms), int(target), int(nh), int(nv))
+
+
+def match_cfg(max_dist=50.0, ratio=0.9, max_disp=100, thickness=0):
+    return MatchCfg(float(max_dist), float(ratio), int(max_disp), int(thickness))
+
+
+class Context:
+    def __init__(self, device=0, max_images=2, max_rows=1024, max_cols=2048, max_features=4096,
+                 max_raw_per_bin=32768, max_bins=9):
+        self.limits = Limits(max_images, max_rows, max_cols, max_features, max_raw_per_bin, max_bins)
+        self._h = C.c_void_p()
+        rc = lib().pslam_create(int(device), C.byref(self.limits), C.byref(self._h))
+        if rc != 0:
+            msg = lib().pslam_last_error(self._h).decode() if self._h else "no usable CUDA device"
+            if self._h:
+                lib().pslam_destroy(self._h)
+                self._h = None
+            raise PslamError(rc, msg)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().pslam_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def _chk(self, rc):
+        if rc < 0:
+            raise PslamError(rc, lib().pslam_last_error(self._h).decode())
+        return rc
+
+    @property
+    def launches(self):
+        return lib().pslam_launch_count(self._h)
+
+    @property
+    def stream(self):
+        return lib().pslam_stream(self._h)
+
+    def synchronize(self):
+        self._chk(lib().pslam_synchronize(self._h))
+
+    # ---- stage 1 ------------------------------------------------------------------------------
+    def fast_detect(self, img, thr, nms=True, cap=200000):
+        img = np.ascontiguousarray(img, np.uint8)
+        xy = np.zeros((cap, 2), np.float32)
+        resp = np.zeros(cap, np.float32)
+        n = self._chk(lib().pslam_fast_detect(self._h, _p(img), img.shape[0], img.shape[1], img.shape[1],
+                                              int(thr), int(nms), cap, _p(xy), _p(resp)))
+        assert n <= cap
+        return xy[:n].copy(), resp[:n].copy()
+
+    def blur7(self, img):
+        img = np.ascontiguousarray(img, np.uint8)
+        out = np.zeros_like(img)
+        self._chk(lib().pslam_blur7(self._h, _p(img), img.shape[0], img.shape[1], img.shape[1], _p(out)))
+        return out
+
+    def extract_binned(self, img, cfg, mask=None):
+        img = np.ascontiguousarray(img, np.uint8)
+        cap = self.limits.max_features
+        xy = np.zeros((cap, 2), np.float32)
+        resp = np.zeros(cap, np.float32)
+        inten = np.zeros(cap, np.float32)
+        desc = np.zeros((cap, 32), np.uint8)
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        n = self._chk(lib().pslam_extract_binned(self._h, _p(img), img.shape[0], img.shape[1], img.shape[1],
+                                                 C.byref(cfg), _p(m), cap, _p(xy), _p(resp), _p(inten), _p(desc)))
+        return dict(xy=xy[:n].copy(), response=resp[:n].copy(), intensity=inten[:n].copy(), desc=desc[:n].copy())
+
+    def extract_binned_batch_dev(self, d_ptr, n_images, rows, cols, stride, image_pitch, cfg):
+        self._chk(lib().pslam_extract_binned_batch_dev(self._h, C.c_void_p(d_ptr), int(n_images), int(rows),
+                                                       int(cols), int(stride), C.c_longlong(image_pitch),
+                                                       C.byref(cfg)))
+
+    def feature_counts(self, n_images):
+        c = np.zeros(n_images, np.int32)
+        self._chk(lib().pslam_download_feature_counts(self._h, int(n_images), _p(c)))
+        return c
+
+    def download_features(self, slot):
+        cap = self.limits.max_features
+        xy = np.zeros((cap, 2), np.float32)
+        resp = np.zeros(cap, np.float32)
+        inten = np.zeros(cap, np.float32)
+        desc = np.zeros((cap, 32), np.uint8)
+        n = self._chk(lib().pslam_download_features(self._h, int(slot), cap, _p(xy), _p(resp), _p(inten), _p(desc)))
+        return dict(xy=xy[:n].copy(), response=resp[:n].copy(), intensity=inten[:n].copy(), desc=desc[:n].copy())
+
+    # ---- stage 2a -----------------------------------------------------------------------------
+    def match_epipolar(self, xy_f, desc_f, xy_m, desc_m, cfg):
+        xy_f = np.ascontiguousarray(xy_f, np.float32).reshape(-1, 2)
+        xy_m = np.ascontiguousarray(xy_m, np.float32).reshape(-1, 2)
+        desc_f = np.ascontiguousarray(desc_f, np.uint8).reshape(-1, 32)
+        desc_m = np.ascontiguousarray(desc_m, np.uint8).reshape(-1, 32)
+        cap = max(len(xy_f), 1)
+        fi, mi, d = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap, np.float32)
+        n = self._chk(lib().pslam_match_epipolar(self._h, len(xy_f), _p(xy_f), _p(desc_f), len(xy_m), _p(xy_m),
+                                                 _p(desc_m), C.byref(cfg), cap, _p(fi), _p(mi), _p(d)))
+        return fi[:n].copy(), mi[:n].copy(), d[:n].copy()
+
+    def stereo_adaptor(self, left, right, ecfg, mcfg):
+        left = np.ascontiguousarray(left, np.uint8)
+        right = np.ascontiguousarray(right, np.uint8)
+        cap = self.limits.max_features
+        uvuv = np.zeros((cap, 4), np.float32)
+        inten = np.zeros(cap, np.float32)
+        desc = np.zeros((cap, 32), np.uint8)
+        n = self._chk(lib().pslam_stereo_adaptor(self._h, _p(left), _p(right), left.shape[0], left.shape[1],
+                                                 left.shape[1], C.byref(ecfg), C.byref(mcfg), cap, _p(uvuv),
+                                                 _p(inten), _p(desc)))
+        return dict(uvuv=uvuv[:n].copy(), intensity=inten[:n].copy(), desc=desc[:n].copy())
+
+    def stereo_frontend_batch_dev(self, d_ptr, n_pairs, rows, cols, stride, image_pitch, ecfg, mcfg):
+        self._chk(lib().pslam_stereo_frontend_batch_dev(self._h, C.c_void_p(d_ptr), int(n_pairs), int(rows),
+                                                        int(cols), int(stride), C.c_longlong(image_pitch),
+                                                        C.byref(ecfg), C.byref(mcfg)))
+
+    def stereo_frontend_batch(self, h_images, n_pairs, rows, cols, stride, image_pitch, ecfg, mcfg):
+        """h_images: numpy array or raw host pointer (int)"""
+        ptr = C.c_void_p(h_images) if isinstance(h_images, int) else _p(h_images)
+        self._chk(lib().pslam_stereo_frontend_batch(self._h, ptr, int(n_pairs), int(rows), int(cols),
+                                                    int(stride), C.c_longlong(image_pitch), C.byref(ecfg),
+                                                    C.byref(mcfg)))
+
+    def stereo_counts(self, n_pairs):
+        c = np.zeros(n_pairs, np.int32)
+        self._chk(lib().pslam_download_stereo_counts(self._h, int(n_pairs), _p(c)))
+        return c
+
+    def download_stereo_points(self, pair):
+        cap = self.limits.max_features
+        uvuv = np.zeros((cap, 4), np.float32)
+        li, ri = np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+        d = np.zeros(cap, np.float32)
+        n = self._chk(lib().pslam_download_stereo_points(self._h, int(pair), cap, _p(uvuv), _p(li), _p(ri), _p(d)))
+        return dict(uvuv=uvuv[:n].copy(), left_idx=li[:n].copy(), right_idx=ri[:n].copy(), distance=d[:n].copy())
+
+    # ---- stage 2b -----------------------------------------------------------------------------
+    def bf_best2(self, desc_f, desc_m):
+        desc_f = np.ascontiguousarray(desc_f, np.uint8).reshape(-1, 32)
+        desc_m = np.ascontiguousarray(desc_m, np.uint8).reshape(-1, 32)
+        n = len(desc_f)
+        best, second, idx = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.int32)
+        self._chk(lib().pslam_bf_best2(self._h, n, _p(desc_f), len(desc_m), _p(desc_m), _p(best), _p(second), _p(idx)))
+        return best, second, idx
+
+    def bf_best2_dev(self, nq, d_q, nt, d_t, d_best, d_second, d_idx):
+        self._chk(lib().pslam_bf_best2_dev(self._h, int(nq), C.c_void_p(d_q), int(nt), C.c_void_p(d_t),
+                                           C.c_void_p(d_best), C.c_void_p(d_second), C.c_void_p(d_idx)))
+
+    def match_bruteforce(self, desc_f, desc_m, cfg):
+        desc_f = np.ascontiguousarray(desc_f, np.uint8).reshape(-1, 32)
+        desc_m = np.ascontiguousarray(desc_m, np.uint8).reshape(-1, 32)
+        cap = max(min(len(desc_f), len(desc_m)), 1)
+        fi, mi, d = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap, np.float32)
+        n = self._chk(lib().pslam_match_bruteforce(self._h, len(desc_f), _p(desc_f), len(desc_m), _p(desc_m),
+                                                   C.byref(cfg), cap, _p(fi), _p(mi), _p(d)))
+        return fi[:n].copy(), mi[:n].copy(), d[:n].copy()
+
+    # ---- stage 2c -----------------------------------------------------------------------------
+    def projective_set_fixed(self, coords, desc):
+        coords = np.ascontiguousarray(coords, np.float32)
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        self._n_fixed = len(coords)
+        self._chk(lib().pslam_projective_set_fixed(self._h, len(coords), _p(coords), coords.shape[1], _p(desc)))
+
+    def projective_set_moving(self, xyz, desc):
+        xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        self._n_moving = len(xyz)
+        self._chk(lib().pslam_projective_set_moving(self._h, len(xyz), _p(xyz), _p(desc)))
+
+    def projective_match(self, pose12, K, rows, cols, shape="circle", radius=10, descriptor_distance=50.0,
+                         ratio=0.9, range_min=0.1, range_max=1000.0):
+        cfg = ProjectiveCfg()
+        cfg.K[:] = [float(v) for v in np.asarray(K, np.float32).reshape(9)]
+        cfg.canvas_rows, cfg.canvas_cols = int(rows), int(cols)
+        cfg.range_min, cfg.range_max = float(range_min), float(range_max)
+        cfg.shape = SHAPES[shape]
+        cfg.search_radius_pixels = int(radius)
+        cfg.descriptor_distance = float(descriptor_distance)
+        cfg.maximum_distance_ratio_to_second_best = float(ratio)
+        pose12 = np.ascontiguousarray(pose12, np.float32).reshape(12)
+        cap = max(self._n_fixed, 1)
+        fi, mi, d = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap, np.float32)
+        nproj = C.c_int(0)
+        n = self._chk(lib().pslam_projective_match(self._h, self._n_fixed, self._n_moving, _p(pose12),
+                                                   C.byref(cfg), cap, _p(fi), _p(mi), _p(d), C.byref(nproj)))
+        return fi[:n].copy(), mi[:n].copy(), d[:n].copy(), nproj.value
+
+    # ---- stages 3 + 4 -------------------------------------------------------------------------
+    @staticmethod
+    def linearize_cfg(kind, K, cols, rows, baseline=(0, 0, 0), mean_disparity=0.0, robustifier="saturated",
+                      chi_threshold=25.0):
+        c = LinearizeCfg()
+        c.kind = FACTORS[kind]
+        c.K[:] = [float(v) for v in np.asarray(K, np.float64).reshape(9)]
+        c.image_cols, c.image_rows = float(cols), float(rows)
+        c.baseline[:] = [float(v) for v in baseline]
+        c.mean_disparity = float(mean_disparity)
+        c.robustifier = ROBUST[robustifier]
+        c.chi_threshold = float(chi_threshold)
+        return c
+
+    def linearize(self, cfg, pose12, moving_xyz, fixed_meas, corr_fixed, corr_moving, info_diag):
+        pose12 = np.ascontiguousarray(pose12, np.float64).reshape(12)
+        moving_xyz = np.ascontiguousarray(moving_xyz, np.float64).reshape(-1, 3)
+        fixed_meas = np.ascontiguousarray(fixed_meas, np.float64)
+        cf = np.ascontiguousarray(corr_fixed, np.int32)
+        cm = np.ascontiguousarray(corr_moving, np.int32)
+        info = np.ascontiguousarray(info_diag, np.float64).reshape(-1, 3)
+        assert len(info) == len(fixed_meas)
+        H, b, st = np.zeros(36, np.float64), np.zeros(6, np.float64), np.zeros(4, np.float64)
+        self._chk(lib().pslam_linearize_se3(self._h, C.byref(cfg), _p(pose12), len(moving_xyz), _p(moving_xyz),
+                                            len(fixed_meas), _p(fixed_meas), fixed_meas.shape[1], len(cf),
+                                            _p(cf), _p(cm), _p(info), _p(H), _p(b), _p(st)))
+        return H.reshape(6, 6), b, dict(chi=st[0], inliers=int(st[1]), outliers=int(st[2]), suppressed=int(st[3]))
+
+    def gn_step(self, H, b, damping, pose12):
+        H = np.ascontiguousarray(H, np.float64).reshape(36)
+        b = np.ascontiguousarray(b, np.float64).reshape(6)
+        pose = np.ascontiguousarray(pose12, np.float64).reshape(12).copy()
+        dx = np.zeros(6, np.float64)
+        self._chk(lib().pslam_gn_step(self._h, _p(H), _p(b), C.c_double(damping), _p(pose), _p(dx)))
+        return pose, dx

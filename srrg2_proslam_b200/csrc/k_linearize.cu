@@ -1,0 +1,330 @@
+// k_linearize.cu -- stages 3+4 (sm_100a): SE3 projective factor error + Jacobian per
+// correspondence and the fp64 reduction of the 6x6 H / 6x1 b normal equations.
+//
+// Replaces srrg2_solver's FactorCorrespondenceDriven_::compute over
+// SE3RectifiedStereoProjectiveErrorFactor / SE3ProjectiveDepthErrorFactor / SE3ProjectiveErrorFactor
+// with RobustifierSaturated / RobustifierClamp (external code; wiring at
+// .../registration/aligner_slice_processor_projective.cpp:27-112, use at tests/test_aligners.cpp:586-638,
+// in-tree analogue of the accumulate loop: .../mapping/landmarks/landmark_estimator_pose_based_smoother_impl.cpp:48-106).
+// The arithmetic (operation order included) is that of oracle/pslam_oracle_solver.hpp.
+//
+// One thread per correspondence (grid-stride), 21 + 6 + 1 fp64 partial sums and 3 counters per
+// thread, warp-shuffle tree, one partial row per CTA, a last single-CTA pass adds the rows in
+// index order (deterministic -- no fp64 atomics).
+#include "pslam_internal.cuh"
+#include "pslam_kernels.cuh"
+
+namespace {
+
+constexpr int LZ_THREADS = 256;
+constexpr int LZ_NACC = 32;  // 21 H (upper) + 6 b + chi + inliers + outliers + suppressed + pad
+
+struct LinParams {
+  int kind, robustifier;
+  double K[9];
+  double cols, rows;
+  double baseline[3];
+  double mean_disparity, chi_threshold;
+  double R[9], t[3];
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ bool error_and_jacobian(const LinParams& c, const double* pm,
+                                                   const double* z, double* e, double* J) {
+  const double* R = c.R;
+  double pc[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    pc[i] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(R[3 * i], pm[0]), __dmul_rn(R[3 * i + 1], pm[1])),
+                                __dmul_rn(R[3 * i + 2], pm[2])), c.t[i]);
+  if (pc[2] <= 0) return false;
+  const double* K = c.K;
+  const double hx = __dadd_rn(__dadd_rn(__dmul_rn(K[0], pc[0]), __dmul_rn(K[1], pc[1])), __dmul_rn(K[2], pc[2]));
+  const double hy = __dadd_rn(__dadd_rn(__dmul_rn(K[3], pc[0]), __dmul_rn(K[4], pc[1])), __dmul_rn(K[5], pc[2]));
+  const double hz = __dadd_rn(__dadd_rn(__dmul_rn(K[6], pc[0]), __dmul_rn(K[7], pc[1])), __dmul_rn(K[8], pc[2]));
+  const double iz = __ddiv_rn(1.0, hz);
+  const double u = __dmul_rn(hx, iz), v = __dmul_rn(hy, iz);
+  if (u < 0 || u > c.cols || v < 0 || v > c.rows) return false;
+  double Jx[18];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    Jx[6 * i + 0] = R[3 * i + 0];
+    Jx[6 * i + 1] = R[3 * i + 1];
+    Jx[6 * i + 2] = R[3 * i + 2];
+    Jx[6 * i + 3] = __dmul_rn(-2.0, __dsub_rn(__dmul_rn(R[3 * i + 1], pm[2]), __dmul_rn(R[3 * i + 2], pm[1])));
+    Jx[6 * i + 4] = __dmul_rn(-2.0, __dadd_rn(__dmul_rn(-R[3 * i + 0], pm[2]), __dmul_rn(R[3 * i + 2], pm[0])));
+    Jx[6 * i + 5] = __dmul_rn(-2.0, __dsub_rn(__dmul_rn(R[3 * i + 0], pm[1]), __dmul_rn(R[3 * i + 1], pm[0])));
+  }
+  double KJ[18];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 6; ++j)
+      KJ[6 * i + j] = __dadd_rn(__dadd_rn(__dmul_rn(K[3 * i], Jx[j]), __dmul_rn(K[3 * i + 1], Jx[6 + j])),
+                                __dmul_rn(K[3 * i + 2], Jx[12 + j]));
+  const double iz2 = __dmul_rn(iz, iz);
+  const double hx_iz2 = __dmul_rn(hx, iz2), hy_iz2 = __dmul_rn(hy, iz2);
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    J[j] = __dsub_rn(__dmul_rn(KJ[j], iz), __dmul_rn(hx_iz2, KJ[12 + j]));
+    J[6 + j] = __dsub_rn(__dmul_rn(KJ[6 + j], iz), __dmul_rn(hy_iz2, KJ[12 + j]));
+  }
+  e[0] = __dsub_rn(u, z[0]);
+  e[1] = __dsub_rn(v, z[1]);
+  if (c.kind == 0) {
+    const double hxr = __dadd_rn(hx, c.baseline[0]);
+    e[2] = __dsub_rn(__dmul_rn(hxr, iz), z[2]);
+    const double hxr_iz2 = __dmul_rn(hxr, iz2);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) J[12 + j] = __dsub_rn(__dmul_rn(KJ[j], iz), __dmul_rn(hxr_iz2, KJ[12 + j]));
+    if (c.mean_disparity > 0) {
+      double w = __dadd_rn(0.01, __ddiv_rn(__dsub_rn(z[0], z[2]), c.mean_disparity));
+      if (w > 1) w = 1;
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) J[6 * i + j] = __dmul_rn(J[6 * i + j], w);
+    }
+  } else if (c.kind == 1) {
+    e[2] = __dsub_rn(pc[2], z[2]);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) J[12 + j] = Jx[12 + j];
+  } else {
+    e[2] = 0;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) J[12 + j] = 0;
+  }
+  return true;
+}
+
+__global__ void __launch_bounds__(LZ_THREADS)
+linearize_kernel(LinParams c, const double* __restrict__ moving_xyz,
+                 const double* __restrict__ fixed_meas, int fixed_dim, int n_corr,
+                 const int* __restrict__ corr_fixed, const int* __restrict__ corr_moving,
+                 const double* __restrict__ info_diag, double* __restrict__ partials) {
+  __shared__ double s_part[LZ_THREADS / 32][LZ_NACC];
+  double acc[LZ_NACC];
+#pragma unroll
+  for (int i = 0; i < LZ_NACC; ++i) acc[i] = 0;
+  const int edim = (c.kind == 2) ? 2 : 3;
+  for (int k = blockIdx.x * LZ_THREADS + threadIdx.x; k < n_corr; k += gridDim.x * LZ_THREADS) {
+    const int fi = corr_fixed[k], mi = corr_moving[k];
+    double pm[3] = {moving_xyz[3 * (size_t) mi], moving_xyz[3 * (size_t) mi + 1], moving_xyz[3 * (size_t) mi + 2]};
+    double z[3] = {0, 0, 0};
+    for (int i = 0; i < 3 && i < fixed_dim; ++i) z[i] = fixed_meas[(size_t) fixed_dim * fi + i];
+    double e[3], J[18];
+    if (!error_and_jacobian(c, pm, z, e, J)) {
+      acc[30] += 1;
+      continue;
+    }
+    const double om[3] = {info_diag[3 * (size_t) fi], info_diag[3 * (size_t) fi + 1], info_diag[3 * (size_t) fi + 2]};
+    double chi = 0;
+    for (int i = 0; i < edim; ++i) chi = __dadd_rn(chi, __dmul_rn(__dmul_rn(e[i], om[i]), e[i]));
+    double scale = 1;
+    if (c.robustifier != 0 && chi > c.chi_threshold) {
+      acc[29] += 1;
+      scale = (c.robustifier == 1) ? __ddiv_rn(c.chi_threshold, chi) : 0.0;
+    } else {
+      acc[28] += 1;
+    }
+    acc[27] += __dmul_rn(chi, scale);
+    for (int i = 0; i < edim; ++i) {
+      const double w = __dmul_rn(om[i], scale);
+      int h = 0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+        const double Jw = __dmul_rn(J[6 * i + a], w);
+        acc[21 + a] += __dmul_rn(Jw, e[i]);
+#pragma unroll
+        for (int b = a; b < 6; ++b) acc[h++] += __dmul_rn(Jw, J[6 * i + b]);
+      }
+    }
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < LZ_NACC - 1; ++i) {
+    const double s = warp_sum(acc[i]);
+    if (lane == 0) s_part[wid][i] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < LZ_NACC - 1) {
+    double s = 0;
+    for (int w = 0; w < LZ_THREADS / 32; ++w) s += s_part[w][threadIdx.x];
+    partials[(size_t) blockIdx.x * LZ_NACC + threadIdx.x] = s;
+  }
+}
+
+// out[0..35] H (full symmetric), [36..41] b, [42] chi, [43] inliers, [44] outliers, [45] suppressed
+__global__ void linearize_finish_kernel(const double* __restrict__ partials, int n_blocks,
+                                        double* __restrict__ out) {
+  __shared__ double s[LZ_NACC];
+  const int i = threadIdx.x;
+  if (i < LZ_NACC - 1) {
+    double v = 0;
+    for (int b = 0; b < n_blocks; ++b) v += partials[(size_t) b * LZ_NACC + i];
+    s[i] = v;
+  }
+  __syncthreads();
+  if (i == 0) {
+    int h = 0;
+    for (int a = 0; a < 6; ++a)
+      for (int b = a; b < 6; ++b) {
+        out[6 * a + b] = s[h];
+        out[6 * b + a] = s[h];
+        ++h;
+      }
+    for (int a = 0; a < 6; ++a) out[36 + a] = s[21 + a];
+    out[42] = s[27];
+    out[43] = s[28];
+    out[44] = s[29];
+    out[45] = s[30];
+  }
+}
+
+// (H + damping I) dx = -b by Cholesky; pose <- pose * v2t(dx)   (IterationAlgorithmGN, one 6x6 block)
+// io: [0..35] H, [36..41] b, [42] damping, [43..54] pose12 in/out, [55..60] dx out, [61] status
+__global__ void gn_step_kernel(double* __restrict__ io) {
+  if (threadIdx.x != 0) return;
+  double A[36], L[36];
+  for (int i = 0; i < 36; ++i) {
+    A[i] = io[i];
+    L[i] = 0;
+  }
+  for (int i = 0; i < 6; ++i) A[7 * i] += io[42];
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j <= i; ++j) {
+      double s = A[6 * i + j];
+      for (int k = 0; k < j; ++k) s = __dsub_rn(s, __dmul_rn(L[6 * i + k], L[6 * j + k]));
+      if (i == j) {
+        if (!(s > 0)) {
+          io[61] = -1;
+          return;
+        }
+        L[6 * i + i] = sqrt(s);
+      } else {
+        L[6 * i + j] = __ddiv_rn(s, L[6 * j + j]);
+      }
+    }
+  double y[6], dx[6];
+  for (int i = 0; i < 6; ++i) {
+    double s = -io[36 + i];
+    for (int k = 0; k < i; ++k) s = __dsub_rn(s, __dmul_rn(L[6 * i + k], y[k]));
+    y[i] = __ddiv_rn(s, L[6 * i + i]);
+  }
+  for (int i = 5; i >= 0; --i) {
+    double s = y[i];
+    for (int k = i + 1; k < 6; ++k) s = __dsub_rn(s, __dmul_rn(L[6 * k + i], dx[k]));
+    dx[i] = __ddiv_rn(s, L[6 * i + i]);
+  }
+  // v2t(dx)
+  double x = dx[3], yq = dx[4], z = dx[5];
+  const double n2 = __dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(yq, yq)), __dmul_rn(z, z));
+  double w;
+  if (n2 < 1.0) {
+    w = sqrt(__dsub_rn(1.0, n2));
+  } else {
+    const double n = sqrt(n2);
+    x = __ddiv_rn(x, n);
+    yq = __ddiv_rn(yq, n);
+    z = __ddiv_rn(z, n);
+    w = 0;
+  }
+  double D[9];
+  D[0] = __dsub_rn(1.0, __dmul_rn(2.0, __dadd_rn(__dmul_rn(yq, yq), __dmul_rn(z, z))));
+  D[1] = __dmul_rn(2.0, __dsub_rn(__dmul_rn(x, yq), __dmul_rn(z, w)));
+  D[2] = __dmul_rn(2.0, __dadd_rn(__dmul_rn(x, z), __dmul_rn(yq, w)));
+  D[3] = __dmul_rn(2.0, __dadd_rn(__dmul_rn(x, yq), __dmul_rn(z, w)));
+  D[4] = __dsub_rn(1.0, __dmul_rn(2.0, __dadd_rn(__dmul_rn(x, x), __dmul_rn(z, z))));
+  D[5] = __dmul_rn(2.0, __dsub_rn(__dmul_rn(yq, z), __dmul_rn(x, w)));
+  D[6] = __dmul_rn(2.0, __dsub_rn(__dmul_rn(x, z), __dmul_rn(yq, w)));
+  D[7] = __dmul_rn(2.0, __dadd_rn(__dmul_rn(yq, z), __dmul_rn(x, w)));
+  D[8] = __dsub_rn(1.0, __dmul_rn(2.0, __dadd_rn(__dmul_rn(x, x), __dmul_rn(yq, yq))));
+  double R[9], t[3];
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) R[3 * i + j] = io[43 + 4 * i + j];
+    t[i] = io[43 + 4 * i + 3];
+  }
+  double Rn[9], tn[3];
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j)
+      Rn[3 * i + j] = __dadd_rn(__dadd_rn(__dmul_rn(R[3 * i], D[j]), __dmul_rn(R[3 * i + 1], D[3 + j])),
+                                __dmul_rn(R[3 * i + 2], D[6 + j]));
+    tn[i] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(R[3 * i], dx[0]), __dmul_rn(R[3 * i + 1], dx[1])),
+                                __dmul_rn(R[3 * i + 2], dx[2])), t[i]);
+  }
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) io[43 + 4 * i + j] = Rn[3 * i + j];
+    io[43 + 4 * i + 3] = tn[i];
+  }
+  for (int i = 0; i < 6; ++i) io[55 + i] = dx[i];
+  io[61] = 0;
+}
+
+}  // namespace
+
+int pslam_k_linearize(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, const double* pose12,
+                      int n_moving, const double* d_moving_xyz, int n_fixed,
+                      const double* d_fixed_meas, int fixed_dim, int n_corr, const int* d_corr_fixed,
+                      const int* d_corr_moving, const double* d_info_diag, double* h_H36,
+                      double* h_b6, double* h_stats4) {
+  (void) n_moving;
+  (void) n_fixed;
+  LinParams c;
+  c.kind = cfg->kind;
+  c.robustifier = cfg->robustifier;
+  for (int i = 0; i < 9; ++i) c.K[i] = cfg->K[i];
+  c.cols = cfg->image_cols;
+  c.rows = cfg->image_rows;
+  for (int i = 0; i < 3; ++i) c.baseline[i] = cfg->baseline[i];
+  c.mean_disparity = cfg->mean_disparity;
+  c.chi_threshold = cfg->chi_threshold;
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) c.R[3 * i + j] = pose12[4 * i + j];
+    c.t[i] = pose12[4 * i + 3];
+  }
+  int blocks = (n_corr + LZ_THREADS - 1) / LZ_THREADS;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 592) blocks = 592;  // 4 CTAs per SM on 148 SMs
+  // the tail of the scratch buffer holds the partial rows and the result
+  const size_t need = sizeof(double) * ((size_t) blocks * LZ_NACC + 64);
+  if (need > ctx->scratch_bytes) return pslam_set_error(ctx, PSLAM_E_CAPACITY, "linearize: scratch too small", cudaSuccess);
+  double* partials = reinterpret_cast<double*>(ctx->d_scratch + ctx->scratch_bytes - need);
+  double* out = partials + (size_t) blocks * LZ_NACC;
+  linearize_kernel<<<blocks, LZ_THREADS, 0, ctx->stream>>>(c, d_moving_xyz, d_fixed_meas, fixed_dim,
+                                                           n_corr, d_corr_fixed, d_corr_moving,
+                                                           d_info_diag, partials);
+  PSLAM_LAUNCH_CHECK(ctx, "linearize_kernel");
+  linearize_finish_kernel<<<1, 32, 0, ctx->stream>>>(partials, blocks, out);
+  PSLAM_LAUNCH_CHECK(ctx, "linearize_finish_kernel");
+  double* h = reinterpret_cast<double*>(ctx->h_pinned);
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(h, out, sizeof(double) * 46, cudaMemcpyDeviceToHost, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  memcpy(h_H36, h, sizeof(double) * 36);
+  memcpy(h_b6, h + 36, sizeof(double) * 6);
+  memcpy(h_stats4, h + 42, sizeof(double) * 4);
+  return PSLAM_OK;
+}
+
+int pslam_k_gn_step(pslam_ctx* ctx, const double* H36, const double* b6, double damping,
+                    double* pose12, double* dx6) {
+  double* h = reinterpret_cast<double*>(ctx->h_pinned);
+  memcpy(h, H36, sizeof(double) * 36);
+  memcpy(h + 36, b6, sizeof(double) * 6);
+  h[42] = damping;
+  memcpy(h + 43, pose12, sizeof(double) * 12);
+  double* d = reinterpret_cast<double*>(ctx->d_scratch + ctx->scratch_bytes - 64 * sizeof(double));
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d, h, sizeof(double) * 62, cudaMemcpyHostToDevice, ctx->stream));
+  gn_step_kernel<<<1, 32, 0, ctx->stream>>>(d);
+  PSLAM_LAUNCH_CHECK(ctx, "gn_step_kernel");
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(h, d, sizeof(double) * 62, cudaMemcpyDeviceToHost, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (h[61] != 0) return pslam_set_error(ctx, PSLAM_E_NOT_SPD, "gn_step: H + damping*I is not positive definite", cudaSuccess);
+  memcpy(pose12, h + 43, sizeof(double) * 12);
+  if (dx6) memcpy(dx6, h + 55, sizeof(double) * 6);
+  return PSLAM_OK;
+}

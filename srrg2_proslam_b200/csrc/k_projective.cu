@@ -1,0 +1,373 @@
+// k_projective.cu -- stage 2c (sm_100a): projective landmark-to-keypoint window matching.
+//
+// Replaces, for CorrespondenceFinderProjective{Square,Circle,Rhombus}:
+//   _initializeDatabase      .../correspondence_finders/correspondence_finder_projective_square_impl.cpp:7-31
+//   projector->compute       srrg2_core PointProjectorPinhole_ (call site ..._projective_base_impl.cpp:165-166)
+//   _findNearestNeighbors    ..._square_impl.cpp:33-118, ..._circle_impl.cpp:7-94, ..._rhombus_impl.cpp:7-93
+//   _filterCorrespondences   ..._projective_base_impl.cpp:39-102
+//
+// The lattice is sorted by row ONLY with an unstable std::sort in the reference; the scan order
+// inside equal rows breaks Hamming ties, so one lane replays libstdc++'s introsort once per fixed
+// cloud (cached until the next set_fixed, like the reference's _initializeDatabase).  The window
+// search runs one warp per projected point: lanes stride over the row band, each keeps its two
+// lexicographically smallest (distance, lattice position) keys, a shuffle tree merges them --
+// which equals the reference's sequential best / second-best update with "first wins" ties.
+#include <float.h>
+
+#include <unordered_map>
+#include <vector>
+
+#include "libstdcxx_sort.h"
+#include "pslam_internal.cuh"
+#include "pslam_kernels.cuh"
+
+namespace {
+
+struct RowLess {  // [](a, b) { return a.row < b.row; }   (square_impl.cpp:27-29)
+  __device__ __forceinline__ bool operator()(const unsigned long long& a,
+                                             const unsigned long long& b) const {
+    return (int) (a >> 32) < (int) (b >> 32);
+  }
+};
+
+// lattice element = (row << 32) | (col << 16) | index   (Element{int16 row, col, index}, square.h:37-47)
+__global__ void __launch_bounds__(32)
+lattice_build_kernel(const float* __restrict__ coords, int dim, int n,
+                     unsigned long long* __restrict__ lattice, int smem_cap) {
+  extern __shared__ __align__(16) unsigned long long s_l[];
+  const int lane = threadIdx.x;
+  unsigned long long* a = (n <= smem_cap) ? s_l : lattice;
+  for (int i = lane; i < n; i += 32) {
+    const short row = (short) coords[(size_t) dim * i + 1];  // int16(coordinates(1))
+    const short col = (short) coords[(size_t) dim * i + 0];
+    a[i] = ((unsigned long long) (unsigned) (int) row << 32) |
+           ((unsigned long long) (unsigned short) col << 16) | (unsigned long long) (unsigned short) i;
+  }
+  __syncwarp();
+  if (lane == 0) pslam_sort::std_sort(a, n, RowLess());
+  __syncwarp();
+  if (a != lattice)
+    for (int i = lane; i < n; i += 32) lattice[i] = a[i];
+}
+
+__device__ __forceinline__ void top2_insert(unsigned& k1, unsigned& k2, unsigned k) {
+  if (k < k1) {
+    k2 = k1;
+    k1 = k;
+  } else if (k < k2) {
+    k2 = k;
+  }
+}
+
+struct ProjParams {
+  float R[9], t[3], K[9];
+  float canvas_cols, canvas_rows, range_min, range_max;
+  int shape, radius;
+};
+
+// cand[4*m + {0,1,2,3}] = {fixed_best, dist_best, fixed_second, dist_second}, -1 where absent.
+// One warp per moving point.
+constexpr int PJ_WARPS = 8;
+__global__ void __launch_bounds__(PJ_WARPS * 32)
+projective_search_kernel(ProjParams pp, const float* __restrict__ moving_xyz, int n_moving,
+                         const uint32_t* __restrict__ desc_moving,
+                         const unsigned long long* __restrict__ lattice, int n_fixed,
+                         const uint32_t* __restrict__ desc_fixed, int* __restrict__ cand,
+                         int* __restrict__ n_projected) {
+  extern __shared__ int s_width[];  // circle: width per |height| (0..radius)
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (pp.shape == 1) {
+    const int r2 = pp.radius * pp.radius;
+    for (int h = threadIdx.x; h <= pp.radius; h += PJ_WARPS * 32)
+      s_width[h] = (int) sqrt((double) (r2 - h * h)) + 1;  // circle_impl.cpp:51-54
+    __syncthreads();
+  }
+  const int m = blockIdx.x * PJ_WARPS + wid;
+  if (m >= n_moving) return;
+  // ---- pinhole projection, fp32, operation order of oracle/pslam_oracle_solver.hpp::project_point
+  const float px = moving_xyz[3 * m], py = moving_xyz[3 * m + 1], pz = moving_xyz[3 * m + 2];
+  float c[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    c[i] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(pp.R[3 * i], px), __fmul_rn(pp.R[3 * i + 1], py)),
+                               __fmul_rn(pp.R[3 * i + 2], pz)), pp.t[i]);
+  bool valid = !(c[2] < pp.range_min || c[2] > pp.range_max);
+  float u = 0, v = 0;
+  if (valid) {
+    const float hx = __fadd_rn(__fadd_rn(__fmul_rn(pp.K[0], c[0]), __fmul_rn(pp.K[1], c[1])), __fmul_rn(pp.K[2], c[2]));
+    const float hy = __fadd_rn(__fadd_rn(__fmul_rn(pp.K[3], c[0]), __fmul_rn(pp.K[4], c[1])), __fmul_rn(pp.K[5], c[2]));
+    const float hz = __fadd_rn(__fadd_rn(__fmul_rn(pp.K[6], c[0]), __fmul_rn(pp.K[7], c[1])), __fmul_rn(pp.K[8], c[2]));
+    u = __fdiv_rn(hx, hz);
+    v = __fdiv_rn(hy, hz);
+    valid = !(u < 0.0f || u > pp.canvas_cols || v < 0.0f || v > pp.canvas_rows);
+  }
+  int* out = cand + 4 * (size_t) m;
+  if (!valid) {
+    if (lane == 0) {
+      out[0] = -2;  // not projected
+      out[1] = 0;
+      out[2] = -1;
+      out[3] = 0;
+    }
+    return;
+  }
+  if (lane == 0) atomicAdd(n_projected, 1);
+  const int row = (short) roundf(v), col = (short) roundf(u);  // std::round -> int16
+  const int r = pp.radius;
+  const int row_min = (short) (row - r), row_max = (short) (row + r + 1);
+  const int col_min = (short) (col - r - 1), col_max = (short) (col + r + 1);
+  // first lattice position with row >= row_min
+  int lo = 0, hi = n_fixed;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if ((int) (lattice[mid] >> 32) < row_min) lo = mid + 1; else hi = mid;
+  }
+  const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(desc_moving) + 2 * (size_t) m);
+  const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(desc_moving) + 2 * (size_t) m + 1);
+  unsigned k1 = 0xffffffffu, k2 = 0xffffffffu;  // (dist << 16) | lattice position
+  for (int base = lo; base < n_fixed; base += 32) {
+    const int pos = base + lane;
+    bool more = false;
+    if (pos < n_fixed) {
+      const unsigned long long e = lattice[pos];
+      const int erow = (int) (e >> 32), ecol = (int) (short) ((e >> 16) & 0xffffu);
+      if (erow < row_max) {
+        more = true;
+        bool in_window;
+        if (pp.shape == 0) {
+          in_window = ecol > col_min && ecol < col_max;
+        } else if (pp.shape == 1) {
+          const int height = erow - row;
+          const int width = s_width[height < 0 ? -height : height];
+          in_window = ecol > col - width && ecol < col + width;
+        } else {
+          int width = (short) (erow - row_min + 1);
+          if (width > (short) r) width = (short) (row_max - erow);
+          in_window = ecol > col - width && ecol < col + width;
+        }
+        if (in_window) {
+          const int fi = (int) (e & 0xffffu);
+          const uint4 f0 = __ldg(reinterpret_cast<const uint4*>(desc_fixed) + 2 * (size_t) fi);
+          const uint4 f1 = __ldg(reinterpret_cast<const uint4*>(desc_fixed) + 2 * (size_t) fi + 1);
+          const unsigned d = (unsigned) hamming256(q0, q1, f0, f1);
+          top2_insert(k1, k2, (d << 16) | (unsigned) pos);
+        }
+      }
+    }
+    if (!__any_sync(0xffffffffu, more)) break;
+  }
+  // merge the lanes' sorted pairs
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned a1 = __shfl_xor_sync(0xffffffffu, k1, o);
+    const unsigned a2 = __shfl_xor_sync(0xffffffffu, k2, o);
+    top2_insert(k1, k2, a1);
+    top2_insert(k1, k2, a2);
+  }
+  if (lane == 0) {
+    out[0] = (k1 != 0xffffffffu) ? (int) (lattice[k1 & 0xffffu] & 0xffffu) : -1;
+    out[1] = (int) (k1 >> 16);
+    out[2] = (k2 != 0xffffffffu) ? (int) (lattice[k2 & 0xffffu] & 0xffffu) : -1;
+    out[3] = (int) (k2 >> 16);
+  }
+}
+
+// per fixed: lowest and second lowest response over its candidates in insertion order
+// (order key = 2 * moving_idx + {0 best, 1 second}); key = (dist << 32) | order
+__global__ void filter_min1_kernel(const int* __restrict__ cand, int n_moving,
+                                   unsigned long long* __restrict__ key1) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * n_moving) return;
+  const int m = i >> 1, s = i & 1;
+  const int f = cand[4 * m + 2 * s];
+  if (f < 0) return;
+  const unsigned long long k = ((unsigned long long) (unsigned) cand[4 * m + 2 * s + 1] << 32) | (unsigned) i;
+  atomicMin(key1 + f, k);
+}
+__global__ void filter_min2_kernel(const int* __restrict__ cand, int n_moving,
+                                   const unsigned long long* __restrict__ key1,
+                                   unsigned long long* __restrict__ key2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * n_moving) return;
+  const int m = i >> 1, s = i & 1;
+  const int f = cand[4 * m + 2 * s];
+  if (f < 0) return;
+  const unsigned long long k = ((unsigned long long) (unsigned) cand[4 * m + 2 * s + 1] << 32) | (unsigned) i;
+  if (k != key1[f]) atomicMin(key2 + f, k);
+}
+// accepted[f] = moving index (>= 0) and dist, or -1
+__global__ void filter_accept_kernel(int n_fixed, const unsigned long long* __restrict__ key1,
+                                     const unsigned long long* __restrict__ key2, float max_dist,
+                                     float max_ratio, int* __restrict__ acc_moving,
+                                     float* __restrict__ acc_dist) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n_fixed) return;
+  const unsigned long long a = key1[f], b = key2[f];
+  int res = -1;
+  float dist = 0;
+  if (a != ~0ULL) {
+    const float lowest = (float) (unsigned) (a >> 32);
+    const float second = (b != ~0ULL) ? (float) (unsigned) (b >> 32) : FLT_MAX;
+    if (lowest < max_dist && __fdiv_rn(lowest, second) < max_ratio) {  // base_impl.cpp:67-69
+      const unsigned order = (unsigned) (a & 0xffffffffu);
+      // bijectivity (:82-99): the moving point's own best candidate is its first entry
+      if ((order & 1u) == 0) {
+        res = (int) (order >> 1);
+        dist = lowest;
+      }
+    }
+  }
+  acc_moving[f] = res;
+  acc_dist[f] = dist;
+}
+
+}  // namespace
+
+static inline size_t al256(size_t x) { return (x + 255) & ~(size_t) 255; }
+
+// Scratch layout of the projective matcher (persistent between set_fixed / set_moving / match):
+//   [fixed coords f32 n*dim][fixed desc][lattice u64][moving xyz][moving desc][cand][key1][key2][acc]
+struct ProjState {
+  int n_fixed, fixed_dim, n_moving;
+  float* d_fixed;
+  uint32_t* d_desc_fixed;
+  unsigned long long* d_lattice;
+  float* d_moving;
+  uint32_t* d_desc_moving;
+  int* d_cand;
+  unsigned long long *d_key1, *d_key2;
+  int* d_acc_m;
+  float* d_acc_d;
+  int* d_nproj;
+};
+
+static int proj_layout(pslam_ctx* ctx, ProjState& st, int n_fixed, int dim, int n_moving) {
+  uint8_t* p = ctx->d_scratch;
+  const int M = PSLAM_MAX_FEATURES_HARD * 2;  // generous fixed-size regions so that set_* calls are independent
+  if (n_fixed > M || n_moving > 65536)
+    return pslam_set_error(ctx, PSLAM_E_CAPACITY, "projective: too many points", cudaSuccess);
+  st.d_fixed = (float*) p; p += al256(sizeof(float) * 4 * (size_t) M);
+  st.d_desc_fixed = (uint32_t*) p; p += al256(32 * (size_t) M);
+  st.d_lattice = (unsigned long long*) p; p += al256(8 * (size_t) M);
+  st.d_key1 = (unsigned long long*) p; p += al256(8 * (size_t) M);
+  st.d_key2 = (unsigned long long*) p; p += al256(8 * (size_t) M);
+  st.d_acc_m = (int*) p; p += al256(4 * (size_t) M);
+  st.d_acc_d = (float*) p; p += al256(4 * (size_t) M);
+  st.d_nproj = (int*) p; p += 256;
+  st.d_moving = (float*) p; p += al256(sizeof(float) * 3 * (size_t) 65536);
+  st.d_desc_moving = (uint32_t*) p; p += al256(32 * (size_t) 65536);
+  st.d_cand = (int*) p; p += al256(16 * (size_t) 65536);
+  if ((size_t) (p - ctx->d_scratch) > ctx->scratch_bytes)
+    return pslam_set_error(ctx, PSLAM_E_CAPACITY, "projective: scratch too small", cudaSuccess);
+  st.n_fixed = n_fixed;
+  st.fixed_dim = dim;
+  st.n_moving = n_moving;
+  return PSLAM_OK;
+}
+
+int pslam_k_projective_set_fixed(pslam_ctx* ctx, int n_fixed, const float* h_coords, int dim,
+                                 const uint8_t* h_desc) {
+  ProjState st;
+  int rc = proj_layout(ctx, st, n_fixed, dim, 0);
+  if (rc) return rc;
+  if (n_fixed == 0) return PSLAM_OK;
+  if (n_fixed >= 32767)
+    return pslam_set_error(ctx, PSLAM_E_INVALID, "projective: int16 lattice needs < 32767 fixed points", cudaSuccess);
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(st.d_fixed, h_coords, sizeof(float) * dim * (size_t) n_fixed, cudaMemcpyHostToDevice, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(st.d_desc_fixed, h_desc, 32 * (size_t) n_fixed, cudaMemcpyHostToDevice, ctx->stream));
+  const int smem_cap = 16384;
+  const size_t smem = 8 * (size_t) (n_fixed < smem_cap ? n_fixed : smem_cap);
+  if (smem > 48 * 1024)
+    PSLAM_CUDA_TRY(ctx, cudaFuncSetAttribute(lattice_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  lattice_build_kernel<<<1, 32, smem, ctx->stream>>>(st.d_fixed, dim, n_fixed, st.d_lattice, smem_cap);
+  PSLAM_LAUNCH_CHECK(ctx, "lattice_build_kernel");
+  return PSLAM_OK;
+}
+
+int pslam_k_projective_set_moving(pslam_ctx* ctx, int n_moving, const float* h_xyz, const uint8_t* h_desc) {
+  ProjState st;
+  int rc = proj_layout(ctx, st, 0, 2, n_moving);
+  if (rc) return rc;
+  if (n_moving == 0) return PSLAM_OK;
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(st.d_moving, h_xyz, sizeof(float) * 3 * (size_t) n_moving, cudaMemcpyHostToDevice, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(st.d_desc_moving, h_desc, 32 * (size_t) n_moving, cudaMemcpyHostToDevice, ctx->stream));
+  return PSLAM_OK;
+}
+
+int pslam_k_projective_match(pslam_ctx* ctx, int n_fixed, int n_moving, const float* pose12,
+                             const pslam_projective_cfg* cfg, int capacity, int* h_fixed, int* h_moving,
+                             float* h_dist, int* n_projected) {
+  ProjState st;
+  int rc = proj_layout(ctx, st, n_fixed, 2, n_moving);
+  if (rc) return rc;
+  if (n_projected) *n_projected = 0;
+  if (n_fixed == 0 || n_moving == 0) return 0;
+  ProjParams pp;
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) pp.R[3 * i + j] = pose12[4 * i + j];
+    pp.t[i] = pose12[4 * i + 3];
+  }
+  for (int i = 0; i < 9; ++i) pp.K[i] = cfg->K[i];
+  pp.canvas_cols = (float) cfg->canvas_cols;
+  pp.canvas_rows = (float) cfg->canvas_rows;
+  pp.range_min = cfg->range_min;
+  pp.range_max = cfg->range_max;
+  pp.shape = cfg->shape;
+  pp.radius = cfg->search_radius_pixels;
+  if (pp.radius < 0 || pp.radius > 16000)
+    return pslam_set_error(ctx, PSLAM_E_INVALID, "projective: bad search radius", cudaSuccess);
+  PSLAM_CUDA_TRY(ctx, cudaMemsetAsync(st.d_key1, 0xff, 8 * (size_t) n_fixed, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaMemsetAsync(st.d_key2, 0xff, 8 * (size_t) n_fixed, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaMemsetAsync(st.d_nproj, 0, 4, ctx->stream));
+  const size_t smem = sizeof(int) * (size_t) (pp.radius + 1);
+  if (smem > 48 * 1024)
+    PSLAM_CUDA_TRY(ctx, cudaFuncSetAttribute(projective_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  projective_search_kernel<<<(n_moving + PJ_WARPS - 1) / PJ_WARPS, PJ_WARPS * 32, smem, ctx->stream>>>(
+    pp, st.d_moving, n_moving, st.d_desc_moving, st.d_lattice, n_fixed, st.d_desc_fixed, st.d_cand,
+    st.d_nproj);
+  PSLAM_LAUNCH_CHECK(ctx, "projective_search_kernel");
+  const int nb = (2 * n_moving + 255) / 256;
+  filter_min1_kernel<<<nb, 256, 0, ctx->stream>>>(st.d_cand, n_moving, st.d_key1);
+  PSLAM_LAUNCH_CHECK(ctx, "filter_min1_kernel");
+  filter_min2_kernel<<<nb, 256, 0, ctx->stream>>>(st.d_cand, n_moving, st.d_key1, st.d_key2);
+  PSLAM_LAUNCH_CHECK(ctx, "filter_min2_kernel");
+  filter_accept_kernel<<<(n_fixed + 255) / 256, 256, 0, ctx->stream>>>(
+    n_fixed, st.d_key1, st.d_key2, cfg->descriptor_distance,
+    cfg->maximum_distance_ratio_to_second_best, st.d_acc_m, st.d_acc_d);
+  PSLAM_LAUNCH_CHECK(ctx, "filter_accept_kernel");
+
+  // D2H: per-moving candidate pairs (for the reference's output ORDER) and per-fixed decisions
+  std::vector<int> cand(4 * (size_t) n_moving), acc_m(n_fixed);
+  std::vector<float> acc_d(n_fixed);
+  int nproj = 0;
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(cand.data(), st.d_cand, 16 * (size_t) n_moving, cudaMemcpyDeviceToHost, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(acc_m.data(), st.d_acc_m, 4 * (size_t) n_fixed, cudaMemcpyDeviceToHost, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(acc_d.data(), st.d_acc_d, 4 * (size_t) n_fixed, cudaMemcpyDeviceToHost, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(&nproj, st.d_nproj, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (n_projected) *n_projected = nproj;
+  // Output order of the reference = iteration order of
+  //   std::unordered_map<size_t, CorrespondenceVector> reserved with fixed->size() and filled in
+  //   candidate order (base_impl.cpp:185-200, 50).  Replayed with the real container: keys only.
+  std::unordered_map<size_t, int> by_fixed;
+  by_fixed.reserve((size_t) n_fixed);
+  for (int m = 0; m < n_moving; ++m) {
+    const int fb = cand[4 * (size_t) m], fs = cand[4 * (size_t) m + 2];
+    if (fb >= 0) {
+      by_fixed.emplace((size_t) fb, 0);
+      if (fs >= 0) by_fixed.emplace((size_t) fs, 0);
+    }
+  }
+  int n_out = 0;
+  for (const auto& kv : by_fixed) {
+    const int f = (int) kv.first;
+    if (acc_m[f] < 0) continue;
+    if (n_out < capacity) {
+      h_fixed[n_out] = f;
+      h_moving[n_out] = acc_m[f];
+      h_dist[n_out] = acc_d[f];
+    }
+    ++n_out;
+  }
+  return n_out;
+}

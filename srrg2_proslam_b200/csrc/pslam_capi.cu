@@ -1,0 +1,521 @@
+// pslam_capi.cu -- the C ABI (include/pslam_cuda.h): context management and the entry points that
+// sequence the sm_100a kernels on the context's stream.  No CPU fallback exists: every compute entry
+// point launches kernels; without a usable CUDA device pslam_create fails with PSLAM_E_CUDA.
+#include <math.h>
+
+#include <new>
+#include <vector>
+
+#include "pslam_internal.cuh"
+#include "pslam_kernels.cuh"
+
+namespace {
+
+int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+template <typename T>
+cudaError_t dmalloc(T** p, size_t n) {
+  return cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T));
+}
+
+int check_flags(pslam_ctx* ctx) {
+  int* h = reinterpret_cast<int*>(ctx->h_pinned);
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(h, ctx->d_flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (h[0]) {
+    char msg[160];
+    snprintf(msg, sizeof(msg), "capacity exceeded (flags=%d: 1 max_raw_per_bin, 2 max_features, 4 candidates)", h[0]);
+    PSLAM_CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_flags, 0, sizeof(int), ctx->stream));
+    return pslam_set_error(ctx, PSLAM_E_CAPACITY, msg, cudaSuccess);
+  }
+  return PSLAM_OK;
+}
+
+int validate_extract(pslam_ctx* ctx, int n_images, int rows, int cols, const pslam_extract_cfg* cfg) {
+  if (!ctx || !cfg) return PSLAM_E_INVALID;
+  if (n_images < 0 || n_images > ctx->lim.max_images || rows <= 0 || cols <= 0 ||
+      rows > ctx->lim.max_rows || cols > ctx->lim.max_cols)
+    return pslam_set_error(ctx, PSLAM_E_CAPACITY, "image batch exceeds the context limits", cudaSuccess);
+  // reference: IntensityFeatureExtractorBinned_::init throws on these (binned.cpp:13-28)
+  if (cfg->number_of_detectors_vertical <= 0)
+    return pslam_set_error(ctx, PSLAM_E_INVALID, "IntensityFeatureExtractor::init|ERROR: invalid number of vertical detectors (check configuration!)", cudaSuccess);
+  if (cfg->number_of_detectors_horizontal <= 0)
+    return pslam_set_error(ctx, PSLAM_E_INVALID, "IntensityFeatureExtractor::init|ERROR: invalid number of horizontal detectors (check configuration!)", cudaSuccess);
+  if (cfg->number_of_detectors_horizontal * cfg->number_of_detectors_vertical > ctx->lim.max_bins)
+    return pslam_set_error(ctx, PSLAM_E_CAPACITY, "more detection regions than pslam_limits.max_bins", cudaSuccess);
+  if (rows < 8 || cols < 8)
+    return pslam_set_error(ctx, PSLAM_E_INVALID, "image smaller than 8x8", cudaSuccess);
+  return PSLAM_OK;
+}
+
+// detect -> select -> assemble -> describe for images already on the device
+int run_extract(pslam_ctx* ctx, const uint8_t* d_images, long long image_pitch, int n_images, int rows,
+                int cols, int stride, const pslam_extract_cfg* cfg, const uint8_t* d_mask) {
+  int rc;
+  ctx->rows = rows;
+  ctx->cols = cols;
+  ctx->n_images = n_images;
+  if (n_images == 0) return PSLAM_OK;
+  if ((rc = pslam_k_fast_blur(ctx, d_images, image_pitch, n_images, rows, cols, stride,
+                              (int) cfg->detector_threshold, cfg->enable_non_maximum_suppression))) return rc;
+  int nh = cfg->number_of_detectors_horizontal, nv = cfg->number_of_detectors_vertical;
+  // quota = size_t(float(target) / regions)   (binned.cpp:72-75)
+  const float qf = static_cast<float>(cfg->target_number_of_keypoints) / static_cast<float>((size_t) (nh * nv));
+  unsigned long long quota = qf <= 0.0f ? 0ULL : (unsigned long long) qf;
+  if (d_mask) {  // "only perform binning if mask is not set" (binned.cpp:167)
+    nh = nv = 1;
+    quota = ~0ULL;
+  }
+  if ((rc = pslam_k_bin_select(ctx, n_images, rows, cols, nh, nv, quota, d_mask))) return rc;
+  if ((rc = pslam_k_assemble(ctx, d_images, image_pitch, stride, n_images, rows, cols, nh * nv, 31))) return rc;
+  if ((rc = pslam_k_describe(ctx, n_images))) return rc;
+  return PSLAM_OK;
+}
+
+int upload_images(pslam_ctx* ctx, const uint8_t* h, int n_images, int rows, int cols, int stride,
+                  long long image_pitch_bytes) {
+  // one strided copy per batch when the host layout allows it, else one per image
+  for (int i = 0; i < n_images; ++i) {
+    PSLAM_CUDA_TRY(ctx, cudaMemcpy2DAsync(ctx->d_images + (size_t) i * ctx->img_slot, ctx->img_pitch,
+                                          h + (size_t) i * image_pitch_bytes, stride, cols, rows,
+                                          cudaMemcpyHostToDevice, ctx->stream));
+  }
+  return PSLAM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* pslam_version(void) { return "srrg2_proslam_b200 0.1 (sm_100a)"; }
+
+int pslam_create(int device, const pslam_limits* lim, pslam_ctx** out) {
+  if (!lim || !out) return PSLAM_E_INVALID;
+  *out = nullptr;
+  if (lim->max_images <= 0 || lim->max_rows <= 0 || lim->max_cols <= 0 || lim->max_features <= 0 ||
+      lim->max_features > PSLAM_MAX_FEATURES_HARD || lim->max_raw_per_bin <= 0 || lim->max_bins <= 0)
+    return PSLAM_E_INVALID;
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0 || device < 0 || device >= n_dev) {
+    cudaGetLastError();
+    return PSLAM_E_CUDA;  // no CPU fallback
+  }
+  pslam_ctx* ctx = new (std::nothrow) pslam_ctx();
+  if (!ctx) return PSLAM_E_INVALID;
+  memset(ctx, 0, sizeof(*ctx));
+  ctx->device = device;
+  ctx->lim = *lim;
+  *out = ctx;  // returned even on failure so that pslam_last_error is readable; caller destroys
+  PSLAM_CUDA_TRY(ctx, cudaSetDevice(device));
+  PSLAM_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  ctx->img_pitch = round_up(lim->max_cols, 128);
+  ctx->map_pitch = round_up(lim->max_cols, 128);
+  ctx->img_slot = (size_t) ctx->img_pitch * lim->max_rows;
+  ctx->map_slot = (size_t) ctx->map_pitch * lim->max_rows;
+  const size_t NI = lim->max_images, MF = lim->max_features, NP = (lim->max_images + 1) / 2;
+  PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_images, NI * ctx->img_slot));
+  PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_nms, NI * ctx->map_slot));
+  PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_blur, NI * ctx->map_slot));
+  PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_mask, ctx->map_slot));
+  PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_raw, NI * lim->max_bins * (size_t) lim->max_raw_per_bin));
+  PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_raw_count, NI * lim->max_bins));
+  PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_sel_count, NI * lim->max_bins));
+  PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_xy, NI * MF));
+  PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_resp, NI * MF));
+  PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_inten, NI * MF));
+  PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_desc, NI * MF * 8));
+  PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_count, NI));
+  PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_st_uvuv, NP * MF));
+  PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_st_left, NP * MF));
+  PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_st_right, NP * MF));
+  PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_st_dist, NP * MF));
+  PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_st_count, NP));
+  PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_ep_fixed, NP * MF));
+  PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_ep_moving, NP * MF));
+  PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_ep_dist, NP * MF));
+  PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_ep_count, NP));
+  PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_flags, 4));
+  PSLAM_CUDA_TRY(ctx, cudaMemset(ctx->d_flags, 0, 4 * sizeof(int)));
+  PSLAM_CUDA_TRY(ctx, cudaMemset(ctx->d_count, 0, NI * sizeof(int)));
+  ctx->scratch_bytes = (size_t) 64 << 20;
+  PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_scratch, ctx->scratch_bytes));
+  ctx->pinned_bytes = 1 << 20;
+  PSLAM_CUDA_TRY(ctx, cudaMallocHost(&ctx->h_pinned, ctx->pinned_bytes));
+  int rc = pslam_k_upload_pattern(ctx);
+  if (rc) return rc;
+  return PSLAM_OK;
+}
+
+void pslam_destroy(pslam_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  void* bufs[] = {ctx->d_images, ctx->d_nms, ctx->d_blur, ctx->d_mask, ctx->d_raw, ctx->d_raw_count,
+                  ctx->d_sel_count, ctx->d_xy, ctx->d_resp, ctx->d_inten, ctx->d_desc, ctx->d_count,
+                  ctx->d_st_uvuv, ctx->d_st_left, ctx->d_st_right, ctx->d_st_dist, ctx->d_st_count,
+                  ctx->d_ep_fixed, ctx->d_ep_moving, ctx->d_ep_dist, ctx->d_ep_count, ctx->d_flags,
+                  ctx->d_scratch};
+  for (void* b : bufs)
+    if (b) cudaFree(b);
+  if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* pslam_last_error(const pslam_ctx* ctx) { return ctx ? ctx->err : "null context"; }
+long long pslam_launch_count(const pslam_ctx* ctx) { return ctx ? ctx->launches : 0; }
+void* pslam_stream(const pslam_ctx* ctx) { return ctx ? (void*) ctx->stream : nullptr; }
+int pslam_synchronize(pslam_ctx* ctx) {
+  if (!ctx) return PSLAM_E_INVALID;
+  PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return PSLAM_OK;
+}
+
+// ---- stage 1 ------------------------------------------------------------------------------------
+int pslam_extract_binned_batch_dev(pslam_ctx* ctx, const uint8_t* d_images, int n_images, int rows,
+                                   int cols, int stride, long long image_pitch_bytes,
+                                   const pslam_extract_cfg* cfg) {
+  int rc = validate_extract(ctx, n_images, rows, cols, cfg);
+  if (rc) return rc;
+  PSLAM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  return run_extract(ctx, d_images, image_pitch_bytes, n_images, rows, cols, stride, cfg, nullptr);
+}
+
+int pslam_download_feature_counts(pslam_ctx* ctx, int n_images, int* counts) {
+  if (!ctx || n_images > ctx->lim.max_images) return PSLAM_E_INVALID;
+  int rc = check_flags(ctx);
+  if (rc) return rc;
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(counts, ctx->d_count, sizeof(int) * n_images, cudaMemcpyDeviceToHost, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return PSLAM_OK;
+}
+
+int pslam_download_features(pslam_ctx* ctx, int slot, int capacity, float* xy, float* response,
+                            float* intensity, uint8_t* desc) {
+  if (!ctx || slot < 0 || slot >= ctx->lim.max_images) return PSLAM_E_INVALID;
+  int rc = check_flags(ctx);
+  if (rc) return rc;
+  int* h = reinterpret_cast<int*>(ctx->h_pinned);
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(h, ctx->d_count + slot, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  const int n = h[0];
+  const int m = n < capacity ? n : capacity;
+  const size_t o = (size_t) slot * ctx->lim.max_features;
+  if (m > 0) {
+    if (xy) PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(xy, ctx->d_xy + o, sizeof(float2) * m, cudaMemcpyDeviceToHost, ctx->stream));
+    if (response) PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(response, ctx->d_resp + o, sizeof(float) * m, cudaMemcpyDeviceToHost, ctx->stream));
+    if (intensity) PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(intensity, ctx->d_inten + o, sizeof(float) * m, cudaMemcpyDeviceToHost, ctx->stream));
+    if (desc) PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(desc, ctx->d_desc + o * 8, 32 * (size_t) m, cudaMemcpyDeviceToHost, ctx->stream));
+    PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return n;
+}
+
+int pslam_extract_binned(pslam_ctx* ctx, const uint8_t* image, int rows, int cols, int stride,
+                         const pslam_extract_cfg* cfg, const uint8_t* mask, int capacity, float* xy,
+                         float* response, float* intensity, uint8_t* desc) {
+  int rc = validate_extract(ctx, 1, rows, cols, cfg);
+  if (rc) return rc;
+  if (!image) return PSLAM_E_INVALID;
+  PSLAM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if ((rc = upload_images(ctx, image, 1, rows, cols, stride, 0))) return rc;
+  const uint8_t* d_mask = nullptr;
+  if (mask) {
+    PSLAM_CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_mask, 0, ctx->map_slot, ctx->stream));
+    PSLAM_CUDA_TRY(ctx, cudaMemcpy2DAsync(ctx->d_mask, ctx->map_pitch, mask, cols, cols, rows, cudaMemcpyHostToDevice, ctx->stream));
+    d_mask = ctx->d_mask;
+  }
+  if ((rc = run_extract(ctx, ctx->d_images, (long long) ctx->img_slot, 1, rows, cols, ctx->img_pitch, cfg, d_mask))) return rc;
+  return pslam_download_features(ctx, 0, capacity, xy, response, intensity, desc);
+}
+
+int pslam_fast_detect(pslam_ctx* ctx, const uint8_t* image, int rows, int cols, int stride,
+                      int threshold, int nms, int capacity, float* xy, float* response) {
+  pslam_extract_cfg cfg{(float) threshold, nms, 0, 1, 1};
+  int rc = validate_extract(ctx, 1, rows, cols, &cfg);
+  if (rc) return rc;
+  PSLAM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if ((rc = upload_images(ctx, image, 1, rows, cols, stride, 0))) return rc;
+  if ((rc = pslam_k_fast_blur(ctx, ctx->d_images, (long long) ctx->img_slot, 1, rows, cols, ctx->img_pitch, threshold, nms))) return rc;
+  if ((rc = pslam_k_bin_select(ctx, 1, rows, cols, 1, 1, ~0ULL, nullptr))) return rc;
+  // no ORB border filter here: border 0 keeps every FAST keypoint
+  if ((rc = pslam_k_assemble(ctx, ctx->d_images, (long long) ctx->img_slot, ctx->img_pitch, 1, rows, cols, 1, 0))) return rc;
+  return pslam_download_features(ctx, 0, capacity, xy, response, nullptr, nullptr);
+}
+
+int pslam_blur7(pslam_ctx* ctx, const uint8_t* image, int rows, int cols, int stride, uint8_t* out) {
+  pslam_extract_cfg cfg{255.0f, 1, 0, 1, 1};
+  int rc = validate_extract(ctx, 1, rows, cols, &cfg);
+  if (rc) return rc;
+  PSLAM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if ((rc = upload_images(ctx, image, 1, rows, cols, stride, 0))) return rc;
+  if ((rc = pslam_k_fast_blur(ctx, ctx->d_images, (long long) ctx->img_slot, 1, rows, cols, ctx->img_pitch, 255, 1))) return rc;
+  PSLAM_CUDA_TRY(ctx, cudaMemcpy2DAsync(out, cols, ctx->d_blur, ctx->map_pitch, cols, rows, cudaMemcpyDeviceToHost, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return PSLAM_OK;
+}
+
+// ---- stage 2a -----------------------------------------------------------------------------------
+static int upload_cloud(pslam_ctx* ctx, int slot, int n, const float* xy, const uint8_t* desc) {
+  if (n > ctx->lim.max_features) return pslam_set_error(ctx, PSLAM_E_CAPACITY, "cloud larger than pslam_limits.max_features", cudaSuccess);
+  const size_t o = (size_t) slot * ctx->lim.max_features;
+  if (n > 0) {
+    PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_xy + o, xy, sizeof(float2) * n, cudaMemcpyHostToDevice, ctx->stream));
+    PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_desc + o * 8, desc, 32 * (size_t) n, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_count + slot, &n, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // &n is a stack variable
+  return PSLAM_OK;
+}
+
+int pslam_match_epipolar(pslam_ctx* ctx, int n_fixed, const float* xy_fixed, const uint8_t* desc_fixed,
+                         int n_moving, const float* xy_moving, const uint8_t* desc_moving,
+                         const pslam_match_cfg* cfg, int capacity, int* fixed_idx, int* moving_idx,
+                         float* distance) {
+  if (!ctx || !cfg || n_fixed < 0 || n_moving < 0 || ctx->lim.max_images < 2) return PSLAM_E_INVALID;
+  PSLAM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = upload_cloud(ctx, 0, n_fixed, xy_fixed, desc_fixed))) return rc;
+  if ((rc = upload_cloud(ctx, 1, n_moving, xy_moving, desc_moving))) return rc;
+  if ((rc = pslam_k_epipolar(ctx, 1, cfg))) return rc;
+  int* h = reinterpret_cast<int*>(ctx->h_pinned);
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(h, ctx->d_ep_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  const int n = h[0];
+  const int m = n < capacity ? n : capacity;
+  if (m > 0) {
+    PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(fixed_idx, ctx->d_ep_fixed, sizeof(int) * m, cudaMemcpyDeviceToHost, ctx->stream));
+    PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(moving_idx, ctx->d_ep_moving, sizeof(int) * m, cudaMemcpyDeviceToHost, ctx->stream));
+    PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(distance, ctx->d_ep_dist, sizeof(float) * m, cudaMemcpyDeviceToHost, ctx->stream));
+    PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return n;
+}
+
+// ---- stage 1 + 2a -------------------------------------------------------------------------------
+int pslam_stereo_frontend_batch_dev(pslam_ctx* ctx, const uint8_t* d_images, int n_pairs, int rows,
+                                    int cols, int stride, long long image_pitch_bytes,
+                                    const pslam_extract_cfg* ecfg, const pslam_match_cfg* mcfg) {
+  if (!mcfg) return PSLAM_E_INVALID;
+  int rc = validate_extract(ctx, 2 * n_pairs, rows, cols, ecfg);
+  if (rc) return rc;
+  PSLAM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if ((rc = run_extract(ctx, d_images, image_pitch_bytes, 2 * n_pairs, rows, cols, stride, ecfg, nullptr))) return rc;
+  if (n_pairs > 0 && (rc = pslam_k_epipolar(ctx, n_pairs, mcfg))) return rc;
+  return PSLAM_OK;
+}
+
+int pslam_stereo_frontend_batch(pslam_ctx* ctx, const uint8_t* h_images, int n_pairs, int rows,
+                                int cols, int stride, long long image_pitch_bytes,
+                                const pslam_extract_cfg* ecfg, const pslam_match_cfg* mcfg) {
+  if (!mcfg || !h_images) return PSLAM_E_INVALID;
+  int rc = validate_extract(ctx, 2 * n_pairs, rows, cols, ecfg);
+  if (rc) return rc;
+  PSLAM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (stride == cols && image_pitch_bytes == (long long) rows * cols && cols == ctx->img_pitch &&
+      (size_t) rows * cols == ctx->img_slot) {
+    PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_images, h_images, (size_t) 2 * n_pairs * ctx->img_slot, cudaMemcpyHostToDevice, ctx->stream));
+  } else if ((rc = upload_images(ctx, h_images, 2 * n_pairs, rows, cols, stride, image_pitch_bytes))) {
+    return rc;
+  }
+  if ((rc = run_extract(ctx, ctx->d_images, (long long) ctx->img_slot, 2 * n_pairs, rows, cols, ctx->img_pitch, ecfg, nullptr))) return rc;
+  if (n_pairs > 0 && (rc = pslam_k_epipolar(ctx, n_pairs, mcfg))) return rc;
+  return PSLAM_OK;
+}
+
+int pslam_download_stereo_counts(pslam_ctx* ctx, int n_pairs, int* counts) {
+  if (!ctx || 2 * n_pairs > ctx->lim.max_images + 1) return PSLAM_E_INVALID;
+  int rc = check_flags(ctx);
+  if (rc) return rc;
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(counts, ctx->d_st_count, sizeof(int) * n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return PSLAM_OK;
+}
+
+int pslam_download_stereo_points(pslam_ctx* ctx, int pair, int capacity, float* uvuv, int* left_idx,
+                                 int* right_idx, float* distance) {
+  if (!ctx || pair < 0 || 2 * pair >= ctx->lim.max_images) return PSLAM_E_INVALID;
+  int rc = check_flags(ctx);
+  if (rc) return rc;
+  int* h = reinterpret_cast<int*>(ctx->h_pinned);
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(h, ctx->d_st_count + pair, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  const int n = h[0];
+  const int m = n < capacity ? n : capacity;
+  const size_t o = (size_t) pair * ctx->lim.max_features;
+  if (m > 0) {
+    if (uvuv) PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(uvuv, ctx->d_st_uvuv + o, sizeof(float4) * m, cudaMemcpyDeviceToHost, ctx->stream));
+    if (left_idx) PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(left_idx, ctx->d_st_left + o, sizeof(int) * m, cudaMemcpyDeviceToHost, ctx->stream));
+    if (right_idx) PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(right_idx, ctx->d_st_right + o, sizeof(int) * m, cudaMemcpyDeviceToHost, ctx->stream));
+    if (distance) PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(distance, ctx->d_st_dist + o, sizeof(float) * m, cudaMemcpyDeviceToHost, ctx->stream));
+    PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return n;
+}
+
+int pslam_stereo_adaptor(pslam_ctx* ctx, const uint8_t* left, const uint8_t* right, int rows, int cols,
+                         int stride, const pslam_extract_cfg* ecfg, const pslam_match_cfg* mcfg,
+                         int capacity, float* uvuv, float* intensity, uint8_t* desc) {
+  if (!ctx || !left || !right || !mcfg) return PSLAM_E_INVALID;
+  int rc = validate_extract(ctx, 2, rows, cols, ecfg);
+  if (rc) return rc;
+  PSLAM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if ((rc = upload_images(ctx, left, 1, rows, cols, stride, 0))) return rc;
+  PSLAM_CUDA_TRY(ctx, cudaMemcpy2DAsync(ctx->d_images + ctx->img_slot, ctx->img_pitch, right, stride, cols, rows, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = run_extract(ctx, ctx->d_images, (long long) ctx->img_slot, 2, rows, cols, ctx->img_pitch, ecfg, nullptr))) return rc;
+  if ((rc = pslam_k_epipolar(ctx, 1, mcfg))) return rc;
+  std::vector<int> li((size_t) ctx->lim.max_features);
+  const int n = pslam_download_stereo_points(ctx, 0, capacity, uvuv, li.data(), nullptr, nullptr);
+  if (n < 0) return n;
+  const int m = n < capacity ? n : capacity;
+  if (m > 0 && (intensity || desc)) {
+    // descriptor + intensity of the LEFT feature (stereo_projective.cpp:114-116): gather on the host
+    std::vector<float> inten((size_t) ctx->lim.max_features);
+    std::vector<uint8_t> d(32 * (size_t) ctx->lim.max_features);
+    const int nl = pslam_download_features(ctx, 0, ctx->lim.max_features, nullptr, nullptr, inten.data(), d.data());
+    if (nl < 0) return nl;
+    for (int i = 0; i < m; ++i) {
+      if (intensity) intensity[i] = inten[li[i]];
+      if (desc) memcpy(desc + 32 * (size_t) i, d.data() + 32 * (size_t) li[i], 32);
+    }
+  }
+  return n;
+}
+
+// ---- stage 2b -----------------------------------------------------------------------------------
+static int bf_upload(pslam_ctx* ctx, int nf, const uint8_t* df, int nm, const uint8_t* dm,
+                     uint32_t** d_f, uint32_t** d_m, size_t* used) {
+  const size_t bf = ((size_t) 32 * nf + 255) & ~(size_t) 255, bm = ((size_t) 32 * nm + 255) & ~(size_t) 255;
+  if (bf + bm + (16 << 20) > ctx->scratch_bytes)
+    return pslam_set_error(ctx, PSLAM_E_CAPACITY, "bruteforce: descriptor sets exceed the scratch buffer", cudaSuccess);
+  // descriptors live at the END of the scratch buffer, the kernels carve from the front
+  *d_f = reinterpret_cast<uint32_t*>(ctx->d_scratch + ctx->scratch_bytes - bf - bm);
+  *d_m = reinterpret_cast<uint32_t*>(ctx->d_scratch + ctx->scratch_bytes - bm);
+  if (nf > 0) PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(*d_f, df, (size_t) 32 * nf, cudaMemcpyHostToDevice, ctx->stream));
+  if (nm > 0) PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(*d_m, dm, (size_t) 32 * nm, cudaMemcpyHostToDevice, ctx->stream));
+  *used = bf + bm;
+  return PSLAM_OK;
+}
+
+int pslam_bf_best2_dev(pslam_ctx* ctx, int n_fixed, const uint32_t* d_desc_fixed, int n_moving,
+                       const uint32_t* d_desc_moving, int32_t* d_best, int32_t* d_second,
+                       int32_t* d_best_idx) {
+  if (!ctx || n_fixed < 0 || n_moving < 0) return PSLAM_E_INVALID;
+  PSLAM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  return pslam_k_bf_best2(ctx, n_fixed, d_desc_fixed, n_moving, d_desc_moving, d_best, d_second, d_best_idx);
+}
+
+int pslam_bf_best2(pslam_ctx* ctx, int n_fixed, const uint8_t* desc_fixed, int n_moving,
+                   const uint8_t* desc_moving, int32_t* best, int32_t* second, int32_t* best_idx) {
+  if (!ctx || n_fixed < 0 || n_moving < 0) return PSLAM_E_INVALID;
+  PSLAM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  uint32_t *d_f, *d_m;
+  size_t used;
+  int rc = bf_upload(ctx, n_fixed, desc_fixed, n_moving, desc_moving, &d_f, &d_m, &used);
+  if (rc) return rc;
+  if (n_fixed == 0) return PSLAM_OK;
+  const size_t ob = ((size_t) 4 * n_fixed + 255) & ~(size_t) 255;
+  int32_t* d_out = reinterpret_cast<int32_t*>(ctx->d_scratch + ctx->scratch_bytes - used - 3 * ob);
+  const size_t saved = ctx->scratch_bytes;
+  ctx->scratch_bytes = saved - used - 3 * ob;  // kernels may only carve below the outputs
+  rc = pslam_k_bf_best2(ctx, n_fixed, d_f, n_moving, d_m, d_out, d_out + ob / 4, d_out + 2 * ob / 4);
+  ctx->scratch_bytes = saved;
+  if (rc) return rc;
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(best, d_out, 4 * (size_t) n_fixed, cudaMemcpyDeviceToHost, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(second, d_out + ob / 4, 4 * (size_t) n_fixed, cudaMemcpyDeviceToHost, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(best_idx, d_out + 2 * ob / 4, 4 * (size_t) n_fixed, cudaMemcpyDeviceToHost, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return PSLAM_OK;
+}
+
+int pslam_match_bruteforce(pslam_ctx* ctx, int n_fixed, const uint8_t* desc_fixed, int n_moving,
+                           const uint8_t* desc_moving, const pslam_match_cfg* cfg, int capacity,
+                           int* fixed_idx, int* moving_idx, float* distance) {
+  if (!ctx || !cfg || n_fixed < 0 || n_moving < 0) return PSLAM_E_INVALID;
+  PSLAM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  uint32_t *d_f, *d_m;
+  size_t used;
+  int rc = bf_upload(ctx, n_fixed, desc_fixed, n_moving, desc_moving, &d_f, &d_m, &used);
+  if (rc) return rc;
+  const size_t saved = ctx->scratch_bytes;
+  ctx->scratch_bytes = saved - used;
+  rc = pslam_k_bf_match(ctx, n_fixed, d_f, n_moving, d_m, cfg->maximum_descriptor_distance,
+                        cfg->maximum_distance_ratio_to_second_best, capacity, fixed_idx, moving_idx, distance);
+  ctx->scratch_bytes = saved;
+  return rc;
+}
+
+// ---- stage 2c -----------------------------------------------------------------------------------
+int pslam_projective_set_fixed(pslam_ctx* ctx, int n_fixed, const float* coords, int dim, const uint8_t* desc) {
+  if (!ctx || n_fixed < 0 || dim < 2 || dim > 4) return PSLAM_E_INVALID;
+  PSLAM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  return pslam_k_projective_set_fixed(ctx, n_fixed, coords, dim, desc);
+}
+int pslam_projective_set_moving(pslam_ctx* ctx, int n_moving, const float* xyz, const uint8_t* desc) {
+  if (!ctx || n_moving < 0) return PSLAM_E_INVALID;
+  PSLAM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  return pslam_k_projective_set_moving(ctx, n_moving, xyz, desc);
+}
+int pslam_projective_match(pslam_ctx* ctx, int n_fixed, int n_moving, const float* pose12,
+                           const pslam_projective_cfg* cfg, int capacity, int* fixed_idx,
+                           int* moving_idx, float* distance, int* n_projected) {
+  if (!ctx || !cfg || !pose12) return PSLAM_E_INVALID;
+  PSLAM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  return pslam_k_projective_match(ctx, n_fixed, n_moving, pose12, cfg, capacity, fixed_idx, moving_idx, distance, n_projected);
+}
+int pslam_match_projective(pslam_ctx* ctx, int n_fixed, const float* fixed_coords, int fixed_dim,
+                           const uint8_t* desc_fixed, int n_moving, const float* moving_xyz,
+                           const uint8_t* desc_moving, const float* pose12,
+                           const pslam_projective_cfg* cfg, int capacity, int* fixed_idx,
+                           int* moving_idx, float* distance, int* n_projected) {
+  int rc;
+  if ((rc = pslam_projective_set_fixed(ctx, n_fixed, fixed_coords, fixed_dim, desc_fixed))) return rc;
+  if ((rc = pslam_projective_set_moving(ctx, n_moving, moving_xyz, desc_moving))) return rc;
+  return pslam_projective_match(ctx, n_fixed, n_moving, pose12, cfg, capacity, fixed_idx, moving_idx, distance, n_projected);
+}
+
+// ---- stages 3 + 4 -------------------------------------------------------------------------------
+int pslam_linearize_se3(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, const double* pose12,
+                        int n_moving, const double* moving_xyz, int n_fixed, const double* fixed_meas,
+                        int fixed_dim, int n_corr, const int* corr_fixed, const int* corr_moving,
+                        const double* info_diag, double* H36, double* b6, double* stats4) {
+  if (!ctx || !cfg || !pose12 || n_corr < 0 || fixed_dim < 2 || fixed_dim > 4) return PSLAM_E_INVALID;
+  if (cfg->kind < 0 || cfg->kind > 2 || cfg->robustifier < 0 || cfg->robustifier > 2) return PSLAM_E_INVALID;
+  PSLAM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  // validate indices on the host (the reference asserts; we refuse)
+  for (int k = 0; k < n_corr; ++k)
+    if (corr_fixed[k] < 0 || corr_fixed[k] >= n_fixed || corr_moving[k] < 0 || corr_moving[k] >= n_moving)
+      return pslam_set_error(ctx, PSLAM_E_INVALID, "linearize: correspondence index out of range", cudaSuccess);
+  uint8_t* p = ctx->d_scratch;
+  auto carve = [&](size_t bytes) {
+    uint8_t* r = p;
+    p += (bytes + 255) & ~(size_t) 255;
+    return r;
+  };
+  double* d_mv = (double*) carve(sizeof(double) * 3 * (size_t) n_moving);
+  double* d_fx = (double*) carve(sizeof(double) * fixed_dim * (size_t) n_fixed);
+  double* d_info = (double*) carve(sizeof(double) * 3 * (size_t) n_fixed);
+  int* d_cf = (int*) carve(sizeof(int) * (size_t) n_corr);
+  int* d_cm = (int*) carve(sizeof(int) * (size_t) n_corr);
+  if ((size_t) (p - ctx->d_scratch) + (1 << 20) > ctx->scratch_bytes)
+    return pslam_set_error(ctx, PSLAM_E_CAPACITY, "linearize: scratch too small", cudaSuccess);
+  if (n_moving) PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_mv, moving_xyz, sizeof(double) * 3 * (size_t) n_moving, cudaMemcpyHostToDevice, ctx->stream));
+  if (n_fixed) {
+    PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_fx, fixed_meas, sizeof(double) * fixed_dim * (size_t) n_fixed, cudaMemcpyHostToDevice, ctx->stream));
+    PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_info, info_diag, sizeof(double) * 3 * (size_t) n_fixed, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (n_corr) {
+    PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_cf, corr_fixed, sizeof(int) * (size_t) n_corr, cudaMemcpyHostToDevice, ctx->stream));
+    PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_cm, corr_moving, sizeof(int) * (size_t) n_corr, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  return pslam_k_linearize(ctx, cfg, pose12, n_moving, d_mv, n_fixed, d_fx, fixed_dim, n_corr, d_cf, d_cm, d_info, H36, b6, stats4);
+}
+
+int pslam_gn_step(pslam_ctx* ctx, const double* H36, const double* b6, double damping, double* pose12,
+                  double* dx6) {
+  if (!ctx || !H36 || !b6 || !pose12) return PSLAM_E_INVALID;
+  PSLAM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  return pslam_k_gn_step(ctx, H36, b6, damping, pose12, dx6);
+}
+
+}  // extern "C"

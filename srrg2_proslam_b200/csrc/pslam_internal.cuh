@@ -1,0 +1,132 @@
+// pslam_internal.cuh -- context layout and device helpers shared by the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/pslam_cuda.h"
+
+#define PSLAM_MAX_FEATURES_HARD 8192
+
+// ---- HBM-resident state of one context ------------------------------------------------------
+// Layout (all sized once from pslam_limits; nothing is allocated on the hot path):
+//   images   u8  [max_images][max_rows][img_pitch]          staging for the host-pointer entry points
+//   nms_map  u8  [max_images][max_rows][map_pitch]          0 = no keypoint, else FAST response + 1
+//   blur     u8  [max_images][max_rows][map_pitch]          ORB 7x7 integer Gaussian
+//   raw      u32 [max_images][max_bins][max_raw_per_bin]    (pixel index << 8 | response + 1), row-major per bin
+//   features SoA [max_images][max_features]: xy float2, response f32, intensity f32, desc 8 x u32
+//   stereo   SoA [max_images/2][max_features]: uvuv float4, left/right feature index, distance
+// map_pitch and img_pitch are multiples of 128 so every row starts on a 128 B line.
+struct pslam_ctx {
+  int device;
+  cudaStream_t stream;
+  pslam_limits lim;
+  char err[512];
+  long long launches;
+  int img_pitch, map_pitch;
+  size_t img_slot, map_slot;  // bytes per image slot
+  uint8_t* d_images;
+  uint8_t* d_nms;
+  uint8_t* d_blur;
+  uint8_t* d_mask;  // [max_rows][map_pitch], single image (host entry point only)
+  uint32_t* d_raw;
+  int* d_raw_count;
+  int* d_sel_count;
+  float2* d_xy;
+  float* d_resp;
+  float* d_inten;
+  uint32_t* d_desc;
+  int* d_count;
+  // stereo results
+  float4* d_st_uvuv;
+  int* d_st_left;
+  int* d_st_right;
+  float* d_st_dist;
+  int* d_st_count;
+  // raw epipolar correspondences (before the disparity filter), per pair
+  int* d_ep_fixed;
+  int* d_ep_moving;
+  float* d_ep_dist;
+  int* d_ep_count;
+  int* d_flags;  // [0] capacity overflow bits
+  // generic scratch for the host-pointer matchers / solver
+  uint8_t* d_scratch;
+  size_t scratch_bytes;
+  void* h_pinned;  // small pinned staging (counts, flags, H/b)
+  size_t pinned_bytes;
+  // geometry of the last batch
+  int rows, cols, n_images;
+};
+
+#define PSLAM_FLAG_RAW_OVERFLOW 1
+#define PSLAM_FLAG_FEATURE_OVERFLOW 2
+#define PSLAM_FLAG_CANDIDATE_OVERFLOW 4
+
+static inline int pslam_set_error(pslam_ctx* ctx, int code, const char* what, cudaError_t e) {
+  if (ctx) {
+    if (e != cudaSuccess)
+      snprintf(ctx->err, sizeof(ctx->err), "%s: %s", what, cudaGetErrorString(e));
+    else
+      snprintf(ctx->err, sizeof(ctx->err), "%s", what);
+  }
+  return code;
+}
+
+#define PSLAM_CUDA_TRY(ctx, call)                                              \
+  do {                                                                         \
+    cudaError_t e__ = (call);                                                  \
+    if (e__ != cudaSuccess) return pslam_set_error(ctx, PSLAM_E_CUDA, #call, e__); \
+  } while (0)
+
+#define PSLAM_LAUNCH_CHECK(ctx, name)                                          \
+  do {                                                                         \
+    (ctx)->launches++;                                                         \
+    cudaError_t e__ = cudaGetLastError();                                      \
+    if (e__ != cudaSuccess) return pslam_set_error(ctx, PSLAM_E_CUDA, name, e__); \
+  } while (0)
+
+#ifdef __CUDACC__
+// ---- device helpers ---------------------------------------------------------------------------
+__device__ __forceinline__ int reflect101(int i, int n) {
+  // single reflection is enough: |overhang| <= 4 << n
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * (n - 1) - i;
+  return i;
+}
+
+// exclusive scan of one int per thread over a block of NT threads (NT multiple of 32, <= 1024);
+// returns the exclusive prefix, *total receives the block sum.  s_warp: >= 33 ints of smem.
+template <int NT>
+__device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp, int* total) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  __syncthreads();  // protect s_warp reuse across calls
+  if (lane == 31) s_warp[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    int w = (lane < NT / 32) ? s_warp[lane] : 0;
+    int wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += t;
+    }
+    if (lane < NT / 32) s_warp[lane] = wi - w;  // exclusive warp offsets
+    if (lane == 31) s_warp[32] = wi;
+  }
+  __syncthreads();
+  *total = s_warp[32];
+  return s_warp[wid] + incl - v;
+}
+
+__device__ __forceinline__ int hamming256(const uint4 a0, const uint4 a1, const uint4 b0, const uint4 b1) {
+  return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+         __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+#endif

@@ -1,0 +1,41 @@
+// pslam_kernels.cuh -- host-callable launchers of the sm_100a kernels (one per pipeline step).
+#pragma once
+#include "pslam_internal.cuh"
+
+// k_detect.cu
+int pslam_k_upload_pattern(pslam_ctx* ctx);
+int pslam_k_fast_blur(pslam_ctx* ctx, const uint8_t* d_images, long long image_pitch, int n_images,
+                      int rows, int cols, int stride, int thr, int nms);
+int pslam_k_bin_select(pslam_ctx* ctx, int n_images, int rows, int cols, int nh, int nv,
+                       unsigned long long quota, const uint8_t* d_mask);
+int pslam_k_assemble(pslam_ctx* ctx, const uint8_t* d_images, long long image_pitch, int stride,
+                     int n_images, int rows, int cols, int nbins, int border);
+int pslam_k_describe(pslam_ctx* ctx, int n_images);
+
+// k_epipolar.cu
+int pslam_k_epipolar(pslam_ctx* ctx, int n_pairs, const pslam_match_cfg* cfg);
+
+// k_bruteforce.cu
+int pslam_k_bf_best2(pslam_ctx* ctx, int n_fixed, const uint32_t* d_desc_fixed, int n_moving,
+                     const uint32_t* d_desc_moving, int32_t* d_best, int32_t* d_second,
+                     int32_t* d_best_idx);
+int pslam_k_bf_match(pslam_ctx* ctx, int n_fixed, const uint32_t* d_desc_fixed, int n_moving,
+                     const uint32_t* d_desc_moving, float max_dist, float max_ratio, int capacity,
+                     int* h_fixed, int* h_moving, float* h_dist);
+
+// k_projective.cu
+int pslam_k_projective_set_fixed(pslam_ctx* ctx, int n_fixed, const float* h_coords, int dim,
+                                 const uint8_t* h_desc);
+int pslam_k_projective_set_moving(pslam_ctx* ctx, int n_moving, const float* h_xyz, const uint8_t* h_desc);
+int pslam_k_projective_match(pslam_ctx* ctx, int n_fixed, int n_moving, const float* pose12,
+                             const pslam_projective_cfg* cfg, int capacity, int* h_fixed,
+                             int* h_moving, float* h_dist, int* n_projected);
+
+// k_linearize.cu
+int pslam_k_linearize(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, const double* pose12,
+                      int n_moving, const double* d_moving_xyz, int n_fixed,
+                      const double* d_fixed_meas, int fixed_dim, int n_corr, const int* d_corr_fixed,
+                      const int* d_corr_moving, const double* d_info_diag, double* h_H36,
+                      double* h_b6, double* h_stats4);
+int pslam_k_gn_step(pslam_ctx* ctx, const double* H36, const double* b6, double damping,
+                    double* pose12, double* dx6);

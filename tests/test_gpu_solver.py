@@ -1,0 +1,91 @@
+"""GPU parity, stages 3+4 (SE3 factor linearisation, H/b reduction, GN step) vs the fp64 oracle.
+Tolerance: relative 1e-9 on H and b (BASELINE.json north_star), 1e-9 on the pose update."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+K = np.array([718.856, 0, 607.193, 0, 718.856, 185.216, 0, 0, 1], np.float64)
+RTOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def ctx(oracle):
+    from srrg2_proslam_b200 import capi
+    c = capi.Context(max_images=2, max_rows=64, max_cols=128, max_features=256, max_raw_per_bin=1024)
+    yield c
+    c.close()
+
+
+def synth(n, kind, seed, outlier_frac=0.1):
+    rng = np.random.default_rng(seed)
+    xyz = np.stack([rng.uniform(-8, 8, n), rng.uniform(-2, 2, n), rng.uniform(3, 40, n)], 1)
+    xyz[: n // 20, 2] = -1.0  # behind the camera -> suppressed
+    ang = 0.02
+    R = np.array([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]])
+    t = np.array([0.05, -0.02, 0.4])
+    pc = xyz @ R.T + t
+    h = pc @ K.reshape(3, 3).T
+    u, v = h[:, 0] / h[:, 2], h[:, 1] / h[:, 2]
+    noise = rng.normal(0, 0.5, (n, 3))
+    out = rng.random(n) < outlier_frac
+    noise[out] *= 40
+    if kind == "stereo":
+        meas = np.stack([u + noise[:, 0], v + noise[:, 1], (h[:, 0] - 386.1448) / h[:, 2] + noise[:, 2], v], 1)
+    elif kind == "depth":
+        meas = np.stack([u + noise[:, 0], v + noise[:, 1], pc[:, 2] + 0.01 * noise[:, 2]], 1)
+    else:
+        meas = np.stack([u + noise[:, 0], v + noise[:, 1]], 1)
+    perm = rng.permutation(n)
+    cf, cm = perm.astype(np.int32), np.arange(n, dtype=np.int32)
+    meas_f = np.zeros_like(meas)
+    meas_f[cf] = meas[cm]
+    info = np.tile({"stereo": [1, 2, 1], "depth": [1, 1, 10], "mono": [1, 1, 0]}[kind], (n, 1)).astype(np.float64)
+    info *= rng.uniform(0.5, 3.0, (n, 1))
+    pose0 = np.concatenate([np.eye(3), np.zeros((3, 1))], 1).reshape(12)
+    return xyz, meas_f, cf, cm, info, pose0
+
+
+@pytest.mark.parametrize("kind", ["stereo", "depth", "mono"])
+@pytest.mark.parametrize("n", [0, 1, 7, 300, 5000, 100000])
+@pytest.mark.parametrize("robust,chi", [("saturated", 25.0), ("clamp", 10.0), ("none", 1.0)])
+def test_linearize(ctx, kind, n, robust, chi):
+    xyz, meas, cf, cm, info, pose = synth(max(n, 1), kind, 17 + n)
+    cf, cm = cf[:n], cm[:n]
+    md = 35.0 if kind == "stereo" and n % 2 else 0.0
+    ocfg = O.linearize_cfg(kind, K, 1241, 376, (-386.1448, 0, 0), md, robust, chi)
+    gcfg = ctx.linearize_cfg(kind, K, 1241, 376, (-386.1448, 0, 0), md, robust, chi)
+    Ho, bo, so = O.linearize(ocfg, pose, xyz, meas, cf, cm, info)
+    Hg, bg, sg = ctx.linearize(gcfg, pose, xyz, meas, cf, cm, info)
+    assert (sg["inliers"], sg["outliers"], sg["suppressed"]) == (so["inliers"], so["outliers"], so["suppressed"])
+    scale_H, scale_b = max(np.abs(Ho).max(), 1e-300), max(np.abs(bo).max(), 1e-300)
+    assert np.abs(Hg - Ho).max() <= RTOL * scale_H
+    assert np.abs(bg - bo).max() <= RTOL * scale_b
+    assert abs(sg["chi"] - so["chi"]) <= RTOL * max(abs(so["chi"]), 1e-300)
+    assert np.array_equal(Hg, Hg.T)
+
+
+@pytest.mark.parametrize("kind,damping", [("stereo", 1.0), ("depth", 0.1), ("mono", 0.0)])
+def test_gauss_newton_converges_like_oracle(ctx, kind, damping):
+    xyz, meas, cf, cm, info, pose = synth(400, kind, 99, outlier_frac=0.05)
+    ocfg = O.linearize_cfg(kind, K, 1241, 376, (-386.1448, 0, 0), 0.0, "saturated", 25.0)
+    gcfg = ctx.linearize_cfg(kind, K, 1241, 376, (-386.1448, 0, 0), 0.0, "saturated", 25.0)
+    po, pg = pose.copy(), pose.copy()
+    for it in range(15):
+        Ho, bo, _ = O.linearize(ocfg, po, xyz, meas, cf, cm, info)
+        rc, po, dxo = O.gn_step(Ho, bo, damping, po)
+        assert rc == 0
+        Hg, bg, _ = ctx.linearize(gcfg, pg, xyz, meas, cf, cm, info)
+        pg, dxg = ctx.gn_step(Hg, bg, damping, pg)
+        assert np.abs(pg - po).max() < 1e-9
+    # recovered the synthetic motion (t = (0.05,-0.02,0.4), 0.02 rad about y)
+    assert abs(pg[3] - 0.05) < 0.05 and abs(pg[11] - 0.4) < 0.1
+
+
+def test_gn_not_spd(ctx):
+    from srrg2_proslam_b200 import capi
+    with pytest.raises(capi.PslamError) as e:
+        ctx.gn_step(np.zeros((6, 6)), np.ones(6), 0.0, np.eye(3, 4).reshape(12))
+    assert e.value.code == capi.PSLAM_E_NOT_SPD
