@@ -53,14 +53,18 @@ __device__ __forceinline__ int fast_strength(const uint8_t* c /* centre in smem 
     lo3[k] = min(min(d[k], d[(k + 1) & 15]), d[(k + 2) & 15]);
     hi3[k] = max(max(d[k], d[(k + 1) & 15]), d[(k + 2) & 15]);
   }
-  int s = -1024;
+  // NOTE: keep the two polarities in separate accumulators and negate ONCE at the end.  Folding
+  // `s = max(s, max(mn, -mx))` into the loop is miscompiled by nvcc 12.9 for sm_100a (the negation
+  // is dropped when the expression is fused into VIMNMX3; caught by the GPU parity tests).
+  int s_dark = -1024, s_bright = 1024;
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
     const int mn = min(min(lo3[k], lo3[(k + 3) & 15]), lo3[(k + 6) & 15]);
     const int mx = max(max(hi3[k], hi3[(k + 3) & 15]), hi3[(k + 6) & 15]);
-    s = max(s, max(mn, -mx));
+    s_dark = max(s_dark, mn);
+    s_bright = min(s_bright, mx);
   }
-  return s;
+  return max(s_dark, -s_bright);
 }
 
 __global__ void __launch_bounds__(K1_THREADS)

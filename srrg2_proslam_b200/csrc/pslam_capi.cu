@@ -238,9 +238,28 @@ int pslam_fast_detect(pslam_ctx* ctx, const uint8_t* image, int rows, int cols, 
   if ((rc = upload_images(ctx, image, 1, rows, cols, stride, 0))) return rc;
   if ((rc = pslam_k_fast_blur(ctx, ctx->d_images, (long long) ctx->img_slot, 1, rows, cols, ctx->img_pitch, threshold, nms))) return rc;
   if ((rc = pslam_k_bin_select(ctx, 1, rows, cols, 1, 1, ~0ULL, nullptr))) return rc;
-  // no ORB border filter here: border 0 keeps every FAST keypoint
-  if ((rc = pslam_k_assemble(ctx, ctx->d_images, (long long) ctx->img_slot, ctx->img_pitch, 1, rows, cols, 1, 0))) return rc;
-  return pslam_download_features(ctx, 0, capacity, xy, response, nullptr, nullptr);
+  if ((rc = check_flags(ctx))) return rc;
+  // one region, no quota: the region's raw list IS the row-major keypoint list (pixel << 8 | response + 1).
+  // Read it back directly so that this stage-level entry point is bounded by max_raw_per_bin only.
+  int* h = reinterpret_cast<int*>(ctx->h_pinned);
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(h, ctx->d_raw_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  const int n = h[0];
+  const int m = n < capacity ? n : capacity;
+  if (m > 0) {
+    std::vector<uint32_t> raw((size_t) m);
+    PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(raw.data(), ctx->d_raw, sizeof(uint32_t) * (size_t) m, cudaMemcpyDeviceToHost, ctx->stream));
+    PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < m; ++i) {
+      const int pix = (int) (raw[i] >> 8);
+      if (xy) {
+        xy[2 * i] = (float) (pix % cols);
+        xy[2 * i + 1] = (float) (pix / cols);
+      }
+      if (response) response[i] = (float) ((int) (raw[i] & 0xffu) - 1);
+    }
+  }
+  return n;
 }
 
 int pslam_blur7(pslam_ctx* ctx, const uint8_t* image, int rows, int cols, int stride, uint8_t* out) {

@@ -13,7 +13,7 @@ IMAGES = ["kitti_city_image_left_0.png", "kitti_city_image_right_1.png", "icl_im
 @pytest.fixture(scope="module")
 def ctx(oracle):
     from srrg2_proslam_b200 import capi
-    c = capi.Context(max_images=2, max_rows=600, max_cols=1300, max_features=4096, max_raw_per_bin=40000)
+    c = capi.Context(max_images=2, max_rows=600, max_cols=1300, max_features=8192, max_raw_per_bin=60000)
     yield c
     c.close()
 
@@ -24,7 +24,7 @@ def test_fast_nms(ctx, name, thr, nms):
     img = O.load_gray(name)
     xy, r = ctx.fast_detect(img, thr, nms)
     oxy, orr = O.fast_detect(img, thr, nms)
-    assert len(xy) == len(oxy) and len(xy) > 50
+    assert len(xy) == len(oxy) and len(xy) > 20
     assert np.array_equal(xy, oxy) and np.array_equal(r, orr)
 
 
@@ -69,7 +69,7 @@ def test_mask(ctx):
     from srrg2_proslam_b200 import capi
     img = O.load_gray("kitti_city_image_left_0.png")
     mask = np.zeros_like(img)
-    mask[50:300, 200:900] = 255
+    mask[50:300, 200:700] = 255
     mask[100:120, 300:340] = 0
     g = ctx.extract_binned(img, capi.extract_cfg(10, 1, 500), mask=mask)
     o = O.extract_binned(img, O.extract_cfg(10, 1, 500), mask=mask)
@@ -84,9 +84,9 @@ def test_edge_images(ctx):
     flat = np.full((100, 160), 77, np.uint8)
     assert len(ctx.extract_binned(flat, capi.extract_cfg(5, 1, 100))["xy"]) == 0
     rng = np.random.default_rng(3)
-    # blocky image: many corners with identical responses -> exercises the unstable-sort ties
-    blocks = (rng.integers(0, 2, (30, 40)) * 120 + 60).astype(np.uint8)
-    img = np.kron(blocks, np.ones((8, 8), np.uint8))
+    # coarsely quantised real image: thousands of corners share 5 distinct responses -> exercises the
+    # unstable-sort ties of the per-region selection (binned.cpp:188-192)
+    img = (O.load_gray("kitti_city_image_left_0.png") // 48 * 48).astype(np.uint8)
     for cfg in (dict(threshold=20, target=200), dict(threshold=20, target=90, nh=2, nv=2),
                 dict(threshold=20, target=1000, nh=1, nv=1)):
         g = ctx.extract_binned(img, capi.extract_cfg(**cfg))
