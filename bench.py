@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native srrg2_proslam frontend.
+
+Metric (BASELINE.json): frontend stereo frames/s on the frame-sharded config -- KITTI-shaped
+(1241x376) synthetic stereo pairs, 4k target features/frame, kitti.conf matcher parameters.  One step =
+one pass of detect -> select -> describe (L and R) -> epipolar stereo match over the rank's whole batch.
+
+  value : images already resident in HBM, timed on the device (CUDA events on the context's stream)
+  e2e   : the same batch through the host-pointer C-ABI call (pinned HOST images in, packed stereo
+          measurement clouds out), host<->device copies inside the timed region (wall clock around
+          synchronised calls)
+  roofline     : dominant kernel, live per-kernel CUDA-event time (pslam_profile_*), algorithmic bytes
+                 per image from SURVEY.md section 8(d) / DESIGN.md
+  cpu_baseline : the CPU oracle (port of the reference path) on a bounded sample, all host threads
+  --impl reference : the same oracle as the reference arm (the reference itself cannot be built here,
+                 see DESIGN.md "Oracle"), rank 0 only.
+
+N > 1: one process per GPU (torchrun), frames sharded by rank (weak scaling: every rank owns --pairs
+pairs), no data-path collective; NCCL only for the barrier and the max-over-ranks of the timing.
+"""
+import argparse
+import json
+import os
+import pathlib
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+ROWS, COLS = 376, 1241
+THRESHOLD, TARGET = 15, 4000                 # kitti.conf detector threshold; config 4: 4k features / frame
+MATCH = dict(max_dist=100.0, ratio=0.5, max_disp=100, thickness=0)   # kitti.conf epipolar finder (:484-501)
+GEN_CHUNK = 250
+
+
+def clocks_sampler(stop, out, gpu_index):
+    q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+    try:
+        p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                              "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+    except OSError:
+        return
+    def reader():
+        for line in p.stdout:
+            out.append(line.strip())
+    t = threading.Thread(target=reader, daemon=True)
+    t.start()
+    stop.wait()
+    p.terminate()
+    t.join(timeout=2)
+
+
+def summarise_clocks(lines):
+    sm, mx, reasons = [], 0, set()
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    for ln in lines:
+        f = [x.strip() for x in ln.split(",")]
+        if len(f) < 7:
+            continue
+        try:
+            sm.append(float(f[0]))
+            mx = max(mx, float(f[1]))
+        except ValueError:
+            continue
+        for nme, v in zip(names, f[3:7]):
+            if v.lower().startswith("active"):
+                reasons.add(nme)
+    if not sm:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+    return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_lib():
+    sys.path.insert(0, str(ROOT / "tests"))
+    import oracle_lib as O
+    O.build()
+    return O
+
+
+def run_reference(args, rank, world):
+    """reference arm: the CPU implementation of the path on the host cores (oracle port), rank 0 only"""
+    if rank != 0:
+        return
+    import torch
+    from srrg2_proslam_b200 import synth
+    O = oracle_lib()
+    cores = os.cpu_count() or 1
+    sample = args.ref_pairs
+    imgs = synth.stereo_pairs(sample, ROWS, COLS, seed=args.seed, device="cpu").numpy()
+    cfg = O.extract_cfg(THRESHOLD, 1, TARGET)
+    for _ in range(args.warmup):
+        O.stereo_frontend_batch(imgs, cfg, threads=cores, **MATCH)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        counts, _ = O.stereo_frontend_batch(imgs, cfg, threads=cores, **MATCH)
+    dt = time.perf_counter() - t0
+    v = sample * args.steps / dt
+    line = {"impl": "reference", "metric": "frontend_stereo_frames_per_s", "value": v, "unit": "frames/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": workload_config(args, sample),
+            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
+                             "sample": f"{sample} stereo pairs of the workload per step (CPU generator, same seed)"},
+            "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "mean_stereo_points_per_frame": float(np.mean(counts))}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, pairs):
+    return {"workload": "frame-sharded stereo frontend: KITTI-shaped synthetic stereo pairs (BASELINE config 4)",
+            "pairs_per_gpu": pairs, "image": f"{COLS}x{ROWS} u8", "target_features_per_frame": TARGET,
+            "detector": f"FAST-9/16 thr {THRESHOLD} + NMS, 3x3 bins, ORB-256",
+            "matcher": "epipolar max_dist 100 ratio 0.5 disparity<=100 thickness 0 (kitti.conf)",
+            "stages": "detect+select+describe (L,R) -> epipolar stereo match -> stereo measurement cloud",
+            "l2": "inputs larger than L2 (no flush needed)", "parallelism": f"frames sharded over {args.gpus} GPU(s)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--pairs", type=int, default=10000, help="stereo pairs per GPU per step")
+    ap.add_argument("--work-images", type=int, default=512, help="pipeline chunk (images)")
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--cpu-pairs", type=int, default=0, help="cpu_baseline sample (0 = auto, ~10-30 s)")
+    ap.add_argument("--ref-pairs", type=int, default=256, help="--impl reference: pairs per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-hamming", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from srrg2_proslam_b200 import capi, synth
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    P = args.pairs
+    # ---- synthetic workload, generated on the device (plumbing), one seed per chunk and rank ----
+    images = torch.empty((P, 2, ROWS, COLS), dtype=torch.uint8, device=dev)
+    for i, base in enumerate(range(0, P, GEN_CHUNK)):
+        n = min(GEN_CHUNK, P - base)
+        images[base:base + n] = synth.stereo_pairs(n, ROWS, COLS, seed=args.seed + 100003 * rank + i, device=dev)
+    torch.cuda.synchronize()
+    img_bytes = ROWS * COLS
+
+    ctx = capi.Context(device=local, max_images=2 * P, max_rows=ROWS, max_cols=COLS, max_features=4096,
+                       max_raw_per_bin=8192, max_bins=9, work_images=args.work_images)
+    ecfg = capi.extract_cfg(THRESHOLD, 1, TARGET)
+    mcfg = capi.match_cfg(**MATCH)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+
+    def step_dev():
+        ctx.stereo_frontend_batch_dev(images.data_ptr(), P, ROWS, COLS, COLS, img_bytes, ecfg, mcfg)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ctx.synchronize()
+
+    # ---- device-resident leg -------------------------------------------------------------------
+    for _ in range(args.warmup):
+        step_dev()
+    ctx.synchronize()
+    counts = ctx.stereo_counts(P)          # also raises on any capacity overflow
+    clk_lines, stop = [], threading.Event()
+    sampler = threading.Thread(target=clocks_sampler, args=(stop, clk_lines, local), daemon=True)
+    sampler.start()
+    time.sleep(0.3)
+    ctx.profile_enable(True)
+    barrier()
+    launches0 = ctx.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_dev()
+    e1.record(stream)
+    barrier()
+    gpu_launches = ctx.launches - launches0
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    prof = ctx.profile_read()
+    ctx.profile_enable(False)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    value = world * P * args.steps / (ms_total * 1e-3)
+
+    # ---- end-to-end leg: pinned host images in, packed stereo clouds out -------------------------
+    h_images = torch.empty((P, 2, ROWS, COLS), dtype=torch.uint8, pin_memory=True)
+    h_images.copy_(images)
+    torch.cuda.synchronize()
+    total_pts = int(counts.sum())
+    cap_pts = int(total_pts * 1.05) + 1024
+    out = {"offsets": np.zeros(P + 1, np.int64)}
+    pin = {"uvuv": torch.empty((cap_pts, 4), dtype=torch.float32, pin_memory=True),
+           "intensity": torch.empty((cap_pts,), dtype=torch.float32, pin_memory=True),
+           "desc": torch.empty((cap_pts, 32), dtype=torch.uint8, pin_memory=True)}
+    out.update({k: v.numpy() for k, v in pin.items()})
+    want = ("uvuv", "intensity", "desc")
+
+    def step_e2e():
+        ctx.stereo_frontend_batch(h_images.data_ptr(), P, ROWS, COLS, COLS, img_bytes, ecfg, mcfg)
+        return ctx.download_stereo_batch(P, cap_pts, want=want, out=out)
+
+    for _ in range(2):
+        res = step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = step_e2e()
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * P * args.steps / float(e2e_s.item())
+    stop.set()
+    sampler.join(timeout=3)
+    n_pts = int(res["n"])
+    h2d = 2 * P * img_bytes
+    d2h = (P + 1) * 8 + n_pts * (16 + 4 + 32)
+
+    # ---- roofline of the dominant kernel (live event times over the timed region) ----------------
+    peaks = {}
+    pk = ROOT / "MEASURED_PEAKS.json"
+    if pk.exists():
+        peaks = json.loads(pk.read_text())
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    n_img = 2 * P * args.steps
+    mean_feat = float(ctx.feature_counts(2 * P).mean())
+    # algorithmic bytes per image of stage 1: image read once + selected keypoints (x, y,
+    # response, intensity: 16 B) + descriptors (32 B); per kernel: its own compulsory input + output
+    alg = {
+        "fast_blur_kernel": ROWS * COLS + mean_feat * 48,   # the stage-1 figure is billed to its dominant kernel
+        "bin_compact_kernel": ROWS * COLS,
+        "bin_sort_kernel": 9 * 8192 * 4 * 0 + mean_feat * 8,
+        "assemble_features_kernel": mean_feat * (4 + 16),
+        "orb_describe_kernel": mean_feat * (31 * 31 + 32),
+        "epipolar_kernel": 2 * mean_feat * (32 + 8),
+    }
+    kernels = {}
+    tot_kernel_ms = sum(v[0] for v in prof.values()) or 1.0
+    for name, (kms, cnt) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
+        units = n_img if name != "epipolar_kernel" else n_img / 2
+        a = alg.get(name)
+        kernels[name] = {"ms_total": kms, "launches": cnt, "share": kms / tot_kernel_ms,
+                         "us_per_image": 1e3 * kms / n_img,
+                         "alg_gbs": (a * units / (kms * 1e-3) / 1e9) if a and kms > 0 else None}
+    top = next(iter(kernels)) if kernels else None
+    roofline = None
+    if top:
+        k = kernels[top]
+        ach = k["alg_gbs"] or 0.0
+        roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "avg_launch_ms": k["ms_total"] / max(k["launches"], 1),
+                    "alg_bytes_per_image": alg.get(top), "share_of_kernel_time": k["share"]}
+        tr = ROOT / "profiles" / "traffic.json"
+        if tr.exists():
+            t = json.loads(tr.read_text()).get(top)
+            if t:
+                roofline["traffic"] = t.get("dram_bytes_per_launch")
+                roofline["traffic_source"] = t.get("source")
+
+    line = {"metric": "frontend_stereo_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": workload_config(args, P),
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "pslam_stereo_frontend_batch + pslam_download_stereo_batch (host pointers)"},
+            "gpu_launches": int(gpu_launches), "roofline": roofline, "kernels": kernels,
+            "clocks": summarise_clocks(clk_lines),
+            "mean_features_per_image": mean_feat, "mean_stereo_points_per_frame": float(counts.mean())}
+
+    # ---- secondary metric: Hamming GPair/s (BASELINE config 5, 64k x 64k) -------------------------
+    if not args.no_hamming:
+        nq = nt = 65536
+        q, t = synth.hamming_sets(nq, nt, seed=args.seed)
+        dq, dt_ = torch.from_numpy(q).to(dev), torch.from_numpy(t).to(dev)
+        ob = torch.empty((3, nq), dtype=torch.int32, device=dev)
+        def sweep():
+            ctx.bf_best2_dev(nq, dq.data_ptr(), nt, dt_.data_ptr(), ob[0].data_ptr(), ob[1].data_ptr(), ob[2].data_ptr())
+        for _ in range(3):
+            sweep()
+        barrier()
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0.record(stream)
+        reps = 10
+        for _ in range(reps):
+            sweep()
+        h1.record(stream)
+        barrier()
+        hms = torch.tensor([h0.elapsed_time(h1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(hms, op=dist.ReduceOp.MAX)
+        gpairs = world * nq * nt * reps / (float(hms.item()) * 1e-3) / 1e9
+        sm_mhz = line["clocks"]["sm_mhz"] or 1965.0
+        line["hamming"] = {"metric": "hamming_best2_gpairs_per_s", "value": gpairs, "unit": "GPair/s",
+                           "config": {"workload": "64k x 64k 256-bit descriptors per GPU (BASELINE config 5), "
+                                                  "query rows sharded by rank, train set replicated"},
+                           "ms_per_sweep": float(hms.item()) / reps}
+
+    # ---- CPU baseline (rank 0, N = 1 only): the oracle on a bounded sample -----------------------
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        O = oracle_lib()
+        cores = os.cpu_count() or 1
+        ocfg = O.extract_cfg(THRESHOLD, 1, TARGET)
+        probe = images[:cores].cpu().numpy()
+        t0 = time.perf_counter()
+        O.stereo_frontend_batch(probe, ocfg, threads=cores, **MATCH)
+        per_round = time.perf_counter() - t0
+        sample = args.cpu_pairs or int(min(P, max(cores, cores * round(15.0 / max(per_round, 1e-3)))))
+        simgs = images[:sample].cpu().numpy()
+        t0 = time.perf_counter()
+        ccounts, cchk = O.stereo_frontend_batch(simgs, ocfg, threads=cores, **MATCH)
+        cdt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": sample / cdt, "unit": "frames/s", "cores": cores, "kind": "port",
+                                "sample": f"first {sample} stereo pairs of the same batch, {cdt:.1f} s, all host threads",
+                                "parity_counts_equal": bool(np.array_equal(ccounts, counts[:sample]))}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -39,12 +39,14 @@ typedef struct pslam_ctx pslam_ctx;
 
 /* Context limits: size the device-resident buffers once (no allocation on the hot path). */
 typedef struct {
-  int max_images;        /* images per batch (a stereo pair is 2 images) */
+  int max_images;        /* images per batch (a stereo pair is 2 images): capacity of the result stores */
   int max_rows;          /* image height limit */
   int max_cols;          /* image width limit */
   int max_features;      /* selected features per image, <= 8192 */
   int max_raw_per_bin;   /* FAST corners (after NMS) per detection region before selection */
   int max_bins;          /* detection regions per image (nh * nv) */
+  int work_images;       /* images processed per pipeline chunk (intermediate maps are sized by this,
+                            the feature / stereo stores by max_images); 0 = min(max_images, 512) */
 } pslam_limits;
 
 /* PARAMs of IntensityFeatureExtractorBinned_ (.../sensor_processing/feature_extractors/
@@ -78,6 +80,17 @@ long long pslam_launch_count(const pslam_ctx* ctx);
 /* the CUDA stream all of this context's kernels run on (cudaStream_t as void*) */
 void* pslam_stream(const pslam_ctx* ctx);
 int pslam_synchronize(pslam_ctx* ctx);
+
+/* Per-kernel device timing for bench.py's roofline line (the reference's counterpart is srrg2_core's
+ * Profiler / PROFILE_TIME scopes, e.g. .../feature_extractors/intensity_feature_extractor_binned.cpp:119,140,165).
+ * While enabled, one CUDA event is recorded after every kernel launch; pslam_profile_mark() drops a
+ * marker (call it after the host has queued copies, so that they are not billed to a kernel);
+ * pslam_profile_read() synchronises and returns, per kernel name, the summed device time and launch
+ * count since the last read.  names: capacity x name_len chars.  Returns the number of distinct kernels. */
+int pslam_profile_enable(pslam_ctx* ctx, int enable);
+int pslam_profile_mark(pslam_ctx* ctx);
+int pslam_profile_read(pslam_ctx* ctx, int capacity, char* names, int name_len, double* total_ms,
+                       long long* launches);
 
 /* ---- stage 1: detect + select + describe ---------------------------------------
  * Replaces IntensityFeatureExtractorBinned_::compute(cv::Mat)
@@ -142,6 +155,14 @@ int pslam_download_stereo_counts(pslam_ctx* ctx, int n_pairs, int* counts);
 /* per pair: 4 floats (uL,vL,uR,vR), left feature index, right feature index, distance */
 int pslam_download_stereo_points(pslam_ctx* ctx, int pair, int capacity, float* uvuv, int* left_idx,
                                  int* right_idx, float* distance);
+
+/* whole batch at once, packed: offsets[n_pairs + 1] (CSR), then per stereo point (uL,vL,uR,vR), the LEFT
+ * feature's intensity and 32-byte descriptor (the PointIntensityDescriptor4f cloud the adaptor emits,
+ * raw_data_preprocessor_stereo_projective.cpp:112-118), left / right feature index and Hamming distance.
+ * Any output pointer except offsets may be NULL.  Returns the total number of points. */
+int pslam_download_stereo_batch(pslam_ctx* ctx, int n_pairs, long long capacity_points, long long* offsets,
+                                float* uvuv, float* intensity, uint8_t* desc, int* left_idx, int* right_idx,
+                                float* distance);
 
 /* ---- stage 2b: exhaustive Hamming matching --------------------------------------
  * Replaces CorrespondenceFinderDescriptorBasedBruteforce::compute

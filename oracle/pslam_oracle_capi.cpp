@@ -287,6 +287,57 @@ int orc_stereo_adaptor(const uint8_t* left, const uint8_t* right, int rows, int 
   return write_cloud(meas, cap, 4, uvuv, intensity, desc);
 }
 
+// The frame-independent part of the frontend over a batch of stereo pairs (images 2p, 2p+1 of pair p at
+// images + i * image_pitch), sharded over `threads` std::threads by pair -- the CPU baseline of bench.py
+// (frame-level sharding over the host cores).  Per pair it is exactly
+// orc_stereo_adaptor with the epipolar matcher.  counts[p] = stereo points of pair p; checksum[p] =
+// FNV-1a over the pair's output floats + descriptors (lets bench.py / tests compare whole batches cheaply).
+int orc_stereo_frontend_batch(const uint8_t* images, int n_pairs, int rows, int cols, int stride,
+                              long long image_pitch, const float* cfg5, const float* mcfg4, int threads,
+                              int* counts, unsigned long long* checksum) {
+  const ExtractConfig ec = make_extract_cfg(cfg5);
+  EpipolarConfig c;
+  c.maximum_descriptor_distance = mcfg4[0];
+  c.maximum_distance_ratio_to_second_best = mcfg4[1];
+  c.maximum_disparity_pixels = (unsigned) mcfg4[2];
+  c.epipolar_line_thickness_pixels = (unsigned) mcfg4[3];
+  std::atomic<int> next(0);
+  auto work = [&]() {
+    for (;;) {
+      const int p = next.fetch_add(1);
+      if (p >= n_pairs) break;
+      Cloud L, R, meas;
+      extract_binned(images + (size_t) (2 * p) * image_pitch, rows, cols, stride, ec, nullptr, 0, L);
+      extract_binned(images + (size_t) (2 * p + 1) * image_pitch, rows, cols, stride, ec, nullptr, 0, R);
+      CorrespondenceVector m;
+      match_epipolar(L, R, c, m);
+      assemble_stereo_points(L, R, m, meas);
+      if (counts) counts[p] = (int) meas.size();
+      if (checksum) {
+        unsigned long long h = 1469598103934665603ULL;
+        auto mix = [&h](const void* d, size_t n) {
+          const uint8_t* b = (const uint8_t*) d;
+          for (size_t i = 0; i < n; ++i) h = (h ^ b[i]) * 1099511628211ULL;
+        };
+        for (const auto& q : meas) {
+          const float v[5] = {q.x, q.y, q.z, q.w, q.intensity};
+          mix(v, sizeof(v));
+          mix(q.desc.b, 32);
+        }
+        checksum[p] = h;
+      }
+    }
+  };
+  if (threads <= 1) {
+    work();
+  } else {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t) pool.emplace_back(work);
+    for (auto& t : pool) t.join();
+  }
+  return 0;
+}
+
 // RawDataPreprocessorMonocularDepth::compute; depth image u16 (depth_is_float=0) or f32.
 int orc_mono_depth_adaptor(const uint8_t* img, int rows, int cols, int stride, const void* depth,
                            int depth_is_float, int depth_stride, float depth_scale,

@@ -23,7 +23,8 @@ class PslamError(RuntimeError):
 
 class Limits(C.Structure):
     _fields_ = [("max_images", C.c_int), ("max_rows", C.c_int), ("max_cols", C.c_int),
-                ("max_features", C.c_int), ("max_raw_per_bin", C.c_int), ("max_bins", C.c_int)]
+                ("max_features", C.c_int), ("max_raw_per_bin", C.c_int), ("max_bins", C.c_int),
+                ("work_images", C.c_int)]
 
 
 class ExtractCfg(C.Structure):
@@ -96,8 +97,9 @@ def match_cfg(max_dist=50.0, ratio=0.9, max_disp=100, thickness=0):
 
 class Context:
     def __init__(self, device=0, max_images=2, max_rows=1024, max_cols=2048, max_features=4096,
-                 max_raw_per_bin=32768, max_bins=9):
-        self.limits = Limits(max_images, max_rows, max_cols, max_features, max_raw_per_bin, max_bins)
+                 max_raw_per_bin=32768, max_bins=9, work_images=0):
+        self.limits = Limits(max_images, max_rows, max_cols, max_features, max_raw_per_bin, max_bins,
+                             work_images)
         self._h = C.c_void_p()
         rc = lib().pslam_create(int(device), C.byref(self.limits), C.byref(self._h))
         if rc != 0:
@@ -130,6 +132,21 @@ class Context:
 
     def synchronize(self):
         self._chk(lib().pslam_synchronize(self._h))
+
+    def profile_enable(self, on=True):
+        self._chk(lib().pslam_profile_enable(self._h, int(bool(on))))
+
+    def profile_mark(self):
+        self._chk(lib().pslam_profile_mark(self._h))
+
+    def profile_read(self):
+        """{kernel name: (total device ms, launches)} since the last read"""
+        cap, ln = 48, 64
+        names = C.create_string_buffer(cap * ln)
+        ms = (C.c_double * cap)()
+        cnt = (C.c_longlong * cap)()
+        n = self._chk(lib().pslam_profile_read(self._h, cap, names, ln, ms, cnt))
+        return {names.raw[i * ln:(i + 1) * ln].split(b"\0", 1)[0].decode(): (ms[i], cnt[i]) for i in range(n)}
 
     # ---- stage 1 ------------------------------------------------------------------------------
     def fast_detect(self, img, thr, nms=True, cap=200000):
@@ -226,6 +243,25 @@ class Context:
         d = np.zeros(cap, np.float32)
         n = self._chk(lib().pslam_download_stereo_points(self._h, int(pair), cap, _p(uvuv), _p(li), _p(ri), _p(d)))
         return dict(uvuv=uvuv[:n].copy(), left_idx=li[:n].copy(), right_idx=ri[:n].copy(), distance=d[:n].copy())
+
+    def download_stereo_batch(self, n_pairs, capacity_points, want=("uvuv", "intensity", "desc", "left_idx",
+                                                                   "right_idx", "distance"), out=None):
+        """packed (CSR) stereo result of the last batch; `out` may hold preallocated (pinned) numpy arrays"""
+        out = dict(out or {})
+        cap = int(capacity_points)
+        shapes = dict(uvuv=((cap, 4), np.float32), intensity=((cap,), np.float32), desc=((cap, 32), np.uint8),
+                      left_idx=((cap,), np.int32), right_idx=((cap,), np.int32), distance=((cap,), np.float32))
+        if "offsets" not in out:
+            out["offsets"] = np.zeros(n_pairs + 1, np.int64)
+        for k in want:
+            if k not in out:
+                out[k] = np.empty(*shapes[k])
+        g = lambda k: _p(out[k]) if k in want else None
+        n = self._chk(lib().pslam_download_stereo_batch(self._h, int(n_pairs), C.c_longlong(cap), _p(out["offsets"]),
+                                                        g("uvuv"), g("intensity"), g("desc"), g("left_idx"),
+                                                        g("right_idx"), g("distance")))
+        out["n"] = n
+        return out
 
     # ---- stage 2b -----------------------------------------------------------------------------
     def bf_best2(self, desc_f, desc_m):

@@ -327,15 +327,16 @@ __global__ void __launch_bounds__(K3_THREADS)
 assemble_features_kernel(const uint8_t* __restrict__ images, long long image_pitch, int stride,
                          int rows, int cols, int nbins, int max_bins, int max_raw_per_bin,
                          const uint32_t* __restrict__ raw, const int* __restrict__ sel_count,
-                         int border, int max_features, float2* __restrict__ xy,
+                         int border, int max_features, int slot_base, float2* __restrict__ xy,
                          float* __restrict__ resp, float* __restrict__ inten,
                          int* __restrict__ count, int* __restrict__ flags) {
   __shared__ int s_warp[33];
   const int tid = threadIdx.x, image = blockIdx.x;
   const uint8_t* img = images + (size_t) image * image_pitch;
-  float2* o_xy = xy + (size_t) image * max_features;
-  float* o_resp = resp + (size_t) image * max_features;
-  float* o_int = inten + (size_t) image * max_features;
+  const size_t slot = (size_t) slot_base + image;
+  float2* o_xy = xy + slot * max_features;
+  float* o_resp = resp + slot * max_features;
+  float* o_int = inten + slot * max_features;
   int running = 0;
   for (int b = 0; b < nbins; ++b) {
     const uint32_t* seg = raw + ((size_t) image * max_bins + b) * max_raw_per_bin;
@@ -369,7 +370,7 @@ assemble_features_kernel(const uint8_t* __restrict__ images, long long image_pit
       atomicOr(flags, PSLAM_FLAG_FEATURE_OVERFLOW);
       running = max_features;
     }
-    count[image] = running;
+    count[slot] = running;
   }
 }
 
@@ -385,7 +386,7 @@ __constant__ signed char c_pattern[256 * 4];
 __global__ void __launch_bounds__(K4_WARPS * 32)
 orb_describe_kernel(const uint8_t* __restrict__ blur, int map_pitch, long long map_slot,
                     const float2* __restrict__ xy, const int* __restrict__ count, int max_features,
-                    int n_images, uint32_t* __restrict__ desc) {
+                    int slot_base, uint32_t* __restrict__ desc) {
   __shared__ uint8_t s_patch[K4_WARPS][PATCH * PATCH_PITCH + 3];
   __shared__ uint16_t s_off[16][32];  // [2*k + {a,b}][lane] byte offsets into the patch
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -401,11 +402,12 @@ orb_describe_kernel(const uint8_t* __restrict__ blur, int map_pitch, long long m
   for (int j = 0; j < 16; ++j) off[j] = s_off[j][lane];
 
   const int image = blockIdx.y;
-  const int n = count[image];
+  const size_t slot = (size_t) slot_base + image;
+  const int n = count[slot];
   const uint8_t* b = blur + (size_t) image * map_slot;
   uint8_t* patch = s_patch[wid];
   for (int i = blockIdx.x * K4_WARPS + wid; i < n; i += gridDim.x * K4_WARPS) {
-    const float2 p = xy[(size_t) image * max_features + i];
+    const float2 p = xy[slot * max_features + i];
     const int x = (int) p.x, y = (int) p.y;
     const uint8_t* src = b + (size_t) (y - 15) * map_pitch + (x - 15);
     __syncwarp();
@@ -425,7 +427,7 @@ orb_describe_kernel(const uint8_t* __restrict__ blur, int map_pitch, long long m
     const uint32_t b2 = __shfl_down_sync(0xffffffffu, byte, 2);
     const uint32_t b3 = __shfl_down_sync(0xffffffffu, byte, 3);
     if ((lane & 3) == 0) {
-      desc[((size_t) image * max_features + i) * 8 + (lane >> 2)] = byte | (b1 << 8) | (b2 << 16) | (b3 << 24);
+      desc[(slot * max_features + i) * 8 + (lane >> 2)] = byte | (b1 << 8) | (b2 << 16) | (b3 << 24);
     }
   }
 }
@@ -471,23 +473,23 @@ int pslam_k_bin_select(pslam_ctx* ctx, int n_images, int rows, int cols, int nh,
 }
 
 int pslam_k_assemble(pslam_ctx* ctx, const uint8_t* d_images, long long image_pitch, int stride,
-                     int n_images, int rows, int cols, int nbins, int border) {
+                     int n_images, int rows, int cols, int nbins, int border, int slot_base) {
   assemble_features_kernel<<<n_images, K3_THREADS, 0, ctx->stream>>>(
     d_images, image_pitch, stride, rows, cols, nbins, ctx->lim.max_bins, ctx->lim.max_raw_per_bin,
-    ctx->d_raw, ctx->d_sel_count, border, ctx->lim.max_features, ctx->d_xy, ctx->d_resp,
+    ctx->d_raw, ctx->d_sel_count, border, ctx->lim.max_features, slot_base, ctx->d_xy, ctx->d_resp,
     ctx->d_inten, ctx->d_count, ctx->d_flags);
   PSLAM_LAUNCH_CHECK(ctx, "assemble_features_kernel");
   return PSLAM_OK;
 }
 
-int pslam_k_describe(pslam_ctx* ctx, int n_images) {
+int pslam_k_describe(pslam_ctx* ctx, int n_images, int slot_base) {
   // enough warps for max_features per image, capped: grid-stride over the image's features
   int bx = (ctx->lim.max_features + K4_WARPS - 1) / K4_WARPS;
   if (bx > 64) bx = 64;
   dim3 grid(bx, n_images);
   orb_describe_kernel<<<grid, K4_WARPS * 32, 0, ctx->stream>>>(
     ctx->d_blur, ctx->map_pitch, (long long) ctx->map_slot, ctx->d_xy, ctx->d_count,
-    ctx->lim.max_features, n_images, ctx->d_desc);
+    ctx->lim.max_features, slot_base, ctx->d_desc);
   PSLAM_LAUNCH_CHECK(ctx, "orb_describe_kernel");
   return PSLAM_OK;
 }

@@ -250,7 +250,78 @@ epipolar_kernel(const float2* __restrict__ xy, const uint32_t* __restrict__ desc
   if (tid == 0) st_count[pair] = n_st;
 }
 
+// ---- batch result packing: per-pair padded stores -> CSR (offsets + SoA), the measurement cloud the
+// adaptor hands to the tracker: (uL,vL,uR,vR) + the LEFT feature's intensity and descriptor
+// (raw_data_preprocessor_stereo_projective.cpp:112-118)
+__global__ void __launch_bounds__(1024)
+stereo_offsets_kernel(const int* __restrict__ st_count, int n_pairs, long long* __restrict__ offsets) {
+  __shared__ int s_warp[33];
+  long long running = 0;
+  for (int base = 0; base < n_pairs; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i < n_pairs ? st_count[i] : 0;
+    int total;
+    const int off = block_exclusive_scan<1024>(v, s_warp, &total);
+    if (i < n_pairs) offsets[i] = running + off;
+    running += total;
+  }
+  if (threadIdx.x == 0) offsets[n_pairs] = running;
+}
+
+__global__ void __launch_bounds__(256)
+stereo_pack_kernel(const long long* __restrict__ offsets, const int* __restrict__ st_count, int M,
+                   const float4* __restrict__ st_uvuv, const int* __restrict__ st_left,
+                   const int* __restrict__ st_right, const float* __restrict__ st_dist,
+                   const float* __restrict__ inten, const uint32_t* __restrict__ desc,
+                   float4* __restrict__ o_uvuv, float* __restrict__ o_int, uint4* __restrict__ o_desc,
+                   int* __restrict__ o_left, int* __restrict__ o_right, float* __restrict__ o_dist) {
+  const int pair = blockIdx.x;
+  const int n = st_count[pair];
+  const long long o = offsets[pair];
+  const size_t src = (size_t) pair * M;
+  const size_t left_slot = (size_t) (2 * pair) * M;
+  const uint4* d4 = reinterpret_cast<const uint4*>(desc);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int l = st_left[src + i];
+    o_uvuv[o + i] = st_uvuv[src + i];
+    o_left[o + i] = l;
+    o_right[o + i] = st_right[src + i];
+    o_dist[o + i] = st_dist[src + i];
+    o_int[o + i] = inten[left_slot + l];
+    o_desc[2 * (o + i)] = d4[2 * (left_slot + l)];
+    o_desc[2 * (o + i) + 1] = d4[2 * (left_slot + l) + 1];
+  }
+}
+
 }  // namespace
+
+int pslam_k_pack_stereo(pslam_ctx* ctx, int n_pairs, pslam_packed_stereo* out) {
+  const size_t M = ctx->lim.max_features;
+  const size_t cap = (size_t) n_pairs * M;  // worst case
+  uint8_t* p = ctx->d_scratch;
+  auto carve = [&](size_t bytes) {
+    uint8_t* r = p;
+    p += (bytes + 255) & ~(size_t) 255;
+    return r;
+  };
+  out->d_offsets = (long long*) carve(sizeof(long long) * ((size_t) n_pairs + 1));
+  out->d_uvuv = (float4*) carve(sizeof(float4) * cap);
+  out->d_desc = (uint32_t*) carve(32 * cap);
+  out->d_intensity = (float*) carve(sizeof(float) * cap);
+  out->d_left = (int*) carve(sizeof(int) * cap);
+  out->d_right = (int*) carve(sizeof(int) * cap);
+  out->d_dist = (float*) carve(sizeof(float) * cap);
+  if ((size_t) (p - ctx->d_scratch) > ctx->scratch_bytes)
+    return pslam_set_error(ctx, PSLAM_E_CAPACITY, "pack_stereo: scratch too small for this batch", cudaSuccess);
+  stereo_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_st_count, n_pairs, out->d_offsets);
+  PSLAM_LAUNCH_CHECK(ctx, "stereo_offsets_kernel");
+  stereo_pack_kernel<<<n_pairs, 256, 0, ctx->stream>>>(
+    out->d_offsets, ctx->d_st_count, (int) M, ctx->d_st_uvuv, ctx->d_st_left, ctx->d_st_right,
+    ctx->d_st_dist, ctx->d_inten, ctx->d_desc, out->d_uvuv, out->d_intensity,
+    reinterpret_cast<uint4*>(out->d_desc), out->d_left, out->d_right, out->d_dist);
+  PSLAM_LAUNCH_CHECK(ctx, "stereo_pack_kernel");
+  return PSLAM_OK;
+}
 
 static size_t ep_smem_bytes(int M) {
   int P = 1;

@@ -2,12 +2,33 @@
 // sequence the sm_100a kernels on the context's stream.  No CPU fallback exists: every compute entry
 // point launches kernels; without a usable CUDA device pslam_create fails with PSLAM_E_CUDA.
 #include <math.h>
+#include <stdlib.h>
 
 #include <new>
 #include <vector>
 
 #include "pslam_internal.cuh"
 #include "pslam_kernels.cuh"
+
+void pslam_prof_mark(pslam_ctx* ctx, const char* name) {
+  if (ctx->prof_n == ctx->prof_cap) {
+    const int cap = ctx->prof_cap ? 2 * ctx->prof_cap : 1024;
+    cudaEvent_t* ev = (cudaEvent_t*) realloc(ctx->prof_ev, sizeof(cudaEvent_t) * cap);
+    const char** nm = (const char**) realloc(ctx->prof_name, sizeof(char*) * cap);
+    if (!ev || !nm) {
+      if (ev) ctx->prof_ev = ev;
+      if (nm) ctx->prof_name = nm;
+      return;
+    }
+    ctx->prof_ev = ev;
+    ctx->prof_name = nm;
+    for (int i = ctx->prof_cap; i < cap; ++i) cudaEventCreate(&ctx->prof_ev[i]);
+    ctx->prof_cap = cap;
+  }
+  cudaEventRecord(ctx->prof_ev[ctx->prof_n], ctx->stream);
+  ctx->prof_name[ctx->prof_n] = name;
+  ctx->prof_n++;
+}
 
 namespace {
 
@@ -48,33 +69,99 @@ int validate_extract(pslam_ctx* ctx, int n_images, int rows, int cols, const psl
   return PSLAM_OK;
 }
 
-// detect -> select -> assemble -> describe for images already on the device
-int run_extract(pslam_ctx* ctx, const uint8_t* d_images, long long image_pitch, int n_images, int rows,
-                int cols, int stride, const pslam_extract_cfg* cfg, const uint8_t* d_mask) {
+// quota + region grid of IntensityFeatureExtractorBinned_::init (binned.cpp:72-75), mask => no binning (:167)
+struct SelectPlan {
+  int nh, nv;
+  unsigned long long quota;
+};
+SelectPlan make_plan(const pslam_extract_cfg* cfg, bool masked) {
+  SelectPlan p;
+  p.nh = cfg->number_of_detectors_horizontal;
+  p.nv = cfg->number_of_detectors_vertical;
+  const float qf = static_cast<float>(cfg->target_number_of_keypoints) / static_cast<float>((size_t) (p.nh * p.nv));
+  p.quota = qf <= 0.0f ? 0ULL : (unsigned long long) qf;
+  if (masked) {
+    p.nh = p.nv = 1;
+    p.quota = ~0ULL;
+  }
+  return p;
+}
+
+// detect -> select -> assemble -> describe for ONE chunk (<= work_images images) already on the device;
+// features land in store slots slot_base .. slot_base + n_images - 1
+int run_extract_chunk(pslam_ctx* ctx, const uint8_t* d_images, long long image_pitch, int n_images, int rows,
+                      int cols, int stride, const pslam_extract_cfg* cfg, const uint8_t* d_mask, int slot_base) {
   int rc;
-  ctx->rows = rows;
-  ctx->cols = cols;
-  ctx->n_images = n_images;
-  if (n_images == 0) return PSLAM_OK;
   if ((rc = pslam_k_fast_blur(ctx, d_images, image_pitch, n_images, rows, cols, stride,
                               (int) cfg->detector_threshold, cfg->enable_non_maximum_suppression))) return rc;
-  int nh = cfg->number_of_detectors_horizontal, nv = cfg->number_of_detectors_vertical;
-  // quota = size_t(float(target) / regions)   (binned.cpp:72-75)
-  const float qf = static_cast<float>(cfg->target_number_of_keypoints) / static_cast<float>((size_t) (nh * nv));
-  unsigned long long quota = qf <= 0.0f ? 0ULL : (unsigned long long) qf;
-  if (d_mask) {  // "only perform binning if mask is not set" (binned.cpp:167)
-    nh = nv = 1;
-    quota = ~0ULL;
-  }
-  if ((rc = pslam_k_bin_select(ctx, n_images, rows, cols, nh, nv, quota, d_mask))) return rc;
-  if ((rc = pslam_k_assemble(ctx, d_images, image_pitch, stride, n_images, rows, cols, nh * nv, 31))) return rc;
-  if ((rc = pslam_k_describe(ctx, n_images))) return rc;
+  const SelectPlan plan = make_plan(cfg, d_mask != nullptr);
+  if ((rc = pslam_k_bin_select(ctx, n_images, rows, cols, plan.nh, plan.nv, plan.quota, d_mask))) return rc;
+  if ((rc = pslam_k_assemble(ctx, d_images, image_pitch, stride, n_images, rows, cols, plan.nh * plan.nv, 31, slot_base))) return rc;
+  if ((rc = pslam_k_describe(ctx, n_images, slot_base))) return rc;
   return PSLAM_OK;
 }
 
+// the whole batch, device-resident images, in chunks of work_images
+int run_extract(pslam_ctx* ctx, const uint8_t* d_images, long long image_pitch, int n_images, int rows,
+                int cols, int stride, const pslam_extract_cfg* cfg, const uint8_t* d_mask) {
+  ctx->rows = rows;
+  ctx->cols = cols;
+  ctx->n_images = n_images;
+  for (int base = 0; base < n_images; base += ctx->work_images) {
+    const int n = n_images - base < ctx->work_images ? n_images - base : ctx->work_images;
+    int rc = run_extract_chunk(ctx, d_images + (size_t) base * image_pitch, image_pitch, n, rows, cols, stride, cfg, d_mask, base);
+    if (rc) return rc;
+  }
+  return PSLAM_OK;
+}
+
+// the whole batch, HOST images: uploads on copy_stream into the double-buffered staging area overlap the
+// kernels of the previous chunk on the compute stream
+int run_extract_host(pslam_ctx* ctx, const uint8_t* h_images, long long image_pitch, int n_images, int rows,
+                     int cols, int stride, const pslam_extract_cfg* cfg) {
+  ctx->rows = rows;
+  ctx->cols = cols;
+  ctx->n_images = n_images;
+  const size_t half = (size_t) ctx->work_images * ctx->img_slot;
+  // the staging buffers may still be read by kernels of an earlier call: order the uploads after them
+  PSLAM_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_free[0], ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[0], 0));
+  int chunk = 0;
+  for (int base = 0; base < n_images; base += ctx->work_images, ++chunk) {
+    const int n = n_images - base < ctx->work_images ? n_images - base : ctx->work_images;
+    const int buf = chunk & 1;
+    uint8_t* stage = ctx->d_images + buf * half;
+    if (chunk >= 2) PSLAM_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[buf], 0));
+    const uint8_t* src = h_images + (size_t) base * image_pitch;
+    if (stride == cols && image_pitch == (long long) rows * cols) {
+      // densely packed host images: one 2-D copy (row = one image) re-pitches the whole chunk... rows differ in
+      // pitch (cols vs img_pitch), so copy image rows: width cols, height rows * n with source pitch cols only
+      // works when the destination slot is rows * img_pitch -- it is when max_rows == rows
+      if ((size_t) rows * ctx->img_pitch == ctx->img_slot) {
+        PSLAM_CUDA_TRY(ctx, cudaMemcpy2DAsync(stage, ctx->img_pitch, src, cols, cols, (size_t) rows * n, cudaMemcpyHostToDevice, ctx->copy_stream));
+      } else {
+        for (int i = 0; i < n; ++i)
+          PSLAM_CUDA_TRY(ctx, cudaMemcpy2DAsync(stage + (size_t) i * ctx->img_slot, ctx->img_pitch, src + (size_t) i * image_pitch, stride, cols, rows, cudaMemcpyHostToDevice, ctx->copy_stream));
+      }
+    } else {
+      for (int i = 0; i < n; ++i)
+        PSLAM_CUDA_TRY(ctx, cudaMemcpy2DAsync(stage + (size_t) i * ctx->img_slot, ctx->img_pitch, src + (size_t) i * image_pitch, stride, cols, rows, cudaMemcpyHostToDevice, ctx->copy_stream));
+    }
+    PSLAM_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_ready[buf], ctx->copy_stream));
+    PSLAM_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_ready[buf], 0));
+    if (ctx->prof_enabled) pslam_prof_mark(ctx, nullptr);  // the wait for the upload is not kernel time
+    int rc = run_extract_chunk(ctx, stage, (long long) ctx->img_slot, n, rows, cols, ctx->img_pitch, cfg, nullptr, base);
+    if (rc) return rc;
+    PSLAM_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_free[buf], ctx->stream));
+  }
+  return PSLAM_OK;
+}
+
+// single-image / single-pair entry points: upload into staging buffer 0 on the compute stream
 int upload_images(pslam_ctx* ctx, const uint8_t* h, int n_images, int rows, int cols, int stride,
                   long long image_pitch_bytes) {
-  // one strided copy per batch when the host layout allows it, else one per image
+  if (n_images > ctx->work_images)
+    return pslam_set_error(ctx, PSLAM_E_CAPACITY, "more images than pslam_limits.work_images", cudaSuccess);
   for (int i = 0; i < n_images; ++i) {
     PSLAM_CUDA_TRY(ctx, cudaMemcpy2DAsync(ctx->d_images + (size_t) i * ctx->img_slot, ctx->img_pitch,
                                           h + (size_t) i * image_pitch_bytes, stride, cols, rows,
@@ -108,18 +195,27 @@ int pslam_create(int device, const pslam_limits* lim, pslam_ctx** out) {
   *out = ctx;  // returned even on failure so that pslam_last_error is readable; caller destroys
   PSLAM_CUDA_TRY(ctx, cudaSetDevice(device));
   PSLAM_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  PSLAM_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    PSLAM_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_ready[i], cudaEventDisableTiming));
+    PSLAM_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_free[i], cudaEventDisableTiming));
+  }
+  ctx->work_images = lim->work_images > 0 ? lim->work_images : (lim->max_images < 512 ? lim->max_images : 512);
+  if (ctx->work_images > lim->max_images) ctx->work_images = lim->max_images;
+  if (ctx->work_images > 65535) ctx->work_images = 65535;  // gridDim.z / gridDim.y
   ctx->img_pitch = round_up(lim->max_cols, 128);
   ctx->map_pitch = round_up(lim->max_cols, 128);
   ctx->img_slot = (size_t) ctx->img_pitch * lim->max_rows;
   ctx->map_slot = (size_t) ctx->map_pitch * lim->max_rows;
   const size_t NI = lim->max_images, MF = lim->max_features, NP = (lim->max_images + 1) / 2;
-  PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_images, NI * ctx->img_slot));
-  PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_nms, NI * ctx->map_slot));
-  PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_blur, NI * ctx->map_slot));
+  const size_t NW = ctx->work_images;
+  PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_images, 2 * NW * ctx->img_slot));
+  PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_nms, NW * ctx->map_slot));
+  PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_blur, NW * ctx->map_slot));
   PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_mask, ctx->map_slot));
-  PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_raw, NI * lim->max_bins * (size_t) lim->max_raw_per_bin));
-  PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_raw_count, NI * lim->max_bins));
-  PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_sel_count, NI * lim->max_bins));
+  PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_raw, NW * lim->max_bins * (size_t) lim->max_raw_per_bin));
+  PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_raw_count, NW * lim->max_bins));
+  PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_sel_count, NW * lim->max_bins));
   PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_xy, NI * MF));
   PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_resp, NI * MF));
   PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_inten, NI * MF));
@@ -137,7 +233,10 @@ int pslam_create(int device, const pslam_limits* lim, pslam_ctx** out) {
   PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_flags, 4));
   PSLAM_CUDA_TRY(ctx, cudaMemset(ctx->d_flags, 0, 4 * sizeof(int)));
   PSLAM_CUDA_TRY(ctx, cudaMemset(ctx->d_count, 0, NI * sizeof(int)));
+  // scratch: matcher / solver temporaries, and the packed (CSR) stereo result of a whole batch
   ctx->scratch_bytes = (size_t) 64 << 20;
+  const size_t pack_bytes = NP * MF * 64 + NP * 8 + (1 << 20);
+  if (NI > 2 && pack_bytes > ctx->scratch_bytes) ctx->scratch_bytes = pack_bytes;
   PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_scratch, ctx->scratch_bytes));
   ctx->pinned_bytes = 1 << 20;
   PSLAM_CUDA_TRY(ctx, cudaMallocHost(&ctx->h_pinned, ctx->pinned_bytes));
@@ -158,7 +257,15 @@ void pslam_destroy(pslam_ctx* ctx) {
   for (void* b : bufs)
     if (b) cudaFree(b);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  for (int i = 0; i < ctx->prof_cap; ++i) cudaEventDestroy(ctx->prof_ev[i]);
+  free(ctx->prof_ev);
+  free(ctx->prof_name);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->ev_ready[i]) cudaEventDestroy(ctx->ev_ready[i]);
+    if (ctx->ev_free[i]) cudaEventDestroy(ctx->ev_free[i]);
+  }
   delete ctx;
 }
 
@@ -169,6 +276,53 @@ int pslam_synchronize(pslam_ctx* ctx) {
   if (!ctx) return PSLAM_E_INVALID;
   PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return PSLAM_OK;
+}
+
+// ---- per-kernel device timing ---------------------------------------------------------------------
+int pslam_profile_enable(pslam_ctx* ctx, int enable) {
+  if (!ctx) return PSLAM_E_INVALID;
+  PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->prof_enabled = enable ? 1 : 0;
+  ctx->prof_n = 0;
+  return PSLAM_OK;
+}
+
+int pslam_profile_mark(pslam_ctx* ctx) {
+  if (!ctx) return PSLAM_E_INVALID;
+  if (ctx->prof_enabled) pslam_prof_mark(ctx, nullptr);
+  return PSLAM_OK;
+}
+
+int pslam_profile_read(pslam_ctx* ctx, int capacity, char* names, int name_len, double* total_ms,
+                       long long* launches) {
+  if (!ctx || capacity <= 0 || !names || name_len <= 1 || !total_ms || !launches) return PSLAM_E_INVALID;
+  PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  int n_names = 0;
+  std::vector<const char*> seen;
+  for (int i = 1; i < ctx->prof_n; ++i) {
+    const char* nm = ctx->prof_name[i];
+    if (!nm) continue;  // interval ending at a marker: host gap / copies, not a kernel
+    float ms = 0.0f;
+    if (cudaEventElapsedTime(&ms, ctx->prof_ev[i - 1], ctx->prof_ev[i]) != cudaSuccess) {
+      cudaGetLastError();
+      continue;
+    }
+    int k = -1;
+    for (int j = 0; j < n_names; ++j)
+      if (seen[j] == nm || strcmp(seen[j], nm) == 0) { k = j; break; }
+    if (k < 0) {
+      if (n_names == capacity) continue;
+      k = n_names++;
+      seen.push_back(nm);
+      snprintf(names + (size_t) k * name_len, name_len, "%s", nm);
+      total_ms[k] = 0.0;
+      launches[k] = 0;
+    }
+    total_ms[k] += ms;
+    launches[k] += 1;
+  }
+  ctx->prof_n = 0;
+  return n_names;
 }
 
 // ---- stage 1 ------------------------------------------------------------------------------------
@@ -319,6 +473,7 @@ int pslam_stereo_frontend_batch_dev(pslam_ctx* ctx, const uint8_t* d_images, int
   int rc = validate_extract(ctx, 2 * n_pairs, rows, cols, ecfg);
   if (rc) return rc;
   PSLAM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (ctx->prof_enabled) pslam_prof_mark(ctx, nullptr);
   if ((rc = run_extract(ctx, d_images, image_pitch_bytes, 2 * n_pairs, rows, cols, stride, ecfg, nullptr))) return rc;
   if (n_pairs > 0 && (rc = pslam_k_epipolar(ctx, n_pairs, mcfg))) return rc;
   return PSLAM_OK;
@@ -331,13 +486,7 @@ int pslam_stereo_frontend_batch(pslam_ctx* ctx, const uint8_t* h_images, int n_p
   int rc = validate_extract(ctx, 2 * n_pairs, rows, cols, ecfg);
   if (rc) return rc;
   PSLAM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  if (stride == cols && image_pitch_bytes == (long long) rows * cols && cols == ctx->img_pitch &&
-      (size_t) rows * cols == ctx->img_slot) {
-    PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_images, h_images, (size_t) 2 * n_pairs * ctx->img_slot, cudaMemcpyHostToDevice, ctx->stream));
-  } else if ((rc = upload_images(ctx, h_images, 2 * n_pairs, rows, cols, stride, image_pitch_bytes))) {
-    return rc;
-  }
-  if ((rc = run_extract(ctx, ctx->d_images, (long long) ctx->img_slot, 2 * n_pairs, rows, cols, ctx->img_pitch, ecfg, nullptr))) return rc;
+  if ((rc = run_extract_host(ctx, h_images, image_pitch_bytes, 2 * n_pairs, rows, cols, stride, ecfg))) return rc;
   if (n_pairs > 0 && (rc = pslam_k_epipolar(ctx, n_pairs, mcfg))) return rc;
   return PSLAM_OK;
 }
@@ -370,6 +519,35 @@ int pslam_download_stereo_points(pslam_ctx* ctx, int pair, int capacity, float* 
     PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   }
   return n;
+}
+
+int pslam_download_stereo_batch(pslam_ctx* ctx, int n_pairs, long long capacity_points, long long* offsets,
+                                float* uvuv, float* intensity, uint8_t* desc, int* left_idx, int* right_idx,
+                                float* distance) {
+  if (!ctx || n_pairs < 0 || 2 * n_pairs > ctx->lim.max_images + 1 || !offsets) return PSLAM_E_INVALID;
+  PSLAM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  int rc = check_flags(ctx);
+  if (rc) return rc;
+  offsets[0] = 0;
+  if (n_pairs == 0) return 0;
+  pslam_packed_stereo pk;
+  if ((rc = pslam_k_pack_stereo(ctx, n_pairs, &pk))) return rc;
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(offsets, pk.d_offsets, sizeof(long long) * ((size_t) n_pairs + 1), cudaMemcpyDeviceToHost, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  const long long total = offsets[n_pairs];
+  if (total > capacity_points)
+    return pslam_set_error(ctx, PSLAM_E_CAPACITY, "download_stereo_batch: capacity_points too small", cudaSuccess);
+  if (total > 0) {
+    const size_t n = (size_t) total;
+    if (uvuv) PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(uvuv, pk.d_uvuv, sizeof(float4) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (intensity) PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(intensity, pk.d_intensity, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (desc) PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(desc, pk.d_desc, 32 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (left_idx) PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(left_idx, pk.d_left, sizeof(int) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (right_idx) PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(right_idx, pk.d_right, sizeof(int) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (distance) PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(distance, pk.d_dist, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return total > 0x7fffffffLL ? 0x7fffffff : (int) total;
 }
 
 int pslam_stereo_adaptor(pslam_ctx* ctx, const uint8_t* left, const uint8_t* right, int rows, int cols,

@@ -11,16 +11,21 @@
 
 // ---- HBM-resident state of one context ------------------------------------------------------
 // Layout (all sized once from pslam_limits; nothing is allocated on the hot path):
-//   images   u8  [max_images][max_rows][img_pitch]          staging for the host-pointer entry points
-//   nms_map  u8  [max_images][max_rows][map_pitch]          0 = no keypoint, else FAST response + 1
-//   blur     u8  [max_images][max_rows][map_pitch]          ORB 7x7 integer Gaussian
-//   raw      u32 [max_images][max_bins][max_raw_per_bin]    (pixel index << 8 | response + 1), row-major per bin
+// Stage 1 runs in chunks of `work_images` images so that the intermediate maps of a chunk stay
+// L2-resident between the kernels that produce and consume them; only the stores are batch-sized.
+//   images   u8  [2][work_images][max_rows][img_pitch]      double-buffered staging (host-pointer entry points)
+//   nms_map  u8  [work_images][max_rows][map_pitch]         0 = no keypoint, else FAST response + 1
+//   blur     u8  [work_images][max_rows][map_pitch]         ORB 7x7 integer Gaussian
+//   raw      u32 [work_images][max_bins][max_raw_per_bin]   (pixel index << 8 | response + 1), row-major per bin
 //   features SoA [max_images][max_features]: xy float2, response f32, intensity f32, desc 8 x u32
 //   stereo   SoA [max_images/2][max_features]: uvuv float4, left/right feature index, distance
 // map_pitch and img_pitch are multiples of 128 so every row starts on a 128 B line.
 struct pslam_ctx {
   int device;
-  cudaStream_t stream;
+  cudaStream_t stream;       // all kernels
+  cudaStream_t copy_stream;  // host->device image uploads of the batched host entry point
+  cudaEvent_t ev_ready[2], ev_free[2];  // double-buffered staging hand-shake
+  int work_images;           // chunk size (images) of the stage-1 pipeline
   pslam_limits lim;
   char err[512];
   long long launches;
@@ -57,7 +62,15 @@ struct pslam_ctx {
   size_t pinned_bytes;
   // geometry of the last batch
   int rows, cols, n_images;
+  // optional per-kernel device timing (pslam_profile_*): one CUDA event after every launch; the interval
+  // between consecutive events on the in-order stream is attributed to the kernel that ends it
+  int prof_enabled;
+  cudaEvent_t* prof_ev;
+  const char** prof_name;
+  int prof_n, prof_cap;
 };
+
+void pslam_prof_mark(pslam_ctx* ctx, const char* name);  // pslam_capi.cu
 
 #define PSLAM_FLAG_RAW_OVERFLOW 1
 #define PSLAM_FLAG_FEATURE_OVERFLOW 2
@@ -82,6 +95,7 @@ static inline int pslam_set_error(pslam_ctx* ctx, int code, const char* what, cu
 #define PSLAM_LAUNCH_CHECK(ctx, name)                                          \
   do {                                                                         \
     (ctx)->launches++;                                                         \
+    if ((ctx)->prof_enabled) pslam_prof_mark(ctx, name);                       \
     cudaError_t e__ = cudaGetLastError();                                      \
     if (e__ != cudaSuccess) return pslam_set_error(ctx, PSLAM_E_CUDA, name, e__); \
   } while (0)

@@ -8,12 +8,24 @@ int pslam_k_fast_blur(pslam_ctx* ctx, const uint8_t* d_images, long long image_p
                       int rows, int cols, int stride, int thr, int nms);
 int pslam_k_bin_select(pslam_ctx* ctx, int n_images, int rows, int cols, int nh, int nv,
                        unsigned long long quota, const uint8_t* d_mask);
+// slot_base: feature-store slot of the chunk's first image (maps / raw lists are chunk-local)
 int pslam_k_assemble(pslam_ctx* ctx, const uint8_t* d_images, long long image_pitch, int stride,
-                     int n_images, int rows, int cols, int nbins, int border);
-int pslam_k_describe(pslam_ctx* ctx, int n_images);
+                     int n_images, int rows, int cols, int nbins, int border, int slot_base);
+int pslam_k_describe(pslam_ctx* ctx, int n_images, int slot_base);
 
 // k_epipolar.cu
 int pslam_k_epipolar(pslam_ctx* ctx, int n_pairs, const pslam_match_cfg* cfg);
+
+// packed (CSR) stereo result of a batch, carved from the context scratch: offsets[n_pairs + 1] then SoA
+struct pslam_packed_stereo {
+  long long* d_offsets;
+  float4* d_uvuv;
+  float* d_intensity;
+  uint32_t* d_desc;
+  int *d_left, *d_right;
+  float* d_dist;
+};
+int pslam_k_pack_stereo(pslam_ctx* ctx, int n_pairs, pslam_packed_stereo* out);
 
 // k_bruteforce.cu
 int pslam_k_bf_best2(pslam_ctx* ctx, int n_fixed, const uint32_t* d_desc_fixed, int n_moving,

@@ -177,6 +177,34 @@ def stereo_adaptor(left, right, cfg, matcher="epipolar", max_dist=50.0, ratio=0.
                 n_left=nl.value, n_right=nr.value, n_matches=nm.value)
 
 
+def stereo_frontend_batch(images, cfg, max_dist=50.0, ratio=0.9, max_disp=100, thickness=0, threads=1):
+    """images: u8 [n_pairs, 2, rows, cols]; returns (counts int32[n_pairs], checksum uint64[n_pairs])"""
+    images = np.ascontiguousarray(images, np.uint8)
+    n, two, rows, cols = images.shape
+    assert two == 2
+    m = np.array([max_dist, ratio, max_disp, thickness], np.float32)
+    counts = np.zeros(n, np.int32)
+    chk = np.zeros(n, np.uint64)
+    lib().orc_stereo_frontend_batch(_p(images), n, rows, cols, cols, C.c_longlong(rows * cols), _p(cfg), _p(m),
+                                    int(threads), _p(counts), _p(chk))
+    return counts, chk
+
+
+def fnv1a_points(uvuv, intensity, desc):
+    """the per-pair checksum of orc_stereo_frontend_batch, for results obtained elsewhere (vectorised)"""
+    h = 1469598103934665603
+    n = len(uvuv)
+    if n == 0:
+        return np.uint64(h)
+    rec = np.concatenate([np.ascontiguousarray(uvuv, np.float32).view(np.uint8).reshape(n, 16),
+                          np.ascontiguousarray(intensity, np.float32).view(np.uint8).reshape(n, 4),
+                          np.ascontiguousarray(desc, np.uint8).reshape(n, 32)], axis=1).reshape(-1)
+    M = (1 << 64) - 1
+    for b in rec.tolist():
+        h = ((h ^ b) * 1099511628211) & M
+    return np.uint64(h)
+
+
 def mono_depth_adaptor(img, depth, cfg, depth_scale=1.0, cap=20000):
     img = _img(img)
     is_float = depth.dtype == np.float32

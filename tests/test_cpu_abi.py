@@ -29,7 +29,7 @@ def test_exports_every_declared_symbol(built):
 
 def test_version_and_struct_sizes(built):
     assert b"sm_100a" in built.lib().pslam_version()
-    assert ctypes.sizeof(built.Limits) == 24 and ctypes.sizeof(built.ExtractCfg) == 20
+    assert ctypes.sizeof(built.Limits) == 28 and ctypes.sizeof(built.ExtractCfg) == 20
     assert ctypes.sizeof(built.MatchCfg) == 16
 
 
