@@ -253,9 +253,8 @@ def main():
     # algorithmic bytes per image of stage 1: image read once + selected keypoints (x, y,
     # response, intensity: 16 B) + descriptors (32 B); per kernel: its own compulsory input + output
     alg = {
-        "fast_blur_kernel": ROWS * COLS + mean_feat * 48,   # the stage-1 figure is billed to its dominant kernel
-        "bin_compact_kernel": ROWS * COLS,
-        "bin_sort_kernel": 9 * 8192 * 4 * 0 + mean_feat * 8,
+        "fast_blur_rows_kernel": ROWS * COLS + mean_feat * 48,   # the stage-1 figure is billed to its dominant kernel
+        "bin_select_kernel": mean_feat * 2.2 * 8,  # ~2.2x raw keypoints per kept one: row-list read + raw-list write
         "assemble_features_kernel": mean_feat * (4 + 16),
         "orb_describe_kernel": mean_feat * (31 * 31 + 32),
         "epipolar_kernel": 2 * mean_feat * (32 + 8),

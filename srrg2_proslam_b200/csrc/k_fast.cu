@@ -1,0 +1,595 @@
+// k_fast.cu -- stage 1 front half (sm_100a): FAST-9/16 + 3x3 NMS fused with the ORB 7x7 integer blur in
+// ONE pass over the image, and the per-region ordered gather + std::sort-exact selection.
+//
+// Reference path replaced:
+//   cv::FastFeatureDetector::detect (TYPE_9_16) called at
+//     .../sensor_processing/feature_extractors/intensity_feature_extractor_binned.cpp:139-147
+//   the 7x7 sigma-2 Gaussian inside cv::ORB::compute (OpenCV 3 fixed point), called at
+//     .../feature_extractors/intensity_feature_extractor_base.cpp:52
+//   bucket + std::sort + quota of IntensityFeatureExtractorBinned_::computeKeypoints (binned.cpp:164-200)
+//
+// K1 `fast_blur_rows_kernel` -- "marching" design.  A CTA owns a band of BH image rows over the whole image
+// width; a warp owns a 256-pixel strip, a lane 8 adjacent pixels (two 32-bit words).  The CTA walks down
+// the band one row per step and keeps a 7-row window of (a) the raw pixels and (b) the horizontally
+// filtered rows in REGISTERS, so every pixel is loaded from HBM/L2 once and the inner loops are word-wide:
+//   * blur: horizontal 7-tap as 2 x dp4a on byte quads, vertical 7-tap as 7 x dp2a on packed u16 pairs
+//     (exact: sum k_i k_j p <= 257*257*255 < 2^25), (v + 2^15) >> 16, min 255;
+//   * FAST compass pre-test on 16-bit SWAR pixel pairs: ring > c + t  <=>  bit 9 of (r + 512 - c - t - 1);
+//     a 9-arc always contains two adjacent compass points, so (N|S) & (E|W) per polarity is necessary;
+//   * candidates go to a per-warp shared-memory queue and are scored 32 at a time, one per lane, with only
+//     the polarity the pre-test saw (a pixel cannot be a bright AND a dark 9-arc corner: 9 + 9 > 16);
+//     score = max over the 16 arcs of min over the arc, written to a band-sized score tile in shared memory;
+//   * after the band: 3x3 NMS over the score tile and ordered emission of (col, response + 1) into per-row
+//     keypoint lists (row-major = the order cv::FAST emits), no dense NMS map ever goes to HBM.
+// Blur values closer than 3 px to the image border are NOT the reflect-101 values (nothing on the path reads
+// them: ORB only describes keypoints >= 31 px from the border and samples <= 13 px + the 3 px filter reach);
+// `blur_border_kernel` patches them for the stage-level entry point pslam_blur7.
+//
+// K2 `bin_select_kernel`: per (region, image) gather of the region's keypoints from the row lists in
+// row-major order, then the reference's selection (keep all if fewer than quota, else unstable std::sort by
+// response and keep the first quota) replayed move-for-move (libstdcxx_sort.h).
+#include "libstdcxx_sort.h"
+#include "pslam_internal.cuh"
+#include "pslam_kernels.cuh"
+
+namespace {
+
+constexpr int BH = 32;            // rows per band
+constexpr int QCAP = 512;         // per-warp candidate ring (entries); one push phase adds <= 256
+constexpr unsigned FULL = 0xffffffffu;
+constexpr unsigned M16 = 0x00ff00ffu;
+constexpr unsigned K9 = 0x02000200u;  // bit 9 of both 16-bit lanes
+
+__host__ __device__ inline int score_pitch(int n_strips) { return n_strips * 256 + 8; }  // bytes, multiple of 4
+
+// ---- row load: 8 pixels starting at column x (any alignment), clamped into the row ------------------------
+// Split in two so that the loads of row r+1 are in flight while row r is processed: `issue` only emits the
+// (up to three) aligned 32-bit loads, `finish` funnel-shifts them into place one marching step later.
+struct Raw3 {
+  unsigned w0, w1, w2;
+};
+__device__ __forceinline__ Raw3 load8_issue(const uint8_t* __restrict__ row, int x, int cols) {
+  int xl = x < 0 ? 0 : x;
+  if (xl > cols - 8) xl = cols - 8;
+  const uint8_t* a = row + xl;
+  const unsigned s = (unsigned) (uintptr_t) a & 3u;
+  const unsigned* wp = reinterpret_cast<const unsigned*>(a - s);
+  Raw3 r;
+  r.w0 = __ldg(wp);
+  r.w1 = __ldg(wp + 1);
+  r.w2 = s ? __ldg(wp + 2) : 0u;  // when aligned the third word is not needed (and may be out of bounds)
+  return r;
+}
+__device__ __forceinline__ void load8_finish(const Raw3& r, const uint8_t* __restrict__ row, int x, int cols,
+                                             unsigned& lo, unsigned& hi) {
+  int xl = x < 0 ? 0 : x;
+  if (xl > cols - 8) xl = cols - 8;
+  const unsigned sh = ((unsigned) (uintptr_t) (row + xl) & 3u) * 8u;
+  lo = __funnelshift_r(r.w0, r.w1, sh);
+  hi = __funnelshift_r(r.w1, r.w2, sh);
+  const int d = x - xl;  // > 0 only for lanes hanging over the right image edge: shift the valid bytes into place
+  if (d > 0) {
+    const unsigned long long v = d >= 8 ? 0ull : ((((unsigned long long) hi) << 32) | lo) >> (8 * d);
+    lo = (unsigned) v;
+    hi = (unsigned) (v >> 32);
+  }
+}
+
+// ---- FAST score of one candidate, one polarity (bright: ring brighter than the centre) ---------------------
+__device__ __forceinline__ int fast_score_polar(const uint8_t* __restrict__ p, int stride, bool bright) {
+  const int c = __ldg(p);
+  const int sgn = bright ? -1 : 1;  // d_k = sgn * (c - r_k): positive where the ring differs in the tested direction
+  const int cs = c * sgn;
+  int d[16];
+  d[0] = cs - sgn * (int) __ldg(p + 3 * stride);
+  d[1] = cs - sgn * (int) __ldg(p + 3 * stride + 1);
+  d[2] = cs - sgn * (int) __ldg(p + 2 * stride + 2);
+  d[3] = cs - sgn * (int) __ldg(p + stride + 3);
+  d[4] = cs - sgn * (int) __ldg(p + 3);
+  d[5] = cs - sgn * (int) __ldg(p - stride + 3);
+  d[6] = cs - sgn * (int) __ldg(p - 2 * stride + 2);
+  d[7] = cs - sgn * (int) __ldg(p - 3 * stride + 1);
+  d[8] = cs - sgn * (int) __ldg(p - 3 * stride);
+  d[9] = cs - sgn * (int) __ldg(p - 3 * stride - 1);
+  d[10] = cs - sgn * (int) __ldg(p - 2 * stride - 2);
+  d[11] = cs - sgn * (int) __ldg(p - stride - 3);
+  d[12] = cs - sgn * (int) __ldg(p - 3);
+  d[13] = cs - sgn * (int) __ldg(p + stride - 3);
+  d[14] = cs - sgn * (int) __ldg(p + 2 * stride - 2);
+  d[15] = cs - sgn * (int) __ldg(p + 3 * stride - 1);
+  int lo3[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) lo3[k] = min(min(d[k], d[(k + 1) & 15]), d[(k + 2) & 15]);
+  int s = -1024;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) s = max(s, min(min(lo3[k], lo3[(k + 3) & 15]), lo3[(k + 6) & 15]));
+  return s;
+}
+
+struct RowRegs {
+  unsigned hl, a0, a1, hr;  // pixels x0-4..x0-1 | x0..x0+3 | x0+4..x0+7 | x0+8..x0+11
+};
+
+// horizontal 7-tap of the 8 own pixels -> 4 words of packed u16 pairs
+__device__ __forceinline__ void hblur8(const RowRegs& r, unsigned h[4]) {
+  const unsigned KA = 18u | (34u << 8) | (49u << 16) | (55u << 24);  // taps -3..0
+  const unsigned KB = 49u | (34u << 8) | (18u << 16);                // taps +1..+3
+  // byte quads of the 16-byte window at offsets 1..12 (offset o = pixel x0 - 4 + o)
+  const unsigned q1 = __byte_perm(r.hl, r.a0, 0x4321), q2 = __byte_perm(r.hl, r.a0, 0x5432),
+                 q3 = __byte_perm(r.hl, r.a0, 0x6543), q4 = r.a0;
+  const unsigned q5 = __byte_perm(r.a0, r.a1, 0x4321), q6 = __byte_perm(r.a0, r.a1, 0x5432),
+                 q7 = __byte_perm(r.a0, r.a1, 0x6543), q8 = r.a1;
+  const unsigned q9 = __byte_perm(r.a1, r.hr, 0x4321), q10 = __byte_perm(r.a1, r.hr, 0x5432),
+                 q11 = __byte_perm(r.a1, r.hr, 0x6543), q12 = r.hr;
+  const unsigned h0 = __dp4a(q1, KA, __dp4a(q5, KB, 0u)), h1 = __dp4a(q2, KA, __dp4a(q6, KB, 0u));
+  const unsigned h2 = __dp4a(q3, KA, __dp4a(q7, KB, 0u)), h3 = __dp4a(q4, KA, __dp4a(q8, KB, 0u));
+  const unsigned h4 = __dp4a(q5, KA, __dp4a(q9, KB, 0u)), h5 = __dp4a(q6, KA, __dp4a(q10, KB, 0u));
+  const unsigned h6 = __dp4a(q7, KA, __dp4a(q11, KB, 0u)), h7 = __dp4a(q8, KA, __dp4a(q12, KB, 0u));
+  h[0] = h0 | (h1 << 16);  // <= 257 * 255 = 65535 each
+  h[1] = h2 | (h3 << 16);
+  h[2] = h4 | (h5 << 16);
+  h[3] = h6 | (h7 << 16);
+}
+
+// vertical 7-tap over the window (rows r-6 .. r as hm6 .. h0) for one packed pair -> two output bytes in bits 0-7 / 8-15
+__device__ __forceinline__ unsigned vblur_pair(unsigned hm6, unsigned hm5, unsigned hm4, unsigned hm3, unsigned hm2,
+                                               unsigned hm1, unsigned h0) {
+  const unsigned T18 = 18u | (18u << 24), T34 = 34u | (34u << 24), T49 = 49u | (49u << 24), T55 = 55u | (55u << 24);
+  unsigned lo = 32768u, hi = 32768u;
+  lo = __dp2a_lo(hm6, T18, lo); hi = __dp2a_hi(hm6, T18, hi);
+  lo = __dp2a_lo(hm5, T34, lo); hi = __dp2a_hi(hm5, T34, hi);
+  lo = __dp2a_lo(hm4, T49, lo); hi = __dp2a_hi(hm4, T49, hi);
+  lo = __dp2a_lo(hm3, T55, lo); hi = __dp2a_hi(hm3, T55, hi);
+  lo = __dp2a_lo(hm2, T49, lo); hi = __dp2a_hi(hm2, T49, hi);
+  lo = __dp2a_lo(hm1, T34, lo); hi = __dp2a_hi(hm1, T34, hi);
+  lo = __dp2a_lo(h0, T18, lo);  hi = __dp2a_hi(h0, T18, hi);
+  lo = min(lo, 0x00ffffffu);
+  hi = min(hi, 0x00ffffffu);
+  return __byte_perm(lo, hi, 0x0062);  // (lo >> 16) | ((hi >> 16) << 8)
+}
+
+// compass pre-test for the 8 own pixels of the centre row; returns 8-bit masks (bit j = pixel x0 + j)
+__device__ __forceinline__ void pretest8(const RowRegs& n, const RowRegs& c, const RowRegs& s, unsigned t1,
+                                         unsigned& m_bright, unsigned& m_dark) {
+  // centre pairs: E0 = (p0,p2) O0 = (p1,p3) E1 = (p4,p6) O1 = (p5,p7)
+  const unsigned cE0 = c.a0 & M16, cO0 = __byte_perm(c.a0, 0u, 0x4341), cE1 = c.a1 & M16, cO1 = __byte_perm(c.a1, 0u, 0x4341);
+  const unsigned nE0 = n.a0 & M16, nO0 = __byte_perm(n.a0, 0u, 0x4341), nE1 = n.a1 & M16, nO1 = __byte_perm(n.a1, 0u, 0x4341);
+  const unsigned sE0 = s.a0 & M16, sO0 = __byte_perm(s.a0, 0u, 0x4341), sE1 = s.a1 & M16, sO1 = __byte_perm(s.a1, 0u, 0x4341);
+  // east (+3) / west (-3) ring pairs on the centre row
+  const unsigned f36 = __funnelshift_r(c.a0, c.a1, 24);   // p3..p6
+  const unsigned f710 = __funnelshift_r(c.a1, c.hr, 24);  // p7..p10
+  const unsigned gm30 = __funnelshift_r(c.hl, c.a0, 8);   // p-3..p0
+  const unsigned f25 = __funnelshift_r(c.a0, c.a1, 16);   // p2..p5
+  const unsigned eE0 = f36 & M16 /*(3,5)*/, eO0 = cE1 /*(4,6)*/, eE1 = f710 & M16 /*(7,9)*/, eO1 = c.hr & M16 /*(8,10)*/;
+  const unsigned wE0 = gm30 & M16 /*(-3,-1)*/, wO0 = __byte_perm(gm30, 0u, 0x4341) /*(-2,0)*/, wE1 = cO0 /*(1,3)*/,
+                 wO1 = f25 & M16 /*(2,4)*/;
+#define PSLAM_PRETEST(C, N, S, E, W, OUTB, OUTD)                                            \
+  {                                                                                         \
+    const unsigned kb = K9 - (C) - t1; /* + ring: bit 9 <=> ring > c + t */                 \
+    const unsigned kd = K9 + (C) - t1; /* - ring: bit 9 <=> ring < c - t */                 \
+    OUTB = (((N) + kb) | ((S) + kb)) & (((E) + kb) | ((W) + kb)) & K9;                      \
+    OUTD = ((kd - (N)) | (kd - (S))) & ((kd - (E)) | (kd - (W))) & K9;                      \
+  }
+  unsigned bE0, bO0, bE1, bO1, dE0, dO0, dE1, dO1;
+  PSLAM_PRETEST(cE0, nE0, sE0, eE0, wE0, bE0, dE0)
+  PSLAM_PRETEST(cO0, nO0, sO0, eO0, wO0, bO0, dO0)
+  PSLAM_PRETEST(cE1, nE1, sE1, eE1, wE1, bE1, dE1)
+  PSLAM_PRETEST(cO1, nO1, sO1, eO1, wO1, bO1, dO1)
+#undef PSLAM_PRETEST
+  // bit 9 -> pixel (0|1|4|5), bit 25 -> pixel (2|3|6|7)
+  const unsigned ub = (bE0 >> 9) | (bO0 >> 8) | (bE1 >> 5) | (bO1 >> 4);
+  const unsigned ud = (dE0 >> 9) | (dO0 >> 8) | (dE1 >> 5) | (dO1 >> 4);
+  m_bright = (ub | (ub >> 14)) & 0xffu;
+  m_dark = (ud | (ud >> 14)) & 0xffu;
+}
+
+struct K1Args {
+  const uint8_t* images;
+  long long image_pitch;
+  int rows, cols, stride, thr, nms;
+  uint8_t* blur;
+  int map_pitch;
+  long long map_slot;
+  int* row_count;      // [images][max_rows]
+  uint32_t* row_kp;    // [images][max_rows][row_cap]  (col << 8) | (response + 1)
+  int row_cap, max_rows;
+};
+
+__host__ __device__ inline int bits_pitch(int n_strips) { return (score_pitch(n_strips) + 31) / 32; }  // words / tile row
+
+__global__ void __launch_bounds__(512)
+fast_blur_rows_kernel(const K1Args a) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_strips = blockDim.x >> 5;
+  const int SP = score_pitch(n_strips), BW = bits_pitch(n_strips);
+  // shared memory: score tile | corner bitmap | per-warp candidate rings | per-warp corner lists (NMS phase)
+  uint8_t* s_score = smem;                                                     // [BH + 2][SP], pixel column c at byte c + 4
+  unsigned* s_bits = reinterpret_cast<unsigned*>(smem + (size_t) (BH + 2) * SP);  // [BH + 2][BW], bit = byte index in the row
+  unsigned* s_queue = s_bits + (BH + 2) * BW + warp * QCAP;
+  unsigned short* s_list = reinterpret_cast<unsigned short*>(s_bits + (BH + 2) * BW + n_strips * QCAP) + (size_t) warp * (BW * 32);
+  const int by = blockIdx.x * BH, image = blockIdx.y;
+  const uint8_t* img = a.images + (size_t) image * a.image_pitch;
+  uint8_t* blur = a.blur + (size_t) image * a.map_slot;
+  const int rows = a.rows, cols = a.cols, stride = a.stride, thr = a.thr;
+  const int x0 = warp * 256 + lane * 8;
+  const int xe = lane == 0 ? x0 - 8 : x0 + 8;  // strip-edge lanes fetch the neighbour strip's pixels themselves
+  const bool edge = lane == 0 || lane == 31;
+
+  for (int i = tid; i < ((BH + 2) * SP + (BH + 2) * BW * 4) / 4; i += blockDim.x) reinterpret_cast<unsigned*>(smem)[i] = 0u;
+  __syncthreads();
+
+  // FAST centres: 3 <= x <= cols - 4
+  unsigned colmask = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (x0 + j >= 3 && x0 + j <= cols - 4) colmask |= 1u << j;
+  colmask |= colmask << 8;  // bright bits 0-7, dark bits 8-15
+  const unsigned t1 = (unsigned) (thr + 1) * 0x00010001u;
+  const bool store_ok = x0 < a.map_pitch;
+  unsigned q_head = 0, q_tail = 0;
+
+  RowRegs R[7];
+  unsigned H[7][4];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) {
+    R[i].hl = R[i].a0 = R[i].a1 = R[i].hr = 0u;
+    H[i][0] = H[i][1] = H[i][2] = H[i][3] = 0u;
+  }
+
+  auto row_ptr = [&](int r) {
+    const int yy = r < 0 ? 0 : (r >= rows ? rows - 1 : r);
+    return img + (size_t) yy * stride;
+  };
+  auto score_batch = [&](unsigned entry, bool active) {
+    if (active) {
+      const int col = entry & 0xffff, trow = (entry >> 16) & 0x7fff;
+      const bool bright = (entry >> 31) != 0;
+      const int y = by - 1 + trow;
+      const int s = fast_score_polar(img + (size_t) y * stride + col, stride, bright);
+      if (s > thr) {
+        const int ci = col + 4;
+        s_score[trow * SP + ci] = (uint8_t) s;  // 1..255; response = s - 1
+        atomicOr(&s_bits[trow * BW + (ci >> 5)], 1u << (ci & 31));
+      }
+    }
+  };
+  // mask: bits 0-7 bright candidates, 8-15 dark candidates of the lane's 8 pixels
+  auto push_and_drain = [&](unsigned mask, int trow) {
+    const int cnt = __popc(mask);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(FULL, incl, o);
+      if (lane >= o) incl += t;
+    }
+    const int total = __shfl_sync(FULL, incl, 31);
+    if (total == 0) return;
+    unsigned pos = q_tail + incl - cnt;
+    const unsigned ebase = ((unsigned) trow << 16) | (unsigned) x0;
+    while (mask) {
+      const unsigned i = __ffs(mask) - 1;
+      mask &= mask - 1;
+      s_queue[pos & (QCAP - 1)] = ebase + (i & 7u) + ((i & 8u) ? 0u : 0x80000000u);
+      ++pos;
+    }
+    q_tail += total;
+    __syncwarp();
+    while (q_tail - q_head >= 32) {
+      score_batch(s_queue[(q_head + lane) & (QCAP - 1)], true);
+      q_head += 32;
+    }
+    __syncwarp();
+  };
+
+  // software pipeline: the loads of the next row are issued one marching step ahead
+  Raw3 nx = load8_issue(row_ptr(by - 4), x0, cols), ne = {0u, 0u, 0u};
+  if (edge) ne = load8_issue(row_ptr(by - 4), xe, cols);
+
+  // one marching step: image row r enters window slot S
+#define PSLAM_STEP(S)                                                                                         \
+  if (base + (S) < BH + 8) {                                                                                  \
+    const int r = by - 4 + base + (S);                                                                        \
+    const uint8_t* rowp = row_ptr(r);                                                                         \
+    RowRegs& cur = R[(S)];                                                                                    \
+    load8_finish(nx, rowp, x0, cols, cur.a0, cur.a1);                                                         \
+    cur.hl = __shfl_up_sync(FULL, cur.a1, 1);                                                                 \
+    cur.hr = __shfl_down_sync(FULL, cur.a0, 1);                                                               \
+    if (edge) {                                                                                               \
+      unsigned e0, e1;                                                                                        \
+      load8_finish(ne, rowp, xe, cols, e0, e1);                                                               \
+      if (lane == 0) cur.hl = e1; else cur.hr = e0;                                                           \
+    }                                                                                                         \
+    if (base + (S) + 1 < BH + 8) {                                                                            \
+      const uint8_t* nrow = row_ptr(r + 1);                                                                   \
+      nx = load8_issue(nrow, x0, cols);                                                                       \
+      if (edge) ne = load8_issue(nrow, xe, cols);                                                             \
+    }                                                                                                         \
+    hblur8(cur, H[(S)]);                                                                                      \
+    const int rc = r - 3; /* blur output row and FAST centre row */                                           \
+    if (rc >= by && rc < by + BH && rc < rows && store_ok) {                                                  \
+      unsigned o[4];                                                                                          \
+      _Pragma("unroll") for (int k = 0; k < 4; ++k)                                                           \
+        o[k] = vblur_pair(H[((S) + 1) % 7][k], H[((S) + 2) % 7][k], H[((S) + 3) % 7][k], H[((S) + 4) % 7][k], \
+                          H[((S) + 5) % 7][k], H[((S) + 6) % 7][k], H[(S)][k]);                               \
+      uint2 w;                                                                                                \
+      w.x = __byte_perm(o[0], o[1], 0x5410);                                                                  \
+      w.y = __byte_perm(o[2], o[3], 0x5410);                                                                  \
+      *reinterpret_cast<uint2*>(blur + (size_t) rc * a.map_pitch + x0) = w;                                   \
+    }                                                                                                         \
+    if (rc >= by - 1 && rc <= by + BH && rc >= 3 && rc < rows - 3) {                                          \
+      unsigned mb, md;                                                                                        \
+      pretest8(R[((S) + 1) % 7], R[((S) + 4) % 7], cur, t1, mb, md);                                          \
+      push_and_drain((mb | (md << 8)) & colmask, rc - (by - 1));                                              \
+    }                                                                                                         \
+  }
+
+  for (int base = 0; base < BH + 8; base += 7) {
+    PSLAM_STEP(0) PSLAM_STEP(1) PSLAM_STEP(2) PSLAM_STEP(3) PSLAM_STEP(4) PSLAM_STEP(5) PSLAM_STEP(6)
+  }
+#undef PSLAM_STEP
+  // drain what is left in the queue (< 32 entries)
+  {
+    const unsigned left = q_tail - q_head;
+    score_batch(s_queue[(q_head + lane) & (QCAP - 1)], (unsigned) lane < left);
+  }
+  __syncthreads();
+
+  // ---- 3x3 NMS + ordered emission into the per-row keypoint lists ----
+  // per tile row: (A) ordered compaction of the corner bitmap into a list of byte indices, (B) one corner per
+  // lane: compare with the 8 neighbours in the score tile, ballot, append survivors in column order.
+  for (int t = 1 + warp; t <= BH; t += n_strips) {
+    const int y = by - 1 + t;
+    if (y >= rows) break;
+    int n_list = 0;
+    for (int g = 0; g < BW; g += 32) {
+      const int j = g + lane;
+      unsigned w = j < BW ? s_bits[t * BW + j] : 0u;
+      const int cnt = __popc(w);
+      int incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int tt = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += tt;
+      }
+      int pos = n_list + incl - cnt;
+      while (w) {
+        const int b = __ffs(w) - 1;
+        w &= w - 1;
+        s_list[pos++] = (unsigned short) (32 * j + b);
+      }
+      n_list += __shfl_sync(FULL, incl, 31);
+    }
+    __syncwarp();
+    uint32_t* out = a.row_kp + ((size_t) image * a.max_rows + y) * a.row_cap;
+    int count = 0;
+    for (int k0 = 0; k0 < n_list; k0 += 32) {
+      const int k = k0 + lane;
+      bool keep = false;
+      unsigned entry = 0;
+      if (k < n_list) {
+        const int ci = s_list[k];
+        const uint8_t* sc = s_score + (size_t) t * SP + ci;
+        const int sv = sc[0];
+        keep = true;
+        int val = 1;  // without NMS the response is 0
+        if (a.nms) {
+          int m = max(max(sc[-SP - 1], sc[-SP]), max(sc[-SP + 1], sc[-1]));
+          m = max(m, max(max(sc[1], sc[SP - 1]), max(sc[SP], sc[SP + 1])));
+          keep = m > 0 ? sv > m : sv >= 2;  // response s-1 strictly greater than every neighbour's (0 for non-corners)
+          val = sv;
+        }
+        entry = ((unsigned) (ci - 4) << 8) | (unsigned) val;
+      }
+      const unsigned bal = __ballot_sync(FULL, keep);
+      if (keep) {
+        const int pos = count + __popc(bal & ((1u << lane) - 1u));
+        if (pos < a.row_cap) out[pos] = entry;
+      }
+      count += __popc(bal);
+    }
+    if (lane == 0) a.row_count[(size_t) image * a.max_rows + y] = count < a.row_cap ? count : a.row_cap;
+    __syncwarp();
+  }
+}
+
+// ---- exact reflect-101 blur on the 3-pixel image frame (pslam_blur7 only) ----------------------------------
+__global__ void blur_border_kernel(const uint8_t* __restrict__ img, int rows, int cols, int stride,
+                                   uint8_t* __restrict__ blur, int map_pitch) {
+  const int n_frame = 2 * 3 * cols + 2 * 3 * (rows - 6 > 0 ? rows - 6 : 0);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_frame) return;
+  int x, y;
+  if (i < 3 * cols) {
+    y = i / cols;
+    x = i - y * cols;
+  } else if (i < 6 * cols) {
+    const int k = i - 3 * cols;
+    y = rows - 3 + k / cols;
+    x = k % cols;
+  } else {
+    const int k = i - 6 * cols, rr = rows - 6;
+    const int side = k / (3 * rr), kk = k % (3 * rr);
+    y = 3 + kk / 3;
+    x = side == 0 ? kk % 3 : cols - 3 + kk % 3;
+  }
+  if (y < 0 || y >= rows) return;
+  const int kq[7] = {18, 34, 49, 55, 49, 34, 18};
+  int v = 0;
+  for (int dy = -3; dy <= 3; ++dy) {
+    const int yy = reflect101(y + dy, rows);
+    int h = 0;
+    for (int dx = -3; dx <= 3; ++dx) h += kq[dx + 3] * img[(size_t) yy * stride + reflect101(x + dx, cols)];
+    v += kq[dy + 3] * h;
+  }
+  blur[(size_t) y * map_pitch + x] = (uint8_t) min(255, (v + 32768) >> 16);
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// K2: gather + select.  grid (regions, images), one CTA of SEL_THREADS threads.
+// -------------------------------------------------------------------------------------------------------------
+constexpr int SEL_THREADS = 64;
+
+struct RespGreater {
+  __device__ __forceinline__ bool operator()(const uint32_t& x, const uint32_t& y) const {
+    return (x & 0xffu) > (y & 0xffu);
+  }
+};
+
+__global__ void __launch_bounds__(SEL_THREADS)
+bin_select_kernel(const int* __restrict__ row_count, const uint32_t* __restrict__ row_kp, int row_cap, int max_rows,
+                  const uint8_t* __restrict__ mask, int mask_pitch, int rows, int cols, int nh, int nv,
+                  float pixel_rows_per_detector, float pixel_cols_per_detector, uint32_t* __restrict__ raw,
+                  int max_raw_per_bin, int max_bins, int* __restrict__ raw_count, int* __restrict__ sel_count,
+                  unsigned long long quota, int sort_cap, int* __restrict__ flags) {
+  extern __shared__ __align__(16) uint32_t s_sort[];
+  __shared__ int s_warp[33];
+  __shared__ int s_rbegin, s_rend, s_cbegin, s_cend;
+  const int tid = threadIdx.x;
+  const int bin = blockIdx.x, image = blockIdx.y;
+  const int rb = bin / nh;
+  uint32_t* seg = raw + ((size_t) image * max_bins + bin) * max_raw_per_bin;
+  if (tid == 0) {
+    s_rbegin = rows;
+    s_rend = 0;
+    s_cbegin = cols;
+    s_cend = 0;
+  }
+  __syncthreads();
+  // rows of this region row: floor(r / pixel_rows_per_detector) == rb   (binned.cpp:84-85)
+  for (int r = tid; r < rows; r += SEL_THREADS) {
+    const float q = floorf(__fdiv_rn((float) r, pixel_rows_per_detector));
+    if ((int) q == rb) {
+      atomicMin(&s_rbegin, r);
+      atomicMax(&s_rend, r + 1);
+    }
+  }
+  // columns: (size_t)((float) row_region + (float) c / pixel_cols_per_detector) == bin (:86-88); monotone in c
+  const float row_region = __fmul_rn((float) rb, (float) nh);
+  for (int c = tid; c < cols; c += SEL_THREADS) {
+    const float f = __fadd_rn((float) (unsigned) row_region, __fdiv_rn((float) c, pixel_cols_per_detector));
+    if ((unsigned) f == (unsigned) bin) {
+      atomicMin(&s_cbegin, c);
+      atomicMax(&s_cend, c + 1);
+    }
+  }
+  __syncthreads();
+  const int rbegin = s_rbegin, rend = s_rend, cbegin = s_cbegin, cend = s_cend;
+  // ordered gather: one thread per image row, rows in chunks of SEL_THREADS
+  int running = 0;
+  for (int base = rbegin; base < rend; base += SEL_THREADS) {
+    const int r = base + tid;
+    int cnt = 0, first = 0, n_r = 0;
+    const uint32_t* src = nullptr;
+    if (r < rend) {
+      n_r = row_count[(size_t) image * max_rows + r];
+      src = row_kp + ((size_t) image * max_rows + r) * row_cap;
+      for (int k = 0; k < n_r; ++k) {
+        const int c = (int) (src[k] >> 8);
+        if (c < cbegin) {
+          first = k + 1;
+          continue;
+        }
+        if (c >= cend) break;
+        if (mask && mask[(size_t) r * mask_pitch + c] == 0) continue;
+        ++cnt;
+      }
+    }
+    int total;
+    const int off = block_exclusive_scan<SEL_THREADS>(cnt, s_warp, &total);
+    if (cnt) {
+      int o = running + off;
+      for (int k = first; k < n_r; ++k) {
+        const uint32_t e = src[k];
+        const int c = (int) (e >> 8);
+        if (c >= cend) break;
+        if (mask && mask[(size_t) r * mask_pitch + c] == 0) continue;
+        if (o < max_raw_per_bin) seg[o] = ((uint32_t) (r * cols + c) << 8) | (e & 0xffu);
+        ++o;
+      }
+    }
+    running += total;
+  }
+  __syncthreads();
+  int n = running;
+  if (n > max_raw_per_bin) {
+    if (tid == 0) atomicOr(flags, PSLAM_FLAG_RAW_OVERFLOW);
+    n = max_raw_per_bin;
+  }
+  // selection (binned.cpp:180-200)
+  int kept = n;
+  if ((unsigned long long) n >= quota) {
+    kept = (int) quota;
+    if (kept > 0) {
+      if (n <= sort_cap) {
+        for (int i = tid; i < n; i += SEL_THREADS) s_sort[i] = seg[i];
+        __syncthreads();
+        if (tid == 0) pslam_sort::std_sort_prefix(s_sort, n, kept, RespGreater());
+        __syncthreads();
+        for (int i = tid; i < kept; i += SEL_THREADS) seg[i] = s_sort[i];
+      } else if (tid == 0) {
+        pslam_sort::std_sort_prefix(seg, n, kept, RespGreater());
+      }
+    }
+  }
+  if (tid == 0) {
+    raw_count[image * max_bins + bin] = n;
+    sel_count[image * max_bins + bin] = kept;
+  }
+}
+
+}  // namespace
+
+// ---- host-side launchers -----------------------------------------------------------------------------------
+int pslam_k_fast_blur(pslam_ctx* ctx, const uint8_t* d_images, long long image_pitch, int n_images,
+                      int rows, int cols, int stride, int thr, int nms) {
+  const int n_strips = (cols + 255) / 256;
+  if (n_strips > 16) return pslam_set_error(ctx, PSLAM_E_CAPACITY, "images wider than 4096 pixels are not supported", cudaSuccess);
+  thr = thr < 0 ? 0 : (thr > 255 ? 255 : thr);
+  K1Args a;
+  a.images = d_images;
+  a.image_pitch = image_pitch;
+  a.rows = rows;
+  a.cols = cols;
+  a.stride = stride;
+  a.thr = thr;
+  a.nms = nms;
+  a.blur = ctx->d_blur;
+  a.map_pitch = ctx->map_pitch;
+  a.map_slot = (long long) ctx->map_slot;
+  a.row_count = ctx->d_row_count;
+  a.row_kp = ctx->d_row_kp;
+  a.row_cap = ctx->map_pitch;
+  a.max_rows = ctx->lim.max_rows;
+  const size_t smem = (size_t) (BH + 2) * score_pitch(n_strips) + (size_t) (BH + 2) * bits_pitch(n_strips) * 4 +
+                      (size_t) n_strips * QCAP * 4 + (size_t) n_strips * bits_pitch(n_strips) * 32 * 2;
+  if (smem > ctx->k1_smem_set) {
+    PSLAM_CUDA_TRY(ctx, cudaFuncSetAttribute(fast_blur_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    ctx->k1_smem_set = smem;
+  }
+  dim3 grid((rows + BH - 1) / BH, n_images);
+  fast_blur_rows_kernel<<<grid, 32 * n_strips, smem, ctx->stream>>>(a);
+  PSLAM_LAUNCH_CHECK(ctx, "fast_blur_rows_kernel");
+  return PSLAM_OK;
+}
+
+int pslam_k_blur_border(pslam_ctx* ctx, const uint8_t* d_image, int rows, int cols, int stride) {
+  const int n_frame = 6 * cols + 6 * (rows > 6 ? rows - 6 : 0);
+  blur_border_kernel<<<(n_frame + 255) / 256, 256, 0, ctx->stream>>>(d_image, rows, cols, stride, ctx->d_blur, ctx->map_pitch);
+  PSLAM_LAUNCH_CHECK(ctx, "blur_border_kernel");
+  return PSLAM_OK;
+}
+
+int pslam_k_bin_select(pslam_ctx* ctx, int n_images, int rows, int cols, int nh, int nv,
+                       unsigned long long quota, const uint8_t* d_mask) {
+  // float arithmetic of IntensityFeatureExtractorBinned_::init (binned.cpp:49-52)
+  const float pr = static_cast<float>(rows) / static_cast<float>((size_t) nv);
+  const float pc = static_cast<float>(cols) / static_cast<float>((size_t) nh);
+  dim3 grid(nh * nv, n_images);
+  const int sort_cap = ctx->lim.max_raw_per_bin < 2048 ? ctx->lim.max_raw_per_bin : 2048;
+  bin_select_kernel<<<grid, SEL_THREADS, (size_t) sort_cap * 4, ctx->stream>>>(
+    ctx->d_row_count, ctx->d_row_kp, ctx->map_pitch, ctx->lim.max_rows, d_mask, ctx->map_pitch, rows, cols, nh, nv, pr,
+    pc, ctx->d_raw, ctx->lim.max_raw_per_bin, ctx->lim.max_bins, ctx->d_raw_count, ctx->d_sel_count, quota, sort_cap,
+    ctx->d_flags);
+  PSLAM_LAUNCH_CHECK(ctx, "bin_select_kernel");
+  return PSLAM_OK;
+}

@@ -66,6 +66,8 @@ int validate_extract(pslam_ctx* ctx, int n_images, int rows, int cols, const psl
     return pslam_set_error(ctx, PSLAM_E_CAPACITY, "more detection regions than pslam_limits.max_bins", cudaSuccess);
   if (rows < 8 || cols < 8)
     return pslam_set_error(ctx, PSLAM_E_INVALID, "image smaller than 8x8", cudaSuccess);
+  if ((long long) rows * cols >= (1LL << 24) || cols > 4096)
+    return pslam_set_error(ctx, PSLAM_E_CAPACITY, "image larger than 2^24 pixels or wider than 4096", cudaSuccess);
   return PSLAM_OK;
 }
 
@@ -212,7 +214,8 @@ int pslam_create(int device, const pslam_limits* lim, pslam_ctx** out) {
   const size_t NI = lim->max_images, MF = lim->max_features, NP = (lim->max_images + 1) / 2;
   const size_t NW = ctx->work_images;
   PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_images, 2 * NW * ctx->img_slot));
-  PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_nms, NW * ctx->map_slot));
+  PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_row_kp, NW * lim->max_rows * (size_t) ctx->map_pitch));
+  PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_row_count, NW * lim->max_rows));
   PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_blur, NW * ctx->map_slot));
   PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_mask, ctx->map_slot));
   PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_raw, NW * lim->max_bins * (size_t) lim->max_raw_per_bin));
@@ -251,7 +254,7 @@ void pslam_destroy(pslam_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  void* bufs[] = {ctx->d_images, ctx->d_nms, ctx->d_blur, ctx->d_mask, ctx->d_raw, ctx->d_raw_count,
+  void* bufs[] = {ctx->d_images, ctx->d_row_kp, ctx->d_row_count, ctx->d_blur, ctx->d_mask, ctx->d_raw, ctx->d_raw_count,
                   ctx->d_sel_count, ctx->d_xy, ctx->d_resp, ctx->d_inten, ctx->d_desc, ctx->d_count,
                   ctx->d_st_uvuv, ctx->d_st_left, ctx->d_st_right, ctx->d_st_dist, ctx->d_st_count,
                   ctx->d_ep_fixed, ctx->d_ep_moving, ctx->d_ep_dist, ctx->d_ep_count, ctx->d_flags,
@@ -425,6 +428,8 @@ int pslam_blur7(pslam_ctx* ctx, const uint8_t* image, int rows, int cols, int st
   PSLAM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   if ((rc = upload_images(ctx, image, 1, rows, cols, stride, 0))) return rc;
   if ((rc = pslam_k_fast_blur(ctx, ctx->d_images, (long long) ctx->img_slot, 1, rows, cols, ctx->img_pitch, 255, 1))) return rc;
+  // the pipeline's blur map is exact except on the 3-pixel frame nothing reads; patch it for this entry point
+  if ((rc = pslam_k_blur_border(ctx, ctx->d_images, rows, cols, ctx->img_pitch))) return rc;
   PSLAM_CUDA_TRY(ctx, cudaMemcpy2DAsync(out, cols, ctx->d_blur, ctx->map_pitch, cols, rows, cudaMemcpyDeviceToHost, ctx->stream));
   PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return PSLAM_OK;

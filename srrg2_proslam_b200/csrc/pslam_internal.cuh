@@ -14,7 +14,8 @@
 // Stage 1 runs in chunks of `work_images` images so that the intermediate maps of a chunk stay
 // L2-resident between the kernels that produce and consume them; only the stores are batch-sized.
 //   images   u8  [2][work_images][max_rows][img_pitch]      double-buffered staging (host-pointer entry points)
-//   nms_map  u8  [work_images][max_rows][map_pitch]         0 = no keypoint, else FAST response + 1
+//   row_kp   u32 [work_images][max_rows][map_pitch]         per-row keypoint lists after NMS, (col << 8) | response + 1,
+//   row_count int [work_images][max_rows]                   ordered by column (only the used prefix is ever touched)
 //   blur     u8  [work_images][max_rows][map_pitch]         ORB 7x7 integer Gaussian
 //   raw      u32 [work_images][max_bins][max_raw_per_bin]   (pixel index << 8 | response + 1), row-major per bin
 //   features SoA [max_images][max_features]: xy float2, response f32, intensity f32, desc 8 x u32
@@ -32,7 +33,9 @@ struct pslam_ctx {
   int img_pitch, map_pitch;
   size_t img_slot, map_slot;  // bytes per image slot
   uint8_t* d_images;
-  uint8_t* d_nms;
+  uint32_t* d_row_kp;
+  int* d_row_count;
+  size_t k1_smem_set;
   uint8_t* d_blur;
   uint8_t* d_mask;  // [max_rows][map_pitch], single image (host entry point only)
   uint32_t* d_raw;

@@ -2,8 +2,9 @@
 #pragma once
 #include "pslam_internal.cuh"
 
-// k_detect.cu
+// k_fast.cu / k_detect.cu
 int pslam_k_upload_pattern(pslam_ctx* ctx);
+int pslam_k_blur_border(pslam_ctx* ctx, const uint8_t* d_image, int rows, int cols, int stride);
 int pslam_k_fast_blur(pslam_ctx* ctx, const uint8_t* d_images, long long image_pitch, int n_images,
                       int rows, int cols, int stride, int thr, int nms);
 int pslam_k_bin_select(pslam_ctx* ctx, int n_images, int rows, int cols, int nh, int nv,
