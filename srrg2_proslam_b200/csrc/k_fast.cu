@@ -195,6 +195,65 @@ struct K1Args {
   int row_cap, max_rows;
 };
 
+// Candidate queue: push this lane's candidates (mask bits 0-7 bright, 8-15 dark pixels x0..x0+7 of tile row
+// trow) in lane order, then score full batches of 32, one candidate per lane.  Deliberately NOT inlined: it is
+// called from the 7 unrolled marching steps and inlining it 7x makes the kernel overflow the instruction cache
+// (ncu: stall_no_instruction was the top stall reason).  Returns the new (head, tail) packed in 64 bits.
+struct ScoreCtx {
+  const uint8_t* img;
+  uint8_t* s_score;
+  unsigned* s_bits;
+  unsigned* s_queue;
+  int stride, by, thr, SP, BW;
+};
+__device__ __forceinline__ void score_entry(const ScoreCtx& c, unsigned entry) {
+  const int col = entry & 0xffff, trow = (entry >> 16) & 0x7fff;
+  const bool bright = (entry >> 31) != 0;
+  const int y = c.by - 1 + trow;
+  const int s = fast_score_polar(c.img + (size_t) y * c.stride + col, c.stride, bright);
+  if (s > c.thr) {
+    const int ci = col + 4;
+    c.s_score[trow * c.SP + ci] = (uint8_t) s;  // 1..255; response = s - 1
+    atomicOr(&c.s_bits[trow * c.BW + (ci >> 5)], 1u << (ci & 31));
+  }
+}
+__device__ __noinline__ unsigned long long push_and_drain(const uint8_t* img, uint8_t* s_score, unsigned* s_bits,
+                                                          unsigned* s_queue, int stride, int by, int thr, int SP,
+                                                          int BW, unsigned mask, unsigned ebase, unsigned q_head,
+                                                          unsigned q_tail, bool flush) {
+  const int lane = threadIdx.x & 31;
+  ScoreCtx c{img, s_score, s_bits, s_queue, stride, by, thr, SP, BW};
+  const int cnt = __popc(mask);
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(FULL, incl, o);
+    if (lane >= o) incl += t;
+  }
+  const int total = __shfl_sync(FULL, incl, 31);
+  if (total) {
+    unsigned pos = q_tail + incl - cnt;
+    while (mask) {
+      const unsigned i = __ffs(mask) - 1;
+      mask &= mask - 1;
+      s_queue[pos & (QCAP - 1)] = ebase + (i & 7u) + ((i & 8u) ? 0u : 0x80000000u);
+      ++pos;
+    }
+    q_tail += total;
+    __syncwarp();
+  }
+  while (q_tail - q_head >= 32) {
+    score_entry(c, s_queue[(q_head + lane) & (QCAP - 1)]);
+    q_head += 32;
+  }
+  if (flush && q_tail != q_head) {  // end of the band: what is left (< 32 entries)
+    if ((unsigned) lane < q_tail - q_head) score_entry(c, s_queue[(q_head + lane) & (QCAP - 1)]);
+    q_head = q_tail;
+  }
+  __syncwarp();
+  return ((unsigned long long) q_tail << 32) | q_head;
+}
+
 __host__ __device__ inline int bits_pitch(int n_strips) { return (score_pitch(n_strips) + 31) / 32; }  // words / tile row
 
 __global__ void __launch_bounds__(512)
@@ -240,98 +299,62 @@ fast_blur_rows_kernel(const K1Args a) {
     const int yy = r < 0 ? 0 : (r >= rows ? rows - 1 : r);
     return img + (size_t) yy * stride;
   };
-  auto score_batch = [&](unsigned entry, bool active) {
-    if (active) {
-      const int col = entry & 0xffff, trow = (entry >> 16) & 0x7fff;
-      const bool bright = (entry >> 31) != 0;
-      const int y = by - 1 + trow;
-      const int s = fast_score_polar(img + (size_t) y * stride + col, stride, bright);
-      if (s > thr) {
-        const int ci = col + 4;
-        s_score[trow * SP + ci] = (uint8_t) s;  // 1..255; response = s - 1
-        atomicOr(&s_bits[trow * BW + (ci >> 5)], 1u << (ci & 31));
-      }
-    }
-  };
-  // mask: bits 0-7 bright candidates, 8-15 dark candidates of the lane's 8 pixels
-  auto push_and_drain = [&](unsigned mask, int trow) {
-    const int cnt = __popc(mask);
-    int incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(FULL, incl, o);
-      if (lane >= o) incl += t;
-    }
-    const int total = __shfl_sync(FULL, incl, 31);
-    if (total == 0) return;
-    unsigned pos = q_tail + incl - cnt;
-    const unsigned ebase = ((unsigned) trow << 16) | (unsigned) x0;
-    while (mask) {
-      const unsigned i = __ffs(mask) - 1;
-      mask &= mask - 1;
-      s_queue[pos & (QCAP - 1)] = ebase + (i & 7u) + ((i & 8u) ? 0u : 0x80000000u);
-      ++pos;
-    }
-    q_tail += total;
-    __syncwarp();
-    while (q_tail - q_head >= 32) {
-      score_batch(s_queue[(q_head + lane) & (QCAP - 1)], true);
-      q_head += 32;
-    }
-    __syncwarp();
-  };
-
   // software pipeline: the loads of the next row are issued one marching step ahead
   Raw3 nx = load8_issue(row_ptr(by - 4), x0, cols), ne = {0u, 0u, 0u};
   if (edge) ne = load8_issue(row_ptr(by - 4), xe, cols);
 
-  // one marching step: image row r enters window slot S
-#define PSLAM_STEP(S)                                                                                         \
-  if (base + (S) < BH + 8) {                                                                                  \
-    const int r = by - 4 + base + (S);                                                                        \
-    const uint8_t* rowp = row_ptr(r);                                                                         \
-    RowRegs& cur = R[(S)];                                                                                    \
-    load8_finish(nx, rowp, x0, cols, cur.a0, cur.a1);                                                         \
-    cur.hl = __shfl_up_sync(FULL, cur.a1, 1);                                                                 \
-    cur.hr = __shfl_down_sync(FULL, cur.a0, 1);                                                               \
-    if (edge) {                                                                                               \
-      unsigned e0, e1;                                                                                        \
-      load8_finish(ne, rowp, xe, cols, e0, e1);                                                               \
-      if (lane == 0) cur.hl = e1; else cur.hr = e0;                                                           \
-    }                                                                                                         \
-    if (base + (S) + 1 < BH + 8) {                                                                            \
-      const uint8_t* nrow = row_ptr(r + 1);                                                                   \
-      nx = load8_issue(nrow, x0, cols);                                                                       \
-      if (edge) ne = load8_issue(nrow, xe, cols);                                                             \
-    }                                                                                                         \
-    hblur8(cur, H[(S)]);                                                                                      \
-    const int rc = r - 3; /* blur output row and FAST centre row */                                           \
-    if (rc >= by && rc < by + BH && rc < rows && store_ok) {                                                  \
-      unsigned o[4];                                                                                          \
-      _Pragma("unroll") for (int k = 0; k < 4; ++k)                                                           \
-        o[k] = vblur_pair(H[((S) + 1) % 7][k], H[((S) + 2) % 7][k], H[((S) + 3) % 7][k], H[((S) + 4) % 7][k], \
-                          H[((S) + 5) % 7][k], H[((S) + 6) % 7][k], H[(S)][k]);                               \
-      uint2 w;                                                                                                \
-      w.x = __byte_perm(o[0], o[1], 0x5410);                                                                  \
-      w.y = __byte_perm(o[2], o[3], 0x5410);                                                                  \
-      *reinterpret_cast<uint2*>(blur + (size_t) rc * a.map_pitch + x0) = w;                                   \
-    }                                                                                                         \
-    if (rc >= by - 1 && rc <= by + BH && rc >= 3 && rc < rows - 3) {                                          \
-      unsigned mb, md;                                                                                        \
-      pretest8(R[((S) + 1) % 7], R[((S) + 4) % 7], cur, t1, mb, md);                                          \
-      push_and_drain((mb | (md << 8)) & colmask, rc - (by - 1));                                              \
-    }                                                                                                         \
+  // one marching step per iteration: image row r enters the window at slot 6 (slot k holds row r - 6 + k).
+  // The window is rotated with register moves instead of unrolling the loop 7x: the unrolled kernel (57 KB of
+  // SASS) stalled on instruction fetch (ncu stall_no_instruction), 48 extra MOVs per row are cheaper.
+#pragma unroll 1
+  for (int step = 0; step < BH + 8; ++step) {
+    const int r = by - 4 + step;
+    const uint8_t* rowp = row_ptr(r);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      R[k] = R[k + 1];
+      H[k][0] = H[k + 1][0];
+      H[k][1] = H[k + 1][1];
+      H[k][2] = H[k + 1][2];
+      H[k][3] = H[k + 1][3];
+    }
+    RowRegs& cur = R[6];
+    load8_finish(nx, rowp, x0, cols, cur.a0, cur.a1);
+    cur.hl = __shfl_up_sync(FULL, cur.a1, 1);
+    cur.hr = __shfl_down_sync(FULL, cur.a0, 1);
+    if (edge) {
+      unsigned e0, e1;
+      load8_finish(ne, rowp, xe, cols, e0, e1);
+      if (lane == 0) cur.hl = e1; else cur.hr = e0;
+    }
+    if (step + 1 < BH + 8) {
+      const uint8_t* nrow = row_ptr(r + 1);
+      nx = load8_issue(nrow, x0, cols);
+      if (edge) ne = load8_issue(nrow, xe, cols);
+    }
+    hblur8(cur, H[6]);
+    const int rc = r - 3;  // blur output row and FAST centre row
+    if (rc >= by && rc < by + BH && rc < rows && store_ok) {
+      unsigned o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o[k] = vblur_pair(H[0][k], H[1][k], H[2][k], H[3][k], H[4][k], H[5][k], H[6][k]);
+      uint2 w;
+      w.x = __byte_perm(o[0], o[1], 0x5410);
+      w.y = __byte_perm(o[2], o[3], 0x5410);
+      *reinterpret_cast<uint2*>(blur + (size_t) rc * a.map_pitch + x0) = w;
+    }
+    if (rc >= by - 1 && rc <= by + BH && rc >= 3 && rc < rows - 3) {
+      unsigned mb, md;
+      pretest8(R[0], R[3], cur, t1, mb, md);
+      const unsigned long long q = push_and_drain(img, s_score, s_bits, s_queue, stride, by, thr, SP, BW,
+                                                  (mb | (md << 8)) & colmask,
+                                                  ((unsigned) (rc - (by - 1)) << 16) | (unsigned) x0, q_head, q_tail, false);
+      q_head = (unsigned) q;
+      q_tail = (unsigned) (q >> 32);
+    }
   }
-
-  for (int base = 0; base < BH + 8; base += 7) {
-    PSLAM_STEP(0) PSLAM_STEP(1) PSLAM_STEP(2) PSLAM_STEP(3) PSLAM_STEP(4) PSLAM_STEP(5) PSLAM_STEP(6)
-  }
-#undef PSLAM_STEP
   // drain what is left in the queue (< 32 entries)
-  {
-    const unsigned left = q_tail - q_head;
-    score_batch(s_queue[(q_head + lane) & (QCAP - 1)], (unsigned) lane < left);
-  }
+  push_and_drain(img, s_score, s_bits, s_queue, stride, by, thr, SP, BW, 0u, 0u, q_head, q_tail, true);
   __syncthreads();
 
   // ---- 3x3 NMS + ordered emission into the per-row keypoint lists ----
