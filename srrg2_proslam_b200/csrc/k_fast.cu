@@ -60,18 +60,21 @@ __device__ __forceinline__ Raw3 load8_issue(const uint8_t* __restrict__ row, int
   r.w2 = s ? __ldg(wp + 2) : 0u;  // when aligned the third word is not needed (and may be out of bounds)
   return r;
 }
-__device__ __forceinline__ void load8_finish(const Raw3& r, const uint8_t* __restrict__ row, int x, int cols,
+// `tail` (warp-uniform) is true only in warps whose pixel range reaches past the right image edge
+__device__ __forceinline__ void load8_finish(const Raw3& r, const uint8_t* __restrict__ row, int x, int cols, bool tail,
                                              unsigned& lo, unsigned& hi) {
   int xl = x < 0 ? 0 : x;
-  if (xl > cols - 8) xl = cols - 8;
+  if (tail && xl > cols - 8) xl = cols - 8;
   const unsigned sh = ((unsigned) (uintptr_t) (row + xl) & 3u) * 8u;
   lo = __funnelshift_r(r.w0, r.w1, sh);
   hi = __funnelshift_r(r.w1, r.w2, sh);
-  const int d = x - xl;  // > 0 only for lanes hanging over the right image edge: shift the valid bytes into place
-  if (d > 0) {
-    const unsigned long long v = d >= 8 ? 0ull : ((((unsigned long long) hi) << 32) | lo) >> (8 * d);
-    lo = (unsigned) v;
-    hi = (unsigned) (v >> 32);
+  if (tail) {
+    const int d = x - xl;  // > 0 only for lanes hanging over the right image edge: shift the valid bytes into place
+    if (d > 0) {
+      const unsigned long long v = d >= 8 ? 0ull : ((((unsigned long long) hi) << 32) | lo) >> (8 * d);
+      lo = (unsigned) v;
+      hi = (unsigned) (v >> 32);
+    }
   }
 }
 
@@ -273,6 +276,7 @@ fast_blur_rows_kernel(const K1Args a) {
   const int x0 = warp * 256 + lane * 8;
   const int xe = lane == 0 ? x0 - 8 : x0 + 8;  // strip-edge lanes fetch the neighbour strip's pixels themselves
   const bool edge = lane == 0 || lane == 31;
+  const bool tail = warp * 256 + 256 + 16 > cols;  // some lane of this warp loads beyond cols - 8
 
   for (int i = tid; i < ((BH + 2) * SP + (BH + 2) * BW * 4) / 4; i += blockDim.x) reinterpret_cast<unsigned*>(smem)[i] = 0u;
   __syncthreads();
@@ -319,12 +323,12 @@ fast_blur_rows_kernel(const K1Args a) {
       H[k][3] = H[k + 1][3];
     }
     RowRegs& cur = R[6];
-    load8_finish(nx, rowp, x0, cols, cur.a0, cur.a1);
+    load8_finish(nx, rowp, x0, cols, tail, cur.a0, cur.a1);
     cur.hl = __shfl_up_sync(FULL, cur.a1, 1);
     cur.hr = __shfl_down_sync(FULL, cur.a0, 1);
     if (edge) {
       unsigned e0, e1;
-      load8_finish(ne, rowp, xe, cols, e0, e1);
+      load8_finish(ne, rowp, xe, cols, tail, e0, e1);
       if (lane == 0) cur.hl = e1; else cur.hr = e0;
     }
     if (step + 1 < BH + 8) {
