@@ -141,6 +141,20 @@ int pslam_stereo_adaptor(pslam_ctx* ctx, const uint8_t* left, const uint8_t* rig
                          int stride, const pslam_extract_cfg* ecfg, const pslam_match_cfg* mcfg,
                          int capacity, float* uvuv, float* intensity, uint8_t* desc);
 
+/* ---- stage 1 + depth lookup: the RGB-D measurement adaptor ------------------------
+ * Replaces RawDataPreprocessorMonocularDepth::compute / _readDepth
+ *   (.../sensor_processing/raw_data_preprocessor_monocular_depth.cpp:50-180):
+ * extract features, read d = depth(rint(v), rint(u)), keep the point iff d > 0 with
+ * z = depth_scaling_factor_to_meters * d, preserving the cloud order (:166-179).
+ * depth_type: 0 = uint16 (TYPE_16UC1), 1 = float (TYPE_32FC1); stride in ELEMENTS.
+ * uvz: 3 floats per point.  *n_features_in_image receives the feature count before the depth
+ * filter (the reference warns when > 25 % are lost, :147-152).  Returns the point count. */
+int pslam_mono_depth_adaptor(pslam_ctx* ctx, const uint8_t* image, int rows, int cols, int stride,
+                             const void* depth, int depth_type, int depth_rows, int depth_cols,
+                             int depth_stride_elements, float depth_scaling_factor_to_meters,
+                             const pslam_extract_cfg* ecfg, int capacity, float* uvz, float* intensity,
+                             uint8_t* desc, int* n_features_in_image);
+
 /* Batched, device-resident: images 2p (left) and 2p+1 (right) of pair p.  Runs the whole
  * frame-independent part of the frontend for n_pairs pairs; results stay on the device
  * (stereo slots p) and can be fetched per pair.  Returns PSLAM_OK. */

@@ -1,0 +1,107 @@
+/* =============================================================================
+ * pslam_plugin.h -- C view of the host-side plugin mirror (libpslam_plugin.so).
+ *
+ * The reference wires its modules by class name in a BOSS `.conf`
+ * (configurations/kitti.conf, icl.conf, euroc.conf) and drives them through the
+ * srrg2 Configurable interface.  libpslam_plugin.so holds the
+ * C++ mirror of that interface for the frontend hot path (srrg2_proslam_b200/host/);
+ * these entry points expose it to non-C++ callers (the Python parity tests read like
+ * the reference's gtest files: load the .conf, look a module up by name, set PARAMs,
+ * hand it clouds / images, call compute()).  All arithmetic happens in libpslam_cuda.so.
+ *
+ * Every function returns 0 / a count on success and a negative value on failure;
+ * psp_last_error() then holds the text of the std::runtime_error the C++ module threw
+ * (the same texts the reference throws).
+ * ========================================================================== */
+#ifndef PSLAM_PLUGIN_H
+#define PSLAM_PLUGIN_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct psp_manager psp_manager; /* ConfigurableManager */
+typedef struct psp_module psp_module;   /* a Configurable owned by its manager */
+
+const char* psp_last_error(void);
+int psp_set_device(int device);
+
+/* ---- ConfigurableManager: srrg2_core::ConfigurableManager::read / getByName / create ---------- */
+psp_manager* psp_manager_create(void);
+void psp_manager_destroy(psp_manager* m);
+int psp_manager_read(psp_manager* m, const char* conf_path);
+int psp_manager_read_string(psp_manager* m, const char* conf_text);
+/* writes the named modules and everything they link to (all modules when n_names == 0) */
+int psp_manager_write(psp_manager* m, const char* conf_path, int n_names, const char* const* names);
+int psp_manager_count(psp_manager* m);
+psp_module* psp_manager_at(psp_manager* m, int index);
+psp_module* psp_manager_get_by_name(psp_manager* m, const char* name);
+psp_module* psp_manager_create_module(psp_manager* m, const char* class_name, const char* name);
+/* 1 when `class_name` is backed by a CUDA class of this library, 0 when it would load as a generic module */
+int psp_class_is_registered(const char* class_name);
+
+/* ---- Configurable: class name, PARAM access, links ------------------------------------------ */
+const char* psp_module_class_name(psp_module* c);
+const char* psp_module_name(psp_module* c);
+int psp_module_is_generic(psp_module* c);
+int psp_module_has_param(psp_module* c, const char* param);
+int psp_module_set_number(psp_module* c, const char* param, double value);
+int psp_module_get_number(psp_module* c, const char* param, double* value);
+int psp_module_set_string(psp_module* c, const char* param, const char* value);
+const char* psp_module_get_string(psp_module* c, const char* param);
+int psp_module_set_numbers(psp_module* c, const char* param, int n, const double* values);
+int psp_module_get_numbers(psp_module* c, const char* param, int capacity, double* values);
+int psp_module_set_link(psp_module* c, const char* param, psp_module* target_or_null);
+psp_module* psp_module_get_link(psp_module* c, const char* param);
+
+/* ---- IntensityFeatureExtractorBinned{2D,3D}: setFeatures + compute(image) -------------------- */
+int psp_extractor_compute(psp_module* extractor, const uint8_t* image, int rows, int cols, int stride,
+                          const uint8_t* mask_or_null, int capacity, float* xy, float* intensity, uint8_t* desc);
+
+/* ---- RawDataPreprocessorStereoProjective: setRawData + setMeas + compute ---------------------
+ * uvuv: 4 floats per point.  *status receives the adaptor's _status (0 Error, 1 Initializing, 2 Ready). */
+int psp_stereo_adaptor_compute(psp_module* adaptor, const uint8_t* left, const uint8_t* right, int rows, int cols,
+                               int stride, int capacity, float* uvuv, float* intensity, uint8_t* desc, int* status);
+/* ---- RawDataPreprocessorMonocularDepth (depth_type 0 = uint16, 1 = float) -------------------- */
+int psp_mono_depth_adaptor_compute(psp_module* adaptor, const uint8_t* image, int rows, int cols, int stride,
+                                   const void* depth, int depth_type, int depth_rows, int depth_cols,
+                                   int depth_stride_elements, int capacity, float* uvz, float* intensity,
+                                   uint8_t* desc, int* status);
+
+/* ---- CorrespondenceFinder*: setFixed / setMoving / setLocalMapInSensor / compute --------------
+ * Clouds are copied into the module (the reference holds non-owning pointers; the copy keeps the C
+ * interface free of lifetime rules).  coords: n x dim floats, desc: n x 32 bytes. */
+int psp_finder_set_fixed(psp_module* finder, int n, int dim, const float* coords, const uint8_t* desc);
+int psp_finder_set_moving(psp_module* finder, int n, int dim, const float* coords, const uint8_t* desc);
+int psp_finder_set_local_map_in_sensor(psp_module* finder, const float* pose12);
+int psp_finder_compute(psp_module* finder, int capacity, int* fixed_idx, int* moving_idx, float* response);
+/* projective finders: dynamic state (projective_base.h:82-97,130-154): radius, descriptor distance,
+ * iteration, converged flag, number of device searches so far */
+int psp_projective_finder_state(psp_module* finder, int* search_radius_pixels, float* descriptor_distance,
+                                int* current_iteration, int* has_converged, int* number_of_searches);
+int psp_projective_finder_set_state(psp_module* finder, int search_radius_pixels, float descriptor_distance);
+/* camera matrix of a PointIntensityDescriptor3fProjectorPinhole (set at runtime from camera info) */
+int psp_projector_set_camera_matrix(psp_module* projector, const float* K9);
+
+/* ---- MultiAligner3DQR + AlignerSliceProcessorProjective{,Depth,Stereo} ------------------------
+ * fixed: the adapted measurements (dim 4 stereo / 3 depth / 2 mono); moving: 3-D scene points.
+ * n_opt_or_null: statistics().numberOfOptimizations() per moving point. */
+int psp_aligner_set_fixed(psp_module* aligner, int n, int dim, const float* coords, const uint8_t* desc);
+int psp_aligner_set_moving(psp_module* aligner, int n, const float* xyz, const uint8_t* desc, const int* n_opt_or_null);
+int psp_aligner_set_moving_in_fixed(psp_module* aligner, const float* pose12);
+/* platform transform used by the stereo slice: translation of the left camera in the right camera [m] */
+int psp_aligner_set_left_camera_in_right(psp_module* aligner, const float* t3);
+/* returns the aligner status (0 Fail, 1 Success, 2 NotEnoughCorrespondences, 3 NotEnoughInliers) */
+int psp_aligner_compute(psp_module* aligner, double* moving_in_fixed12, int* iterations, int* num_correspondences,
+                        int* num_inliers, double* chi);
+/* per-iteration stats of the last compute: rows of (num_correspondences, num_inliers, num_outliers, chi) */
+int psp_aligner_iteration_stats(psp_module* aligner, int capacity, double* rows4);
+/* correspondences of the projective slice after the last compute */
+int psp_aligner_correspondences(psp_module* aligner, int capacity, int* fixed_idx, int* moving_idx, float* response);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSLAM_PLUGIN_H */

@@ -126,6 +126,53 @@ orb_describe_kernel(const uint8_t* __restrict__ blur, int map_pitch, long long m
   }
 }
 
+
+// ---- monocular + depth adaptor: order-preserving compaction of the features with a valid depth ---------------
+// Replaces RawDataPreprocessorMonocularDepth::_readDepth (.../sensor_processing/raw_data_preprocessor_monocular_depth.cpp:157-180):
+// d = depth(rint(v), rint(u)) converted to float; keep the point iff d > 0; z = scale * d (one fp32 multiply).
+// One CTA per image; chunks of MD_THREADS features, block scan keeps the cloud order.
+constexpr int MD_THREADS = 256;
+__global__ void __launch_bounds__(MD_THREADS)
+mono_depth_kernel(const void* __restrict__ depth, int depth_type, int depth_rows, int depth_cols, int depth_stride,
+                  float scale, const float2* __restrict__ xy, const float* __restrict__ inten,
+                  const uint32_t* __restrict__ desc, const int* __restrict__ count, int max_features, int slot,
+                  float* __restrict__ out_uvz, float* __restrict__ out_inten, uint32_t* __restrict__ out_desc,
+                  int* __restrict__ out_count) {
+  __shared__ int s_warp[33];
+  const size_t base = (size_t) slot * max_features;
+  const int n = count[slot];
+  int running = 0;
+  for (int b = 0; b < n; b += MD_THREADS) {
+    const int i = b + threadIdx.x;
+    float d = 0.f;
+    float2 p = make_float2(0.f, 0.f);
+    if (i < n) {
+      p = xy[base + i];
+      const int r = (int) rintf(p.y), c = (int) rintf(p.x);
+      if (r >= 0 && r < depth_rows && c >= 0 && c < depth_cols) {
+        const size_t o = (size_t) r * depth_stride + c;
+        d = depth_type == 0 ? (float) reinterpret_cast<const unsigned short*>(depth)[o] : reinterpret_cast<const float*>(depth)[o];
+      }
+    }
+    const int keep = (i < n && d > 0.f) ? 1 : 0;
+    int total;
+    const int off = block_exclusive_scan<MD_THREADS>(keep, s_warp, &total);
+    if (keep) {
+      const size_t o = (size_t) running + off;
+      out_uvz[3 * o] = p.x;
+      out_uvz[3 * o + 1] = p.y;
+      out_uvz[3 * o + 2] = __fmul_rn(scale, d);
+      out_inten[o] = inten[base + i];
+      const uint4* src = reinterpret_cast<const uint4*>(desc + (base + i) * 8);
+      uint4* dst = reinterpret_cast<uint4*>(out_desc + o * 8);
+      dst[0] = src[0];
+      dst[1] = src[1];
+    }
+    running += total;
+  }
+  if (threadIdx.x == 0) *out_count = running;
+}
+
 }  // namespace
 
 // ---- host-side launchers -----------------------------------------------------------------------
@@ -153,5 +200,15 @@ int pslam_k_describe(pslam_ctx* ctx, int n_images, int slot_base) {
     ctx->d_blur, ctx->map_pitch, (long long) ctx->map_slot, ctx->d_xy, ctx->d_count,
     ctx->lim.max_features, slot_base, ctx->d_desc);
   PSLAM_LAUNCH_CHECK(ctx, "orb_describe_kernel");
+  return PSLAM_OK;
+}
+
+int pslam_k_mono_depth(pslam_ctx* ctx, const void* d_depth, int depth_type, int depth_rows, int depth_cols,
+                       int depth_stride, float scale, int slot, float* d_uvz, float* d_inten, uint32_t* d_desc,
+                       int* d_count) {
+  mono_depth_kernel<<<1, MD_THREADS, 0, ctx->stream>>>(d_depth, depth_type, depth_rows, depth_cols, depth_stride, scale,
+                                                      ctx->d_xy, ctx->d_inten, ctx->d_desc, ctx->d_count,
+                                                      ctx->lim.max_features, slot, d_uvz, d_inten, d_desc, d_count);
+  PSLAM_LAUNCH_CHECK(ctx, "mono_depth_kernel");
   return PSLAM_OK;
 }

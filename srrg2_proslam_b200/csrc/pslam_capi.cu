@@ -586,6 +586,54 @@ int pslam_stereo_adaptor(pslam_ctx* ctx, const uint8_t* left, const uint8_t* rig
   return n;
 }
 
+
+int pslam_mono_depth_adaptor(pslam_ctx* ctx, const uint8_t* image, int rows, int cols, int stride, const void* depth,
+                             int depth_type, int depth_rows, int depth_cols, int depth_stride_elements,
+                             float depth_scaling_factor_to_meters, const pslam_extract_cfg* ecfg, int capacity,
+                             float* uvz, float* intensity, uint8_t* desc, int* n_features_in_image) {
+  if (!ctx || !image || !depth) return PSLAM_E_INVALID;
+  int rc = validate_extract(ctx, 1, rows, cols, ecfg);
+  if (rc) return rc;
+  if (depth_type != 0 && depth_type != 1)
+    return pslam_set_error(ctx, PSLAM_E_INVALID, "RawDataPreprocessorMonocularDepth::compute|ERROR: unknown depth image type", cudaSuccess);
+  if (depth_rows <= 0)
+    return pslam_set_error(ctx, PSLAM_E_INVALID, "RawDataPreprocessorMonocularDepth::compute|ERROR: depth image has zero rows", cudaSuccess);
+  if (depth_cols <= 0 || depth_stride_elements < depth_cols)
+    return pslam_set_error(ctx, PSLAM_E_INVALID, "RawDataPreprocessorMonocularDepth::compute|ERROR: depth image has zero columns", cudaSuccess);
+  PSLAM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const size_t esz = depth_type == 0 ? 2 : 4;
+  const size_t depth_bytes = ((size_t) depth_rows * depth_stride_elements * esz + 255) & ~(size_t) 255;
+  const size_t mf = (size_t) ctx->lim.max_features;
+  const size_t need = depth_bytes + mf * (12 + 4 + 32) + 256;
+  if (need > ctx->scratch_bytes) return pslam_set_error(ctx, PSLAM_E_CAPACITY, "mono depth adaptor: depth image exceeds the scratch buffer", cudaSuccess);
+  uint8_t* s = ctx->d_scratch;
+  void* d_depth = s;
+  float* d_uvz = reinterpret_cast<float*>(s + depth_bytes);
+  float* d_in = d_uvz + 3 * mf;
+  uint32_t* d_de = reinterpret_cast<uint32_t*>(d_in + mf);
+  int* d_n = reinterpret_cast<int*>(d_de + 8 * mf);
+  if ((rc = upload_images(ctx, image, 1, rows, cols, stride, 0))) return rc;
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_depth, depth, (size_t) depth_rows * depth_stride_elements * esz, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = run_extract(ctx, ctx->d_images, (long long) ctx->img_slot, 1, rows, cols, ctx->img_pitch, ecfg, nullptr))) return rc;
+  if ((rc = pslam_k_mono_depth(ctx, d_depth, depth_type, depth_rows, depth_cols, depth_stride_elements,
+                               depth_scaling_factor_to_meters, 0, d_uvz, d_in, d_de, d_n))) return rc;
+  if ((rc = check_flags(ctx))) return rc;
+  int* h = reinterpret_cast<int*>(ctx->h_pinned);
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(h, d_n, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(h + 1, ctx->d_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  const int n = h[0];
+  if (n_features_in_image) *n_features_in_image = h[1];
+  const int m = n < capacity ? n : capacity;
+  if (m > 0) {
+    if (uvz) PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(uvz, d_uvz, sizeof(float) * 3 * m, cudaMemcpyDeviceToHost, ctx->stream));
+    if (intensity) PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(intensity, d_in, sizeof(float) * m, cudaMemcpyDeviceToHost, ctx->stream));
+    if (desc) PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(desc, d_de, 32 * (size_t) m, cudaMemcpyDeviceToHost, ctx->stream));
+    PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return n;
+}
+
 // ---- stage 2b -----------------------------------------------------------------------------------
 static int bf_upload(pslam_ctx* ctx, int nf, const uint8_t* df, int nm, const uint8_t* dm,
                      uint32_t** d_f, uint32_t** d_m, size_t* used) {

@@ -1,0 +1,725 @@
+// pslam_plugin.cpp -- see pslam_plugin.hpp.  All arithmetic of the hot path runs in libpslam_cuda.so.
+#include "pslam_plugin.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <mutex>
+
+namespace pslam_host {
+
+// ---- small isometry helpers (control flow only: convergence test of the projective finder) --------------------
+Isometry3f Isometry3f::inverse() const {
+  Isometry3f r;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) r.m[4 * i + j] = m[4 * j + i];
+  for (int i = 0; i < 3; ++i) r.m[4 * i + 3] = -(r.m[4 * i] * m[3] + r.m[4 * i + 1] * m[7] + r.m[4 * i + 2] * m[11]);
+  return r;
+}
+Isometry3f Isometry3f::operator*(const Isometry3f& o) const {
+  Isometry3f r;
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j)
+      r.m[4 * i + j] = m[4 * i] * o.m[j] + m[4 * i + 1] * o.m[4 + j] + m[4 * i + 2] * o.m[8 + j];
+    r.m[4 * i + 3] = m[4 * i] * o.m[3] + m[4 * i + 1] * o.m[7] + m[4 * i + 2] * o.m[11] + m[4 * i + 3];
+  }
+  return r;
+}
+void t2tnq(const Isometry3f& T, float v6[6]) {
+  v6[0] = T.m[3];
+  v6[1] = T.m[7];
+  v6[2] = T.m[11];
+  // rotation matrix -> unit quaternion (Eigen's branch structure), then w >= 0 and the vector part
+  const float r00 = T.m[0], r01 = T.m[1], r02 = T.m[2], r10 = T.m[4], r11 = T.m[5], r12 = T.m[6], r20 = T.m[8],
+              r21 = T.m[9], r22 = T.m[10];
+  float w, x, y, z;
+  float t = r00 + r11 + r22;
+  if (t > 0.f) {
+    t = std::sqrt(t + 1.f);
+    w = 0.5f * t;
+    t = 0.5f / t;
+    x = (r21 - r12) * t;
+    y = (r02 - r20) * t;
+    z = (r10 - r01) * t;
+  } else {
+    int i = 0;
+    if (r11 > r00) i = 1;
+    if (r22 > (i == 0 ? r00 : r11)) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    auto R = [&](int a, int b) { return T.m[4 * a + b]; };
+    t = std::sqrt(R(i, i) - R(j, j) - R(k, k) + 1.f);
+    float q[3];
+    q[i] = 0.5f * t;
+    t = 0.5f / t;
+    w = (R(k, j) - R(j, k)) * t;
+    q[j] = (R(j, i) + R(i, j)) * t;
+    q[k] = (R(k, i) + R(i, k)) * t;
+    x = q[0];
+    y = q[1];
+    z = q[2];
+  }
+  const float n = std::sqrt(w * w + x * x + y * y + z * z);
+  const float s = (w < 0.f ? -1.f : 1.f) / n;
+  v6[3] = x * s;
+  v6[4] = y * s;
+  v6[5] = z * s;
+}
+
+// ---- device context ---------------------------------------------------------------------------------------------
+namespace {
+std::mutex g_mutex;
+pslam_ctx* g_ctx = nullptr;
+int g_device = 0, g_rows = 0, g_cols = 0;
+constexpr int kMaxFeatures = 8192;
+}  // namespace
+
+void PslamDevice::setDevice(int device) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  g_device = device;
+}
+
+void PslamDevice::release() {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  if (g_ctx) pslam_destroy(g_ctx);
+  g_ctx = nullptr;
+  g_rows = g_cols = 0;
+}
+
+pslam_ctx* PslamDevice::context(int rows, int cols) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  if (g_ctx && rows <= g_rows && cols <= g_cols) return g_ctx;
+  const int nr = std::max({rows, g_rows, 480}), nc = std::max({cols, g_cols, 1280});
+  if (g_ctx) pslam_destroy(g_ctx);
+  g_ctx = nullptr;
+  pslam_limits lim{};
+  lim.max_images = 2;
+  lim.max_rows = nr;
+  lim.max_cols = nc;
+  lim.max_features = kMaxFeatures;
+  lim.max_raw_per_bin = 32768;
+  lim.max_bins = 64;
+  lim.work_images = 2;
+  pslam_ctx* ctx = nullptr;
+  const int rc = pslam_create(g_device, &lim, &ctx);
+  if (rc != PSLAM_OK) {
+    std::string msg = std::string("PslamDevice::context|ERROR: no usable CUDA device (there is no CPU fallback): ") +
+                      (ctx ? pslam_last_error(ctx) : "pslam_create failed");
+    if (ctx) pslam_destroy(ctx);
+    throw std::runtime_error(msg);
+  }
+  g_ctx = ctx;
+  g_rows = nr;
+  g_cols = nc;
+  return g_ctx;
+}
+
+void PslamDevice::check(int rc, const char* where) {
+  if (rc >= 0) return;
+  const char* e = g_ctx ? pslam_last_error(g_ctx) : "";
+  // PSLAM_E_INVALID carries the reference's own std::runtime_error text
+  if (rc == PSLAM_E_INVALID && e && *e) throw std::runtime_error(e);
+  throw std::runtime_error(std::string(where) + "|ERROR: " + (e && *e ? e : "CUDA path failed") + " (code " + std::to_string(rc) + ")");
+}
+
+float Solver::damping() const {
+  auto gn = std::dynamic_pointer_cast<IterationAlgorithmGN>(param_algorithm.value());
+  return gn ? gn->param_damping.value() : 0.f;
+}
+
+// ---- feature extractor ------------------------------------------------------------------------------------------
+void IntensityFeatureExtractorBinnedCUDA::init() {
+  if (!_config_changed) return;
+  // binned.cpp:13-28
+  if (param_number_of_detectors_vertical.value() <= 0)
+    throw std::runtime_error("IntensityFeatureExtractor::init|ERROR: invalid number of vertical detectors (check configuration!)");
+  if (param_number_of_detectors_horizontal.value() <= 0)
+    throw std::runtime_error("IntensityFeatureExtractor::init|ERROR: invalid number of horizontal detectors (check configuration!)");
+  if (_image_rows == 0)
+    throw std::runtime_error("IntensityFeatureExtractor::init|ERROR: invalid number of image rows (check configuration!)");
+  if (_image_cols == 0)
+    throw std::runtime_error("IntensityFeatureExtractor::init|ERROR: invalid number of image cols (check configuration!)");
+  // base.cpp:105-176: the CUDA path implements the detector / descriptor pair every shipped configuration uses
+  const std::string& det = param_detector_type.value();
+  if (det != "FAST") {
+    if (det == "BRISK-512" || det == "ORB-256" || det == "MSER" || det == "GFTT")
+      throw std::runtime_error("IntensityFeatureExtractor::_setDetector|ERROR: detector type not available in the CUDA path: " + det);
+    throw std::runtime_error("IntensityFeatureExtractor::_setDetector|ERROR: unknown detector type chosen: " + det);
+  }
+  const std::string& desc = param_descriptor_type.value();
+  if (desc != "ORB-256") {
+    if (desc == "BRIEF-256" || desc == "BRISK-512" || desc == "FREAK-512")
+      throw std::runtime_error("IntensityFeatureExtractor::_setDescriptor|ERROR: descriptor type not available in the CUDA path: " + desc);
+    throw std::runtime_error("IntensityFeatureExtractor::_setDescriptor|ERROR: unknown descriptor type chosen: " + desc);
+  }
+  std::cerr << "IntensityFeatureExtractorBinned_::init|initialized for image sources [" << _image_rows << " x " << _image_cols
+            << "] with detector grid [" << param_number_of_detectors_vertical.value() << " x "
+            << param_number_of_detectors_horizontal.value() << "]" << std::endl;
+  _config_changed = false;
+}
+
+pslam_extract_cfg IntensityFeatureExtractorBinnedCUDA::cudaConfig() const {
+  pslam_extract_cfg c{};
+  c.detector_threshold = param_detector_threshold.value();
+  c.enable_non_maximum_suppression = param_enable_non_maximum_suppression.value() ? 1 : 0;
+  c.target_number_of_keypoints = param_target_number_of_keypoints.value();
+  c.number_of_detectors_horizontal = param_number_of_detectors_horizontal.value();
+  c.number_of_detectors_vertical = param_number_of_detectors_vertical.value();
+  return c;
+}
+
+void IntensityFeatureExtractorBinnedCUDA::prepare(int rows, int cols) {
+  if ((size_t) rows != _image_rows || (size_t) cols != _image_cols) {  // base.cpp:60-66: re-init on new dimensions
+    _image_rows = rows;
+    _image_cols = cols;
+    _config_changed = true;
+  }
+  init();
+}
+
+void IntensityFeatureExtractorBinnedCUDA::compute(const ImageView& image) {
+  if (!_features) throw std::runtime_error("IntensityFeatureExtractor::compute|ERROR: features not set");
+  prepare(image.rows, image.cols);
+  pslam_ctx* ctx = PslamDevice::context(image.rows, image.cols);
+  const pslam_extract_cfg cfg = cudaConfig();
+  std::vector<float> xy(2 * (size_t) kMaxFeatures), response(kMaxFeatures);
+  PointIntensityDescriptorCloud& out = *_features;
+  out.dim = _point_dim;
+  out.number_of_optimizations.clear();
+  out.resize(kMaxFeatures);
+  const int n = pslam_extract_binned(ctx, image.data, image.rows, image.cols, image.stride, &cfg,
+                                     _mask_set ? _mask.data : nullptr, kMaxFeatures, xy.data(), response.data(),
+                                     out.intensity.data(), out.descriptor.data());
+  if (n < 0) out.resize(0);
+  PslamDevice::check(n, "IntensityFeatureExtractor::compute");
+  out.resize(n);
+  for (int i = 0; i < n; ++i) {  // AoS fill of base.cpp:73-84: coordinates(0) = x, (1) = y, remaining dimensions 0
+    float* p = out.point(i);
+    p[0] = xy[2 * i];
+    p[1] = xy[2 * i + 1];
+    for (int d = 2; d < _point_dim; ++d) p[d] = 0.f;
+  }
+}
+
+// ---- descriptor based finders -----------------------------------------------------------------------------------
+void CorrespondenceFinderDescriptorBasedBruteforceCUDA::_preCompute() {
+  if (!_fixed) throw std::runtime_error("CorrespondenceFinderDescriptorBased::compute|ERROR: fixed not set");
+  if (!_moving) throw std::runtime_error("CorrespondenceFinderDescriptorBased::compute|ERROR: moving not set");
+  if (!_correspondences) throw std::runtime_error("CorrespondenceFinderDescriptorBased::compute|ERROR: correspondences not set");
+  if (_fixed->empty()) std::cerr << "CorrespondenceFinderDescriptorBased::compute|WARNING: no points in fixed" << std::endl;
+  if (_moving->empty()) std::cerr << "CorrespondenceFinderDescriptorBased::compute|WARNING: no points in moving" << std::endl;
+}
+
+void CorrespondenceFinderDescriptorBasedBruteforceCUDA::_postCompute() {
+  _fixed_changed_flag = false;
+  _moving_changed_flag = false;
+  if (_correspondences->empty())
+    std::cerr << "CorrespondenceFinderDescriptorBased::compute|WARNING: no correspondences found" << std::endl;
+}
+
+namespace {
+void fill(CorrespondenceVector& out, int n, const std::vector<int>& f, const std::vector<int>& m, const std::vector<float>& d) {
+  out.resize(n);
+  for (int i = 0; i < n; ++i) out[i] = Correspondence{f[i], m[i], d[i]};
+}
+// 2-D image coordinates of a cloud (epipolar finder: truncated (row, col) = (y, x), epipolar_impl.cpp:8-20)
+std::vector<float> xy_of(const PointIntensityDescriptorCloud& c) {
+  std::vector<float> xy(2 * c.size());
+  for (size_t i = 0; i < c.size(); ++i) {
+    xy[2 * i] = c.point(i)[0];
+    xy[2 * i + 1] = c.point(i)[1];
+  }
+  return xy;
+}
+}  // namespace
+
+void CorrespondenceFinderDescriptorBasedBruteforceCUDA::compute() {
+  _preCompute();
+  if (!_fixed_changed_flag && !_moving_changed_flag) return;  // bruteforce_impl.cpp:13-15
+  pslam_ctx* ctx = PslamDevice::context();
+  pslam_match_cfg cfg{};
+  cfg.maximum_descriptor_distance = param_maximum_descriptor_distance.value();
+  cfg.maximum_distance_ratio_to_second_best = param_maximum_distance_ratio_to_second_best.value();
+  const int cap = (int) std::min(_fixed->size(), _moving->size()) + 1;
+  std::vector<int> f(cap), m(cap);
+  std::vector<float> d(cap);
+  const int n = pslam_match_bruteforce(ctx, (int) _fixed->size(), _fixed->descriptor.data(), (int) _moving->size(),
+                                       _moving->descriptor.data(), &cfg, cap, f.data(), m.data(), d.data());
+  PslamDevice::check(n, "CorrespondenceFinderDescriptorBasedBruteforce::compute");
+  fill(*_correspondences, n, f, m, d);
+  _postCompute();
+}
+
+pslam_match_cfg CorrespondenceFinderDescriptorBasedEpipolarCUDA::cudaConfig() const {
+  pslam_match_cfg cfg{};
+  cfg.maximum_descriptor_distance = param_maximum_descriptor_distance.value();
+  cfg.maximum_distance_ratio_to_second_best = param_maximum_distance_ratio_to_second_best.value();
+  cfg.maximum_disparity_pixels = (int) param_maximum_disparity_pixels.value();
+  cfg.epipolar_line_thickness_pixels = (int) param_epipolar_line_thickness_pixels.value();
+  return cfg;
+}
+
+void CorrespondenceFinderDescriptorBasedEpipolarCUDA::compute() {
+  _preCompute();
+  if (!_fixed_changed_flag && !_moving_changed_flag) return;  // epipolar_impl.cpp:49-51
+  pslam_ctx* ctx = PslamDevice::context();
+  const pslam_match_cfg cfg = cudaConfig();
+  const std::vector<float> xf = xy_of(*_fixed), xm = xy_of(*_moving);
+  const int cap = (int) _fixed->size() + 1;
+  std::vector<int> f(cap), m(cap);
+  std::vector<float> d(cap);
+  const int n = pslam_match_epipolar(ctx, (int) _fixed->size(), xf.data(), _fixed->descriptor.data(), (int) _moving->size(),
+                                     xm.data(), _moving->descriptor.data(), &cfg, cap, f.data(), m.data(), d.data());
+  PslamDevice::check(n, "CorrespondenceFinderDescriptorBasedEpipolar::compute");
+  fill(*_correspondences, n, f, m, d);
+  _postCompute();
+}
+
+// ---- projective finder: host state machine (projective_base_impl.cpp:104-293), device search + filter ---------
+void CorrespondenceFinderProjectiveCUDA::compute() {
+  _preCompute();
+  pslam_ctx* ctx = PslamDevice::context();
+  if (_fixed_changed_flag || _moving_changed_flag || _config_changed) {
+    const bool fixed_changed = _fixed_changed_flag, moving_changed = _moving_changed_flag;
+    _fixed_changed_flag = false;
+    _moving_changed_flag = false;
+    if ((_search_radius_pixels == 0 && _descriptor_distance == 0) || _config_changed) {
+      _search_radius_pixels = param_maximum_search_radius_pixels.value();
+      _descriptor_distance = param_minimum_descriptor_distance.value();
+      std::cerr << "CorrespondenceFinderProjective::compute|initialized search radius (px): " << _search_radius_pixels
+                << " descriptor distance: " << _descriptor_distance
+                << " maximum distance ratio: " << param_maximum_distance_ratio_to_second_best.value() << std::endl;
+    }
+    _has_converged = false;
+    _current_iteration = 0;
+    _local_map_in_sensor_previous.setIdentity();
+    // _initializeDatabase (square_impl.cpp:7-31): the row-sorted lattice is built and cached on the device
+    if (fixed_changed || _config_changed)
+      PslamDevice::check(pslam_projective_set_fixed(ctx, (int) _fixed->size(), _fixed->coordinates.data(), _fixed->dim,
+                                                    _fixed->descriptor.data()),
+                         "CorrespondenceFinderProjective::compute");
+    if (moving_changed || _config_changed) {
+      if (_moving->dim != 3) throw std::runtime_error("CorrespondenceFinderProjective::compute|ERROR: moving cloud must be 3D");
+      PslamDevice::check(pslam_projective_set_moving(ctx, (int) _moving->size(), _moving->coordinates.data(),
+                                                     _moving->descriptor.data()),
+                         "CorrespondenceFinderProjective::compute");
+    }
+    _config_changed = false;
+  }
+  if (_has_converged) {  // correspondences are not touched (:137-141)
+    _postCompute();
+    return;
+  }
+  if (!param_projector.value()) throw std::runtime_error("CorrespondenceFinderProjective::compute|ERROR: projector not set");
+  const ProjectorPinhole& projector = *param_projector.value();
+
+  // periodically re-project; always for iterations 0 and 1 (:162-178)
+  if (!(_current_iteration % param_number_of_solver_iterations_per_projection.value() == 0 || _current_iteration == 1)) {
+    _local_map_in_sensor_previous = _local_map_in_sensor;
+    ++_current_iteration;
+    _postCompute();
+    return;
+  }
+  float v6[6];
+  t2tnq(_local_map_in_sensor.inverse() * _local_map_in_sensor_previous, v6);  // cameraPose() * previous (:181-183)
+  float n2 = 0;
+  for (float v : v6) n2 += v * v;
+  const float estimate_change_norm = std::sqrt(n2);
+  _local_map_in_sensor_previous = _local_map_in_sensor;
+
+  // projector->compute + _findNearestNeighbors + _filterCorrespondences: one device call
+  pslam_projective_cfg cfg{};
+  for (int i = 0; i < 9; ++i) cfg.K[i] = projector.cameraMatrix()[i];
+  cfg.canvas_rows = (int) projector.param_canvas_rows.value();
+  cfg.canvas_cols = (int) projector.param_canvas_cols.value();
+  cfg.range_min = projector.param_range_min.value();
+  cfg.range_max = projector.param_range_max.value();
+  cfg.shape = _shape;
+  cfg.search_radius_pixels = (int) _search_radius_pixels;
+  cfg.descriptor_distance = _descriptor_distance;
+  cfg.maximum_distance_ratio_to_second_best = param_maximum_distance_ratio_to_second_best.value();
+  const int cap = (int) _fixed->size() + 1;
+  std::vector<int> f(cap), m(cap);
+  std::vector<float> d(cap);
+  int n_projected = 0;
+  const int n = pslam_projective_match(ctx, (int) _fixed->size(), (int) _moving->size(), _local_map_in_sensor.m, &cfg, cap,
+                                       f.data(), m.data(), d.data(), &n_projected);
+  PslamDevice::check(n, "CorrespondenceFinderProjective::compute");
+  ++_number_of_searches;
+  if (n_projected == 0) std::cerr << "CorrespondenceFinderProjective::compute|WARNING: all projections failed" << std::endl;
+
+  const float matching_ratio = static_cast<float>(n) / _fixed->size();
+  if (matching_ratio < param_minimum_matching_ratio.value()) {
+    std::cerr << "CorrespondenceFinderProjective::compute|low matching ratio: " << matching_ratio << " (" << n << "/"
+              << _fixed->size() << ") target: " << param_minimum_matching_ratio.value() << std::endl;
+    if (_search_radius_pixels < param_maximum_search_radius_pixels.value() ||
+        _descriptor_distance > param_minimum_descriptor_distance.value()) {
+      _search_radius_pixels = param_maximum_search_radius_pixels.value();
+      _descriptor_distance = param_minimum_descriptor_distance.value();
+      std::cerr << "CorrespondenceFinderProjective|WARNING: bad initial guess - triggering internal repeat with increased search radius"
+                << std::endl;
+      if (matching_ratio == 0) {
+        std::cerr << "CorrespondenceFinderProjective|WARNING: complete track loss - fallback to identity motion guess" << std::endl;
+        _local_map_in_sensor.setIdentity();
+        _current_iteration = 0;
+      } else {
+        ++_current_iteration;
+      }
+      return compute();  // recursion terminates as soon as the thresholds are saturated
+    }
+  }
+  fill(*_correspondences, n, f, m, d);
+  if (estimate_change_norm < param_maximum_estimate_change_norm_for_convergence.value() &&
+      _current_iteration > param_minimum_number_of_iterations.value()) {
+    _has_converged = true;
+    if (matching_ratio > param_minimum_matching_ratio.value()) {
+      _search_radius_pixels = std::max<size_t>(_search_radius_pixels - param_search_radius_step_size_pixels.value(),
+                                               param_minimum_search_radius_pixels.value());
+      _descriptor_distance = std::min(_descriptor_distance + param_descriptor_distance_step_size_pixels.value(),
+                                      param_maximum_descriptor_distance.value());
+    }
+  }
+  ++_current_iteration;
+  _postCompute();
+}
+
+// ---- stereo adaptor ---------------------------------------------------------------------------------------------
+RawDataPreprocessorStereoProjectiveCUDA::RawDataPreprocessorStereoProjectiveCUDA() {}
+
+bool RawDataPreprocessorStereoProjectiveCUDA::setRawData(const ImageView& left, const ImageView& right) {
+  _raw_set = false;
+  _status = Error;
+  if (!left.data)
+    throw std::runtime_error("RawDataPreprocessorStereoProjective::setMeasurement|ERROR, ImageMessage not found - topic [ " +
+                             param_topic_camera_left.value() + " ]");
+  if (!right.data)
+    throw std::runtime_error("RawDataPreprocessorStereoProjective::setMeasurement|ERROR, ImageMessage not found - topic [ " +
+                             param_topic_camera_right.value() + " ]");
+  _left = left;
+  _right = right;
+  _raw_set = true;
+  _raw_data_changed_flag = true;
+  _status = Initializing;
+  return true;
+}
+
+void RawDataPreprocessorStereoProjectiveCUDA::compute() {
+  _status = Error;
+  if (!_raw_set) throw std::runtime_error("RawDataPreprocessorStereoProjective::compute|measurement not set");
+  if (!_raw_data_changed_flag) {
+    _status = Ready;
+    return;
+  }
+  if (!_meas) throw std::runtime_error("RawDataPreprocessorStereoProjective::compute|destination buffer not set");
+  _meas->clear();
+  if (!param_feature_extractor.value() || !param_feature_extractor_right.value() || !param_correspondence_finder.value())
+    throw std::runtime_error("RawDataPreprocessorStereoProjective::compute|ERROR: feature extractor / correspondence finder not set");
+  auto epipolar = std::dynamic_pointer_cast<CorrespondenceFinderDescriptorBasedEpipolarCUDA>(param_correspondence_finder.value());
+  IntensityFeatureExtractorBinnedCUDA& ex_l = *param_feature_extractor.value();
+  IntensityFeatureExtractorBinnedCUDA& ex_r = *param_feature_extractor_right.value();
+  const pslam_extract_cfg cl = ex_l.cudaConfig(), cr = ex_r.cudaConfig();
+  const bool same_extractor = cl.detector_threshold == cr.detector_threshold &&
+                              cl.enable_non_maximum_suppression == cr.enable_non_maximum_suppression &&
+                              cl.target_number_of_keypoints == cr.target_number_of_keypoints &&
+                              cl.number_of_detectors_horizontal == cr.number_of_detectors_horizontal &&
+                              cl.number_of_detectors_vertical == cr.number_of_detectors_vertical;
+  _meas->dim = 4;
+  if (epipolar && same_extractor && _left.rows == _right.rows && _left.cols == _right.cols && _left.stride == _right.stride) {
+    // the shipped wiring (kitti.conf / euroc.conf): ONE device call, features never leave HBM between the stages
+    ex_l.prepare(_left.rows, _left.cols);  // the extractors' own init(): PARAM validation, same error texts
+    ex_r.prepare(_right.rows, _right.cols);
+    pslam_ctx* ctx = PslamDevice::context(_left.rows, _left.cols);
+    const pslam_match_cfg mcfg = epipolar->cudaConfig();
+    _meas->resize(kMaxFeatures);
+    const int n = pslam_stereo_adaptor(ctx, _left.data, _right.data, _left.rows, _left.cols, _left.stride, &cl, &mcfg, kMaxFeatures,
+                                       _meas->coordinates.data(), _meas->intensity.data(), _meas->descriptor.data());
+    if (n < 0) _meas->resize(0);
+    PslamDevice::check(n, "RawDataPreprocessorStereoProjective::compute");
+    _meas->resize(n);
+  } else {
+    // general wiring (e.g. a brute-force finder, different extractors): compose the module calls (:77-132)
+    PointIntensityDescriptorCloud features_left(3), features_right(3);
+    ex_l.setFeatures(&features_left);
+    ex_l.compute(_left);
+    ex_r.setFeatures(&features_right);
+    ex_r.compute(_right);
+    CorrespondenceVector stereo_matches;
+    auto& finder = *param_correspondence_finder.value();
+    finder.setFixed(&features_left);
+    finder.setMoving(&features_right);
+    finder.setCorrespondences(&stereo_matches);
+    finder.compute();
+    _meas->resize(stereo_matches.size());
+    size_t k = 0;
+    for (const Correspondence& c : stereo_matches) {
+      const float* l = features_left.point(c.fixed_idx);
+      const float* r = features_right.point(c.moving_idx);
+      if (l[0] - r[0] < 0 || l[1] - r[1] < 0) continue;  // :120-128
+      float* p = _meas->point(k);
+      p[0] = l[0];
+      p[1] = l[1];
+      p[2] = r[0];
+      p[3] = r[1];
+      _meas->intensity[k] = features_left.intensity[c.fixed_idx];
+      std::copy_n(features_left.descriptor.data() + 32 * (size_t) c.fixed_idx, 32, _meas->descriptor.data() + 32 * k);
+      ++k;
+    }
+    _meas->resize(k);
+  }
+  _raw_data_changed_flag = false;
+  _status = Ready;
+}
+
+// ---- monocular + depth adaptor ------------------------------------------------------------------------------------
+bool RawDataPreprocessorMonocularDepthCUDA::setRawData(const ImageView& intensity, const DepthView& depth) {
+  _raw_set = false;
+  _status = Error;
+  if (!intensity.data)
+    throw std::runtime_error("RawDataPreprocessorMonocularDepth::setMeasurement|ERROR, ImageMessage not found - topic [ " +
+                             param_topic_rgb.value() + " ]");
+  if (!depth.data)
+    throw std::runtime_error("RawDataPreprocessorMonocularDepth::setMeasurement|ERROR, ImageMessage not found - topic [ " +
+                             param_topic_depth.value() + " ]");
+  _intensity = intensity;
+  _depth = depth;
+  _raw_set = true;
+  _raw_data_changed_flag = true;
+  _status = Initializing;
+  return true;
+}
+
+void RawDataPreprocessorMonocularDepthCUDA::compute() {
+  _status = Error;
+  if (!_raw_set) throw std::runtime_error("RawDataPreprocessorMonocularDepth::compute|ERROR: measurement not set");
+  if (!_meas) throw std::runtime_error("RawDataPreprocessorMonocularDepth::compute|ERROR: destination buffer not set");
+  if (!_raw_data_changed_flag) {
+    _status = Ready;
+    return;
+  }
+  _meas->clear();
+  if (_intensity.rows == 0) throw std::runtime_error("RawDataPreprocessorMonocularDepth::compute|ERROR: intensity image has zero rows");
+  if (_intensity.cols == 0) throw std::runtime_error("RawDataPreprocessorMonocularDepth::compute|ERROR: intensity image has zero columns");
+  if (_depth.rows == 0) throw std::runtime_error("RawDataPreprocessorMonocularDepth::compute|ERROR: depth image has zero rows");
+  if (_depth.cols == 0) throw std::runtime_error("RawDataPreprocessorMonocularDepth::compute|ERROR: depth image has zero columns");
+  if (_depth.type != 0 && _depth.type != 1) throw std::runtime_error("RawDataPreprocessorMonocularDepth::compute|ERROR: unknown depth image type");
+  if (!param_feature_extractor.value()) throw std::runtime_error("RawDataPreprocessorMonocularDepth::compute|ERROR: feature extractor not set");
+  pslam_ctx* ctx = PslamDevice::context(_intensity.rows, _intensity.cols);
+  const pslam_extract_cfg cfg = param_feature_extractor->cudaConfig();
+  _meas->dim = 3;
+  _meas->resize(kMaxFeatures);
+  int n_in_image = 0;
+  const int n = pslam_mono_depth_adaptor(ctx, _intensity.data, _intensity.rows, _intensity.cols, _intensity.stride, _depth.data,
+                                         _depth.type, _depth.rows, _depth.cols, _depth.stride_elements,
+                                         param_depth_scaling_factor_to_meters.value(), &cfg, kMaxFeatures,
+                                         _meas->coordinates.data(), _meas->intensity.data(), _meas->descriptor.data(), &n_in_image);
+  if (n < 0) _meas->resize(0);
+  PslamDevice::check(n, "RawDataPreprocessorMonocularDepth::compute");
+  _meas->resize(n);
+  _raw_data_changed_flag = false;
+  if (n_in_image == 0) std::cerr << "RawDataPreprocessorMonocularDepth::compute|WARNING: no features found" << std::endl;
+  if (_meas->empty()) {
+    std::cerr << "RawDataPreprocessorMonocularDepth::compute|WARNING: no adapted measurements generated" << std::endl;
+    _status = Error;
+    return;
+  }
+  const size_t without = (size_t) n_in_image - _meas->size();
+  if (static_cast<float>(without) / n_in_image > 0.25)
+    std::cerr << "RawDataPreprocessorMonocularDepth::compute|WARNING: high number of points without depth: " << without << "/"
+              << n_in_image << std::endl;
+  _status = Ready;
+}
+
+// ---- aligner slice ----------------------------------------------------------------------------------------------
+AlignerSliceProcessorProjectiveCUDA::AlignerSliceProcessorProjectiveCUDA(int kind) : _kind(kind) {
+  // aligner_slice_processor_projective.cpp:7-20: saturated robustifier with chi threshold 100^2 by default
+  auto r = std::make_shared<RobustifierSaturated>();
+  r->setName("aligner_robustifier");
+  r->param_chi_threshold.setValue(100 * 100);
+  param_robustifier.setValue(r);
+  setName("aligner_slice_projective");
+  param_diagonal_info_matrix.setValue(std::vector<float>(kind == 2 ? 2 : 3, 0.f));  // DiagInfoVector::Zero()
+}
+
+void AlignerSliceProcessorProjectiveCUDA::bindFixed() {
+  if (_kind != 0) return;
+  // stereo: mean disparity over the fixed slice, fp32 accumulation in cloud order (.cpp:78-88)
+  if (_fixed_slice && !_fixed_slice->empty()) {
+    float accumulated_disparity = 0;
+    for (size_t i = 0; i < _fixed_slice->size(); ++i) accumulated_disparity += _fixed_slice->point(i)[0] - _fixed_slice->point(i)[2];
+    _mean_disparity = accumulated_disparity / _fixed_slice->size();
+  } else {
+    _mean_disparity = 0;
+  }
+}
+
+void AlignerSliceProcessorProjectiveCUDA::setupFactor() {
+  if (!_fixed_slice || !_moving_slice) throw std::runtime_error("AlignerSliceProjective_|fixed / moving slice not set");
+  if (!param_projector.value()) throw std::runtime_error("AlignerSliceProjective_|projector not set");
+  const ProjectorPinhole& projector = *param_projector.value();
+  _factor.kind = _kind;
+  for (int i = 0; i < 9; ++i) _factor.K[i] = projector.cameraMatrix()[i];
+  _factor.image_cols = projector.param_canvas_cols.value();
+  _factor.image_rows = projector.param_canvas_rows.value();
+  const std::vector<float>& diag = param_diagonal_info_matrix.value();
+  if ((int) diag.size() != (_kind == 2 ? 2 : 3)) throw std::runtime_error("AlignerSliceProjective_|diagonal_info_matrix has the wrong dimension");
+  // per-correspondence information, indexed by the FIXED index (.cpp:41-57)
+  _fixed_information_diagonals.resize(3 * _fixed_slice->size());
+  constexpr size_t minimum_number_of_updates = 2;
+  for (const Correspondence& c : _correspondences) {
+    float d[3] = {diag[0], diag[1], diag.size() > 2 ? diag[2] : 0.f};
+    const int n_opt = _moving_slice->number_of_optimizations.empty() ? 0 : _moving_slice->number_of_optimizations[c.moving_idx];
+    if ((size_t) n_opt > minimum_number_of_updates) {
+      const float s = (float) (1 + std::log((double) n_opt));  // Vector3f *= (1 + std::log(size_t)): double, then Scalar
+      for (float& x : d) x *= s;
+    }
+    for (int k = 0; k < 3; ++k) _fixed_information_diagonals[3 * (size_t) c.fixed_idx + k] = d[k];
+  }
+  RobustifierBase* rob = param_robustifier.value().get();
+  _factor.robustifier = rob ? rob->kind() : 0;
+  _factor.chi_threshold = rob ? rob->param_chi_threshold.value() : 0.0;
+  _factor.baseline[0] = _factor.baseline[1] = _factor.baseline[2] = 0;
+  _factor.mean_disparity = 0;
+  if (_kind == 0) {
+    if (!_baseline_set) {  // baseline [pixel * m] = K * t_left_in_right, fp32 (.cpp:93-103)
+      const std::array<float, 9>& K = projector.cameraMatrix();
+      for (int i = 0; i < 3; ++i)
+        _baseline_left_in_right_pixelsmeters[i] =
+          K[3 * i] * _t_left_in_right[0] + K[3 * i + 1] * _t_left_in_right[1] + K[3 * i + 2] * _t_left_in_right[2];
+      _baseline_set = true;
+    }
+    for (int i = 0; i < 3; ++i) _factor.baseline[i] = _baseline_left_in_right_pixelsmeters[i];
+    if (param_enable_inverse_depth_weighting.value()) _factor.mean_disparity = _mean_disparity;  // (.cpp:107-112)
+  }
+}
+
+// ---- aligner ----------------------------------------------------------------------------------------------------
+void MultiAligner3DQRCUDA::setMovingInFixed(const Isometry3f& T) {
+  for (int i = 0; i < 12; ++i) _estimate[i] = T.m[i];
+}
+
+AlignerSliceProcessorProjectiveCUDA* MultiAligner3DQRCUDA::projectiveSlice() const {
+  for (const auto& s : param_slice_processors.value())
+    if (auto p = std::dynamic_pointer_cast<AlignerSliceProcessorProjectiveCUDA>(s)) return p.get();
+  return nullptr;
+}
+
+void MultiAligner3DQRCUDA::compute() {
+  _status = Fail;
+  _stats.clear();
+  AlignerSliceProcessorProjectiveCUDA* slice = projectiveSlice();
+  if (!slice) throw std::runtime_error("MultiAligner::compute|ERROR: no projective slice processor configured");
+  if (!_fixed || !_moving) throw std::runtime_error("MultiAligner::compute|ERROR: fixed / moving not set");
+  if (!slice->param_finder.value()) throw std::runtime_error("MultiAligner::compute|ERROR: slice has no correspondence finder");
+  if (!param_solver.value()) throw std::runtime_error("MultiAligner::compute|ERROR: solver not set");
+  if (_fixed->dim != slice->fixedDim()) throw std::runtime_error("MultiAligner::compute|ERROR: fixed cloud dimension does not match the slice's factor");
+  pslam_ctx* ctx = PslamDevice::context();
+  CorrespondenceFinderBase& finder = *slice->param_finder.value();
+  slice->setFixed(_fixed);
+  slice->setMoving(_moving);
+  slice->bindFixed();
+  finder.setFixed(_fixed);
+  finder.setMoving(_moving);
+  finder.setCorrespondences(&slice->correspondences());
+  const double damping = param_solver->damping();
+
+  // device inputs of the factor (fp64): moving points and fixed measurements do not change over the iterations
+  std::vector<double> moving_xyz(_moving->coordinates.begin(), _moving->coordinates.end());
+  std::vector<double> fixed_meas(_fixed->coordinates.begin(), _fixed->coordinates.end());
+  std::vector<int> cf, cm;
+  AlignerIterationStats last;
+  bool enough = true;
+  for (int it = 0; it < param_max_iterations.value(); ++it) {
+    Isometry3f X;
+    for (int i = 0; i < 12; ++i) X.m[i] = (float) _estimate[i];
+    finder.setLocalMapInSensor(X);
+    finder.compute();
+    const CorrespondenceVector& corr = slice->correspondences();
+    AlignerIterationStats st;
+    st.iteration = it;
+    st.num_correspondences = (int) corr.size();
+    if ((int) corr.size() < std::max(slice->param_min_num_correspondences.value(), 1)) {
+      enough = false;
+      _stats.push_back(st);
+      break;
+    }
+    slice->setupFactor();
+    cf.resize(corr.size());
+    cm.resize(corr.size());
+    for (size_t k = 0; k < corr.size(); ++k) {
+      cf[k] = corr[k].fixed_idx;
+      cm[k] = corr[k].moving_idx;
+    }
+    double H[36], b[6], stats4[4], dx[6];
+    PslamDevice::check(pslam_linearize_se3(ctx, &slice->factorConfig(), _estimate.data(), (int) _moving->size(), moving_xyz.data(),
+                                           (int) _fixed->size(), fixed_meas.data(), _fixed->dim, (int) corr.size(), cf.data(),
+                                           cm.data(), slice->informationDiagonals().data(), H, b, stats4),
+                       "MultiAligner::compute");
+    st.chi = stats4[0];
+    st.num_inliers = (int) stats4[1];
+    st.num_outliers = (int) stats4[2];
+    st.num_suppressed = (int) stats4[3];
+    const int rc = pslam_gn_step(ctx, H, b, damping, _estimate.data(), dx);
+    _stats.push_back(st);
+    last = st;
+    if (rc == PSLAM_E_NOT_SPD) break;  // degenerate system: keep the last estimate
+    PslamDevice::check(rc, "MultiAligner::compute");
+  }
+  if (!enough) {
+    _status = NotEnoughCorrespondences;
+    return;
+  }
+  _status = last.num_inliers >= param_min_num_inliers.value() ? Success : NotEnoughInliers;
+}
+
+// ---- registration -----------------------------------------------------------------------------------------------
+namespace {
+template <int Dim>
+struct ExtractorD : IntensityFeatureExtractorBinnedCUDA {
+  ExtractorD() : IntensityFeatureExtractorBinnedCUDA(Dim) {}
+};
+template <int Shape>
+struct ProjectiveS : CorrespondenceFinderProjectiveCUDA {
+  ProjectiveS() : CorrespondenceFinderProjectiveCUDA(Shape) {}
+};
+template <int Kind>
+struct SliceK : AlignerSliceProcessorProjectiveCUDA {
+  SliceK() : AlignerSliceProcessorProjectiveCUDA(Kind) {}
+};
+template <typename T>
+void reg(const std::string& reference_name) {
+  PSLAM_REGISTER_CLASS_AS(T, reference_name);           // the unchanged .conf selects the CUDA-backed class
+  PSLAM_REGISTER_CLASS_AS(T, reference_name + "CUDA");  // explicit name, SURVEY.md 8b
+}
+}  // namespace
+
+void registerTypes() {
+  static bool done = false;
+  if (done) return;
+  done = true;
+  // sensor_processing/instances.cpp:11-17
+  reg<ExtractorD<2>>("IntensityFeatureExtractorBinned2D");
+  reg<ExtractorD<3>>("IntensityFeatureExtractorBinned3D");
+  reg<RawDataPreprocessorStereoProjectiveCUDA>("RawDataPreprocessorStereoProjective");
+  reg<RawDataPreprocessorMonocularDepthCUDA>("RawDataPreprocessorMonocularDepth");
+  // registration/instances.cpp:51-76
+  for (const char* dims : {"2D2D", "2D3D", "3D3D", "4D3D"}) {
+    reg<CorrespondenceFinderDescriptorBasedBruteforceCUDA>(std::string("CorrespondenceFinderDescriptorBasedBruteforce") + dims);
+  }
+  for (const char* dims : {"2D2D", "3D3D"}) reg<CorrespondenceFinderDescriptorBasedEpipolarCUDA>(std::string("CorrespondenceFinderDescriptorBasedEpipolar") + dims);
+  for (const char* dims : {"2D3D", "3D3D", "4D3D"}) {
+    reg<ProjectiveS<0>>(std::string("CorrespondenceFinderProjectiveSquare") + dims);
+    reg<ProjectiveS<1>>(std::string("CorrespondenceFinderProjectiveCircle") + dims);
+    reg<ProjectiveS<2>>(std::string("CorrespondenceFinderProjectiveRhombus") + dims);
+  }
+  reg<SliceK<2>>("AlignerSliceProcessorProjective");
+  reg<SliceK<1>>("AlignerSliceProcessorProjectiveDepth");
+  reg<SliceK<0>>("AlignerSliceProcessorProjectiveStereo");
+  reg<SliceK<0>>("AlignerSliceProcessorProjectiveStereoWithSensor");  // kitti_in_baselink.conf
+  reg<MultiAligner3DQRCUDA>("MultiAligner3DQR");
+  // srrg2_core / srrg2_solver modules the hot-path classes link to
+  PSLAM_REGISTER_CLASS_AS(ProjectorPinhole, "PointIntensityDescriptor3fProjectorPinhole");
+  PSLAM_REGISTER_CLASS_AS(RobustifierSaturated, "RobustifierSaturated");
+  PSLAM_REGISTER_CLASS_AS(RobustifierClamp, "RobustifierClamp");
+  PSLAM_REGISTER_CLASS_AS(IterationAlgorithmGN, "IterationAlgorithmGN");
+  PSLAM_REGISTER_CLASS_AS(Solver, "Solver");
+}
+
+}  // namespace pslam_host

@@ -1,0 +1,382 @@
+// pslam_plugin.hpp -- host-side C++ mirror of the srrg2_proslam plugin classes on the frontend hot path.
+//
+// Same class names (so the shipped .conf files select them), same PARAM names / defaults, same call contract
+// (setFixed / setMoving / setCorrespondences / compute, setFeatures / compute(image), setRawData-like setters,
+// _status), same std::runtime_error texts.  Every compute() forwards the data-parallel work to the sm_100a
+// kernels through the C ABI of include/pslam_cuda.h -- there is no CPU implementation of the arithmetic here;
+// without a CUDA device PslamDevice::context() throws.  What stays on the host is what the reference keeps in
+// its control flow: change flags, the projective finder's adaptive state machine, the aligner iteration loop.
+//
+// Point clouds are SoA mirrors of srrg2_core::PointIntensityDescriptor{2,3,4}fVectorCloud.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <iostream>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/pslam_cuda.h"
+#include "pslam_boss.hpp"
+
+namespace pslam_host {
+
+// srrg2_core::Correspondence(fixed_idx, moving_idx, response)
+struct Correspondence {
+  int fixed_idx = -1, moving_idx = -1;
+  float response = 0;
+};
+using CorrespondenceVector = std::vector<Correspondence>;
+
+// PointIntensityDescriptor_<Dim, float> vector cloud: field<0> coordinates, <1> intensity, <2> descriptor
+struct PointIntensityDescriptorCloud {
+  int dim = 3;
+  std::vector<float> coordinates;       // [n][dim]
+  std::vector<float> intensity;         // [n]
+  std::vector<uint8_t> descriptor;      // [n][32]  (row of the reference's cv::Mat)
+  std::vector<int> number_of_optimizations;  // statistics().numberOfOptimizations(), empty = all 0
+  explicit PointIntensityDescriptorCloud(int dim_ = 3) : dim(dim_) {}
+  size_t size() const { return intensity.size(); }
+  bool empty() const { return intensity.empty(); }
+  void clear() { resize(0); }
+  void resize(size_t n) {
+    coordinates.resize(n * dim);
+    intensity.resize(n);
+    descriptor.resize(n * 32);
+    if (!number_of_optimizations.empty()) number_of_optimizations.resize(n);
+  }
+  float* point(size_t i) { return coordinates.data() + i * dim; }
+  const float* point(size_t i) const { return coordinates.data() + i * dim; }
+};
+
+// row-major 3x4 [R|t] isometry, float like the reference's Isometry3f
+struct Isometry3f {
+  float m[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+  static Isometry3f Identity() { return Isometry3f(); }
+  void setIdentity() { *this = Isometry3f(); }
+  Isometry3f inverse() const;
+  Isometry3f operator*(const Isometry3f& o) const;
+};
+// geometry3d::t2tnq: translation + vector part of the normalised quaternion (w >= 0)
+void t2tnq(const Isometry3f& T, float v6[6]);
+
+// an 8-bit single channel image view (cv::Mat CV_8UC1 / srrg2_core::ImageUInt8)
+struct ImageView {
+  const uint8_t* data = nullptr;
+  int rows = 0, cols = 0, stride = 0;
+};
+// depth image view: TYPE_16UC1 or TYPE_32FC1
+struct DepthView {
+  const void* data = nullptr;
+  int rows = 0, cols = 0, stride_elements = 0;
+  int type = 0;  // 0 = u16, 1 = f32, anything else = unknown
+};
+
+// process-wide device context shared by all modules (the reference is single threaded)
+class PslamDevice {
+public:
+  static pslam_ctx* context(int rows = 0, int cols = 0);  // grows on demand; throws std::runtime_error without a GPU
+  static void release();
+  static void setDevice(int device);
+  static void check(int rc, const char* where);  // negative rc -> std::runtime_error(pslam_last_error)
+};
+
+// ---- PointIntensityDescriptor3fProjectorPinhole (srrg2_core; configurations/kitti.conf:164-179) -------------
+class ProjectorPinhole : public Configurable {
+public:
+  PARAM(PropertyUnsignedInt, canvas_cols, "canvas width [pixels]", 0, nullptr);
+  PARAM(PropertyUnsignedInt, canvas_rows, "canvas height [pixels]", 0, nullptr);
+  PARAM(PropertyFloat, range_max, "maximum range [m]", 1000.f, nullptr);
+  PARAM(PropertyFloat, range_min, "minimum range [m]", 0.3f, nullptr);
+  void setCameraMatrix(const std::array<float, 9>& K) { _K = K; }
+  const std::array<float, 9>& cameraMatrix() const { return _K; }
+
+private:
+  std::array<float, 9> _K{{1, 0, 0, 0, 1, 0, 0, 0, 1}};
+};
+
+// ---- srrg2_solver pieces the .conf wires into the aligner ----------------------------------------------------
+class RobustifierBase : public Configurable {
+public:
+  PARAM(PropertyFloat, chi_threshold, "threshold of chi after which the kernel is active", 1.f, nullptr);
+  virtual int kind() const = 0;  // pslam_linearize_cfg.robustifier
+};
+class RobustifierSaturated : public RobustifierBase {
+public:
+  int kind() const override { return 1; }
+};
+class RobustifierClamp : public RobustifierBase {
+public:
+  int kind() const override { return 2; }
+};
+class IterationAlgorithmGN : public Configurable {
+public:
+  PARAM(PropertyFloat, damping, "damping factor, the higher the closer to gradient descend. Default:0", 0.f, nullptr);
+};
+class Solver : public Configurable {
+public:
+  PARAM(PropertyConfigurable_<Configurable>, algorithm, "pointer to the optimization algorithm (GN/LM or others)",
+        std::static_pointer_cast<Configurable>(std::make_shared<IterationAlgorithmGN>()), nullptr);
+  PARAM(PropertyVector_<int>, max_iterations, "maximum iterations if no stopping criteria is set", std::vector<int>(), nullptr);
+  float damping() const;
+};
+
+// ---- IntensityFeatureExtractorBinned_ (sensor_processing/feature_extractors/intensity_feature_extractor_binned.{h,cpp},
+//      ..._base.{h,cpp}) ---------------------------------------------------------------------------------------
+class IntensityFeatureExtractorBinnedCUDA : public Configurable {
+public:
+  explicit IntensityFeatureExtractorBinnedCUDA(int point_dim = 3) : _point_dim(point_dim) {}
+  PARAM(PropertyString, descriptor_type, "OpenCV descriptor type (BRIEF-256, BRIEF-512, ORB-256, FREAK-512, ..)", "ORB-256", &_config_changed);
+  PARAM(PropertyString, detector_type, "OpenCV detector type for point tracking (FAST, MSER, GFTT, BRISK-512, ORB-256, ..)", "FAST", &_config_changed);
+  PARAM(PropertyFloat, detector_threshold, "scalar that maps to the first parameter of the chosen detector (if applicable)", 10, &_config_changed);
+  PARAM(PropertyFloat, target_bin_width_pixels, "minimum required distance between detected features (if applicable)", 10, &_config_changed);
+  PARAM(PropertyBool, enable_non_maximum_suppression, "enables non maximum suppression (filtering) of detected features (if applicable)", true, &_config_changed);
+  PARAM(PropertyInt, target_number_of_keypoints, "target number of keypoints to detect (accumulative over all detectors)", 500, &_config_changed);
+  PARAM(PropertyInt, number_of_detectors_horizontal, "number of detectors on the horizontal image axis (cols)", 3, &_config_changed);
+  PARAM(PropertyInt, number_of_detectors_vertical, "number of detectors on the vertical image axis (rows)", 3, &_config_changed);
+
+  void init();   // binned.cpp:7-106: validates the configuration (same error texts)
+  void clear() { _config_changed = true; }
+  void setFeatures(PointIntensityDescriptorCloud* features) { _features = features; }
+  void setKeypointDetectionMask(const ImageView& mask) {  // base.h:128-132
+    _mask = mask;
+    _mask_set = mask.data != nullptr;
+  }
+  void compute(const ImageView& image);  // base.cpp:55-85
+  void prepare(int rows, int cols);      // latch the image size and (re-)run init()
+  size_t imageRows() const { return _image_rows; }
+  size_t imageCols() const { return _image_cols; }
+  pslam_extract_cfg cudaConfig() const;
+  int pointDim() const { return _point_dim; }
+
+private:
+  int _point_dim;
+  bool _config_changed = true;
+  size_t _image_rows = 0, _image_cols = 0;
+  PointIntensityDescriptorCloud* _features = nullptr;
+  ImageView _mask;
+  bool _mask_set = false;
+};
+
+// ---- descriptor-based finders (registration/correspondence_finders/correspondence_finder_descriptor_based_*.h) --
+class CorrespondenceFinderBase : public Configurable {
+public:
+  void setFixed(const PointIntensityDescriptorCloud* fixed) {
+    _fixed = fixed;
+    _fixed_changed_flag = true;
+  }
+  void setMoving(const PointIntensityDescriptorCloud* moving) {
+    _moving = moving;
+    _moving_changed_flag = true;
+  }
+  void setCorrespondences(CorrespondenceVector* c) { _correspondences = c; }
+  void setLocalMapInSensor(const Isometry3f& T) { _local_map_in_sensor = T; }
+  const Isometry3f& localMapInSensor() const { return _local_map_in_sensor; }
+  virtual void compute() = 0;
+
+protected:
+  const PointIntensityDescriptorCloud* _fixed = nullptr;
+  const PointIntensityDescriptorCloud* _moving = nullptr;
+  CorrespondenceVector* _correspondences = nullptr;
+  Isometry3f _local_map_in_sensor;
+  bool _fixed_changed_flag = false, _moving_changed_flag = false;
+};
+
+class CorrespondenceFinderDescriptorBasedBruteforceCUDA : public CorrespondenceFinderBase {
+public:
+  PARAM(PropertyFloat, maximum_descriptor_distance, "maximum permitted descriptor distance for a match", 50.0f, nullptr);
+  PARAM(PropertyFloat, maximum_distance_ratio_to_second_best, "Lowe's distance to drop ambiguous match candidates", 0.9f, nullptr);
+  PARAM(PropertyFloat, minimum_matching_ratio, "desired minimum matching ratio with current configuration (signals transgressions)", 0.25f, nullptr);
+  void compute() override;  // bruteforce_impl.cpp:6-155
+
+protected:
+  void _preCompute();   // :201-228
+  void _postCompute();  // :230-243
+};
+
+class CorrespondenceFinderDescriptorBasedEpipolarCUDA : public CorrespondenceFinderDescriptorBasedBruteforceCUDA {
+public:
+  PARAM(PropertyUnsignedInt, maximum_disparity_pixels, "maximum disparity search range in pixels", 100, nullptr);
+  PARAM(PropertyUnsignedInt, epipolar_line_thickness_pixels, "epipolar line search thickness in pixels (0 for perfect horizontal calibration)", 0, nullptr);
+  void compute() override;  // epipolar_impl.cpp:44-219
+  pslam_match_cfg cudaConfig() const;
+};
+
+// ---- projective finders (correspondence_finder_projective_base.h + square / circle / rhombus) -----------------
+class CorrespondenceFinderProjectiveCUDA : public CorrespondenceFinderDescriptorBasedBruteforceCUDA {
+public:
+  explicit CorrespondenceFinderProjectiveCUDA(int shape = 1) : _shape(shape) {}
+  PARAM(PropertyFloat, minimum_descriptor_distance, "minimum permitted descriptor distance for a match (initial)", 25.0f, &_config_changed);
+  PARAM(PropertyFloat, descriptor_distance_step_size_pixels, "descriptor distance step size (increase/decrease)", 5, &_config_changed);
+  PARAM(PropertyUnsignedInt, maximum_search_radius_pixels, "maximum projective region search radius in pixels", 100, &_config_changed);
+  PARAM(PropertyUnsignedInt, minimum_search_radius_pixels, "minimum projective region search radius in pixels", 10, &_config_changed);
+  PARAM(PropertyUnsignedInt, search_radius_step_size_pixels, "search radius step size (increase/decrease) in pixels", 5, &_config_changed);
+  PARAM(PropertyConfigurable_<ProjectorPinhole>, projector, "pinhole projector used for projective descriptor matching",
+        std::make_shared<ProjectorPinhole>(), &_config_changed);
+  PARAM(PropertyUnsignedInt, minimum_number_of_iterations, "minimum number of iterations to perform recomputes (forced)", 10, &_config_changed);
+  PARAM(PropertyFloat, maximum_estimate_change_norm_for_convergence, "maximum allowed transform estimate change threshold for assuming convergence", 1e-5f, &_config_changed);
+  PARAM(PropertyUnsignedInt, number_of_solver_iterations_per_projection, "minimum number of solver iterations (on estimate) to await before reprojecting points", 25, &_config_changed);
+
+  void compute() override;  // projective_base_impl.cpp:104-293 (state machine); search + filter on the device
+  void setSearchradiusPixels(size_t r) {  // projective_base.h:82-85
+    _search_radius_pixels = r;
+    _config_changed = false;
+  }
+  size_t searchRadiusPixels() const { return _search_radius_pixels; }
+  void setDescriptorDistance(float d) {  // :94-97
+    _descriptor_distance = d;
+    _config_changed = false;
+  }
+  float descriptorDistance() const { return _descriptor_distance; }
+  bool hasConverged() const { return _has_converged; }
+  size_t currentIteration() const { return _current_iteration; }
+  int numberOfSearches() const { return _number_of_searches; }
+  int shape() const { return _shape; }
+
+private:
+  int _shape;
+  bool _config_changed = true;
+  size_t _search_radius_pixels = 0;
+  float _descriptor_distance = 0;
+  Isometry3f _local_map_in_sensor_previous;
+  bool _has_converged = false;
+  size_t _current_iteration = 0;
+  int _number_of_searches = 0;
+};
+
+// ---- measurement adaptors (sensor_processing/raw_data_preprocessor_{stereo_projective,monocular_depth}.{h,cpp}) --
+class RawDataPreprocessorBase : public Configurable {
+public:
+  enum Status { Error = 0, Initializing = 1, Ready = 2 };
+  Status status() const { return _status; }
+  void setMeas(PointIntensityDescriptorCloud* meas) { _meas = meas; }
+
+protected:
+  Status _status = Error;
+  PointIntensityDescriptorCloud* _meas = nullptr;
+  bool _raw_data_changed_flag = false;
+};
+
+class RawDataPreprocessorStereoProjectiveCUDA : public RawDataPreprocessorBase {
+public:
+  RawDataPreprocessorStereoProjectiveCUDA();
+  PARAM(PropertyConfigurable_<IntensityFeatureExtractorBinnedCUDA>, feature_extractor,
+        "feature extractor used to detect keypoints and compute descriptors", std::make_shared<IntensityFeatureExtractorBinnedCUDA>(3), nullptr);
+  PARAM(PropertyConfigurable_<IntensityFeatureExtractorBinnedCUDA>, feature_extractor_right,
+        "feature extractor used to detect keypoints and compute descriptors in the right frame", std::make_shared<IntensityFeatureExtractorBinnedCUDA>(3), nullptr);
+  PARAM(PropertyConfigurable_<CorrespondenceFinderDescriptorBasedBruteforceCUDA>, correspondence_finder,
+        "descriptor-based correspondence finder used to compute stereo matches",
+        std::static_pointer_cast<CorrespondenceFinderDescriptorBasedBruteforceCUDA>(std::make_shared<CorrespondenceFinderDescriptorBasedEpipolarCUDA>()), nullptr);
+  PARAM(PropertyString, topic_camera_left, "left rgb image topic [/camera_left/image_raw]", "/camera_left/image_raw", nullptr);
+  PARAM(PropertyString, topic_camera_right, "right rgb image topic [/camera_right/image_raw]", "/camera_right/image_raw", nullptr);
+  // setRawData (stereo_projective.cpp:6-44): a message pack of exactly two images
+  bool setRawData(const ImageView& left, const ImageView& right);
+  void compute();  // :46-134
+
+private:
+  ImageView _left, _right;
+  bool _raw_set = false;
+};
+
+class RawDataPreprocessorMonocularDepthCUDA : public RawDataPreprocessorBase {
+public:
+  PARAM(PropertyConfigurable_<IntensityFeatureExtractorBinnedCUDA>, feature_extractor,
+        "feature extractor used to detect keypoints and compute descriptors", std::make_shared<IntensityFeatureExtractorBinnedCUDA>(3), nullptr);
+  PARAM(PropertyString, topic_rgb, "rgb image topic [/camera/rgb/image]", "/camera/rgb/image", nullptr);
+  PARAM(PropertyString, topic_depth, "topic depth image [/camera/depth/image]", "/camera/depth/image", nullptr);
+  PARAM(PropertyFloat, depth_scaling_factor_to_meters, "scaling factor used to obtain depth in meters from pixel values", 1.0f, nullptr);
+  bool setRawData(const ImageView& intensity, const DepthView& depth);
+  void compute();  // monocular_depth.cpp:50-180
+
+private:
+  ImageView _intensity;
+  DepthView _depth;
+  bool _raw_set = false;
+};
+
+// ---- aligner slice processors (registration/aligner_slice_processor_projective.{h,cpp}) -----------------------
+class AlignerSliceProcessorProjectiveCUDA : public Configurable {
+public:
+  // factor kind: 0 rectified stereo (fixed 4-D), 1 projective depth (fixed 3-D), 2 projective (fixed 2-D)
+  explicit AlignerSliceProcessorProjectiveCUDA(int kind = 2);
+  PARAM(PropertyVector_<float>, diagonal_info_matrix, "value of the information matrix's diagonal", std::vector<float>(), nullptr);
+  PARAM(PropertyConfigurable_<ProjectorPinhole>, projector, "link to a projector where to take the infor for the factor", nullptr, nullptr);
+  PARAM(PropertyConfigurable_<CorrespondenceFinderBase>, finder, "correspondence finder used in this cue", nullptr, nullptr);
+  PARAM(PropertyConfigurable_<RobustifierBase>, robustifier, "robustifier used on this slice", nullptr, nullptr);
+  PARAM(PropertyString, fixed_slice_name, "name of the slice in the fixed scene", "points", nullptr);
+  PARAM(PropertyString, moving_slice_name, "name of the slice in the moving scene", "points", nullptr);
+  PARAM(PropertyInt, min_num_correspondences, "minimum number of correspondences in this slice", 0, nullptr);
+  // stereo only (aligner_slice_processor_projective.h:129-151)
+  PARAM(PropertyString, frame_camera_left, "topic for the camera left info", "camera_left", nullptr);
+  PARAM(PropertyString, frame_camera_right, "topic for the camera right info", "camera_right", nullptr);
+  PARAM(PropertyBool, enable_inverse_depth_weighting, "toggles point weighting by inverse depth", false, nullptr);
+  PARAM(PropertyBool, enable_point_covariance_integration, "toggles individual point covariance integration", false, nullptr);
+
+  int kind() const { return _kind; }
+  int fixedDim() const { return _kind == 0 ? 4 : (_kind == 1 ? 3 : 2); }
+  // platform->getTransform(left_camera_in_right, frame_camera_left, frame_camera_right) (.cpp:95-103)
+  void setLeftCameraInRight(const float t_left_in_right[3]) {
+    for (int i = 0; i < 3; ++i) _t_left_in_right[i] = t_left_in_right[i];
+    _baseline_set = false;
+  }
+  void setFixed(const PointIntensityDescriptorCloud* f) { _fixed_slice = f; }
+  void setMoving(const PointIntensityDescriptorCloud* m) { _moving_slice = m; }
+  void bindFixed();    // stereo: mean disparity (.cpp:75-89)
+  void setupFactor();  // K, image dim, per-correspondence information (.cpp:27-73), stereo extras (:91-112)
+  CorrespondenceVector& correspondences() { return _correspondences; }
+  const pslam_linearize_cfg& factorConfig() const { return _factor; }
+  const std::vector<double>& informationDiagonals() const { return _fixed_information_diagonals; }
+  float meanDisparity() const { return _mean_disparity; }
+  const PointIntensityDescriptorCloud* fixedSlice() const { return _fixed_slice; }
+  const PointIntensityDescriptorCloud* movingSlice() const { return _moving_slice; }
+
+private:
+  int _kind;
+  const PointIntensityDescriptorCloud* _fixed_slice = nullptr;
+  const PointIntensityDescriptorCloud* _moving_slice = nullptr;
+  CorrespondenceVector _correspondences;
+  std::vector<double> _fixed_information_diagonals;  // 3 per fixed point
+  pslam_linearize_cfg _factor{};
+  float _mean_disparity = 0;
+  float _t_left_in_right[3] = {0, 0, 0};
+  float _baseline_left_in_right_pixelsmeters[3] = {0, 0, 0};
+  bool _baseline_set = false;
+};
+
+// ---- MultiAligner3DQR (srrg2_slam_interfaces, external; iteration structure: SURVEY App. E.6) ------------------
+struct AlignerIterationStats {
+  int iteration = 0, num_correspondences = 0, num_inliers = 0, num_outliers = 0, num_suppressed = 0;
+  double chi = 0;
+};
+class MultiAligner3DQRCUDA : public Configurable {
+public:
+  enum Status { Fail = 0, Success = 1, NotEnoughCorrespondences = 2, NotEnoughInliers = 3 };
+  PARAM(PropertyBool, enable_inlier_only_runs, "toggles additional inlier only runs if sufficient inliers are available", false, nullptr);
+  PARAM(PropertyBool, keep_only_inlier_correspondences, "toggles removal of correspondences which factors are not inliers in the last iteration", false, nullptr);
+  PARAM(PropertyInt, max_iterations, "maximum number of iterations", 10, nullptr);
+  PARAM(PropertyInt, min_num_inliers, "minimum number ofinliers", 10, nullptr);
+  PARAM_VECTOR(PropertyConfigurableVector_<Configurable>, slice_processors, "slices", nullptr);
+  PARAM(PropertyConfigurable_<Solver>, solver, "this solver", std::make_shared<Solver>(), nullptr);
+  PARAM(PropertyConfigurable_<Configurable>, termination_criteria, "termination criteria, not set=max iterations", nullptr, nullptr);
+
+  void setFixed(const PointIntensityDescriptorCloud* f) { _fixed = f; }
+  void setMoving(const PointIntensityDescriptorCloud* m) { _moving = m; }
+  void setMovingInFixed(const Isometry3f& T);
+  const std::array<double, 12>& movingInFixed() const { return _estimate; }
+  Status status() const { return _status; }
+  void compute();
+  const std::vector<AlignerIterationStats>& iterationStats() const { return _stats; }
+  AlignerSliceProcessorProjectiveCUDA* projectiveSlice() const;
+
+private:
+  const PointIntensityDescriptorCloud* _fixed = nullptr;
+  const PointIntensityDescriptorCloud* _moving = nullptr;
+  std::array<double, 12> _estimate{{1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0}};
+  Status _status = Fail;
+  std::vector<AlignerIterationStats> _stats;
+};
+
+// registers every class above under the reference's names and under the ...CUDA names (idempotent)
+void registerTypes();
+
+}  // namespace pslam_host

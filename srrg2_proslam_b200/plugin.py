@@ -1,0 +1,253 @@
+"""ctypes harness over libpslam_plugin.so (include/pslam_plugin.h): the host-side C++ mirror of the srrg2_proslam
+plugin classes.  Used by tests/ only -- it lets the parity tests read like the reference's gtest files: load a
+`.conf`, fetch a module by name, set PARAMs, hand it images / clouds, call compute()."""
+import ctypes as C
+import pathlib
+
+import numpy as np
+
+LIB_PATH = pathlib.Path(__file__).resolve().parent / "libpslam_plugin.so"
+_lib = None
+
+
+class PluginError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise RuntimeError(f"{LIB_PATH} is missing: build it with `make -C srrg2_proslam_b200/host` "
+                               "(or __graft_entry__.build())")
+        _lib = C.CDLL(str(LIB_PATH))
+        for name in ("psp_last_error", "psp_module_class_name", "psp_module_name", "psp_module_get_string"):
+            getattr(_lib, name).restype = C.c_char_p
+        for name in ("psp_manager_create", "psp_manager_at", "psp_manager_get_by_name", "psp_manager_create_module",
+                     "psp_module_get_link"):
+            getattr(_lib, name).restype = C.c_void_p
+    return _lib
+
+
+def _chk(rc):
+    if rc < 0:
+        raise PluginError(lib().psp_last_error().decode())
+    return rc
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Module:
+    """a Configurable owned by a Manager"""
+
+    def __init__(self, handle, manager):
+        self.h = C.c_void_p(handle)
+        self.manager = manager  # keeps the owner alive
+
+    @property
+    def class_name(self):
+        return lib().psp_module_class_name(self.h).decode()
+
+    @property
+    def name(self):
+        return lib().psp_module_name(self.h).decode()
+
+    @property
+    def is_generic(self):
+        return bool(lib().psp_module_is_generic(self.h))
+
+    def has(self, param):
+        return bool(lib().psp_module_has_param(self.h, param.encode()))
+
+    def set(self, param, value):
+        L = lib()
+        if isinstance(value, Module) or value is None:
+            _chk(L.psp_module_set_link(self.h, param.encode(), value.h if value is not None else None))
+        elif isinstance(value, str):
+            _chk(L.psp_module_set_string(self.h, param.encode(), value.encode()))
+        elif isinstance(value, (list, tuple, np.ndarray)):
+            v = np.asarray(value, np.float64)
+            _chk(L.psp_module_set_numbers(self.h, param.encode(), len(v), _p(v)))
+        else:
+            _chk(L.psp_module_set_number(self.h, param.encode(), C.c_double(float(value))))
+        return self
+
+    def get(self, param):
+        v = C.c_double()
+        _chk(lib().psp_module_get_number(self.h, param.encode(), C.byref(v)))
+        return v.value
+
+    def get_string(self, param):
+        return lib().psp_module_get_string(self.h, param.encode()).decode()
+
+    def get_numbers(self, param):
+        buf = np.zeros(64, np.float64)
+        n = _chk(lib().psp_module_get_numbers(self.h, param.encode(), 64, _p(buf)))
+        return buf[:n].copy()
+
+    def link(self, param):
+        h = lib().psp_module_get_link(self.h, param.encode())
+        return Module(h, self.manager) if h else None
+
+    # ---- IntensityFeatureExtractorBinned ------------------------------------------------------------------
+    def extract(self, img, mask=None, cap=8192):
+        img = np.ascontiguousarray(img, np.uint8)
+        rows, cols = img.shape
+        xy = np.zeros((cap, 2), np.float32)
+        inten = np.zeros(cap, np.float32)
+        desc = np.zeros((cap, 32), np.uint8)
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        n = _chk(lib().psp_extractor_compute(self.h, _p(img), rows, cols, cols, _p(m), cap, _p(xy), _p(inten), _p(desc)))
+        return {"xy": xy[:n].copy(), "intensity": inten[:n].copy(), "desc": desc[:n].copy()}
+
+    # ---- RawDataPreprocessorStereoProjective ----------------------------------------------------------------
+    def stereo_adaptor(self, left, right, cap=8192):
+        left = np.ascontiguousarray(left, np.uint8)
+        right = np.ascontiguousarray(right, np.uint8)
+        rows, cols = left.shape
+        uvuv = np.zeros((cap, 4), np.float32)
+        inten = np.zeros(cap, np.float32)
+        desc = np.zeros((cap, 32), np.uint8)
+        status = C.c_int(-1)
+        n = _chk(lib().psp_stereo_adaptor_compute(self.h, _p(left), _p(right), rows, cols, cols, cap, _p(uvuv), _p(inten),
+                                                  _p(desc), C.byref(status)))
+        return {"uvuv": uvuv[:n].copy(), "intensity": inten[:n].copy(), "desc": desc[:n].copy(), "status": status.value}
+
+    # ---- RawDataPreprocessorMonocularDepth ------------------------------------------------------------------
+    def mono_depth_adaptor(self, img, depth, cap=8192):
+        img = np.ascontiguousarray(img, np.uint8)
+        rows, cols = img.shape
+        if depth.dtype == np.uint16:
+            dtype = 0
+        elif depth.dtype == np.float32:
+            dtype = 1
+        else:
+            dtype = 7
+        depth = np.ascontiguousarray(depth)
+        uvz = np.zeros((cap, 3), np.float32)
+        inten = np.zeros(cap, np.float32)
+        desc = np.zeros((cap, 32), np.uint8)
+        status = C.c_int(-1)
+        n = _chk(lib().psp_mono_depth_adaptor_compute(self.h, _p(img), rows, cols, cols, _p(depth), dtype, depth.shape[0],
+                                                      depth.shape[1], depth.shape[1], cap, _p(uvz), _p(inten), _p(desc),
+                                                      C.byref(status)))
+        return {"uvz": uvz[:n].copy(), "intensity": inten[:n].copy(), "desc": desc[:n].copy(), "status": status.value}
+
+    # ---- CorrespondenceFinder* ------------------------------------------------------------------------------
+    def set_fixed(self, coords, desc):
+        coords = np.ascontiguousarray(coords, np.float32)
+        desc = np.ascontiguousarray(desc, np.uint8)
+        _chk(lib().psp_finder_set_fixed(self.h, len(coords), coords.shape[1] if coords.ndim == 2 else 2, _p(coords), _p(desc)))
+
+    def set_moving(self, coords, desc):
+        coords = np.ascontiguousarray(coords, np.float32)
+        desc = np.ascontiguousarray(desc, np.uint8)
+        _chk(lib().psp_finder_set_moving(self.h, len(coords), coords.shape[1] if coords.ndim == 2 else 3, _p(coords), _p(desc)))
+
+    def set_local_map_in_sensor(self, pose12):
+        pose12 = np.ascontiguousarray(pose12, np.float32).reshape(12)
+        _chk(lib().psp_finder_set_local_map_in_sensor(self.h, _p(pose12)))
+
+    def compute(self, cap=16384):
+        f = np.zeros(cap, np.int32)
+        m = np.zeros(cap, np.int32)
+        d = np.zeros(cap, np.float32)
+        n = _chk(lib().psp_finder_compute(self.h, cap, _p(f), _p(m), _p(d)))
+        return f[:n].copy(), m[:n].copy(), d[:n].copy()
+
+    def projective_state(self):
+        r, it, cv, ns = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        dd = C.c_float()
+        _chk(lib().psp_projective_finder_state(self.h, C.byref(r), C.byref(dd), C.byref(it), C.byref(cv), C.byref(ns)))
+        return {"radius": r.value, "descriptor_distance": dd.value, "iteration": it.value, "converged": bool(cv.value),
+                "searches": ns.value}
+
+    def set_projective_state(self, radius, descriptor_distance):
+        _chk(lib().psp_projective_finder_set_state(self.h, int(radius), C.c_float(descriptor_distance)))
+
+    def set_camera_matrix(self, K):
+        K = np.ascontiguousarray(K, np.float32).reshape(9)
+        _chk(lib().psp_projector_set_camera_matrix(self.h, _p(K)))
+
+    # ---- MultiAligner3DQR -----------------------------------------------------------------------------------
+    def aligner_set_fixed(self, coords, desc):
+        coords = np.ascontiguousarray(coords, np.float32)
+        desc = np.ascontiguousarray(desc, np.uint8)
+        _chk(lib().psp_aligner_set_fixed(self.h, len(coords), coords.shape[1], _p(coords), _p(desc)))
+
+    def aligner_set_moving(self, xyz, desc, n_opt=None):
+        xyz = np.ascontiguousarray(xyz, np.float32)
+        desc = np.ascontiguousarray(desc, np.uint8)
+        no = None if n_opt is None else np.ascontiguousarray(n_opt, np.int32)
+        _chk(lib().psp_aligner_set_moving(self.h, len(xyz), _p(xyz), _p(desc), _p(no)))
+
+    def aligner_set_moving_in_fixed(self, pose12):
+        pose12 = np.ascontiguousarray(pose12, np.float32).reshape(12)
+        _chk(lib().psp_aligner_set_moving_in_fixed(self.h, _p(pose12)))
+
+    def aligner_set_left_camera_in_right(self, t3):
+        t3 = np.ascontiguousarray(t3, np.float32).reshape(3)
+        _chk(lib().psp_aligner_set_left_camera_in_right(self.h, _p(t3)))
+
+    def aligner_compute(self):
+        pose = np.zeros(12, np.float64)
+        it, nc, ni = C.c_int(), C.c_int(), C.c_int()
+        chi = C.c_double()
+        status = _chk(lib().psp_aligner_compute(self.h, _p(pose), C.byref(it), C.byref(nc), C.byref(ni), C.byref(chi)))
+        rows = np.zeros((max(it.value, 1), 4), np.float64)
+        _chk(lib().psp_aligner_iteration_stats(self.h, len(rows), _p(rows)))
+        f = np.zeros(16384, np.int32)
+        m = np.zeros(16384, np.int32)
+        d = np.zeros(16384, np.float32)
+        n = _chk(lib().psp_aligner_correspondences(self.h, 16384, _p(f), _p(m), _p(d)))
+        return {"status": status, "pose": pose, "iterations": it.value, "num_correspondences": nc.value,
+                "num_inliers": ni.value, "chi": chi.value, "stats": rows[:it.value],
+                "corr": (f[:n].copy(), m[:n].copy(), d[:n].copy())}
+
+
+class Manager:
+    """srrg2_core::ConfigurableManager: read a .conf, look modules up by name"""
+
+    def __init__(self, conf_path=None, text=None):
+        self.h = C.c_void_p(lib().psp_manager_create())
+        if conf_path is not None:
+            self.read(conf_path)
+        if text is not None:
+            _chk(lib().psp_manager_read_string(self.h, text.encode()))
+
+    def close(self):
+        if self.h:
+            lib().psp_manager_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def read(self, path):
+        return _chk(lib().psp_manager_read(self.h, str(path).encode()))
+
+    def write(self, path, names=()):
+        arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
+        _chk(lib().psp_manager_write(self.h, str(path).encode(), len(names), arr))
+
+    def __len__(self):
+        return lib().psp_manager_count(self.h)
+
+    def modules(self):
+        return [Module(lib().psp_manager_at(self.h, i), self) for i in range(len(self))]
+
+    def get(self, name):
+        h = lib().psp_manager_get_by_name(self.h, name.encode())
+        if not h:
+            raise KeyError(name)
+        return Module(h, self)
+
+    def create(self, class_name, name=""):
+        h = lib().psp_manager_create_module(self.h, class_name.encode(), name.encode())
+        return Module(h, self)
+
+
+def is_registered(class_name):
+    return bool(lib().psp_class_is_registered(class_name.encode()))

@@ -55,6 +55,13 @@ def load_gray(name):
     return im
 
 
+def load_depth(name):
+    """16-bit depth fixtures (re-encoded losslessly from the reference's .pgm by tools/make_golden.py)"""
+    im = load_gray(name)
+    assert im.dtype == np.uint16, name
+    return im
+
+
 def fast_detect(img, thr, nms=True, mask=None, cap=200000):
     img = _img(img)
     xy = np.zeros((cap, 2), np.float32)
@@ -374,3 +381,63 @@ def pose_mul(a, b):
     o = np.zeros(12, np.float64)
     lib().orc_pose_mul_f64(_p(a), _p(b), _p(o))
     return o
+
+
+# ---- aligner loop (srrg2_slam_interfaces MultiAligner3DQR, external) --------------------------
+# ORACLE restatement of one frame-to-map alignment, built from the oracle primitives above: per iteration
+# finder.compute (state machine + window search + filter) -> setupFactor (per-correspondence information,
+# aligner_slice_processor_projective.cpp:41-57; stereo mean disparity :78-88) -> linearise (fp64) -> GN step.
+ALIGNER_STATUS = {"Fail": 0, "Success": 1, "NotEnoughCorrespondences": 2, "NotEnoughInliers": 3}
+
+
+def mean_disparity_f32(fixed):
+    """fp32 accumulation in cloud order (aligner_slice_processor_projective.cpp:80-85)"""
+    acc = np.float32(0)
+    for p in np.asarray(fixed, np.float32):
+        acc = np.float32(acc + np.float32(p[0] - p[2]))
+    return float(np.float32(acc / np.float32(len(fixed)))) if len(fixed) else 0.0
+
+
+def align(pf, kind, K, rows, cols, fixed, moving_xyz, diag, init_pose=None, n_opt=None, baseline=(0, 0, 0),
+          inverse_depth_weighting=False, robustifier="saturated", chi_threshold=25.0, max_iterations=100,
+          damping=0.0, min_num_inliers=6, min_num_correspondences=0):
+    """pf: an O.ProjectiveFinder with fixed / moving already set.  Returns dict(status, pose, stats, corr)."""
+    fixed = np.ascontiguousarray(fixed, np.float32)
+    moving_xyz = np.ascontiguousarray(moving_xyz, np.float32).reshape(-1, 3)
+    pose = np.eye(3, 4, dtype=np.float64).reshape(12) if init_pose is None else \
+        np.asarray(init_pose, np.float32).astype(np.float64).reshape(12)
+    md = mean_disparity_f32(fixed) if (kind == "stereo" and inverse_depth_weighting) else 0.0
+    lcfg = linearize_cfg(kind, np.asarray(K, np.float32), cols, rows, np.asarray(baseline, np.float32), md,
+                         robustifier, chi_threshold)
+    diag = np.asarray(diag, np.float32)
+    d3 = np.zeros(3, np.float32)
+    d3[:len(diag)] = diag
+    stats, corr, enough = [], (np.zeros(0, np.int32),) * 2 + (np.zeros(0, np.float32),), True
+    last = None
+    for it in range(max_iterations):
+        pf.set_estimate(pose.astype(np.float32))
+        corr = pf.compute()
+        fi, mi, _ = corr
+        if len(fi) < max(min_num_correspondences, 1):
+            stats.append((len(fi), 0, 0, 0.0))
+            enough = False
+            break
+        info = np.zeros((len(fixed), 3), np.float64)
+        for f, m in zip(fi, mi):
+            d = d3.copy()
+            n = 0 if n_opt is None else int(n_opt[m])
+            if n > 2:
+                d = (d * np.float32(1 + np.log(float(n)))).astype(np.float32)
+            info[f] = d
+        H, b, st = linearize(lcfg, pose, moving_xyz, fixed, fi, mi, info)
+        rc, new_pose, _ = gn_step(H, b, damping, pose)
+        last = st
+        stats.append((len(fi), st["inliers"], st["outliers"], st["chi"]))
+        if rc != 0:
+            break
+        pose = new_pose
+    if not enough:
+        status = ALIGNER_STATUS["NotEnoughCorrespondences"]
+    else:
+        status = ALIGNER_STATUS["Success"] if last and last["inliers"] >= min_num_inliers else ALIGNER_STATUS["NotEnoughInliers"]
+    return {"status": status, "pose": pose, "stats": np.asarray(stats, np.float64).reshape(-1, 4), "corr": corr}

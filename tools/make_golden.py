@@ -40,3 +40,22 @@ shutil.copy(REF / "scene_flow/gt_stereo_matching_threshold-100.txt",
             OUT / "scene_flow_gt_stereo_matching_threshold-100.txt")
 (OUT / "MANIFEST.json").write_text(json.dumps(manifest, indent=1, sort_keys=True) + "\n")
 print(len(manifest), "fixtures ->", OUT)
+
+# ---- hot-path subsets of the shipped configurations -------------------------------------------------------
+# The full files are read UNCHANGED from /root/reference/configurations by our BOSS reader
+# (srrg2_proslam_b200/host/pslam_boss.cpp) and the modules on the frontend path -- with everything they link
+# to -- are written back by our writer.  The GPU box has no /root/reference, so these derived files are what the
+# `-m gpu` plugin tests load there; tests/test_plugin_cpu.py checks here that they agree with the originals.
+sys.path.insert(0, str(OUT.parent.parent))
+from srrg2_proslam_b200 import plugin as P  # noqa: E402
+
+CONF = pathlib.Path("/root/reference/configurations")
+HOT = {"kitti": ["adaptor_stereo_projective", "aligner", "cf_bruteforce"],
+       "euroc": ["adaptor_stereo_projective", "aligner", "cf_bruteforce"],
+       "icl": ["tracker_slice_processor_projective_depth", "aligner", "cf_bruteforce_2d", "cf_bruteforce_3d"]}
+(OUT / "configurations").mkdir(exist_ok=True)
+for name, roots in HOT.items():
+    m = P.Manager(CONF / f"{name}.conf")
+    roots = [r for r in roots if any(x.name == r for x in m.modules())]
+    m.write(OUT / "configurations" / f"{name}_hotpath.conf", roots)
+    print(name, "->", roots)
