@@ -8,6 +8,7 @@
 #include "pslam_kernels.cuh"
 
 #include "../../include/pslam_orb_pattern.h"
+#include "orb_schedule.h"
 
 namespace {
 
@@ -69,52 +70,102 @@ assemble_features_kernel(const uint8_t* __restrict__ images, long long image_pit
 }
 
 // ---------------------------------------------------------------------------------------------
-// K3b: ORB-256 (angle 0, bit_pattern_31_) on the blurred image: one warp per keypoint, the
-// 31x31 patch staged in shared memory, lane l computes descriptor byte l (pairs 8l..8l+7).
+// K3b: ORB-256 (angle 0, bit_pattern_31_) on the blurred image: one warp per keypoint, lane l computes
+// descriptor byte l (pairs 8l..8l+7).
+//   * staging: ONE TMA box load (cp.async.bulk.tensor.3d) per keypoint brings the patch from the blur map (L2 / HBM)
+//     straight into shared memory -- no LSU wavefronts for the patch bytes.  A TMA box has to start on a 16-byte
+//     boundary (an unaligned start coordinate faults: tools/debug/dbg_tma.cu), so the box is the 48 x 31 bytes at
+//     ((x-15) & ~15, y-15, image) and every sample offset gets shift = (x-15) & 15 added.  Two patch buffers per
+//     warp: the box of the next keypoint is in flight while the current one is sampled; one mbarrier per buffer.
+//     (The LDG-based staging this replaces ran at 90 % l1tex utilisation: profiles/r01d_other_kernels_ncu.txt.)
+//   * sampling: 16 byte loads per lane from the dense 48-byte rows in the bank-conflict-minimising order of
+//     orb_schedule.h (which pair a lane visits when, and which end it reads first, is free: the bits are
+//     reassembled in registers).
 // ---------------------------------------------------------------------------------------------
 constexpr int K4_WARPS = 8;
-constexpr int PATCH = 31, PATCH_PITCH = 33;
+constexpr int PATCH = 31, PATCH_BOX_BYTES = PATCH * PSLAM_ORB_PATCH_PITCH, PATCH_BUF = 1536;
+static_assert(PSLAM_ORB_PATCH_PITCH == 48, "the TMA box rows are 48 bytes: 15 bytes of alignment slack + 31 + 2");
 
 __constant__ signed char c_pattern[256 * 4];
+// per-lane schedule tables: read with lane-varying indices, so they live in global memory (coalesced, L1 / L2
+// resident) -- the constant cache would serialise the 32 different addresses of a warp
+__device__ uint16_t g_sched_off[16][32];
+__device__ uint8_t g_sched_bit[8][32];
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void tma_patch_load(const CUtensorMap* tmap, uint32_t dst, uint32_t bar, int x0, int y0, int img) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(PATCH_BOX_BYTES) : "memory");
+  asm volatile(
+    "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+    ::"r"(dst), "l"(tmap), "r"(bar), "r"(x0), "r"(y0), "r"(img)
+    : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+    "{\n"
+    ".reg .pred p;\n"
+    "WAIT_%=:\n"
+    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+    "@p bra DONE_%=;\n"
+    "bra WAIT_%=;\n"
+    "DONE_%=:\n"
+    "}" ::"r"(bar), "r"(parity)
+    : "memory");
+}
 
 __global__ void __launch_bounds__(K4_WARPS * 32)
-orb_describe_kernel(const uint8_t* __restrict__ blur, int map_pitch, long long map_slot,
-                    const float2* __restrict__ xy, const int* __restrict__ count, int max_features,
-                    int slot_base, uint32_t* __restrict__ desc) {
-  __shared__ uint8_t s_patch[K4_WARPS][PATCH * PATCH_PITCH + 3];
-  __shared__ uint16_t s_off[16][32];  // [2*k + {a,b}][lane] byte offsets into the patch
+orb_describe_kernel(const __grid_constant__ CUtensorMap tmap, const float2* __restrict__ xy,
+                    const int* __restrict__ count, int max_features, int slot_base, uint32_t* __restrict__ desc) {
+  __shared__ __align__(128) uint8_t s_patch[K4_WARPS][2][PATCH_BUF];
+  __shared__ __align__(8) unsigned long long s_bar[K4_WARPS][2];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < 512; i += K4_WARPS * 32) {
-    const int l = i & 31, j = i >> 5;  // j = 2*k + ab
-    const int pair = 8 * l + (j >> 1);
-    const int xo = c_pattern[4 * pair + 2 * (j & 1)], yo = c_pattern[4 * pair + 2 * (j & 1) + 1];
-    s_off[j][l] = (uint16_t) ((yo + 15) * PATCH_PITCH + (xo + 15));
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar[wid][0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar[wid][1])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  __syncthreads();
-  uint16_t off[16];
+  __syncwarp();
+  // this lane's schedule: byte offsets of the 16 samples, (bit position | flip << 3) of the 8 pairs
+  unsigned off[8], bits = 0;
 #pragma unroll
-  for (int j = 0; j < 16; ++j) off[j] = s_off[j][lane];
-
+  for (int j = 0; j < 8; ++j) {
+    off[j] = (unsigned) __ldg(&g_sched_off[2 * j][lane]) | ((unsigned) __ldg(&g_sched_off[2 * j + 1][lane]) << 16);
+    bits |= (unsigned) __ldg(&g_sched_bit[j][lane]) << (4 * j);
+  }
   const int image = blockIdx.y;
   const size_t slot = (size_t) slot_base + image;
   const int n = count[slot];
-  const uint8_t* b = blur + (size_t) image * map_slot;
-  uint8_t* patch = s_patch[wid];
-  for (int i = blockIdx.x * K4_WARPS + wid; i < n; i += gridDim.x * K4_WARPS) {
-    const float2 p = xy[slot * max_features + i];
-    const int x = (int) p.x, y = (int) p.y;
-    const uint8_t* src = b + (size_t) (y - 15) * map_pitch + (x - 15);
+  const float2* pxy = xy + slot * max_features;
+  const int stride = gridDim.x * K4_WARPS;
+  const uint32_t bar0 = smem_u32(&s_bar[wid][0]), buf0 = smem_u32(&s_patch[wid][0][0]);
+  int i = blockIdx.x * K4_WARPS + wid;
+  if (i < n && lane == 0) {
+    const float2 p = pxy[i];
+    tma_patch_load(&tmap, buf0, bar0, ((int) p.x - 15) & ~15, (int) p.y - 15, image);
+  }
+  for (int k = 0; i < n; i += stride, ++k) {
+    const int b = k & 1;
+    // all lanes are done with buffer b ^ 1 (sampled in the previous iteration): refill it with the next patch
     __syncwarp();
-    if (lane < PATCH) {
-#pragma unroll 4
-      for (int r = 0; r < PATCH; ++r) patch[r * PATCH_PITCH + lane] = __ldg(src + (size_t) r * map_pitch + lane);
+    if (lane == 0 && i + stride < n) {
+      const float2 p = pxy[i + stride];
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      tma_patch_load(&tmap, buf0 + (b ^ 1) * PATCH_BUF, bar0 + (b ^ 1) * 8, ((int) p.x - 15) & ~15, (int) p.y - 15, image);
     }
-    __syncwarp();
+    const int shift = ((int) pxy[i].x - 15) & 15;  // column of the patch inside the aligned box
+    mbar_wait(bar0 + b * 8, (unsigned) (k >> 1) & 1u);
+    const uint8_t* patch8 = s_patch[wid][b] + shift;
     uint32_t byte = 0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int a = patch[off[2 * k]], c = patch[off[2 * k + 1]];
-      byte |= (uint32_t) (a < c) << k;
+    for (int j = 0; j < 8; ++j) {
+      const int first = patch8[off[j] & 0xffffu], second = patch8[off[j] >> 16];
+      const unsigned bj = bits >> (4 * j);
+      const int m = -(int) ((bj >> 3) & 1u);          // flip: (second, first) were read as (first, second)
+      const int d = ((first - second) ^ m) - m;        // a - c  with a = end A, c = end B of the pair
+      byte |= ((unsigned) d >> 31) << (bj & 7u);       // bit = (a < c)
     }
     // gather 4 bytes into one word: lanes 4w..4w+3 -> word w
     const uint32_t b1 = __shfl_down_sync(0xffffffffu, byte, 1);
@@ -125,7 +176,6 @@ orb_describe_kernel(const uint8_t* __restrict__ blur, int map_pitch, long long m
     }
   }
 }
-
 
 // ---- monocular + depth adaptor: order-preserving compaction of the features with a valid depth ---------------
 // Replaces RawDataPreprocessorMonocularDepth::_readDepth (.../sensor_processing/raw_data_preprocessor_monocular_depth.cpp:157-180):
@@ -178,6 +228,8 @@ mono_depth_kernel(const void* __restrict__ depth, int depth_type, int depth_rows
 // ---- host-side launchers -----------------------------------------------------------------------
 int pslam_k_upload_pattern(pslam_ctx* ctx) {
   PSLAM_CUDA_TRY(ctx, cudaMemcpyToSymbol(c_pattern, PSLAM_ORB_PATTERN, sizeof(PSLAM_ORB_PATTERN)));
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyToSymbol(g_sched_off, PSLAM_ORB_SCHED_OFF, sizeof(PSLAM_ORB_SCHED_OFF)));
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyToSymbol(g_sched_bit, PSLAM_ORB_SCHED_BIT, sizeof(PSLAM_ORB_SCHED_BIT)));
   return PSLAM_OK;
 }
 
@@ -192,14 +244,39 @@ int pslam_k_assemble(pslam_ctx* ctx, const uint8_t* d_images, long long image_pi
 }
 
 int pslam_k_describe(pslam_ctx* ctx, int n_images, int slot_base) {
-  // enough warps for max_features per image, capped: grid-stride over the image's features
+  // few CTAs per image: every warp amortises its schedule load over ~max_features / (16 * 8) keypoints
   int bx = (ctx->lim.max_features + K4_WARPS - 1) / K4_WARPS;
-  if (bx > 64) bx = 64;
+  if (bx > 16) bx = 16;
   dim3 grid(bx, n_images);
-  orb_describe_kernel<<<grid, K4_WARPS * 32, 0, ctx->stream>>>(
-    ctx->d_blur, ctx->map_pitch, (long long) ctx->map_slot, ctx->d_xy, ctx->d_count,
-    ctx->lim.max_features, slot_base, ctx->d_desc);
+  orb_describe_kernel<<<grid, K4_WARPS * 32, 0, ctx->stream>>>(ctx->blur_tmap, ctx->d_xy, ctx->d_count,
+                                                              ctx->lim.max_features, slot_base, ctx->d_desc);
   PSLAM_LAUNCH_CHECK(ctx, "orb_describe_kernel");
+  return PSLAM_OK;
+}
+
+// TMA descriptor of the blur maps (created once per context).  cuTensorMapEncodeTiled is fetched through the
+// runtime (cudaGetDriverEntryPoint), so the library does not link against libcuda.
+int pslam_k_make_blur_tmap(pslam_ctx* ctx, int work_images) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  PSLAM_CUDA_TRY(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (!fn || qres != cudaDriverEntryPointSuccess)
+    return pslam_set_error(ctx, PSLAM_E_CUDA, "cuTensorMapEncodeTiled is not available in this driver", cudaSuccess);
+  const cuuint64_t dims[3] = {(cuuint64_t) ctx->map_pitch, (cuuint64_t) ctx->lim.max_rows, (cuuint64_t) work_images};
+  const cuuint64_t strides[2] = {(cuuint64_t) ctx->map_pitch, (cuuint64_t) ctx->map_slot};  // bytes, dims 1 and 2
+  const cuuint32_t box[3] = {PSLAM_ORB_PATCH_PITCH, PATCH, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = ((EncodeFn) fn)(&ctx->blur_tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, ctx->d_blur, dims, strides, box, estr,
+                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char msg[96];
+    snprintf(msg, sizeof msg, "cuTensorMapEncodeTiled failed (CUresult %d)", (int) r);
+    return pslam_set_error(ctx, PSLAM_E_CUDA, msg, cudaSuccess);
+  }
   return PSLAM_OK;
 }
 

@@ -5,12 +5,12 @@
 // and the assembly loop of RawDataPreprocessorStereoProjective::compute
 //   (.../sensor_processing/raw_data_preprocessor_stereo_projective.cpp:105-132).
 //
-// One CTA per stereo pair.  Both feature sets are sorted by (row, col) with a shared-memory bitonic
-// sort (keys are unique, so any sort gives the reference's std::sort order, :36-41).  The
-// reference's single running `index_right` only couples left features of the SAME image row
-// (it is reset to the first right feature of the next row by the two skip loops, :97-126), so each
-// run of equal-row left features is scanned by one thread exactly as the reference does, all
-// runs in parallel.  Results are emitted in the reference's scan order by a block-wide scan.
+// One CTA per stereo pair.  Both feature sets are sorted by (row, col) in shared memory (keys are unique, so any
+// sort gives the reference's std::sort order, :36-41): counting sort by row for the device pipeline, bitonic sort
+// for arbitrary host coordinates.  The reference's single running `index_right` only couples left features of the
+// SAME image row (it is reset to the first right feature of the next row by the two skip loops, :97-126), so the
+// row runs are independent: one warp per run, descriptors of the run in registers, shuffle argmin with the
+// reference's tie rules.  Results are emitted in the reference's scan order by a block-wide scan.
 #include <float.h>
 
 #include "pslam_internal.cuh"
@@ -18,16 +18,10 @@
 
 namespace {
 
-constexpr int EP_THREADS = 512;
+constexpr int EP_THREADS = 256;
+constexpr int EP_ROWS = 4096;  // counting-sort path: 0 <= row < EP_ROWS (the device pipeline: row < max_rows)
 
-struct EpSmem {
-  unsigned long long* keys;  // [P]
-  short *rowL, *colL, *idxL, *rowR, *colR, *idxR;  // [M] each
-  short* match;              // [M] sorted right position matched to sorted left position, -1 none
-  unsigned short* dist;      // [M]
-  unsigned char* usedR;      // [M]
-};
-
+// ---- (row, col) sort, general path: shared-memory bitonic sort of 64-bit keys (any 32-bit row, 16-bit col) ----
 __device__ __forceinline__ void ep_sort_side(const float2* __restrict__ xy, int n, int P,
                                              unsigned long long* keys, short* row, short* col,
                                              short* idx) {
@@ -68,6 +62,62 @@ __device__ __forceinline__ void ep_sort_side(const float2* __restrict__ xy, int 
   __syncthreads();
 }
 
+// ---- (row, col) sort, pipeline path: counting sort by row + per-row insertion sort by column.  Keys are unique,
+// so the result is the order std::sort gives the reference (epipolar_impl.cpp:36-41).
+// hist / cursor: EP_ROWS + 1 unsigned shorts each; tmp: n uint32 ((col << 16) | idx)
+__device__ __forceinline__ void ep_count_sort_side(const float2* __restrict__ xy, int n, unsigned short* hist,
+                                                   unsigned short* cursor, uint32_t* tmp, short* row, short* col,
+                                                   short* idx, int* s_warp) {
+  const int tid = threadIdx.x;
+  for (int r = tid; r <= EP_ROWS; r += EP_THREADS) hist[r] = 0;
+  __syncthreads();
+  // 16-bit shared atomics do not exist: count into the aligned 32-bit word that holds the pair
+  unsigned* hist32 = reinterpret_cast<unsigned*>(hist);
+  for (int i = tid; i < n; i += EP_THREADS) {
+    const int r = (int) xy[i].y;
+    atomicAdd(&hist32[r >> 1], (r & 1) ? 0x10000u : 1u);
+  }
+  __syncthreads();
+  // exclusive scan over rows: EP_ROWS / EP_THREADS consecutive rows per thread
+  constexpr int PER = EP_ROWS / EP_THREADS;
+  int local[PER], sum = 0;
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    local[k] = sum;
+    sum += hist[tid * PER + k];
+  }
+  int total;
+  const int base = block_exclusive_scan<EP_THREADS>(sum, s_warp, &total);
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    hist[tid * PER + k] = (unsigned short) (base + local[k]);  // start of row
+    cursor[tid * PER + k] = (unsigned short) (base + local[k]);
+  }
+  if (tid == 0) hist[EP_ROWS] = (unsigned short) total;
+  __syncthreads();
+  unsigned* cur32 = reinterpret_cast<unsigned*>(cursor);
+  for (int i = tid; i < n; i += EP_THREADS) {
+    const float2 p = xy[i];
+    const int r = (int) p.y, c = (int) p.x;
+    const unsigned old = atomicAdd(&cur32[r >> 1], (r & 1) ? 0x10000u : 1u);
+    const int pos = (r & 1) ? (int) (old >> 16) : (int) (old & 0xffffu);
+    tmp[pos] = ((unsigned) c << 16) | (unsigned) i;
+    row[pos] = (short) r;  // every slot of a row's range holds that row
+  }
+  __syncthreads();
+  // order inside a row: rank of (col, idx) among the row's entries (unique values), one thread per feature
+  for (int i = tid; i < n; i += EP_THREADS) {
+    const int r = row[i];
+    const int b = hist[r], e = hist[r + 1];
+    const uint32_t v = tmp[i];
+    int rank = 0;
+    for (int j = b; j < e; ++j) rank += tmp[j] < v ? 1 : 0;
+    col[b + rank] = (short) (v >> 16);
+    idx[b + rank] = (short) (v & 0xffffu);
+  }
+  __syncthreads();
+}
+
 // ordered in-place removal of flagged entries from (row, col, idx); tmp >= 3*n shorts
 __device__ __forceinline__ int ep_compact(short* row, short* col, short* idx, int n,
                                           const unsigned char* removed, short* tmp, int* s_warp) {
@@ -96,6 +146,15 @@ __device__ __forceinline__ int ep_compact(short* row, short* col, short* idx, in
   return running;
 }
 
+// GENERAL = true : any coordinates (host-pointer entry point), bitonic sort
+// GENERAL = false: 0 <= row < EP_ROWS (device pipeline), counting sort -- no 64-bit key array in shared memory
+//
+// Matching: the reference's running `index_right` only couples left features of the SAME image row (it is reset to
+// the first right feature of the next row by the two skip loops, :97-126).  One WARP owns a left row run: lane t
+// holds the descriptor of the run's t-th left and t-th right feature in registers (one round of loads per run);
+// the left features are visited in order, each lane scores "its" right candidate and a 5-step shuffle butterfly
+// yields (best, second, first position of the best) with the reference's tie rules.
+template <bool GENERAL>
 __global__ void __launch_bounds__(EP_THREADS)
 epipolar_kernel(const float2* __restrict__ xy, const uint32_t* __restrict__ desc,
                 const int* __restrict__ count, int M, float max_dist, float max_ratio, int max_disp,
@@ -105,17 +164,18 @@ epipolar_kernel(const float2* __restrict__ xy, const uint32_t* __restrict__ desc
                 float* __restrict__ st_dist, int* __restrict__ st_count) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ int s_warp[33];
-  const int tid = threadIdx.x;
+  __shared__ int s_nruns;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int pair = blockIdx.x;
   const int imgL = 2 * pair, imgR = 2 * pair + 1;
   int nL = count[imgL], nR = count[imgR];
-  int P = 1;
-  while (P < max(nL, nR)) P <<= 1;
 
-  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem);
+  // shared memory: [sort scratch] | rowL colL idxL rowR colR idxR | match dist | usedR usedL | runs
   int Pmax = 1;
   while (Pmax < M) Pmax <<= 1;
-  short* rowL = reinterpret_cast<short*>(smem + (size_t) Pmax * 8);
+  size_t scratch = GENERAL ? (size_t) Pmax * 8 : (size_t) (EP_ROWS + 2) * 2 * 2;
+  if (scratch < (size_t) M * 6) scratch = (size_t) M * 6;  // ep_compact needs 3 * M shorts (same rule as ep_smem_bytes)
+  short* rowL = reinterpret_cast<short*>(smem + scratch);
   short* colL = rowL + M;
   short* idxL = colL + M;
   short* rowR = idxL + M;
@@ -125,14 +185,26 @@ epipolar_kernel(const float2* __restrict__ xy, const uint32_t* __restrict__ desc
   unsigned short* dist = reinterpret_cast<unsigned short*>(match + M);
   unsigned char* usedR = reinterpret_cast<unsigned char*>(dist + M);
   unsigned char* usedL = usedR + M;
+  short* runs = reinterpret_cast<short*>(usedL + M);  // [M] starts of the left row runs
 
   const float2* xyL = xy + (size_t) imgL * M;
   const float2* xyR = xy + (size_t) imgR * M;
   const uint4* descL = reinterpret_cast<const uint4*>(desc + (size_t) imgL * M * 8);
   const uint4* descR = reinterpret_cast<const uint4*>(desc + (size_t) imgR * M * 8);
 
-  ep_sort_side(xyL, nL, P, keys, rowL, colL, idxL);
-  ep_sort_side(xyR, nR, P, keys, rowR, colR, idxR);
+  if (GENERAL) {
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem);
+    int P = 1;
+    while (P < max(nL, nR)) P <<= 1;
+    ep_sort_side(xyL, nL, P, keys, rowL, colL, idxL);
+    ep_sort_side(xyR, nR, P, keys, rowR, colR, idxR);
+  } else {
+    unsigned short* hist = reinterpret_cast<unsigned short*>(smem);
+    unsigned short* cursor = hist + EP_ROWS + 2;
+    uint32_t* tmp = reinterpret_cast<uint32_t*>(match);  // match + dist = 4 M bytes, not in use yet
+    ep_count_sort_side(xyL, nL, hist, cursor, tmp, rowL, colL, idxL, s_warp);
+    ep_count_sort_side(xyR, nR, hist, cursor, tmp, rowR, colR, idxR, s_warp);
+  }
 
   int* o_fixed = ep_fixed + (size_t) pair * M;
   int* o_moving = ep_moving + (size_t) pair * M;
@@ -148,45 +220,124 @@ epipolar_kernel(const float2* __restrict__ xy, const uint32_t* __restrict__ desc
       usedL[i] = 0;
     }
     for (int i = tid; i < nR; i += EP_THREADS) usedR[i] = 0;
+    // ordered list of the left row-run starts
+    int n_runs = 0;
+    for (int base = 0; base < nL; base += EP_THREADS) {
+      const int i = base + tid;
+      const int is_start = (i < nL && (i == 0 || rowL[i] != rowL[i - 1])) ? 1 : 0;
+      int total;
+      const int o = block_exclusive_scan<EP_THREADS>(is_start, s_warp, &total);
+      if (is_start) runs[n_runs + o] = (short) i;
+      n_runs += total;
+    }
     __syncthreads();
     if (nR > 0) {
-      for (int i = tid; i < nL; i += EP_THREADS) {
-        if (i != 0 && rowL[i] == rowL[i - 1]) continue;  // not the start of a row run
-        const int row_left = rowL[i] + off;
+      for (int run = wid; run < n_runs; run += EP_THREADS / 32) {
+        const int i0 = runs[run];
+        const int i1 = run + 1 < n_runs ? (int) runs[run + 1] : nL;
+        const int row_left = rowL[i0] + off;
         int lo = 0, hi = nR;  // first right feature with row >= row_left
         while (lo < hi) {
           const int mid = (lo + hi) >> 1;
           if (rowR[mid] < row_left) lo = mid + 1; else hi = mid;
         }
-        int index_right = lo;
-        for (int j = i; j < nL && rowL[j] == rowL[i]; ++j) {
-          if (index_right >= nR || rowR[index_right] != row_left) break;
-          const int col_left = colL[j];
-          const uint4 a0 = __ldg(descL + 2 * (int) idxL[j]), a1 = __ldg(descL + 2 * (int) idxL[j] + 1);
-          int best = INT_MAX, second = INT_MAX, best_pos = 0;
-          for (int s = index_right; s < nR && rowR[s] == row_left; ++s) {
-            const int disparity = col_left - colR[s];
-            if (disparity < 0) break;
-            if (disparity > max_disp) continue;
-            const uint4 b0 = __ldg(descR + 2 * (int) idxR[s]), b1 = __ldg(descR + 2 * (int) idxR[s] + 1);
-            const int d = hamming256(a0, a1, b0, b1);
-            if (d < best) {
-              second = best;
-              best = d;
-              best_pos = s;
-            } else if (d < second) {
-              second = d;
-            }
+        const int s0 = lo;
+        if (s0 >= nR || rowR[s0] != row_left) continue;
+        hi = nR;  // first right feature with row > row_left
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (rowR[mid] <= row_left) lo = mid + 1; else hi = mid;
+        }
+        const int s1 = lo;
+        const int nr = s1 - s0;
+        // right side: up to 32 features of the row live in registers (lane t <-> s0 + t); longer rows are read
+        // from L1 / L2 per left feature, 32 candidates at a time
+        const bool cached = nr <= 32;
+        uint4 b0 = make_uint4(0, 0, 0, 0), b1 = b0;
+        int cr = 0;
+        if (cached && lane < nr) {
+          const int f = idxR[s0 + lane];
+          b0 = __ldg(descR + 2 * f);
+          b1 = __ldg(descR + 2 * f + 1);
+          cr = colR[s0 + lane];
+        }
+        int ir = s0;  // the reference's index_right
+        for (int jb = i0; jb < i1 && ir < s1; jb += 32) {
+          // left side: 32 features of the run at a time in registers (lane t <-> jb + t)
+          uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0;
+          int cl = 0;
+          if (jb + lane < i1) {
+            const int f = idxL[jb + lane];
+            a0 = __ldg(descL + 2 * f);
+            a1 = __ldg(descL + 2 * f + 1);
+            cl = colL[jb + lane];
           }
-          if (best == INT_MAX) continue;
-          const float fb = (float) best;
-          const float fs = (second == INT_MAX) ? FLT_MAX : (float) second;
-          if (fb < max_dist && __fdiv_rn(fb, fs) < max_ratio) {  // :171-173
-            match[j] = (short) best_pos;
-            dist[j] = (unsigned short) best;
-            usedL[j] = 1;
-            usedR[best_pos] = 1;
-            index_right = best_pos + 1;  // ordering constraint :181
+          const int nj = min(32, i1 - jb);
+          for (int jj = 0; jj < nj; ++jj) {
+            if (ir >= s1) break;  // :128-131
+            const int col_left = __shfl_sync(0xffffffffu, cl, jj);
+            uint4 q0, q1;
+            q0.x = __shfl_sync(0xffffffffu, a0.x, jj); q0.y = __shfl_sync(0xffffffffu, a0.y, jj);
+            q0.z = __shfl_sync(0xffffffffu, a0.z, jj); q0.w = __shfl_sync(0xffffffffu, a0.w, jj);
+            q1.x = __shfl_sync(0xffffffffu, a1.x, jj); q1.y = __shfl_sync(0xffffffffu, a1.y, jj);
+            q1.z = __shfl_sync(0xffffffffu, a1.z, jj); q1.w = __shfl_sync(0xffffffffu, a1.w, jj);
+            // candidates: s >= index_right with 0 <= col_left - colR[s] <= max_disp.  The right run is sorted by
+            // column, so the reference's "disparity < 0 => break" drops exactly the candidates with disparity < 0.
+            int best = INT_MAX, second = INT_MAX, pos = INT_MAX;
+            if (cached) {
+              const int s = s0 + lane;
+              const int disparity = col_left - cr;
+              if (s >= ir && lane < nr && disparity >= 0 && disparity <= max_disp) {
+                best = hamming256(q0, q1, b0, b1);
+                pos = s;
+              }
+            } else {
+              int lo2 = ir, hi2 = s1;  // skip the features left of the disparity window
+              while (lo2 < hi2) {
+                const int mid = (lo2 + hi2) >> 1;
+                if (col_left - (int) colR[mid] > max_disp) lo2 = mid + 1; else hi2 = mid;
+              }
+              for (int sb = lo2; sb < s1; sb += 32) {
+                const int s = sb + lane;
+                const int disparity = s < s1 ? col_left - (int) colR[s] : -1;
+                if (disparity >= 0 && disparity <= max_disp) {
+                  const int f = idxR[s];
+                  const int d = hamming256(q0, q1, __ldg(descR + 2 * f), __ldg(descR + 2 * f + 1));
+                  if (d < best) {  // this lane's candidates arrive in scan order
+                    second = best;
+                    best = d;
+                    pos = s;
+                  } else if (d < second) {
+                    second = d;
+                  }
+                }
+                if (__any_sync(0xffffffffu, disparity < 0)) break;
+              }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              const int ob = __shfl_xor_sync(0xffffffffu, best, o), os = __shfl_xor_sync(0xffffffffu, second, o),
+                        op = __shfl_xor_sync(0xffffffffu, pos, o);
+              if (ob < best || (ob == best && op < pos)) {  // the other side wins (first position wins ties)
+                second = min(os, best);
+                best = ob;
+                pos = op;
+              } else {
+                second = min(second, ob);
+              }
+            }
+            if (best == INT_MAX) continue;
+            const float fb = (float) best;
+            const float fs = (second == INT_MAX) ? FLT_MAX : (float) second;
+            if (fb < max_dist && __fdiv_rn(fb, fs) < max_ratio) {  // :171-173
+              if (lane == 0) {
+                match[jb + jj] = (short) pos;
+                dist[jb + jj] = (unsigned short) best;
+                usedL[jb + jj] = 1;
+                usedR[pos] = 1;
+              }
+              ir = pos + 1;  // ordering constraint :181
+            }
           }
         }
       }
@@ -210,8 +361,9 @@ epipolar_kernel(const float2* __restrict__ xy, const uint32_t* __restrict__ desc
     }
     if (oi + 1 < n_offsets) {  // prune matched candidates, keeping the order (:189-205)
       __syncthreads();
-      nL = ep_compact(rowL, colL, idxL, nL, usedL, reinterpret_cast<short*>(keys), s_warp);
-      nR = ep_compact(rowR, colR, idxR, nR, usedR, reinterpret_cast<short*>(keys), s_warp);
+      short* ctmp = reinterpret_cast<short*>(smem);  // the sort scratch holds >= 3 * M shorts (ep_smem_bytes)
+      nL = ep_compact(rowL, colL, idxL, nL, usedL, ctmp, s_warp);
+      nR = ep_compact(rowR, colR, idxR, nR, usedR, ctmp, s_warp);
     }
   }
   if (n_out > M) n_out = M;
@@ -323,20 +475,22 @@ int pslam_k_pack_stereo(pslam_ctx* ctx, int n_pairs, pslam_packed_stereo* out) {
   return PSLAM_OK;
 }
 
-static size_t ep_smem_bytes(int M) {
+static size_t ep_smem_bytes(int M, bool general) {
   int P = 1;
   while (P < M) P <<= 1;
-  return (size_t) P * 8 + (size_t) M * (7 * 2 + 2 + 2);
+  // sort scratch (also the 3 * M shorts of ep_compact) | 6 coordinate arrays, match, dist (shorts) | usedR, usedL | runs
+  size_t scratch = general ? (size_t) P * 8 : (size_t) (EP_ROWS + 2) * 2 * 2;
+  if (scratch < (size_t) M * 6) scratch = (size_t) M * 6;
+  return scratch + (size_t) M * (8 * 2 + 2 + 2);
 }
 
-int pslam_k_epipolar(pslam_ctx* ctx, int n_pairs, const pslam_match_cfg* cfg) {
+int pslam_k_epipolar(pslam_ctx* ctx, int n_pairs, const pslam_match_cfg* cfg, int general) {
   const int M = ctx->lim.max_features;
-  const size_t smem = ep_smem_bytes(M);
-  if (smem > 48 * 1024) {
-    PSLAM_CUDA_TRY(ctx, cudaFuncSetAttribute(epipolar_kernel,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-  }
-  epipolar_kernel<<<n_pairs, EP_THREADS, smem, ctx->stream>>>(
+  if (ctx->lim.max_rows > EP_ROWS) general = 1;
+  const size_t smem = ep_smem_bytes(M, general != 0);
+  auto kernel = general ? epipolar_kernel<true> : epipolar_kernel<false>;
+  if (smem > 48 * 1024) PSLAM_CUDA_TRY(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  kernel<<<n_pairs, EP_THREADS, smem, ctx->stream>>>(
     ctx->d_xy, ctx->d_desc, ctx->d_count, M, cfg->maximum_descriptor_distance,
     cfg->maximum_distance_ratio_to_second_best, cfg->maximum_disparity_pixels,
     cfg->epipolar_line_thickness_pixels, ctx->d_ep_fixed, ctx->d_ep_moving, ctx->d_ep_dist,

@@ -542,17 +542,22 @@ bin_select_kernel(const int* __restrict__ row_count, const uint32_t* __restrict_
     if (tid == 0) atomicOr(flags, PSLAM_FLAG_RAW_OVERFLOW);
     n = max_raw_per_bin;
   }
-  // selection (binned.cpp:180-200)
+  // selection (binned.cpp:180-200): keep all when fewer than the quota, else unstable std::sort by response and keep
+  // the first `quota` -- replayed move for move (libstdcxx_sort.h), warp-parallel when the region fits shared memory
   int kept = n;
   if ((unsigned long long) n >= quota) {
     kept = (int) quota;
     if (kept > 0) {
       if (n <= sort_cap) {
+        unsigned short* s_rpos = reinterpret_cast<unsigned short*>(s_sort + sort_cap);
         for (int i = tid; i < n; i += SEL_THREADS) s_sort[i] = seg[i];
         __syncthreads();
-        if (tid == 0) pslam_sort::std_sort_prefix(s_sort, n, kept, RespGreater());
+        if (tid < 32) {
+          const int se = pslam_sort::warp_std_sort_prefix(s_sort, s_rpos, n, kept, RespGreater());
+          if (tid == 0) s_rbegin = se;
+        }
         __syncthreads();
-        for (int i = tid; i < kept; i += SEL_THREADS) seg[i] = s_sort[i];
+        pslam_sort::block_final_positions<SEL_THREADS>(s_sort, s_rbegin, kept, seg, RespGreater());
       } else if (tid == 0) {
         pslam_sort::std_sort_prefix(seg, n, kept, RespGreater());
       }
@@ -613,7 +618,7 @@ int pslam_k_bin_select(pslam_ctx* ctx, int n_images, int rows, int cols, int nh,
   const float pc = static_cast<float>(cols) / static_cast<float>((size_t) nh);
   dim3 grid(nh * nv, n_images);
   const int sort_cap = ctx->lim.max_raw_per_bin < 2048 ? ctx->lim.max_raw_per_bin : 2048;
-  bin_select_kernel<<<grid, SEL_THREADS, (size_t) sort_cap * 4, ctx->stream>>>(
+  bin_select_kernel<<<grid, SEL_THREADS, (size_t) sort_cap * 6, ctx->stream>>>(
     ctx->d_row_count, ctx->d_row_kp, ctx->map_pitch, ctx->lim.max_rows, d_mask, ctx->map_pitch, rows, cols, nh, nv, pr,
     pc, ctx->d_raw, ctx->lim.max_raw_per_bin, ctx->lim.max_bins, ctx->d_raw_count, ctx->d_sel_count, quota, sort_cap,
     ctx->d_flags);

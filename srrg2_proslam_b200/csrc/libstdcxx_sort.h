@@ -200,4 +200,129 @@ PSLAM_HD void std_sort(T* a, int n, Comp comp) {
   std_sort_prefix(a, n, n, comp);
 }
 
+
+#if defined(__CUDACC__)
+// ---------------------------------------------------------------------------------------------------------
+// Warp-parallel replay of the same algorithm (device only).  Bit-exact with std_sort_prefix:
+//   * the unguarded Hoare partition is a pure function of the range's ORIGINAL contents: the k-th swap pairs the
+//     k-th "left stopper" (ascending index i with !comp(a[i], pivot)) with the k-th "right stopper" (descending
+//     index j with !comp(pivot, a[j])) for as long as L_k < R_k; the returned cut is L_0 when nothing is swapped,
+//     else min(L_K, R_{K-1}) with K the number of swaps.  Stoppers are found with ballots, 32 positions per step.
+//   * the final insertion sort is a STABLE sort of a sequence whose inversions are confined to quicksort leaves of
+//     <= 16 elements, so the final position of element i is i - #{j in [i-16, i): comp(a[i], a[j])}
+//     + #{j in (i, i+16]: comp(a[j], a[i])} -- evaluated by all threads of the block at once.
+// Control flow (introsort loop, pruning to the first `need` outputs, depth limit) is executed uniformly by the warp;
+// median-of-3 and the heap-sort fallback stay on lane 0.  tools/../tests: tests/test_gpu_stage1.py compares the
+// selected keypoints with the oracle (which calls the real std::sort) on every golden image.
+// a: shared memory, n <= 65535.  rpos: shared scratch of n uint16.  Must be called by all 32 lanes of one warp.
+// Returns sorted_end (see std_sort_prefix); the caller finishes with block_final_positions().
+template <typename T, typename Comp>
+__device__ __forceinline__ int warp_partition_(T* a, unsigned short* rpos, int first, int last, int pivot, Comp comp) {
+  const unsigned FULLM = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  const T p = a[pivot];
+  int nR = 0;
+  for (int base = last; base > first; base -= 32) {  // right stoppers, descending
+    const int i = base - 1 - lane;
+    const bool f = i >= first && !comp(p, a[i]);
+    const unsigned bal = __ballot_sync(FULLM, f);
+    if (f) rpos[nR + __popc(bal & lt)] = (unsigned short) i;
+    nR += __popc(bal);
+  }
+  __syncwarp();
+  int nL = 0, K = 0, lnext = 0x7fffffff;
+  for (int base = first; base < last; base += 32) {  // left stoppers, ascending; swap while L_k < R_k
+    const int i = base + lane;
+    const bool f = i < last && !comp(a[i], p);
+    const unsigned bal = __ballot_sync(FULLM, f);
+    const int k = nL + __popc(bal & lt);
+    int y = -1;
+    if (f && k < nR) y = rpos[k];
+    const bool do_swap = f && y > i;
+    const unsigned sw = __ballot_sync(FULLM, do_swap);
+    __syncwarp();
+    if (do_swap) {
+      const T t = a[y];
+      a[y] = a[i];
+      a[i] = t;
+    }
+    K += __popc(sw);
+    nL += __popc(bal);
+    const unsigned stop = bal & ~sw;  // first stopper that is not swapped = L_K
+    if (stop) {
+      lnext = base + (__ffs(stop) - 1);
+      break;
+    }
+  }
+  __syncwarp();
+  if (K > 0) {
+    const int r = rpos[K - 1];
+    return lnext < r ? lnext : r;
+  }
+  return lnext;
+}
+
+template <typename T, typename Comp>
+__device__ __forceinline__ int warp_std_sort_prefix(T* a, unsigned short* rpos, int n, int need, Comp comp) {
+  const int threshold = 16;
+  const int lane = threadIdx.x & 31;
+  if (n <= threshold) return n;
+  // explicit stack of deferred right parts: entry s lives in lane s (depth <= 2 * floor(log2 n) <= 30 entries)
+  int st_first = 0, st_last = 0, st_depth = 0;
+  int sp = 0;
+  int sorted_end = n;
+  if (lane == 0) {
+    st_first = 0;
+    st_last = n;
+    st_depth = 2 * lg_(n);
+  }
+  sp = 1;
+  while (sp > 0) {
+    --sp;
+    int first = __shfl_sync(0xffffffffu, st_first, sp), last = __shfl_sync(0xffffffffu, st_last, sp),
+        depth = __shfl_sync(0xffffffffu, st_depth, sp);
+    while (last - first > threshold) {
+      if (depth == 0) {
+        if (lane == 0) heap_sort_(a + first, last - first, comp);
+        __syncwarp();
+        break;
+      }
+      --depth;
+      const int mid = first + (last - first) / 2;
+      if (lane == 0) move_median_to_first_(a, first, first + 1, mid, last - 1, comp);
+      __syncwarp();
+      const int cut = warp_partition_(a, rpos, first + 1, last, first, comp);
+      if (cut < need) {
+        if (lane == sp) {
+          st_first = cut;
+          st_last = last;
+          st_depth = depth;
+        }
+        ++sp;
+      } else if (cut < sorted_end) {
+        sorted_end = cut;
+      }
+      last = cut;
+    }
+  }
+  __syncwarp();
+  return sorted_end;
+}
+
+// final insertion sort as a windowed stable rank; thread-parallel over the block.  out[pos] receives a[i] for the
+// positions pos < keep (the caller only needs the kept prefix).  Call after a __syncthreads().
+template <int NT, typename T, typename Comp>
+__device__ __forceinline__ void block_final_positions(const T* a, int sorted_end, int keep, T* out, Comp comp) {
+  for (int i = threadIdx.x; i < sorted_end; i += NT) {
+    const T v = a[i];
+    int pos = i;
+    const int lo = i - 16 > 0 ? i - 16 : 0, hi = i + 16 < sorted_end - 1 ? i + 16 : sorted_end - 1;
+    for (int j = lo; j < i; ++j) pos -= comp(v, a[j]) ? 1 : 0;
+    for (int j = i + 1; j <= hi; ++j) pos += comp(a[j], v) ? 1 : 0;
+    if (pos < keep) out[pos] = v;
+  }
+}
+#endif  // __CUDACC__
+
 }  // namespace pslam_sort

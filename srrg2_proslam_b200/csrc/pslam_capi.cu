@@ -247,6 +247,7 @@ int pslam_create(int device, const pslam_limits* lim, pslam_ctx** out) {
   PSLAM_CUDA_TRY(ctx, cudaMallocHost(&ctx->h_pinned, ctx->pinned_bytes));
   int rc = pslam_k_upload_pattern(ctx);
   if (rc) return rc;
+  if ((rc = pslam_k_make_blur_tmap(ctx, (int) NW))) return rc;
   return PSLAM_OK;
 }
 
@@ -457,7 +458,7 @@ int pslam_match_epipolar(pslam_ctx* ctx, int n_fixed, const float* xy_fixed, con
   int rc;
   if ((rc = upload_cloud(ctx, 0, n_fixed, xy_fixed, desc_fixed))) return rc;
   if ((rc = upload_cloud(ctx, 1, n_moving, xy_moving, desc_moving))) return rc;
-  if ((rc = pslam_k_epipolar(ctx, 1, cfg))) return rc;
+  if ((rc = pslam_k_epipolar(ctx, 1, cfg, 1))) return rc;
   int* h = reinterpret_cast<int*>(ctx->h_pinned);
   PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(h, ctx->d_ep_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -482,7 +483,7 @@ int pslam_stereo_frontend_batch_dev(pslam_ctx* ctx, const uint8_t* d_images, int
   PSLAM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   if (ctx->prof_enabled) pslam_prof_mark(ctx, nullptr);
   if ((rc = run_extract(ctx, d_images, image_pitch_bytes, 2 * n_pairs, rows, cols, stride, ecfg, nullptr))) return rc;
-  if (n_pairs > 0 && (rc = pslam_k_epipolar(ctx, n_pairs, mcfg))) return rc;
+  if (n_pairs > 0 && (rc = pslam_k_epipolar(ctx, n_pairs, mcfg, 0))) return rc;
   return PSLAM_OK;
 }
 
@@ -494,7 +495,7 @@ int pslam_stereo_frontend_batch(pslam_ctx* ctx, const uint8_t* h_images, int n_p
   if (rc) return rc;
   PSLAM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   if ((rc = run_extract_host(ctx, h_images, image_pitch_bytes, 2 * n_pairs, rows, cols, stride, ecfg))) return rc;
-  if (n_pairs > 0 && (rc = pslam_k_epipolar(ctx, n_pairs, mcfg))) return rc;
+  if (n_pairs > 0 && (rc = pslam_k_epipolar(ctx, n_pairs, mcfg, 0))) return rc;
   return PSLAM_OK;
 }
 
@@ -567,7 +568,7 @@ int pslam_stereo_adaptor(pslam_ctx* ctx, const uint8_t* left, const uint8_t* rig
   if ((rc = upload_images(ctx, left, 1, rows, cols, stride, 0))) return rc;
   PSLAM_CUDA_TRY(ctx, cudaMemcpy2DAsync(ctx->d_images + ctx->img_slot, ctx->img_pitch, right, stride, cols, rows, cudaMemcpyHostToDevice, ctx->stream));
   if ((rc = run_extract(ctx, ctx->d_images, (long long) ctx->img_slot, 2, rows, cols, ctx->img_pitch, ecfg, nullptr))) return rc;
-  if ((rc = pslam_k_epipolar(ctx, 1, mcfg))) return rc;
+  if ((rc = pslam_k_epipolar(ctx, 1, mcfg, 0))) return rc;
   std::vector<int> li((size_t) ctx->lim.max_features);
   const int n = pslam_download_stereo_points(ctx, 0, capacity, uvuv, li.data(), nullptr, nullptr);
   if (n < 0) return n;

@@ -1,5 +1,6 @@
 // pslam_internal.cuh -- context layout and device helpers shared by the sm_100a kernels.
 #pragma once
+#include <cuda.h>  // CUtensorMap (types only: the driver entry point is fetched through the runtime)
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -37,6 +38,7 @@ struct pslam_ctx {
   int* d_row_count;
   size_t k1_smem_set;
   uint8_t* d_blur;
+  CUtensorMap blur_tmap;  // TMA view of the blur maps: u8 [work_images][max_rows][map_pitch], box {32, 31, 1}
   uint8_t* d_mask;  // [max_rows][map_pitch], single image (host entry point only)
   uint32_t* d_raw;
   int* d_raw_count;

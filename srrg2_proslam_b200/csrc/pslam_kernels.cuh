@@ -13,12 +13,14 @@ int pslam_k_bin_select(pslam_ctx* ctx, int n_images, int rows, int cols, int nh,
 int pslam_k_assemble(pslam_ctx* ctx, const uint8_t* d_images, long long image_pitch, int stride,
                      int n_images, int rows, int cols, int nbins, int border, int slot_base);
 int pslam_k_describe(pslam_ctx* ctx, int n_images, int slot_base);
+int pslam_k_make_blur_tmap(pslam_ctx* ctx, int work_images);
 int pslam_k_mono_depth(pslam_ctx* ctx, const void* d_depth, int depth_type, int depth_rows, int depth_cols,
                        int depth_stride, float scale, int slot, float* d_uvz, float* d_inten, uint32_t* d_desc,
                        int* d_count);
 
 // k_epipolar.cu
-int pslam_k_epipolar(pslam_ctx* ctx, int n_pairs, const pslam_match_cfg* cfg);
+// general != 0: arbitrary host coordinates (bitonic sort); 0: coordinates produced by the extractor (row < max_rows)
+int pslam_k_epipolar(pslam_ctx* ctx, int n_pairs, const pslam_match_cfg* cfg, int general);
 
 // packed (CSR) stereo result of a batch, carved from the context scratch: offsets[n_pairs + 1] then SoA
 struct pslam_packed_stereo {
