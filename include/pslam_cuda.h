@@ -104,6 +104,18 @@ int pslam_extract_binned(pslam_ctx* ctx, const uint8_t* image, int rows, int col
                          const pslam_extract_cfg* cfg, const uint8_t* mask_or_null, int capacity,
                          float* xy, float* response, float* intensity, uint8_t* desc);
 
+/* Replaces IntensityFeatureExtractorSelective_::compute in tracking mode
+ *   (.../feature_extractors/intensity_feature_extractor_selective.cpp:49-205 + base.cpp:45-85):
+ * FAST over the whole image once; keypoints inside `tracking_mask` (rows x cols, non-zero = the rectangles the
+ * reference paints around the projections, :80-144) come first in row-major order, then -- if enable_seeding
+ * (PARAM enable_seeding_when_tracking, :166-174) -- the keypoints of the complement, also row-major.  No binning,
+ * no quota (the selective extractor keeps every detection).  *n_tracking receives the size of the first group.
+ * Seeding mode without projections (:179-198) is pslam_extract_binned with mask_or_null. */
+int pslam_extract_selective(pslam_ctx* ctx, const uint8_t* image, int rows, int cols, int stride,
+                            const pslam_extract_cfg* cfg, const uint8_t* tracking_mask, int enable_seeding,
+                            int capacity, float* xy, float* response, float* intensity, uint8_t* desc,
+                            int* n_tracking);
+
 /* Batched, device-resident variant: `n_images` images of identical size, image i at
  * d_images + i * image_pitch_bytes.  Results stay in the context's feature store
  * (slot i <- image i) for the matchers; read them back with pslam_download_features. */
@@ -177,6 +189,15 @@ int pslam_download_stereo_points(pslam_ctx* ctx, int pair, int capacity, float* 
 int pslam_download_stereo_batch(pslam_ctx* ctx, int n_pairs, long long capacity_points, long long* offsets,
                                 float* uvuv, float* intensity, uint8_t* desc, int* left_idx, int* right_idx,
                                 float* distance);
+
+/* ---- N1 (next after the path): rigid-stereo triangulation ----------------------------
+ * Replaces TriangulatorRigidStereo::compute / triangulateRectifiedMidpoint
+ *   (.../mapping/triangulator_rigid_stereo.cpp:7-85), the direct consumer of the stereo adaptor's (uL,vL,uR,vR)
+ * cloud.  baseline_pixels_x = (K * t_right_in_left).x (:104-105).  xyz: 3 floats per input point, index-aligned
+ * with the input; valid[i] = 0 marks the INVALID placeholders of points with xL - xR < minimum_disparity_pixels
+ * (:38-45).  Returns the number of valid points. */
+int pslam_triangulate(pslam_ctx* ctx, int n, const float* uvuv, const float* K9, float baseline_pixels_x,
+                      float minimum_disparity_pixels, float infinity_depth_meters, float* xyz, uint8_t* valid);
 
 /* ---- stage 2b: exhaustive Hamming matching --------------------------------------
  * Replaces CorrespondenceFinderDescriptorBasedBruteforce::compute

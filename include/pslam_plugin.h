@@ -60,6 +60,12 @@ psp_module* psp_module_get_link(psp_module* c, const char* param);
 int psp_extractor_compute(psp_module* extractor, const uint8_t* image, int rows, int cols, int stride,
                           const uint8_t* mask_or_null, int capacity, float* xy, float* intensity, uint8_t* desc);
 
+/* setProjections(cloud, radius) (base.h:100-106): the next compute() of a selective extractor runs in tracking mode;
+ * coords: n x dim floats (x, y first).  psp_extractor_number_of_tracking_keypoints: size of the tracking group of
+ * the last compute (IntensityFeatureExtractorSelective{2D,3D} only). */
+int psp_extractor_set_projections(psp_module* extractor, int n, int dim, const float* coords, int radius);
+int psp_extractor_number_of_tracking_keypoints(psp_module* extractor);
+
 /* ---- RawDataPreprocessorStereoProjective: setRawData + setMeas + compute ---------------------
  * uvuv: 4 floats per point.  *status receives the adaptor's _status (0 Error, 1 Initializing, 2 Ready). */
 int psp_stereo_adaptor_compute(psp_module* adaptor, const uint8_t* left, const uint8_t* right, int rows, int cols,

@@ -264,6 +264,17 @@ class Context:
         return out
 
     # ---- stage 2b -----------------------------------------------------------------------------
+    def triangulate(self, uvuv, K, b_x, min_disparity=1.0, infinity_depth=None):
+        uvuv = np.ascontiguousarray(uvuv, np.float32).reshape(-1, 4)
+        K = np.ascontiguousarray(K, np.float32).reshape(9)
+        if infinity_depth is None:
+            infinity_depth = float(np.sqrt(np.finfo(np.float32).max))
+        xyz = np.zeros((len(uvuv), 3), np.float32)
+        valid = np.zeros(len(uvuv), np.uint8)
+        n = self._chk(lib().pslam_triangulate(self._h, len(uvuv), _p(uvuv), _p(K), C.c_float(b_x), C.c_float(min_disparity),
+                                              C.c_float(infinity_depth), _p(xyz), _p(valid)))
+        return xyz, valid.astype(bool), n
+
     def bf_best2(self, desc_f, desc_m):
         desc_f = np.ascontiguousarray(desc_f, np.uint8).reshape(-1, 32)
         desc_m = np.ascontiguousarray(desc_m, np.uint8).reshape(-1, 32)

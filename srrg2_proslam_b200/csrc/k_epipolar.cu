@@ -445,6 +445,34 @@ stereo_pack_kernel(const long long* __restrict__ offsets, const int* __restrict_
   }
 }
 
+
+// ---- N1: TriangulatorRigidStereo::compute / triangulateRectifiedMidpoint ---------------------------
+//   .../mapping/triangulator_rigid_stereo.cpp:7-85.  fp32, operation order of the reference (no FMA contraction):
+//   depth = b_x / (xL - xR) (infinity depth at zero disparity), x = 1 / f_x * (xL - c_x) * depth,
+//   y = 1 / f_y * ((yL + yR) / 2 - c_y) * depth; points with xL - xR < minimum_disparity are kept as INVALID
+//   placeholders (coordinates 0) so that the output stays index-aligned with the input (:38-45).
+__global__ void triangulate_kernel(const float4* __restrict__ uvuv, long long n, float fx, float fy, float cx, float cy,
+                                   float b_x, float min_disparity, float infinity_depth, float* __restrict__ xyz,
+                                   unsigned char* __restrict__ valid) {
+  const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = uvuv[i];
+  float x = 0.f, y = 0.f, z = 0.f;
+  unsigned char ok = 0;
+  if (!(__fsub_rn(p.x, p.z) < min_disparity)) {
+    float depth = infinity_depth;
+    if (p.x > p.z) depth = __fdiv_rn(b_x, __fsub_rn(p.x, p.z));
+    z = depth;
+    x = __fmul_rn(__fmul_rn(__fdiv_rn(1.f, fx), __fsub_rn(p.x, cx)), depth);
+    y = __fmul_rn(__fmul_rn(__fdiv_rn(1.f, fy), __fsub_rn(__fdiv_rn(__fadd_rn(p.y, p.w), 2.f), cy)), depth);
+    ok = 1;
+  }
+  xyz[3 * i] = x;
+  xyz[3 * i + 1] = y;
+  xyz[3 * i + 2] = z;
+  valid[i] = ok;
+}
+
 }  // namespace
 
 int pslam_k_pack_stereo(pslam_ctx* ctx, int n_pairs, pslam_packed_stereo* out) {
@@ -497,5 +525,15 @@ int pslam_k_epipolar(pslam_ctx* ctx, int n_pairs, const pslam_match_cfg* cfg, in
     ctx->d_ep_count, ctx->d_st_uvuv, ctx->d_st_left, ctx->d_st_right, ctx->d_st_dist,
     ctx->d_st_count);
   PSLAM_LAUNCH_CHECK(ctx, "epipolar_kernel");
+  return PSLAM_OK;
+}
+
+int pslam_k_triangulate(pslam_ctx* ctx, const float4* d_uvuv, long long n, const float* K9, float b_x, float min_disparity,
+                        float infinity_depth, float* d_xyz, unsigned char* d_valid) {
+  if (n <= 0) return PSLAM_OK;
+  const int threads = 256;
+  triangulate_kernel<<<(unsigned) ((n + threads - 1) / threads), threads, 0, ctx->stream>>>(
+    d_uvuv, n, K9[0], K9[4], K9[2], K9[5], b_x, min_disparity, infinity_depth, d_xyz, d_valid);
+  PSLAM_LAUNCH_CHECK(ctx, "triangulate_kernel");
   return PSLAM_OK;
 }

@@ -464,7 +464,7 @@ struct RespGreater {
 
 __global__ void __launch_bounds__(SEL_THREADS)
 bin_select_kernel(const int* __restrict__ row_count, const uint32_t* __restrict__ row_kp, int row_cap, int max_rows,
-                  const uint8_t* __restrict__ mask, int mask_pitch, int rows, int cols, int nh, int nv,
+                  const uint8_t* __restrict__ mask, int mask_pitch, int mask_invert, int rows, int cols, int nh, int nv,
                   float pixel_rows_per_detector, float pixel_cols_per_detector, uint32_t* __restrict__ raw,
                   int max_raw_per_bin, int max_bins, int* __restrict__ raw_count, int* __restrict__ sel_count,
                   unsigned long long quota, int sort_cap, int* __restrict__ flags) {
@@ -517,7 +517,7 @@ bin_select_kernel(const int* __restrict__ row_count, const uint32_t* __restrict_
           continue;
         }
         if (c >= cend) break;
-        if (mask && mask[(size_t) r * mask_pitch + c] == 0) continue;
+        if (mask && ((mask[(size_t) r * mask_pitch + c] == 0) != (mask_invert != 0))) continue;
         ++cnt;
       }
     }
@@ -529,7 +529,7 @@ bin_select_kernel(const int* __restrict__ row_count, const uint32_t* __restrict_
         const uint32_t e = src[k];
         const int c = (int) (e >> 8);
         if (c >= cend) break;
-        if (mask && mask[(size_t) r * mask_pitch + c] == 0) continue;
+        if (mask && ((mask[(size_t) r * mask_pitch + c] == 0) != (mask_invert != 0))) continue;
         if (o < max_raw_per_bin) seg[o] = ((uint32_t) (r * cols + c) << 8) | (e & 0xffu);
         ++o;
       }
@@ -612,14 +612,14 @@ int pslam_k_blur_border(pslam_ctx* ctx, const uint8_t* d_image, int rows, int co
 }
 
 int pslam_k_bin_select(pslam_ctx* ctx, int n_images, int rows, int cols, int nh, int nv,
-                       unsigned long long quota, const uint8_t* d_mask) {
+                       unsigned long long quota, const uint8_t* d_mask, int mask_invert) {
   // float arithmetic of IntensityFeatureExtractorBinned_::init (binned.cpp:49-52)
   const float pr = static_cast<float>(rows) / static_cast<float>((size_t) nv);
   const float pc = static_cast<float>(cols) / static_cast<float>((size_t) nh);
   dim3 grid(nh * nv, n_images);
   const int sort_cap = ctx->lim.max_raw_per_bin < 2048 ? ctx->lim.max_raw_per_bin : 2048;
   bin_select_kernel<<<grid, SEL_THREADS, (size_t) sort_cap * 6, ctx->stream>>>(
-    ctx->d_row_count, ctx->d_row_kp, ctx->map_pitch, ctx->lim.max_rows, d_mask, ctx->map_pitch, rows, cols, nh, nv, pr,
+    ctx->d_row_count, ctx->d_row_kp, ctx->map_pitch, ctx->lim.max_rows, d_mask, ctx->map_pitch, mask_invert, rows, cols, nh, nv, pr,
     pc, ctx->d_raw, ctx->lim.max_raw_per_bin, ctx->lim.max_bins, ctx->d_raw_count, ctx->d_sel_count, quota, sort_cap,
     ctx->d_flags);
   PSLAM_LAUNCH_CHECK(ctx, "bin_select_kernel");

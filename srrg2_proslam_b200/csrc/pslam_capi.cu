@@ -97,7 +97,7 @@ int run_extract_chunk(pslam_ctx* ctx, const uint8_t* d_images, long long image_p
   if ((rc = pslam_k_fast_blur(ctx, d_images, image_pitch, n_images, rows, cols, stride,
                               (int) cfg->detector_threshold, cfg->enable_non_maximum_suppression))) return rc;
   const SelectPlan plan = make_plan(cfg, d_mask != nullptr);
-  if ((rc = pslam_k_bin_select(ctx, n_images, rows, cols, plan.nh, plan.nv, plan.quota, d_mask))) return rc;
+  if ((rc = pslam_k_bin_select(ctx, n_images, rows, cols, plan.nh, plan.nv, plan.quota, d_mask, 0))) return rc;
   if ((rc = pslam_k_assemble(ctx, d_images, image_pitch, stride, n_images, rows, cols, plan.nh * plan.nv, 31, slot_base))) return rc;
   if ((rc = pslam_k_describe(ctx, n_images, slot_base))) return rc;
   return PSLAM_OK;
@@ -389,6 +389,44 @@ int pslam_extract_binned(pslam_ctx* ctx, const uint8_t* image, int rows, int col
   return pslam_download_features(ctx, 0, capacity, xy, response, intensity, desc);
 }
 
+int pslam_extract_selective(pslam_ctx* ctx, const uint8_t* image, int rows, int cols, int stride,
+                            const pslam_extract_cfg* cfg, const uint8_t* tracking_mask, int enable_seeding,
+                            int capacity, float* xy, float* response, float* intensity, uint8_t* desc,
+                            int* n_tracking) {
+  int rc = validate_extract(ctx, 2, rows, cols, cfg);
+  if (rc) return rc;
+  if (!image || !tracking_mask) return PSLAM_E_INVALID;
+  PSLAM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if ((rc = upload_images(ctx, image, 1, rows, cols, stride, 0))) return rc;
+  PSLAM_CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_mask, 0, ctx->map_slot, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaMemcpy2DAsync(ctx->d_mask, ctx->map_pitch, tracking_mask, cols, cols, rows, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->rows = rows;
+  ctx->cols = cols;
+  ctx->n_images = 1;
+  // ONE FAST + blur pass; the tracking keypoints (mask != 0) go to feature slot 0, the seeding keypoints
+  // (complement of the mask, selective.cpp:78-79) to slot 1 -- each in row-major order, no binning, no quota
+  if ((rc = pslam_k_fast_blur(ctx, ctx->d_images, (long long) ctx->img_slot, 1, rows, cols, ctx->img_pitch,
+                              (int) cfg->detector_threshold, cfg->enable_non_maximum_suppression))) return rc;
+  const int passes = enable_seeding ? 2 : 1;
+  for (int pass = 0; pass < passes; ++pass) {
+    if ((rc = pslam_k_bin_select(ctx, 1, rows, cols, 1, 1, ~0ULL, ctx->d_mask, pass))) return rc;
+    if ((rc = pslam_k_assemble(ctx, ctx->d_images, (long long) ctx->img_slot, ctx->img_pitch, 1, rows, cols, 1, 31, pass))) return rc;
+    if ((rc = pslam_k_describe(ctx, 1, pass))) return rc;
+  }
+  const int n0 = pslam_download_features(ctx, 0, capacity, xy, response, intensity, desc);
+  if (n0 < 0) return n0;
+  if (n_tracking) *n_tracking = n0;
+  int n1 = 0;
+  if (enable_seeding) {
+    const int used = n0 < capacity ? n0 : capacity;
+    n1 = pslam_download_features(ctx, 1, capacity - used, xy ? xy + 2 * (size_t) used : nullptr,
+                                 response ? response + used : nullptr, intensity ? intensity + used : nullptr,
+                                 desc ? desc + 32 * (size_t) used : nullptr);
+    if (n1 < 0) return n1;
+  }
+  return n0 + n1;
+}
+
 int pslam_fast_detect(pslam_ctx* ctx, const uint8_t* image, int rows, int cols, int stride,
                       int threshold, int nms, int capacity, float* xy, float* response) {
   pslam_extract_cfg cfg{(float) threshold, nms, 0, 1, 1};
@@ -397,7 +435,7 @@ int pslam_fast_detect(pslam_ctx* ctx, const uint8_t* image, int rows, int cols, 
   PSLAM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   if ((rc = upload_images(ctx, image, 1, rows, cols, stride, 0))) return rc;
   if ((rc = pslam_k_fast_blur(ctx, ctx->d_images, (long long) ctx->img_slot, 1, rows, cols, ctx->img_pitch, threshold, nms))) return rc;
-  if ((rc = pslam_k_bin_select(ctx, 1, rows, cols, 1, 1, ~0ULL, nullptr))) return rc;
+  if ((rc = pslam_k_bin_select(ctx, 1, rows, cols, 1, 1, ~0ULL, nullptr, 0))) return rc;
   if ((rc = check_flags(ctx))) return rc;
   // one region, no quota: the region's raw list IS the row-major keypoint list (pixel << 8 | response + 1).
   // Read it back directly so that this stage-level entry point is bounded by max_raw_per_bin only.
@@ -633,6 +671,32 @@ int pslam_mono_depth_adaptor(pslam_ctx* ctx, const uint8_t* image, int rows, int
     PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   }
   return n;
+}
+
+// ---- N1: rigid-stereo triangulation ---------------------------------------------------------------
+int pslam_triangulate(pslam_ctx* ctx, int n, const float* uvuv, const float* K9, float baseline_pixels_x,
+                      float minimum_disparity_pixels, float infinity_depth_meters, float* xyz, uint8_t* valid) {
+  if (!ctx || n < 0 || !K9 || (n > 0 && (!uvuv || !xyz))) return PSLAM_E_INVALID;
+  if (n == 0) return 0;
+  PSLAM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const size_t need = (size_t) n * (16 + 12 + 1) + 1024;
+  if (need > ctx->scratch_bytes) return pslam_set_error(ctx, PSLAM_E_CAPACITY, "triangulate: too many points for the scratch buffer", cudaSuccess);
+  float4* d_in = reinterpret_cast<float4*>(ctx->d_scratch);
+  float* d_xyz = reinterpret_cast<float*>(ctx->d_scratch + (((size_t) n * 16 + 255) & ~(size_t) 255));
+  unsigned char* d_valid = reinterpret_cast<unsigned char*>(d_xyz + 3 * (size_t) n);
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_in, uvuv, (size_t) n * 16, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = pslam_k_triangulate(ctx, d_in, n, K9, baseline_pixels_x, minimum_disparity_pixels, infinity_depth_meters, d_xyz, d_valid);
+  if (rc) return rc;
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(xyz, d_xyz, (size_t) n * 12, cudaMemcpyDeviceToHost, ctx->stream));
+  std::vector<unsigned char> v((size_t) n);
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(v.data(), d_valid, (size_t) n, cudaMemcpyDeviceToHost, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  int n_valid = 0;
+  for (int i = 0; i < n; ++i) {
+    if (valid) valid[i] = v[i];
+    n_valid += v[i];
+  }
+  return n_valid;
 }
 
 // ---- stage 2b -----------------------------------------------------------------------------------

@@ -8,7 +8,7 @@ int pslam_k_blur_border(pslam_ctx* ctx, const uint8_t* d_image, int rows, int co
 int pslam_k_fast_blur(pslam_ctx* ctx, const uint8_t* d_images, long long image_pitch, int n_images,
                       int rows, int cols, int stride, int thr, int nms);
 int pslam_k_bin_select(pslam_ctx* ctx, int n_images, int rows, int cols, int nh, int nv,
-                       unsigned long long quota, const uint8_t* d_mask);
+                       unsigned long long quota, const uint8_t* d_mask, int mask_invert);
 // slot_base: feature-store slot of the chunk's first image (maps / raw lists are chunk-local)
 int pslam_k_assemble(pslam_ctx* ctx, const uint8_t* d_images, long long image_pitch, int stride,
                      int n_images, int rows, int cols, int nbins, int border, int slot_base);
@@ -32,6 +32,8 @@ struct pslam_packed_stereo {
   float* d_dist;
 };
 int pslam_k_pack_stereo(pslam_ctx* ctx, int n_pairs, pslam_packed_stereo* out);
+int pslam_k_triangulate(pslam_ctx* ctx, const float4* d_uvuv, long long n, const float* K9, float b_x, float min_disparity,
+                        float infinity_depth, float* d_xyz, unsigned char* d_valid);
 
 // k_bruteforce.cu
 int pslam_k_bf_best2(pslam_ctx* ctx, int n_fixed, const uint32_t* d_desc_fixed, int n_moving,

@@ -125,18 +125,8 @@ float Solver::damping() const {
   return gn ? gn->param_damping.value() : 0.f;
 }
 
-// ---- feature extractor ------------------------------------------------------------------------------------------
-void IntensityFeatureExtractorBinnedCUDA::init() {
-  if (!_config_changed) return;
-  // binned.cpp:13-28
-  if (param_number_of_detectors_vertical.value() <= 0)
-    throw std::runtime_error("IntensityFeatureExtractor::init|ERROR: invalid number of vertical detectors (check configuration!)");
-  if (param_number_of_detectors_horizontal.value() <= 0)
-    throw std::runtime_error("IntensityFeatureExtractor::init|ERROR: invalid number of horizontal detectors (check configuration!)");
-  if (_image_rows == 0)
-    throw std::runtime_error("IntensityFeatureExtractor::init|ERROR: invalid number of image rows (check configuration!)");
-  if (_image_cols == 0)
-    throw std::runtime_error("IntensityFeatureExtractor::init|ERROR: invalid number of image cols (check configuration!)");
+// ---- feature extractors -----------------------------------------------------------------------------------------
+void IntensityFeatureExtractorBaseCUDA::checkDetectorAndDescriptor() const {
   // base.cpp:105-176: the CUDA path implements the detector / descriptor pair every shipped configuration uses
   const std::string& det = param_detector_type.value();
   if (det != "FAST") {
@@ -150,23 +140,19 @@ void IntensityFeatureExtractorBinnedCUDA::init() {
       throw std::runtime_error("IntensityFeatureExtractor::_setDescriptor|ERROR: descriptor type not available in the CUDA path: " + desc);
     throw std::runtime_error("IntensityFeatureExtractor::_setDescriptor|ERROR: unknown descriptor type chosen: " + desc);
   }
-  std::cerr << "IntensityFeatureExtractorBinned_::init|initialized for image sources [" << _image_rows << " x " << _image_cols
-            << "] with detector grid [" << param_number_of_detectors_vertical.value() << " x "
-            << param_number_of_detectors_horizontal.value() << "]" << std::endl;
-  _config_changed = false;
 }
 
-pslam_extract_cfg IntensityFeatureExtractorBinnedCUDA::cudaConfig() const {
+pslam_extract_cfg IntensityFeatureExtractorBaseCUDA::cudaConfig() const {
   pslam_extract_cfg c{};
   c.detector_threshold = param_detector_threshold.value();
   c.enable_non_maximum_suppression = param_enable_non_maximum_suppression.value() ? 1 : 0;
   c.target_number_of_keypoints = param_target_number_of_keypoints.value();
-  c.number_of_detectors_horizontal = param_number_of_detectors_horizontal.value();
-  c.number_of_detectors_vertical = param_number_of_detectors_vertical.value();
+  c.number_of_detectors_horizontal = 1;
+  c.number_of_detectors_vertical = 1;
   return c;
 }
 
-void IntensityFeatureExtractorBinnedCUDA::prepare(int rows, int cols) {
+void IntensityFeatureExtractorBaseCUDA::prepare(int rows, int cols) {
   if ((size_t) rows != _image_rows || (size_t) cols != _image_cols) {  // base.cpp:60-66: re-init on new dimensions
     _image_rows = rows;
     _image_cols = cols;
@@ -175,21 +161,23 @@ void IntensityFeatureExtractorBinnedCUDA::prepare(int rows, int cols) {
   init();
 }
 
-void IntensityFeatureExtractorBinnedCUDA::compute(const ImageView& image) {
+void IntensityFeatureExtractorBaseCUDA::compute(const ImageView& image) {
   if (!_features) throw std::runtime_error("IntensityFeatureExtractor::compute|ERROR: features not set");
   prepare(image.rows, image.cols);
   pslam_ctx* ctx = PslamDevice::context(image.rows, image.cols);
-  const pslam_extract_cfg cfg = cudaConfig();
   std::vector<float> xy(2 * (size_t) kMaxFeatures), response(kMaxFeatures);
   PointIntensityDescriptorCloud& out = *_features;
   out.dim = _point_dim;
   out.number_of_optimizations.clear();
   out.resize(kMaxFeatures);
-  const int n = pslam_extract_binned(ctx, image.data, image.rows, image.cols, image.stride, &cfg,
-                                     _mask_set ? _mask.data : nullptr, kMaxFeatures, xy.data(), response.data(),
-                                     out.intensity.data(), out.descriptor.data());
+  const int n = extract(ctx, image, kMaxFeatures, xy.data(), response.data(), out.intensity.data(), out.descriptor.data());
+  _mask_set = false;  // the detection mask is consumed by one call (selective.cpp:203, binned.cpp:206)
   if (n < 0) out.resize(0);
   PslamDevice::check(n, "IntensityFeatureExtractor::compute");
+  if (n > kMaxFeatures) {
+    out.resize(0);
+    throw std::runtime_error("IntensityFeatureExtractor::compute|ERROR: more features than the device context holds");
+  }
   out.resize(n);
   for (int i = 0; i < n; ++i) {  // AoS fill of base.cpp:73-84: coordinates(0) = x, (1) = y, remaining dimensions 0
     float* p = out.point(i);
@@ -197,6 +185,111 @@ void IntensityFeatureExtractorBinnedCUDA::compute(const ImageView& image) {
     p[1] = xy[2 * i + 1];
     for (int d = 2; d < _point_dim; ++d) p[d] = 0.f;
   }
+}
+
+void IntensityFeatureExtractorBinnedCUDA::init() {
+  if (!_config_changed) return;
+  // binned.cpp:13-28
+  if (param_number_of_detectors_vertical.value() <= 0)
+    throw std::runtime_error("IntensityFeatureExtractor::init|ERROR: invalid number of vertical detectors (check configuration!)");
+  if (param_number_of_detectors_horizontal.value() <= 0)
+    throw std::runtime_error("IntensityFeatureExtractor::init|ERROR: invalid number of horizontal detectors (check configuration!)");
+  if (_image_rows == 0)
+    throw std::runtime_error("IntensityFeatureExtractor::init|ERROR: invalid number of image rows (check configuration!)");
+  if (_image_cols == 0)
+    throw std::runtime_error("IntensityFeatureExtractor::init|ERROR: invalid number of image cols (check configuration!)");
+  checkDetectorAndDescriptor();
+  std::cerr << "IntensityFeatureExtractorBinned_::init|initialized for image sources [" << _image_rows << " x " << _image_cols
+            << "] with detector grid [" << param_number_of_detectors_vertical.value() << " x "
+            << param_number_of_detectors_horizontal.value() << "]" << std::endl;
+  _config_changed = false;
+}
+
+pslam_extract_cfg IntensityFeatureExtractorBinnedCUDA::cudaConfig() const {
+  pslam_extract_cfg c = IntensityFeatureExtractorBaseCUDA::cudaConfig();
+  c.number_of_detectors_horizontal = param_number_of_detectors_horizontal.value();
+  c.number_of_detectors_vertical = param_number_of_detectors_vertical.value();
+  return c;
+}
+
+int IntensityFeatureExtractorBinnedCUDA::extract(pslam_ctx* ctx, const ImageView& image, int capacity, float* xy, float* response,
+                                                 float* intensity, uint8_t* desc) {
+  const pslam_extract_cfg cfg = cudaConfig();
+  return pslam_extract_binned(ctx, image.data, image.rows, image.cols, image.stride, &cfg, _mask_set ? _mask.data : nullptr,
+                              capacity, xy, response, intensity, desc);
+}
+
+void IntensityFeatureExtractorSelectiveCUDA::init() {
+  if (!_config_changed) return;
+  if (_image_rows == 0)
+    throw std::runtime_error("IntensityFeatureExtractorSelective_::init|ERROR: invalid number of image rows (check configuration!)");
+  if (_image_cols == 0)
+    throw std::runtime_error("IntensityFeatureExtractorSelective_::init|ERROR: invalid number of image cols (check configuration!)");
+  checkDetectorAndDescriptor();
+  std::cerr << "IntensityFeatureExtractor::init|initialized for image sources [" << _image_rows << " x " << _image_cols << "]" << std::endl;
+  _config_changed = false;
+}
+
+int IntensityFeatureExtractorSelectiveCUDA::extract(pslam_ctx* ctx, const ImageView& image, int capacity, float* xy,
+                                                    float* response, float* intensity, uint8_t* desc) {
+  const pslam_extract_cfg cfg = cudaConfig();
+  _n_tracking = 0;
+  if (_projections && !_projections->empty()) {
+    // tracking phase (selective.cpp:63-178): rectangles of half-size radius + 10 around the projections
+    const int rows = image.rows, cols = image.cols;
+    constexpr int16_t base_radius = 10;
+    const int16_t radius_pixels = (int16_t) (_projection_detection_radius + base_radius);
+    const int16_t radius_x2 = 2 * radius_pixels;
+    _tracking_mask.assign((size_t) rows * cols, 0);
+    const bool to_left = param_enable_full_distance_to_left.value(), to_right = param_enable_full_distance_to_right.value();
+    for (size_t k = 0; k < _projections->size(); ++k) {
+      const float* c = _projections->point(k);
+      const int16_t row = (int16_t) std::round(c[1]), col = (int16_t) std::round(c[0]);
+      const int16_t tl_row = std::max<int>(row - radius_pixels, 0);
+      const int16_t height = std::min<int16_t>(radius_x2, (int16_t) (rows - tl_row));
+      int x0, w;
+      if (to_left && to_right) {
+        x0 = 0;
+        w = cols;
+      } else if (to_left) {
+        x0 = 0;
+        w = col;
+      } else if (to_right) {
+        x0 = col;
+        w = (int16_t) (cols - col);
+      } else {
+        const int16_t tl_col = std::max<int>(col - radius_pixels, 0);
+        x0 = tl_col;
+        w = std::min<int16_t>(radius_x2, (int16_t) (cols - tl_col));
+      }
+      // cv::Mat(rect).setTo(1); a rectangle reaching outside the image asserts in the reference
+      for (int r = tl_row; r < tl_row + height && r < rows; ++r)
+        for (int x = std::max(x0, 0); x < x0 + w && x < cols; ++x) _tracking_mask[(size_t) r * cols + x] = 1;
+    }
+    int n_tracking = 0;
+    const int n = pslam_extract_selective(ctx, image.data, rows, cols, image.stride, &cfg, _tracking_mask.data(),
+                                          param_enable_seeding_when_tracking.value() ? 1 : 0, capacity, xy, response, intensity,
+                                          desc, &n_tracking);
+    if (n >= 0) {
+      _n_tracking = n_tracking;
+      if (n_tracking == 0)
+        std::cerr << "IntensityFeatureExtractorSelective_::computeKeypoints|WARNING: no keypoints detected for projected regions: "
+                  << _projections->size() << std::endl;
+    }
+    _projections = nullptr;  // :177
+    return n;
+  }
+  // seeding phase (selective.cpp:181-198): every FAST keypoint (optionally inside the external mask), no selection
+  std::vector<uint8_t> all;
+  const uint8_t* mask = _mask_set ? _mask.data : nullptr;
+  if (!mask) {
+    all.assign((size_t) image.rows * image.cols, 1);
+    mask = all.data();
+  }
+  const int n = pslam_extract_binned(ctx, image.data, image.rows, image.cols, image.stride, &cfg, mask, capacity, xy, response,
+                                     intensity, desc);
+  if (n == 0) std::cerr << "IntensityFeatureExtractorSelective_::computeKeypoints|WARNING: unable to seed keypoints" << std::endl;
+  return n;
 }
 
 // ---- descriptor based finders -----------------------------------------------------------------------------------
@@ -413,8 +506,8 @@ void RawDataPreprocessorStereoProjectiveCUDA::compute() {
   if (!param_feature_extractor.value() || !param_feature_extractor_right.value() || !param_correspondence_finder.value())
     throw std::runtime_error("RawDataPreprocessorStereoProjective::compute|ERROR: feature extractor / correspondence finder not set");
   auto epipolar = std::dynamic_pointer_cast<CorrespondenceFinderDescriptorBasedEpipolarCUDA>(param_correspondence_finder.value());
-  IntensityFeatureExtractorBinnedCUDA& ex_l = *param_feature_extractor.value();
-  IntensityFeatureExtractorBinnedCUDA& ex_r = *param_feature_extractor_right.value();
+  IntensityFeatureExtractorBaseCUDA& ex_l = *param_feature_extractor.value();
+  IntensityFeatureExtractorBaseCUDA& ex_r = *param_feature_extractor_right.value();
   const pslam_extract_cfg cl = ex_l.cudaConfig(), cr = ex_r.cudaConfig();
   const bool same_extractor = cl.detector_threshold == cr.detector_threshold &&
                               cl.enable_non_maximum_suppression == cr.enable_non_maximum_suppression &&
@@ -422,7 +515,8 @@ void RawDataPreprocessorStereoProjectiveCUDA::compute() {
                               cl.number_of_detectors_horizontal == cr.number_of_detectors_horizontal &&
                               cl.number_of_detectors_vertical == cr.number_of_detectors_vertical;
   _meas->dim = 4;
-  if (epipolar && same_extractor && _left.rows == _right.rows && _left.cols == _right.cols && _left.stride == _right.stride) {
+  const bool binned = dynamic_cast<IntensityFeatureExtractorBinnedCUDA*>(&ex_l) && dynamic_cast<IntensityFeatureExtractorBinnedCUDA*>(&ex_r);
+  if (epipolar && binned && same_extractor && _left.rows == _right.rows && _left.cols == _right.cols && _left.stride == _right.stride) {
     // the shipped wiring (kitti.conf / euroc.conf): ONE device call, features never leave HBM between the stages
     ex_l.prepare(_left.rows, _left.cols);  // the extractors' own init(): PARAM validation, same error texts
     ex_r.prepare(_right.rows, _right.cols);
@@ -438,9 +532,13 @@ void RawDataPreprocessorStereoProjectiveCUDA::compute() {
     // general wiring (e.g. a brute-force finder, different extractors): compose the module calls (:77-132)
     PointIntensityDescriptorCloud features_left(3), features_right(3);
     ex_l.setFeatures(&features_left);
+    ex_l.setProjections(_projections, _projection_radius);
     ex_l.compute(_left);
+    // right frame: fine-grained detection for triangulation, using the left points as priors (:84-88)
     ex_r.setFeatures(&features_right);
+    ex_r.setProjections(&features_left, _projection_radius);
     ex_r.compute(_right);
+    _projections = nullptr;
     CorrespondenceVector stereo_matches;
     auto& finder = *param_correspondence_finder.value();
     finder.setFixed(&features_left);
@@ -502,6 +600,8 @@ void RawDataPreprocessorMonocularDepthCUDA::compute() {
   if (_depth.type != 0 && _depth.type != 1) throw std::runtime_error("RawDataPreprocessorMonocularDepth::compute|ERROR: unknown depth image type");
   if (!param_feature_extractor.value()) throw std::runtime_error("RawDataPreprocessorMonocularDepth::compute|ERROR: feature extractor not set");
   pslam_ctx* ctx = PslamDevice::context(_intensity.rows, _intensity.cols);
+  if (!dynamic_cast<IntensityFeatureExtractorBinnedCUDA*>(param_feature_extractor.value().get()))
+    throw std::runtime_error("RawDataPreprocessorMonocularDepth::compute|ERROR: the CUDA adaptor is wired for the binned feature extractor");
   const pslam_extract_cfg cfg = param_feature_extractor->cudaConfig();
   _meas->dim = 3;
   _meas->resize(kMaxFeatures);
@@ -675,6 +775,10 @@ template <int Dim>
 struct ExtractorD : IntensityFeatureExtractorBinnedCUDA {
   ExtractorD() : IntensityFeatureExtractorBinnedCUDA(Dim) {}
 };
+template <int Dim>
+struct SelectiveD : IntensityFeatureExtractorSelectiveCUDA {
+  SelectiveD() : IntensityFeatureExtractorSelectiveCUDA(Dim) {}
+};
 template <int Shape>
 struct ProjectiveS : CorrespondenceFinderProjectiveCUDA {
   ProjectiveS() : CorrespondenceFinderProjectiveCUDA(Shape) {}
@@ -697,6 +801,8 @@ void registerTypes() {
   // sensor_processing/instances.cpp:11-17
   reg<ExtractorD<2>>("IntensityFeatureExtractorBinned2D");
   reg<ExtractorD<3>>("IntensityFeatureExtractorBinned3D");
+  reg<SelectiveD<2>>("IntensityFeatureExtractorSelective2D");
+  reg<SelectiveD<3>>("IntensityFeatureExtractorSelective3D");
   reg<RawDataPreprocessorStereoProjectiveCUDA>("RawDataPreprocessorStereoProjective");
   reg<RawDataPreprocessorMonocularDepthCUDA>("RawDataPreprocessorMonocularDepth");
   // registration/instances.cpp:51-76

@@ -121,23 +121,26 @@ public:
   float damping() const;
 };
 
-// ---- IntensityFeatureExtractorBinned_ (sensor_processing/feature_extractors/intensity_feature_extractor_binned.{h,cpp},
-//      ..._base.{h,cpp}) ---------------------------------------------------------------------------------------
-class IntensityFeatureExtractorBinnedCUDA : public Configurable {
+// ---- IntensityFeatureExtractor_ (sensor_processing/feature_extractors/intensity_feature_extractor_base.{h,cpp}) and its
+//      two implementations ..._binned.{h,cpp}, ..._selective.{h,cpp} ------------------------------------------------
+class IntensityFeatureExtractorBaseCUDA : public Configurable {
 public:
-  explicit IntensityFeatureExtractorBinnedCUDA(int point_dim = 3) : _point_dim(point_dim) {}
+  explicit IntensityFeatureExtractorBaseCUDA(int point_dim = 3) : _point_dim(point_dim) {}
   PARAM(PropertyString, descriptor_type, "OpenCV descriptor type (BRIEF-256, BRIEF-512, ORB-256, FREAK-512, ..)", "ORB-256", &_config_changed);
   PARAM(PropertyString, detector_type, "OpenCV detector type for point tracking (FAST, MSER, GFTT, BRISK-512, ORB-256, ..)", "FAST", &_config_changed);
   PARAM(PropertyFloat, detector_threshold, "scalar that maps to the first parameter of the chosen detector (if applicable)", 10, &_config_changed);
   PARAM(PropertyFloat, target_bin_width_pixels, "minimum required distance between detected features (if applicable)", 10, &_config_changed);
   PARAM(PropertyBool, enable_non_maximum_suppression, "enables non maximum suppression (filtering) of detected features (if applicable)", true, &_config_changed);
   PARAM(PropertyInt, target_number_of_keypoints, "target number of keypoints to detect (accumulative over all detectors)", 500, &_config_changed);
-  PARAM(PropertyInt, number_of_detectors_horizontal, "number of detectors on the horizontal image axis (cols)", 3, &_config_changed);
-  PARAM(PropertyInt, number_of_detectors_vertical, "number of detectors on the vertical image axis (rows)", 3, &_config_changed);
 
-  void init();   // binned.cpp:7-106: validates the configuration (same error texts)
+  virtual void init() = 0;
   void clear() { _config_changed = true; }
   void setFeatures(PointIntensityDescriptorCloud* features) { _features = features; }
+  // base.h:100-106: projections enable masked detection (selective extractor; ignored by the binned one)
+  void setProjections(const PointIntensityDescriptorCloud* projections, size_t projection_detection_radius) {
+    _projections = projections;
+    _projection_detection_radius = projection_detection_radius;
+  }
   void setKeypointDetectionMask(const ImageView& mask) {  // base.h:128-132
     _mask = mask;
     _mask_set = mask.data != nullptr;
@@ -146,16 +149,51 @@ public:
   void prepare(int rows, int cols);      // latch the image size and (re-)run init()
   size_t imageRows() const { return _image_rows; }
   size_t imageCols() const { return _image_cols; }
-  pslam_extract_cfg cudaConfig() const;
+  virtual pslam_extract_cfg cudaConfig() const;
   int pointDim() const { return _point_dim; }
 
-private:
+protected:
+  void checkDetectorAndDescriptor() const;  // base.cpp:105-176
+  // device pass: fills xy / response / intensity / descriptor, returns the feature count
+  virtual int extract(pslam_ctx* ctx, const ImageView& image, int capacity, float* xy, float* response, float* intensity,
+                      uint8_t* desc) = 0;
   int _point_dim;
   bool _config_changed = true;
   size_t _image_rows = 0, _image_cols = 0;
   PointIntensityDescriptorCloud* _features = nullptr;
+  const PointIntensityDescriptorCloud* _projections = nullptr;
+  size_t _projection_detection_radius = 0;
   ImageView _mask;
   bool _mask_set = false;
+};
+
+class IntensityFeatureExtractorBinnedCUDA : public IntensityFeatureExtractorBaseCUDA {
+public:
+  explicit IntensityFeatureExtractorBinnedCUDA(int point_dim = 3) : IntensityFeatureExtractorBaseCUDA(point_dim) {}
+  PARAM(PropertyInt, number_of_detectors_horizontal, "number of detectors on the horizontal image axis (cols)", 3, &_config_changed);
+  PARAM(PropertyInt, number_of_detectors_vertical, "number of detectors on the vertical image axis (rows)", 3, &_config_changed);
+  void init() override;  // binned.cpp:7-106: validates the configuration (same error texts)
+  pslam_extract_cfg cudaConfig() const override;
+
+protected:
+  int extract(pslam_ctx* ctx, const ImageView& image, int capacity, float* xy, float* response, float* intensity,
+              uint8_t* desc) override;
+};
+
+class IntensityFeatureExtractorSelectiveCUDA : public IntensityFeatureExtractorBaseCUDA {
+public:
+  explicit IntensityFeatureExtractorSelectiveCUDA(int point_dim = 3) : IntensityFeatureExtractorBaseCUDA(point_dim) {}
+  PARAM(PropertyBool, enable_full_distance_to_left, "enables complete detection from the projection to the left image border", false, &_config_changed);
+  PARAM(PropertyBool, enable_full_distance_to_right, "enables complete detection from the projection to the right image border", false, &_config_changed);
+  PARAM(PropertyBool, enable_seeding_when_tracking, "enables new point seeding when in tracking mode", true, &_config_changed);
+  void init() override;  // selective.cpp:6-46
+  size_t numberOfTrackingKeypoints() const { return _n_tracking; }
+
+protected:
+  int extract(pslam_ctx* ctx, const ImageView& image, int capacity, float* xy, float* response, float* intensity,
+              uint8_t* desc) override;  // selective.cpp:49-205
+  std::vector<uint8_t> _tracking_mask;
+  size_t _n_tracking = 0;
 };
 
 // ---- descriptor-based finders (registration/correspondence_finders/correspondence_finder_descriptor_based_*.h) --
@@ -250,8 +288,15 @@ public:
   enum Status { Error = 0, Initializing = 1, Ready = 2 };
   Status status() const { return _status; }
   void setMeas(PointIntensityDescriptorCloud* meas) { _meas = meas; }
+  // raw_data_preprocessor_descriptor_based.hpp:27-30: projections of the tracked points, handed to the extractor
+  void setProjections(const PointIntensityDescriptorCloud* projections, size_t projection_radius) {
+    _projections = projections;
+    _projection_radius = projection_radius;
+  }
 
 protected:
+  const PointIntensityDescriptorCloud* _projections = nullptr;
+  size_t _projection_radius = 0;
   Status _status = Error;
   PointIntensityDescriptorCloud* _meas = nullptr;
   bool _raw_data_changed_flag = false;
@@ -260,10 +305,10 @@ protected:
 class RawDataPreprocessorStereoProjectiveCUDA : public RawDataPreprocessorBase {
 public:
   RawDataPreprocessorStereoProjectiveCUDA();
-  PARAM(PropertyConfigurable_<IntensityFeatureExtractorBinnedCUDA>, feature_extractor,
-        "feature extractor used to detect keypoints and compute descriptors", std::make_shared<IntensityFeatureExtractorBinnedCUDA>(3), nullptr);
-  PARAM(PropertyConfigurable_<IntensityFeatureExtractorBinnedCUDA>, feature_extractor_right,
-        "feature extractor used to detect keypoints and compute descriptors in the right frame", std::make_shared<IntensityFeatureExtractorBinnedCUDA>(3), nullptr);
+  PARAM(PropertyConfigurable_<IntensityFeatureExtractorBaseCUDA>, feature_extractor,
+        "feature extractor used to detect keypoints and compute descriptors", std::static_pointer_cast<IntensityFeatureExtractorBaseCUDA>(std::make_shared<IntensityFeatureExtractorBinnedCUDA>(3)), nullptr);
+  PARAM(PropertyConfigurable_<IntensityFeatureExtractorBaseCUDA>, feature_extractor_right,
+        "feature extractor used to detect keypoints and compute descriptors in the right frame", std::static_pointer_cast<IntensityFeatureExtractorBaseCUDA>(std::make_shared<IntensityFeatureExtractorBinnedCUDA>(3)), nullptr);
   PARAM(PropertyConfigurable_<CorrespondenceFinderDescriptorBasedBruteforceCUDA>, correspondence_finder,
         "descriptor-based correspondence finder used to compute stereo matches",
         std::static_pointer_cast<CorrespondenceFinderDescriptorBasedBruteforceCUDA>(std::make_shared<CorrespondenceFinderDescriptorBasedEpipolarCUDA>()), nullptr);
@@ -280,8 +325,8 @@ private:
 
 class RawDataPreprocessorMonocularDepthCUDA : public RawDataPreprocessorBase {
 public:
-  PARAM(PropertyConfigurable_<IntensityFeatureExtractorBinnedCUDA>, feature_extractor,
-        "feature extractor used to detect keypoints and compute descriptors", std::make_shared<IntensityFeatureExtractorBinnedCUDA>(3), nullptr);
+  PARAM(PropertyConfigurable_<IntensityFeatureExtractorBaseCUDA>, feature_extractor,
+        "feature extractor used to detect keypoints and compute descriptors", std::static_pointer_cast<IntensityFeatureExtractorBaseCUDA>(std::make_shared<IntensityFeatureExtractorBinnedCUDA>(3)), nullptr);
   PARAM(PropertyString, topic_rgb, "rgb image topic [/camera/rgb/image]", "/camera/rgb/image", nullptr);
   PARAM(PropertyString, topic_depth, "topic depth image [/camera/depth/image]", "/camera/depth/image", nullptr);
   PARAM(PropertyFloat, depth_scaling_factor_to_meters, "scaling factor used to obtain depth in meters from pixel values", 1.0f, nullptr);

@@ -270,7 +270,7 @@ psp_module* psp_module_get_link(psp_module* c, const char* param) {
 int psp_extractor_compute(psp_module* extractor, const uint8_t* image, int rows, int cols, int stride,
                           const uint8_t* mask, int capacity, float* xy, float* intensity, uint8_t* desc) {
   return guard([&] {
-    auto* ex = as<IntensityFeatureExtractorBinnedCUDA>(extractor, "IntensityFeatureExtractorBinned");
+    auto* ex = as<IntensityFeatureExtractorBaseCUDA>(extractor, "IntensityFeatureExtractor");
     PointIntensityDescriptorCloud cloud(ex->pointDim());
     ex->setFeatures(&cloud);
     ImageView m;
@@ -287,6 +287,26 @@ int psp_extractor_compute(psp_module* extractor, const uint8_t* image, int rows,
     }
     copy_cloud(cloud, capacity, nullptr, intensity, desc);
     return n;
+  });
+}
+
+int psp_extractor_set_projections(psp_module* extractor, int n, int dim, const float* coords, int radius) {
+  return guard([&] {
+    auto* ex = as<IntensityFeatureExtractorBaseCUDA>(extractor, "IntensityFeatureExtractor");
+    Storage& st = storage_of(mod(extractor));
+    st.moving.dim = dim;
+    st.moving.number_of_optimizations.clear();
+    st.moving.resize(n);
+    if (n > 0) std::memcpy(st.moving.coordinates.data(), coords, sizeof(float) * (size_t) n * dim);
+    ex->setProjections(n > 0 ? &st.moving : nullptr, (size_t) radius);
+    return 0;
+  });
+}
+
+int psp_extractor_number_of_tracking_keypoints(psp_module* extractor) {
+  return guard([&] {
+    auto* ex = as<IntensityFeatureExtractorSelectiveCUDA>(extractor, "IntensityFeatureExtractorSelective");
+    return (int) ex->numberOfTrackingKeypoints();
   });
 }
 

@@ -102,6 +102,13 @@ class Module:
         n = _chk(lib().psp_extractor_compute(self.h, _p(img), rows, cols, cols, _p(m), cap, _p(xy), _p(inten), _p(desc)))
         return {"xy": xy[:n].copy(), "intensity": inten[:n].copy(), "desc": desc[:n].copy()}
 
+    def set_projections(self, coords, radius):
+        coords = np.ascontiguousarray(coords, np.float32)
+        _chk(lib().psp_extractor_set_projections(self.h, len(coords), coords.shape[1], _p(coords), int(radius)))
+
+    def number_of_tracking_keypoints(self):
+        return _chk(lib().psp_extractor_number_of_tracking_keypoints(self.h))
+
     # ---- RawDataPreprocessorStereoProjective ----------------------------------------------------------------
     def stereo_adaptor(self, left, right, cap=8192):
         left = np.ascontiguousarray(left, np.uint8)

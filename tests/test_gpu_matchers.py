@@ -184,3 +184,18 @@ def test_projective(ctx, feats, shape, radius, dd, ratio):
     if shape == "circle" and (radius, dd, ratio) == (10, 50, 0.9):
         assert len(gf) == 90  # tests/test_correspondence_finders.cpp:509
     assert same_corr((gf, gm, gd), o)  # including the unordered_map output order
+
+
+def test_triangulate(ctx):  # mapping/triangulator_rigid_stereo.cpp:7-85
+    m0, _ = kitti_chain()
+    b_x = float(np.float32(718.856) * np.float32(0.537166))
+    uvuv = m0["uvuv"].copy()
+    uvuv[3, 2] = uvuv[3, 0]          # zero disparity -> infinity depth when the minimum disparity allows it
+    uvuv[5, 2] = uvuv[5, 0] - 0.5    # below the default minimum disparity of 1 px -> INVALID placeholder
+    for min_disp in (0.0, 1.0):
+        g, valid, n_valid = ctx.triangulate(uvuv, K_KITTI, b_x, min_disp)
+        o, n_inv = O.triangulate(uvuv, K_KITTI, b_x, min_disp)
+        assert np.array_equal(g, o)  # bit-exact fp32, same operation order
+        assert n_valid == len(uvuv) - n_inv == int(valid.sum())
+        assert (min_disp == 0.0) == bool(valid[3]) and (min_disp == 0.0) == bool(valid[5])
+    assert ctx.triangulate(np.zeros((0, 4), np.float32), K_KITTI, b_x)[2] == 0

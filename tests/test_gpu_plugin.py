@@ -279,3 +279,56 @@ def test_aligner_not_enough_correspondences(P):
     al.aligner_set_left_camera_in_right([-BASELINE_M, 0, 0])
     g = al.aligner_compute()
     assert g["status"] == O.ALIGNER_STATUS["NotEnoughCorrespondences"]
+
+
+def paint_tracking_mask(rows, cols, projections, radius, to_left=False, to_right=False):
+    """test-side restatement of the rectangles of intensity_feature_extractor_selective.cpp:80-144"""
+    mask = np.zeros((rows, cols), np.uint8)
+    rp = radius + 10
+    for x, y in projections:
+        row, col = int(np.round(y)), int(np.round(x))
+        tl_row = max(row - rp, 0)
+        h = min(2 * rp, rows - tl_row)
+        if to_left and to_right:
+            x0, w = 0, cols
+        elif to_left:
+            x0, w = 0, col
+        elif to_right:
+            x0, w = col, cols - col
+        else:
+            x0 = max(col - rp, 0)
+            w = min(2 * rp, cols - x0)
+        mask[tl_row:tl_row + h, x0:x0 + w] = 1
+    return mask
+
+
+@pytest.mark.parametrize("to_left,to_right,seeding", [(False, False, True), (True, False, True), (False, True, False), (True, True, True)])
+def test_selective_extractor(P, to_left, to_right, seeding):
+    """IntensityFeatureExtractorSelective3D (intensity_feature_extractor_selective.cpp:49-205): tracking keypoints in the
+    painted rectangles first, seeded keypoints of the complement after, every FAST detection kept; without projections
+    plain detection.  Oracle: cv::FAST-with-mask semantics = the masked mode of the oracle extractor."""
+    m = P.Manager()
+    ex = m.create("IntensityFeatureExtractorSelective3D", "selective")
+    ex.set("detector_threshold", 25).set("enable_full_distance_to_left", int(to_left)).set("enable_full_distance_to_right", int(to_right))
+    ex.set("enable_seeding_when_tracking", int(seeding))
+    img = O.load_gray("kitti_city_image_left_1.png")
+    rows, cols = img.shape
+    cfg = O.extract_cfg(25, 1, 10 ** 6, 1, 1)
+    plain = ex.extract(img)  # seeding phase: no projections
+    o_all = O.extract_binned(img, cfg, mask=np.ones_like(img))
+    assert len(plain["xy"]) == len(o_all["xy"]) > 300
+    for k in ("xy", "intensity", "desc"):
+        assert np.array_equal(plain[k], o_all[k]), k
+    rng = np.random.default_rng(5)
+    proj = np.stack([rng.uniform(0, cols - 1, 40), rng.uniform(0, rows - 1, 40), np.zeros(40)], 1).astype(np.float32)
+    ex.set_projections(proj, 12)
+    g = ex.extract(img)
+    mask = paint_tracking_mask(rows, cols, proj[:, :2], 12, to_left, to_right)
+    o_t = O.extract_binned(img, cfg, mask=mask)
+    parts = [o_t] + ([O.extract_binned(img, cfg, mask=1 - mask)] if seeding else [])
+    assert ex.number_of_tracking_keypoints() == len(o_t["xy"]) > 0
+    for k in ("xy", "intensity", "desc"):
+        assert np.array_equal(g[k], np.concatenate([p[k] for p in parts])), k
+    # projections are consumed by one compute (:177): the next call seeds again
+    again = ex.extract(img)
+    assert np.array_equal(again["xy"], plain["xy"])

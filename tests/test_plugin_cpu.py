@@ -31,7 +31,8 @@ def test_exports_every_declared_symbol(P):
 
 
 # class names a .conf may use to select the CUDA-backed modules
-HOT_CLASSES = ["IntensityFeatureExtractorBinned2D", "IntensityFeatureExtractorBinned3D", "RawDataPreprocessorStereoProjective",
+HOT_CLASSES = ["IntensityFeatureExtractorBinned2D", "IntensityFeatureExtractorBinned3D", "IntensityFeatureExtractorSelective2D",
+               "IntensityFeatureExtractorSelective3D", "RawDataPreprocessorStereoProjective",
                "RawDataPreprocessorMonocularDepth", "CorrespondenceFinderDescriptorBasedEpipolar2D2D",
                "CorrespondenceFinderDescriptorBasedEpipolar3D3D", "AlignerSliceProcessorProjective",
                "AlignerSliceProcessorProjectiveDepth", "AlignerSliceProcessorProjectiveStereo", "MultiAligner3DQR"]
