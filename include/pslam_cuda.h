@@ -272,6 +272,16 @@ int pslam_linearize_se3(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, const do
                         int n_moving, const double* moving_xyz, int n_fixed, const double* fixed_meas,
                         int fixed_dim, int n_corr, const int* corr_fixed, const int* corr_moving,
                         const double* info_diag, double* H36, double* b6, double* stats4);
+/* n_iterations x { linearise -> H, b -> (H + damping I) dx = -b -> pose <- pose * v2t(dx) } in ONE kernel launch: what the
+ * aligner runs between two re-projections of the correspondence finder (correspondences and information matrices are
+ * constant in between).  pose12 in/out; poses12 (n_iterations x 12, pose after each update) and
+ * stats4 (n_iterations x {chi, inliers, outliers, suppressed}) may be NULL.  *iterations_done receives the number of
+ * linearised iterations (their stats are valid); PSLAM_E_NOT_SPD when the last of them could not be solved (the pose
+ * keeps its last valid value), PSLAM_OK otherwise. */
+int pslam_gn_iterate(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, int n_iterations, double damping, double* pose12,
+                     int n_moving, const double* moving_xyz, int n_fixed, const double* fixed_meas, int fixed_dim,
+                     int n_corr, const int* corr_fixed, const int* corr_moving, const double* info_diag,
+                     double* poses12, double* stats4, int* iterations_done);
 /* (H + damping I) dx = -b, pose <- pose * v2t(dx) on the device (one thread, fp64 Cholesky) */
 int pslam_gn_step(pslam_ctx* ctx, const double* H36, const double* b6, double damping, double* pose12,
                   double* dx6);

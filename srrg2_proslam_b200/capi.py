@@ -355,6 +355,24 @@ class Context:
                                             _p(cf), _p(cm), _p(info), _p(H), _p(b), _p(st)))
         return H.reshape(6, 6), b, dict(chi=st[0], inliers=int(st[1]), outliers=int(st[2]), suppressed=int(st[3]))
 
+    def gn_iterate(self, cfg, n_iterations, damping, pose12, moving_xyz, fixed_meas, corr_fixed, corr_moving, info_diag):
+        """n_iterations fused {linearise -> H,b -> solve -> update}; returns (pose, poses[n,12], stats[n,4], done, spd_ok)"""
+        pose = np.ascontiguousarray(pose12, np.float64).reshape(12).copy()
+        moving_xyz = np.ascontiguousarray(moving_xyz, np.float64).reshape(-1, 3)
+        fixed_meas = np.ascontiguousarray(fixed_meas, np.float64)
+        cf = np.ascontiguousarray(corr_fixed, np.int32)
+        cm = np.ascontiguousarray(corr_moving, np.int32)
+        info = np.ascontiguousarray(info_diag, np.float64).reshape(-1, 3)
+        poses = np.zeros((max(n_iterations, 1), 12), np.float64)
+        stats = np.zeros((max(n_iterations, 1), 4), np.float64)
+        done = C.c_int(0)
+        rc = lib().pslam_gn_iterate(self._h, C.byref(cfg), int(n_iterations), C.c_double(damping), _p(pose), len(moving_xyz),
+                                    _p(moving_xyz), len(fixed_meas), _p(fixed_meas), fixed_meas.shape[1], len(cf), _p(cf),
+                                    _p(cm), _p(info), _p(poses), _p(stats), C.byref(done))
+        if rc != PSLAM_E_NOT_SPD:
+            self._chk(rc)
+        return pose, poses[:done.value], stats[:done.value], done.value, rc != PSLAM_E_NOT_SPD
+
     def gn_step(self, H, b, damping, pose12):
         H = np.ascontiguousarray(H, np.float64).reshape(36)
         b = np.ascontiguousarray(b, np.float64).reshape(6)

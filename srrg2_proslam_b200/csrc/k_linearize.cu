@@ -102,6 +102,42 @@ __device__ __forceinline__ bool error_and_jacobian(const LinParams& c, const dou
   return true;
 }
 
+// accumulate one correspondence into the thread's partial sums (FactorCorrespondenceDriven_::compute analogue)
+__device__ __forceinline__ void accumulate_correspondence(const LinParams& c, int edim, const double* __restrict__ moving_xyz,
+                                                          const double* __restrict__ fixed_meas, int fixed_dim, int fi, int mi,
+                                                          const double* __restrict__ info_diag, double* acc) {
+  double pm[3] = {moving_xyz[3 * (size_t) mi], moving_xyz[3 * (size_t) mi + 1], moving_xyz[3 * (size_t) mi + 2]};
+  double z[3] = {0, 0, 0};
+  for (int i = 0; i < 3 && i < fixed_dim; ++i) z[i] = fixed_meas[(size_t) fixed_dim * fi + i];
+  double e[3], J[18];
+  if (!error_and_jacobian(c, pm, z, e, J)) {
+    acc[30] += 1;
+    return;
+  }
+  const double om[3] = {info_diag[3 * (size_t) fi], info_diag[3 * (size_t) fi + 1], info_diag[3 * (size_t) fi + 2]};
+  double chi = 0;
+  for (int i = 0; i < edim; ++i) chi = __dadd_rn(chi, __dmul_rn(__dmul_rn(e[i], om[i]), e[i]));
+  double scale = 1;
+  if (c.robustifier != 0 && chi > c.chi_threshold) {
+    acc[29] += 1;
+    scale = (c.robustifier == 1) ? __ddiv_rn(c.chi_threshold, chi) : 0.0;
+  } else {
+    acc[28] += 1;
+  }
+  acc[27] += __dmul_rn(chi, scale);
+  for (int i = 0; i < edim; ++i) {
+    const double w = __dmul_rn(om[i], scale);
+    int h = 0;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      const double Jw = __dmul_rn(J[6 * i + a], w);
+      acc[21 + a] += __dmul_rn(Jw, e[i]);
+#pragma unroll
+      for (int b = a; b < 6; ++b) acc[h++] += __dmul_rn(Jw, J[6 * i + b]);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(LZ_THREADS)
 linearize_kernel(LinParams c, const double* __restrict__ moving_xyz,
                  const double* __restrict__ fixed_meas, int fixed_dim, int n_corr,
@@ -112,39 +148,8 @@ linearize_kernel(LinParams c, const double* __restrict__ moving_xyz,
 #pragma unroll
   for (int i = 0; i < LZ_NACC; ++i) acc[i] = 0;
   const int edim = (c.kind == 2) ? 2 : 3;
-  for (int k = blockIdx.x * LZ_THREADS + threadIdx.x; k < n_corr; k += gridDim.x * LZ_THREADS) {
-    const int fi = corr_fixed[k], mi = corr_moving[k];
-    double pm[3] = {moving_xyz[3 * (size_t) mi], moving_xyz[3 * (size_t) mi + 1], moving_xyz[3 * (size_t) mi + 2]};
-    double z[3] = {0, 0, 0};
-    for (int i = 0; i < 3 && i < fixed_dim; ++i) z[i] = fixed_meas[(size_t) fixed_dim * fi + i];
-    double e[3], J[18];
-    if (!error_and_jacobian(c, pm, z, e, J)) {
-      acc[30] += 1;
-      continue;
-    }
-    const double om[3] = {info_diag[3 * (size_t) fi], info_diag[3 * (size_t) fi + 1], info_diag[3 * (size_t) fi + 2]};
-    double chi = 0;
-    for (int i = 0; i < edim; ++i) chi = __dadd_rn(chi, __dmul_rn(__dmul_rn(e[i], om[i]), e[i]));
-    double scale = 1;
-    if (c.robustifier != 0 && chi > c.chi_threshold) {
-      acc[29] += 1;
-      scale = (c.robustifier == 1) ? __ddiv_rn(c.chi_threshold, chi) : 0.0;
-    } else {
-      acc[28] += 1;
-    }
-    acc[27] += __dmul_rn(chi, scale);
-    for (int i = 0; i < edim; ++i) {
-      const double w = __dmul_rn(om[i], scale);
-      int h = 0;
-#pragma unroll
-      for (int a = 0; a < 6; ++a) {
-        const double Jw = __dmul_rn(J[6 * i + a], w);
-        acc[21 + a] += __dmul_rn(Jw, e[i]);
-#pragma unroll
-        for (int b = a; b < 6; ++b) acc[h++] += __dmul_rn(Jw, J[6 * i + b]);
-      }
-    }
-  }
+  for (int k = blockIdx.x * LZ_THREADS + threadIdx.x; k < n_corr; k += gridDim.x * LZ_THREADS)
+    accumulate_correspondence(c, edim, moving_xyz, fixed_meas, fixed_dim, corr_fixed[k], corr_moving[k], info_diag, acc);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
   for (int i = 0; i < LZ_NACC - 1; ++i) {
@@ -186,33 +191,30 @@ __global__ void linearize_finish_kernel(const double* __restrict__ partials, int
   }
 }
 
-// (H + damping I) dx = -b by Cholesky; pose <- pose * v2t(dx)   (IterationAlgorithmGN, one 6x6 block)
-// io: [0..35] H, [36..41] b, [42] damping, [43..54] pose12 in/out, [55..60] dx out, [61] status
-__global__ void gn_step_kernel(double* __restrict__ io) {
-  if (threadIdx.x != 0) return;
+// (H + damping I) dx = -b by Cholesky; pose <- pose * v2t(dx)   (IterationAlgorithmGN, one 6x6 block).
+// H: full symmetric 6x6.  R (row-major 3x3), t: updated in place.  Returns false when H + damping I is not SPD.
+__device__ __forceinline__ bool gn_solve_update(const double* H, const double* bvec, double damping, double* R, double* t,
+                                                double* dx) {
   double A[36], L[36];
   for (int i = 0; i < 36; ++i) {
-    A[i] = io[i];
+    A[i] = H[i];
     L[i] = 0;
   }
-  for (int i = 0; i < 6; ++i) A[7 * i] += io[42];
+  for (int i = 0; i < 6; ++i) A[7 * i] += damping;
   for (int i = 0; i < 6; ++i)
     for (int j = 0; j <= i; ++j) {
       double s = A[6 * i + j];
       for (int k = 0; k < j; ++k) s = __dsub_rn(s, __dmul_rn(L[6 * i + k], L[6 * j + k]));
       if (i == j) {
-        if (!(s > 0)) {
-          io[61] = -1;
-          return;
-        }
+        if (!(s > 0)) return false;
         L[6 * i + i] = sqrt(s);
       } else {
         L[6 * i + j] = __ddiv_rn(s, L[6 * j + j]);
       }
     }
-  double y[6], dx[6];
+  double y[6];
   for (int i = 0; i < 6; ++i) {
-    double s = -io[36 + i];
+    double s = -bvec[i];
     for (int k = 0; k < i; ++k) s = __dsub_rn(s, __dmul_rn(L[6 * i + k], y[k]));
     y[i] = __ddiv_rn(s, L[6 * i + i]);
   }
@@ -244,11 +246,6 @@ __global__ void gn_step_kernel(double* __restrict__ io) {
   D[6] = __dmul_rn(2.0, __dsub_rn(__dmul_rn(x, z), __dmul_rn(yq, w)));
   D[7] = __dmul_rn(2.0, __dadd_rn(__dmul_rn(yq, z), __dmul_rn(x, w)));
   D[8] = __dsub_rn(1.0, __dmul_rn(2.0, __dadd_rn(__dmul_rn(x, x), __dmul_rn(yq, yq))));
-  double R[9], t[3];
-  for (int i = 0; i < 3; ++i) {
-    for (int j = 0; j < 3; ++j) R[3 * i + j] = io[43 + 4 * i + j];
-    t[i] = io[43 + 4 * i + 3];
-  }
   double Rn[9], tn[3];
   for (int i = 0; i < 3; ++i) {
     for (int j = 0; j < 3; ++j)
@@ -257,12 +254,112 @@ __global__ void gn_step_kernel(double* __restrict__ io) {
     tn[i] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(R[3 * i], dx[0]), __dmul_rn(R[3 * i + 1], dx[1])),
                                 __dmul_rn(R[3 * i + 2], dx[2])), t[i]);
   }
+  for (int i = 0; i < 9; ++i) R[i] = Rn[i];
+  for (int i = 0; i < 3; ++i) t[i] = tn[i];
+  return true;
+}
+
+// io: [0..35] H, [36..41] b, [42] damping, [43..54] pose12 in/out, [55..60] dx out, [61] status
+__global__ void gn_step_kernel(double* __restrict__ io) {
+  if (threadIdx.x != 0) return;
+  double R[9], t[3], dx[6];
   for (int i = 0; i < 3; ++i) {
-    for (int j = 0; j < 3; ++j) io[43 + 4 * i + j] = Rn[3 * i + j];
-    io[43 + 4 * i + 3] = tn[i];
+    for (int j = 0; j < 3; ++j) R[3 * i + j] = io[43 + 4 * i + j];
+    t[i] = io[43 + 4 * i + 3];
+  }
+  if (!gn_solve_update(io, io + 36, io[42], R, t, dx)) {
+    io[61] = -1;
+    return;
+  }
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) io[43 + 4 * i + j] = R[3 * i + j];
+    io[43 + 4 * i + 3] = t[i];
   }
   for (int i = 0; i < 6; ++i) io[55 + i] = dx[i];
   io[61] = 0;
+}
+
+// ---- fused solver iterations: n_iters x { linearise all correspondences -> H, b -> Cholesky -> pose update } in ONE
+// launch, one CTA per problem.  This is what the aligner runs between two re-projections of the correspondence
+// finder (the correspondences, hence the information matrices, do not change in between: SURVEY App. E.6), instead
+// of 2 launches + 2 host round trips per iteration.  out (per iteration): 12 pose (after the update) + chi, inliers,
+// outliers, suppressed.  iters_done: iterations completed (stops early when H + damping I is not SPD).
+constexpr int GN_OUT = 16;
+__global__ void __launch_bounds__(LZ_THREADS)
+gn_iterate_kernel(LinParams c0, double damping, int n_iters, const double* __restrict__ moving_xyz,
+                  const double* __restrict__ fixed_meas, int fixed_dim, int n_corr, const int* __restrict__ corr_fixed,
+                  const int* __restrict__ corr_moving, const double* __restrict__ info_diag, double* __restrict__ out,
+                  int* __restrict__ iters_done) {
+  __shared__ double s_part[LZ_THREADS / 32][LZ_NACC];
+  __shared__ double s_sum[LZ_NACC];
+  __shared__ double s_R[9], s_t[3];
+  __shared__ int s_ok;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x < 9) s_R[threadIdx.x] = c0.R[threadIdx.x];
+  if (threadIdx.x < 3) s_t[threadIdx.x] = c0.t[threadIdx.x];
+  if (threadIdx.x == 0) s_ok = 1;
+  __syncthreads();
+  const int edim = (c0.kind == 2) ? 2 : 3;
+  LinParams c = c0;
+  int done = 0;
+  for (int it = 0; it < n_iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) c.R[i] = s_R[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) c.t[i] = s_t[i];
+    double acc[LZ_NACC];
+#pragma unroll
+    for (int i = 0; i < LZ_NACC; ++i) acc[i] = 0;
+    for (int k = threadIdx.x; k < n_corr; k += LZ_THREADS)
+      accumulate_correspondence(c, edim, moving_xyz, fixed_meas, fixed_dim, corr_fixed[k], corr_moving[k], info_diag, acc);
+#pragma unroll
+    for (int i = 0; i < LZ_NACC - 1; ++i) {
+      const double s = warp_sum(acc[i]);
+      if (lane == 0) s_part[wid][i] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < LZ_NACC - 1) {
+      double s = 0;
+      for (int w = 0; w < LZ_THREADS / 32; ++w) s += s_part[w][threadIdx.x];
+      s_sum[threadIdx.x] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double H[36], bvec[6], R[9], t[3], dx[6];
+      int h = 0;
+      for (int a = 0; a < 6; ++a)
+        for (int b = a; b < 6; ++b) {
+          H[6 * a + b] = s_sum[h];
+          H[6 * b + a] = s_sum[h];
+          ++h;
+        }
+      for (int a = 0; a < 6; ++a) bvec[a] = s_sum[21 + a];
+      for (int i = 0; i < 9; ++i) R[i] = s_R[i];
+      for (int i = 0; i < 3; ++i) t[i] = s_t[i];
+      const bool ok = gn_solve_update(H, bvec, damping, R, t, dx);
+      double* o = out + (size_t) it * GN_OUT;
+      if (ok) {
+        for (int i = 0; i < 9; ++i) s_R[i] = R[i];
+        for (int i = 0; i < 3; ++i) s_t[i] = t[i];
+      }
+      for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) o[4 * i + j] = s_R[3 * i + j];
+        o[4 * i + 3] = s_t[i];
+      }
+      o[12] = s_sum[27];
+      o[13] = s_sum[28];
+      o[14] = s_sum[29];
+      o[15] = s_sum[30];
+      s_ok = ok ? 1 : 0;
+    }
+    __syncthreads();
+    ++done;  // the iteration was linearised (its stats are valid) even when the solve failed
+    if (!s_ok) break;
+  }
+  if (threadIdx.x == 0) {
+    iters_done[0] = done;
+    iters_done[1] = s_ok;
+  }
 }
 
 }  // namespace
@@ -326,5 +423,56 @@ int pslam_k_gn_step(pslam_ctx* ctx, const double* H36, const double* b6, double 
   if (h[61] != 0) return pslam_set_error(ctx, PSLAM_E_NOT_SPD, "gn_step: H + damping*I is not positive definite", cudaSuccess);
   memcpy(pose12, h + 43, sizeof(double) * 12);
   if (dx6) memcpy(dx6, h + 55, sizeof(double) * 6);
+  return PSLAM_OK;
+}
+
+int pslam_k_gn_iterate(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, int n_iters, double damping, double* pose12,
+                       int n_moving, const double* h_moving_xyz, int n_fixed, const double* h_fixed_meas, int fixed_dim,
+                       int n_corr, const int* h_corr_fixed, const int* h_corr_moving, const double* h_info_diag,
+                       double* h_out16, int* h_iters_done, int* h_spd) {
+  LinParams c;
+  c.kind = cfg->kind;
+  c.robustifier = cfg->robustifier;
+  for (int i = 0; i < 9; ++i) c.K[i] = cfg->K[i];
+  c.cols = cfg->image_cols;
+  c.rows = cfg->image_rows;
+  for (int i = 0; i < 3; ++i) c.baseline[i] = cfg->baseline[i];
+  c.mean_disparity = cfg->mean_disparity;
+  c.chi_threshold = cfg->chi_threshold;
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) c.R[3 * i + j] = pose12[4 * i + j];
+    c.t[i] = pose12[4 * i + 3];
+  }
+  auto al = [](size_t x) { return (x + 255) & ~(size_t) 255; };
+  const size_t b_mov = al(24 * (size_t) n_moving), b_fix = al(8 * (size_t) fixed_dim * n_fixed), b_cf = al(4 * (size_t) n_corr),
+               b_info = al(24 * (size_t) n_fixed), b_out = al(8 * (size_t) GN_OUT * n_iters);
+  if (b_mov + b_fix + 2 * b_cf + b_info + b_out + 256 > ctx->scratch_bytes)
+    return pslam_set_error(ctx, PSLAM_E_CAPACITY, "gn_iterate: problem exceeds the scratch buffer", cudaSuccess);
+  if (PSLAM_SOLVER_SCRATCH_OFFSET + b_mov + b_fix + 2 * b_cf + b_info + b_out + 256 > ctx->scratch_bytes)
+    return pslam_set_error(ctx, PSLAM_E_CAPACITY, "gn_iterate: problem exceeds the scratch buffer", cudaSuccess);
+  uint8_t* p = ctx->d_scratch + PSLAM_SOLVER_SCRATCH_OFFSET;
+  double* d_mov = (double*) p; p += b_mov;
+  double* d_fix = (double*) p; p += b_fix;
+  int* d_cf = (int*) p; p += b_cf;
+  int* d_cm = (int*) p; p += b_cf;
+  double* d_info = (double*) p; p += b_info;
+  double* d_out = (double*) p; p += b_out;
+  int* d_done = (int*) p;
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_mov, h_moving_xyz, 24 * (size_t) n_moving, cudaMemcpyHostToDevice, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_fix, h_fixed_meas, 8 * (size_t) fixed_dim * n_fixed, cudaMemcpyHostToDevice, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_cf, h_corr_fixed, 4 * (size_t) n_corr, cudaMemcpyHostToDevice, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_cm, h_corr_moving, 4 * (size_t) n_corr, cudaMemcpyHostToDevice, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_info, h_info_diag, 24 * (size_t) n_fixed, cudaMemcpyHostToDevice, ctx->stream));
+  gn_iterate_kernel<<<1, LZ_THREADS, 0, ctx->stream>>>(c, damping, n_iters, d_mov, d_fix, fixed_dim, n_corr, d_cf, d_cm, d_info,
+                                                      d_out, d_done);
+  PSLAM_LAUNCH_CHECK(ctx, "gn_iterate_kernel");
+  int* h = reinterpret_cast<int*>(ctx->h_pinned);
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(h, d_done, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(h_out16, d_out, 8 * (size_t) GN_OUT * n_iters, cudaMemcpyDeviceToHost, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  const int done = h[0];
+  *h_iters_done = done;
+  *h_spd = h[1];
+  if (done > 0) memcpy(pose12, h_out16 + (size_t) (done - 1) * GN_OUT, sizeof(double) * 12);
   return PSLAM_OK;
 }

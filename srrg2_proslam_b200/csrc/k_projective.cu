@@ -257,7 +257,7 @@ static int proj_layout(pslam_ctx* ctx, ProjState& st, int n_fixed, int dim, int 
   st.d_moving = (float*) p; p += al256(sizeof(float) * 3 * (size_t) 65536);
   st.d_desc_moving = (uint32_t*) p; p += al256(32 * (size_t) 65536);
   st.d_cand = (int*) p; p += al256(16 * (size_t) 65536);
-  if ((size_t) (p - ctx->d_scratch) > ctx->scratch_bytes)
+  if ((size_t) (p - ctx->d_scratch) > PSLAM_SOLVER_SCRATCH_OFFSET || PSLAM_SOLVER_SCRATCH_OFFSET > ctx->scratch_bytes)
     return pslam_set_error(ctx, PSLAM_E_CAPACITY, "projective: scratch too small", cudaSuccess);
   st.n_fixed = n_fixed;
   st.fixed_dim = dim;

@@ -803,7 +803,7 @@ int pslam_linearize_se3(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, const do
   for (int k = 0; k < n_corr; ++k)
     if (corr_fixed[k] < 0 || corr_fixed[k] >= n_fixed || corr_moving[k] < 0 || corr_moving[k] >= n_moving)
       return pslam_set_error(ctx, PSLAM_E_INVALID, "linearize: correspondence index out of range", cudaSuccess);
-  uint8_t* p = ctx->d_scratch;
+  uint8_t* p = ctx->d_scratch + PSLAM_SOLVER_SCRATCH_OFFSET;
   auto carve = [&](size_t bytes) {
     uint8_t* r = p;
     p += (bytes + 255) & ~(size_t) 255;
@@ -826,6 +826,33 @@ int pslam_linearize_se3(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, const do
     PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_cm, corr_moving, sizeof(int) * (size_t) n_corr, cudaMemcpyHostToDevice, ctx->stream));
   }
   return pslam_k_linearize(ctx, cfg, pose12, n_moving, d_mv, n_fixed, d_fx, fixed_dim, n_corr, d_cf, d_cm, d_info, H36, b6, stats4);
+}
+
+int pslam_gn_iterate(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, int n_iterations, double damping, double* pose12,
+                     int n_moving, const double* moving_xyz, int n_fixed, const double* fixed_meas, int fixed_dim,
+                     int n_corr, const int* corr_fixed, const int* corr_moving, const double* info_diag,
+                     double* poses12, double* stats4, int* iterations_done) {
+  if (iterations_done) *iterations_done = 0;
+  if (!ctx || !cfg || !pose12 || n_corr < 0 || n_iterations < 0 || fixed_dim < 2 || fixed_dim > 4) return PSLAM_E_INVALID;
+  if (cfg->kind < 0 || cfg->kind > 2 || cfg->robustifier < 0 || cfg->robustifier > 2) return PSLAM_E_INVALID;
+  if (n_iterations == 0) return PSLAM_OK;
+  if (n_iterations > 4096) return pslam_set_error(ctx, PSLAM_E_INVALID, "gn_iterate: more than 4096 iterations per call", cudaSuccess);
+  PSLAM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  for (int k = 0; k < n_corr; ++k)
+    if (corr_fixed[k] < 0 || corr_fixed[k] >= n_fixed || corr_moving[k] < 0 || corr_moving[k] >= n_moving)
+      return pslam_set_error(ctx, PSLAM_E_INVALID, "gn_iterate: correspondence index out of range", cudaSuccess);
+  std::vector<double> out(16 * (size_t) n_iterations);
+  int done = 0, spd = 1;
+  int rc = pslam_k_gn_iterate(ctx, cfg, n_iterations, damping, pose12, n_moving, moving_xyz, n_fixed, fixed_meas, fixed_dim, n_corr,
+                              corr_fixed, corr_moving, info_diag, out.data(), &done, &spd);
+  if (rc) return rc;
+  for (int i = 0; i < done; ++i) {
+    if (poses12) memcpy(poses12 + 12 * (size_t) i, out.data() + 16 * (size_t) i, sizeof(double) * 12);
+    if (stats4) memcpy(stats4 + 4 * (size_t) i, out.data() + 16 * (size_t) i + 12, sizeof(double) * 4);
+  }
+  if (iterations_done) *iterations_done = done;
+  if (!spd) return pslam_set_error(ctx, PSLAM_E_NOT_SPD, "gn_iterate: H + damping*I is not positive definite", cudaSuccess);
+  return PSLAM_OK;
 }
 
 int pslam_gn_step(pslam_ctx* ctx, const double* H36, const double* b6, double damping, double* pose12,

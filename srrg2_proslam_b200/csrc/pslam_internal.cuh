@@ -9,6 +9,10 @@
 #include "../../include/pslam_cuda.h"
 
 #define PSLAM_MAX_FEATURES_HARD 8192
+// scratch partition: [0, PSLAM_SOLVER_SCRATCH_OFFSET) holds the projective finder's cached clouds / lattice (they persist
+// between set_fixed / set_moving / match calls), the stage-3/4 entry points carve their temporaries above it so that an
+// aligner loop can interleave finder and solver calls
+#define PSLAM_SOLVER_SCRATCH_OFFSET ((size_t) 8 << 20)
 
 // ---- HBM-resident state of one context ------------------------------------------------------
 // Layout (all sized once from pslam_limits; nothing is allocated on the hot path):

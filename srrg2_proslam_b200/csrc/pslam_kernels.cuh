@@ -57,5 +57,9 @@ int pslam_k_linearize(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, const doub
                       const double* d_fixed_meas, int fixed_dim, int n_corr, const int* d_corr_fixed,
                       const int* d_corr_moving, const double* d_info_diag, double* h_H36,
                       double* h_b6, double* h_stats4);
+int pslam_k_gn_iterate(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, int n_iters, double damping, double* pose12,
+                       int n_moving, const double* h_moving_xyz, int n_fixed, const double* h_fixed_meas, int fixed_dim,
+                       int n_corr, const int* h_corr_fixed, const int* h_corr_moving, const double* h_info_diag,
+                       double* h_out16, int* h_iters_done, int* h_spd);
 int pslam_k_gn_step(pslam_ctx* ctx, const double* H36, const double* b6, double damping,
                     double* pose12, double* dx6);

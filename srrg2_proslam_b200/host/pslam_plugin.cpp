@@ -474,6 +474,16 @@ void CorrespondenceFinderProjectiveCUDA::compute() {
   _postCompute();
 }
 
+int CorrespondenceFinderProjectiveCUDA::callsWithoutNewCorrespondences() const {
+  if (_fixed_changed_flag || _moving_changed_flag || _config_changed) return 0;
+  if (_has_converged) return 1 << 30;  // :137-141
+  // the next call sees _current_iteration; it re-projects iff iteration % N == 0 || iteration == 1 (:162-164)
+  const size_t N = param_number_of_solver_iterations_per_projection.value();
+  int n = 0;
+  for (size_t it = _current_iteration; !(it % N == 0 || it == 1); ++it) ++n;
+  return n;
+}
+
 // ---- stereo adaptor ---------------------------------------------------------------------------------------------
 RawDataPreprocessorStereoProjectiveCUDA::RawDataPreprocessorStereoProjectiveCUDA() {}
 
@@ -724,18 +734,20 @@ void MultiAligner3DQRCUDA::compute() {
   std::vector<double> moving_xyz(_moving->coordinates.begin(), _moving->coordinates.end());
   std::vector<double> fixed_meas(_fixed->coordinates.begin(), _fixed->coordinates.end());
   std::vector<int> cf, cm;
+  std::vector<double> poses, stats;
   AlignerIterationStats last;
   bool enough = true;
-  for (int it = 0; it < param_max_iterations.value(); ++it) {
+  const int max_iterations = param_max_iterations.value();
+  for (int it = 0; it < max_iterations;) {
     Isometry3f X;
     for (int i = 0; i < 12; ++i) X.m[i] = (float) _estimate[i];
     finder.setLocalMapInSensor(X);
     finder.compute();
     const CorrespondenceVector& corr = slice->correspondences();
-    AlignerIterationStats st;
-    st.iteration = it;
-    st.num_correspondences = (int) corr.size();
     if ((int) corr.size() < std::max(slice->param_min_num_correspondences.value(), 1)) {
+      AlignerIterationStats st;
+      st.iteration = it;
+      st.num_correspondences = (int) corr.size();
       enough = false;
       _stats.push_back(st);
       break;
@@ -747,20 +759,36 @@ void MultiAligner3DQRCUDA::compute() {
       cf[k] = corr[k].fixed_idx;
       cm[k] = corr[k].moving_idx;
     }
-    double H[36], b[6], stats4[4], dx[6];
-    PslamDevice::check(pslam_linearize_se3(ctx, &slice->factorConfig(), _estimate.data(), (int) _moving->size(), moving_xyz.data(),
-                                           (int) _fixed->size(), fixed_meas.data(), _fixed->dim, (int) corr.size(), cf.data(),
-                                           cm.data(), slice->informationDiagonals().data(), H, b, stats4),
-                       "MultiAligner::compute");
-    st.chi = stats4[0];
-    st.num_inliers = (int) stats4[1];
-    st.num_outliers = (int) stats4[2];
-    st.num_suppressed = (int) stats4[3];
-    const int rc = pslam_gn_step(ctx, H, b, damping, _estimate.data(), dx);
-    _stats.push_back(st);
-    last = st;
+    // The finder keeps these correspondences for its next `quiet` calls (it only re-projects every N-th solver
+    // iteration, correspondence_finder_projective_base_impl.cpp:162-178): run this iteration and those in ONE launch.
+    const int quiet = finder.callsWithoutNewCorrespondences();
+    const int n_fused = std::min(max_iterations - it, quiet >= max_iterations ? max_iterations : quiet + 1);
+    poses.resize(12 * (size_t) n_fused);
+    stats.resize(4 * (size_t) n_fused);
+    int done = 0;
+    const int rc = pslam_gn_iterate(ctx, &slice->factorConfig(), n_fused, damping, _estimate.data(), (int) _moving->size(),
+                                    moving_xyz.data(), (int) _fixed->size(), fixed_meas.data(), _fixed->dim, (int) corr.size(),
+                                    cf.data(), cm.data(), slice->informationDiagonals().data(), poses.data(), stats.data(), &done);
+    for (int j = 0; j < done; ++j) {
+      AlignerIterationStats st;
+      st.iteration = it + j;
+      st.num_correspondences = (int) corr.size();
+      st.chi = stats[4 * (size_t) j];
+      st.num_inliers = (int) stats[4 * (size_t) j + 1];
+      st.num_outliers = (int) stats[4 * (size_t) j + 2];
+      st.num_suppressed = (int) stats[4 * (size_t) j + 3];
+      _stats.push_back(st);
+      last = st;
+    }
     if (rc == PSLAM_E_NOT_SPD) break;  // degenerate system: keep the last estimate
     PslamDevice::check(rc, "MultiAligner::compute");
+    // the finder's own bookkeeping for the fused iterations (iteration counter, previous estimate): host only
+    for (int j = 1; j < done; ++j) {
+      for (int i = 0; i < 12; ++i) X.m[i] = (float) poses[12 * (size_t) (j - 1) + i];
+      finder.setLocalMapInSensor(X);
+      finder.compute();
+    }
+    it += done;
   }
   if (!enough) {
     _status = NotEnoughCorrespondences;

@@ -211,6 +211,9 @@ public:
   void setLocalMapInSensor(const Isometry3f& T) { _local_map_in_sensor = T; }
   const Isometry3f& localMapInSensor() const { return _local_map_in_sensor; }
   virtual void compute() = 0;
+  // number of upcoming compute() calls (estimate changes only) that are guaranteed NOT to change the correspondences;
+  // the aligner fuses that many + 1 solver iterations into one device launch
+  virtual int callsWithoutNewCorrespondences() const { return 0; }
 
 protected:
   const PointIntensityDescriptorCloud* _fixed = nullptr;
@@ -226,6 +229,7 @@ public:
   PARAM(PropertyFloat, maximum_distance_ratio_to_second_best, "Lowe's distance to drop ambiguous match candidates", 0.9f, nullptr);
   PARAM(PropertyFloat, minimum_matching_ratio, "desired minimum matching ratio with current configuration (signals transgressions)", 0.25f, nullptr);
   void compute() override;  // bruteforce_impl.cpp:6-155
+  int callsWithoutNewCorrespondences() const override { return 1 << 30; }  // change flags only (:13-15)
 
 protected:
   void _preCompute();   // :201-228
@@ -269,6 +273,7 @@ public:
   bool hasConverged() const { return _has_converged; }
   size_t currentIteration() const { return _current_iteration; }
   int numberOfSearches() const { return _number_of_searches; }
+  int callsWithoutNewCorrespondences() const override;
   int shape() const { return _shape; }
 
 private:

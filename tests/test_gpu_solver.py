@@ -89,3 +89,34 @@ def test_gn_not_spd(ctx):
     with pytest.raises(capi.PslamError) as e:
         ctx.gn_step(np.zeros((6, 6)), np.ones(6), 0.0, np.eye(3, 4).reshape(12))
     assert e.value.code == capi.PSLAM_E_NOT_SPD
+
+
+@pytest.mark.parametrize("kind,damping,n", [("stereo", 1.0, 400), ("depth", 0.1, 37), ("mono", 0.0, 3000)])
+def test_gn_iterate_fused(ctx, kind, damping, n):
+    """pslam_gn_iterate: K solver iterations in one launch == K x (linearise + GN step) of the oracle"""
+    xyz, meas, cf, cm, info, pose = synth(n, kind, 5 + n, outlier_frac=0.05)
+    ocfg = O.linearize_cfg(kind, K, 1241, 376, (-386.1448, 0, 0), 0.0, "saturated", 25.0)
+    gcfg = ctx.linearize_cfg(kind, K, 1241, 376, (-386.1448, 0, 0), 0.0, "saturated", 25.0)
+    iters = 12
+    pg, poses, stats, done, ok = ctx.gn_iterate(gcfg, iters, damping, pose, xyz, meas, cf, cm, info)
+    assert done == iters and ok
+    po = pose.copy()
+    for it in range(iters):
+        Ho, bo, so = O.linearize(ocfg, po, xyz, meas, cf, cm, info)
+        rc, po, _ = O.gn_step(Ho, bo, damping, po)
+        assert rc == 0
+        assert np.abs(poses[it] - po).max() < 1e-9
+        assert (int(stats[it, 1]), int(stats[it, 2]), int(stats[it, 3])) == (so["inliers"], so["outliers"], so["suppressed"])
+        assert abs(stats[it, 0] - so["chi"]) <= RTOL * max(abs(so["chi"]), 1e-300)
+    assert np.array_equal(pg, poses[-1])
+    # zero iterations: nothing happens
+    p0, _, _, d0, ok0 = ctx.gn_iterate(gcfg, 0, damping, pose, xyz, meas, cf, cm, info)
+    assert d0 == 0 and ok0 and np.array_equal(p0, pose)
+
+
+def test_gn_iterate_not_spd(ctx):
+    xyz, meas, cf, cm, info, pose = synth(50, "stereo", 3)
+    gcfg = ctx.linearize_cfg("stereo", K, 1241, 376, (-386.1448, 0, 0), 0.0, "saturated", 25.0)
+    # no correspondences: H = 0, not positive definite without damping; the first iteration is linearised, not solved
+    pg, poses, stats, done, ok = ctx.gn_iterate(gcfg, 5, 0.0, pose, xyz, meas, cf[:0], cm[:0], info)
+    assert done == 1 and not ok and np.array_equal(pg, pose) and stats[0, 1] == 0
