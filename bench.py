@@ -122,6 +122,65 @@ def workload_config(args, pairs):
             "l2": "inputs larger than L2 (no flush needed)", "parallelism": f"frames sharded over {args.gpus} GPU(s)"}
 
 
+def tracking_lines(ctx, capi, stream, dev):
+    """(1) per-frame latency of the conf-driven aligner (kitti.conf: projective finder + stereo factor + GN, 100
+    iterations) on the KITTI 00 -> 01 pair of tests/golden through the plugin mirror; (2) H,b linearisation throughput
+    on a batched synthetic (2^22 stereo correspondences) against the FP64 pipe."""
+    import cv2
+    import torch
+    from srrg2_proslam_b200 import plugin as P
+    out = {}
+    G = ROOT / "tests" / "golden"
+    K = np.array([718.856, 0, 607.193, 0, 718.856, 185.216, 0, 0, 1], np.float32)
+    ld = lambda n: cv2.imread(str(G / n), cv2.IMREAD_UNCHANGED)
+    small = capi.Context(device=ctx.device, max_images=2, max_rows=376, max_cols=1241,
+                         max_features=2048, max_raw_per_bin=8192)
+    try:
+        e, mcfg = capi.extract_cfg(15, 1, 500), capi.match_cfg(50, 0.8, 100, 0)
+        meas = [small.stereo_adaptor(ld(f"kitti_city_image_left_{i}.png"), ld(f"kitti_city_image_right_{i}.png"), e, mcfg) for i in (0, 1)]
+        xyz, _, _ = small.triangulate(meas[0]["uvuv"], K, float(np.float32(718.856) * np.float32(0.537166)), 0.0)
+    finally:
+        small.close()
+    P.lib().psp_set_device(ctx.device)
+    m = P.Manager(G / "configurations" / "kitti_hotpath.conf")
+    al = m.get("aligner")
+    sl = [x for x in m.modules() if x.class_name == "AlignerSliceProcessorProjectiveStereo"][0]
+    pr = sl.link("projector")
+    pr.set_camera_matrix(K)
+    pr.set("canvas_rows", 376).set("canvas_cols", 1241)
+    al.aligner_set_left_camera_in_right([-0.537166, 0, 0])
+    times = []
+    for rep in range(7):
+        al.aligner_set_fixed(meas[1]["uvuv"], meas[1]["desc"])
+        al.aligner_set_moving(xyz, meas[0]["desc"])
+        al.aligner_set_moving_in_fixed(np.eye(3, 4, dtype=np.float32))
+        t0 = time.perf_counter()
+        r = al.aligner_compute()
+        times.append(time.perf_counter() - t0)
+    out["aligner"] = {"metric": "aligner_ms_per_frame", "value": 1e3 * float(np.median(times[2:])), "unit": "ms",
+                      "iterations": int(r["iterations"]), "correspondences": int(r["num_correspondences"]),
+                      "inliers": int(r["num_inliers"]), "status": int(r["status"]),
+                      "config": "kitti.conf aligner (MultiAligner3DQR -> AlignerSliceProcessorProjectiveStereo -> "
+                                "CorrespondenceFinderProjectiveCircle4D3D), KITTI 00 -> 01 of tests/golden, identity guess"}
+    # batched H,b: one launch over 2^22 correspondences
+    n = 1 << 22
+    rng = np.random.default_rng(0)
+    xyzb = np.stack([rng.uniform(-8, 8, n), rng.uniform(-2, 2, n), rng.uniform(3, 40, n)], 1)
+    h = xyzb @ K.reshape(3, 3).astype(np.float64).T
+    measb = np.stack([h[:, 0] / h[:, 2], h[:, 1] / h[:, 2], (h[:, 0] - 386.1448) / h[:, 2], h[:, 1] / h[:, 2]], 1)
+    measb[:, :3] += rng.normal(0, 0.5, (n, 3))
+    idx = np.arange(n, dtype=np.int32)
+    info = np.tile([1.0, 2.0, 1.0], (n, 1))
+    cfg = ctx.linearize_cfg("stereo", K, 1241, 376, (-386.1448, 0, 0), 0.0, "saturated", 25.0)
+    ms = ctx.linearize_timed(cfg, np.eye(3, 4).reshape(12), xyzb, measb, idx, idx, info, reps=10)
+    flop = 250.0 * n  # SURVEY.md 8d: ~250 fp64 FLOP per correspondence
+    out["linearize"] = {"metric": "linearize_gcorr_per_s", "value": n / (ms * 1e-3) / 1e9, "unit": "GCorr/s", "ms": ms,
+                        "correspondences": n, "fp64_tflops": flop / (ms * 1e-3) / 1e12,
+                        "bytes_per_correspondence": 24 + 32 + 24 + 8,
+                        "hbm_gbs": n * 88 / (ms * 1e-3) / 1e9}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -136,6 +195,7 @@ def main():
     ap.add_argument("--ref-pairs", type=int, default=256, help="--impl reference: pairs per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hamming", action="store_true")
+    ap.add_argument("--no-tracking", action="store_true", help="skip the sequential-stage lines (aligner latency, H/b throughput)")
     args = ap.parse_args()
     if os.environ.get("PSLAM_BENCH_WATCHDOG"):  # debugging aid: dump all Python stacks if the run takes too long
         import faulthandler
@@ -343,6 +403,13 @@ def main():
                            "roofline": {"bound": "int-popc", "achieved": gpairs, "peak": popc_peak, "unit": "GPair/s",
                                         "frac": gpairs / popc_peak,
                                         "peak_source": f"{world} x 148 SM x 16 POPC/clk x {sm_mhz:.0f} MHz (sampled) / 8 POPC per pair"}}
+
+    # ---- sequential stage (latency in microseconds, FP64 throughput on a batched synthetic) ------
+    if rank == 0 and not args.no_tracking:
+        try:
+            line["tracking"] = tracking_lines(ctx, capi, stream, dev)
+        except Exception as e:  # secondary lines must never cost the headline
+            line["tracking"] = {"error": repr(e)}
 
     # ---- CPU baseline (rank 0, N = 1 only): the oracle on a bounded sample -----------------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -272,6 +272,12 @@ int pslam_linearize_se3(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, const do
                         int n_moving, const double* moving_xyz, int n_fixed, const double* fixed_meas,
                         int fixed_dim, int n_corr, const int* corr_fixed, const int* corr_moving,
                         const double* info_diag, double* H36, double* b6, double* stats4);
+/* measurement aid for bench.py: the same linearisation on a batched synthetic, inputs resident in HBM, `reps` passes
+ * timed with CUDA events; *ms_per_call receives the device time of one linearise + reduce pass */
+int pslam_linearize_se3_timed(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, const double* pose12, int n_moving,
+                              const double* moving_xyz, int n_fixed, const double* fixed_meas, int fixed_dim, int n_corr,
+                              const int* corr_fixed, const int* corr_moving, const double* info_diag, int reps,
+                              double* ms_per_call);
 /* n_iterations x { linearise -> H, b -> (H + damping I) dx = -b -> pose <- pose * v2t(dx) } in ONE kernel launch: what the
  * aligner runs between two re-projections of the correspondence finder (correspondences and information matrices are
  * constant in between).  pose12 in/out; poses12 (n_iterations x 12, pose after each update) and

@@ -828,6 +828,65 @@ int pslam_linearize_se3(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, const do
   return pslam_k_linearize(ctx, cfg, pose12, n_moving, d_mv, n_fixed, d_fx, fixed_dim, n_corr, d_cf, d_cm, d_info, H36, b6, stats4);
 }
 
+// bench.py's H,b throughput line: inputs uploaded once into temporary device buffers (a batched synthetic does not fit
+// the context scratch), `reps` linearise + reduce passes timed with CUDA events on the context's stream
+int pslam_linearize_se3_timed(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, const double* pose12, int n_moving,
+                              const double* moving_xyz, int n_fixed, const double* fixed_meas, int fixed_dim, int n_corr,
+                              const int* corr_fixed, const int* corr_moving, const double* info_diag, int reps,
+                              double* ms_per_call) {
+  if (!ctx || !cfg || !pose12 || !ms_per_call || n_corr <= 0 || reps <= 0 || fixed_dim < 2 || fixed_dim > 4) return PSLAM_E_INVALID;
+  PSLAM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  double *d_mv = nullptr, *d_fx = nullptr, *d_info = nullptr;
+  int *d_cf = nullptr, *d_cm = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  int rc = PSLAM_OK;
+  auto cleanup = [&]() {
+    cudaFree(d_mv);
+    cudaFree(d_fx);
+    cudaFree(d_info);
+    cudaFree(d_cf);
+    cudaFree(d_cm);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+  };
+#define TIMED_TRY(call)                                                        \
+  do {                                                                         \
+    cudaError_t e__ = (call);                                                  \
+    if (e__ != cudaSuccess) {                                                  \
+      cleanup();                                                               \
+      return pslam_set_error(ctx, PSLAM_E_CUDA, #call, e__);                   \
+    }                                                                          \
+  } while (0)
+  TIMED_TRY(cudaMalloc(&d_mv, sizeof(double) * 3 * (size_t) n_moving));
+  TIMED_TRY(cudaMalloc(&d_fx, sizeof(double) * fixed_dim * (size_t) n_fixed));
+  TIMED_TRY(cudaMalloc(&d_info, sizeof(double) * 3 * (size_t) n_fixed));
+  TIMED_TRY(cudaMalloc(&d_cf, sizeof(int) * (size_t) n_corr));
+  TIMED_TRY(cudaMalloc(&d_cm, sizeof(int) * (size_t) n_corr));
+  TIMED_TRY(cudaMemcpyAsync(d_mv, moving_xyz, sizeof(double) * 3 * (size_t) n_moving, cudaMemcpyHostToDevice, ctx->stream));
+  TIMED_TRY(cudaMemcpyAsync(d_fx, fixed_meas, sizeof(double) * fixed_dim * (size_t) n_fixed, cudaMemcpyHostToDevice, ctx->stream));
+  TIMED_TRY(cudaMemcpyAsync(d_info, info_diag, sizeof(double) * 3 * (size_t) n_fixed, cudaMemcpyHostToDevice, ctx->stream));
+  TIMED_TRY(cudaMemcpyAsync(d_cf, corr_fixed, sizeof(int) * (size_t) n_corr, cudaMemcpyHostToDevice, ctx->stream));
+  TIMED_TRY(cudaMemcpyAsync(d_cm, corr_moving, sizeof(int) * (size_t) n_corr, cudaMemcpyHostToDevice, ctx->stream));
+  TIMED_TRY(cudaEventCreate(&e0));
+  TIMED_TRY(cudaEventCreate(&e1));
+  double H[36], b[6], st[4];
+  for (int w = 0; w < 2 && rc == PSLAM_OK; ++w)
+    rc = pslam_k_linearize(ctx, cfg, pose12, n_moving, d_mv, n_fixed, d_fx, fixed_dim, n_corr, d_cf, d_cm, d_info, H, b, st);
+  if (rc == PSLAM_OK) {
+    TIMED_TRY(cudaEventRecord(e0, ctx->stream));
+    for (int r = 0; r < reps && rc == PSLAM_OK; ++r)
+      rc = pslam_k_linearize(ctx, cfg, pose12, n_moving, d_mv, n_fixed, d_fx, fixed_dim, n_corr, d_cf, d_cm, d_info, H, b, st);
+    TIMED_TRY(cudaEventRecord(e1, ctx->stream));
+    TIMED_TRY(cudaEventSynchronize(e1));
+    float ms = 0;
+    TIMED_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    *ms_per_call = (double) ms / reps;
+  }
+#undef TIMED_TRY
+  cleanup();
+  return rc;
+}
+
 int pslam_gn_iterate(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, int n_iterations, double damping, double* pose12,
                      int n_moving, const double* moving_xyz, int n_fixed, const double* fixed_meas, int fixed_dim,
                      int n_corr, const int* corr_fixed, const int* corr_moving, const double* info_diag,
