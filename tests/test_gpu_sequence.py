@@ -59,6 +59,11 @@ def test_kitti_00_to_04_odometry(oracle):
     base = (K_KITTI.reshape(3, 3) @ np.array([-BASELINE_M, 0, 0], np.float32)).astype(np.float32)
     ecfg = O.extract_cfg(threshold=15, target=1000)  # kitti.conf extractor (:229-255), epipolar finder (:484-501)
 
+    # ONE finder for the whole sequence, like the plugin module: the adapted search radius / descriptor distance
+    # survive from frame to frame (correspondence_finder_projective_base_impl.cpp:113-122, "once per session")
+    of = O.ProjectiveFinder(K_KITTI, 376, 1241, "circle", max_desc_dist=75, ratio=0.8, min_matching_ratio=0.1,
+                            min_desc_dist=25, desc_step=5, max_radius=50, min_radius=10, radius_step=10,
+                            min_iterations=5, max_change_norm=0.01, iters_per_projection=5)
     g_prev = o_prev = None
     g_00_in_k = np.eye(3, 4).reshape(12)  # camera 00 expressed in camera k (= moving_in_fixed chained)
     o_00_in_k = np.eye(3, 4).reshape(12)
@@ -76,9 +81,6 @@ def test_kitti_00_to_04_odometry(oracle):
             al.aligner_set_moving(xyz, g_prev["desc"])
             al.aligner_set_moving_in_fixed(np.eye(3, 4, dtype=np.float32))
             g = al.aligner_compute()
-            of = O.ProjectiveFinder(K_KITTI, 376, 1241, "circle", max_desc_dist=75, ratio=0.8, min_matching_ratio=0.1,
-                                    min_desc_dist=25, desc_step=5, max_radius=50, min_radius=10, radius_step=10,
-                                    min_iterations=5, max_change_norm=0.01, iters_per_projection=5)
             of.set_fixed(o_meas["uvuv"], o_meas["desc"])
             of.set_moving(xyz, o_prev["desc"])
             o = O.align(of, "stereo", K_KITTI, 376, 1241, o_meas["uvuv"], xyz, [1, 2, 1], baseline=base,
