@@ -5,12 +5,13 @@ sm_100a kernels).  There is no fallback: if the library is missing or no CUDA de
 calls raise.
 """
 import ctypes as C
+import os
 import pathlib
 
 import numpy as np
 
 PKG_DIR = pathlib.Path(__file__).resolve().parent
-LIB_PATH = PKG_DIR / "libpslam_cuda.so"
+LIB_PATH = pathlib.Path(os.environ.get("PSLAM_CUDA_LIB", PKG_DIR / "libpslam_cuda.so"))  # override: kernel tuning experiments only
 
 PSLAM_OK, PSLAM_E_INVALID, PSLAM_E_CUDA, PSLAM_E_CAPACITY, PSLAM_E_NOT_SPD = 0, -1, -2, -3, -4
 

@@ -8,7 +8,7 @@
 //     .../feature_extractors/intensity_feature_extractor_base.cpp:52
 //   bucket + std::sort + quota of IntensityFeatureExtractorBinned_::computeKeypoints (binned.cpp:164-200)
 //
-// K1 `fast_blur_rows_kernel` -- "marching" design.  A CTA owns a band of BH image rows over the whole image
+// K1 `fast_blur_rows_kernel` -- "marching" design.  A CTA owns a band of bh image rows over the whole image
 // width; a warp owns a 256-pixel strip, a lane 8 adjacent pixels (two 32-bit words).  The CTA walks down
 // the band one row per step and keeps a 7-row window of (a) the raw pixels and (b) the horizontally
 // filtered rows in REGISTERS, so every pixel is loaded from HBM/L2 once and the inner loops are word-wide:
@@ -34,13 +34,13 @@
 
 namespace {
 
-constexpr int BH = 32;            // rows per band
-constexpr int QCAP = 512;         // per-warp candidate ring (entries); one push phase adds <= 256
+constexpr int BH_MAX = 32;        // rows per band (upper limit; the launcher picks bh <= BH_MAX, see pslam_k_fast_blur)
+constexpr int QCAP = 1024;        // per-warp candidate ring (16-bit entries = 2 KB); one push phase adds <= 512
 constexpr unsigned FULL = 0xffffffffu;
 constexpr unsigned M16 = 0x00ff00ffu;
 constexpr unsigned K9 = 0x02000200u;  // bit 9 of both 16-bit lanes
 
-__host__ __device__ inline int score_pitch(int n_strips) { return n_strips * 256 + 8; }  // bytes, multiple of 4
+__host__ __device__ inline int score_pitch(int cols) { return (cols + 8 + 3) & ~3; }  // bytes per score-tile row: pixel column c at byte c + 4
 
 // ---- row load: 8 pixels starting at column x (any alignment), clamped into the row ------------------------
 // Split in two so that the loads of row r+1 are in flight while row r is processed: `issue` only emits the
@@ -79,34 +79,52 @@ __device__ __forceinline__ void load8_finish(const Raw3& r, const uint8_t* __res
 }
 
 // ---- FAST score of one candidate, one polarity (bright: ring brighter than the centre) ---------------------
+// 16-bit SIMD: ring differences d_k = +-(c - r_k) biased by 256 (1 .. 511), d_k in the low and d_(k+8) in the high
+// half of one register; min over 3 consecutive, then over 3 of those (9-arc), max over the 16 arcs: 8 + 8 three-input
+// min and 4 max instructions instead of 80 scalar ones.
+__device__ __forceinline__ unsigned swap16(unsigned x) { return __byte_perm(x, 0u, 0x1032); }
 __device__ __forceinline__ int fast_score_polar(const uint8_t* __restrict__ p, int stride, bool bright) {
-  const int c = __ldg(p);
-  const int sgn = bright ? -1 : 1;  // d_k = sgn * (c - r_k): positive where the ring differs in the tested direction
-  const int cs = c * sgn;
-  int d[16];
-  d[0] = cs - sgn * (int) __ldg(p + 3 * stride);
-  d[1] = cs - sgn * (int) __ldg(p + 3 * stride + 1);
-  d[2] = cs - sgn * (int) __ldg(p + 2 * stride + 2);
-  d[3] = cs - sgn * (int) __ldg(p + stride + 3);
-  d[4] = cs - sgn * (int) __ldg(p + 3);
-  d[5] = cs - sgn * (int) __ldg(p - stride + 3);
-  d[6] = cs - sgn * (int) __ldg(p - 2 * stride + 2);
-  d[7] = cs - sgn * (int) __ldg(p - 3 * stride + 1);
-  d[8] = cs - sgn * (int) __ldg(p - 3 * stride);
-  d[9] = cs - sgn * (int) __ldg(p - 3 * stride - 1);
-  d[10] = cs - sgn * (int) __ldg(p - 2 * stride - 2);
-  d[11] = cs - sgn * (int) __ldg(p - stride - 3);
-  d[12] = cs - sgn * (int) __ldg(p - 3);
-  d[13] = cs - sgn * (int) __ldg(p + stride - 3);
-  d[14] = cs - sgn * (int) __ldg(p + 2 * stride - 2);
-  d[15] = cs - sgn * (int) __ldg(p + 3 * stride - 1);
-  int lo3[16];
+  const unsigned c = __ldg(p);
+  const uint8_t *pm3 = p - 3 * stride, *pm2 = p - 2 * stride, *pm1 = p - stride, *pp1 = p + stride, *pp2 = p + 2 * stride,
+                *pp3 = p + 3 * stride;
+  unsigned r[16];
+  r[0] = __ldg(pp3);
+  r[1] = __ldg(pp3 + 1);
+  r[2] = __ldg(pp2 + 2);
+  r[3] = __ldg(pp1 + 3);
+  r[4] = __ldg(p + 3);
+  r[5] = __ldg(pm1 + 3);
+  r[6] = __ldg(pm2 + 2);
+  r[7] = __ldg(pm3 + 1);
+  r[8] = __ldg(pm3);
+  r[9] = __ldg(pm3 - 1);
+  r[10] = __ldg(pm2 - 2);
+  r[11] = __ldg(pm1 - 3);
+  r[12] = __ldg(p - 3);
+  r[13] = __ldg(pp1 - 3);
+  r[14] = __ldg(pp2 - 2);
+  r[15] = __ldg(pp3 - 1);
+  // bright: d = r - c, dark: d = c - r; + 256 per half (no borrow between the halves: every half stays in 1 .. 511)
+  const unsigned kb = (bright ? 256u - c : 256u + c) * 0x00010001u;
+  const unsigned sg = bright ? 1u : 0xffffffffu;
+  unsigned d[10];
 #pragma unroll
-  for (int k = 0; k < 16; ++k) lo3[k] = min(min(d[k], d[(k + 1) & 15]), d[(k + 2) & 15]);
-  int s = -1024;
+  for (int k = 0; k < 8; ++k) d[k] = kb + sg * (r[k] | (r[k + 8] << 16));
+  d[8] = swap16(d[0]);
+  d[9] = swap16(d[1]);
+  unsigned lo3[14];
 #pragma unroll
-  for (int k = 0; k < 16; ++k) s = max(s, min(min(lo3[k], lo3[(k + 3) & 15]), lo3[(k + 6) & 15]));
-  return s;
+  for (int k = 0; k < 8; ++k) lo3[k] = __vimin3_u16x2(d[k], d[k + 1], d[k + 2]);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) lo3[8 + k] = swap16(lo3[k]);
+  unsigned a[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] = __vimin3_u16x2(lo3[k], lo3[k + 3], lo3[k + 6]);
+  unsigned m = __vimax3_u16x2(a[0], a[1], a[2]);
+  m = __vimax3_u16x2(m, a[3], a[4]);
+  m = __vimax3_u16x2(m, a[5], a[6]);
+  m = __vmaxu2(m, a[7]);
+  return (int) max(m & 0xffffu, m >> 16) - 256;
 }
 
 struct RowRegs {
@@ -190,6 +208,7 @@ struct K1Args {
   const uint8_t* images;
   long long image_pitch;
   int rows, cols, stride, thr, nms;
+  int bh;              // rows per band (<= BH_MAX), chosen by the launcher (shared-memory budget)
   uint8_t* blur;
   int map_pitch;
   long long map_slot;
@@ -200,18 +219,18 @@ struct K1Args {
 
 // Candidate queue: push this lane's candidates (mask bits 0-7 bright, 8-15 dark pixels x0..x0+7 of tile row
 // trow) in lane order, then score full batches of 32, one candidate per lane.  Deliberately NOT inlined: it is
-// called from the 7 unrolled marching steps and inlining it 7x makes the kernel overflow the instruction cache
+// called from the marching loop and inlining it makes the kernel overflow the instruction cache
 // (ncu: stall_no_instruction was the top stall reason).  Returns the new (head, tail) packed in 64 bits.
+// Entries are 16 bits: bit 15 = bright, bits 8-13 = tile row, bits 0-7 = column inside the warp's strip.
 struct ScoreCtx {
   const uint8_t* img;
   uint8_t* s_score;
   unsigned* s_bits;
-  unsigned* s_queue;
-  int stride, by, thr, SP, BW;
+  int stride, by, thr, SP, BW, xw;
 };
 __device__ __forceinline__ void score_entry(const ScoreCtx& c, unsigned entry) {
-  const int col = entry & 0xffff, trow = (entry >> 16) & 0x7fff;
-  const bool bright = (entry >> 31) != 0;
+  const int col = c.xw + (entry & 0xffu), trow = (entry >> 8) & 0x3fu;
+  const bool bright = (entry >> 15) != 0;
   const int y = c.by - 1 + trow;
   const int s = fast_score_polar(c.img + (size_t) y * c.stride + col, c.stride, bright);
   if (s > c.thr) {
@@ -221,34 +240,56 @@ __device__ __forceinline__ void score_entry(const ScoreCtx& c, unsigned entry) {
   }
 }
 __device__ __noinline__ unsigned long long push_and_drain(const uint8_t* img, uint8_t* s_score, unsigned* s_bits,
-                                                          unsigned* s_queue, int stride, int by, int thr, int SP,
+                                                          unsigned short* s_queue, int stride, int by, int thr, int SP,
                                                           int BW, unsigned mask, unsigned ebase, unsigned q_head,
                                                           unsigned q_tail, bool flush) {
+  // `mask`: candidates of TWO consecutive tile rows (bits 0-15 row trow, bits 16-31 row trow + 1; per row bits 0-7
+  // bright, 8-15 dark pixels x0 .. x0+7); ebase = trow << 8.  Pushing two rows per call halves the scans.
   const int lane = threadIdx.x & 31;
-  ScoreCtx c{img, s_score, s_bits, s_queue, stride, by, thr, SP, BW};
-  const int cnt = __popc(mask);
-  int incl = cnt;
+  ScoreCtx c{img, s_score, s_bits, stride, by, thr, SP, BW, (int) (threadIdx.x >> 5) * 256};
+  unsigned rest = 0u;
+  bool more;
+  do {
+    int cnt = __popc(mask);
+    int incl = cnt;
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int t = __shfl_up_sync(FULL, incl, o);
-    if (lane >= o) incl += t;
-  }
-  const int total = __shfl_sync(FULL, incl, 31);
-  if (total) {
-    unsigned pos = q_tail + incl - cnt;
-    while (mask) {
-      const unsigned i = __ffs(mask) - 1;
-      mask &= mask - 1;
-      s_queue[pos & (QCAP - 1)] = ebase + (i & 7u) + ((i & 8u) ? 0u : 0x80000000u);
-      ++pos;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(FULL, incl, o);
+      if (lane >= o) incl += t;
     }
-    q_tail += total;
-    __syncwarp();
-  }
-  while (q_tail - q_head >= 32) {
-    score_entry(c, s_queue[(q_head + lane) & (QCAP - 1)]);
-    q_head += 32;
-  }
+    int total = __shfl_sync(FULL, incl, 31);
+    if (total > QCAP - 32) {  // cannot happen on natural images (a pixel passing both polarity pre-tests): one row at a time
+      rest = mask & 0xffff0000u;
+      mask &= 0xffffu;
+      cnt = __popc(mask);
+      incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += t;
+      }
+      total = __shfl_sync(FULL, incl, 31);
+    }
+    if (total) {
+      unsigned pos = q_tail + incl - cnt;
+      const unsigned eb = ebase + lane * 8u;
+      while (mask) {
+        const unsigned i = __ffs(mask) - 1;
+        mask &= mask - 1;
+        s_queue[pos & (QCAP - 1)] = (unsigned short) (eb + (i & 7u) + ((i & 8u) ? 0u : 0x8000u) + ((i & 16u) << 4));
+        ++pos;
+      }
+      q_tail += total;
+      __syncwarp();
+    }
+    while (q_tail - q_head >= 32) {
+      score_entry(c, s_queue[(q_head + lane) & (QCAP - 1)]);
+      q_head += 32;
+    }
+    more = __any_sync(FULL, rest != 0u);
+    mask = rest;
+    rest = 0u;
+  } while (more);
   if (flush && q_tail != q_head) {  // end of the band: what is left (< 32 entries)
     if ((unsigned) lane < q_tail - q_head) score_entry(c, s_queue[(q_head + lane) & (QCAP - 1)]);
     q_head = q_tail;
@@ -257,26 +298,29 @@ __device__ __noinline__ unsigned long long push_and_drain(const uint8_t* img, ui
   return ((unsigned long long) q_tail << 32) | q_head;
 }
 
-__host__ __device__ inline int bits_pitch(int n_strips) { return (score_pitch(n_strips) + 31) / 32; }  // words / tile row
+__host__ __device__ inline int bits_pitch(int cols) { return (score_pitch(cols) + 31) / 32; }  // words / tile row
 
+// 3 CTAs of 5 warps per SM at KITTI width (registers).  The launcher sizes the band so that FOUR CTAs' shared memory
+// would fit: the smaller carve-out leaves ~90 KB instead of ~30 KB of L1 for the image rows the scorer re-reads
+// (measured: -3 % kernel time; a 96-register / 4-CTA build thrashes that L1 and spills, no gain).
 __global__ void __launch_bounds__(512)
 fast_blur_rows_kernel(const K1Args a) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_strips = blockDim.x >> 5;
-  const int SP = score_pitch(n_strips), BW = bits_pitch(n_strips);
-  // shared memory: score tile | corner bitmap | per-warp candidate rings | per-warp corner lists (NMS phase)
+  const int rows = a.rows, cols = a.cols, stride = a.stride, thr = a.thr, BH = a.bh;
+  const int SP = score_pitch(cols), BW = bits_pitch(cols);
+  // shared memory: score tile | corner bitmap | per-warp 2 KB: candidate ring (march) / corner list (NMS phase)
   uint8_t* s_score = smem;                                                     // [BH + 2][SP], pixel column c at byte c + 4
   unsigned* s_bits = reinterpret_cast<unsigned*>(smem + (size_t) (BH + 2) * SP);  // [BH + 2][BW], bit = byte index in the row
-  unsigned* s_queue = s_bits + (BH + 2) * BW + warp * QCAP;
-  unsigned short* s_list = reinterpret_cast<unsigned short*>(s_bits + (BH + 2) * BW + n_strips * QCAP) + (size_t) warp * (BW * 32);
+  unsigned short* s_queue = reinterpret_cast<unsigned short*>(s_bits + (BH + 2) * BW) + warp * QCAP;
+  unsigned short* s_list = s_queue;  // the ring is dead once the band has been scored
   const int by = blockIdx.x * BH, image = blockIdx.y;
   const uint8_t* img = a.images + (size_t) image * a.image_pitch;
   uint8_t* blur = a.blur + (size_t) image * a.map_slot;
-  const int rows = a.rows, cols = a.cols, stride = a.stride, thr = a.thr;
   const int x0 = warp * 256 + lane * 8;
   const int xe = lane == 0 ? x0 - 8 : x0 + 8;  // strip-edge lanes fetch the neighbour strip's pixels themselves
   const bool edge = lane == 0 || lane == 31;
-  const bool tail = warp * 256 + 256 + 16 > cols;  // some lane of this warp loads beyond cols - 8
+  const bool tail = warp * 256 + 256 + 16 > cols;  // some lane of this warp loads beyond cols - 8 (warp-uniform)
 
   for (int i = tid; i < ((BH + 2) * SP + (BH + 2) * BW * 4) / 4; i += blockDim.x) reinterpret_cast<unsigned*>(smem)[i] = 0u;
   __syncthreads();
@@ -289,7 +333,8 @@ fast_blur_rows_kernel(const K1Args a) {
   colmask |= colmask << 8;  // bright bits 0-7, dark bits 8-15
   const unsigned t1 = (unsigned) (thr + 1) * 0x00010001u;
   const bool store_ok = x0 < a.map_pitch;
-  unsigned q_head = 0, q_tail = 0;
+  unsigned q_head = 0, q_tail = 0, pend = 0u, pend_base = 0u;
+  bool have_pend = false;
 
   RowRegs R[7];
   unsigned H[7][4];
@@ -310,10 +355,10 @@ fast_blur_rows_kernel(const K1Args a) {
   // one marching step per iteration: image row r enters the window at slot 6 (slot k holds row r - 6 + k).
   // The window is rotated with register moves instead of unrolling the loop 7x: the unrolled kernel (57 KB of
   // SASS) stalled on instruction fetch (ncu stall_no_instruction), 48 extra MOVs per row are cheaper.
+  const int n_steps = BH + 8;
 #pragma unroll 1
-  for (int step = 0; step < BH + 8; ++step) {
+  for (int step = 0; step < n_steps; ++step) {
     const int r = by - 4 + step;
-    const uint8_t* rowp = row_ptr(r);
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
       R[k] = R[k + 1];
@@ -323,6 +368,7 @@ fast_blur_rows_kernel(const K1Args a) {
       H[k][3] = H[k + 1][3];
     }
     RowRegs& cur = R[6];
+    const uint8_t* rowp = row_ptr(r);
     load8_finish(nx, rowp, x0, cols, tail, cur.a0, cur.a1);
     cur.hl = __shfl_up_sync(FULL, cur.a1, 1);
     cur.hr = __shfl_down_sync(FULL, cur.a0, 1);
@@ -331,7 +377,7 @@ fast_blur_rows_kernel(const K1Args a) {
       load8_finish(ne, rowp, xe, cols, tail, e0, e1);
       if (lane == 0) cur.hl = e1; else cur.hr = e0;
     }
-    if (step + 1 < BH + 8) {
+    if (step + 1 < n_steps) {
       const uint8_t* nrow = row_ptr(r + 1);
       nx = load8_issue(nrow, x0, cols);
       if (edge) ne = load8_issue(nrow, xe, cols);
@@ -350,24 +396,34 @@ fast_blur_rows_kernel(const K1Args a) {
     if (rc >= by - 1 && rc <= by + BH && rc >= 3 && rc < rows - 3) {
       unsigned mb, md;
       pretest8(R[0], R[3], cur, t1, mb, md);
-      const unsigned long long q = push_and_drain(img, s_score, s_bits, s_queue, stride, by, thr, SP, BW,
-                                                  (mb | (md << 8)) & colmask,
-                                                  ((unsigned) (rc - (by - 1)) << 16) | (unsigned) x0, q_head, q_tail, false);
-      q_head = (unsigned) q;
-      q_tail = (unsigned) (q >> 32);
+      const unsigned m16 = (mb | (md << 8)) & colmask;
+      if (!have_pend) {  // rows are pushed in pairs (the executed centre rows of a band are consecutive)
+        pend = m16;
+        pend_base = (unsigned) (rc - (by - 1)) << 8;
+        have_pend = true;
+      } else {
+        const unsigned long long q = push_and_drain(img, s_score, s_bits, s_queue, stride, by, thr, SP, BW,
+                                                    pend | (m16 << 16), pend_base, q_head, q_tail, false);
+        q_head = (unsigned) q;
+        q_tail = (unsigned) (q >> 32);
+        have_pend = false;
+        pend = 0u;
+      }
     }
   }
-  // drain what is left in the queue (< 32 entries)
-  push_and_drain(img, s_score, s_bits, s_queue, stride, by, thr, SP, BW, 0u, 0u, q_head, q_tail, true);
+  // the unpaired last row (if any) and what is left in the queue (< 32 entries)
+  push_and_drain(img, s_score, s_bits, s_queue, stride, by, thr, SP, BW, pend, pend_base, q_head, q_tail, true);
   __syncthreads();
 
   // ---- 3x3 NMS + ordered emission into the per-row keypoint lists ----
-  // per tile row: (A) ordered compaction of the corner bitmap into a list of byte indices, (B) one corner per
-  // lane: compare with the 8 neighbours in the score tile, ballot, append survivors in column order.
+  // per tile row, in groups of 32 bitmap words: (A) ordered compaction of the corner bits into a list of byte
+  // indices, (B) one corner per lane: compare with the 8 neighbours in the score tile, ballot, append survivors
+  // in column order.
   for (int t = 1 + warp; t <= BH; t += n_strips) {
     const int y = by - 1 + t;
     if (y >= rows) break;
-    int n_list = 0;
+    uint32_t* out = a.row_kp + ((size_t) image * a.max_rows + y) * a.row_cap;
+    int count = 0;
     for (int g = 0; g < BW; g += 32) {
       const int j = g + lane;
       unsigned w = j < BW ? s_bits[t * BW + j] : 0u;
@@ -378,44 +434,43 @@ fast_blur_rows_kernel(const K1Args a) {
         const int tt = __shfl_up_sync(FULL, incl, o);
         if (lane >= o) incl += tt;
       }
-      int pos = n_list + incl - cnt;
+      const int n_list = __shfl_sync(FULL, incl, 31);
+      if (n_list == 0) continue;
+      int pos = incl - cnt;
       while (w) {
         const int b = __ffs(w) - 1;
         w &= w - 1;
         s_list[pos++] = (unsigned short) (32 * j + b);
       }
-      n_list += __shfl_sync(FULL, incl, 31);
-    }
-    __syncwarp();
-    uint32_t* out = a.row_kp + ((size_t) image * a.max_rows + y) * a.row_cap;
-    int count = 0;
-    for (int k0 = 0; k0 < n_list; k0 += 32) {
-      const int k = k0 + lane;
-      bool keep = false;
-      unsigned entry = 0;
-      if (k < n_list) {
-        const int ci = s_list[k];
-        const uint8_t* sc = s_score + (size_t) t * SP + ci;
-        const int sv = sc[0];
-        keep = true;
-        int val = 1;  // without NMS the response is 0
-        if (a.nms) {
-          int m = max(max(sc[-SP - 1], sc[-SP]), max(sc[-SP + 1], sc[-1]));
-          m = max(m, max(max(sc[1], sc[SP - 1]), max(sc[SP], sc[SP + 1])));
-          keep = m > 0 ? sv > m : sv >= 2;  // response s-1 strictly greater than every neighbour's (0 for non-corners)
-          val = sv;
+      __syncwarp();
+      for (int k0 = 0; k0 < n_list; k0 += 32) {
+        const int k = k0 + lane;
+        bool keep = false;
+        unsigned entry = 0;
+        if (k < n_list) {
+          const int ci = s_list[k];
+          const uint8_t* sc = s_score + (size_t) t * SP + ci;
+          const int sv = sc[0];
+          keep = true;
+          int val = 1;  // without NMS the response is 0
+          if (a.nms) {
+            int m = max(max(sc[-SP - 1], sc[-SP]), max(sc[-SP + 1], sc[-1]));
+            m = max(m, max(max(sc[1], sc[SP - 1]), max(sc[SP], sc[SP + 1])));
+            keep = m > 0 ? sv > m : sv >= 2;  // response s-1 strictly greater than every neighbour's (0 for non-corners)
+            val = sv;
+          }
+          entry = ((unsigned) (ci - 4) << 8) | (unsigned) val;
         }
-        entry = ((unsigned) (ci - 4) << 8) | (unsigned) val;
+        const unsigned bal = __ballot_sync(FULL, keep);
+        if (keep) {
+          const int pos2 = count + __popc(bal & ((1u << lane) - 1u));
+          if (pos2 < a.row_cap) out[pos2] = entry;
+        }
+        count += __popc(bal);
       }
-      const unsigned bal = __ballot_sync(FULL, keep);
-      if (keep) {
-        const int pos = count + __popc(bal & ((1u << lane) - 1u));
-        if (pos < a.row_cap) out[pos] = entry;
-      }
-      count += __popc(bal);
+      __syncwarp();
     }
     if (lane == 0) a.row_count[(size_t) image * a.max_rows + y] = count < a.row_cap ? count : a.row_cap;
-    __syncwarp();
   }
 }
 
@@ -592,13 +647,24 @@ int pslam_k_fast_blur(pslam_ctx* ctx, const uint8_t* d_images, long long image_p
   a.row_kp = ctx->d_row_kp;
   a.row_cap = ctx->map_pitch;
   a.max_rows = ctx->lim.max_rows;
-  const size_t smem = (size_t) (BH + 2) * score_pitch(n_strips) + (size_t) (BH + 2) * bits_pitch(n_strips) * 4 +
-                      (size_t) n_strips * QCAP * 4 + (size_t) n_strips * bits_pitch(n_strips) * 32 * 2;
+  // band height: the largest bh <= BH_MAX for which the score tile + corner bitmap + 2 KB per warp stay below a quarter
+  // of the SM's shared memory (leaves L1 for the scorer, see the kernel), then evened out over the bands; very wide
+  // images fall back to BH_MAX and one CTA's limit
+  const size_t per_row = (size_t) score_pitch(cols) + (size_t) bits_pitch(cols) * 4, fixed = (size_t) n_strips * QCAP * 2;
+  const size_t budget = (227 * 1024 - 4 * 1024) / 4;
+  int bh_max = BH_MAX;
+  if (budget > fixed + 10 * per_row) {
+    const int fit = (int) ((budget - fixed) / per_row) - 2;
+    if (fit < bh_max) bh_max = fit;
+  }
+  const int n_bands = (rows + bh_max - 1) / bh_max;
+  a.bh = (rows + n_bands - 1) / n_bands;
+  const size_t smem = (size_t) (a.bh + 2) * per_row + fixed;
   if (smem > ctx->k1_smem_set) {
     PSLAM_CUDA_TRY(ctx, cudaFuncSetAttribute(fast_blur_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     ctx->k1_smem_set = smem;
   }
-  dim3 grid((rows + BH - 1) / BH, n_images);
+  dim3 grid(n_bands, n_images);
   fast_blur_rows_kernel<<<grid, 32 * n_strips, smem, ctx->stream>>>(a);
   PSLAM_LAUNCH_CHECK(ctx, "fast_blur_rows_kernel");
   return PSLAM_OK;
