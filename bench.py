@@ -181,6 +181,32 @@ def tracking_lines(ctx, capi, stream, dev):
     return out
 
 
+def scene_clip_line(ctx, capi, dev, hbm_peak):
+    """N2: SceneClipperProjective3D over a device-resident synthetic local map (16 M points with
+    descriptors, about a third visible): one launch projects, clips and compacts in map order.  HBM bound."""
+    import torch
+    n = 1 << 24
+    g = torch.Generator(device=dev).manual_seed(7)
+    xyz = (torch.rand((n, 3), generator=g, device=dev) * 60 - 30).contiguous()
+    desc = torch.randint(0, 2 ** 31 - 1, (n, 8), generator=g, device=dev, dtype=torch.int32)
+    oxyz, ouvz = torch.empty((n, 3), device=dev), torch.empty((n, 3), device=dev)
+    oidx = torch.empty(n, dtype=torch.int32, device=dev)
+    odesc = torch.empty((n, 8), dtype=torch.int32, device=dev)
+    K = np.array([718.856, 0, 607.193, 0, 718.856, 185.216, 0, 0, 1], np.float32)
+    T = np.array([1, 0, 0, 0.3, 0, 1, 0, -0.1, 0, 0, 1, 1.5], np.float32)
+    cfg = capi.clip_cfg(K, ROWS, COLS, T, 0.1, 1000.0)
+    torch.cuda.synchronize()
+    args = (n, xyz.data_ptr(), desc.data_ptr(), cfg, oxyz.data_ptr(), ouvz.data_ptr(), oidx.data_ptr(), odesc.data_ptr())
+    ctx.scene_clip_dev(*args, reps=3)
+    kept, ms = ctx.scene_clip_dev(*args, reps=20)
+    alg = n * 12 + kept * (12 + 12 + 4 + 32 + 32)  # map read once; survivors: xyz, uvz, index, descriptor read + write
+    gbs = alg / (ms * 1e-3) / 1e9
+    return {"metric": "scene_clip_gpoints_per_s", "value": n / (ms * 1e-3) / 1e9, "unit": "GPoint/s", "ms": ms,
+            "map_points": n, "survivors": int(kept),
+            "roofline": {"kernel": "scene_clip_kernel", "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": gbs / hbm_peak, "alg_bytes_per_launch": alg}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -410,6 +436,12 @@ def main():
             line["tracking"] = tracking_lines(ctx, capi, stream, dev)
         except Exception as e:  # secondary lines must never cost the headline
             line["tracking"] = {"error": repr(e)}
+
+    if rank == 0 and not args.no_tracking:
+        try:
+            line["scene_clip"] = scene_clip_line(ctx, capi, dev, hbm_peak)
+        except Exception as e:
+            line["scene_clip"] = {"error": repr(e)}
 
     # ---- CPU baseline (rank 0, N = 1 only): the oracle on a bounded sample -----------------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -199,6 +199,30 @@ int pslam_download_stereo_batch(pslam_ctx* ctx, int n_pairs, long long capacity_
 int pslam_triangulate(pslam_ctx* ctx, int n, const float* uvuv, const float* K9, float baseline_pixels_x,
                       float minimum_disparity_pixels, float infinity_depth_meters, float* xyz, uint8_t* valid);
 
+/* ---- N2 (next after the path): projective scene clipping --------------------------------
+ * Replaces SceneClipperProjective3D::compute (.../mapping/scene_clipper_projective_3d.cpp:9-67): the pinhole
+ * projector (srrg2_core PointProjectorPinhole_::compute) over the WHOLE local map with the camera at
+ * robot_in_local_map * sensor_in_robot (:46); survivors keep the map order (:52) and are moved into the robot frame
+ * when sensor_in_robot is not the identity (:60-62).  Outputs per survivor: point in the sensor / robot frame (xyz),
+ * projection (u, v, depth), index into the full scene (SceneClipper::globalIndices) and the copied descriptor.  Any
+ * output pointer may be NULL.  Poses are row-major 3x4 [R|t].  Returns the number of survivors (or PSLAM_E_*;
+ * PSLAM_E_CAPACITY when more than `capacity` points survive). */
+typedef struct pslam_clip_cfg {
+  float K[9];
+  int canvas_rows, canvas_cols;
+  float range_min, range_max;     /* projector range [m] (kitti.conf:172-179) */
+  float camera_in_map[12];        /* robot_in_local_map * sensor_in_robot */
+  float sensor_in_robot[12];
+  int apply_sensor_in_robot;      /* 0: sensor_in_robot is the identity, nothing is applied (like the reference) */
+} pslam_clip_cfg;
+int pslam_scene_clip(pslam_ctx* ctx, int n, const float* xyz, const uint8_t* desc_or_null, const pslam_clip_cfg* cfg,
+                     int capacity, float* out_xyz, float* out_uvz, int* out_index, uint8_t* out_desc);
+/* device-resident map and outputs (all d_* are device pointers sized for n points; d_desc / outputs may be NULL);
+ * the launch is repeated `reps` times and *ms_per_call (if not NULL) receives the mean CUDA-event time of one pass */
+int pslam_scene_clip_dev(pslam_ctx* ctx, long long n, const float* d_xyz, const uint32_t* d_desc, const pslam_clip_cfg* cfg,
+                         float* d_out_xyz, float* d_out_uvz, int* d_out_index, uint32_t* d_out_desc, long long* n_out,
+                         int reps, double* ms_per_call);
+
 /* ---- stage 2b: exhaustive Hamming matching --------------------------------------
  * Replaces CorrespondenceFinderDescriptorBasedBruteforce::compute
  *   (.../correspondence_finders/correspondence_finder_descriptor_based_bruteforce_impl.cpp:6-294).

@@ -107,6 +107,16 @@ int psp_aligner_iteration_stats(psp_module* aligner, int capacity, double* rows4
 /* correspondences of the projective slice after the last compute */
 int psp_aligner_correspondences(psp_module* aligner, int capacity, int* fixed_idx, int* moving_idx, float* response);
 
+/* ---- SceneClipperProjective3D (mapping/scene_clipper_projective_3d.h:10-40): setFullScene / setRobotInLocalMap /
+ * setSensorInRobot / compute / globalIndices.  intensity may be NULL.  psp_clipper_compute returns the number of
+ * clipped points (in the robot frame, map order), their projections (u, v, depth), indices into the full scene and
+ * descriptors; *status receives SceneClipper::Status (0 Error, 1 Ready, 2 Successful). */
+int psp_clipper_set_full_scene(psp_module* clipper, int n, const float* xyz, const float* intensity, const uint8_t* desc);
+int psp_clipper_set_robot_in_local_map(psp_module* clipper, const float* pose12);
+int psp_clipper_set_sensor_in_robot(psp_module* clipper, const float* pose12);
+int psp_clipper_compute(psp_module* clipper, int capacity, float* xyz, float* uvz, int* global_index, uint8_t* desc,
+                        int* status);
+
 #ifdef __cplusplus
 }
 #endif

@@ -390,6 +390,45 @@ int orc_project(int n, const float* xyz, const float* pose12, const float* K9, i
   return m;
 }
 
+// SceneClipperProjective3D::compute  (.../mapping/scene_clipper_projective_3d.cpp:9-67):
+//   projector->setCameraPose(robot_in_local_map * sensor_in_robot) (:46); projector->compute(full_scene,
+//   clipped_scene, projections, global_indices) (:52); clipped_scene.transformInPlace(sensor_in_robot) when that is
+//   not the identity (:60-62).  camera_in_map12 is the product of :46 (the caller multiplies, like the reference).
+//   out_xyz: survivors in the sensor / robot frame, out_uvz: (u, v, depth), out_index: index into the full scene.
+int orc_scene_clip(int n, const float* xyz, const float* camera_in_map12, const float* sensor_in_robot12_or_null,
+                   const float* K9, int rows, int cols, float rmin, float rmax, float* out_xyz, float* out_uvz,
+                   int* out_index) {
+  ProjectorConfig pc;
+  std::memcpy(pc.K, K9, sizeof(pc.K));
+  pc.canvas_rows = rows;
+  pc.canvas_cols = cols;
+  pc.range_min = rmin;
+  pc.range_max = rmax;
+  const Pose<float> map_in_camera = pose_from(camera_in_map12).inverse();
+  Pose<float> S = Pose<float>::identity();
+  if (sensor_in_robot12_or_null) S = pose_from(sensor_in_robot12_or_null);
+  int m = 0;
+  for (int i = 0; i < n; ++i) {
+    float o[3], c[3];
+    if (!project_point(pc, map_in_camera, xyz + 3 * i, o)) continue;
+    map_in_camera.apply(xyz + 3 * i, c);  // the point in the camera frame (second output of the projector)
+    if (sensor_in_robot12_or_null) {
+      float r[3];
+      S.apply(c, r);
+      c[0] = r[0];
+      c[1] = r[1];
+      c[2] = r[2];
+    }
+    for (int k = 0; k < 3; ++k) {
+      out_xyz[3 * m + k] = c[k];
+      out_uvz[3 * m + k] = o[k];
+    }
+    out_index[m] = i;
+    ++m;
+  }
+  return m;
+}
+
 // ---- stateful projective finder ----------------------------------------------
 struct OrcFinder {
   ProjectiveFinder f;

@@ -47,6 +47,24 @@ class ProjectiveCfg(C.Structure):
                 ("maximum_distance_ratio_to_second_best", C.c_float)]
 
 
+class ClipCfg(C.Structure):
+    """pslam_clip_cfg"""
+    _fields_ = [("K", C.c_float * 9), ("canvas_rows", C.c_int), ("canvas_cols", C.c_int), ("range_min", C.c_float),
+                ("range_max", C.c_float), ("camera_in_map", C.c_float * 12), ("sensor_in_robot", C.c_float * 12),
+                ("apply_sensor_in_robot", C.c_int)]
+
+
+def clip_cfg(K, rows, cols, camera_in_map, range_min=0.1, range_max=1000.0, sensor_in_robot=None):
+    c = ClipCfg()
+    c.K[:] = [float(x) for x in np.asarray(K, np.float32).reshape(9)]
+    c.canvas_rows, c.canvas_cols, c.range_min, c.range_max = int(rows), int(cols), float(range_min), float(range_max)
+    c.camera_in_map[:] = [float(x) for x in np.asarray(camera_in_map, np.float32).reshape(12)]
+    s = np.eye(3, 4, dtype=np.float32) if sensor_in_robot is None else np.asarray(sensor_in_robot, np.float32)
+    c.sensor_in_robot[:] = [float(x) for x in s.reshape(12)]
+    c.apply_sensor_in_robot = 0 if sensor_in_robot is None else 1
+    return c
+
+
 class LinearizeCfg(C.Structure):
     _fields_ = [("kind", C.c_int), ("K", C.c_double * 9), ("image_cols", C.c_double),
                 ("image_rows", C.c_double), ("baseline", C.c_double * 3), ("mean_disparity", C.c_double),
@@ -276,6 +294,31 @@ class Context:
         n = self._chk(lib().pslam_triangulate(self._h, len(uvuv), _p(uvuv), _p(K), C.c_float(b_x), C.c_float(min_disparity),
                                               C.c_float(infinity_depth), _p(xyz), _p(valid)))
         return xyz, valid.astype(bool), n
+
+    # ---- N2: SceneClipperProjective3D ----------------------------------------------------------
+    def scene_clip(self, xyz, cfg, desc=None, capacity=None):
+        xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+        n = len(xyz)
+        cap = n if capacity is None else int(capacity)
+        if desc is not None:
+            desc = np.ascontiguousarray(desc, np.uint8).reshape(n, 32)
+        oxyz, ouvz, oidx = np.zeros((cap, 3), np.float32), np.zeros((cap, 3), np.float32), np.zeros(cap, np.int32)
+        odesc = np.zeros((cap, 32), np.uint8) if desc is not None else None
+        m = self._chk(lib().pslam_scene_clip(self._h, n, _p(xyz), _p(desc) if desc is not None else None, C.byref(cfg), cap,
+                                             _p(oxyz), _p(ouvz), _p(oidx), _p(odesc) if odesc is not None else None))
+        out = {"xyz": oxyz[:m].copy(), "uvz": ouvz[:m].copy(), "index": oidx[:m].copy()}
+        if odesc is not None:
+            out["desc"] = odesc[:m].copy()
+        return out
+
+    def scene_clip_dev(self, n, d_xyz, d_desc, cfg, d_out_xyz, d_out_uvz, d_out_index, d_out_desc, reps=1):
+        """device pointers (ints, 0 = NULL); returns (survivors, mean ms per pass)"""
+        n_out, ms = C.c_longlong(0), C.c_double(0)
+        self._chk(lib().pslam_scene_clip_dev(self._h, C.c_longlong(int(n)), C.c_void_p(d_xyz), C.c_void_p(d_desc or None),
+                                             C.byref(cfg), C.c_void_p(d_out_xyz or None), C.c_void_p(d_out_uvz or None),
+                                             C.c_void_p(d_out_index or None), C.c_void_p(d_out_desc or None),
+                                             C.byref(n_out), int(reps), C.byref(ms)))
+        return n_out.value, ms.value
 
     def bf_best2(self, desc_f, desc_m):
         desc_f = np.ascontiguousarray(desc_f, np.uint8).reshape(-1, 32)

@@ -699,6 +699,107 @@ int pslam_triangulate(pslam_ctx* ctx, int n, const float* uvuv, const float* K9,
   return n_valid;
 }
 
+// ---- N2: projective scene clipping ----------------------------------------------------------------
+// inverse of a row-major 3x4 isometry, fp32, operation order of the oracle's Pose::inverse
+static void clip_invert(const float* T, float* inv) {
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) inv[4 * i + j] = T[4 * j + i];
+  for (int i = 0; i < 3; ++i) inv[4 * i + 3] = -((inv[4 * i] * T[3] + inv[4 * i + 1] * T[7]) + inv[4 * i + 2] * T[11]);
+}
+
+int pslam_scene_clip_dev(pslam_ctx* ctx, long long n, const float* d_xyz, const uint32_t* d_desc, const pslam_clip_cfg* cfg,
+                         float* d_out_xyz, float* d_out_uvz, int* d_out_index, uint32_t* d_out_desc, long long* n_out,
+                         int reps, double* ms_per_call) {
+  if (!ctx || !cfg || n < 0 || (n > 0 && !d_xyz) || (d_out_desc && !d_desc) || reps < 1) return PSLAM_E_INVALID;
+  PSLAM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const size_t state_bytes = pslam_k_scene_clip_state_bytes(n);
+  if (PSLAM_SOLVER_SCRATCH_OFFSET + state_bytes > ctx->scratch_bytes)
+    return pslam_set_error(ctx, PSLAM_E_CAPACITY, "scene_clip: too many points for the scratch buffer", cudaSuccess);
+  unsigned long long* d_state = reinterpret_cast<unsigned long long*>(ctx->d_scratch + PSLAM_SOLVER_SCRATCH_OFFSET);
+  float inv[12];
+  clip_invert(cfg->camera_in_map, inv);
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (ms_per_call) {
+    PSLAM_CUDA_TRY(ctx, cudaEventCreate(&e0));
+    PSLAM_CUDA_TRY(ctx, cudaEventCreate(&e1));
+    cudaEventRecord(e0, ctx->stream);
+  }
+  long long* d_n = nullptr;
+  int rc = PSLAM_OK;
+  for (int r = 0; r < reps && rc == PSLAM_OK; ++r)
+    rc = pslam_k_scene_clip(ctx, n, d_xyz, d_desc, inv, cfg->apply_sensor_in_robot ? cfg->sensor_in_robot : nullptr, cfg->K,
+                            cfg->canvas_rows, cfg->canvas_cols, cfg->range_min, cfg->range_max, d_state, d_out_xyz, d_out_uvz,
+                            d_out_index, d_out_desc, &d_n);
+  if (ms_per_call) {
+    if (rc == PSLAM_OK) {
+      cudaEventRecord(e1, ctx->stream);
+      cudaEventSynchronize(e1);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e0, e1);
+      *ms_per_call = (double) ms / reps;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+  }
+  if (rc) return rc;
+  long long* h_n = reinterpret_cast<long long*>(ctx->h_pinned);
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(h_n, d_n, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (n_out) *n_out = *h_n;
+  return PSLAM_OK;
+}
+
+int pslam_scene_clip(pslam_ctx* ctx, int n, const float* xyz, const uint8_t* desc, const pslam_clip_cfg* cfg, int capacity,
+                     float* out_xyz, float* out_uvz, int* out_index, uint8_t* out_desc) {
+  if (!ctx || !cfg || n < 0 || capacity < 0 || (n > 0 && !xyz) || (out_desc && !desc)) return PSLAM_E_INVALID;
+  if (n == 0) return 0;
+  PSLAM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  // carve: [state][xyz in][desc in][xyz out][uvz out][index out][desc out], above the finder's cache partition
+  auto al = [](size_t b) { return (b + 255) & ~(size_t) 255; };
+  const size_t b_state = al(pslam_k_scene_clip_state_bytes(n)), b_xyz = al((size_t) n * 12), b_desc = desc ? al((size_t) n * 32) : 0,
+               b_idx = al((size_t) n * 4);
+  const size_t need = b_state + 3 * b_xyz + 2 * b_desc + b_idx;
+  // maps that do not fit the context scratch (64 MB) get a temporary device block for this call; a caller that clips
+  // every frame keeps the map in HBM and uses pslam_scene_clip_dev
+  uint8_t* tmp = nullptr;
+  uint8_t* p = ctx->d_scratch + PSLAM_SOLVER_SCRATCH_OFFSET + b_state;
+  if (PSLAM_SOLVER_SCRATCH_OFFSET + need > ctx->scratch_bytes) {
+    PSLAM_CUDA_TRY(ctx, cudaMalloc(&tmp, need));
+    p = tmp;
+  }
+  float* d_xyz = reinterpret_cast<float*>(p);
+  p += b_xyz;
+  uint32_t* d_desc = desc ? reinterpret_cast<uint32_t*>(p) : nullptr;
+  p += b_desc;
+  float* d_oxyz = reinterpret_cast<float*>(p);
+  p += b_xyz;
+  float* d_ouvz = reinterpret_cast<float*>(p);
+  p += b_xyz;
+  int* d_oidx = reinterpret_cast<int*>(p);
+  p += b_idx;
+  uint32_t* d_odesc = desc ? reinterpret_cast<uint32_t*>(p) : nullptr;
+  long long kept = 0;
+  auto run = [&]() -> int {
+    PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_xyz, xyz, (size_t) n * 12, cudaMemcpyHostToDevice, ctx->stream));
+    if (desc) PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_desc, desc, (size_t) n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    const int rc = pslam_scene_clip_dev(ctx, n, d_xyz, d_desc, cfg, d_oxyz, d_ouvz, d_oidx, out_desc ? d_odesc : nullptr, &kept, 1, nullptr);
+    if (rc) return rc;
+    if (kept > capacity) return pslam_set_error(ctx, PSLAM_E_CAPACITY, "scene_clip: more survivors than the output capacity", cudaSuccess);
+    if (kept > 0) {
+      if (out_xyz) PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(out_xyz, d_oxyz, (size_t) kept * 12, cudaMemcpyDeviceToHost, ctx->stream));
+      if (out_uvz) PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(out_uvz, d_ouvz, (size_t) kept * 12, cudaMemcpyDeviceToHost, ctx->stream));
+      if (out_index) PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(out_index, d_oidx, (size_t) kept * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      if (out_desc) PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(out_desc, d_odesc, (size_t) kept * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return PSLAM_OK;
+  };
+  const int rc = run();
+  if (tmp) cudaFree(tmp);
+  if (rc) return rc;
+  return (int) kept;
+}
+
 // ---- stage 2b -----------------------------------------------------------------------------------
 static int bf_upload(pslam_ctx* ctx, int nf, const uint8_t* df, int nm, const uint8_t* dm,
                      uint32_t** d_f, uint32_t** d_m, size_t* used) {

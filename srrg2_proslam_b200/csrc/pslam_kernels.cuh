@@ -63,3 +63,10 @@ int pslam_k_gn_iterate(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, int n_ite
                        double* h_out16, int* h_iters_done, int* h_spd);
 int pslam_k_gn_step(pslam_ctx* ctx, const double* H36, const double* b6, double damping,
                     double* pose12, double* dx6);
+
+// k_scene.cu (N2: projective scene clipping over the whole local map)
+int pslam_k_scene_clip(pslam_ctx* ctx, long long n, const float* d_xyz, const uint32_t* d_desc, const float* map_in_camera12,
+                       const float* sensor_in_robot12, const float* K9, int rows, int cols, float range_min, float range_max,
+                       unsigned long long* d_state, float* d_out_xyz, float* d_out_uvz, int* d_out_index,
+                       uint32_t* d_out_desc, long long** d_n_out);
+size_t pslam_k_scene_clip_state_bytes(long long n);

@@ -637,6 +637,67 @@ void RawDataPreprocessorMonocularDepthCUDA::compute() {
   _status = Ready;
 }
 
+// ---- scene clipper (mapping/scene_clipper_projective_3d.cpp:9-67) -----------------------------------------------
+void SceneClipperProjective3DCUDA::compute() {
+  _status = Error;
+  if (!param_projector.value()) throw std::runtime_error("SceneClipperProjective3D::compute|ERROR: missing projector");
+  if (!_clipped_scene_in_robot) throw std::runtime_error("SceneClipperProjective3D::compute|ERROR: missing clipped scene");
+  if (!_full_scene) throw std::runtime_error("SceneClipperProjective3D::compute|ERROR: missing global scene");
+  if (_full_scene->empty()) {
+    std::cerr << "SceneClipperProjective3D::compute|WARNING: global scene is empty, no clipping will be performed" << std::endl;
+    _status = Ready;
+    return;
+  }
+  if (_full_scene->dim != 3) throw std::runtime_error("SceneClipperProjective3D::compute|ERROR: the scene must hold 3D points");
+  _clipped_scene_in_robot->clear();
+  _global_indices.clear();
+  _projections.clear();
+  const ProjectorPinhole& projector = *param_projector.value();
+  pslam_clip_cfg cfg;
+  for (int i = 0; i < 9; ++i) cfg.K[i] = projector.cameraMatrix()[i];
+  cfg.canvas_rows = (int) projector.param_canvas_rows.value();
+  cfg.canvas_cols = (int) projector.param_canvas_cols.value();
+  cfg.range_min = projector.param_range_min.value();
+  cfg.range_max = projector.param_range_max.value();
+  const Isometry3f camera = _robot_in_local_map * _sensor_in_robot;  // projector->setCameraPose(...), :46
+  bool sensor_is_identity = true;
+  const Isometry3f I;
+  for (int i = 0; i < 12; ++i) {
+    cfg.camera_in_map[i] = camera.m[i];
+    cfg.sensor_in_robot[i] = _sensor_in_robot.m[i];
+    if (_sensor_in_robot.m[i] != I.m[i]) sensor_is_identity = false;
+  }
+  cfg.apply_sensor_in_robot = sensor_is_identity ? 0 : 1;  // :60
+  const int n = (int) _full_scene->size();
+  pslam_ctx* ctx = PslamDevice::context(cfg.canvas_rows, cfg.canvas_cols);
+  PointIntensityDescriptorCloud& out = *_clipped_scene_in_robot;
+  out.dim = 3;
+  out.number_of_optimizations.clear();
+  out.resize(n);
+  _global_indices.resize(n);
+  _projections.resize((size_t) 3 * n);
+  const int kept = pslam_scene_clip(ctx, n, _full_scene->coordinates.data(), _full_scene->descriptor.data(), &cfg, n,
+                                    out.coordinates.data(), _projections.data(), _global_indices.data(), out.descriptor.data());
+  if (kept < 0) {
+    out.resize(0);
+    _global_indices.clear();
+    _projections.clear();
+  }
+  PslamDevice::check(kept, "SceneClipperProjective3D::compute");
+  // the remaining fields of the survivors are copied like the projector copies the whole point (:52)
+  for (int k = 0; k < kept; ++k) out.intensity[k] = _full_scene->intensity[_global_indices[k]];
+  const bool has_stats = !_full_scene->number_of_optimizations.empty();
+  out.resize(kept);
+  if (has_stats) {
+    out.number_of_optimizations.resize(kept);
+    for (int k = 0; k < kept; ++k) out.number_of_optimizations[k] = _full_scene->number_of_optimizations[_global_indices[k]];
+  }
+  _global_indices.resize(kept);
+  _projections.resize((size_t) 3 * kept);
+  if (out.empty()) std::cerr << "SceneClipperProjective3D::compute|WARNING: clipped empty scene" << std::endl;
+  _status = Successful;
+}
+
 // ---- aligner slice ----------------------------------------------------------------------------------------------
 AlignerSliceProcessorProjectiveCUDA::AlignerSliceProcessorProjectiveCUDA(int kind) : _kind(kind) {
   // aligner_slice_processor_projective.cpp:7-20: saturated robustifier with chi threshold 100^2 by default
@@ -848,6 +909,7 @@ void registerTypes() {
   reg<SliceK<0>>("AlignerSliceProcessorProjectiveStereo");
   reg<SliceK<0>>("AlignerSliceProcessorProjectiveStereoWithSensor");  // kitti_in_baselink.conf
   reg<MultiAligner3DQRCUDA>("MultiAligner3DQR");
+  reg<SceneClipperProjective3DCUDA>("SceneClipperProjective3D");  // mapping/instances.cpp
   // srrg2_core / srrg2_solver modules the hot-path classes link to
   PSLAM_REGISTER_CLASS_AS(ProjectorPinhole, "PointIntensityDescriptor3fProjectorPinhole");
   PSLAM_REGISTER_CLASS_AS(RobustifierSaturated, "RobustifierSaturated");

@@ -426,6 +426,34 @@ private:
   std::vector<AlignerIterationStats> _stats;
 };
 
+// ---- SceneClipperProjective3D (mapping/scene_clipper_projective_3d.{h,cpp}) -----------------------
+// srrg2_slam_interfaces::SceneClipper_ contract: setFullScene / setClippedSceneInRobot / setRobotInLocalMap /
+// setSensorInRobot, compute(), status(), globalIndices().  The projection + ordered compaction of the whole local
+// map runs in scene_clip_kernel (pslam_scene_clip).
+class SceneClipperProjective3DCUDA : public Configurable {
+public:
+  enum Status { Error = 0, Ready = 1, Successful = 2 };
+  PARAM(PropertyConfigurable_<ProjectorPinhole>, projector,
+        "pinhole projector used to determine whether points lie in the current view", std::make_shared<ProjectorPinhole>(), nullptr);
+  void setFullScene(const PointIntensityDescriptorCloud* scene) { _full_scene = scene; }
+  void setClippedSceneInRobot(PointIntensityDescriptorCloud* clipped) { _clipped_scene_in_robot = clipped; }
+  void setRobotInLocalMap(const Isometry3f& T) { _robot_in_local_map = T; }
+  void setSensorInRobot(const Isometry3f& T) { _sensor_in_robot = T; }
+  void compute();  // scene_clipper_projective_3d.cpp:9-67
+  Status status() const { return _status; }
+  const std::vector<int>& globalIndices() const { return _global_indices; }
+  // (u, v, depth) of the survivors: the projector's third output, "can be reused for e.g. alignment" (:48-49)
+  const std::vector<float>& projections() const { return _projections; }
+
+private:
+  const PointIntensityDescriptorCloud* _full_scene = nullptr;
+  PointIntensityDescriptorCloud* _clipped_scene_in_robot = nullptr;
+  Isometry3f _robot_in_local_map, _sensor_in_robot;
+  std::vector<int> _global_indices;
+  std::vector<float> _projections;
+  Status _status = Error;
+};
+
 // registers every class above under the reference's names and under the ...CUDA names (idempotent)
 void registerTypes();
 

@@ -504,4 +504,67 @@ int psp_aligner_correspondences(psp_module* aligner, int capacity, int* fixed_id
   });
 }
 
+// ---- SceneClipperProjective3D ----------------------------------------------------------------------------------
+int psp_clipper_set_full_scene(psp_module* clipper, int n, const float* xyz, const float* intensity, const uint8_t* desc) {
+  return guard([&] {
+    auto* c = as<SceneClipperProjective3DCUDA>(clipper, "SceneClipperProjective3D");
+    Storage& st = storage_of(mod(clipper));
+    st.moving.dim = 3;
+    st.moving.number_of_optimizations.clear();
+    st.moving.resize(n);
+    if (n > 0) {
+      std::memcpy(st.moving.coordinates.data(), xyz, sizeof(float) * 3 * (size_t) n);
+      if (intensity) std::memcpy(st.moving.intensity.data(), intensity, sizeof(float) * (size_t) n);
+      else std::fill(st.moving.intensity.begin(), st.moving.intensity.end(), 0.f);
+      std::memcpy(st.moving.descriptor.data(), desc, 32 * (size_t) n);
+    }
+    c->setFullScene(&st.moving);
+    return 0;
+  });
+}
+
+int psp_clipper_set_robot_in_local_map(psp_module* clipper, const float* pose12) {
+  return guard([&] {
+    Isometry3f T;
+    std::memcpy(T.m, pose12, sizeof(T.m));
+    as<SceneClipperProjective3DCUDA>(clipper, "SceneClipperProjective3D")->setRobotInLocalMap(T);
+    return 0;
+  });
+}
+
+int psp_clipper_set_sensor_in_robot(psp_module* clipper, const float* pose12) {
+  return guard([&] {
+    Isometry3f T;
+    std::memcpy(T.m, pose12, sizeof(T.m));
+    as<SceneClipperProjective3DCUDA>(clipper, "SceneClipperProjective3D")->setSensorInRobot(T);
+    return 0;
+  });
+}
+
+int psp_clipper_compute(psp_module* clipper, int capacity, float* xyz, float* uvz, int* global_index, uint8_t* desc,
+                        int* status) {
+  return guard([&] {
+    auto* c = as<SceneClipperProjective3DCUDA>(clipper, "SceneClipperProjective3D");
+    Storage& st = storage_of(mod(clipper));
+    st.fixed.dim = 3;
+    c->setClippedSceneInRobot(&st.fixed);
+    struct StatusOut {
+      SceneClipperProjective3DCUDA* c;
+      int* s;
+      ~StatusOut() {
+        if (s) *s = (int) c->status();
+      }
+    } so{c, status};
+    c->compute();
+    if (c->status() != SceneClipperProjective3DCUDA::Successful) return 0;
+    const int n = copy_cloud(st.fixed, capacity, xyz, nullptr, desc);
+    const int m = n < capacity ? n : capacity;
+    if (m > 0) {
+      if (uvz) std::memcpy(uvz, c->projections().data(), sizeof(float) * 3 * (size_t) m);
+      if (global_index) std::memcpy(global_index, c->globalIndices().data(), sizeof(int) * (size_t) m);
+    }
+    return n;
+  });
+}
+
 }  // extern "C"

@@ -190,6 +190,31 @@ class Module:
         no = None if n_opt is None else np.ascontiguousarray(n_opt, np.int32)
         _chk(lib().psp_aligner_set_moving(self.h, len(xyz), _p(xyz), _p(desc), _p(no)))
 
+    # ---- SceneClipperProjective3D ----------------------------------------------------------------------------------
+    def clipper_set_full_scene(self, xyz, desc, intensity=None):
+        xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(len(xyz), 32)
+        inten = None if intensity is None else np.ascontiguousarray(intensity, np.float32)
+        self._scene_size = len(xyz)
+        _chk(lib().psp_clipper_set_full_scene(self.h, len(xyz), _p(xyz), _p(inten), _p(desc)))
+
+    def clipper_set_robot_in_local_map(self, pose12):
+        pose12 = np.ascontiguousarray(pose12, np.float32).reshape(12)
+        _chk(lib().psp_clipper_set_robot_in_local_map(self.h, _p(pose12)))
+
+    def clipper_set_sensor_in_robot(self, pose12):
+        pose12 = np.ascontiguousarray(pose12, np.float32).reshape(12)
+        _chk(lib().psp_clipper_set_sensor_in_robot(self.h, _p(pose12)))
+
+    def clipper_compute(self):
+        cap = max(1, getattr(self, "_scene_size", 0))
+        xyz, uvz = np.zeros((cap, 3), np.float32), np.zeros((cap, 3), np.float32)
+        idx, desc = np.zeros(cap, np.int32), np.zeros((cap, 32), np.uint8)
+        status = C.c_int(-1)
+        n = _chk(lib().psp_clipper_compute(self.h, cap, _p(xyz), _p(uvz), _p(idx), _p(desc), C.byref(status)))
+        return {"xyz": xyz[:n].copy(), "uvz": uvz[:n].copy(), "index": idx[:n].copy(), "desc": desc[:n].copy(),
+                "status": status.value}
+
     def aligner_set_moving_in_fixed(self, pose12):
         pose12 = np.ascontiguousarray(pose12, np.float32).reshape(12)
         _chk(lib().psp_aligner_set_moving_in_fixed(self.h, _p(pose12)))

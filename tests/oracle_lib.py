@@ -250,6 +250,19 @@ def project(xyz, pose12, K, rows, cols, rmin=0.1, rmax=1000.0):
     return uvz[:n].copy(), idx[:n].copy()
 
 
+def scene_clip(xyz, camera_in_map, K, rows, cols, rmin=0.1, rmax=1000.0, sensor_in_robot=None):
+    """SceneClipperProjective3D::compute (mapping/scene_clipper_projective_3d.cpp:9-67)"""
+    xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+    T = np.ascontiguousarray(camera_in_map, np.float32).reshape(12)
+    S = None if sensor_in_robot is None else np.ascontiguousarray(sensor_in_robot, np.float32).reshape(12)
+    K = np.ascontiguousarray(K, np.float32).reshape(9)
+    n = len(xyz)
+    oxyz, ouvz, oidx = np.zeros((n, 3), np.float32), np.zeros((n, 3), np.float32), np.zeros(n, np.int32)
+    m = lib().orc_scene_clip(n, _p(xyz), _p(T), _p(S) if S is not None else None, _p(K), rows, cols, C.c_float(rmin),
+                             C.c_float(rmax), _p(oxyz), _p(ouvz), _p(oidx))
+    return oxyz[:m].copy(), ouvz[:m].copy(), oidx[:m].copy()
+
+
 SHAPES = {"square": 0, "circle": 1, "rhombus": 2}
 
 
