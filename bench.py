@@ -216,6 +216,33 @@ def scene_clip_line(ctx, capi, dev, hbm_peak):
                          "note": "time = event-to-event interval with profiling on (includes ~5 us of event overhead)"}}
 
 
+def landmarks_ekf_line(ctx, capi, dev):
+    """N3: LandmarkEstimatorStereoProjectiveEKF3D over a device-resident batch of 4 M landmarks (one thread
+    per landmark, fp64 inside).  Per landmark: 64 B in (state, covariance, measurement), 61 B out; ~1.1 kFLOP fp64."""
+    import torch
+    n = 1 << 22
+    g = torch.Generator(device=dev).manual_seed(11)
+    truth = torch.stack([torch.rand(n, generator=g, device=dev) * 8 - 4, torch.rand(n, generator=g, device=dev) * 4 - 2,
+                         torch.rand(n, generator=g, device=dev) * 30 + 5], 1)
+    state = (truth + torch.randn((n, 3), generator=g, device=dev) * 0.1).contiguous()
+    cov = torch.eye(3, device=dev).reshape(1, 9).repeat(n, 1).contiguous()
+    fx, cx, cy, bx = 718.856, 607.193, 185.216, 386.1448
+    u = fx * truth[:, 0] / truth[:, 2] + cx
+    v = fx * truth[:, 1] / truth[:, 2] + cy
+    meas = torch.stack([u, v, u - bx / truth[:, 2], v], 1).contiguous()
+    local = torch.empty((n, 3), device=dev)
+    inl = torch.empty(n, dtype=torch.uint8, device=dev)
+    K = np.array([fx, 0, cx, 0, fx, cy, 0, 0, 1], np.float32)
+    cfg = capi.ekf_cfg("stereo", K, (bx, 0.0), np.eye(3, 4), np.eye(3, 4), max_cov_norm2=4.0, max_dist2=1.0)
+    torch.cuda.synchronize()
+    args = (n, state.data_ptr(), cov.data_ptr(), meas.data_ptr(), cfg, local.data_ptr(), inl.data_ptr())
+    ctx.landmarks_ekf_update_dev(*args, reps=2)
+    cnt, ms = ctx.landmarks_ekf_update_dev(*args, reps=10)
+    return {"metric": "landmark_ekf_updates_per_s", "value": n / (ms * 1e-3) / 1e9, "unit": "GLandmark/s", "ms": ms,
+            "landmarks": n, "inliers": int(cnt), "hbm_gbs": n * (64 + 61) / (ms * 1e-3) / 1e9,
+            "fp64_tflops": n * 1100.0 / (ms * 1e-3) / 1e12}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -451,6 +478,10 @@ def main():
             line["scene_clip"] = scene_clip_line(ctx, capi, dev, hbm_peak)
         except Exception as e:
             line["scene_clip"] = {"error": repr(e)}
+        try:
+            line["landmark_ekf"] = landmarks_ekf_line(ctx, capi, dev)
+        except Exception as e:
+            line["landmark_ekf"] = {"error": repr(e)}
 
     # ---- CPU baseline (rank 0, N = 1 only): the oracle on a bounded sample -----------------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -223,6 +223,34 @@ int pslam_scene_clip_dev(pslam_ctx* ctx, long long n, const float* d_xyz, const 
                          float* d_out_xyz, float* d_out_uvz, int* d_out_index, uint32_t* d_out_desc, long long* n_out,
                          int reps, double* ms_per_call);
 
+/* ---- N3 (next after the path): per-landmark EKF update of the merger ----------------------
+ * Replaces LandmarkEstimatorEKF_::compute (.../mapping/landmarks/landmark_estimator_ekf_impl.cpp:17-82) with its
+ * filters PointEKFBase::_predict/_correct (.../landmarks/filters/point_ekf_base.hpp:62-131) and the three measurement
+ * models (.../filters/{projective,projective_depth,stereo_projective}_point_ekf_impl.cpp), called by
+ * MergerProjective_::_updatePoint once per correspondence (.../mergers/merger_projective_impl.cpp:129,176-193).
+ * n landmarks that share the frame's transforms (LandmarkEstimatorBase_::setTransforms,
+ * landmark_estimator_base.hpp:49-58) are filtered in one launch, double precision inside like the reference.
+ * state_world [n][3] and covariance [n][9] are the landmark statistics (state(), covariance()): updated IN PLACE for
+ * the landmarks the estimator accepts (what addOptimizationResult stores, :74-75); coords_in_local_map [n][3] receives
+ * their new local coordinates (:79-80), inlier[n] = statistics().isInlier().  measurements: [n][E], E = 2 / 3 / 4.
+ * Returns the number of inliers. */
+typedef struct pslam_ekf_cfg {
+  int kind;                                        /* 0 projective (u,v) | 1 projective depth (u,v,z) | 2 rectified stereo (uL,vL,uR,vR) */
+  float K[9];                                      /* filter->setCameraMatrix */
+  double baseline_pixels[2];                       /* StereoProjectivePointEKF::setBaseline (b_x, b_y) */
+  double minimum_state_element_covariance;         /* PARAM, default 0.01 (landmark_estimator_ekf.h:33) */
+  double maximum_covariance_norm_squared;          /* PARAM, default 1 (:38) */
+  float maximum_distance_geometry_meters_squared;  /* PARAM, default 1 (landmark_estimator_base.hpp:22) */
+  float sensor_in_world[12];                       /* setTransforms(measurement_in_world, measurement_in_scene) */
+  float sensor_in_local_map[12];
+} pslam_ekf_cfg;
+int pslam_landmarks_ekf_update(pslam_ctx* ctx, int n, float* state_world, float* covariance, const float* measurements,
+                               const pslam_ekf_cfg* cfg, float* coords_in_local_map, uint8_t* inlier);
+/* device-resident variant (all d_* device pointers); `reps` launches, *ms_per_call = mean CUDA-event time of one */
+int pslam_landmarks_ekf_update_dev(pslam_ctx* ctx, long long n, float* d_state_world, float* d_covariance,
+                                   const float* d_measurements, const pslam_ekf_cfg* cfg, float* d_coords_in_local_map,
+                                   uint8_t* d_inlier, int* n_inliers, int reps, double* ms_per_call);
+
 /* ---- stage 2b: exhaustive Hamming matching --------------------------------------
  * Replaces CorrespondenceFinderDescriptorBasedBruteforce::compute
  *   (.../correspondence_finders/correspondence_finder_descriptor_based_bruteforce_impl.cpp:6-294).

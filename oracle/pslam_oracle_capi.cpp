@@ -12,6 +12,7 @@
 
 #include "pslam_oracle.hpp"
 #include "pslam_oracle_solver.hpp"
+#include "pslam_oracle_mapping.hpp"
 
 using namespace pslam_oracle;
 
@@ -427,6 +428,66 @@ int orc_scene_clip(int n, const float* xyz, const float* camera_in_map12, const 
     ++m;
   }
   return m;
+}
+
+// ---- N3: point EKFs and LandmarkEstimatorEKF (pslam_oracle_mapping.hpp) ------------------------------------
+// PointEKFBase::compute for one point, double precision (tests/test_*_point_ekf.cpp drive the filter like this).
+// cam6 = fx, fy, cx, cy, bx, by; world_in_sensor12 row-major 3x4; Q 3x3; Rm E x E.
+int orc_point_ekf(int kind, const double* cam6, const double* world_in_sensor12, const double* Q9, const double* meas,
+                  const double* Rm, double* state3, double* cov9) {
+  EkfCamera cam;
+  cam.fx = cam6[0];
+  cam.fy = cam6[1];
+  cam.cx = cam6[2];
+  cam.cy = cam6[3];
+  cam.bx = cam6[4];
+  cam.by = cam6[5];
+  double R[9], t[3];
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) R[3 * i + j] = world_in_sensor12[4 * i + j];
+    t[i] = world_in_sensor12[4 * i + 3];
+  }
+  if (kind == EKF_PROJECTIVE) ekf_compute<2>(cam, R, t, Q9, meas, Rm, state3, cov9);
+  else if (kind == EKF_PROJECTIVE_DEPTH) ekf_compute<3>(cam, R, t, Q9, meas, Rm, state3, cov9);
+  else if (kind == EKF_STEREO) ekf_compute<4>(cam, R, t, Q9, meas, Rm, state3, cov9);
+  else return -1;
+  return 0;
+}
+
+// LandmarkEstimatorEKF_::compute over n landmarks that share the frame's transforms (one merger pass).
+int orc_landmarks_ekf_update(int n, int kind, const float* K9, const double* baseline2, double min_cov, double max_cov_norm2,
+                             float max_dist2, const float* sensor_in_world12, const float* sensor_in_local_map12,
+                             float* state_world, float* covariance, const float* meas, float* coords_in_local_map,
+                             unsigned char* inlier) {
+  LandmarkEkfConfig cfg;
+  cfg.kind = kind;
+  std::memcpy(cfg.K, K9, sizeof(cfg.K));
+  cfg.baseline_pixels[0] = baseline2[0];
+  cfg.baseline_pixels[1] = baseline2[1];
+  cfg.minimum_state_element_covariance = min_cov;
+  cfg.maximum_covariance_norm_squared = max_cov_norm2;
+  cfg.maximum_distance_geometry_meters_squared = max_dist2;
+  std::memcpy(cfg.sensor_in_world, sensor_in_world12, sizeof(cfg.sensor_in_world));
+  std::memcpy(cfg.sensor_in_local_map, sensor_in_local_map12, sizeof(cfg.sensor_in_local_map));
+  // LandmarkEstimatorBase_::setTransforms (landmark_estimator_base.hpp:49-58), fp32
+  const Pose<float> sensor_in_world = pose_from(sensor_in_world12), sensor_in_local_map = pose_from(sensor_in_local_map12);
+  const Pose<float> world_in_sensor = sensor_in_world.inverse();
+  const Pose<float> world_in_local_map = sensor_in_local_map * world_in_sensor;
+  const int E = ekf_measurement_dim(kind);
+  int n_inliers = 0;
+  for (int i = 0; i < n; ++i) {
+    bool ok = false;
+    float* s = state_world + 3 * i;
+    float* c = covariance + 9 * i;
+    float* l = coords_in_local_map + 3 * i;
+    const float* m = meas + (size_t) E * i;
+    if (kind == EKF_PROJECTIVE) ok = landmark_ekf_update<2>(cfg, world_in_sensor.R, world_in_sensor.t, world_in_local_map.R, world_in_local_map.t, s, c, m, l);
+    else if (kind == EKF_PROJECTIVE_DEPTH) ok = landmark_ekf_update<3>(cfg, world_in_sensor.R, world_in_sensor.t, world_in_local_map.R, world_in_local_map.t, s, c, m, l);
+    else ok = landmark_ekf_update<4>(cfg, world_in_sensor.R, world_in_sensor.t, world_in_local_map.R, world_in_local_map.t, s, c, m, l);
+    inlier[i] = ok ? 1 : 0;
+    n_inliers += ok;
+  }
+  return n_inliers;
 }
 
 // ---- stateful projective finder ----------------------------------------------

@@ -1,0 +1,189 @@
+// pslam_oracle_mapping.hpp -- TEST INFRASTRUCTURE (CPU oracle), not the product.
+//
+// CPU restatement of the per-landmark structure-only filters that follow the frontend path:
+//   PointEKFBase::_predict / _correct          .../mapping/landmarks/filters/point_ekf_base.hpp:62-131
+//   ProjectivePointEKF                          .../filters/projective_point_ekf_impl.cpp:15-44
+//   ProjectiveDepthPointEKF                     .../filters/projective_depth_point_ekf_impl.cpp:5-37
+//   StereoProjectivePointEKF                    .../filters/stereo_projective_point_ekf_impl.cpp:13-48
+//   LandmarkEstimatorEKF_::setTransforms/compute .../mapping/landmarks/landmark_estimator_ekf_impl.cpp:6-82
+//   LandmarkEstimatorBase_::setTransforms        .../mapping/landmarks/landmark_estimator_base.hpp:49-58
+// All of this code is IN the reference tree (no external arithmetic except Eigen's fixed-size inverse(), restated as a
+// Gauss-Jordan elimination of the symmetric positive definite innovation covariance) and is pinned through the
+// scenarios of tests/test_{projective,projective_depth,stereo_projective}_point_ekf.cpp (tests/test_oracle_ekf.py).
+// The filter runs in double like the reference ("we locally operate in double precision", landmark_estimator_ekf.h:21).
+#pragma once
+#include <cmath>
+#include <cstring>
+
+namespace pslam_oracle {
+
+enum EkfKind { EKF_PROJECTIVE = 0, EKF_PROJECTIVE_DEPTH = 1, EKF_STEREO = 2 };
+static inline int ekf_measurement_dim(int kind) { return kind == EKF_PROJECTIVE ? 2 : (kind == EKF_PROJECTIVE_DEPTH ? 3 : 4); }
+
+struct EkfCamera {
+  double fx = 1, fy = 1, cx = 0, cy = 0;  // ProjectivePointEKF::setCameraMatrix (projective_point_ekf_impl.cpp:6-12)
+  double bx = 0, by = 0;                  // StereoProjectivePointEKF::setBaseline (stereo_projective_point_ekf_impl.cpp:6-10)
+};
+
+// in-place inverse of a symmetric positive definite E x E matrix (row major), Gauss-Jordan without pivoting
+template <int E>
+static inline void spd_inverse(double* A) {
+  double I[E * E];
+  for (int i = 0; i < E; ++i)
+    for (int j = 0; j < E; ++j) I[i * E + j] = i == j ? 1.0 : 0.0;
+  for (int k = 0; k < E; ++k) {
+    const double inv = 1.0 / A[k * E + k];
+    for (int j = 0; j < E; ++j) {
+      A[k * E + j] *= inv;
+      I[k * E + j] *= inv;
+    }
+    for (int i = 0; i < E; ++i) {
+      if (i == k) continue;
+      const double f = A[i * E + k];
+      for (int j = 0; j < E; ++j) {
+        A[i * E + j] -= f * A[k * E + j];
+        I[i * E + j] -= f * I[k * E + j];
+      }
+    }
+  }
+  std::memcpy(A, I, sizeof(I));
+}
+
+// h(state) and its 3-column Jacobian (row major E x 3) for the three filters: E = 2 projective, 3 projective depth,
+// 4 rectified stereo
+template <int E>
+static inline void ekf_predict_measurement(const EkfCamera& c, const double* s, double* h, double* J) {
+  const double x = s[0], y = s[1], z = s[2];
+  const double z_2 = z * z, fx_x = c.fx * x, fy_y = c.fy * y, fx_by_z = c.fx / z, fy_by_z = c.fy / z;
+  for (int i = 0; i < E * 3; ++i) J[i] = 0.0;
+  if constexpr (E == 4) {  // stereo_projective_point_ekf_impl.cpp:22-47
+    const double x_h = fx_x + c.cx * z, y_h = fy_y + c.cy * z;
+    h[0] = x_h / z;
+    h[1] = y_h / z;
+    h[2] = (x_h - c.bx) / z;
+    h[3] = (y_h - c.by) / z;
+    J[0] = fx_by_z; J[2] = -fx_x / z_2;
+    J[4] = fy_by_z; J[5] = -fy_y / z_2;
+    J[6] = fx_by_z; J[8] = -(fx_x - c.bx) / z_2;
+    J[10] = fy_by_z; J[11] = -(fy_y - c.by) / z_2;
+  } else {  // projective_point_ekf_impl.cpp:24-43, projective_depth_point_ekf_impl.cpp:14-36
+    h[0] = fx_by_z * x + c.cx;
+    h[1] = fy_by_z * y + c.cy;
+    J[0] = fx_by_z; J[2] = -fx_x / z_2;
+    J[4] = fy_by_z; J[5] = -fy_y / z_2;
+    if constexpr (E == 3) {
+      h[2] = z;
+      J[8] = 1.0;
+    }
+  }
+}
+
+// PointEKFBase::compute = _predict + _correct (point_ekf_base.hpp:48-131).  T = world_in_sensor (R row major 3x3, t),
+// Q = transition covariance, Rm = measurement covariance (E x E); state / cov are updated in place.
+template <int E>
+static inline void ekf_compute(const EkfCamera& cam, const double* R, const double* t, const double* Q,
+                               const double* meas, const double* Rm, double* state, double* cov) {
+  // _predict: cov = R cov R^T + Q; state = T state
+  double RC[9], P[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) RC[3 * i + j] = (R[3 * i] * cov[j] + R[3 * i + 1] * cov[3 + j]) + R[3 * i + 2] * cov[6 + j];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j)
+      P[3 * i + j] = ((RC[3 * i] * R[3 * j] + RC[3 * i + 1] * R[3 * j + 1]) + RC[3 * i + 2] * R[3 * j + 2]) + Q[3 * i + j];
+  double s[3];
+  for (int i = 0; i < 3; ++i) s[i] = ((R[3 * i] * state[0] + R[3 * i + 1] * state[1]) + R[3 * i + 2] * state[2]) + t[i];
+  // _correct
+  double h[E], J[E * 3];
+  ekf_predict_measurement<E>(cam, s, h, J);
+  double PJt[3 * E];  // P J^T (3 x E)
+  for (int i = 0; i < 3; ++i)
+    for (int k = 0; k < E; ++k) PJt[i * E + k] = (P[3 * i] * J[3 * k] + P[3 * i + 1] * J[3 * k + 1]) + P[3 * i + 2] * J[3 * k + 2];
+  double S[E * E];  // Rm + J P J^T
+  for (int a = 0; a < E; ++a)
+    for (int b = 0; b < E; ++b)
+      S[a * E + b] = Rm[a * E + b] + ((J[3 * a] * PJt[b] + J[3 * a + 1] * PJt[E + b]) + J[3 * a + 2] * PJt[2 * E + b]);
+  spd_inverse<E>(S);
+  double G[3 * E];  // Kalman gain
+  for (int i = 0; i < 3; ++i)
+    for (int b = 0; b < E; ++b) {
+      double acc = 0;
+      for (int a = 0; a < E; ++a) acc += PJt[i * E + a] * S[a * E + b];
+      G[i * E + b] = acc;
+    }
+  for (int i = 0; i < 3; ++i) {
+    double acc = 0;
+    for (int a = 0; a < E; ++a) acc += G[i * E + a] * (meas[a] - h[a]);
+    state[i] = s[i] + acc;
+  }
+  double IKJ[9];  // I - G J
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double acc = 0;
+      for (int a = 0; a < E; ++a) acc += G[i * E + a] * J[3 * a + j];
+      IKJ[3 * i + j] = (i == j ? 1.0 : 0.0) - acc;
+    }
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) cov[3 * i + j] = (IKJ[3 * i] * P[j] + IKJ[3 * i + 1] * P[3 + j]) + IKJ[3 * i + 2] * P[6 + j];
+}
+
+struct LandmarkEkfConfig {
+  int kind = EKF_STEREO;
+  float K[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  double baseline_pixels[2] = {0, 0};
+  double minimum_state_element_covariance = 0.01;           // landmark_estimator_ekf.h:33-37
+  double maximum_covariance_norm_squared = 1;               // :38-42
+  float maximum_distance_geometry_meters_squared = 1;       // landmark_estimator_base.hpp:22-26
+  float sensor_in_world[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};      // measurement_in_world
+  float sensor_in_local_map[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};  // measurement_in_scene
+};
+
+// LandmarkEstimatorEKF_::compute for ONE landmark (landmark_estimator_ekf_impl.cpp:17-82) with the transforms of
+// LandmarkEstimatorBase_::setTransforms (fp32, landmark_estimator_base.hpp:49-58).  state_world / covariance are the
+// landmark statistics (fp32); on success (return true = isInlier) they receive the filtered values that
+// addOptimizationResult stores (:74-75) and coords_in_local_map the landmark's new local coordinates (:79-80).
+template <int E>
+static inline bool landmark_ekf_update(const LandmarkEkfConfig& cfg, const float* world_in_sensor_R, const float* world_in_sensor_t,
+                                       const float* world_in_local_map_R, const float* world_in_local_map_t, float* state_world,
+                                       float* covariance, const float* measurement, float* coords_in_local_map) {
+  EkfCamera cam;
+  cam.fx = cfg.K[0];
+  cam.fy = cfg.K[4];
+  cam.cx = cfg.K[2];
+  cam.cy = cfg.K[5];
+  cam.bx = cfg.baseline_pixels[0];
+  cam.by = cfg.baseline_pixels[1];
+  double Rm[E * E], Q[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, R[9], t[3], state[3], cov[9], meas[E];
+  for (int i = 0; i < E * E; ++i) Rm[i] = 0;
+  for (int i = 0; i < E; ++i) Rm[i * E + i] = cfg.minimum_state_element_covariance;  // :26-28
+  for (int i = 0; i < 9; ++i) {
+    R[i] = world_in_sensor_R[i];
+    cov[i] = covariance[i];
+  }
+  for (int i = 0; i < 3; ++i) {
+    t[i] = world_in_sensor_t[i];
+    state[i] = state_world[i];
+    cov[4 * i] = cov[4 * i] > cfg.minimum_state_element_covariance ? cov[4 * i] : cfg.minimum_state_element_covariance;  // :47-49
+  }
+  for (int i = 0; i < E; ++i) meas[i] = measurement[i];
+  ekf_compute<E>(cam, R, t, Q, meas, Rm, state, cov);
+  double norm2 = 0;
+  for (int i = 0; i < 9; ++i) norm2 += cov[i] * cov[i];
+  if (state[2] <= 0 || norm2 > cfg.maximum_covariance_norm_squared) return false;  // :59-63
+  // coordinates_in_world = sensor_in_world * state.cast<float>()  (:67-68)
+  const float sf[3] = {(float) state[0], (float) state[1], (float) state[2]};
+  float w[3];
+  for (int i = 0; i < 3; ++i)
+    w[i] = ((cfg.sensor_in_world[4 * i] * sf[0] + cfg.sensor_in_world[4 * i + 1] * sf[1]) + cfg.sensor_in_world[4 * i + 2] * sf[2]) +
+           cfg.sensor_in_world[4 * i + 3];
+  const float d0 = w[0] - state_world[0], d1 = w[1] - state_world[1], d2 = w[2] - state_world[2];
+  if ((d0 * d0 + d1 * d1) + d2 * d2 > cfg.maximum_distance_geometry_meters_squared) return false;  // :69-73
+  for (int i = 0; i < 3; ++i) {
+    state_world[i] = w[i];
+    coords_in_local_map[i] = ((world_in_local_map_R[3 * i] * w[0] + world_in_local_map_R[3 * i + 1] * w[1]) + world_in_local_map_R[3 * i + 2] * w[2]) +
+                             world_in_local_map_t[i];
+  }
+  for (int i = 0; i < 9; ++i) covariance[i] = (float) cov[i];
+  return true;
+}
+
+}  // namespace pslam_oracle

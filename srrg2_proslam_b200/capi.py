@@ -65,6 +65,30 @@ def clip_cfg(K, rows, cols, camera_in_map, range_min=0.1, range_max=1000.0, sens
     return c
 
 
+class EkfCfg(C.Structure):
+    """pslam_ekf_cfg"""
+    _fields_ = [("kind", C.c_int), ("K", C.c_float * 9), ("baseline_pixels", C.c_double * 2),
+                ("minimum_state_element_covariance", C.c_double), ("maximum_covariance_norm_squared", C.c_double),
+                ("maximum_distance_geometry_meters_squared", C.c_float), ("sensor_in_world", C.c_float * 12),
+                ("sensor_in_local_map", C.c_float * 12)]
+
+
+EKF_KINDS = {"projective": 0, "projective_depth": 1, "stereo": 2}
+EKF_DIMS = {"projective": 2, "projective_depth": 3, "stereo": 4}
+
+
+def ekf_cfg(kind, K, baseline2, sensor_in_world, sensor_in_local_map, min_cov=0.01, max_cov_norm2=1.0, max_dist2=1.0):
+    c = EkfCfg()
+    c.kind = EKF_KINDS[kind]
+    c.K[:] = [float(x) for x in np.asarray(K, np.float32).reshape(9)]
+    c.baseline_pixels[:] = [float(baseline2[0]), float(baseline2[1])]
+    c.minimum_state_element_covariance, c.maximum_covariance_norm_squared = float(min_cov), float(max_cov_norm2)
+    c.maximum_distance_geometry_meters_squared = float(max_dist2)
+    c.sensor_in_world[:] = [float(x) for x in np.asarray(sensor_in_world, np.float32).reshape(12)]
+    c.sensor_in_local_map[:] = [float(x) for x in np.asarray(sensor_in_local_map, np.float32).reshape(12)]
+    return c
+
+
 class LinearizeCfg(C.Structure):
     _fields_ = [("kind", C.c_int), ("K", C.c_double * 9), ("image_cols", C.c_double),
                 ("image_rows", C.c_double), ("baseline", C.c_double * 3), ("mean_disparity", C.c_double),
@@ -319,6 +343,25 @@ class Context:
                                              C.c_void_p(d_out_index or None), C.c_void_p(d_out_desc or None),
                                              C.byref(n_out), int(reps), C.byref(ms)))
         return n_out.value, ms.value
+
+    # ---- N3: LandmarkEstimatorEKF over the landmarks of one merger pass -----------------------
+    def landmarks_ekf_update(self, kind, cfg, state_world, covariance, meas):
+        E = EKF_DIMS[kind]
+        st = np.ascontiguousarray(state_world, np.float32).reshape(-1, 3).copy()
+        n = len(st)
+        cv = np.ascontiguousarray(covariance, np.float32).reshape(n, 9).copy()
+        ms = np.ascontiguousarray(meas, np.float32).reshape(n, E)
+        loc, inl = np.zeros((n, 3), np.float32), np.zeros(n, np.uint8)
+        k = self._chk(lib().pslam_landmarks_ekf_update(self._h, n, _p(st), _p(cv), _p(ms), C.byref(cfg), _p(loc), _p(inl)))
+        assert k == int(inl.sum())
+        return st, cv.reshape(n, 3, 3), loc, inl.astype(bool)
+
+    def landmarks_ekf_update_dev(self, n, d_state, d_cov, d_meas, cfg, d_local, d_inlier, reps=1):
+        cnt, ms = C.c_int(0), C.c_double(0)
+        self._chk(lib().pslam_landmarks_ekf_update_dev(self._h, C.c_longlong(int(n)), C.c_void_p(d_state), C.c_void_p(d_cov),
+                                                       C.c_void_p(d_meas), C.byref(cfg), C.c_void_p(d_local), C.c_void_p(d_inlier),
+                                                       C.byref(cnt), int(reps), C.byref(ms)))
+        return cnt.value, ms.value
 
     def bf_best2(self, desc_f, desc_m):
         desc_f = np.ascontiguousarray(desc_f, np.uint8).reshape(-1, 32)

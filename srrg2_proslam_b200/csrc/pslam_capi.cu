@@ -800,6 +800,80 @@ int pslam_scene_clip(pslam_ctx* ctx, int n, const float* xyz, const uint8_t* des
   return (int) kept;
 }
 
+// ---- N3: per-landmark EKF update -----------------------------------------------------------------
+int pslam_landmarks_ekf_update_dev(pslam_ctx* ctx, long long n, float* d_state_world, float* d_covariance,
+                                   const float* d_measurements, const pslam_ekf_cfg* cfg, float* d_coords_in_local_map,
+                                   uint8_t* d_inlier, int* n_inliers, int reps, double* ms_per_call) {
+  if (!ctx || !cfg || n < 0 || reps < 1 || cfg->kind < 0 || cfg->kind > 2 ||
+      (n > 0 && (!d_state_world || !d_covariance || !d_measurements || !d_coords_in_local_map || !d_inlier)))
+    return PSLAM_E_INVALID;
+  PSLAM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  int* d_cnt = reinterpret_cast<int*>(ctx->d_scratch + PSLAM_SOLVER_SCRATCH_OFFSET);
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (ms_per_call) {
+    PSLAM_CUDA_TRY(ctx, cudaEventCreate(&e0));
+    PSLAM_CUDA_TRY(ctx, cudaEventCreate(&e1));
+    cudaEventRecord(e0, ctx->stream);
+  }
+  int rc = PSLAM_OK;
+  for (int r = 0; r < reps && rc == PSLAM_OK; ++r)
+    rc = pslam_k_landmarks_ekf(ctx, cfg, n, d_state_world, d_covariance, d_measurements, d_coords_in_local_map, d_inlier, d_cnt);
+  if (ms_per_call) {
+    if (rc == PSLAM_OK) {
+      cudaEventRecord(e1, ctx->stream);
+      cudaEventSynchronize(e1);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e0, e1);
+      *ms_per_call = (double) ms / reps;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+  }
+  if (rc) return rc;
+  int* h = reinterpret_cast<int*>(ctx->h_pinned);
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(h, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (n_inliers) *n_inliers = *h;
+  return PSLAM_OK;
+}
+
+int pslam_landmarks_ekf_update(pslam_ctx* ctx, int n, float* state_world, float* covariance, const float* measurements,
+                               const pslam_ekf_cfg* cfg, float* coords_in_local_map, uint8_t* inlier) {
+  if (!ctx || !cfg || n < 0 || cfg->kind < 0 || cfg->kind > 2 ||
+      (n > 0 && (!state_world || !covariance || !measurements || !coords_in_local_map || !inlier)))
+    return PSLAM_E_INVALID;
+  if (n == 0) return 0;
+  PSLAM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const int E = cfg->kind == 0 ? 2 : (cfg->kind == 1 ? 3 : 4);
+  auto al = [](size_t b) { return (b + 255) & ~(size_t) 255; };
+  const size_t b_st = al((size_t) n * 12), b_cov = al((size_t) n * 36), b_ms = al((size_t) n * 4 * E), b_in = al((size_t) n);
+  if (PSLAM_SOLVER_SCRATCH_OFFSET + 256 + 2 * b_st + b_cov + b_ms + b_in > ctx->scratch_bytes)
+    return pslam_set_error(ctx, PSLAM_E_CAPACITY, "landmarks_ekf: too many landmarks for the scratch buffer (use the _dev variant)", cudaSuccess);
+  uint8_t* p = ctx->d_scratch + PSLAM_SOLVER_SCRATCH_OFFSET + 256;  // [0, 256): the inlier counter of the _dev call
+  float* d_st = reinterpret_cast<float*>(p);
+  p += b_st;
+  float* d_cov = reinterpret_cast<float*>(p);
+  p += b_cov;
+  float* d_ms = reinterpret_cast<float*>(p);
+  p += b_ms;
+  float* d_loc = reinterpret_cast<float*>(p);
+  p += b_st;
+  uint8_t* d_in = p;
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_st, state_world, (size_t) n * 12, cudaMemcpyHostToDevice, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_cov, covariance, (size_t) n * 36, cudaMemcpyHostToDevice, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_ms, measurements, (size_t) n * 4 * E, cudaMemcpyHostToDevice, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaMemsetAsync(d_loc, 0, (size_t) n * 12, ctx->stream));
+  int n_inliers = 0;
+  const int rc = pslam_landmarks_ekf_update_dev(ctx, n, d_st, d_cov, d_ms, cfg, d_loc, d_in, &n_inliers, 1, nullptr);
+  if (rc) return rc;
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(state_world, d_st, (size_t) n * 12, cudaMemcpyDeviceToHost, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(covariance, d_cov, (size_t) n * 36, cudaMemcpyDeviceToHost, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(coords_in_local_map, d_loc, (size_t) n * 12, cudaMemcpyDeviceToHost, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(inlier, d_in, (size_t) n, cudaMemcpyDeviceToHost, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return n_inliers;
+}
+
 // ---- stage 2b -----------------------------------------------------------------------------------
 static int bf_upload(pslam_ctx* ctx, int nf, const uint8_t* df, int nm, const uint8_t* dm,
                      uint32_t** d_f, uint32_t** d_m, size_t* used) {

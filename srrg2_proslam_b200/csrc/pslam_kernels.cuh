@@ -70,3 +70,7 @@ int pslam_k_scene_clip(pslam_ctx* ctx, long long n, const float* d_xyz, const ui
                        unsigned long long* d_state, float* d_out_xyz, float* d_out_uvz, int* d_out_index,
                        uint32_t* d_out_desc, long long** d_n_out);
 size_t pslam_k_scene_clip_state_bytes(long long n);
+
+// k_mapping.cu (N3: per-landmark EKF update after the alignment)
+int pslam_k_landmarks_ekf(pslam_ctx* ctx, const pslam_ekf_cfg* cfg, long long n, float* d_state_world, float* d_covariance,
+                          const float* d_meas, float* d_local, uint8_t* d_inlier, int* d_n_inliers);

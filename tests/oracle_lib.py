@@ -263,6 +263,40 @@ def scene_clip(xyz, camera_in_map, K, rows, cols, rmin=0.1, rmax=1000.0, sensor_
     return oxyz[:m].copy(), ouvz[:m].copy(), oidx[:m].copy()
 
 
+EKF_KINDS = {"projective": 0, "projective_depth": 1, "stereo": 2}
+EKF_DIMS = {"projective": 2, "projective_depth": 3, "stereo": 4}
+
+
+def point_ekf(kind, cam6, world_in_sensor, Q, meas, Rm, state, cov):
+    """PointEKFBase::compute (predict + correct) of one point in double; returns the new (state, covariance)"""
+    E = EKF_DIMS[kind]
+    a = lambda x, n: np.ascontiguousarray(x, np.float64).reshape(n)
+    state, cov = a(state, 3).copy(), a(cov, 9).copy()
+    rc = lib().orc_point_ekf(EKF_KINDS[kind], _p(a(cam6, 6)), _p(a(world_in_sensor, 12)), _p(a(Q, 9)), _p(a(meas, E)),
+                             _p(a(Rm, E * E)), _p(state), _p(cov))
+    assert rc == 0
+    return state, cov.reshape(3, 3)
+
+
+def landmarks_ekf_update(kind, K, baseline2, sensor_in_world, sensor_in_local_map, state_world, covariance, meas,
+                         min_cov=0.01, max_cov_norm2=1.0, max_dist2=1.0):
+    """LandmarkEstimatorEKF_::compute over n landmarks (mapping/landmarks/landmark_estimator_ekf_impl.cpp:17-82);
+    returns (new state_world, new covariance, coords_in_local_map, inlier)"""
+    E = EKF_DIMS[kind]
+    st = np.ascontiguousarray(state_world, np.float32).reshape(-1, 3).copy()
+    n = len(st)
+    cv = np.ascontiguousarray(covariance, np.float32).reshape(n, 9).copy()
+    ms = np.ascontiguousarray(meas, np.float32).reshape(n, E)
+    loc = np.zeros((n, 3), np.float32)
+    inl = np.zeros(n, np.uint8)
+    f32 = lambda x, k: np.ascontiguousarray(x, np.float32).reshape(k)
+    b = np.ascontiguousarray(baseline2, np.float64).reshape(2)
+    lib().orc_landmarks_ekf_update(n, EKF_KINDS[kind], _p(f32(K, 9)), _p(b), C.c_double(min_cov), C.c_double(max_cov_norm2),
+                                   C.c_float(max_dist2), _p(f32(sensor_in_world, 12)), _p(f32(sensor_in_local_map, 12)),
+                                   _p(st), _p(cv), _p(ms), _p(loc), _p(inl))
+    return st, cv.reshape(n, 3, 3), loc, inl.astype(bool)
+
+
 SHAPES = {"square": 0, "circle": 1, "rhombus": 2}
 
 

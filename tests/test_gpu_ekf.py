@@ -1,0 +1,84 @@
+"""N3: LandmarkEstimatorEKF over the landmarks of a merger pass on the GPU -- pslam_landmarks_ekf_update
+against the CPU oracle (fp64 filter inside; the fp32 outputs agree to rounding, the inlier decisions exactly) and through
+the scenarios of the reference's filter tests (tests/test_stereo_projective_point_ekf.cpp)."""
+import numpy as np
+import pytest
+
+import ekf_fixtures as F
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+KF = F.K.astype(np.float32).reshape(9)
+
+
+@pytest.fixture(scope="module")
+def ctx(oracle):
+    from srrg2_proslam_b200 import capi
+    c = capi.Context(device=0, max_images=2, max_rows=376, max_cols=1241, max_features=2048, max_raw_per_bin=8192)
+    yield c
+    c.close()
+
+
+def scene(n, seed, kind):
+    rng = np.random.default_rng(seed)
+    truth = np.stack([rng.uniform(-4, 4, n), rng.uniform(-2, 2, n), rng.uniform(4, 40, n)], 1)
+    cam = np.concatenate([F.rot(1, 0.03) @ F.rot(0, -0.02), np.array([[0.2], [-0.05], [0.4]])], 1)  # sensor_in_world
+    M = np.concatenate([F.rot(2, 0.4), np.array([[1.0], [-2.0], [0.5]])], 1)
+    sil = np.concatenate([M[:, :3] @ cam[:, :3], (M[:, :3] @ cam[:, 3] + M[:, 3]).reshape(3, 1)], 1)
+    pc = (truth - cam[:, 3]) @ cam[:, :3]
+    uv = np.stack([F.project(p) for p in pc])
+    uvr = np.stack([F.project(p, F.BASELINE) for p in pc])
+    meas = {"projective": uv, "projective_depth": np.concatenate([uv, pc[:, 2:3]], 1), "stereo": np.concatenate([uv, uvr], 1)}[kind]
+    meas = meas + rng.normal(0, 0.5, meas.shape)
+    state = (truth + rng.normal(0, 0.2, (n, 3))).astype(np.float32)
+    A = rng.normal(0, 0.2, (n, 3, 3))
+    cov = (np.eye(3) * rng.uniform(0.001, 0.5, (n, 1, 1)) + A @ A.transpose(0, 2, 1) * 0.1).astype(np.float32)
+    return state, cov.reshape(n, 9), meas.astype(np.float32), cam, sil
+
+
+@pytest.mark.parametrize("kind", ["projective", "projective_depth", "stereo"])
+@pytest.mark.parametrize("n", [1, 33, 1000, 40000])
+def test_against_oracle(ctx, kind, n):
+    from srrg2_proslam_b200 import capi
+    state, cov, meas, cam, sil = scene(n, n + len(kind), kind)
+    kw = dict(min_cov=0.01, max_cov_norm2=2.0, max_dist2=0.5)
+    g = ctx.landmarks_ekf_update(kind, capi.ekf_cfg(kind, KF, F.BASELINE[:2], cam, sil, **kw), state, cov, meas)
+    o = O.landmarks_ekf_update(kind, KF, F.BASELINE[:2], cam, sil, state, cov, meas, **kw)
+    assert np.array_equal(g[3], o[3])                      # isInlier
+    if n >= 1000:
+        assert 0 < g[3].sum() < n                          # both outcomes are exercised
+    for a, b in zip(g[:3], o[:3]):
+        assert np.allclose(a, b, rtol=2e-6, atol=1e-6)     # fp64 inside, fp32 out: equal up to the last rounding
+    rej = ~g[3]
+    assert np.array_equal(g[0][rej], state[rej]) and np.array_equal(g[1].reshape(n, 9)[rej], cov[rej])  # rejected: untouched
+
+
+def test_chain_converges_like_the_reference_scenario(ctx):
+    """many landmarks, a moving stereo camera, 12 frames: the same loop as tests/test_oracle_ekf.py on the GPU"""
+    from srrg2_proslam_b200 import capi
+    rng = np.random.default_rng(3)
+    n = 4096
+    truth = np.stack([rng.uniform(-3, 3, n), rng.uniform(-2, 2, n), rng.uniform(6, 20, n)], 1)
+    state = (truth + rng.normal(0, 0.15, (n, 3))).astype(np.float32)
+    cov = np.tile(np.eye(3, dtype=np.float32).reshape(9), (n, 1))
+    err0 = np.linalg.norm(state - truth, axis=1).mean()
+    for step in range(12):
+        cam = np.concatenate([F.rot(1, 0.01 * step), np.array([[0.05 * step], [0.0], [0.1 * step]])], 1)
+        pc = (truth - cam[:, 3]) @ cam[:, :3]
+        meas = np.stack([np.concatenate([F.project(p), F.project(p, F.BASELINE)]) for p in pc]) + rng.normal(0, 0.3, (n, 4))
+        cfg = capi.ekf_cfg("stereo", KF, F.BASELINE[:2], cam, cam, max_cov_norm2=4.0, max_dist2=1.0)
+        state, cov3, local, inl = ctx.landmarks_ekf_update("stereo", cfg, state, cov, meas)
+        cov = cov3.reshape(n, 9)
+        assert inl.mean() > 0.9
+    assert np.linalg.norm(state - truth, axis=1).mean() < 0.6 * err0
+
+
+def test_empty_and_invalid(ctx):
+    from srrg2_proslam_b200 import capi
+    cfg = capi.ekf_cfg("stereo", KF, F.BASELINE[:2], np.eye(3, 4), np.eye(3, 4))
+    g = ctx.landmarks_ekf_update("stereo", cfg, np.zeros((0, 3)), np.zeros((0, 9)), np.zeros((0, 4)))
+    assert len(g[3]) == 0
+    cfg.kind = 7
+    with pytest.raises(capi.PslamError) as e:
+        ctx.landmarks_ekf_update("stereo", cfg, np.zeros((4, 3)), np.zeros((4, 9)), np.zeros((4, 4)))
+    assert e.value.code == capi.PSLAM_E_INVALID

@@ -1,0 +1,80 @@
+"""Pins the oracle's point EKFs (all in-tree reference code: mapping/landmarks/filters/*.cpp,
+point_ekf_base.hpp) through the scenarios and assertions of the reference's tests/test_projective_point_ekf.cpp,
+tests/test_projective_depth_point_ekf.cpp and tests/test_stereo_projective_point_ekf.cpp."""
+import numpy as np
+import pytest
+
+import ekf_fixtures as F
+import oracle_lib as O
+
+MEAS = {"projective": 2, "projective_depth": 3, "stereo": 4}
+
+
+def run_filter(kind, gt, T, meas, Q, Rm_scale, runs=1):
+    E = MEAS[kind]
+    worst = 0.0
+    for _ in range(runs):
+        state, cov = gt[0].copy(), np.eye(3)
+        for j in range(len(T)):
+            state, cov = O.point_ekf(kind, F.CAM6, T[j], Q, meas[j + 1], np.eye(E) * Rm_scale, state, cov)
+            assert np.all(np.isfinite(state)) and np.all(np.isfinite(cov))
+            worst = max(worst, float(np.linalg.norm(state - gt[j + 1])))
+    return worst, cov
+
+
+@pytest.mark.parametrize("motion", ["translation", "rotation", "transform"])
+@pytest.mark.parametrize("kind", ["projective", "projective_depth", "stereo"])
+def test_zero_noise_tracks_exactly(oracle, kind, motion):
+    """..._ZeroNoise tests (test_stereo_projective_point_ekf.cpp:15-109, test_projective_point_ekf.cpp:14-46,160-192,306-338):
+    perfect initial guess, perfect transitions and measurements -> the state follows the ground truth (identity
+    measurement covariance, no transition noise)"""
+    gt, T, mono, depth, stereo = F.transitions(motion, 100)
+    meas = {"projective": mono, "projective_depth": depth, "stereo": stereo}[kind]
+    worst, cov = run_filter(kind, gt, T, meas, np.zeros((3, 3)), 1.0)
+    assert worst < 1e-9
+    assert np.allclose(cov, cov.T, atol=1e-12) and np.all(np.linalg.eigvalsh(0.5 * (cov + cov.T)) > -1e-12)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_full_noise_stays_bounded(oracle, seed):
+    """StereoProjectivePointEKF_Transforms_FullNoise (test_stereo_projective_point_ekf.cpp:111-188): motion noise 0.01,
+    measurement noise 1 px, Q = 0.1 I, R = 10 I; every filter stays within 1 m of the ground truth for 100 transitions.
+    The reference asserts this for its one srand(0) sample; our generator draws other samples, so the 1 m bound is kept
+    for seed 0 and the binocular filter, and 2 m for the weaker monocular filters on the other seeds."""
+    gt, T, mono, depth, stereo = F.transitions("transform", 100, sd_motion=0.01, sd_meas=1.0, seed=seed)
+    for kind, meas in (("projective", mono), ("projective_depth", depth), ("stereo", stereo)):
+        worst, _ = run_filter(kind, gt, T, meas, np.eye(3) * 0.1, 10.0)
+        assert worst < (1.0 if seed == 0 or kind == "stereo" else 2.0), (kind, worst)
+
+
+def test_landmark_estimator_ekf(oracle):
+    """LandmarkEstimatorEKF_::compute (landmark_estimator_ekf_impl.cpp:17-82): a static world point observed from a moving
+    stereo camera converges towards the truth; a measurement that would move the landmark by more than
+    maximum_distance_geometry_meters_squared or leaves a large covariance is rejected (isInlier stays false)"""
+    rng = np.random.default_rng(3)
+    Kf = F.K.astype(np.float32).reshape(9)
+    n = 64
+    truth = np.stack([rng.uniform(-3, 3, n), rng.uniform(-2, 2, n), rng.uniform(6, 20, n)], 1)
+    state = (truth + rng.normal(0, 0.15, (n, 3))).astype(np.float32)
+    cov = np.tile(np.eye(3, dtype=np.float32).reshape(9), (n, 1))
+    err0 = np.linalg.norm(state - truth, axis=1).mean()
+    for step in range(12):
+        cam = np.concatenate([F.rot(1, 0.01 * step), np.array([[0.05 * step], [0.0], [0.1 * step]])], 1)  # sensor_in_world
+        Rw, tw = cam[:, :3], cam[:, 3]
+        pc = (truth - tw) @ Rw  # world -> sensor
+        meas = np.stack([np.concatenate([F.project(p), F.project(p, F.BASELINE)]) for p in pc]) + rng.normal(0, 0.3, (n, 4))
+        # the local map's frame: world moved by M (sensor_in_local_map = M * sensor_in_world => world_in_local_map = M)
+        M = np.concatenate([F.rot(2, 0.4), np.array([[1.0], [-2.0], [0.5]])], 1)
+        sensor_in_local_map = np.concatenate([M[:, :3] @ Rw, (M[:, :3] @ tw + M[:, 3]).reshape(3, 1)], 1)
+        state, cov3, local, inl = O.landmarks_ekf_update("stereo", Kf, F.BASELINE[:2], cam, sensor_in_local_map, state, cov, meas,
+                                                        max_cov_norm2=4.0, max_dist2=1.0)
+        cov = cov3.reshape(n, 9)
+        assert inl.sum() >= n - 4
+        assert np.allclose(local[inl], state[inl] @ M[:, :3].T + M[:, 3], atol=1e-4)
+    assert np.linalg.norm(state - truth, axis=1).mean() < 0.6 * err0
+    # gross outlier: rejected, statistics untouched
+    bad = meas.copy()
+    bad[:, 0] += 150.0
+    bad[:, 2] += 120.0
+    s2, c2, _, inl2 = O.landmarks_ekf_update("stereo", Kf, F.BASELINE[:2], cam, cam, state, cov, bad, max_cov_norm2=4.0, max_dist2=0.01)
+    assert not inl2.any() and np.array_equal(s2, state) and np.array_equal(c2.reshape(n, 9), cov)
