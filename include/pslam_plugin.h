@@ -117,6 +117,14 @@ int psp_clipper_set_sensor_in_robot(psp_module* clipper, const float* pose12);
 int psp_clipper_compute(psp_module* clipper, int capacity, float* xyz, float* uvz, int* global_index, uint8_t* desc,
                         int* status);
 
+/* ---- point EKFs + LandmarkEstimatorEKF (mapping/landmarks/filters/ headers, landmark_estimator_ekf.h:12-63):
+ * filter->setCameraMatrix / setBaseline, estimator->setTransforms, then the batched form of setMeasurement /
+ * setLandmark / compute over the correspondences of one merger pass (see pslam_landmarks_ekf_update). */
+int psp_point_filter_set_camera(psp_module* filter, const float* K9, double baseline_x_pixels, double baseline_y_pixels);
+int psp_landmark_estimator_set_transforms(psp_module* estimator, const float* measurement_in_world12, const float* measurement_in_scene12);
+int psp_landmark_estimator_compute_batch(psp_module* estimator, int n, float* state_world, float* covariance,
+                                         const float* measurements, float* coords_in_local_map, uint8_t* inlier);
+
 #ifdef __cplusplus
 }
 #endif

@@ -698,6 +698,30 @@ void SceneClipperProjective3DCUDA::compute() {
   _status = Successful;
 }
 
+// ---- landmark estimator (mapping/landmarks/landmark_estimator_ekf_impl.cpp) --------------------------------------
+int LandmarkEstimatorEKFCUDA::computeBatch(int n, float* state_world, float* covariance, const float* measurements,
+                                           float* coords_in_local_map, uint8_t* inlier) {
+  if (!param_filter.value()) throw std::runtime_error("LandmarkEstimatorEKF::compute|ERROR: filter not set");
+  const PointEKFCUDA& filter = *param_filter.value();
+  if (filter.kind() != _kind) throw std::runtime_error("LandmarkEstimatorEKF::compute|ERROR: filter type does not match the measurement dimension");
+  pslam_ekf_cfg cfg;
+  cfg.kind = _kind;
+  for (int i = 0; i < 9; ++i) cfg.K[i] = filter.cameraMatrix()[i];
+  cfg.baseline_pixels[0] = filter.baseline()[0];
+  cfg.baseline_pixels[1] = filter.baseline()[1];
+  cfg.minimum_state_element_covariance = param_minimum_state_element_covariance.value();
+  cfg.maximum_covariance_norm_squared = param_maximum_covariance_norm_squared.value();
+  cfg.maximum_distance_geometry_meters_squared = param_maximum_distance_geometry_meters_squared.value();
+  for (int i = 0; i < 12; ++i) {
+    cfg.sensor_in_world[i] = _sensor_in_world.m[i];
+    cfg.sensor_in_local_map[i] = _sensor_in_local_map.m[i];
+  }
+  pslam_ctx* ctx = PslamDevice::context();
+  const int k = pslam_landmarks_ekf_update(ctx, n, state_world, covariance, measurements, &cfg, coords_in_local_map, inlier);
+  PslamDevice::check(k, "LandmarkEstimatorEKF::compute");
+  return k;
+}
+
 // ---- aligner slice ----------------------------------------------------------------------------------------------
 AlignerSliceProcessorProjectiveCUDA::AlignerSliceProcessorProjectiveCUDA(int kind) : _kind(kind) {
   // aligner_slice_processor_projective.cpp:7-20: saturated robustifier with chi threshold 100^2 by default
@@ -876,6 +900,14 @@ template <int Kind>
 struct SliceK : AlignerSliceProcessorProjectiveCUDA {
   SliceK() : AlignerSliceProcessorProjectiveCUDA(Kind) {}
 };
+template <int Kind>
+struct FilterK : PointEKFCUDA {
+  FilterK() : PointEKFCUDA(Kind) {}
+};
+template <int Kind>
+struct EstimatorK : LandmarkEstimatorEKFCUDA {
+  EstimatorK() : LandmarkEstimatorEKFCUDA(Kind) {}
+};
 template <typename T>
 void reg(const std::string& reference_name) {
   PSLAM_REGISTER_CLASS_AS(T, reference_name);           // the unchanged .conf selects the CUDA-backed class
@@ -910,6 +942,12 @@ void registerTypes() {
   reg<SliceK<0>>("AlignerSliceProcessorProjectiveStereoWithSensor");  // kitti_in_baselink.conf
   reg<MultiAligner3DQRCUDA>("MultiAligner3DQR");
   reg<SceneClipperProjective3DCUDA>("SceneClipperProjective3D");  // mapping/instances.cpp
+  reg<FilterK<0>>("ProjectivePointEKF3D");
+  reg<FilterK<1>>("ProjectiveDepthPointEKF3D");
+  reg<FilterK<2>>("StereoProjectivePointEKF3D");
+  reg<EstimatorK<0>>("LandmarkEstimatorProjectiveEKF3D");
+  reg<EstimatorK<1>>("LandmarkEstimatorProjectiveDepthEKF3D");
+  reg<EstimatorK<2>>("LandmarkEstimatorStereoProjectiveEKF3D");
   // srrg2_core / srrg2_solver modules the hot-path classes link to
   PSLAM_REGISTER_CLASS_AS(ProjectorPinhole, "PointIntensityDescriptor3fProjectorPinhole");
   PSLAM_REGISTER_CLASS_AS(RobustifierSaturated, "RobustifierSaturated");

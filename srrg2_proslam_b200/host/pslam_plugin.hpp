@@ -454,6 +454,52 @@ private:
   Status _status = Error;
 };
 
+// ---- point EKFs + LandmarkEstimatorEKF_ (mapping/landmarks/filters/*.h, landmark_estimator_ekf.{h,cpp}) --
+// The filter object only carries the camera model (setCameraMatrix / setBaseline); the arithmetic of
+// PointEKFBase::compute runs in landmarks_ekf_kernel.
+class PointEKFCUDA : public Configurable {
+public:
+  explicit PointEKFCUDA(int kind) : _kind(kind) {}
+  int kind() const { return _kind; }  // 0 ProjectivePointEKF, 1 ProjectiveDepthPointEKF, 2 StereoProjectivePointEKF
+  void setCameraMatrix(const std::array<float, 9>& K) { _K = K; }
+  void setBaseline(double b_x, double b_y) {  // StereoProjectivePointEKF::setBaseline, pixels
+    _b[0] = b_x;
+    _b[1] = b_y;
+  }
+  const std::array<float, 9>& cameraMatrix() const { return _K; }
+  const double* baseline() const { return _b; }
+
+private:
+  int _kind;
+  std::array<float, 9> _K{{1, 0, 0, 0, 1, 0, 0, 0, 1}};
+  double _b[2] = {0, 0};
+};
+
+class LandmarkEstimatorEKFCUDA : public Configurable {
+public:
+  explicit LandmarkEstimatorEKFCUDA(int kind) : _kind(kind) {}
+  PARAM(PropertyConfigurable_<PointEKFCUDA>, filter, "filter instance used to refine the landmark position estimate", nullptr, nullptr);
+  PARAM(PropertyDouble, minimum_state_element_covariance, "minimum per element covariance value (prohibits ill-shaped uncertainties)", 0.01, nullptr);
+  PARAM(PropertyDouble, maximum_covariance_norm_squared, "maximum permitted covariance matrix Frobenius norm value for merging", 1, nullptr);
+  PARAM(PropertyFloat, maximum_distance_geometry_meters_squared,
+        "maximum distance in geometry (i.e. 3D point distance L2 norm) in meters squared", 1, nullptr);
+  // LandmarkEstimatorBase_::setTransforms (landmark_estimator_base.hpp:49-58)
+  void setTransforms(const Isometry3f& measurement_in_world, const Isometry3f& measurement_in_scene) {
+    _sensor_in_world = measurement_in_world;
+    _sensor_in_local_map = measurement_in_scene;
+  }
+  // setMeasurement / setLandmark / compute (landmark_estimator_ekf_impl.cpp:17-82) for ALL correspondences of one merger
+  // pass: state_world [n][3] / covariance [n][9] = landmark statistics (updated in place where isInlier), measurements
+  // [n][MeasurementDim], coords_in_local_map [n][3], inlier [n].  Returns the number of inliers.
+  int computeBatch(int n, float* state_world, float* covariance, const float* measurements, float* coords_in_local_map,
+                   uint8_t* inlier);
+  int measurementDim() const { return _kind == 0 ? 2 : (_kind == 1 ? 3 : 4); }
+
+private:
+  int _kind;
+  Isometry3f _sensor_in_world, _sensor_in_local_map;
+};
+
 // registers every class above under the reference's names and under the ...CUDA names (idempotent)
 void registerTypes();
 

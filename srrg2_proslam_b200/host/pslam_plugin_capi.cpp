@@ -567,4 +567,34 @@ int psp_clipper_compute(psp_module* clipper, int capacity, float* xyz, float* uv
   });
 }
 
+// ---- point EKFs + LandmarkEstimatorEKF --------------------------------------------------------------------------
+int psp_point_filter_set_camera(psp_module* filter, const float* K9, double baseline_x_pixels, double baseline_y_pixels) {
+  return guard([&] {
+    auto* f = as<PointEKFCUDA>(filter, "PointEKF");
+    std::array<float, 9> K;
+    std::memcpy(K.data(), K9, sizeof(float) * 9);
+    f->setCameraMatrix(K);
+    f->setBaseline(baseline_x_pixels, baseline_y_pixels);
+    return 0;
+  });
+}
+
+int psp_landmark_estimator_set_transforms(psp_module* estimator, const float* measurement_in_world12, const float* measurement_in_scene12) {
+  return guard([&] {
+    Isometry3f W, S;
+    std::memcpy(W.m, measurement_in_world12, sizeof(W.m));
+    std::memcpy(S.m, measurement_in_scene12, sizeof(S.m));
+    as<LandmarkEstimatorEKFCUDA>(estimator, "LandmarkEstimatorEKF")->setTransforms(W, S);
+    return 0;
+  });
+}
+
+int psp_landmark_estimator_compute_batch(psp_module* estimator, int n, float* state_world, float* covariance,
+                                         const float* measurements, float* coords_in_local_map, uint8_t* inlier) {
+  return guard([&] {
+    return as<LandmarkEstimatorEKFCUDA>(estimator, "LandmarkEstimatorEKF")
+      ->computeBatch(n, state_world, covariance, measurements, coords_in_local_map, inlier);
+  });
+}
+
 }  // extern "C"

@@ -215,6 +215,25 @@ class Module:
         return {"xyz": xyz[:n].copy(), "uvz": uvz[:n].copy(), "index": idx[:n].copy(), "desc": desc[:n].copy(),
                 "status": status.value}
 
+    # ---- point EKFs + LandmarkEstimatorEKF ---------------------------------------------------------------------------
+    def filter_set_camera(self, K, baseline=(0.0, 0.0)):
+        K = np.ascontiguousarray(K, np.float32).reshape(9)
+        _chk(lib().psp_point_filter_set_camera(self.h, _p(K), C.c_double(baseline[0]), C.c_double(baseline[1])))
+
+    def estimator_set_transforms(self, measurement_in_world, measurement_in_scene):
+        a = np.ascontiguousarray(measurement_in_world, np.float32).reshape(12)
+        b = np.ascontiguousarray(measurement_in_scene, np.float32).reshape(12)
+        _chk(lib().psp_landmark_estimator_set_transforms(self.h, _p(a), _p(b)))
+
+    def estimator_compute_batch(self, state_world, covariance, meas):
+        st = np.ascontiguousarray(state_world, np.float32).reshape(-1, 3).copy()
+        n = len(st)
+        cv = np.ascontiguousarray(covariance, np.float32).reshape(n, 9).copy()
+        ms = np.ascontiguousarray(meas, np.float32).reshape(n, -1)
+        loc, inl = np.zeros((n, 3), np.float32), np.zeros(n, np.uint8)
+        k = _chk(lib().psp_landmark_estimator_compute_batch(self.h, n, _p(st), _p(cv), _p(ms), _p(loc), _p(inl)))
+        return st, cv.reshape(n, 3, 3), loc, inl.astype(bool), k
+
     def aligner_set_moving_in_fixed(self, pose12):
         pose12 = np.ascontiguousarray(pose12, np.float32).reshape(12)
         _chk(lib().psp_aligner_set_moving_in_fixed(self.h, _p(pose12)))

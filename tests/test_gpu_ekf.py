@@ -82,3 +82,27 @@ def test_empty_and_invalid(ctx):
     with pytest.raises(capi.PslamError) as e:
         ctx.landmarks_ekf_update("stereo", cfg, np.zeros((4, 3)), np.zeros((4, 9)), np.zeros((4, 4)))
     assert e.value.code == capi.PSLAM_E_INVALID
+
+
+def test_conf_landmark_estimator_module(oracle):
+    """kitti.conf "landmark_estimator_ekf" (LandmarkEstimatorStereoProjectiveEKF3D -> StereoProjectivePointEKF3D
+    "point_filter") instantiated by class name with the file's thresholds (0.25 / 25 / 0.01), batched compute"""
+    import pathlib
+    from srrg2_proslam_b200 import plugin as P
+    m = P.Manager(pathlib.Path(__file__).resolve().parent / "golden" / "configurations" / "kitti_hotpath.conf")
+    est = m.get("landmark_estimator_ekf")
+    assert est.class_name == "LandmarkEstimatorStereoProjectiveEKF3D" and not est.is_generic
+    flt = est.link("filter")
+    assert flt.class_name == "StereoProjectivePointEKF3D" and flt.name == "point_filter"
+    flt.filter_set_camera(KF, (F.BASELINE[0], F.BASELINE[1]))
+    state, cov, meas, cam, sil = scene(5000, 17, "stereo")
+    est.estimator_set_transforms(cam, sil)
+    g = est.estimator_compute_batch(state, cov, meas)
+    o = O.landmarks_ekf_update("stereo", KF, F.BASELINE[:2], cam, sil, state, cov, meas,
+                               min_cov=est.get("minimum_state_element_covariance"),
+                               max_cov_norm2=est.get("maximum_covariance_norm_squared"),
+                               max_dist2=est.get("maximum_distance_geometry_meters_squared"))
+    assert est.get("maximum_covariance_norm_squared") == 0.25 and est.get("maximum_distance_geometry_meters_squared") == 25
+    assert np.array_equal(g[3], o[3]) and g[4] == int(o[3].sum()) and 0 < g[4] < 5000
+    for a, b in zip(g[:3], o[:3]):
+        assert np.allclose(a, b, rtol=2e-6, atol=1e-6)

@@ -36,7 +36,9 @@ HOT_CLASSES = ["IntensityFeatureExtractorBinned2D", "IntensityFeatureExtractorBi
                "RawDataPreprocessorMonocularDepth", "CorrespondenceFinderDescriptorBasedEpipolar2D2D",
                "CorrespondenceFinderDescriptorBasedEpipolar3D3D", "AlignerSliceProcessorProjective",
                "AlignerSliceProcessorProjectiveDepth", "AlignerSliceProcessorProjectiveStereo", "MultiAligner3DQR",
-               "SceneClipperProjective3D"]
+               "SceneClipperProjective3D", "LandmarkEstimatorProjectiveEKF3D", "LandmarkEstimatorProjectiveDepthEKF3D",
+               "LandmarkEstimatorStereoProjectiveEKF3D", "ProjectivePointEKF3D", "ProjectiveDepthPointEKF3D",
+               "StereoProjectivePointEKF3D"]
 HOT_CLASSES += [f"CorrespondenceFinderDescriptorBasedBruteforce{d}" for d in ("2D2D", "2D3D", "3D3D", "4D3D")]
 HOT_CLASSES += [f"CorrespondenceFinderProjective{s}{d}" for s in ("Square", "Circle", "Rhombus") for d in ("2D3D", "3D3D", "4D3D")]
 
@@ -158,7 +160,7 @@ def test_hotpath_fixtures(P):
 def test_hotpath_fixtures_are_current(P, tmp_path):
     """the committed fixtures are what tools/make_golden.py derives from the unchanged files"""
     m = P.Manager(REF_CONF / "kitti.conf")
-    m.write(tmp_path / "k.conf", ["adaptor_stereo_projective", "aligner", "cf_bruteforce", "clipper_stereo_projective"])
+    m.write(tmp_path / "k.conf", ["adaptor_stereo_projective", "aligner", "cf_bruteforce", "clipper_stereo_projective", "landmark_estimator_ekf"])
     assert (tmp_path / "k.conf").read_text() == (GOLDEN / "kitti_hotpath.conf").read_text()
 
 
