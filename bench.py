@@ -181,6 +181,13 @@ def tracking_lines(ctx, capi, stream, dev):
     return out
 
 
+def scene_traffic():
+    tr = ROOT / "profiles" / "traffic.json"
+    if tr.exists():
+        return json.loads(tr.read_text()).get("scene_flags_kernel", {}).get("dram_bytes_per_launch")
+    return None
+
+
 def scene_clip_line(ctx, capi, dev, hbm_peak):
     """N2: SceneClipperProjective3D over a device-resident synthetic local map (16 M points with
     descriptors, about a third visible): one launch projects, clips and compacts in map order.  HBM bound."""
@@ -212,7 +219,7 @@ def scene_clip_line(ctx, capi, dev, hbm_peak):
             "map_points": n, "survivors": int(kept), "alg_gbs_whole_pass": alg_all / (ms * 1e-3) / 1e9,
             "kernels_us": prof,
             "roofline": {"kernel": "scene_flags_kernel", "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": gbs / hbm_peak, "alg_bytes_per_launch": alg_flags,
+                         "frac": gbs / hbm_peak, "alg_bytes_per_launch": alg_flags, "traffic": scene_traffic(),
                          "note": "time = event-to-event interval with profiling on (includes ~5 us of event overhead)"}}
 
 
