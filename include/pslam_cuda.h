@@ -251,6 +251,15 @@ int pslam_landmarks_ekf_update_dev(pslam_ctx* ctx, long long n, float* d_state_w
                                    const float* d_measurements, const pslam_ekf_cfg* cfg, float* d_coords_in_local_map,
                                    uint8_t* d_inlier, int* n_inliers, int reps, double* ms_per_call);
 
+/* LandmarkEstimatorWeightedMean_::compute (.../mapping/landmarks/landmark_estimator_weighted_mean_impl.cpp:7-41) over the
+ * n landmarks of one merger pass: running mean of the landmark's world position with the point re-observed in the sensor
+ * frame (landmark_in_sensor [n][3], setLandmarkInSensor), weight = numberOfOptimizations + 1, geometric-distance gate.
+ * fp32, bit exact.  state_world is updated in place for the inliers; returns their number. */
+int pslam_landmarks_weighted_mean_update(pslam_ctx* ctx, int n, float* state_world, const int* number_of_optimizations,
+                                         const float* landmark_in_sensor, const float* sensor_in_world12,
+                                         const float* sensor_in_local_map12, float maximum_distance_geometry_meters_squared,
+                                         float* coords_in_local_map, uint8_t* inlier);
+
 /* ---- stage 2b: exhaustive Hamming matching --------------------------------------
  * Replaces CorrespondenceFinderDescriptorBasedBruteforce::compute
  *   (.../correspondence_finders/correspondence_finder_descriptor_based_bruteforce_impl.cpp:6-294).

@@ -125,6 +125,10 @@ int psp_landmark_estimator_set_transforms(psp_module* estimator, const float* me
 int psp_landmark_estimator_compute_batch(psp_module* estimator, int n, float* state_world, float* covariance,
                                          const float* measurements, float* coords_in_local_map, uint8_t* inlier);
 
+/* LandmarkEstimatorWeightedMean{2D3D,3D3D,4D3D}: psp_landmark_estimator_set_transforms, then the batched compute */
+int psp_landmark_estimator_weighted_mean_batch(psp_module* estimator, int n, float* state_world, const int* number_of_optimizations,
+                                               const float* landmark_in_sensor, float* coords_in_local_map, uint8_t* inlier);
+
 #ifdef __cplusplus
 }
 #endif

@@ -490,6 +490,23 @@ int orc_landmarks_ekf_update(int n, int kind, const float* K9, const double* bas
   return n_inliers;
 }
 
+// LandmarkEstimatorWeightedMean_::compute over n landmarks of one merger pass (fp32).
+int orc_landmarks_weighted_mean_update(int n, float max_dist2, const float* sensor_in_world12, const float* sensor_in_local_map12,
+                                       float* state_world, const int* number_of_optimizations, const float* landmark_in_sensor,
+                                       float* coords_in_local_map, unsigned char* inlier) {
+  const Pose<float> sensor_in_world = pose_from(sensor_in_world12), sensor_in_local_map = pose_from(sensor_in_local_map12);
+  const Pose<float> world_in_local_map = sensor_in_local_map * sensor_in_world.inverse();
+  int k = 0;
+  for (int i = 0; i < n; ++i) {
+    const bool ok = landmark_weighted_mean_update(sensor_in_world.R, sensor_in_world.t, world_in_local_map.R, world_in_local_map.t, max_dist2,
+                                                  number_of_optimizations[i], landmark_in_sensor + 3 * i, state_world + 3 * i,
+                                                  coords_in_local_map + 3 * i);
+    inlier[i] = ok ? 1 : 0;
+    k += ok;
+  }
+  return k;
+}
+
 // ---- stateful projective finder ----------------------------------------------
 struct OrcFinder {
   ProjectiveFinder f;

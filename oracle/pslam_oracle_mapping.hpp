@@ -7,6 +7,7 @@
 //   StereoProjectivePointEKF                    .../filters/stereo_projective_point_ekf_impl.cpp:13-48
 //   LandmarkEstimatorEKF_::setTransforms/compute .../mapping/landmarks/landmark_estimator_ekf_impl.cpp:6-82
 //   LandmarkEstimatorBase_::setTransforms        .../mapping/landmarks/landmark_estimator_base.hpp:49-58
+//   LandmarkEstimatorWeightedMean_::compute      .../mapping/landmarks/landmark_estimator_weighted_mean_impl.cpp:7-41
 // All of this code is IN the reference tree (no external arithmetic except Eigen's fixed-size inverse(), restated as a
 // Gauss-Jordan elimination of the symmetric positive definite innovation covariance) and is pinned through the
 // scenarios of tests/test_{projective,projective_depth,stereo_projective}_point_ekf.cpp (tests/test_oracle_ekf.py).
@@ -183,6 +184,25 @@ static inline bool landmark_ekf_update(const LandmarkEkfConfig& cfg, const float
                              world_in_local_map_t[i];
   }
   for (int i = 0; i < 9; ++i) covariance[i] = (float) cov[i];
+  return true;
+}
+
+// LandmarkEstimatorWeightedMean_::compute for ONE landmark, fp32
+// (.../mapping/landmarks/landmark_estimator_weighted_mean_impl.cpp:7-41).  sensor_in_world / world_in_local_map: R row
+// major 3x3 + t.  Returns isInlier; on success state_world (what addOptimizationResult stores, :35) and the local
+// coordinates (:39) are written.
+static inline bool landmark_weighted_mean_update(const float* sw_R, const float* sw_t, const float* wl_R, const float* wl_t,
+                                                 float max_dist2, int number_of_optimizations, const float* landmark_in_sensor,
+                                                 float* state_world, float* coords_in_local_map) {
+  float upd[3], w[3];
+  for (int i = 0; i < 3; ++i)
+    upd[i] = ((sw_R[3 * i] * landmark_in_sensor[0] + sw_R[3 * i + 1] * landmark_in_sensor[1]) + sw_R[3 * i + 2] * landmark_in_sensor[2]) + sw_t[i];  // :20-21
+  const float n1 = (float) (number_of_optimizations + 1);  // :23
+  for (int i = 0; i < 3; ++i) w[i] = (n1 * state_world[i] + upd[i]) / (n1 + 1);  // :25-27
+  const float d0 = w[0] - state_world[0], d1 = w[1] - state_world[1], d2 = w[2] - state_world[2];
+  if ((d0 * d0 + d1 * d1) + d2 * d2 > max_dist2) return false;  // :30-34
+  for (int i = 0; i < 3; ++i) state_world[i] = w[i];
+  for (int i = 0; i < 3; ++i) coords_in_local_map[i] = ((wl_R[3 * i] * w[0] + wl_R[3 * i + 1] * w[1]) + wl_R[3 * i + 2] * w[2]) + wl_t[i];
   return true;
 }
 

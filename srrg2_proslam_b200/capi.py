@@ -363,6 +363,19 @@ class Context:
                                                        C.byref(cnt), int(reps), C.byref(ms)))
         return cnt.value, ms.value
 
+    def landmarks_weighted_mean_update(self, sensor_in_world, sensor_in_local_map, state_world, n_opt, landmark_in_sensor, max_dist2=1.0):
+        st = np.ascontiguousarray(state_world, np.float32).reshape(-1, 3).copy()
+        n = len(st)
+        no = np.ascontiguousarray(n_opt, np.int32).reshape(n)
+        ls = np.ascontiguousarray(landmark_in_sensor, np.float32).reshape(n, 3)
+        loc, inl = np.zeros((n, 3), np.float32), np.zeros(n, np.uint8)
+        a = np.ascontiguousarray(sensor_in_world, np.float32).reshape(12)
+        b = np.ascontiguousarray(sensor_in_local_map, np.float32).reshape(12)
+        k = self._chk(lib().pslam_landmarks_weighted_mean_update(self._h, n, _p(st), _p(no), _p(ls), _p(a), _p(b), C.c_float(max_dist2),
+                                                                 _p(loc), _p(inl)))
+        assert k == int(inl.sum())
+        return st, loc, inl.astype(bool)
+
     def bf_best2(self, desc_f, desc_m):
         desc_f = np.ascontiguousarray(desc_f, np.uint8).reshape(-1, 32)
         desc_m = np.ascontiguousarray(desc_m, np.uint8).reshape(-1, 32)

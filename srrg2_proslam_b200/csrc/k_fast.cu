@@ -221,7 +221,7 @@ struct K1Args {
 // trow) in lane order, then score full batches of 32, one candidate per lane.  Deliberately NOT inlined: it is
 // called from the marching loop and inlining it makes the kernel overflow the instruction cache
 // (ncu: stall_no_instruction was the top stall reason).  Returns the new (head, tail) packed in 64 bits.
-// Entries are 16 bits: bit 15 = bright, bits 8-13 = tile row, bits 0-7 = column inside the warp's strip.
+// Entries are 16 bits, see score_entry.
 struct ScoreCtx {
   const uint8_t* img;
   uint8_t* s_score;
@@ -229,8 +229,11 @@ struct ScoreCtx {
   int stride, by, thr, SP, BW, xw;
 };
 __device__ __forceinline__ void score_entry(const ScoreCtx& c, unsigned entry) {
-  const int col = c.xw + (entry & 0xffu), trow = (entry >> 8) & 0x3fu;
-  const bool bright = (entry >> 15) != 0;
+  // entry = [tile row of the pair : 6][lane : 5][bit index i : 5], i = [second row : 1][dark : 1][pixel : 3] -- the push
+  // loop (one or two active lanes per iteration) only adds i, the decoding happens here with all 32 lanes busy
+  const unsigned i = entry & 31u;
+  const int col = c.xw + ((entry >> 2) & 0xf8u) + (i & 7u), trow = (entry >> 10) + (i >> 4);
+  const bool bright = (i & 8u) == 0u;
   const int y = c.by - 1 + trow;
   const int s = fast_score_polar(c.img + (size_t) y * c.stride + col, c.stride, bright);
   if (s > c.thr) {
@@ -244,7 +247,7 @@ __device__ __noinline__ unsigned long long push_and_drain(const uint8_t* img, ui
                                                           int BW, unsigned mask, unsigned ebase, unsigned q_head,
                                                           unsigned q_tail, bool flush) {
   // `mask`: candidates of TWO consecutive tile rows (bits 0-15 row trow, bits 16-31 row trow + 1; per row bits 0-7
-  // bright, 8-15 dark pixels x0 .. x0+7); ebase = trow << 8.  Pushing two rows per call halves the scans.
+  // bright, 8-15 dark pixels x0 .. x0+7); ebase = trow << 10.  Pushing two rows per call halves the scans.
   const int lane = threadIdx.x & 31;
   ScoreCtx c{img, s_score, s_bits, stride, by, thr, SP, BW, (int) (threadIdx.x >> 5) * 256};
   unsigned rest = 0u;
@@ -272,11 +275,11 @@ __device__ __noinline__ unsigned long long push_and_drain(const uint8_t* img, ui
     }
     if (total) {
       unsigned pos = q_tail + incl - cnt;
-      const unsigned eb = ebase + lane * 8u;
+      const unsigned eb = ebase + lane * 32u;
       while (mask) {
         const unsigned i = __ffs(mask) - 1;
         mask &= mask - 1;
-        s_queue[pos & (QCAP - 1)] = (unsigned short) (eb + (i & 7u) + ((i & 8u) ? 0u : 0x8000u) + ((i & 16u) << 4));
+        s_queue[pos & (QCAP - 1)] = (unsigned short) (eb + i);
         ++pos;
       }
       q_tail += total;
@@ -399,7 +402,7 @@ fast_blur_rows_kernel(const K1Args a) {
       const unsigned m16 = (mb | (md << 8)) & colmask;
       if (!have_pend) {  // rows are pushed in pairs (the executed centre rows of a band are consecutive)
         pend = m16;
-        pend_base = (unsigned) (rc - (by - 1)) << 8;
+        pend_base = (unsigned) (rc - (by - 1)) << 10;
         have_pend = true;
       } else {
         const unsigned long long q = push_and_drain(img, s_score, s_bits, s_queue, stride, by, thr, SP, BW,

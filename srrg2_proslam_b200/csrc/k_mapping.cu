@@ -189,6 +189,47 @@ landmarks_ekf_kernel(const EkfParams p, long long n, float* __restrict__ state_w
   if ((threadIdx.x & 31) == 0 && bal) atomicAdd(n_inliers, __popc(bal));
 }
 
+// LandmarkEstimatorWeightedMean_::compute (.../mapping/landmarks/landmark_estimator_weighted_mean_impl.cpp:7-41), fp32,
+// operation order of the oracle (bit exact): one thread per landmark
+struct WmParams {
+  float sw[12];         // sensor_in_world, row-major 3x4
+  float Rl[9], tl[3];   // world_in_local_map
+  float max_dist2;
+};
+__global__ void __launch_bounds__(256)
+landmarks_weighted_mean_kernel(const WmParams p, long long n, float* __restrict__ state_world, const int* __restrict__ n_opt,
+                               const float* __restrict__ landmark_in_sensor, float* __restrict__ coords_in_local_map,
+                               uint8_t* __restrict__ inlier, int* __restrict__ n_inliers) {
+  const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  bool ok = false;
+  if (i < n) {
+    const float lx = landmark_in_sensor[3 * i], ly = landmark_in_sensor[3 * i + 1], lz = landmark_in_sensor[3 * i + 2];
+    const float s0 = state_world[3 * i], s1 = state_world[3 * i + 1], s2 = state_world[3 * i + 2];
+    const float st[3] = {s0, s1, s2};
+    const float n1 = (float) (n_opt[i] + 1), n2 = __fadd_rn(n1, 1.0f);
+    float w[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float upd = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(p.sw[4 * a], lx), __fmul_rn(p.sw[4 * a + 1], ly)), __fmul_rn(p.sw[4 * a + 2], lz)), p.sw[4 * a + 3]);
+      w[a] = __fdiv_rn(__fadd_rn(__fmul_rn(n1, st[a]), upd), n2);
+    }
+    const float d0 = __fsub_rn(w[0], s0), d1 = __fsub_rn(w[1], s1), d2 = __fsub_rn(w[2], s2);
+    const float dist2 = __fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2));
+    ok = !(dist2 > p.max_dist2);
+    if (ok) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        state_world[3 * i + a] = w[a];
+        coords_in_local_map[3 * i + a] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(p.Rl[3 * a], w[0]), __fmul_rn(p.Rl[3 * a + 1], w[1])),
+                                                             __fmul_rn(p.Rl[3 * a + 2], w[2])), p.tl[a]);
+      }
+    }
+    inlier[i] = ok ? 1 : 0;
+  }
+  const unsigned bal = __ballot_sync(0xffffffffu, ok);
+  if ((threadIdx.x & 31) == 0 && bal) atomicAdd(n_inliers, __popc(bal));
+}
+
 }  // namespace
 
 // all pointers are device pointers; d_n_inliers: one int, zeroed here
@@ -228,5 +269,29 @@ int pslam_k_landmarks_ekf(pslam_ctx* ctx, const pslam_ekf_cfg* cfg, long long n,
   else if (cfg->kind == 2) landmarks_ekf_kernel<4><<<grid, 128, 0, ctx->stream>>>(p, n, d_state_world, d_covariance, d_meas, d_local, d_inlier, d_n_inliers);
   else return pslam_set_error(ctx, PSLAM_E_INVALID, "landmarks_ekf: unknown filter kind", cudaSuccess);
   PSLAM_LAUNCH_CHECK(ctx, "landmarks_ekf_kernel");
+  return PSLAM_OK;
+}
+
+int pslam_k_landmarks_weighted_mean(pslam_ctx* ctx, const float* sensor_in_world12, const float* sensor_in_local_map12, float max_dist2,
+                                    long long n, float* d_state_world, const int* d_n_opt, const float* d_landmark_in_sensor,
+                                    float* d_local, uint8_t* d_inlier, int* d_n_inliers) {
+  WmParams p;
+  const float* A = sensor_in_world12;
+  const float* L = sensor_in_local_map12;
+  float Rw[9], tw[3];  // world_in_sensor, fp32 (LandmarkEstimatorBase_::setTransforms)
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) Rw[3 * i + j] = A[4 * j + i];
+  for (int i = 0; i < 3; ++i) tw[i] = -((Rw[3 * i] * A[3] + Rw[3 * i + 1] * A[7]) + Rw[3 * i + 2] * A[11]);
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) p.Rl[3 * i + j] = (L[4 * i] * Rw[j] + L[4 * i + 1] * Rw[3 + j]) + L[4 * i + 2] * Rw[6 + j];
+    p.tl[i] = ((L[4 * i] * tw[0] + L[4 * i + 1] * tw[1]) + L[4 * i + 2] * tw[2]) + L[4 * i + 3];
+  }
+  for (int i = 0; i < 12; ++i) p.sw[i] = A[i];
+  p.max_dist2 = max_dist2;
+  PSLAM_CUDA_TRY(ctx, cudaMemsetAsync(d_n_inliers, 0, sizeof(int), ctx->stream));
+  if (n == 0) return PSLAM_OK;
+  landmarks_weighted_mean_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, ctx->stream>>>(p, n, d_state_world, d_n_opt, d_landmark_in_sensor, d_local,
+                                                                                      d_inlier, d_n_inliers);
+  PSLAM_LAUNCH_CHECK(ctx, "landmarks_weighted_mean_kernel");
   return PSLAM_OK;
 }

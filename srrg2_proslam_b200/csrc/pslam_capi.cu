@@ -874,6 +874,46 @@ int pslam_landmarks_ekf_update(pslam_ctx* ctx, int n, float* state_world, float*
   return n_inliers;
 }
 
+int pslam_landmarks_weighted_mean_update(pslam_ctx* ctx, int n, float* state_world, const int* number_of_optimizations,
+                                         const float* landmark_in_sensor, const float* sensor_in_world12,
+                                         const float* sensor_in_local_map12, float maximum_distance_geometry_meters_squared,
+                                         float* coords_in_local_map, uint8_t* inlier) {
+  if (!ctx || n < 0 || !sensor_in_world12 || !sensor_in_local_map12 ||
+      (n > 0 && (!state_world || !number_of_optimizations || !landmark_in_sensor || !coords_in_local_map || !inlier)))
+    return PSLAM_E_INVALID;
+  if (n == 0) return 0;
+  PSLAM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  auto al = [](size_t b) { return (b + 255) & ~(size_t) 255; };
+  const size_t b3 = al((size_t) n * 12), b1 = al((size_t) n * 4), bi = al((size_t) n);
+  if (PSLAM_SOLVER_SCRATCH_OFFSET + 256 + 3 * b3 + b1 + bi > ctx->scratch_bytes)
+    return pslam_set_error(ctx, PSLAM_E_CAPACITY, "landmarks_weighted_mean: too many landmarks for the scratch buffer", cudaSuccess);
+  int* d_cnt = reinterpret_cast<int*>(ctx->d_scratch + PSLAM_SOLVER_SCRATCH_OFFSET);
+  uint8_t* p = ctx->d_scratch + PSLAM_SOLVER_SCRATCH_OFFSET + 256;
+  float* d_st = reinterpret_cast<float*>(p);
+  p += b3;
+  float* d_ls = reinterpret_cast<float*>(p);
+  p += b3;
+  float* d_loc = reinterpret_cast<float*>(p);
+  p += b3;
+  int* d_no = reinterpret_cast<int*>(p);
+  p += b1;
+  uint8_t* d_in = p;
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_st, state_world, (size_t) n * 12, cudaMemcpyHostToDevice, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_ls, landmark_in_sensor, (size_t) n * 12, cudaMemcpyHostToDevice, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_no, number_of_optimizations, (size_t) n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaMemsetAsync(d_loc, 0, (size_t) n * 12, ctx->stream));
+  const int rc = pslam_k_landmarks_weighted_mean(ctx, sensor_in_world12, sensor_in_local_map12, maximum_distance_geometry_meters_squared, n,
+                                                 d_st, d_no, d_ls, d_loc, d_in, d_cnt);
+  if (rc) return rc;
+  int* h = reinterpret_cast<int*>(ctx->h_pinned);
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(h, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(state_world, d_st, (size_t) n * 12, cudaMemcpyDeviceToHost, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(coords_in_local_map, d_loc, (size_t) n * 12, cudaMemcpyDeviceToHost, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(inlier, d_in, (size_t) n, cudaMemcpyDeviceToHost, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return *h;
+}
+
 // ---- stage 2b -----------------------------------------------------------------------------------
 static int bf_upload(pslam_ctx* ctx, int nf, const uint8_t* df, int nm, const uint8_t* dm,
                      uint32_t** d_f, uint32_t** d_m, size_t* used) {

@@ -74,3 +74,6 @@ size_t pslam_k_scene_clip_state_bytes(long long n);
 // k_mapping.cu (N3: per-landmark EKF update after the alignment)
 int pslam_k_landmarks_ekf(pslam_ctx* ctx, const pslam_ekf_cfg* cfg, long long n, float* d_state_world, float* d_covariance,
                           const float* d_meas, float* d_local, uint8_t* d_inlier, int* d_n_inliers);
+int pslam_k_landmarks_weighted_mean(pslam_ctx* ctx, const float* sensor_in_world12, const float* sensor_in_local_map12, float max_dist2,
+                                    long long n, float* d_state_world, const int* d_n_opt, const float* d_landmark_in_sensor,
+                                    float* d_local, uint8_t* d_inlier, int* d_n_inliers);

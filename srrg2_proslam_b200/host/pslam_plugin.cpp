@@ -722,6 +722,16 @@ int LandmarkEstimatorEKFCUDA::computeBatch(int n, float* state_world, float* cov
   return k;
 }
 
+int LandmarkEstimatorWeightedMeanCUDA::computeBatch(int n, float* state_world, const int* number_of_optimizations,
+                                                    const float* landmark_in_sensor, float* coords_in_local_map, uint8_t* inlier) {
+  pslam_ctx* ctx = PslamDevice::context();
+  const int k = pslam_landmarks_weighted_mean_update(ctx, n, state_world, number_of_optimizations, landmark_in_sensor, _sensor_in_world.m,
+                                                     _sensor_in_local_map.m, param_maximum_distance_geometry_meters_squared.value(),
+                                                     coords_in_local_map, inlier);
+  PslamDevice::check(k, "LandmarkEstimatorWeightedMean::compute");
+  return k;
+}
+
 // ---- aligner slice ----------------------------------------------------------------------------------------------
 AlignerSliceProcessorProjectiveCUDA::AlignerSliceProcessorProjectiveCUDA(int kind) : _kind(kind) {
   // aligner_slice_processor_projective.cpp:7-20: saturated robustifier with chi threshold 100^2 by default
@@ -945,6 +955,7 @@ void registerTypes() {
   reg<FilterK<0>>("ProjectivePointEKF3D");
   reg<FilterK<1>>("ProjectiveDepthPointEKF3D");
   reg<FilterK<2>>("StereoProjectivePointEKF3D");
+  for (const char* dims : {"2D3D", "3D3D", "4D3D"}) reg<LandmarkEstimatorWeightedMeanCUDA>(std::string("LandmarkEstimatorWeightedMean") + dims);
   reg<EstimatorK<0>>("LandmarkEstimatorProjectiveEKF3D");
   reg<EstimatorK<1>>("LandmarkEstimatorProjectiveDepthEKF3D");
   reg<EstimatorK<2>>("LandmarkEstimatorStereoProjectiveEKF3D");

@@ -500,6 +500,24 @@ private:
   Isometry3f _sensor_in_world, _sensor_in_local_map;
 };
 
+// ---- LandmarkEstimatorWeightedMean_ (mapping/landmarks/landmark_estimator_weighted_mean.{h,cpp}) -------------------
+class LandmarkEstimatorWeightedMeanCUDA : public Configurable {
+public:
+  PARAM(PropertyFloat, maximum_distance_geometry_meters_squared,
+        "maximum distance in geometry (i.e. 3D point distance L2 norm) in meters squared", 1, nullptr);
+  void setTransforms(const Isometry3f& measurement_in_world, const Isometry3f& measurement_in_scene) {
+    _sensor_in_world = measurement_in_world;
+    _sensor_in_local_map = measurement_in_scene;
+  }
+  // setLandmarkInSensor / setLandmark / compute (landmark_estimator_weighted_mean_impl.cpp:7-41) for all correspondences
+  // of one merger pass; number_of_optimizations = statistics().numberOfOptimizations() of every landmark
+  int computeBatch(int n, float* state_world, const int* number_of_optimizations, const float* landmark_in_sensor,
+                   float* coords_in_local_map, uint8_t* inlier);
+
+private:
+  Isometry3f _sensor_in_world, _sensor_in_local_map;
+};
+
 // registers every class above under the reference's names and under the ...CUDA names (idempotent)
 void registerTypes();
 

@@ -584,7 +584,8 @@ int psp_landmark_estimator_set_transforms(psp_module* estimator, const float* me
     Isometry3f W, S;
     std::memcpy(W.m, measurement_in_world12, sizeof(W.m));
     std::memcpy(S.m, measurement_in_scene12, sizeof(S.m));
-    as<LandmarkEstimatorEKFCUDA>(estimator, "LandmarkEstimatorEKF")->setTransforms(W, S);
+    if (auto* wm = dynamic_cast<LandmarkEstimatorWeightedMeanCUDA*>(mod(estimator))) wm->setTransforms(W, S);
+    else as<LandmarkEstimatorEKFCUDA>(estimator, "LandmarkEstimatorEKF")->setTransforms(W, S);
     return 0;
   });
 }
@@ -594,6 +595,14 @@ int psp_landmark_estimator_compute_batch(psp_module* estimator, int n, float* st
   return guard([&] {
     return as<LandmarkEstimatorEKFCUDA>(estimator, "LandmarkEstimatorEKF")
       ->computeBatch(n, state_world, covariance, measurements, coords_in_local_map, inlier);
+  });
+}
+
+int psp_landmark_estimator_weighted_mean_batch(psp_module* estimator, int n, float* state_world, const int* number_of_optimizations,
+                                               const float* landmark_in_sensor, float* coords_in_local_map, uint8_t* inlier) {
+  return guard([&] {
+    return as<LandmarkEstimatorWeightedMeanCUDA>(estimator, "LandmarkEstimatorWeightedMean")
+      ->computeBatch(n, state_world, number_of_optimizations, landmark_in_sensor, coords_in_local_map, inlier);
   });
 }
 

@@ -234,6 +234,15 @@ class Module:
         k = _chk(lib().psp_landmark_estimator_compute_batch(self.h, n, _p(st), _p(cv), _p(ms), _p(loc), _p(inl)))
         return st, cv.reshape(n, 3, 3), loc, inl.astype(bool), k
 
+    def estimator_weighted_mean_batch(self, state_world, n_opt, landmark_in_sensor):
+        st = np.ascontiguousarray(state_world, np.float32).reshape(-1, 3).copy()
+        n = len(st)
+        no = np.ascontiguousarray(n_opt, np.int32).reshape(n)
+        ls = np.ascontiguousarray(landmark_in_sensor, np.float32).reshape(n, 3)
+        loc, inl = np.zeros((n, 3), np.float32), np.zeros(n, np.uint8)
+        k = _chk(lib().psp_landmark_estimator_weighted_mean_batch(self.h, n, _p(st), _p(no), _p(ls), _p(loc), _p(inl)))
+        return st, loc, inl.astype(bool), k
+
     def aligner_set_moving_in_fixed(self, pose12):
         pose12 = np.ascontiguousarray(pose12, np.float32).reshape(12)
         _chk(lib().psp_aligner_set_moving_in_fixed(self.h, _p(pose12)))

@@ -297,6 +297,19 @@ def landmarks_ekf_update(kind, K, baseline2, sensor_in_world, sensor_in_local_ma
     return st, cv.reshape(n, 3, 3), loc, inl.astype(bool)
 
 
+def landmarks_weighted_mean_update(sensor_in_world, sensor_in_local_map, state_world, n_opt, landmark_in_sensor, max_dist2=1.0):
+    """LandmarkEstimatorWeightedMean_::compute over n landmarks (landmark_estimator_weighted_mean_impl.cpp:7-41)"""
+    st = np.ascontiguousarray(state_world, np.float32).reshape(-1, 3).copy()
+    n = len(st)
+    no = np.ascontiguousarray(n_opt, np.int32).reshape(n)
+    ls = np.ascontiguousarray(landmark_in_sensor, np.float32).reshape(n, 3)
+    loc, inl = np.zeros((n, 3), np.float32), np.zeros(n, np.uint8)
+    f32 = lambda x: np.ascontiguousarray(x, np.float32).reshape(12)
+    lib().orc_landmarks_weighted_mean_update(n, C.c_float(max_dist2), _p(f32(sensor_in_world)), _p(f32(sensor_in_local_map)), _p(st),
+                                             _p(no), _p(ls), _p(loc), _p(inl))
+    return st, loc, inl.astype(bool)
+
+
 SHAPES = {"square": 0, "circle": 1, "rhombus": 2}
 
 

@@ -106,3 +106,38 @@ def test_conf_landmark_estimator_module(oracle):
     assert np.array_equal(g[3], o[3]) and g[4] == int(o[3].sum()) and 0 < g[4] < 5000
     for a, b in zip(g[:3], o[:3]):
         assert np.allclose(a, b, rtol=2e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("n", [1, 257, 50000])
+def test_weighted_mean_bit_exact(ctx, n):
+    rng = np.random.default_rng(n)
+    truth = rng.uniform(-5, 5, (n, 3)) + np.array([0, 0, 12.0])
+    state = (truth + rng.normal(0, 0.5, (n, 3))).astype(np.float32)
+    n_opt = rng.integers(0, 30, n).astype(np.int32)
+    cam = np.concatenate([F.rot(1, 0.1) @ F.rot(2, -0.05), np.array([[0.3], [0.1], [-0.2]])], 1)
+    M = np.concatenate([F.rot(0, 0.2), np.array([[2.0], [0.5], [-1.0]])], 1)
+    sil = np.concatenate([M[:, :3] @ cam[:, :3], (M[:, :3] @ cam[:, 3] + M[:, 3]).reshape(3, 1)], 1)
+    in_sensor = ((truth - cam[:, 3]) @ cam[:, :3] + rng.normal(0, 0.4, (n, 3))).astype(np.float32)
+    g = ctx.landmarks_weighted_mean_update(cam, sil, state, n_opt, in_sensor, max_dist2=0.02)
+    o = O.landmarks_weighted_mean_update(cam, sil, state, n_opt, in_sensor, max_dist2=0.02)
+    for a, b in zip(g, o):
+        assert np.array_equal(a, b)  # fp32, bit exact
+    if n > 1000:
+        assert 0 < g[2].sum() < n
+
+
+def test_conf_weighted_mean_module(oracle):
+    import pathlib
+    from srrg2_proslam_b200 import plugin as P
+    m = P.Manager(pathlib.Path(__file__).resolve().parent / "golden" / "configurations" / "kitti_hotpath.conf")
+    est = m.get("landmark_estimator_weighted_mean")
+    assert est.class_name == "LandmarkEstimatorWeightedMean4D3D" and est.get("maximum_distance_geometry_meters_squared") == 100
+    rng = np.random.default_rng(9)
+    n = 3000
+    state = rng.uniform(-5, 5, (n, 3)).astype(np.float32) + np.array([0, 0, 15], np.float32)
+    in_sensor = state + rng.normal(0, 3.0, (n, 3)).astype(np.float32)
+    n_opt = rng.integers(0, 5, n).astype(np.int32)
+    est.estimator_set_transforms(np.eye(3, 4), np.eye(3, 4))
+    g = est.estimator_weighted_mean_batch(state, n_opt, in_sensor)
+    o = O.landmarks_weighted_mean_update(np.eye(3, 4), np.eye(3, 4), state, n_opt, in_sensor, max_dist2=100.0)
+    assert np.array_equal(g[0], o[0]) and np.array_equal(g[1], o[1]) and np.array_equal(g[2], o[2]) and g[3] == int(o[2].sum())

@@ -78,3 +78,24 @@ def test_landmark_estimator_ekf(oracle):
     bad[:, 2] += 120.0
     s2, c2, _, inl2 = O.landmarks_ekf_update("stereo", Kf, F.BASELINE[:2], cam, cam, state, cov, bad, max_cov_norm2=4.0, max_dist2=0.01)
     assert not inl2.any() and np.array_equal(s2, state) and np.array_equal(c2.reshape(n, 9), cov)
+
+
+def test_landmark_estimator_weighted_mean(oracle):
+    """LandmarkEstimatorWeightedMean_::compute (landmark_estimator_weighted_mean_impl.cpp:7-41): the mean converges to the
+    true position when the re-observations are exact (tests/test_landmark_estimators.cpp:29-69), a jump farther than the
+    geometric gate is rejected"""
+    rng = np.random.default_rng(5)
+    n = 200
+    truth = rng.uniform(-5, 5, (n, 3)) + np.array([0, 0, 12.0])
+    state = (truth + rng.normal(0, 0.3, (n, 3))).astype(np.float32)
+    n_opt = np.zeros(n, np.int32)
+    for step in range(20):
+        cam = np.concatenate([F.rot(1, 0.02 * step), np.array([[0.1 * step], [0.0], [0.05 * step]])], 1)
+        in_sensor = (truth - cam[:, 3]) @ cam[:, :3]
+        state, local, inl = O.landmarks_weighted_mean_update(cam, cam, state, n_opt, in_sensor, max_dist2=1.0)
+        assert inl.all() and np.allclose(local, state, atol=1e-5)  # sensor_in_local_map = sensor_in_world => local map = world
+        n_opt += 1
+    assert np.abs(state - truth).max() < 0.05
+    far = in_sensor + np.array([0, 0, 50.0])
+    s2, _, inl2 = O.landmarks_weighted_mean_update(cam, cam, state, n_opt, far, max_dist2=1.0)
+    assert not inl2.any() and np.array_equal(s2, state)
