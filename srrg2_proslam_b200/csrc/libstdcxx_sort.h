@@ -247,6 +247,7 @@ __device__ __forceinline__ int warp_partition_(T* a, unsigned short* rpos, int f
       a[y] = a[i];
       a[i] = t;
     }
+    __syncwarp();  // the next round may read a swapped position (compute-sanitizer racecheck)
     K += __popc(sw);
     nL += __popc(bal);
     const unsigned stop = bal & ~sw;  // first stopper that is not swapped = L_K

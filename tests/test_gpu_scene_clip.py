@@ -110,6 +110,13 @@ def test_device_resident(ctx):
     assert np.array_equal(oidx[:m].cpu().numpy(), exp_idx)
     assert np.array_equal(oxyz[:m].cpu().numpy(), exp_xyz) and np.array_equal(ouvz[:m].cpu().numpy(), exp_uvz)
     assert torch.equal(odesc[:m], desc[torch.from_numpy(exp_idx).cuda().long()])
+    # a map that does not start on a 16-byte boundary (row 1 of the tensor: +12 bytes) takes the non-TMA staging path
+    n2 = 100001
+    sub = xyz[1:1 + n2]
+    assert sub.data_ptr() % 16 != 0
+    m2, _ = ctx.scene_clip_dev(n2, sub.data_ptr(), 0, cfg, oxyz.data_ptr(), ouvz.data_ptr(), oidx.data_ptr(), 0, reps=1)
+    e2 = O.scene_clip(sub.cpu().numpy(), T, F.K_KITTI, 376, 1241, 0.1, 1000.0)
+    assert m2 == len(e2[2]) and np.array_equal(oidx[:m2].cpu().numpy(), e2[2]) and np.array_equal(oxyz[:m2].cpu().numpy(), e2[0])
 
 
 def test_conf_clipper_module(oracle):
