@@ -161,12 +161,12 @@ epipolar_kernel(const float2* __restrict__ xy, const uint32_t* __restrict__ desc
                 int thickness, int* __restrict__ ep_fixed, int* __restrict__ ep_moving,
                 float* __restrict__ ep_dist, int* __restrict__ ep_count,
                 float4* __restrict__ st_uvuv, int* __restrict__ st_left, int* __restrict__ st_right,
-                float* __restrict__ st_dist, int* __restrict__ st_count) {
+                float* __restrict__ st_dist, int* __restrict__ st_count, int pair_base) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ int s_warp[33];
   __shared__ int s_nruns;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int pair = blockIdx.x;
+  const int pair = pair_base + blockIdx.x;
   const int imgL = 2 * pair, imgR = 2 * pair + 1;
   int nL = count[imgL], nR = count[imgR];
 
@@ -512,7 +512,7 @@ static size_t ep_smem_bytes(int M, bool general) {
   return scratch + (size_t) M * (8 * 2 + 2 + 2);
 }
 
-int pslam_k_epipolar(pslam_ctx* ctx, int n_pairs, const pslam_match_cfg* cfg, int general) {
+int pslam_k_epipolar(pslam_ctx* ctx, int n_pairs, const pslam_match_cfg* cfg, int general, int pair_base) {
   const int M = ctx->lim.max_features;
   if (ctx->lim.max_rows > EP_ROWS) general = 1;
   const size_t smem = ep_smem_bytes(M, general != 0);
@@ -523,7 +523,7 @@ int pslam_k_epipolar(pslam_ctx* ctx, int n_pairs, const pslam_match_cfg* cfg, in
     cfg->maximum_distance_ratio_to_second_best, cfg->maximum_disparity_pixels,
     cfg->epipolar_line_thickness_pixels, ctx->d_ep_fixed, ctx->d_ep_moving, ctx->d_ep_dist,
     ctx->d_ep_count, ctx->d_st_uvuv, ctx->d_st_left, ctx->d_st_right, ctx->d_st_dist,
-    ctx->d_st_count);
+    ctx->d_st_count, pair_base);
   PSLAM_LAUNCH_CHECK(ctx, "epipolar_kernel");
   return PSLAM_OK;
 }

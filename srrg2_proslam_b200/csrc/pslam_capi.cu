@@ -104,8 +104,10 @@ int run_extract_chunk(pslam_ctx* ctx, const uint8_t* d_images, long long image_p
 }
 
 // the whole batch, device-resident images, in chunks of work_images
+// `mcfg` != nullptr (stereo batches, even work_images): the stereo pairs of a chunk are matched right after the chunk's
+// descriptors were written, while they are still L2 resident (and, for host images, while the next chunk uploads)
 int run_extract(pslam_ctx* ctx, const uint8_t* d_images, long long image_pitch, int n_images, int rows,
-                int cols, int stride, const pslam_extract_cfg* cfg, const uint8_t* d_mask) {
+                int cols, int stride, const pslam_extract_cfg* cfg, const uint8_t* d_mask, const pslam_match_cfg* mcfg = nullptr) {
   ctx->rows = rows;
   ctx->cols = cols;
   ctx->n_images = n_images;
@@ -113,6 +115,7 @@ int run_extract(pslam_ctx* ctx, const uint8_t* d_images, long long image_pitch, 
     const int n = n_images - base < ctx->work_images ? n_images - base : ctx->work_images;
     int rc = run_extract_chunk(ctx, d_images + (size_t) base * image_pitch, image_pitch, n, rows, cols, stride, cfg, d_mask, base);
     if (rc) return rc;
+    if (mcfg && n / 2 > 0 && (rc = pslam_k_epipolar(ctx, n / 2, mcfg, 0, base / 2))) return rc;
   }
   return PSLAM_OK;
 }
@@ -120,7 +123,7 @@ int run_extract(pslam_ctx* ctx, const uint8_t* d_images, long long image_pitch, 
 // the whole batch, HOST images: uploads on copy_stream into the double-buffered staging area overlap the
 // kernels of the previous chunk on the compute stream
 int run_extract_host(pslam_ctx* ctx, const uint8_t* h_images, long long image_pitch, int n_images, int rows,
-                     int cols, int stride, const pslam_extract_cfg* cfg) {
+                     int cols, int stride, const pslam_extract_cfg* cfg, const pslam_match_cfg* mcfg = nullptr) {
   ctx->rows = rows;
   ctx->cols = cols;
   ctx->n_images = n_images;
@@ -156,7 +159,8 @@ int run_extract_host(pslam_ctx* ctx, const uint8_t* h_images, long long image_pi
     if (ctx->prof_enabled) pslam_prof_mark(ctx, nullptr);  // the wait for the upload is not kernel time
     int rc = run_extract_chunk(ctx, d_src, d_pitch, n, rows, cols, d_stride, cfg, nullptr, base);
     if (rc) return rc;
-    PSLAM_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_free[buf], ctx->stream));
+    PSLAM_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_free[buf], ctx->stream));  // the matcher below does not read the staging buffer
+    if (mcfg && n / 2 > 0 && (rc = pslam_k_epipolar(ctx, n / 2, mcfg, 0, base / 2))) return rc;
   }
   return PSLAM_OK;
 }
@@ -520,6 +524,8 @@ int pslam_stereo_frontend_batch_dev(pslam_ctx* ctx, const uint8_t* d_images, int
   if (rc) return rc;
   PSLAM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   if (ctx->prof_enabled) pslam_prof_mark(ctx, nullptr);
+  // device-resident images: ONE matcher launch over all pairs after the last chunk (one CTA per pair: a launch per
+  // 256-pair chunk leaves a third of the SMs idle and measured 0.94 instead of 0.60 us / image)
   if ((rc = run_extract(ctx, d_images, image_pitch_bytes, 2 * n_pairs, rows, cols, stride, ecfg, nullptr))) return rc;
   if (n_pairs > 0 && (rc = pslam_k_epipolar(ctx, n_pairs, mcfg, 0))) return rc;
   return PSLAM_OK;
@@ -532,8 +538,11 @@ int pslam_stereo_frontend_batch(pslam_ctx* ctx, const uint8_t* h_images, int n_p
   int rc = validate_extract(ctx, 2 * n_pairs, rows, cols, ecfg);
   if (rc) return rc;
   PSLAM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  if ((rc = run_extract_host(ctx, h_images, image_pitch_bytes, 2 * n_pairs, rows, cols, stride, ecfg))) return rc;
-  if (n_pairs > 0 && (rc = pslam_k_epipolar(ctx, n_pairs, mcfg, 0))) return rc;
+  // host images: the pipeline is bound by the PCIe uploads, so every chunk's pairs are matched as soon as its
+  // descriptors exist -- hidden behind the next chunk's upload instead of running after the last one (+6.5 % end to end)
+  const bool per_chunk = (ctx->work_images & 1) == 0;  // pairs never straddle a chunk
+  if ((rc = run_extract_host(ctx, h_images, image_pitch_bytes, 2 * n_pairs, rows, cols, stride, ecfg, per_chunk ? mcfg : nullptr))) return rc;
+  if (!per_chunk && n_pairs > 0 && (rc = pslam_k_epipolar(ctx, n_pairs, mcfg, 0))) return rc;
   return PSLAM_OK;
 }
 

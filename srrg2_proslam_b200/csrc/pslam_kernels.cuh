@@ -20,7 +20,7 @@ int pslam_k_mono_depth(pslam_ctx* ctx, const void* d_depth, int depth_type, int 
 
 // k_epipolar.cu
 // general != 0: arbitrary host coordinates (bitonic sort); 0: coordinates produced by the extractor (row < max_rows)
-int pslam_k_epipolar(pslam_ctx* ctx, int n_pairs, const pslam_match_cfg* cfg, int general);
+int pslam_k_epipolar(pslam_ctx* ctx, int n_pairs, const pslam_match_cfg* cfg, int general, int pair_base = 0);
 
 // packed (CSR) stereo result of a batch, carved from the context scratch: offsets[n_pairs + 1] then SoA
 struct pslam_packed_stereo {
