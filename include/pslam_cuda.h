@@ -260,6 +260,28 @@ int pslam_landmarks_weighted_mean_update(pslam_ctx* ctx, int n, float* state_wor
                                          const float* sensor_in_local_map12, float maximum_distance_geometry_meters_squared,
                                          float* coords_in_local_map, uint8_t* inlier);
 
+/* LandmarkEstimatorPoseBasedSmoother_::compute (.../mapping/landmarks/landmark_estimator_pose_based_smoother_impl.cpp:6-148,
+ * kitti.conf "landmark_estimator_smoother") over the n landmarks of one merger pass, fp32, bit exact against the CPU
+ * restatement.  Every landmark brings its WHOLE measurement history, the current measurement included (the reference
+ * appends it first, :15-19), in CSR form: offsets[n + 1]; per measurement the frame it was taken in (index into
+ * frames_sensor_in_world [n_frames][12], row-major 3x4), its image point (u, v) and the point in that camera frame
+ * (setLandmarkInSensor).  state_world / number_of_optimizations are the landmark statistics, updated in place exactly
+ * where the reference updates them (mean below minimum_number_of_measurements_for_optimization, Gauss-Newton result or
+ * mean reset above); coords_in_local_map[n][3], inlier[n] = isInlier.  Returns the number of inliers. */
+typedef struct pslam_smoother_cfg {
+  float K[9];                                                  /* setCameraMatrix */
+  unsigned maximum_number_of_iterations;                       /* PARAM, default 100 */
+  float convergence_criterion_minimum_chi2_delta;              /* PARAM, default 1e-5 */
+  float maximum_reprojection_error_pixels_squared;             /* PARAM, default 100 */
+  unsigned minimum_number_of_measurements_for_optimization;    /* PARAM, default 3 */
+  float maximum_distance_geometry_meters_squared;              /* PARAM, default 1 */
+  float sensor_in_world[12], sensor_in_local_map[12];          /* setTransforms of the current frame */
+} pslam_smoother_cfg;
+int pslam_landmarks_smoother_update(pslam_ctx* ctx, int n, float* state_world, int* number_of_optimizations, int n_frames,
+                                    const float* frames_sensor_in_world, const int* offsets, const int* hist_frame,
+                                    const float* hist_uv, const float* hist_point_in_camera, const pslam_smoother_cfg* cfg,
+                                    float* coords_in_local_map, uint8_t* inlier);
+
 /* ---- stage 2b: exhaustive Hamming matching --------------------------------------
  * Replaces CorrespondenceFinderDescriptorBasedBruteforce::compute
  *   (.../correspondence_finders/correspondence_finder_descriptor_based_bruteforce_impl.cpp:6-294).

@@ -129,6 +129,14 @@ int psp_landmark_estimator_compute_batch(psp_module* estimator, int n, float* st
 int psp_landmark_estimator_weighted_mean_batch(psp_module* estimator, int n, float* state_world, const int* number_of_optimizations,
                                                const float* landmark_in_sensor, float* coords_in_local_map, uint8_t* inlier);
 
+/* LandmarkEstimatorPoseBasedSmoother{2D3D,3D3D,4D3D}: setCameraMatrix, psp_landmark_estimator_set_transforms, then the
+ * batched compute over CSR measurement histories (see pslam_landmarks_smoother_update) */
+int psp_landmark_smoother_set_camera_matrix(psp_module* estimator, const float* K9);
+int psp_landmark_smoother_compute_batch(psp_module* estimator, int n, float* state_world, int* number_of_optimizations, int n_frames,
+                                        const float* frames_sensor_in_world, const int* offsets, const int* hist_frame,
+                                        const float* hist_uv, const float* hist_point_in_camera, float* coords_in_local_map,
+                                        uint8_t* inlier);
+
 #ifdef __cplusplus
 }
 #endif

@@ -507,6 +507,45 @@ int orc_landmarks_weighted_mean_update(int n, float max_dist2, const float* sens
   return k;
 }
 
+// LandmarkEstimatorPoseBasedSmoother_::compute over n landmarks; histories in CSR form (offsets[n + 1]).
+// params5 = max iterations, chi2 delta, max reprojection error^2, min measurements, max distance^2
+int orc_landmarks_smoother_update(int n, const float* K9, const float* params5, int n_frames, const float* frames_sensor_in_world,
+                                  const float* sensor_in_world12, const float* sensor_in_local_map12, const int* offsets,
+                                  const int* hist_frame, const float* hist_uv, const float* hist_point_in_camera, float* state_world,
+                                  int* number_of_optimizations, float* coords_in_local_map, unsigned char* inlier) {
+  SmootherConfig cfg;
+  std::memcpy(cfg.K, K9, sizeof(cfg.K));
+  cfg.maximum_number_of_iterations = (unsigned) params5[0];
+  cfg.convergence_criterion_minimum_chi2_delta = params5[1];
+  cfg.maximum_reprojection_error_pixels_squared = params5[2];
+  cfg.minimum_number_of_measurements_for_optimization = (unsigned) params5[3];
+  cfg.maximum_distance_geometry_meters_squared = params5[4];
+  std::vector<float> wis((size_t) 12 * n_frames);
+  for (int f = 0; f < n_frames; ++f) {
+    const Pose<float> inv = pose_from(frames_sensor_in_world + 12 * f).inverse();
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) wis[12 * f + 4 * i + j] = inv.R[3 * i + j];
+      wis[12 * f + 4 * i + 3] = inv.t[i];
+    }
+  }
+  const Pose<float> wl = pose_from(sensor_in_local_map12) * pose_from(sensor_in_world12).inverse();
+  float wl12[12];
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) wl12[4 * i + j] = wl.R[3 * i + j];
+    wl12[4 * i + 3] = wl.t[i];
+  }
+  int k = 0;
+  for (int i = 0; i < n; ++i) {
+    const int o = offsets[i], m = offsets[i + 1] - o;
+    const bool ok = landmark_smoother_update(cfg, frames_sensor_in_world, wis.data(), wl12, m, hist_frame + o, hist_uv + 2 * (size_t) o,
+                                             hist_point_in_camera + 3 * (size_t) o, state_world + 3 * i, number_of_optimizations + i,
+                                             coords_in_local_map + 3 * i);
+    inlier[i] = ok ? 1 : 0;
+    k += ok;
+  }
+  return k;
+}
+
 // ---- stateful projective finder ----------------------------------------------
 struct OrcFinder {
   ProjectiveFinder f;

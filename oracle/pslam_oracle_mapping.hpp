@@ -15,6 +15,7 @@
 #pragma once
 #include <cmath>
 #include <cstring>
+#include <utility>
 
 namespace pslam_oracle {
 
@@ -204,6 +205,178 @@ static inline bool landmark_weighted_mean_update(const float* sw_R, const float*
   for (int i = 0; i < 3; ++i) state_world[i] = w[i];
   for (int i = 0; i < 3; ++i) coords_in_local_map[i] = ((wl_R[3 * i] * w[0] + wl_R[3 * i + 1] * w[1]) + wl_R[3 * i + 2] * w[2]) + wl_t[i];
   return true;
+}
+
+// -----------------------------------------------------------------------------------------------------------------
+// LandmarkEstimatorPoseBasedSmoother_::compute  (.../mapping/landmarks/landmark_estimator_pose_based_smoother_impl.cpp:6-148)
+// fp32 like the reference.  The landmark's measurement history lives in srrg2_core's PointStatisticsField3D (external,
+// un-vendored); what the reference code shows of it is restated here as plain arrays:
+//   CameraMeasurement(point_in_image, point_in_camera, sensor_in_world, world_in_sensor)  (:16-19) with the accessors
+//   camera_from_world * point_in_camera -> world (:142) and world_from_camera * world -> camera (:60), i.e. one
+//   sensor pose per frame: `frame[k]` indexes the tables frames_sensor_in_world / frames_world_in_sensor (R row major
+//   3x3 + t, 12 floats).  The history handed in already contains the current measurement (addMeasurement, :15).
+//   [upstream, not verifiable here] addOptimizationResult(x) is taken to store x as the state and to increment
+//   numberOfOptimizations by one (consistent with the asserts at :127,135).
+// Eigen's Matrix3f::fullPivLu().solve (:112) is restated as full-pivot Gaussian elimination with Eigen's rank rule.
+// -----------------------------------------------------------------------------------------------------------------
+struct SmootherConfig {
+  float K[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  unsigned maximum_number_of_iterations = 100;                     // landmark_estimator_pose_based_smoother.h:14-18
+  float convergence_criterion_minimum_chi2_delta = 1e-5f;          // :19-23
+  float maximum_reprojection_error_pixels_squared = 100;           // :24-28
+  unsigned minimum_number_of_measurements_for_optimization = 3;    // :29-33
+  float maximum_distance_geometry_meters_squared = 1;              // landmark_estimator_base.hpp:22-26
+};
+
+static inline void smoother_apply(const float* T12, const float* p, float* o) {  // Isometry3f * Vector3f
+  for (int i = 0; i < 3; ++i) o[i] = ((T12[4 * i] * p[0] + T12[4 * i + 1] * p[1]) + T12[4 * i + 2] * p[2]) + T12[4 * i + 3];
+}
+
+// x = A^-1 rhs for a 3x3 system with full pivoting (Eigen::FullPivLU::solve semantics, rank threshold eps * 3)
+static inline void full_piv_lu_solve3(const float* A_in, const float* rhs, float* x) {
+  float A[9];
+  for (int i = 0; i < 9; ++i) A[i] = A_in[i];
+  int rp[3] = {0, 1, 2}, cp[3] = {0, 1, 2};  // row / column transpositions applied so far
+  float c[3] = {rhs[0], rhs[1], rhs[2]};
+  float maxpivot = 0;
+  int nonzero = 3;
+  for (int k = 0; k < 3; ++k) {
+    int br = k, bc = k;
+    float best = -1;
+    for (int j = k; j < 3; ++j)       // column-major scan, the first maximum wins (Eigen's maxCoeff visitor)
+      for (int i = k; i < 3; ++i) {
+        const float v = std::fabs(A[3 * i + j]);
+        if (v > best) {
+          best = v;
+          br = i;
+          bc = j;
+        }
+      }
+    if (best == 0.0f) {
+      nonzero = k;
+      break;
+    }
+    if (best > maxpivot) maxpivot = best;
+    if (br != k) {
+      for (int j = 0; j < 3; ++j) std::swap(A[3 * k + j], A[3 * br + j]);
+      std::swap(c[k], c[br]);
+      std::swap(rp[k], rp[br]);
+    }
+    if (bc != k) {
+      for (int i = 0; i < 3; ++i) std::swap(A[3 * i + k], A[3 * i + bc]);
+      std::swap(cp[k], cp[bc]);
+    }
+    for (int i = k + 1; i < 3; ++i) A[3 * i + k] /= A[3 * k + k];
+    for (int i = k + 1; i < 3; ++i)
+      for (int j = k + 1; j < 3; ++j) A[3 * i + j] -= A[3 * i + k] * A[3 * k + j];
+  }
+  // rank: pivots above maxpivot * epsilon * 3
+  const float thr = maxpivot * (1.1920929e-7f * 3.0f);
+  int rank = 0;
+  for (int k = 0; k < nonzero; ++k) rank += std::fabs(A[3 * k + k]) > thr;
+  // forward substitution with the unit lower factor
+  for (int i = 1; i < 3; ++i)
+    for (int j = 0; j < i; ++j) c[i] -= A[3 * i + j] * c[j];
+  // back substitution on the leading rank x rank block of U
+  float y[3] = {0, 0, 0};
+  for (int i = rank - 1; i >= 0; --i) {
+    float acc = c[i];
+    for (int j = i + 1; j < rank; ++j) acc -= A[3 * i + j] * y[j];
+    y[i] = acc / A[3 * i + i];
+  }
+  for (int k = 0; k < 3; ++k) x[cp[k]] = y[k];
+  (void) rp;
+}
+
+// One landmark.  frames_*: tables of 12 floats per frame; hist_*: this landmark's n_meas measurements.
+// world_in_local_map12: LandmarkEstimatorBase_::setTransforms.  Returns isInlier; state_world / number_of_optimizations
+// / coords_in_local_map are updated exactly where the reference updates them.
+static inline bool landmark_smoother_update(const SmootherConfig& cfg, const float* frames_sensor_in_world,
+                                            const float* frames_world_in_sensor, const float* world_in_local_map12, int n_meas,
+                                            const int* hist_frame, const float* hist_uv, const float* hist_point_in_camera,
+                                            float* state_world, int* number_of_optimizations, float* coords_in_local_map) {
+  const float initial[3] = {state_world[0], state_world[1], state_world[2]};
+  float w[3] = {initial[0], initial[1], initial[2]};
+  auto mean_in_world = [&](float* out) {  // _setMeanCoordinatesInWorld (:137-146)
+    float acc[3] = {0, 0, 0};
+    for (int k = 0; k < n_meas; ++k) {
+      float p[3];
+      smoother_apply(frames_sensor_in_world + 12 * hist_frame[k], hist_point_in_camera + 3 * k, p);
+      for (int i = 0; i < 3; ++i) acc[i] += p[i];
+    }
+    for (int i = 0; i < 3; ++i) out[i] = acc[i] / (float) n_meas;
+  };
+  if ((unsigned) n_meas < cfg.minimum_number_of_measurements_for_optimization) {  // :29-43
+    mean_in_world(w);
+    const float d0 = w[0] - initial[0], d1 = w[1] - initial[1], d2 = w[2] - initial[2];
+    if ((d0 * d0 + d1 * d1) + d2 * d2 < cfg.maximum_distance_geometry_meters_squared) {
+      smoother_apply(world_in_local_map12, w, coords_in_local_map);
+      for (int i = 0; i < 3; ++i) state_world[i] = w[i];
+      *number_of_optimizations = n_meas;
+      return true;
+    }
+    return false;
+  }
+  const float* K = cfg.K;
+  float prev = 0;
+  int n_inliers = 0;
+  for (unsigned it = 0; it < cfg.maximum_number_of_iterations; ++it) {  // :49-123
+    float H[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, b[3] = {0, 0, 0}, total = 0;
+    int n_outliers = 0;
+    for (int k = 0; k < n_meas; ++k) {
+      const float* T = frames_world_in_sensor + 12 * hist_frame[k];
+      float cam[3];
+      smoother_apply(T, w, cam);
+      if (cam[2] <= 0) {
+        ++n_outliers;
+        continue;
+      }
+      float ph[3];
+      for (int i = 0; i < 3; ++i) ph[i] = (K[3 * i] * cam[0] + K[3 * i + 1] * cam[1]) + K[3 * i + 2] * cam[2];
+      const float c = ph[2], inv_c = 1.0f / c, inv_c2 = inv_c * inv_c;
+      const float e[3] = {ph[0] / c - hist_uv[2 * k], ph[1] / c - hist_uv[2 * k + 1], c - hist_point_in_camera[3 * k + 2]};
+      float om[3] = {1.0f, 1.0f, 10.0f};  // :56-57
+      const float e2 = (e[0] * om[0] * e[0] + e[1] * om[1] * e[1]) + e[2] * om[2] * e[2];
+      total += e2;
+      if (e2 > cfg.maximum_reprojection_error_pixels_squared) {  // saturated kernel (:80-84)
+        const float s = cfg.maximum_reprojection_error_pixels_squared / e2;
+        for (int i = 0; i < 3; ++i) om[i] *= s;
+        ++n_outliers;
+      }
+      float Jl[9], J[9];
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) Jl[3 * i + j] = (K[3 * i] * T[j] + K[3 * i + 1] * T[4 + j]) + K[3 * i + 2] * T[8 + j];  // K * R (:87)
+      const float a = -ph[0] * inv_c2, bb = -ph[1] * inv_c2;
+      for (int j = 0; j < 3; ++j) {
+        J[j] = inv_c * Jl[j] + a * Jl[6 + j];
+        J[3 + j] = inv_c * Jl[3 + j] + bb * Jl[6 + j];
+        J[6 + j] = Jl[6 + j];
+      }
+      for (int i = 0; i < 3; ++i) {
+        const float t0 = J[i] * om[0], t1 = J[3 + i] * om[1], t2 = J[6 + i] * om[2];  // row i of J^T Omega
+        for (int j = 0; j < 3; ++j) H[3 * i + j] += (t0 * J[j] + t1 * J[3 + j]) + t2 * J[6 + j];
+        b[i] += (t0 * e[0] + t1 * e[1]) + t2 * e[2];
+      }
+    }
+    const float nb[3] = {-b[0], -b[1], -b[2]};
+    float dx[3];
+    full_piv_lu_solve3(H, nb, dx);
+    for (int i = 0; i < 3; ++i) w[i] += dx[i];
+    n_inliers = n_meas - n_outliers;
+    if (std::fabs(total - prev) < cfg.convergence_criterion_minimum_chi2_delta) break;
+    prev = total;
+  }
+  bool inlier = false;
+  if (n_inliers > *number_of_optimizations) {  // :126-131
+    for (int i = 0; i < 3; ++i) state_world[i] = w[i];
+    *number_of_optimizations += 1;
+    inlier = true;
+  } else {  // :134-139
+    mean_in_world(w);
+    for (int i = 0; i < 3; ++i) state_world[i] = w[i];
+  }
+  smoother_apply(world_in_local_map12, w, coords_in_local_map);  // :142
+  return inlier;
 }
 
 }  // namespace pslam_oracle

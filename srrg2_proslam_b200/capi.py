@@ -89,6 +89,26 @@ def ekf_cfg(kind, K, baseline2, sensor_in_world, sensor_in_local_map, min_cov=0.
     return c
 
 
+class SmootherCfg(C.Structure):
+    """pslam_smoother_cfg"""
+    _fields_ = [("K", C.c_float * 9), ("maximum_number_of_iterations", C.c_uint),
+                ("convergence_criterion_minimum_chi2_delta", C.c_float), ("maximum_reprojection_error_pixels_squared", C.c_float),
+                ("minimum_number_of_measurements_for_optimization", C.c_uint), ("maximum_distance_geometry_meters_squared", C.c_float),
+                ("sensor_in_world", C.c_float * 12), ("sensor_in_local_map", C.c_float * 12)]
+
+
+def smoother_cfg(K, sensor_in_world, sensor_in_local_map, max_iterations=100, chi2_delta=1e-5, max_reproj2=100.0, min_measurements=3,
+                 max_dist2=1.0):
+    c = SmootherCfg()
+    c.K[:] = [float(x) for x in np.asarray(K, np.float32).reshape(9)]
+    c.maximum_number_of_iterations, c.minimum_number_of_measurements_for_optimization = int(max_iterations), int(min_measurements)
+    c.convergence_criterion_minimum_chi2_delta = float(chi2_delta)
+    c.maximum_reprojection_error_pixels_squared, c.maximum_distance_geometry_meters_squared = float(max_reproj2), float(max_dist2)
+    c.sensor_in_world[:] = [float(x) for x in np.asarray(sensor_in_world, np.float32).reshape(12)]
+    c.sensor_in_local_map[:] = [float(x) for x in np.asarray(sensor_in_local_map, np.float32).reshape(12)]
+    return c
+
+
 class LinearizeCfg(C.Structure):
     _fields_ = [("kind", C.c_int), ("K", C.c_double * 9), ("image_cols", C.c_double),
                 ("image_rows", C.c_double), ("baseline", C.c_double * 3), ("mean_disparity", C.c_double),
@@ -375,6 +395,24 @@ class Context:
                                                                  _p(loc), _p(inl)))
         assert k == int(inl.sum())
         return st, loc, inl.astype(bool)
+
+    def landmarks_smoother_update(self, K, frames_sensor_in_world, sensor_in_world, sensor_in_local_map, offsets, hist_frame, hist_uv,
+                                  hist_point_in_camera, state_world, n_opt, **kw):
+        """same signature as tests/oracle_lib.landmarks_smoother_update"""
+        st = np.ascontiguousarray(state_world, np.float32).reshape(-1, 3).copy()
+        n = len(st)
+        no = np.ascontiguousarray(n_opt, np.int32).reshape(n).copy()
+        fr = np.ascontiguousarray(frames_sensor_in_world, np.float32).reshape(-1, 12)
+        off = np.ascontiguousarray(offsets, np.int32).reshape(n + 1)
+        hf = np.ascontiguousarray(hist_frame, np.int32)
+        uv = np.ascontiguousarray(hist_uv, np.float32).reshape(len(hf), 2)
+        pic = np.ascontiguousarray(hist_point_in_camera, np.float32).reshape(len(hf), 3)
+        cfg = smoother_cfg(K, sensor_in_world, sensor_in_local_map, **kw)
+        loc, inl = np.zeros((n, 3), np.float32), np.zeros(n, np.uint8)
+        k = self._chk(lib().pslam_landmarks_smoother_update(self._h, n, _p(st), _p(no), len(fr), _p(fr), _p(off), _p(hf), _p(uv), _p(pic),
+                                                            C.byref(cfg), _p(loc), _p(inl)))
+        assert k == int(inl.sum())
+        return st, no, loc, inl.astype(bool)
 
     def bf_best2(self, desc_f, desc_m):
         desc_f = np.ascontiguousarray(desc_f, np.uint8).reshape(-1, 32)

@@ -923,6 +923,84 @@ int pslam_landmarks_weighted_mean_update(pslam_ctx* ctx, int n, float* state_wor
   return *h;
 }
 
+int pslam_landmarks_smoother_update(pslam_ctx* ctx, int n, float* state_world, int* number_of_optimizations, int n_frames,
+                                    const float* frames_sensor_in_world, const int* offsets, const int* hist_frame,
+                                    const float* hist_uv, const float* hist_point_in_camera, const pslam_smoother_cfg* cfg,
+                                    float* coords_in_local_map, uint8_t* inlier) {
+  if (!ctx || !cfg || n < 0 || n_frames < 0 ||
+      (n > 0 && (!state_world || !number_of_optimizations || !frames_sensor_in_world || !offsets || !hist_frame || !hist_uv ||
+                 !hist_point_in_camera || !coords_in_local_map || !inlier)))
+    return PSLAM_E_INVALID;
+  if (n == 0) return 0;
+  const int total = offsets[n];
+  if (offsets[0] != 0 || total < 0) return pslam_set_error(ctx, PSLAM_E_INVALID, "landmarks_smoother: offsets must start at 0", cudaSuccess);
+  for (int i = 0; i < n; ++i)
+    if (offsets[i + 1] < offsets[i]) return pslam_set_error(ctx, PSLAM_E_INVALID, "landmarks_smoother: offsets must not decrease", cudaSuccess);
+  for (int k = 0; k < total; ++k)
+    if (hist_frame[k] < 0 || hist_frame[k] >= n_frames) return pslam_set_error(ctx, PSLAM_E_INVALID, "landmarks_smoother: frame index out of range", cudaSuccess);
+  PSLAM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  // frames: world_in_sensor = sensor_in_world^-1 (what the measurements store, :16-19); current frame: world_in_local_map
+  std::vector<float> wis((size_t) 12 * n_frames);
+  auto invert = [](const float* T, float* inv) {
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) inv[4 * i + j] = T[4 * j + i];
+    for (int i = 0; i < 3; ++i) inv[4 * i + 3] = -((inv[4 * i] * T[3] + inv[4 * i + 1] * T[7]) + inv[4 * i + 2] * T[11]);
+  };
+  for (int f = 0; f < n_frames; ++f) invert(frames_sensor_in_world + 12 * f, wis.data() + 12 * f);
+  float cur_inv[12], wl[12];
+  invert(cfg->sensor_in_world, cur_inv);
+  const float* L = cfg->sensor_in_local_map;
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) wl[4 * i + j] = (L[4 * i] * cur_inv[j] + L[4 * i + 1] * cur_inv[4 + j]) + L[4 * i + 2] * cur_inv[8 + j];
+    wl[4 * i + 3] = ((L[4 * i] * cur_inv[3] + L[4 * i + 1] * cur_inv[7]) + L[4 * i + 2] * cur_inv[11]) + L[4 * i + 3];
+  }
+  auto al = [](size_t b) { return (b + 255) & ~(size_t) 255; };
+  const size_t b_fr = al((size_t) n_frames * 48), b_off = al((size_t) (n + 1) * 4), b_hf = al((size_t) total * 4), b_uv = al((size_t) total * 8),
+               b_pc = al((size_t) total * 12), b3 = al((size_t) n * 12), b1 = al((size_t) n * 4), bi = al((size_t) n);
+  if (PSLAM_SOLVER_SCRATCH_OFFSET + 256 + 2 * b_fr + b_off + b_hf + b_uv + b_pc + 2 * b3 + b1 + bi > ctx->scratch_bytes)
+    return pslam_set_error(ctx, PSLAM_E_CAPACITY, "landmarks_smoother: histories exceed the scratch buffer", cudaSuccess);
+  int* d_cnt = reinterpret_cast<int*>(ctx->d_scratch + PSLAM_SOLVER_SCRATCH_OFFSET);
+  uint8_t* p = ctx->d_scratch + PSLAM_SOLVER_SCRATCH_OFFSET + 256;
+  auto take = [&](size_t bytes) {
+    uint8_t* r = p;
+    p += bytes;
+    return r;
+  };
+  float* d_siw = reinterpret_cast<float*>(take(b_fr));
+  float* d_wis = reinterpret_cast<float*>(take(b_fr));
+  int* d_off = reinterpret_cast<int*>(take(b_off));
+  int* d_hf = reinterpret_cast<int*>(take(b_hf));
+  float* d_uv = reinterpret_cast<float*>(take(b_uv));
+  float* d_pc = reinterpret_cast<float*>(take(b_pc));
+  float* d_st = reinterpret_cast<float*>(take(b3));
+  float* d_loc = reinterpret_cast<float*>(take(b3));
+  int* d_no = reinterpret_cast<int*>(take(b1));
+  uint8_t* d_in = take(bi);
+  cudaStream_t s = ctx->stream;
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_siw, frames_sensor_in_world, (size_t) n_frames * 48, cudaMemcpyHostToDevice, s));
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_wis, wis.data(), (size_t) n_frames * 48, cudaMemcpyHostToDevice, s));
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_off, offsets, (size_t) (n + 1) * 4, cudaMemcpyHostToDevice, s));
+  if (total > 0) {
+    PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_hf, hist_frame, (size_t) total * 4, cudaMemcpyHostToDevice, s));
+    PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_uv, hist_uv, (size_t) total * 8, cudaMemcpyHostToDevice, s));
+    PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_pc, hist_point_in_camera, (size_t) total * 12, cudaMemcpyHostToDevice, s));
+  }
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_st, state_world, (size_t) n * 12, cudaMemcpyHostToDevice, s));
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_no, number_of_optimizations, (size_t) n * 4, cudaMemcpyHostToDevice, s));
+  PSLAM_CUDA_TRY(ctx, cudaMemsetAsync(d_loc, 0, (size_t) n * 12, s));
+  PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(s));  // `wis` is pageable host memory owned by this call
+  const int rc = pslam_k_landmarks_smoother(ctx, cfg, wl, n, d_siw, d_wis, d_off, d_hf, d_uv, d_pc, d_st, d_no, d_loc, d_in, d_cnt);
+  if (rc) return rc;
+  int* h = reinterpret_cast<int*>(ctx->h_pinned);
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(h, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, s));
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(state_world, d_st, (size_t) n * 12, cudaMemcpyDeviceToHost, s));
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(number_of_optimizations, d_no, (size_t) n * 4, cudaMemcpyDeviceToHost, s));
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(coords_in_local_map, d_loc, (size_t) n * 12, cudaMemcpyDeviceToHost, s));
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(inlier, d_in, (size_t) n, cudaMemcpyDeviceToHost, s));
+  PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  return *h;
+}
+
 // ---- stage 2b -----------------------------------------------------------------------------------
 static int bf_upload(pslam_ctx* ctx, int nf, const uint8_t* df, int nm, const uint8_t* dm,
                      uint32_t** d_f, uint32_t** d_m, size_t* used) {

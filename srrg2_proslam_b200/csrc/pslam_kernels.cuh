@@ -77,3 +77,9 @@ int pslam_k_landmarks_ekf(pslam_ctx* ctx, const pslam_ekf_cfg* cfg, long long n,
 int pslam_k_landmarks_weighted_mean(pslam_ctx* ctx, const float* sensor_in_world12, const float* sensor_in_local_map12, float max_dist2,
                                     long long n, float* d_state_world, const int* d_n_opt, const float* d_landmark_in_sensor,
                                     float* d_local, uint8_t* d_inlier, int* d_n_inliers);
+
+// k_smoother.cu (N3: LandmarkEstimatorPoseBasedSmoother)
+int pslam_k_landmarks_smoother(pslam_ctx* ctx, const pslam_smoother_cfg* cfg, const float* world_in_local_map12, int n,
+                               const float* d_frames_siw, const float* d_frames_wis, const int* d_offsets, const int* d_hist_frame,
+                               const float* d_hist_uv, const float* d_hist_pic, float* d_state_world, int* d_n_opt, float* d_local,
+                               uint8_t* d_inlier, int* d_n_inliers);

@@ -732,6 +732,28 @@ int LandmarkEstimatorWeightedMeanCUDA::computeBatch(int n, float* state_world, c
   return k;
 }
 
+int LandmarkEstimatorPoseBasedSmootherCUDA::computeBatch(int n, float* state_world, int* number_of_optimizations, int n_frames,
+                                                         const float* frames_sensor_in_world, const int* offsets, const int* hist_frame,
+                                                         const float* hist_uv, const float* hist_point_in_camera,
+                                                         float* coords_in_local_map, uint8_t* inlier) {
+  pslam_smoother_cfg cfg;
+  for (int i = 0; i < 9; ++i) cfg.K[i] = _K[i];
+  cfg.maximum_number_of_iterations = param_maximum_number_of_iterations.value();
+  cfg.convergence_criterion_minimum_chi2_delta = param_convergence_criterion_minimum_chi2_delta.value();
+  cfg.maximum_reprojection_error_pixels_squared = param_maximum_reprojection_error_pixels_squared.value();
+  cfg.minimum_number_of_measurements_for_optimization = param_minimum_number_of_measurements_for_optimization.value();
+  cfg.maximum_distance_geometry_meters_squared = param_maximum_distance_geometry_meters_squared.value();
+  for (int i = 0; i < 12; ++i) {
+    cfg.sensor_in_world[i] = _sensor_in_world.m[i];
+    cfg.sensor_in_local_map[i] = _sensor_in_local_map.m[i];
+  }
+  pslam_ctx* ctx = PslamDevice::context();
+  const int k = pslam_landmarks_smoother_update(ctx, n, state_world, number_of_optimizations, n_frames, frames_sensor_in_world, offsets,
+                                                hist_frame, hist_uv, hist_point_in_camera, &cfg, coords_in_local_map, inlier);
+  PslamDevice::check(k, "LandmarkEstimatorPoseBasedSmoother::compute");
+  return k;
+}
+
 // ---- aligner slice ----------------------------------------------------------------------------------------------
 AlignerSliceProcessorProjectiveCUDA::AlignerSliceProcessorProjectiveCUDA(int kind) : _kind(kind) {
   // aligner_slice_processor_projective.cpp:7-20: saturated robustifier with chi threshold 100^2 by default
@@ -956,6 +978,7 @@ void registerTypes() {
   reg<FilterK<1>>("ProjectiveDepthPointEKF3D");
   reg<FilterK<2>>("StereoProjectivePointEKF3D");
   for (const char* dims : {"2D3D", "3D3D", "4D3D"}) reg<LandmarkEstimatorWeightedMeanCUDA>(std::string("LandmarkEstimatorWeightedMean") + dims);
+  for (const char* dims : {"2D3D", "3D3D", "4D3D"}) reg<LandmarkEstimatorPoseBasedSmootherCUDA>(std::string("LandmarkEstimatorPoseBasedSmoother") + dims);
   reg<EstimatorK<0>>("LandmarkEstimatorProjectiveEKF3D");
   reg<EstimatorK<1>>("LandmarkEstimatorProjectiveDepthEKF3D");
   reg<EstimatorK<2>>("LandmarkEstimatorStereoProjectiveEKF3D");

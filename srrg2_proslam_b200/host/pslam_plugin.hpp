@@ -518,6 +518,32 @@ private:
   Isometry3f _sensor_in_world, _sensor_in_local_map;
 };
 
+// ---- LandmarkEstimatorPoseBasedSmoother_ (mapping/landmarks/landmark_estimator_pose_based_smoother.{h,cpp}) ----------
+class LandmarkEstimatorPoseBasedSmootherCUDA : public Configurable {
+public:
+  PARAM(PropertyUnsignedInt, maximum_number_of_iterations, "maximum number of LS iterations", 100, nullptr);
+  PARAM(PropertyFloat, convergence_criterion_minimum_chi2_delta, "convergence delta", 1e-5f, nullptr);
+  PARAM(PropertyFloat, maximum_reprojection_error_pixels_squared, "maximum kernel reprojection error (pixels squared)", 100, nullptr);
+  PARAM(PropertyUnsignedInt, minimum_number_of_measurements_for_optimization,
+        "minimum number of required measurements before optimizing (otherwise averaging)", 3, nullptr);
+  PARAM(PropertyFloat, maximum_distance_geometry_meters_squared,
+        "maximum distance in geometry (i.e. 3D point distance L2 norm) in meters squared", 1, nullptr);
+  void setCameraMatrix(const std::array<float, 9>& K) { _K = K; }
+  void setTransforms(const Isometry3f& measurement_in_world, const Isometry3f& measurement_in_scene) {
+    _sensor_in_world = measurement_in_world;
+    _sensor_in_local_map = measurement_in_scene;
+  }
+  // compute() for all correspondences of one merger pass; the measurement histories (current measurement included) are
+  // handed over in CSR form, see pslam_landmarks_smoother_update
+  int computeBatch(int n, float* state_world, int* number_of_optimizations, int n_frames, const float* frames_sensor_in_world,
+                   const int* offsets, const int* hist_frame, const float* hist_uv, const float* hist_point_in_camera,
+                   float* coords_in_local_map, uint8_t* inlier);
+
+private:
+  std::array<float, 9> _K{{0, 0, 0, 0, 0, 0, 0, 0, 0}};
+  Isometry3f _sensor_in_world, _sensor_in_local_map;
+};
+
 // registers every class above under the reference's names and under the ...CUDA names (idempotent)
 void registerTypes();
 

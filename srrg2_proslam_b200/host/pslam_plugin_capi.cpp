@@ -585,6 +585,7 @@ int psp_landmark_estimator_set_transforms(psp_module* estimator, const float* me
     std::memcpy(W.m, measurement_in_world12, sizeof(W.m));
     std::memcpy(S.m, measurement_in_scene12, sizeof(S.m));
     if (auto* wm = dynamic_cast<LandmarkEstimatorWeightedMeanCUDA*>(mod(estimator))) wm->setTransforms(W, S);
+    else if (auto* sm = dynamic_cast<LandmarkEstimatorPoseBasedSmootherCUDA*>(mod(estimator))) sm->setTransforms(W, S);
     else as<LandmarkEstimatorEKFCUDA>(estimator, "LandmarkEstimatorEKF")->setTransforms(W, S);
     return 0;
   });
@@ -603,6 +604,26 @@ int psp_landmark_estimator_weighted_mean_batch(psp_module* estimator, int n, flo
   return guard([&] {
     return as<LandmarkEstimatorWeightedMeanCUDA>(estimator, "LandmarkEstimatorWeightedMean")
       ->computeBatch(n, state_world, number_of_optimizations, landmark_in_sensor, coords_in_local_map, inlier);
+  });
+}
+
+int psp_landmark_smoother_set_camera_matrix(psp_module* estimator, const float* K9) {
+  return guard([&] {
+    std::array<float, 9> K;
+    std::memcpy(K.data(), K9, sizeof(float) * 9);
+    as<LandmarkEstimatorPoseBasedSmootherCUDA>(estimator, "LandmarkEstimatorPoseBasedSmoother")->setCameraMatrix(K);
+    return 0;
+  });
+}
+
+int psp_landmark_smoother_compute_batch(psp_module* estimator, int n, float* state_world, int* number_of_optimizations, int n_frames,
+                                        const float* frames_sensor_in_world, const int* offsets, const int* hist_frame,
+                                        const float* hist_uv, const float* hist_point_in_camera, float* coords_in_local_map,
+                                        uint8_t* inlier) {
+  return guard([&] {
+    return as<LandmarkEstimatorPoseBasedSmootherCUDA>(estimator, "LandmarkEstimatorPoseBasedSmoother")
+      ->computeBatch(n, state_world, number_of_optimizations, n_frames, frames_sensor_in_world, offsets, hist_frame, hist_uv,
+                     hist_point_in_camera, coords_in_local_map, inlier);
   });
 }
 

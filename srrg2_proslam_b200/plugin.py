@@ -243,6 +243,24 @@ class Module:
         k = _chk(lib().psp_landmark_estimator_weighted_mean_batch(self.h, n, _p(st), _p(no), _p(ls), _p(loc), _p(inl)))
         return st, loc, inl.astype(bool), k
 
+    def smoother_set_camera_matrix(self, K):
+        K = np.ascontiguousarray(K, np.float32).reshape(9)
+        _chk(lib().psp_landmark_smoother_set_camera_matrix(self.h, _p(K)))
+
+    def smoother_compute_batch(self, frames_sensor_in_world, offsets, hist_frame, hist_uv, hist_point_in_camera, state_world, n_opt):
+        st = np.ascontiguousarray(state_world, np.float32).reshape(-1, 3).copy()
+        n = len(st)
+        no = np.ascontiguousarray(n_opt, np.int32).reshape(n).copy()
+        fr = np.ascontiguousarray(frames_sensor_in_world, np.float32).reshape(-1, 12)
+        off = np.ascontiguousarray(offsets, np.int32).reshape(n + 1)
+        hf = np.ascontiguousarray(hist_frame, np.int32)
+        uv = np.ascontiguousarray(hist_uv, np.float32).reshape(len(hf), 2)
+        pic = np.ascontiguousarray(hist_point_in_camera, np.float32).reshape(len(hf), 3)
+        loc, inl = np.zeros((n, 3), np.float32), np.zeros(n, np.uint8)
+        _chk(lib().psp_landmark_smoother_compute_batch(self.h, n, _p(st), _p(no), len(fr), _p(fr), _p(off), _p(hf), _p(uv), _p(pic),
+                                                       _p(loc), _p(inl)))
+        return st, no, loc, inl.astype(bool)
+
     def aligner_set_moving_in_fixed(self, pose12):
         pose12 = np.ascontiguousarray(pose12, np.float32).reshape(12)
         _chk(lib().psp_aligner_set_moving_in_fixed(self.h, _p(pose12)))

@@ -65,3 +65,75 @@ def transitions(kind, n=100, sd_motion=0.0, sd_meas=0.0, seed=0):
         gt.append(p.copy())
         measure(p)
     return np.array(gt), np.array(T_noisy), np.array(mono), np.array(depth), np.array(stereo)
+
+
+# ---- the "LandmarkWorldNoNoise" scenario of tests/test_landmark_estimators.cpp:262-330 -----------------------------------
+K_WORLD = np.array([200, 0, 100, 0, 200, 100, 0, 0, 1], np.float32)  # projection_matrix (:268), canvas 200 x 200 (:269)
+BASELINE_WORLD_M = 0.5                                                # offset_second_sensor (:274)
+
+
+def landmark_world(n_points=1000, n_poses=10, seed=0):
+    """poses: sensor_in_world [n_poses][3][4] from the identity to a translation of (10, 10, 10) with a small deviation
+    (:277-281); points around (10, 10, 10) +- 10 (:283-285); per pose the visible points with their exact stereo
+    measurement (uL, vL, uR, vR) and their coordinates in the sensor frame."""
+    rng = np.random.default_rng(seed)
+    poses = []
+    for k in range(n_poses):
+        t = np.full(3, 10.0 * k / (n_poses - 1)) + (rng.normal(0, 0.01, 3) if k else 0)
+        poses.append(np.concatenate([np.eye(3), t.reshape(3, 1)], 1))
+    poses = np.array(poses, np.float32)
+    pts = (np.array([10, 10, 10]) + rng.uniform(-10, 10, (n_points, 3)) + np.array([0, 0, 12.0])).astype(np.float32)
+    K = K_WORLD.reshape(3, 3).astype(np.float64)
+    frames = []
+    for T in poses.astype(np.float64):
+        pc = (pts.astype(np.float64) - T[:, 3]) @ T[:, :3]
+        h = pc @ K.T
+        uv = h[:, :2] / h[:, 2:3]
+        vis = (pc[:, 2] > 0.5) & (uv[:, 0] >= 0) & (uv[:, 0] <= 200) & (uv[:, 1] >= 0) & (uv[:, 1] <= 200)
+        uvr = uv.copy()
+        uvr[:, 0] -= K[0, 0] * BASELINE_WORLD_M / pc[:, 2]
+        frames.append(dict(visible=np.flatnonzero(vis), stereo=np.concatenate([uv, uvr], 1).astype(np.float32),
+                           in_sensor=pc.astype(np.float32)))
+    return poses, pts, frames
+
+
+def unproject_world(uv, depth):
+    """LandmarkWorldNoNoise::getPointUnprojected (tests/test_landmark_estimators.cpp:349-358)"""
+    fx, fy, cx, cy = K_WORLD[0], K_WORLD[4], K_WORLD[2], K_WORLD[5]
+    d = depth.astype(np.float32)
+    return np.stack([d / fx * (uv[:, 0] - cx), d / fy * (uv[:, 1] - cy), d], 1).astype(np.float32)
+
+
+def run_smoother_scenario(update, n_points=1000, n_poses=10, seed=0):
+    """drives `update(K, frames_sensor_in_world, sensor_in_world, sensor_in_local_map, offsets, hist_frame, hist_uv,
+    hist_point_in_camera, state_world, n_opt)` like the reference test drives the estimator (:210-258): landmarks seeded
+    from the first frame with 1e-4 noise, every later frame re-observes its visible landmarks.  Returns (state, truth)."""
+    rng = np.random.default_rng(seed + 100)
+    poses, pts, frames = landmark_world(n_points, n_poses, seed)
+    ids = frames[0]["visible"]
+    lm_of = {int(p): i for i, p in enumerate(ids)}
+    in0 = frames[0]["in_sensor"][ids] + (1e-4 * rng.uniform(-1, 1, (len(ids), 3))).astype(np.float32)
+    state = (in0 @ poses[0][:, :3].T + poses[0][:, 3]).astype(np.float32)
+    n_opt = np.zeros(len(ids), np.int32)
+    hist = [[(0, frames[0]["stereo"][p, :2], frames[0]["in_sensor"][p])] for p in ids]
+    for f in range(1, n_poses):
+        sel = [lm_of[int(p)] for p in frames[f]["visible"] if int(p) in lm_of]
+        if not sel:
+            continue
+        pidx = ids[sel]
+        uv = frames[f]["stereo"][pidx, :2]
+        pic = unproject_world(uv, frames[f]["in_sensor"][pidx, 2])
+        for j, i in enumerate(sel):
+            hist[i].append((f, uv[j], pic[j]))
+        off = np.zeros(len(sel) + 1, np.int32)
+        hf, huv, hpc = [], [], []
+        for j, i in enumerate(sel):
+            off[j + 1] = off[j] + len(hist[i])
+            for (ff, a, b) in hist[i]:
+                hf.append(ff)
+                huv.append(a)
+                hpc.append(b)
+        st, no, loc, inl = update(K_WORLD, poses[:f + 1], poses[f], poses[f], off, np.array(hf, np.int32), np.array(huv, np.float32),
+                                  np.array(hpc, np.float32), state[sel], n_opt[sel])
+        state[sel], n_opt[sel] = st, no
+    return state, pts[ids], n_opt

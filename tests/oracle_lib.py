@@ -310,6 +310,27 @@ def landmarks_weighted_mean_update(sensor_in_world, sensor_in_local_map, state_w
     return st, loc, inl.astype(bool)
 
 
+def landmarks_smoother_update(K, frames_sensor_in_world, sensor_in_world, sensor_in_local_map, offsets, hist_frame, hist_uv,
+                              hist_point_in_camera, state_world, n_opt, max_iterations=100, chi2_delta=1e-5, max_reproj2=100.0,
+                              min_measurements=3, max_dist2=1.0):
+    """LandmarkEstimatorPoseBasedSmoother_::compute over n landmarks (landmark_estimator_pose_based_smoother_impl.cpp:6-148);
+    the histories (CSR) already contain the current measurement.  Returns (state_world, n_opt, coords_in_local_map, inlier)."""
+    st = np.ascontiguousarray(state_world, np.float32).reshape(-1, 3).copy()
+    n = len(st)
+    no = np.ascontiguousarray(n_opt, np.int32).reshape(n).copy()
+    fr = np.ascontiguousarray(frames_sensor_in_world, np.float32).reshape(-1, 12)
+    off = np.ascontiguousarray(offsets, np.int32).reshape(n + 1)
+    hf = np.ascontiguousarray(hist_frame, np.int32)
+    uv = np.ascontiguousarray(hist_uv, np.float32).reshape(len(hf), 2)
+    pic = np.ascontiguousarray(hist_point_in_camera, np.float32).reshape(len(hf), 3)
+    par = np.array([max_iterations, chi2_delta, max_reproj2, min_measurements, max_dist2], np.float32)
+    loc, inl = np.zeros((n, 3), np.float32), np.zeros(n, np.uint8)
+    f32 = lambda x, k: np.ascontiguousarray(x, np.float32).reshape(k)
+    lib().orc_landmarks_smoother_update(n, _p(f32(K, 9)), _p(par), len(fr), _p(fr), _p(f32(sensor_in_world, 12)),
+                                        _p(f32(sensor_in_local_map, 12)), _p(off), _p(hf), _p(uv), _p(pic), _p(st), _p(no), _p(loc), _p(inl))
+    return st, no, loc, inl.astype(bool)
+
+
 SHAPES = {"square": 0, "circle": 1, "rhombus": 2}
 
 

@@ -141,3 +141,81 @@ def test_conf_weighted_mean_module(oracle):
     g = est.estimator_weighted_mean_batch(state, n_opt, in_sensor)
     o = O.landmarks_weighted_mean_update(np.eye(3, 4), np.eye(3, 4), state, n_opt, in_sensor, max_dist2=100.0)
     assert np.array_equal(g[0], o[0]) and np.array_equal(g[1], o[1]) and np.array_equal(g[2], o[2]) and g[3] == int(o[2].sum())
+
+
+def test_smoother_no_noise_world_bit_exact(ctx):
+    """LandmarkWorldNoNoise / LandmarkEstimatorPoseBasedSmoother4D3D (tests/test_landmark_estimators.cpp:210-258): the GPU
+    runs the whole scenario with the SAME states as the CPU restatement in every frame (fp32, bit exact), and ends within
+    the reference's 1 mm of the true positions"""
+    calls = []
+
+    def both(*a):
+        g = ctx.landmarks_smoother_update(*a)
+        o = O.landmarks_smoother_update(*a)
+        for x, y in zip(g, o):
+            assert np.array_equal(x, y)
+        calls.append(int(g[3].sum()))
+        return g
+
+    state, truth, n_opt = F.run_smoother_scenario(both)
+    assert len(calls) == 9 and np.linalg.norm(state - truth, axis=1).max() < 1e-3 and n_opt.max() >= 3
+
+
+@pytest.mark.parametrize("n", [1, 300, 20000])
+def test_smoother_random_histories(ctx, n):
+    """ragged histories (1 .. 12 measurements), noisy observations, outliers that trip the saturated kernel, landmarks
+    behind a camera: every branch of the estimator, bit exact"""
+    rng = np.random.default_rng(n)
+    F_ = 12
+    frames = np.array([np.concatenate([F.rot(1, 0.02 * k) @ F.rot(0, 0.01 * k), np.array([[0.15 * k], [0.02 * k], [0.1 * k]])], 1)
+                       for k in range(F_)], np.float32)
+    truth = np.stack([rng.uniform(-4, 4, n), rng.uniform(-3, 3, n), rng.uniform(3, 25, n)], 1)
+    lens = rng.integers(1, 13, n)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    hf = np.concatenate([np.sort(rng.choice(F_, L, replace=False)) for L in lens]).astype(np.int32)
+    owner = np.repeat(np.arange(n), lens)
+    T = frames[hf].astype(np.float64)
+    pc = np.einsum("kij,kj->ki", T[:, :, :3].transpose(0, 2, 1), truth[owner] - T[:, :, 3])
+    pc += rng.normal(0, 0.02, pc.shape)
+    bad = rng.random(len(pc)) < 0.05
+    pc[bad] += rng.normal(0, 3.0, (int(bad.sum()), 3))
+    K = F.K_WORLD.reshape(3, 3).astype(np.float64)
+    h = pc @ K.T
+    uv = h[:, :2] / h[:, 2:3] + rng.normal(0, 0.4, (len(pc), 2))
+    state = (truth + rng.normal(0, 0.3, (n, 3))).astype(np.float32)
+    n_opt = rng.integers(0, 6, n).astype(np.int32)
+    args = (F.K_WORLD, frames, frames[-1], frames[-1], off, hf, uv.astype(np.float32), pc.astype(np.float32), state, n_opt)
+    kw = dict(max_dist2=0.3, max_reproj2=25.0)
+    g = ctx.landmarks_smoother_update(*args, **kw)
+    o = O.landmarks_smoother_update(*args, **kw)
+    for x, y in zip(g, o):
+        assert np.array_equal(x, y)
+    if n > 1000:
+        assert 0 < g[3].sum() < n
+
+
+def test_conf_smoother_module(oracle):
+    """kitti.conf "landmark_estimator_smoother" (LandmarkEstimatorPoseBasedSmoother4D3D, the estimator of merger_triangulation)
+    by class name with the file's parameters, driven through the no-noise scenario"""
+    import pathlib
+    from srrg2_proslam_b200 import plugin as P
+    m = P.Manager(pathlib.Path(__file__).resolve().parent / "golden" / "configurations" / "kitti_hotpath.conf")
+    est = m.get("landmark_estimator_smoother")
+    assert est.class_name == "LandmarkEstimatorPoseBasedSmoother4D3D" and not est.is_generic
+    assert est.get("maximum_number_of_iterations") == 100 and est.get("maximum_distance_geometry_meters_squared") == 100
+    est.smoother_set_camera_matrix(F.K_WORLD)
+    kw = dict(max_iterations=int(est.get("maximum_number_of_iterations")), chi2_delta=est.get("convergence_criterion_minimum_chi2_delta"),
+              max_reproj2=est.get("maximum_reprojection_error_pixels_squared"),
+              min_measurements=int(est.get("minimum_number_of_measurements_for_optimization")),
+              max_dist2=est.get("maximum_distance_geometry_meters_squared"))
+
+    def update(K, frames, siw, sil, off, hf, uv, pic, state, n_opt):
+        est.estimator_set_transforms(siw, sil)
+        g = est.smoother_compute_batch(frames, off, hf, uv, pic, state, n_opt)
+        o = O.landmarks_smoother_update(K, frames, siw, sil, off, hf, uv, pic, state, n_opt, **kw)
+        for x, y in zip(g, o):
+            assert np.array_equal(x, y)
+        return g
+
+    state, truth, n_opt = F.run_smoother_scenario(update, n_points=400)
+    assert np.linalg.norm(state - truth, axis=1).max() < 1e-3

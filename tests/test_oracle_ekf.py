@@ -99,3 +99,30 @@ def test_landmark_estimator_weighted_mean(oracle):
     far = in_sensor + np.array([0, 0, 50.0])
     s2, _, inl2 = O.landmarks_weighted_mean_update(cam, cam, state, n_opt, far, max_dist2=1.0)
     assert not inl2.any() and np.array_equal(s2, state)
+
+
+def test_pose_based_smoother_no_noise_world(oracle):
+    """LandmarkWorldNoNoise / LandmarkEstimatorPoseBasedSmoother4D3D (tests/test_landmark_estimators.cpp:210-258,332-347):
+    1000 points, 10 poses, exact observations -> every landmark state ends within 1 mm of its true world position"""
+    state, truth, n_opt = F.run_smoother_scenario(O.landmarks_smoother_update)
+    assert len(state) > 100
+    err = np.linalg.norm(state - truth, axis=1)
+    assert err.max() < 1e-3, err.max()
+    assert n_opt.max() >= 3  # the Gauss-Newton branch ran (three or more measurements)
+
+
+def test_full_piv_lu_and_rejection(oracle):
+    """a re-observation far from the landmark is averaged in but rejected by the geometric gate while the landmark has
+    fewer than three measurements (landmark_estimator_pose_based_smoother_impl.cpp:29-43)"""
+    poses = np.array([np.eye(3, 4), np.concatenate([np.eye(3), [[0.1], [0], [0]]], 1)], np.float32)
+    truth = np.array([[0.5, -0.2, 8.0]], np.float32)
+    off = np.array([0, 2], np.int32)
+    hf = np.array([0, 1], np.int32)
+    uv = np.array([[112.5, 95.0], [110.0, 95.0]], np.float32)
+    pic = np.array([[0.5, -0.2, 8.0], [0.4, -0.2, 80.0]], np.float32)  # second depth is absurd
+    st, no, loc, inl = O.landmarks_smoother_update(F.K_WORLD, poses, poses[1], poses[1], off, hf, uv, pic, truth, np.zeros(1, np.int32),
+                                                   max_dist2=1.0)
+    assert not inl[0] and np.array_equal(st, truth) and no[0] == 0
+    pic[1] = [0.4, -0.2, 8.0]
+    st, no, loc, inl = O.landmarks_smoother_update(F.K_WORLD, poses, poses[1], poses[1], off, hf, uv, pic, truth, np.zeros(1, np.int32))
+    assert inl[0] and no[0] == 2 and np.allclose(st, truth, atol=1e-5)

@@ -39,7 +39,8 @@ HOT_CLASSES = ["IntensityFeatureExtractorBinned2D", "IntensityFeatureExtractorBi
                "SceneClipperProjective3D", "LandmarkEstimatorProjectiveEKF3D", "LandmarkEstimatorProjectiveDepthEKF3D",
                "LandmarkEstimatorStereoProjectiveEKF3D", "ProjectivePointEKF3D", "ProjectiveDepthPointEKF3D",
                "StereoProjectivePointEKF3D", "LandmarkEstimatorWeightedMean2D3D", "LandmarkEstimatorWeightedMean3D3D",
-               "LandmarkEstimatorWeightedMean4D3D"]
+               "LandmarkEstimatorWeightedMean4D3D", "LandmarkEstimatorPoseBasedSmoother2D3D",
+               "LandmarkEstimatorPoseBasedSmoother3D3D", "LandmarkEstimatorPoseBasedSmoother4D3D"]
 HOT_CLASSES += [f"CorrespondenceFinderDescriptorBasedBruteforce{d}" for d in ("2D2D", "2D3D", "3D3D", "4D3D")]
 HOT_CLASSES += [f"CorrespondenceFinderProjective{s}{d}" for s in ("Square", "Circle", "Rhombus") for d in ("2D3D", "3D3D", "4D3D")]
 
@@ -162,7 +163,7 @@ def test_hotpath_fixtures_are_current(P, tmp_path):
     """the committed fixtures are what tools/make_golden.py derives from the unchanged files"""
     m = P.Manager(REF_CONF / "kitti.conf")
     m.write(tmp_path / "k.conf", ["adaptor_stereo_projective", "aligner", "cf_bruteforce", "clipper_stereo_projective", "landmark_estimator_ekf",
-                                 "landmark_estimator_weighted_mean"])
+                                 "landmark_estimator_weighted_mean", "landmark_estimator_smoother"])
     assert (tmp_path / "k.conf").read_text() == (GOLDEN / "kitti_hotpath.conf").read_text()
 
 

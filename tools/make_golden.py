@@ -51,7 +51,7 @@ from srrg2_proslam_b200 import plugin as P  # noqa: E402
 
 CONF = pathlib.Path("/root/reference/configurations")
 HOT = {"kitti": ["adaptor_stereo_projective", "aligner", "cf_bruteforce", "clipper_stereo_projective", "landmark_estimator_ekf",
-                 "landmark_estimator_weighted_mean"],
+                 "landmark_estimator_weighted_mean", "landmark_estimator_smoother"],
        "euroc": ["adaptor_stereo_projective", "aligner", "cf_bruteforce", "clipper_stereo_projective"],
        "icl": ["tracker_slice_processor_projective_depth", "aligner", "cf_bruteforce_2d", "cf_bruteforce_3d"]}
 (OUT / "configurations").mkdir(exist_ok=True)
