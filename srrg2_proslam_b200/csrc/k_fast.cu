@@ -42,40 +42,32 @@ constexpr unsigned K9 = 0x02000200u;  // bit 9 of both 16-bit lanes
 
 __host__ __device__ inline int score_pitch(int cols) { return (cols + 8 + 3) & ~3; }  // bytes per score-tile row: pixel column c at byte c + 4
 
-// ---- row load: 8 pixels starting at column x (any alignment), clamped into the row ------------------------
-// Split in two so that the loads of row r+1 are in flight while row r is processed: `issue` only emits the
-// (up to three) aligned 32-bit loads, `finish` funnel-shifts them into place one marching step later.
-struct Raw3 {
-  unsigned w0, w1, w2;
+// ---- row load: every lane fetches ONE naturally aligned 8-byte chunk ------------------------------------------
+// Image rows start at any byte (KITTI: 1241-byte pitch).  With a = row + warp * 256 + lane * 8 and d = a & 7 (the same
+// for every lane and warp of a row) the lane loads the chunk at a - d; its 8 pixels are bytes d .. d + 7 of (own chunk,
+// next lane's chunk), the next chunk comes by shuffle.  Only the strip-edge lanes load more: lane 0 the chunk before
+// (left halo), lane 31 the two chunks after.  Aligned chunks never straddle an allocation granule, so a chunk that
+// starts inside the image is always readable; chunks that would start behind the row's last pixel are clamped to the
+// chunk holding that pixel (their bytes belong to columns >= cols, which nothing uses).  Split in two so that the loads
+// of row r + 1 are in flight while row r is processed.
+struct RawQ {
+  uint2 q, e0, e1;
 };
-__device__ __forceinline__ Raw3 load8_issue(const uint8_t* __restrict__ row, int x, int cols) {
-  int xl = x < 0 ? 0 : x;
-  if (xl > cols - 8) xl = cols - 8;
-  const uint8_t* a = row + xl;
-  const unsigned s = (unsigned) (uintptr_t) a & 3u;
-  const unsigned* wp = reinterpret_cast<const unsigned*>(a - s);
-  Raw3 r;
-  r.w0 = __ldg(wp);
-  r.w1 = __ldg(wp + 1);
-  r.w2 = s ? __ldg(wp + 2) : 0u;  // when aligned the third word is not needed (and may be out of bounds)
-  return r;
-}
-// `tail` (warp-uniform) is true only in warps whose pixel range reaches past the right image edge
-__device__ __forceinline__ void load8_finish(const Raw3& r, const uint8_t* __restrict__ row, int x, int cols, bool tail,
-                                             unsigned& lo, unsigned& hi) {
-  int xl = x < 0 ? 0 : x;
-  if (tail && xl > cols - 8) xl = cols - 8;
-  const unsigned sh = ((unsigned) (uintptr_t) (row + xl) & 3u) * 8u;
-  lo = __funnelshift_r(r.w0, r.w1, sh);
-  hi = __funnelshift_r(r.w1, r.w2, sh);
-  if (tail) {
-    const int d = x - xl;  // > 0 only for lanes hanging over the right image edge: shift the valid bytes into place
-    if (d > 0) {
-      const unsigned long long v = d >= 8 ? 0ull : ((((unsigned long long) hi) << 32) | lo) >> (8 * d);
-      lo = (unsigned) v;
-      hi = (unsigned) (v >> 32);
-    }
+__device__ __forceinline__ RawQ loadq_issue(const uint8_t* __restrict__ row, int xw, int lane, bool has_left, int cols) {
+  const uint8_t* a = row + xw;
+  const uint8_t* c = a - ((uintptr_t) a & 7u);
+  const uint8_t* last = row + (cols - 1);
+  last -= (uintptr_t) last & 7u;
+  RawQ r;
+  r.e0 = r.e1 = make_uint2(0u, 0u);
+  const uint8_t* cc = c < last ? c : last;
+  r.q = __ldg(reinterpret_cast<const uint2*>(cc));
+  if (lane == 0 && has_left) r.e0 = __ldg(reinterpret_cast<const uint2*>(cc - 8));
+  if (lane == 31) {
+    r.e0 = __ldg(reinterpret_cast<const uint2*>(c + 8 < last ? c + 8 : last));
+    r.e1 = __ldg(reinterpret_cast<const uint2*>(c + 16 < last ? c + 16 : last));
   }
+  return r;
 }
 
 // ---- FAST score of one candidate, one polarity (bright: ring brighter than the centre) ---------------------
@@ -321,9 +313,7 @@ fast_blur_rows_kernel(const K1Args a) {
   const uint8_t* img = a.images + (size_t) image * a.image_pitch;
   uint8_t* blur = a.blur + (size_t) image * a.map_slot;
   const int x0 = warp * 256 + lane * 8;
-  const int xe = lane == 0 ? x0 - 8 : x0 + 8;  // strip-edge lanes fetch the neighbour strip's pixels themselves
-  const bool edge = lane == 0 || lane == 31;
-  const bool tail = warp * 256 + 256 + 16 > cols;  // some lane of this warp loads beyond cols - 8 (warp-uniform)
+  const bool has_left = warp > 0;  // lane 0 of strip 0 has no left halo (columns < 0)
 
   for (int i = tid; i < ((BH + 2) * SP + (BH + 2) * BW * 4) / 4; i += blockDim.x) reinterpret_cast<unsigned*>(smem)[i] = 0u;
   __syncthreads();
@@ -352,8 +342,7 @@ fast_blur_rows_kernel(const K1Args a) {
     return img + (size_t) yy * stride;
   };
   // software pipeline: the loads of the next row are issued one marching step ahead
-  Raw3 nx = load8_issue(row_ptr(by - 4), x0, cols), ne = {0u, 0u, 0u};
-  if (edge) ne = load8_issue(row_ptr(by - 4), xe, cols);
+  RawQ nx = loadq_issue(row_ptr(by - 4), x0, lane, has_left, cols);
 
   // one marching step per iteration: image row r enters the window at slot 6 (slot k holds row r - 6 + k).
   // The window is rotated with register moves instead of unrolling the loop 7x: the unrolled kernel (57 KB of
@@ -371,20 +360,23 @@ fast_blur_rows_kernel(const K1Args a) {
       H[k][3] = H[k + 1][3];
     }
     RowRegs& cur = R[6];
-    const uint8_t* rowp = row_ptr(r);
-    load8_finish(nx, rowp, x0, cols, tail, cur.a0, cur.a1);
-    cur.hl = __shfl_up_sync(FULL, cur.a1, 1);
-    cur.hr = __shfl_down_sync(FULL, cur.a0, 1);
-    if (edge) {
-      unsigned e0, e1;
-      load8_finish(ne, rowp, xe, cols, tail, e0, e1);
-      if (lane == 0) cur.hl = e1; else cur.hr = e0;
+    {
+      const unsigned d = (unsigned) (uintptr_t) (row_ptr(r) + x0) & 7u;  // uniform over the CTA
+      const bool hi = d >= 4u;
+      const unsigned sh = (d & 3u) * 8u;
+      uint2 qn;
+      qn.x = __shfl_down_sync(FULL, nx.q.x, 1);
+      qn.y = __shfl_down_sync(FULL, nx.q.y, 1);
+      if (lane == 31) qn = nx.e0;
+      const unsigned w0 = hi ? nx.q.y : nx.q.x, w1 = hi ? qn.x : nx.q.y, w2 = hi ? qn.y : qn.x;
+      cur.a0 = __funnelshift_r(w0, w1, sh);
+      cur.a1 = __funnelshift_r(w1, w2, sh);
+      cur.hl = __shfl_up_sync(FULL, cur.a1, 1);
+      cur.hr = __shfl_down_sync(FULL, cur.a0, 1);
+      if (lane == 0) cur.hl = hi ? __funnelshift_r(nx.q.x, nx.q.y, sh) : __funnelshift_r(nx.e0.y, nx.q.x, sh);
+      if (lane == 31) cur.hr = hi ? __funnelshift_r(nx.e0.y, nx.e1.x, sh) : __funnelshift_r(nx.e0.x, nx.e0.y, sh);
     }
-    if (step + 1 < n_steps) {
-      const uint8_t* nrow = row_ptr(r + 1);
-      nx = load8_issue(nrow, x0, cols);
-      if (edge) ne = load8_issue(nrow, xe, cols);
-    }
+    if (step + 1 < n_steps) nx = loadq_issue(row_ptr(r + 1), x0, lane, has_left, cols);
     hblur8(cur, H[6]);
     const int rc = r - 3;  // blur output row and FAST centre row
     if (rc >= by && rc < by + BH && rc < rows && store_ok) {
