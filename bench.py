@@ -415,7 +415,9 @@ def main():
         if tr.exists():
             t = json.loads(tr.read_text()).get(top)
             if t:
-                roofline["traffic"] = t.get("dram_bytes_per_launch")
+                # the capture was taken at `images_per_launch` images per launch: scale to this run's chunk size
+                per_image = t.get("dram_bytes_per_launch", 0) / max(t.get("images_per_launch", args.work_images), 1)
+                roofline["traffic"] = int(per_image * n_img / max(k["launches"], 1))
                 roofline["traffic_source"] = t.get("source")
 
     line = {"metric": "frontend_stereo_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world,
