@@ -295,10 +295,11 @@ __device__ __noinline__ unsigned long long push_and_drain(const uint8_t* img, ui
 
 __host__ __device__ inline int bits_pitch(int cols) { return (score_pitch(cols) + 31) / 32; }  // words / tile row
 
-// 3 CTAs of 5 warps per SM at KITTI width (registers).  The launcher sizes the band so that FOUR CTAs' shared memory
-// would fit: the smaller carve-out leaves ~90 KB instead of ~30 KB of L1 for the image rows the scorer re-reads
-// (measured: -3 % kernel time; a 96-register / 4-CTA build thrashes that L1 and spills, no gain).
-__global__ void __launch_bounds__(512)
+// 96 registers (no spills): 4 CTAs of 5 warps per SM at KITTI width, and the launcher sizes the band so that four CTAs'
+// shared memory fits as well (20 resident warps instead of 15: -3.5 % kernel time).  An earlier, fatter version of the
+// kernel (107-119 registers) spilled at this limit and thrashed the small L1 that 4 x 54 KB of shared memory leave
+// (hit rate 71 % -> 42 %); the aligned-chunk row loads and the SIMD scorer brought the footprint down.
+__global__ void __maxnreg__(96)
 fast_blur_rows_kernel(const K1Args a) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_strips = blockDim.x >> 5;
