@@ -38,6 +38,27 @@ MATCH = dict(max_dist=100.0, ratio=0.5, max_disp=100, thickness=0)   # kitti.con
 GEN_CHUNK = 250
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """the contract is ONE JSON line on stdout: libraries (NCCL prints its version banner there) get stderr instead"""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def clocks_sampler(stop, out, gpu_index):
     q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -110,7 +131,7 @@ def run_reference(args, rank, world):
                              "sample": f"{sample} stereo pairs of the workload per step (CPU generator, same seed)"},
             "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "mean_stereo_points_per_frame": float(np.mean(counts))}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, pairs):
@@ -271,6 +292,7 @@ def main():
         faulthandler.dump_traceback_later(float(os.environ["PSLAM_BENCH_WATCHDOG"]), exit=True)
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
 
+    quiet_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -510,7 +532,7 @@ def main():
                                 "sample": f"first {sample} stereo pairs of the same batch, {cdt:.1f} s, all host threads",
                                 "parity_counts_equal": bool(np.array_equal(ccounts, counts[:sample]))}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
