@@ -441,6 +441,8 @@ def main():
                 per_image = t.get("dram_bytes_per_launch", 0) / max(t.get("images_per_launch", args.work_images), 1)
                 roofline["traffic"] = int(per_image * n_img / max(k["launches"], 1))
                 roofline["traffic_source"] = t.get("source")
+                # why the HBM fraction is small: the kernel is instruction-issue bound (same ncu capture)
+                roofline["ncu"] = {k: t[k] for k in ("issue_active_pct", "alu_pipe_pct", "dram_throughput_pct", "registers", "ctas_per_sm") if k in t}
 
     line = {"metric": "frontend_stereo_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
