@@ -183,6 +183,23 @@ def tracking_lines(ctx, capi, stream, dev):
                       "inliers": int(r["num_inliers"]), "status": int(r["status"]),
                       "config": "kitti.conf aligner (MultiAligner3DQR -> AlignerSliceProcessorProjectiveStereo -> "
                                 "CorrespondenceFinderProjectiveCircle4D3D), KITTI 00 -> 01 of tests/golden, identity guess"}
+    try:  # the same alignment through the CPU oracle (C kernels driven by a Python loop, one thread) for context
+        O = oracle_lib()
+        base = (K.reshape(3, 3) @ np.array([-0.537166, 0, 0], np.float32)).astype(np.float32)
+        t_cpu = []
+        for rep in range(3):
+            of = O.ProjectiveFinder(K, 376, 1241, "circle", max_desc_dist=75, ratio=0.8, min_matching_ratio=0.1, min_desc_dist=25,
+                                    desc_step=5, max_radius=50, min_radius=10, radius_step=10, min_iterations=5,
+                                    max_change_norm=0.01, iters_per_projection=5)
+            of.set_fixed(meas[1]["uvuv"], meas[1]["desc"])
+            of.set_moving(xyz, meas[0]["desc"])
+            t0 = time.perf_counter()
+            O.align(of, "stereo", K, 376, 1241, meas[1]["uvuv"], xyz, [1, 2, 1], baseline=base, inverse_depth_weighting=True,
+                    chi_threshold=25.0, max_iterations=100, damping=1.0, min_num_inliers=6, min_num_correspondences=10)
+            t_cpu.append(time.perf_counter() - t0)
+        out["aligner"]["cpu_oracle_ms"] = 1e3 * float(np.median(t_cpu))
+    except Exception as e:
+        out["aligner"]["cpu_oracle_ms"] = repr(e)
     # batched H,b: one launch over 2^22 correspondences
     n = 1 << 22
     rng = np.random.default_rng(0)
