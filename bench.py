@@ -160,6 +160,17 @@ def tracking_lines(ctx, capi, stream, dev):
         e, mcfg = capi.extract_cfg(15, 1, 500), capi.match_cfg(50, 0.8, 100, 0)
         meas = [small.stereo_adaptor(ld(f"kitti_city_image_left_{i}.png"), ld(f"kitti_city_image_right_{i}.png"), e, mcfg) for i in (0, 1)]
         xyz, _, _ = small.triangulate(meas[0]["uvuv"], K, float(np.float32(718.856) * np.float32(0.537166)), 0.0)
+        # per-frame latency of the stereo adaptor (host images in, measurement cloud out: detect + describe L, R, match)
+        L1, R1 = ld("kitti_city_image_left_1.png"), ld("kitti_city_image_right_1.png")
+        e1k = capi.extract_cfg(15, 1, 1000)
+        ta = []
+        for rep in range(12):
+            t0 = time.perf_counter()
+            r1 = small.stereo_adaptor(L1, R1, e1k, capi.match_cfg(**MATCH))
+            ta.append(time.perf_counter() - t0)
+        out["adaptor"] = {"metric": "stereo_adaptor_ms_per_frame", "value": 1e3 * float(np.median(ta[2:])), "unit": "ms",
+                          "stereo_points": int(len(r1["uvuv"])),
+                          "config": "kitti.conf adaptor_stereo_projective on KITTI frame 01 of tests/golden (1241x376 pair, host pointers)"}
     finally:
         small.close()
     P.lib().psp_set_device(ctx.device)
