@@ -165,6 +165,7 @@ epipolar_kernel(const float2* __restrict__ xy, const uint32_t* __restrict__ desc
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ int s_warp[33];
   __shared__ int s_nruns;
+  __shared__ int s_next_run;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int pair = pair_base + blockIdx.x;
   const int imgL = 2 * pair, imgR = 2 * pair + 1;
@@ -230,9 +231,16 @@ epipolar_kernel(const float2* __restrict__ xy, const uint32_t* __restrict__ desc
       if (is_start) runs[n_runs + o] = (short) i;
       n_runs += total;
     }
+    if (tid == 0) s_next_run = 0;
     __syncthreads();
     if (nR > 0) {
-      for (int run = wid; run < n_runs; run += EP_THREADS / 32) {
+      // row runs are handed out dynamically (their cost varies with the row's population: with a static round-robin
+      // a quarter of the kernel's stall samples sat at the barrier below)
+      while (true) {
+        int run = 0;
+        if (lane == 0) run = atomicAdd(&s_next_run, 1);
+        run = __shfl_sync(0xffffffffu, run, 0);
+        if (run >= n_runs) break;
         const int i0 = runs[run];
         const int i1 = run + 1 < n_runs ? (int) runs[run + 1] : nL;
         const int row_left = rowL[i0] + off;
