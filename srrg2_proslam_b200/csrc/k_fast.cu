@@ -561,28 +561,59 @@ bin_select_kernel(const int* __restrict__ row_count, const uint32_t* __restrict_
     if (r < rend) {
       n_r = row_count[(size_t) image * max_rows + r];
       src = row_kp + ((size_t) image * max_rows + r) * row_cap;
-      for (int k = 0; k < n_r; ++k) {
-        const int c = (int) (src[k] >> 8);
-        if (c < cbegin) {
-          first = k + 1;
-          continue;
+      // four list entries per load (rows are 16-byte aligned and row_cap is a multiple of 4): the walk is a chain of
+      // dependent L2 accesses, a quarter as many now
+      bool done = false;
+      for (int k0 = 0; k0 < n_r && !done; k0 += 4) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + k0));
+        const uint32_t e4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int k = k0 + u;
+          if (done || k >= n_r) {
+            done = true;
+            continue;
+          }
+          const int c = (int) (e4[u] >> 8);
+          if (c < cbegin) {
+            first = k + 1;
+            continue;
+          }
+          if (c >= cend) {
+            done = true;
+            continue;
+          }
+          if (mask && ((mask[(size_t) r * mask_pitch + c] == 0) != (mask_invert != 0))) continue;
+          ++cnt;
         }
-        if (c >= cend) break;
-        if (mask && ((mask[(size_t) r * mask_pitch + c] == 0) != (mask_invert != 0))) continue;
-        ++cnt;
       }
     }
     int total;
     const int off = block_exclusive_scan<SEL_THREADS>(cnt, s_warp, &total);
     if (cnt) {
       int o = running + off;
-      for (int k = first; k < n_r; ++k) {
-        const uint32_t e = src[k];
-        const int c = (int) (e >> 8);
-        if (c >= cend) break;
-        if (mask && ((mask[(size_t) r * mask_pitch + c] == 0) != (mask_invert != 0))) continue;
-        if (o < max_raw_per_bin) seg[o] = ((uint32_t) (r * cols + c) << 8) | (e & 0xffu);
-        ++o;
+      bool done = false;
+      for (int k0 = first & ~3; k0 < n_r && !done; k0 += 4) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + k0));
+        const uint32_t e4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int k = k0 + u;
+          if (k < first) continue;
+          if (done || k >= n_r) {
+            done = true;
+            continue;
+          }
+          const uint32_t e = e4[u];
+          const int c = (int) (e >> 8);
+          if (c >= cend) {
+            done = true;
+            continue;
+          }
+          if (mask && ((mask[(size_t) r * mask_pitch + c] == 0) != (mask_invert != 0))) continue;
+          if (o < max_raw_per_bin) seg[o] = ((uint32_t) (r * cols + c) << 8) | (e & 0xffu);
+          ++o;
+        }
       }
     }
     running += total;
