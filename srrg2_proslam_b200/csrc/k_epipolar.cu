@@ -244,19 +244,30 @@ epipolar_kernel(const float2* __restrict__ xy, const uint32_t* __restrict__ desc
         const int i0 = runs[run];
         const int i1 = run + 1 < n_runs ? (int) runs[run + 1] : nL;
         const int row_left = rowL[i0] + off;
-        int lo = 0, hi = nR;  // first right feature with row >= row_left
-        while (lo < hi) {
-          const int mid = (lo + hi) >> 1;
-          if (rowR[mid] < row_left) lo = mid + 1; else hi = mid;
+        int s0, s1;
+        if (!GENERAL && oi == 0) {
+          // first pass of the pipeline path: the counting sort of the RIGHT side left its row starts in the scratch
+          // (nothing has been removed yet), no search needed
+          if (row_left < 0 || row_left >= EP_ROWS) continue;
+          const unsigned short* row_start = reinterpret_cast<const unsigned short*>(smem);
+          s0 = row_start[row_left];
+          s1 = row_start[row_left + 1];
+          if (s0 == s1) continue;
+        } else {
+          int lo = 0, hi = nR;  // first right feature with row >= row_left
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (rowR[mid] < row_left) lo = mid + 1; else hi = mid;
+          }
+          s0 = lo;
+          if (s0 >= nR || rowR[s0] != row_left) continue;
+          hi = nR;  // first right feature with row > row_left
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (rowR[mid] <= row_left) lo = mid + 1; else hi = mid;
+          }
+          s1 = lo;
         }
-        const int s0 = lo;
-        if (s0 >= nR || rowR[s0] != row_left) continue;
-        hi = nR;  // first right feature with row > row_left
-        while (lo < hi) {
-          const int mid = (lo + hi) >> 1;
-          if (rowR[mid] <= row_left) lo = mid + 1; else hi = mid;
-        }
-        const int s1 = lo;
         const int nr = s1 - s0;
         // right side: up to 32 features of the row live in registers (lane t <-> s0 + t); longer rows are read
         // from L1 / L2 per left feature, 32 candidates at a time
