@@ -333,16 +333,20 @@ epipolar_kernel(const float2* __restrict__ xy, const uint32_t* __restrict__ desc
                 if (__any_sync(0xffffffffu, disparity < 0)) break;
               }
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-              const int ob = __shfl_xor_sync(0xffffffffu, best, o), os = __shfl_xor_sync(0xffffffffu, second, o),
-                        op = __shfl_xor_sync(0xffffffffu, pos, o);
-              if (ob < best || (ob == best && op < pos)) {  // the other side wins (first position wins ties)
-                second = min(os, best);
-                best = ob;
-                pos = op;
+            // warp argmin with the reference's tie rule (equal distance: the first position wins) as ONE hardware
+            // reduction over (distance << 16 | position); the second best distance is the minimum over the other lanes'
+            // best and the winner lane's own second (REDUX.MIN; a 5-step shuffle butterfly cost 5x as many instructions)
+            {
+              const unsigned key = best == INT_MAX ? 0xffffffffu : (((unsigned) best << 16) | (unsigned) pos);
+              const unsigned kmin = __reduce_min_sync(0xffffffffu, key);
+              const unsigned other = (key == kmin) ? (unsigned) second : (unsigned) best;
+              const unsigned smin = __reduce_min_sync(0xffffffffu, other);
+              if (kmin == 0xffffffffu) {
+                best = INT_MAX;
               } else {
-                second = min(second, ob);
+                best = (int) (kmin >> 16);
+                pos = (int) (kmin & 0xffffu);
+                second = (int) smin;
               }
             }
             if (best == INT_MAX) continue;
