@@ -138,7 +138,7 @@ __device__ __forceinline__ void accumulate_correspondence(const LinParams& c, in
   }
 }
 
-__global__ void __launch_bounds__(LZ_THREADS)
+__global__ void __launch_bounds__(LZ_THREADS, 2)
 linearize_kernel(LinParams c, const double* __restrict__ moving_xyz,
                  const double* __restrict__ fixed_meas, int fixed_dim, int n_corr,
                  const int* __restrict__ corr_fixed, const int* __restrict__ corr_moving,
