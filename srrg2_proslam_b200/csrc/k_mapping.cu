@@ -54,7 +54,7 @@ __device__ __forceinline__ void spd_inverse(double* A) {
 }
 
 template <int E>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 landmarks_ekf_kernel(const EkfParams p, long long n, float* __restrict__ state_world, float* __restrict__ covariance,
                      const float* __restrict__ meas, float* __restrict__ coords_in_local_map, uint8_t* __restrict__ inlier,
                      int* __restrict__ n_inliers) {
