@@ -111,7 +111,7 @@ projective_search_kernel(ProjParams pp, const float* __restrict__ moving_xyz, in
     }
     return;
   }
-  if (lane == 0) atomicAdd(n_projected, 1);
+  if (lane == 0 && n_projected) atomicAdd(n_projected, 1);
   const int row = (short) roundf(v), col = (short) roundf(u);  // std::round -> int16
   const int r = pp.radius;
   const int row_min = (short) (row - r), row_max = (short) (row + r + 1);
@@ -172,53 +172,67 @@ projective_search_kernel(ProjParams pp, const float* __restrict__ moving_xyz, in
   }
 }
 
-// per fixed: lowest and second lowest response over its candidates in insertion order
-// (order key = 2 * moving_idx + {0 best, 1 second}); key = (dist << 32) | order
-__global__ void filter_min1_kernel(const int* __restrict__ cand, int n_moving,
-                                   unsigned long long* __restrict__ key1) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 2 * n_moving) return;
-  const int m = i >> 1, s = i & 1;
-  const int f = cand[4 * m + 2 * s];
-  if (f < 0) return;
-  const unsigned long long k = ((unsigned long long) (unsigned) cand[4 * m + 2 * s + 1] << 32) | (unsigned) i;
-  atomicMin(key1 + f, k);
-}
-__global__ void filter_min2_kernel(const int* __restrict__ cand, int n_moving,
-                                   const unsigned long long* __restrict__ key1,
-                                   unsigned long long* __restrict__ key2) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 2 * n_moving) return;
-  const int m = i >> 1, s = i & 1;
-  const int f = cand[4 * m + 2 * s];
-  if (f < 0) return;
-  const unsigned long long k = ((unsigned long long) (unsigned) cand[4 * m + 2 * s + 1] << 32) | (unsigned) i;
-  if (k != key1[f]) atomicMin(key2 + f, k);
-}
-// accepted[f] = moving index (>= 0) and dist, or -1
-__global__ void filter_accept_kernel(int n_fixed, const unsigned long long* __restrict__ key1,
-                                     const unsigned long long* __restrict__ key2, float max_dist,
-                                     float max_ratio, int* __restrict__ acc_moving,
-                                     float* __restrict__ acc_dist) {
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= n_fixed) return;
-  const unsigned long long a = key1[f], b = key2[f];
-  int res = -1;
-  float dist = 0;
-  if (a != ~0ULL) {
-    const float lowest = (float) (unsigned) (a >> 32);
-    const float second = (b != ~0ULL) ? (float) (unsigned) (b >> 32) : FLT_MAX;
-    if (lowest < max_dist && __fdiv_rn(lowest, second) < max_ratio) {  // base_impl.cpp:67-69
-      const unsigned order = (unsigned) (a & 0xffffffffu);
-      // bijectivity (:82-99): the moving point's own best candidate is its first entry
-      if ((order & 1u) == 0) {
-        res = (int) (order >> 1);
-        dist = lowest;
+// Filtering (_filterCorrespondences, projective_base_impl.cpp:39-102): per fixed point the lowest and second lowest
+// response over its candidates in insertion order (order key = 2 * moving_idx + {0 best, 1 second}; key = (dist << 32) |
+// order), Lowe's ratio + distance threshold, then bijectivity (the moving point's own best candidate is its first entry).
+// The three filter passes (+ the initialisation of their keys and the count of projected points) in ONE launch of one
+// CTA: per frame the finder is called ~20 times on a few hundred points, so the search is bound by launch and copy
+// latencies, not by work -- 3 memsets + 3 kernels + 4 copies became 1 kernel + 1 copy.  `out` is the contiguous block the
+// host downloads: [n_projected][acc_moving x n_fixed][acc_dist x n_fixed (float bits)][cand x 4 n_moving].
+constexpr int FF_THREADS = 1024;
+__global__ void __launch_bounds__(FF_THREADS)
+filter_fused_kernel(const int* __restrict__ cand, int n_moving, int n_fixed, unsigned long long* __restrict__ key1,
+                    unsigned long long* __restrict__ key2, float max_dist, float max_ratio, int* __restrict__ out) {
+  __shared__ int s_proj;
+  const int tid = threadIdx.x;
+  if (tid == 0) s_proj = 0;
+  for (int f = tid; f < n_fixed; f += FF_THREADS) {
+    key1[f] = ~0ULL;
+    key2[f] = ~0ULL;
+  }
+  __syncthreads();
+  int proj = 0;
+  for (int i = tid; i < 2 * n_moving; i += FF_THREADS) {  // pass 1: lowest response per fixed point
+    const int m = i >> 1, s = i & 1;
+    const int f = cand[4 * m + 2 * s];
+    if (s == 0 && f != -2) ++proj;  // -2 marks "not projected" (projective_search_kernel)
+    if (f < 0) continue;
+    const unsigned long long k = ((unsigned long long) (unsigned) cand[4 * m + 2 * s + 1] << 32) | (unsigned) i;
+    atomicMin(key1 + f, k);
+  }
+  if (proj) atomicAdd(&s_proj, proj);
+  __syncthreads();
+  for (int i = tid; i < 2 * n_moving; i += FF_THREADS) {  // pass 2: second lowest
+    const int m = i >> 1, s = i & 1;
+    const int f = cand[4 * m + 2 * s];
+    if (f < 0) continue;
+    const unsigned long long k = ((unsigned long long) (unsigned) cand[4 * m + 2 * s + 1] << 32) | (unsigned) i;
+    if (k != key1[f]) atomicMin(key2 + f, k);
+  }
+  __syncthreads();
+  if (tid == 0) out[0] = s_proj;
+  int* acc_moving = out + 1;
+  int* acc_dist = out + 1 + n_fixed;
+  for (int f = tid; f < n_fixed; f += FF_THREADS) {  // pass 3: thresholds + bijectivity
+    const unsigned long long a = key1[f], b = key2[f];
+    int res = -1;
+    float dist = 0;
+    if (a != ~0ULL) {
+      const float lowest = (float) (unsigned) (a >> 32);
+      const float second = (b != ~0ULL) ? (float) (unsigned) (b >> 32) : FLT_MAX;
+      if (lowest < max_dist && __fdiv_rn(lowest, second) < max_ratio) {  // base_impl.cpp:67-69
+        const unsigned order = (unsigned) (a & 0xffffffffu);
+        if ((order & 1u) == 0) {  // bijectivity (:82-99)
+          res = (int) (order >> 1);
+          dist = lowest;
+        }
       }
     }
+    acc_moving[f] = res;
+    acc_dist[f] = __float_as_int(dist);
   }
-  acc_moving[f] = res;
-  acc_dist[f] = dist;
+  int* cand_out = out + 1 + 2 * n_fixed;
+  for (int i = tid; i < 4 * n_moving; i += FF_THREADS) cand_out[i] = cand[i];
 }
 
 }  // namespace
@@ -316,35 +330,32 @@ int pslam_k_projective_match(pslam_ctx* ctx, int n_fixed, int n_moving, const fl
   pp.radius = cfg->search_radius_pixels;
   if (pp.radius < 0 || pp.radius > 16000)
     return pslam_set_error(ctx, PSLAM_E_INVALID, "projective: bad search radius", cudaSuccess);
-  PSLAM_CUDA_TRY(ctx, cudaMemsetAsync(st.d_key1, 0xff, 8 * (size_t) n_fixed, ctx->stream));
-  PSLAM_CUDA_TRY(ctx, cudaMemsetAsync(st.d_key2, 0xff, 8 * (size_t) n_fixed, ctx->stream));
-  PSLAM_CUDA_TRY(ctx, cudaMemsetAsync(st.d_nproj, 0, 4, ctx->stream));
   const size_t smem = sizeof(int) * (size_t) (pp.radius + 1);
   if (smem > 48 * 1024)
     PSLAM_CUDA_TRY(ctx, cudaFuncSetAttribute(projective_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   projective_search_kernel<<<(n_moving + PJ_WARPS - 1) / PJ_WARPS, PJ_WARPS * 32, smem, ctx->stream>>>(
-    pp, st.d_moving, n_moving, st.d_desc_moving, st.d_lattice, n_fixed, st.d_desc_fixed, st.d_cand,
-    st.d_nproj);
+    pp, st.d_moving, n_moving, st.d_desc_moving, st.d_lattice, n_fixed, st.d_desc_fixed, st.d_cand, nullptr);
   PSLAM_LAUNCH_CHECK(ctx, "projective_search_kernel");
-  const int nb = (2 * n_moving + 255) / 256;
-  filter_min1_kernel<<<nb, 256, 0, ctx->stream>>>(st.d_cand, n_moving, st.d_key1);
-  PSLAM_LAUNCH_CHECK(ctx, "filter_min1_kernel");
-  filter_min2_kernel<<<nb, 256, 0, ctx->stream>>>(st.d_cand, n_moving, st.d_key1, st.d_key2);
-  PSLAM_LAUNCH_CHECK(ctx, "filter_min2_kernel");
-  filter_accept_kernel<<<(n_fixed + 255) / 256, 256, 0, ctx->stream>>>(
-    n_fixed, st.d_key1, st.d_key2, cfg->descriptor_distance,
-    cfg->maximum_distance_ratio_to_second_best, st.d_acc_m, st.d_acc_d);
-  PSLAM_LAUNCH_CHECK(ctx, "filter_accept_kernel");
-
-  // D2H: per-moving candidate pairs (for the reference's output ORDER) and per-fixed decisions
-  std::vector<int> cand(4 * (size_t) n_moving), acc_m(n_fixed);
-  std::vector<float> acc_d(n_fixed);
-  int nproj = 0;
-  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(cand.data(), st.d_cand, 16 * (size_t) n_moving, cudaMemcpyDeviceToHost, ctx->stream));
-  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(acc_m.data(), st.d_acc_m, 4 * (size_t) n_fixed, cudaMemcpyDeviceToHost, ctx->stream));
-  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(acc_d.data(), st.d_acc_d, 4 * (size_t) n_fixed, cudaMemcpyDeviceToHost, ctx->stream));
-  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(&nproj, st.d_nproj, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  // one filter launch, one download (see filter_fused_kernel); the result block lives above the finder's cache partition
+  const size_t n_words = 1 + 2 * (size_t) n_fixed + 4 * (size_t) n_moving;
+  if (PSLAM_SOLVER_SCRATCH_OFFSET + 4 * n_words > ctx->scratch_bytes)
+    return pslam_set_error(ctx, PSLAM_E_CAPACITY, "projective: scratch too small for the result block", cudaSuccess);
+  int* d_out = reinterpret_cast<int*>(ctx->d_scratch + PSLAM_SOLVER_SCRATCH_OFFSET);
+  filter_fused_kernel<<<1, FF_THREADS, 0, ctx->stream>>>(st.d_cand, n_moving, n_fixed, st.d_key1, st.d_key2, cfg->descriptor_distance,
+                                                         cfg->maximum_distance_ratio_to_second_best, d_out);
+  PSLAM_LAUNCH_CHECK(ctx, "filter_fused_kernel");
+  std::vector<int> pageable;
+  int* h_out = reinterpret_cast<int*>(ctx->h_pinned);
+  if (4 * n_words > ctx->pinned_bytes) {
+    pageable.resize(n_words);
+    h_out = pageable.data();
+  }
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(h_out, d_out, 4 * n_words, cudaMemcpyDeviceToHost, ctx->stream));
   PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  const int nproj = h_out[0];
+  const int* acc_m = h_out + 1;
+  const float* acc_d = reinterpret_cast<const float*>(h_out + 1 + n_fixed);
+  const int* cand = h_out + 1 + 2 * (size_t) n_fixed;
   if (n_projected) *n_projected = nproj;
   // Output order of the reference = iteration order of
   //   std::unordered_map<size_t, CorrespondenceVector> reserved with fixed->size() and filled in
