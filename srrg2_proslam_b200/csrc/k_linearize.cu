@@ -451,25 +451,50 @@ int pslam_k_gn_iterate(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, int n_ite
   if (PSLAM_SOLVER_SCRATCH_OFFSET + b_mov + b_fix + 2 * b_cf + b_info + b_out + 256 > ctx->scratch_bytes)
     return pslam_set_error(ctx, PSLAM_E_CAPACITY, "gn_iterate: problem exceeds the scratch buffer", cudaSuccess);
   uint8_t* p = ctx->d_scratch + PSLAM_SOLVER_SCRATCH_OFFSET;
+  uint8_t* const d_in = p;
   double* d_mov = (double*) p; p += b_mov;
   double* d_fix = (double*) p; p += b_fix;
   int* d_cf = (int*) p; p += b_cf;
   int* d_cm = (int*) p; p += b_cf;
   double* d_info = (double*) p; p += b_info;
-  double* d_out = (double*) p; p += b_out;
-  int* d_done = (int*) p;
-  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_mov, h_moving_xyz, 24 * (size_t) n_moving, cudaMemcpyHostToDevice, ctx->stream));
-  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_fix, h_fixed_meas, 8 * (size_t) fixed_dim * n_fixed, cudaMemcpyHostToDevice, ctx->stream));
-  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_cf, h_corr_fixed, 4 * (size_t) n_corr, cudaMemcpyHostToDevice, ctx->stream));
-  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_cm, h_corr_moving, 4 * (size_t) n_corr, cudaMemcpyHostToDevice, ctx->stream));
-  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_info, h_info_diag, 24 * (size_t) n_fixed, cudaMemcpyHostToDevice, ctx->stream));
+  const size_t in_bytes = (size_t) (p - d_in);
+  int* d_done = (int*) p; p += 256;  // [iterations done, spd flag], directly in front of the per-iteration rows: one download
+  double* d_out = (double*) p;
+  const size_t out_bytes = 256 + 8 * (size_t) GN_OUT * n_iters;
+  // per frame this is called ~20 times on a few hundred points: the call is bound by copy / launch latencies.  The five
+  // inputs are packed into the pinned staging block and travel as ONE copy, the results come back as ONE copy.
+  uint8_t* h_stage = reinterpret_cast<uint8_t*>(ctx->h_pinned);
+  const bool packed = in_bytes + out_bytes <= ctx->pinned_bytes;
+  if (packed) {
+    memcpy(h_stage + ((uint8_t*) d_mov - d_in), h_moving_xyz, 24 * (size_t) n_moving);
+    memcpy(h_stage + ((uint8_t*) d_fix - d_in), h_fixed_meas, 8 * (size_t) fixed_dim * n_fixed);
+    memcpy(h_stage + ((uint8_t*) d_cf - d_in), h_corr_fixed, 4 * (size_t) n_corr);
+    memcpy(h_stage + ((uint8_t*) d_cm - d_in), h_corr_moving, 4 * (size_t) n_corr);
+    memcpy(h_stage + ((uint8_t*) d_info - d_in), h_info_diag, 24 * (size_t) n_fixed);
+    PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_in, h_stage, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  } else {
+    PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_mov, h_moving_xyz, 24 * (size_t) n_moving, cudaMemcpyHostToDevice, ctx->stream));
+    PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_fix, h_fixed_meas, 8 * (size_t) fixed_dim * n_fixed, cudaMemcpyHostToDevice, ctx->stream));
+    PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_cf, h_corr_fixed, 4 * (size_t) n_corr, cudaMemcpyHostToDevice, ctx->stream));
+    PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_cm, h_corr_moving, 4 * (size_t) n_corr, cudaMemcpyHostToDevice, ctx->stream));
+    PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_info, h_info_diag, 24 * (size_t) n_fixed, cudaMemcpyHostToDevice, ctx->stream));
+  }
   gn_iterate_kernel<<<1, LZ_THREADS, 0, ctx->stream>>>(c, damping, n_iters, d_mov, d_fix, fixed_dim, n_corr, d_cf, d_cm, d_info,
                                                       d_out, d_done);
   PSLAM_LAUNCH_CHECK(ctx, "gn_iterate_kernel");
-  int* h = reinterpret_cast<int*>(ctx->h_pinned);
-  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(h, d_done, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(h_out16, d_out, 8 * (size_t) GN_OUT * n_iters, cudaMemcpyDeviceToHost, ctx->stream));
-  PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  int h_small[2];
+  const int* h = h_small;
+  if (packed) {
+    uint8_t* h_res = h_stage + in_bytes;
+    PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(h_res, d_done, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    h = reinterpret_cast<const int*>(h_res);
+    memcpy(h_out16, h_res + 256, 8 * (size_t) GN_OUT * n_iters);
+  } else {
+    PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(h_small, d_done, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(h_out16, d_out, 8 * (size_t) GN_OUT * n_iters, cudaMemcpyDeviceToHost, ctx->stream));
+    PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
   const int done = h[0];
   *h_iters_done = done;
   *h_spd = h[1];
