@@ -684,8 +684,21 @@ int pslam_k_fast_blur(pslam_ctx* ctx, const uint8_t* d_images, long long image_p
     const int fit = (int) ((budget - fixed) / per_row) - 2;
     if (fit < bh_max) bh_max = fit;
   }
-  const int n_bands = (rows + bh_max - 1) / bh_max;
+  int n_bands = (rows + bh_max - 1) / bh_max;
   a.bh = (rows + n_bands - 1) / n_bands;
+  // latency mode: a launch over one or two images (the per-frame adaptor) would occupy a fraction of the SMs with long
+  // serial marches; shorter bands (>= 8 rows; each band re-computes 8 halo rows) put about one CTA on every SM instead
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+  if ((long long) n_images * n_bands < sms) {
+    const int want = (sms + n_images - 1) / n_images;
+    int bh = (rows + want - 1) / want;
+    if (bh < 8) bh = 8;
+    if (bh < a.bh) {
+      a.bh = bh;
+      n_bands = (rows + bh - 1) / bh;
+    }
+  }
   const size_t smem = (size_t) (a.bh + 2) * per_row + fixed;
   if (smem > ctx->k1_smem_set) {
     PSLAM_CUDA_TRY(ctx, cudaFuncSetAttribute(fast_blur_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
