@@ -83,7 +83,12 @@ assemble_features_kernel(const uint8_t* __restrict__ images, long long image_pit
 //     reassembled in registers).
 // ---------------------------------------------------------------------------------------------
 constexpr int K4_WARPS = 8;
-constexpr int PATCH = 31, PATCH_BOX_BYTES = PATCH * PSLAM_ORB_PATCH_PITCH, PATCH_BUF = 1536;
+// bit_pattern_31_ only reaches +-13 pixels (include/pslam_orb_pattern.h), so the box holds the 27 rows y - 13 .. y + 13:
+// rows y +- 14, 15 of the nominal 31 x 31 patch are never sampled and stay in L2 (the kernel is L2 bound: -13 % traffic).
+// The schedule's byte offsets are relative to row y - 15; dropping two rows shifts every sample by the same 96 bytes
+// (24 words), which rotates all banks alike and keeps the schedule conflict-free.
+constexpr int PATCH = 27, PATCH_ROW0 = 13, PATCH_SKIP = (15 - PATCH_ROW0) * PSLAM_ORB_PATCH_PITCH;
+constexpr int PATCH_BOX_BYTES = PATCH * PSLAM_ORB_PATCH_PITCH, PATCH_BUF = 1536;
 static_assert(PSLAM_ORB_PATCH_PITCH == 48, "the TMA box rows are 48 bytes: 15 bytes of alignment slack + 31 + 2");
 
 __constant__ signed char c_pattern[256 * 4];
@@ -144,7 +149,7 @@ orb_describe_kernel(const __grid_constant__ CUtensorMap tmap, const float2* __re
   int i = blockIdx.x * K4_WARPS + wid;
   if (i < n && lane == 0) {
     const float2 p = pxy[i];
-    tma_patch_load(&tmap, buf0, bar0, ((int) p.x - 15) & ~15, (int) p.y - 15, image);
+    tma_patch_load(&tmap, buf0, bar0, ((int) p.x - 15) & ~15, (int) p.y - PATCH_ROW0, image);
   }
   for (int k = 0; i < n; i += stride, ++k) {
     const int b = k & 1;
@@ -153,11 +158,11 @@ orb_describe_kernel(const __grid_constant__ CUtensorMap tmap, const float2* __re
     if (lane == 0 && i + stride < n) {
       const float2 p = pxy[i + stride];
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      tma_patch_load(&tmap, buf0 + (b ^ 1) * PATCH_BUF, bar0 + (b ^ 1) * 8, ((int) p.x - 15) & ~15, (int) p.y - 15, image);
+      tma_patch_load(&tmap, buf0 + (b ^ 1) * PATCH_BUF, bar0 + (b ^ 1) * 8, ((int) p.x - 15) & ~15, (int) p.y - PATCH_ROW0, image);
     }
     const int shift = ((int) pxy[i].x - 15) & 15;  // column of the patch inside the aligned box
     mbar_wait(bar0 + b * 8, (unsigned) (k >> 1) & 1u);
-    const uint8_t* patch8 = s_patch[wid][b] + shift;
+    const uint8_t* patch8 = s_patch[wid][b] + shift - PATCH_SKIP;  // offsets of the schedule start at row y - 15
     uint32_t byte = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
