@@ -109,3 +109,24 @@ def test_errors(ctx):
     big = np.zeros((700, 100), np.uint8)
     with pytest.raises(capi.PslamError):
         ctx.extract_binned(big, capi.extract_cfg(5, 1, 100))
+
+
+def test_strided_single_image(ctx):
+    """per-frame entry point with a row stride larger than the width: a view that still fits the staging slot travels as one
+    linear copy and is processed with its host stride, a wider one takes the 2-D re-pitching copy; same features either way"""
+    import ctypes as C
+    from srrg2_proslam_b200 import capi
+    img = O.load_gray("kitti_city_image_left_0.png")
+    rows, cols = img.shape
+    cfg, ocfg = capi.extract_cfg(15, 1, 1000), O.extract_cfg(15, 1, 1000)
+    want = O.extract_binned(img, ocfg)
+    for stride in (cols + 7, cols + 39, 2 * cols):  # 1248, 1280 (= the slot pitch), 2482 (does not fit the slot: 2-D copy)
+        buf = np.full((rows, stride), 255, np.uint8)
+        buf[:, :cols] = img
+        cap = ctx.limits.max_features
+        xy, resp = np.zeros((cap, 2), np.float32), np.zeros(cap, np.float32)
+        inten, desc = np.zeros(cap, np.float32), np.zeros((cap, 32), np.uint8)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        n = capi.lib().pslam_extract_binned(ctx._h, p(buf), rows, cols, stride, C.byref(cfg), None, cap, p(xy), p(resp), p(inten), p(desc))
+        assert n == len(want["xy"]), (stride, n)
+        assert np.array_equal(xy[:n], want["xy"]) and np.array_equal(desc[:n], want["desc"]) and np.array_equal(inten[:n], want["intensity"])
