@@ -19,6 +19,7 @@
 namespace {
 
 constexpr int EP_THREADS = 256;
+constexpr int EP_ROWS_LEAN = 512;   // lean variant: image rows <= 510 (KITTI 376, ICL / EuRoC 480)
 constexpr int EP_ROWS = 4096;  // counting-sort path: 0 <= row < EP_ROWS (the device pipeline: row < max_rows)
 
 // ---- (row, col) sort, general path: shared-memory bitonic sort of 64-bit keys (any 32-bit row, 16-bit col) ----
@@ -64,12 +65,13 @@ __device__ __forceinline__ void ep_sort_side(const float2* __restrict__ xy, int 
 
 // ---- (row, col) sort, pipeline path: counting sort by row + per-row insertion sort by column.  Keys are unique,
 // so the result is the order std::sort gives the reference (epipolar_impl.cpp:36-41).
-// hist / cursor: EP_ROWS + 1 unsigned shorts each; tmp: n uint32 ((col << 16) | idx)
+// hist / cursor: ROWS + 1 unsigned shorts each; tmp: n uint32 ((col << 16) | idx)
+template <int ROWS>
 __device__ __forceinline__ void ep_count_sort_side(const float2* __restrict__ xy, int n, unsigned short* hist,
                                                    unsigned short* cursor, uint32_t* tmp, short* row, short* col,
                                                    short* idx, int* s_warp) {
   const int tid = threadIdx.x;
-  for (int r = tid; r <= EP_ROWS; r += EP_THREADS) hist[r] = 0;
+  for (int r = tid; r <= ROWS; r += EP_THREADS) hist[r] = 0;
   __syncthreads();
   // 16-bit shared atomics do not exist: count into the aligned 32-bit word that holds the pair
   unsigned* hist32 = reinterpret_cast<unsigned*>(hist);
@@ -79,7 +81,7 @@ __device__ __forceinline__ void ep_count_sort_side(const float2* __restrict__ xy
   }
   __syncthreads();
   // exclusive scan over rows: EP_ROWS / EP_THREADS consecutive rows per thread
-  constexpr int PER = EP_ROWS / EP_THREADS;
+  constexpr int PER = ROWS / EP_THREADS;
   int local[PER], sum = 0;
 #pragma unroll
   for (int k = 0; k < PER; ++k) {
@@ -93,7 +95,7 @@ __device__ __forceinline__ void ep_count_sort_side(const float2* __restrict__ xy
     hist[tid * PER + k] = (unsigned short) (base + local[k]);  // start of row
     cursor[tid * PER + k] = (unsigned short) (base + local[k]);
   }
-  if (tid == 0) hist[EP_ROWS] = (unsigned short) total;
+  if (tid == 0) hist[ROWS] = (unsigned short) total;
   __syncthreads();
   unsigned* cur32 = reinterpret_cast<unsigned*>(cursor);
   for (int i = tid; i < n; i += EP_THREADS) {
@@ -154,7 +156,10 @@ __device__ __forceinline__ int ep_compact(short* row, short* col, short* idx, in
 // holds the descriptor of the run's t-th left and t-th right feature in registers (one round of loads per run);
 // the left features are visited in order, each lane scores "its" right candidate and a 5-step shuffle butterfly
 // yields (best, second, first position of the best) with the reference's tie rules.
-template <bool GENERAL>
+// LEAN (pipeline path, thickness 0, image rows <= EP_ROWS_LEAN - 2): one pass, so nothing is ever removed -- no used
+// flags, no row array of the right side after its sort, run starts bounded by the image height, and a histogram of
+// EP_ROWS_LEAN instead of EP_ROWS rows: 16 instead of 26 bytes of shared memory per feature, 3 instead of 2 CTAs per SM.
+template <bool GENERAL, bool LEAN>
 __global__ void __launch_bounds__(EP_THREADS)
 epipolar_kernel(const float2* __restrict__ xy, const uint32_t* __restrict__ desc,
                 const int* __restrict__ count, int M, float max_dist, float max_ratio, int max_disp,
@@ -172,21 +177,27 @@ epipolar_kernel(const float2* __restrict__ xy, const uint32_t* __restrict__ desc
   int nL = count[imgL], nR = count[imgR];
 
   // shared memory: [sort scratch] | rowL colL idxL rowR colR idxR | match dist | usedR usedL | runs
+  // LEAN:          [hist cursor]  | rowL colL idxL colR idxR | match (= rowR during the sorts) dist | runs[ROWS]
+  constexpr int ROWS = LEAN ? EP_ROWS_LEAN : EP_ROWS;
   int Pmax = 1;
   while (Pmax < M) Pmax <<= 1;
-  size_t scratch = GENERAL ? (size_t) Pmax * 8 : (size_t) (EP_ROWS + 2) * 2 * 2;
-  if (scratch < (size_t) M * 6) scratch = (size_t) M * 6;  // ep_compact needs 3 * M shorts (same rule as ep_smem_bytes)
+  size_t scratch = GENERAL ? (size_t) Pmax * 8 : (size_t) (ROWS + 2) * 2 * 2;
+  if (!LEAN && scratch < (size_t) M * 6) scratch = (size_t) M * 6;  // ep_compact needs 3 * M shorts (same rule as ep_smem_bytes)
+  scratch = (scratch + 15) & ~(size_t) 15;
   short* rowL = reinterpret_cast<short*>(smem + scratch);
   short* colL = rowL + M;
   short* idxL = colL + M;
-  short* rowR = idxL + M;
-  short* colR = rowR + M;
+  short* rowR = LEAN ? nullptr : idxL + M;
+  short* colR = LEAN ? idxL + M : rowR + M;
   short* idxR = colR + M;
   short* match = idxR + M;
   unsigned short* dist = reinterpret_cast<unsigned short*>(match + M);
-  unsigned char* usedR = reinterpret_cast<unsigned char*>(dist + M);
-  unsigned char* usedL = usedR + M;
-  short* runs = reinterpret_cast<short*>(usedL + M);  // [M] starts of the left row runs
+  unsigned char* usedR = LEAN ? nullptr : reinterpret_cast<unsigned char*>(dist + M);
+  unsigned char* usedL = LEAN ? nullptr : usedR + M;
+  short* runs = LEAN ? reinterpret_cast<short*>(dist + M) : reinterpret_cast<short*>(usedL + M);  // starts of the left row runs
+  // LEAN: the sort needs a row array per side and M words of `tmp`; tmp = (match, dist) as before, the right side's
+  // rows go to the tail of the run-start array's region, which is sized for them (ep_smem_bytes)
+  if (LEAN) rowR = runs;
 
   const float2* xyL = xy + (size_t) imgL * M;
   const float2* xyR = xy + (size_t) imgR * M;
@@ -201,10 +212,10 @@ epipolar_kernel(const float2* __restrict__ xy, const uint32_t* __restrict__ desc
     ep_sort_side(xyR, nR, P, keys, rowR, colR, idxR);
   } else {
     unsigned short* hist = reinterpret_cast<unsigned short*>(smem);
-    unsigned short* cursor = hist + EP_ROWS + 2;
+    unsigned short* cursor = hist + ROWS + 2;
     uint32_t* tmp = reinterpret_cast<uint32_t*>(match);  // match + dist = 4 M bytes, not in use yet
-    ep_count_sort_side(xyL, nL, hist, cursor, tmp, rowL, colL, idxL, s_warp);
-    ep_count_sort_side(xyR, nR, hist, cursor, tmp, rowR, colR, idxR, s_warp);
+    ep_count_sort_side<ROWS>(xyL, nL, hist, cursor, tmp, rowL, colL, idxL, s_warp);
+    ep_count_sort_side<ROWS>(xyR, nR, hist, cursor, tmp, rowR, colR, idxR, s_warp);
   }
 
   int* o_fixed = ep_fixed + (size_t) pair * M;
@@ -218,9 +229,10 @@ epipolar_kernel(const float2* __restrict__ xy, const uint32_t* __restrict__ desc
     const int off = (oi == 0) ? 0 : ((oi & 1) ? (oi + 1) / 2 : -(oi / 2));
     for (int i = tid; i < nL; i += EP_THREADS) {
       match[i] = -1;
-      usedL[i] = 0;
+      if (!LEAN) usedL[i] = 0;
     }
-    for (int i = tid; i < nR; i += EP_THREADS) usedR[i] = 0;
+    if (!LEAN)
+      for (int i = tid; i < nR; i += EP_THREADS) usedR[i] = 0;
     // ordered list of the left row-run starts
     int n_runs = 0;
     for (int base = 0; base < nL; base += EP_THREADS) {
@@ -248,7 +260,7 @@ epipolar_kernel(const float2* __restrict__ xy, const uint32_t* __restrict__ desc
         if (!GENERAL && oi == 0) {
           // first pass of the pipeline path: the counting sort of the RIGHT side left its row starts in the scratch
           // (nothing has been removed yet), no search needed
-          if (row_left < 0 || row_left >= EP_ROWS) continue;
+          if (row_left < 0 || row_left >= ROWS) continue;
           const unsigned short* row_start = reinterpret_cast<const unsigned short*>(smem);
           s0 = row_start[row_left];
           s1 = row_start[row_left + 1];
@@ -356,8 +368,10 @@ epipolar_kernel(const float2* __restrict__ xy, const uint32_t* __restrict__ desc
               if (lane == 0) {
                 match[jb + jj] = (short) pos;
                 dist[jb + jj] = (unsigned short) best;
-                usedL[jb + jj] = 1;
-                usedR[pos] = 1;
+                if (!LEAN) {
+                  usedL[jb + jj] = 1;
+                  usedR[pos] = 1;
+                }
               }
               ir = pos + 1;  // ordering constraint :181
             }
@@ -382,7 +396,7 @@ epipolar_kernel(const float2* __restrict__ xy, const uint32_t* __restrict__ desc
       }
       n_out += total;
     }
-    if (oi + 1 < n_offsets) {  // prune matched candidates, keeping the order (:189-205)
+    if (!LEAN && oi + 1 < n_offsets) {  // prune matched candidates, keeping the order (:189-205)
       __syncthreads();
       short* ctmp = reinterpret_cast<short*>(smem);  // the sort scratch holds >= 3 * M shorts (ep_smem_bytes)
       nL = ep_compact(rowL, colL, idxL, nL, usedL, ctmp, s_warp);
@@ -526,20 +540,26 @@ int pslam_k_pack_stereo(pslam_ctx* ctx, int n_pairs, pslam_packed_stereo* out) {
   return PSLAM_OK;
 }
 
-static size_t ep_smem_bytes(int M, bool general) {
+static size_t ep_smem_bytes(int M, bool general, bool lean) {
   int P = 1;
   while (P < M) P <<= 1;
+  if (lean) {  // hist + cursor | 5 coordinate arrays, match, dist (shorts) | run starts; the right rows use that last region
+    const size_t scratch = (((size_t) (EP_ROWS_LEAN + 2) * 2 * 2) + 15) & ~(size_t) 15;
+    return scratch + (size_t) M * (7 * 2) + (size_t) M * 2;
+  }
   // sort scratch (also the 3 * M shorts of ep_compact) | 6 coordinate arrays, match, dist (shorts) | usedR, usedL | runs
   size_t scratch = general ? (size_t) P * 8 : (size_t) (EP_ROWS + 2) * 2 * 2;
   if (scratch < (size_t) M * 6) scratch = (size_t) M * 6;
+  scratch = (scratch + 15) & ~(size_t) 15;
   return scratch + (size_t) M * (8 * 2 + 2 + 2);
 }
 
 int pslam_k_epipolar(pslam_ctx* ctx, int n_pairs, const pslam_match_cfg* cfg, int general, int pair_base) {
   const int M = ctx->lim.max_features;
   if (ctx->lim.max_rows > EP_ROWS) general = 1;
-  const size_t smem = ep_smem_bytes(M, general != 0);
-  auto kernel = general ? epipolar_kernel<true> : epipolar_kernel<false>;
+  const bool lean = !general && cfg->epipolar_line_thickness_pixels == 0 && ctx->lim.max_rows <= EP_ROWS_LEAN - 2;
+  const size_t smem = ep_smem_bytes(M, general != 0, lean);
+  auto kernel = general ? epipolar_kernel<true, false> : (lean ? epipolar_kernel<false, true> : epipolar_kernel<false, false>);
   if (smem > 48 * 1024) PSLAM_CUDA_TRY(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   kernel<<<n_pairs, EP_THREADS, smem, ctx->stream>>>(
     ctx->d_xy, ctx->d_desc, ctx->d_count, M, cfg->maximum_descriptor_distance,
