@@ -282,6 +282,37 @@ int pslam_landmarks_smoother_update(pslam_ctx* ctx, int n, float* state_world, i
                                     const float* hist_uv, const float* hist_point_in_camera, const pslam_smoother_cfg* cfg,
                                     float* coords_in_local_map, uint8_t* inlier);
 
+/* MergerProjective_::compute binning (.../mapping/mergers/merger_projective_impl.cpp:8-171 update pass, :194-309
+ * _addPoints), the step that decides WHICH correspondences update their landmark and WHICH measurements become new
+ * landmarks; the per-landmark update itself is pslam_landmarks_*_update above, the triangulation of the additions
+ * pslam_triangulate.  measurements [n_meas][dim]: dim 4 = stereo (uL, vL, uR, vR), dim 3 = (u, v, depth); a measurement's
+ * bin is (round(v / (canvas_rows / number_of_row_bins)), round(u / (canvas_cols / number_of_col_bins))) (:82-83), bins
+ * form an (number_of_row_bins + 1) x (number_of_col_bins + 1) grid; a bin outside it (the reference asserts it cannot
+ * happen, :84-85) returns PSLAM_E_INVALID.  Decisions are identical to the reference's sequential walk, bit for bit. */
+enum { PSLAM_MERGER_BASE = 0,     /* _isBetterForAddition = false (merger_projective.h:89-92): first arrival keeps the bin */
+       PSLAM_MERGER_STEREO = 1,   /* larger disparity uL - uR wins (merger_projective_rigid_stereo_impl.cpp:42-52) */
+       PSLAM_MERGER_DEPTH = 2 };  /* smaller depth wins (merger_projective_depth_ekf_impl.cpp:44-52) */
+typedef struct pslam_merger_cfg {
+  int canvas_rows, canvas_cols;                 /* param_projector: canvas_rows / canvas_cols */
+  int number_of_row_bins, number_of_col_bins;   /* PARAM, defaults 10 / 30 */
+  float maximum_distance_appearance;            /* PARAM, default 50 */
+  int enable_binning;                           /* MergerCorrespondence_ PARAM enable_binning */
+  int kind;                                     /* PSLAM_MERGER_* */
+} pslam_merger_cfg;
+/* number of 32-bit words of the blocked-bin bitmap (bit = bin_row * (number_of_col_bins + 1) + bin_col) */
+int pslam_merger_occupancy_words(const pslam_merger_cfg* cfg);
+/* update pass (:61-135): selected[c] = 1 where the reference calls _updatePoint for correspondence c (appearance gate
+ * passed, bin not yet blocked by an earlier correspondence); occupied_bins receives the blocked bins for the addition
+ * pass.  corr_moving[c] = measurement index, corr_response[c] = matching distance.  Returns the number selected. */
+int pslam_merger_select_updates(pslam_ctx* ctx, const float* measurements, int dim, int n_meas, const int* corr_moving,
+                                const float* corr_response, int n_corr, const pslam_merger_cfg* cfg, uint8_t* selected,
+                                uint32_t* occupied_bins);
+/* addition pass (:205-253): winners[k] = measurement index of the k-th entry of the reference's points_in_image_to_add
+ * (one per free bin, in order of the bin's first arrival, the occupant chosen by _isBetterForAddition); occupied_bins
+ * may be NULL (no correspondences: nothing is blocked).  winners has room for n_meas entries.  Returns their number. */
+int pslam_merger_select_additions(pslam_ctx* ctx, const float* measurements, int dim, int n_meas, const pslam_merger_cfg* cfg,
+                                  const uint32_t* occupied_bins, int* winners);
+
 /* ---- stage 2b: exhaustive Hamming matching --------------------------------------
  * Replaces CorrespondenceFinderDescriptorBasedBruteforce::compute
  *   (.../correspondence_finders/correspondence_finder_descriptor_based_bruteforce_impl.cpp:6-294).

@@ -698,4 +698,50 @@ void orc_pose_mul_f64(const double* a12, const double* b12, double* out12) {
   pose_to(pose_from(a12) * pose_from(b12), out12);
 }
 
+
+// MergerProjective_::compute binning.  cfg7 = canvas rows, canvas cols, row bins, col bins, enable_binning, kind, (unused);
+// the blocked bins travel as a bitmap over the (row bins + 1) x (col bins + 1) grid, bit = bin_row * (col bins + 1) + bin_col
+// (-1 when a bin leaves that grid: the reference asserts it cannot, merger_projective_impl.cpp:84-85)
+static MergerConfig merger_cfg_from(const int* cfg6, float max_dist) {
+  MergerConfig m;
+  m.canvas_rows = cfg6[0];
+  m.canvas_cols = cfg6[1];
+  m.number_of_row_bins = (unsigned) cfg6[2];
+  m.number_of_col_bins = (unsigned) cfg6[3];
+  m.enable_binning = cfg6[4] != 0;
+  m.kind = cfg6[5];
+  m.maximum_distance_appearance = max_dist;
+  return m;
+}
+
+int orc_merger_select_updates(const int* cfg6, float max_dist, const float* meas, int dim, const int* corr_moving,
+                              const float* corr_response, int n_corr, unsigned char* selected, unsigned* occupied_words, int n_words) {
+  const MergerConfig cfg = merger_cfg_from(cfg6, max_dist);
+  MergerBinMap occupied;
+  const int n = merger_select_updates(cfg, meas, dim, corr_moving, corr_response, n_corr, selected, occupied);
+  for (int w = 0; w < n_words; ++w) occupied_words[w] = 0;
+  for (const auto& row : occupied)
+    for (const auto& col : row.second) {
+      if (row.first > cfg.number_of_row_bins || col.first > cfg.number_of_col_bins) return -1;
+      const size_t b = row.first * (cfg.number_of_col_bins + 1) + col.first;
+      occupied_words[b >> 5] |= 1u << (b & 31);
+    }
+  return n;
+}
+
+int orc_merger_select_additions(const int* cfg6, const float* meas, int dim, int n_meas, const unsigned* occupied_words, int* winners) {
+  const MergerConfig cfg = merger_cfg_from(cfg6, 0.f);
+  MergerBinMap occupied;
+  if (occupied_words)
+    for (size_t r = 0; r <= cfg.number_of_row_bins; ++r)
+      for (size_t c = 0; c <= cfg.number_of_col_bins; ++c) {
+        const size_t b = r * (cfg.number_of_col_bins + 1) + c;
+        if ((occupied_words[b >> 5] >> (b & 31)) & 1u) occupied[r][c] = 0;
+      }
+  std::vector<int> w;
+  merger_select_additions(cfg, meas, dim, n_meas, occupied, w);
+  for (size_t k = 0; k < w.size(); ++k) winners[k] = w[k];
+  return (int) w.size();
+}
+
 }  // extern "C"

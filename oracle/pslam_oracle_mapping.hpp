@@ -15,7 +15,9 @@
 #pragma once
 #include <cmath>
 #include <cstring>
+#include <unordered_map>
 #include <utility>
+#include <vector>
 
 namespace pslam_oracle {
 
@@ -377,6 +379,95 @@ static inline bool landmark_smoother_update(const SmootherConfig& cfg, const flo
   }
   smoother_apply(world_in_local_map12, w, coords_in_local_map);  // :142
   return inlier;
+}
+
+// -----------------------------------------------------------------------------
+// MergerProjective_::compute binning  (.../mapping/mergers/merger_projective_impl.cpp)
+//   the sequential walk of the reference, map of maps included: which correspondences reach _updatePoint (:61-135)
+//   and which measurements form points_in_image_to_add (:205-253).  Measurements are [n][dim] floats, dim 4 = stereo
+//   (uL, vL, uR, vR), dim 3 = (u, v, depth).
+// -----------------------------------------------------------------------------
+enum MergerKind { MERGER_BASE = 0, MERGER_STEREO = 1, MERGER_DEPTH = 2 };
+
+struct MergerConfig {
+  int canvas_rows = 0, canvas_cols = 0;                   // param_projector (merger_projective.h:36-40)
+  unsigned number_of_row_bins = 10, number_of_col_bins = 30;  // merger_projective.h:46-55
+  float maximum_distance_appearance = 50;                 // merger_projective.h:41-45
+  bool enable_binning = true;                             // MergerCorrespondence_ (srrg2_slam_interfaces)
+  int kind = MERGER_STEREO;
+};
+
+using MergerBinMap = std::unordered_map<size_t, std::unordered_map<size_t, size_t>>;  // merger_projective.h:11-12
+
+// merger_projective.h:89-92 / merger_projective_rigid_stereo_impl.cpp:42-52 / merger_projective_depth_ekf_impl.cpp:44-52
+static inline bool merger_is_better_for_addition(int kind, const float* a, const float* b) {
+  if (kind == MERGER_STEREO) return (a[0] - a[2]) > (b[0] - b[2]);
+  if (kind == MERGER_DEPTH) return a[2] < b[2];
+  return false;
+}
+
+// update pass (:61-135): selected[c] = the reference reaches _updatePoint for correspondence c.  Returns their number.
+static inline int merger_select_updates(const MergerConfig& cfg, const float* meas, int dim, const int* corr_moving,
+                                        const float* corr_response, int n_corr, unsigned char* selected, MergerBinMap& occupied) {
+  const float row_w = static_cast<float>(cfg.canvas_rows) / static_cast<float>(cfg.number_of_row_bins);  // :31-34
+  const float col_w = static_cast<float>(cfg.canvas_cols) / static_cast<float>(cfg.number_of_col_bins);
+  int n = 0;
+  for (int c = 0; c < n_corr; ++c) {
+    selected[c] = 0;
+    if (corr_response[c] > cfg.maximum_distance_appearance) continue;  // :72-75
+    const size_t index_measurement = (size_t) corr_moving[c];
+    const float* m = meas + index_measurement * dim;
+    const size_t bin_row = std::round(m[1] / row_w), bin_col = std::round(m[0] / col_w);  // :82-83
+    if (cfg.enable_binning) {  // :88-121
+      auto it_row = occupied.find(bin_row);
+      if (it_row != occupied.end()) {
+        if (it_row->second.find(bin_col) == it_row->second.end()) it_row->second.insert(std::make_pair(bin_col, index_measurement));
+        else continue;  // skip multiple merges in the same bin
+      } else {
+        std::unordered_map<size_t, size_t> column_candidates;
+        column_candidates.insert(std::make_pair(bin_col, index_measurement));
+        occupied.insert(std::make_pair(bin_row, column_candidates));
+      }
+    }
+    selected[c] = 1;  // :125 _updatePoint
+    ++n;
+  }
+  return n;
+}
+
+// addition pass (:205-253): the source measurement of every entry of points_in_image_to_add, in its order
+static inline void merger_select_additions(const MergerConfig& cfg, const float* meas, int dim, int n_meas, const MergerBinMap& occupied,
+                                           std::vector<int>& winners) {
+  winners.clear();
+  if (!cfg.enable_binning) {  // :250-253
+    for (int i = 0; i < n_meas; ++i) winners.push_back(i);
+    return;
+  }
+  const float row_w = static_cast<float>(cfg.canvas_rows) / static_cast<float>(cfg.number_of_row_bins);
+  const float col_w = static_cast<float>(cfg.canvas_cols) / static_cast<float>(cfg.number_of_col_bins);
+  MergerBinMap addition;
+  for (int i = 0; i < n_meas; ++i) {
+    const float* m = meas + (size_t) i * dim;
+    const size_t bin_row = std::round(m[1] / row_w), bin_col = std::round(m[0] / col_w);  // :215-216
+    auto it_tracked = occupied.find(bin_row);  // :221-227
+    if (it_tracked != occupied.end() && it_tracked->second.find(bin_col) != it_tracked->second.end()) continue;
+    auto it_row = addition.find(bin_row);
+    if (it_row != addition.end()) {
+      auto it_col = it_row->second.find(bin_col);
+      if (it_col != it_row->second.end()) {
+        const size_t slot = it_col->second;  // :233-240: replace the occupant when the candidate is better
+        if (merger_is_better_for_addition(cfg.kind, m, meas + (size_t) winners[slot] * dim)) winners[slot] = i;
+      } else {
+        it_row->second.insert(std::make_pair(bin_col, winners.size()));
+        winners.push_back(i);
+      }
+    } else {
+      std::unordered_map<size_t, size_t> column_candidates;
+      column_candidates.insert(std::make_pair(bin_col, winners.size()));
+      addition.insert(std::make_pair(bin_row, column_candidates));
+      winners.push_back(i);
+    }
+  }
 }
 
 }  // namespace pslam_oracle

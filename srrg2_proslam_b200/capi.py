@@ -73,6 +73,20 @@ class EkfCfg(C.Structure):
                 ("sensor_in_local_map", C.c_float * 12)]
 
 
+class MergerCfg(C.Structure):
+    """pslam_merger_cfg"""
+    _fields_ = [("canvas_rows", C.c_int), ("canvas_cols", C.c_int), ("number_of_row_bins", C.c_int), ("number_of_col_bins", C.c_int),
+                ("maximum_distance_appearance", C.c_float), ("enable_binning", C.c_int), ("kind", C.c_int)]
+
+
+MERGER_KINDS = {"base": 0, "stereo": 1, "depth": 2}
+
+
+def merger_cfg(canvas_rows, canvas_cols, row_bins=10, col_bins=30, max_distance_appearance=50.0, enable_binning=True, kind="stereo"):
+    return MergerCfg(int(canvas_rows), int(canvas_cols), int(row_bins), int(col_bins), float(max_distance_appearance),
+                     int(bool(enable_binning)), MERGER_KINDS[kind])
+
+
 EKF_KINDS = {"projective": 0, "projective_depth": 1, "stereo": 2}
 EKF_DIMS = {"projective": 2, "projective_depth": 3, "stereo": 4}
 
@@ -413,6 +427,29 @@ class Context:
                                                             C.byref(cfg), _p(loc), _p(inl)))
         assert k == int(inl.sum())
         return st, no, loc, inl.astype(bool)
+
+    def merger_select_updates(self, cfg, measurements, corr_moving, corr_response):
+        """MergerProjective_::compute update pass: (selected[n_corr] bool, blocked-bin bitmap words)"""
+        m = np.ascontiguousarray(measurements, np.float32)
+        m = m.reshape(-1, m.shape[-1] if m.ndim == 2 else 4)
+        mv = np.ascontiguousarray(corr_moving, np.int32).reshape(-1)
+        rs = np.ascontiguousarray(corr_response, np.float32).reshape(len(mv))
+        sel = np.zeros(len(mv), np.uint8)
+        occ = np.zeros(self._chk(lib().pslam_merger_occupancy_words(C.byref(cfg))), np.uint32)
+        k = self._chk(lib().pslam_merger_select_updates(self._h, _p(m), m.shape[1], len(m), _p(mv), _p(rs), len(mv), C.byref(cfg), _p(sel),
+                                                        _p(occ)))
+        assert k == int(sel.sum())
+        return sel.astype(bool), occ
+
+    def merger_select_additions(self, cfg, measurements, occupied=None):
+        """MergerProjective_::_addPoints binning: source measurement index of every addition candidate, in order"""
+        m = np.ascontiguousarray(measurements, np.float32)
+        m = m.reshape(-1, m.shape[-1] if m.ndim == 2 else 4)
+        win = np.zeros(max(len(m), 1), np.int32)
+        occ = None if occupied is None else np.ascontiguousarray(occupied, np.uint32)
+        k = self._chk(lib().pslam_merger_select_additions(self._h, _p(m), m.shape[1], len(m), C.byref(cfg),
+                                                          None if occ is None else _p(occ), _p(win)))
+        return win[:k].copy()
 
     def bf_best2(self, desc_f, desc_m):
         desc_f = np.ascontiguousarray(desc_f, np.uint8).reshape(-1, 32)

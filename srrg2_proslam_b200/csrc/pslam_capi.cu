@@ -942,6 +942,103 @@ int pslam_landmarks_weighted_mean_update(pslam_ctx* ctx, int n, float* state_wor
   return *h;
 }
 
+// ---- N3: MergerProjective_::compute binning ------------------------------------------------------------------
+static int merger_cfg_ok(const pslam_merger_cfg* cfg, int dim) {
+  if (!cfg || (dim != 3 && dim != 4) || cfg->number_of_row_bins < 1 || cfg->number_of_col_bins < 1 || cfg->canvas_rows < 1 ||
+      cfg->canvas_cols < 1 || cfg->kind < PSLAM_MERGER_BASE || cfg->kind > PSLAM_MERGER_DEPTH ||
+      (cfg->kind == PSLAM_MERGER_STEREO && dim != 4))
+    return 0;
+  // "row / col bin width must be at least 1 pixel" (merger_projective_impl.cpp:36-47)
+  if ((float) cfg->canvas_rows / (float) cfg->number_of_row_bins < 1 || (float) cfg->canvas_cols / (float) cfg->number_of_col_bins < 1)
+    return 0;
+  return 1;
+}
+
+int pslam_merger_occupancy_words(const pslam_merger_cfg* cfg) {
+  if (!cfg || cfg->number_of_row_bins < 1 || cfg->number_of_col_bins < 1) return PSLAM_E_INVALID;
+  const long long bins = (long long) (cfg->number_of_row_bins + 1) * (cfg->number_of_col_bins + 1);
+  return (int) ((bins + 31) / 32);
+}
+
+int pslam_merger_select_updates(pslam_ctx* ctx, const float* measurements, int dim, int n_meas, const int* corr_moving,
+                                const float* corr_response, int n_corr, const pslam_merger_cfg* cfg, uint8_t* selected,
+                                uint32_t* occupied_bins) {
+  if (!ctx || !merger_cfg_ok(cfg, dim) || n_meas < 0 || n_corr < 0 || !occupied_bins || (n_meas > 0 && !measurements) ||
+      (n_corr > 0 && (!corr_moving || !corr_response || !selected)))
+    return PSLAM_E_INVALID;
+  const int n_words = pslam_merger_occupancy_words(cfg);
+  if ((size_t) n_words * 32 * 12 > 200 * 1024)
+    return pslam_set_error(ctx, PSLAM_E_CAPACITY, "merger: bin grid does not fit shared memory", cudaSuccess);
+  if (n_corr == 0) {
+    for (int w = 0; w < n_words; ++w) occupied_bins[w] = 0;
+    return 0;
+  }
+  PSLAM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  auto al = [](size_t b) { return (b + 255) & ~(size_t) 255; };
+  const size_t bm = al((size_t) n_meas * dim * 4), bc = al((size_t) n_corr * 4), bs = al((size_t) n_corr), bw = al((size_t) n_words * 4);
+  if (PSLAM_SOLVER_SCRATCH_OFFSET + 256 + bm + 2 * bc + bs + bw > ctx->scratch_bytes)
+    return pslam_set_error(ctx, PSLAM_E_CAPACITY, "merger: too many measurements for the scratch buffer", cudaSuccess);
+  int* d_res = reinterpret_cast<int*>(ctx->d_scratch + PSLAM_SOLVER_SCRATCH_OFFSET);
+  uint8_t* p = ctx->d_scratch + PSLAM_SOLVER_SCRATCH_OFFSET + 256;
+  float* d_meas = reinterpret_cast<float*>(p);
+  p += bm;
+  int* d_mv = reinterpret_cast<int*>(p);
+  p += bc;
+  float* d_rs = reinterpret_cast<float*>(p);
+  p += bc;
+  uint8_t* d_sel = p;
+  p += bs;
+  unsigned* d_occ = reinterpret_cast<unsigned*>(p);
+  if (n_meas > 0)
+    PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_meas, measurements, (size_t) n_meas * dim * 4, cudaMemcpyHostToDevice, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_mv, corr_moving, (size_t) n_corr * 4, cudaMemcpyHostToDevice, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_rs, corr_response, (size_t) n_corr * 4, cudaMemcpyHostToDevice, ctx->stream));
+  const int rc = pslam_k_merger_select_updates(ctx, cfg, d_meas, dim, n_meas, d_mv, d_rs, n_corr, d_sel, d_occ, n_words, d_res);
+  if (rc) return rc;
+  int* h = reinterpret_cast<int*>(ctx->h_pinned);
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(h, d_res, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(selected, d_sel, (size_t) n_corr, cudaMemcpyDeviceToHost, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(occupied_bins, d_occ, (size_t) n_words * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (h[1]) return pslam_set_error(ctx, PSLAM_E_INVALID, "merger: measurement outside the bin grid / correspondence index out of range", cudaSuccess);
+  return h[0];
+}
+
+int pslam_merger_select_additions(pslam_ctx* ctx, const float* measurements, int dim, int n_meas, const pslam_merger_cfg* cfg,
+                                  const uint32_t* occupied_bins, int* winners) {
+  if (!ctx || !merger_cfg_ok(cfg, dim) || n_meas < 0 || (n_meas > 0 && (!measurements || !winners))) return PSLAM_E_INVALID;
+  if (n_meas == 0) return 0;
+  const int n_words = pslam_merger_occupancy_words(cfg);
+  if ((size_t) n_words * 32 * 12 > 200 * 1024)
+    return pslam_set_error(ctx, PSLAM_E_CAPACITY, "merger: bin grid does not fit shared memory", cudaSuccess);
+  PSLAM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  auto al = [](size_t b) { return (b + 255) & ~(size_t) 255; };
+  const size_t bm = al((size_t) n_meas * dim * 4), bi = al((size_t) n_meas * 4), bw = al((size_t) n_words * 4);
+  if (PSLAM_SOLVER_SCRATCH_OFFSET + 256 + bm + bi + bw > ctx->scratch_bytes)
+    return pslam_set_error(ctx, PSLAM_E_CAPACITY, "merger: too many measurements for the scratch buffer", cudaSuccess);
+  int* d_res = reinterpret_cast<int*>(ctx->d_scratch + PSLAM_SOLVER_SCRATCH_OFFSET);
+  uint8_t* p = ctx->d_scratch + PSLAM_SOLVER_SCRATCH_OFFSET + 256;
+  float* d_meas = reinterpret_cast<float*>(p);
+  p += bm;
+  int* d_win = reinterpret_cast<int*>(p);
+  p += bi;
+  unsigned* d_occ = reinterpret_cast<unsigned*>(p);
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_meas, measurements, (size_t) n_meas * dim * 4, cudaMemcpyHostToDevice, ctx->stream));
+  if (occupied_bins)
+    PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_occ, occupied_bins, (size_t) n_words * 4, cudaMemcpyHostToDevice, ctx->stream));
+  const int rc = pslam_k_merger_select_additions(ctx, cfg, d_meas, dim, n_meas, occupied_bins ? d_occ : nullptr, d_win, d_res);
+  if (rc) return rc;
+  int* h = reinterpret_cast<int*>(ctx->h_pinned);
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(h, d_res, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (h[1]) return pslam_set_error(ctx, PSLAM_E_INVALID, "merger: measurement outside the bin grid", cudaSuccess);
+  if (h[0] > 0) {
+    PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(winners, d_win, (size_t) h[0] * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return h[0];
+}
+
 int pslam_landmarks_smoother_update(pslam_ctx* ctx, int n, float* state_world, int* number_of_optimizations, int n_frames,
                                     const float* frames_sensor_in_world, const int* offsets, const int* hist_frame,
                                     const float* hist_uv, const float* hist_point_in_camera, const pslam_smoother_cfg* cfg,

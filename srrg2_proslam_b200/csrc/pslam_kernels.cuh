@@ -78,6 +78,13 @@ int pslam_k_landmarks_weighted_mean(pslam_ctx* ctx, const float* sensor_in_world
                                     long long n, float* d_state_world, const int* d_n_opt, const float* d_landmark_in_sensor,
                                     float* d_local, uint8_t* d_inlier, int* d_n_inliers);
 
+// k_merger.cu (N3: MergerProjective_::compute binning)
+int pslam_k_merger_select_updates(pslam_ctx* ctx, const pslam_merger_cfg* cfg, const float* d_meas, int dim, int n_meas,
+                                  const int* d_corr_moving, const float* d_corr_response, int n_corr, unsigned char* d_selected,
+                                  unsigned* d_occupied, int n_words, int* d_result);
+int pslam_k_merger_select_additions(pslam_ctx* ctx, const pslam_merger_cfg* cfg, const float* d_meas, int dim, int n_meas,
+                                    const unsigned* d_occupied, int* d_winners, int* d_result);
+
 // k_smoother.cu (N3: LandmarkEstimatorPoseBasedSmoother)
 int pslam_k_landmarks_smoother(pslam_ctx* ctx, const pslam_smoother_cfg* cfg, const float* world_in_local_map12, int n,
                                const float* d_frames_siw, const float* d_frames_wis, const int* d_offsets, const int* d_hist_frame,

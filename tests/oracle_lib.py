@@ -331,6 +331,42 @@ def landmarks_smoother_update(K, frames_sensor_in_world, sensor_in_world, sensor
     return st, no, loc, inl.astype(bool)
 
 
+MERGER_KINDS = {"base": 0, "stereo": 1, "depth": 2}
+
+
+def _merger_cfg6(canvas_rows, canvas_cols, row_bins, col_bins, enable_binning, kind):
+    return np.array([canvas_rows, canvas_cols, row_bins, col_bins, int(bool(enable_binning)), MERGER_KINDS[kind]], np.int32)
+
+
+def merger_select_updates(measurements, corr_moving, corr_response, canvas_rows, canvas_cols, row_bins=10, col_bins=30,
+                          max_distance_appearance=50.0, enable_binning=True, kind="stereo"):
+    """MergerProjective_::compute update pass (merger_projective_impl.cpp:61-135), the sequential walk:
+    (selected[n_corr] bool, blocked-bin bitmap words)"""
+    m = np.ascontiguousarray(measurements, np.float32)
+    mv = np.ascontiguousarray(corr_moving, np.int32).reshape(-1)
+    rs = np.ascontiguousarray(corr_response, np.float32).reshape(len(mv))
+    sel = np.zeros(max(len(mv), 1), np.uint8)
+    occ = np.zeros(((row_bins + 1) * (col_bins + 1) + 31) // 32, np.uint32)
+    k = lib().orc_merger_select_updates(_p(_merger_cfg6(canvas_rows, canvas_cols, row_bins, col_bins, enable_binning, kind)),
+                                        C.c_float(max_distance_appearance), _p(m), m.shape[1], _p(mv), _p(rs), len(mv), _p(sel),
+                                        _p(occ), len(occ))
+    if k < 0:
+        raise ValueError("measurement outside the bin grid")
+    return sel[:len(mv)].astype(bool), occ
+
+
+def merger_select_additions(measurements, occupied, canvas_rows, canvas_cols, row_bins=10, col_bins=30, enable_binning=True,
+                            kind="stereo"):
+    """MergerProjective_::_addPoints binning (merger_projective_impl.cpp:205-253): source measurement index of every entry of
+    points_in_image_to_add, in its order"""
+    m = np.ascontiguousarray(measurements, np.float32)
+    win = np.zeros(max(len(m), 1), np.int32)
+    occ = None if occupied is None else np.ascontiguousarray(occupied, np.uint32)
+    k = lib().orc_merger_select_additions(_p(_merger_cfg6(canvas_rows, canvas_cols, row_bins, col_bins, enable_binning, kind)), _p(m),
+                                          m.shape[1], len(m), None if occ is None else _p(occ), _p(win))
+    return win[:k].copy()
+
+
 SHAPES = {"square": 0, "circle": 1, "rhombus": 2}
 
 

@@ -125,3 +125,21 @@ def test_batch_empty_and_limits(oracle):
         assert ctx.download_stereo_batch(1, 16)["n"] == 0
     finally:
         ctx.close()
+
+
+@pytest.mark.parametrize("max_rows", [376, 510, 511, 600, 4200])
+def test_batch_matcher_shared_memory_layouts(oracle, max_rows):
+    """the pipeline matcher picks its shared-memory layout from the context's row limit: the lean one-pass layout up to
+    510 rows, the full counting-sort layout up to 4096, the bitonic one above -- all three give the oracle's result"""
+    from srrg2_proslam_b200 import capi, synth
+    n = 3
+    imgs = synth.stereo_pairs(n, seed=77, device="cuda").cpu().numpy()
+    rows, cols = imgs.shape[2:]
+    ctx = capi.Context(max_images=2 * n, max_rows=max(rows, max_rows), max_cols=cols, max_features=4096,
+                       max_raw_per_bin=8192, work_images=4)
+    try:
+        e, m = capi.extract_cfg(15, 1, 4000), capi.match_cfg(**MATCH)
+        ctx.stereo_frontend_batch(imgs, n, rows, cols, cols, rows * cols, e, m)
+        check_batch(ctx, imgs, ctx.download_stereo_batch(n, 4096 * n), O.extract_cfg(15, 1, 4000))
+    finally:
+        ctx.close()
