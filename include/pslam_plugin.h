@@ -129,6 +129,18 @@ int psp_landmark_estimator_compute_batch(psp_module* estimator, int n, float* st
 int psp_landmark_estimator_weighted_mean_batch(psp_module* estimator, int n, float* state_world, const int* number_of_optimizations,
                                                const float* landmark_in_sensor, float* coords_in_local_map, uint8_t* inlier);
 
+/* MergerRigidStereoTriangulation / MergerRigidStereoProjectiveEKF / MergerProjectiveDepthEKF
+ * (mapping/mergers/merger_projective_impl.cpp:8-309): the binning of compute() on the device.
+ *   psp_merger_select_updates    update pass (:61-135): selected[c] = 1 where _updatePoint is reached; the module keeps
+ *                                the blocked bins.  measurements [n_meas][dim], dim 4 (uL,vL,uR,vR) or 3 (u,v,depth).
+ *   psp_merger_wants_additions   1 when compute() would call _addPoints after `merged` successful updates (:56-58,:158-165)
+ *   psp_merger_select_additions  binning of _addPoints (:205-253): winners[k] = measurement behind the k-th addition
+ *                                candidate (room for n_meas); returns their number. */
+int psp_merger_select_updates(psp_module* merger, const float* measurements, int dim, int n_meas, const int* corr_moving,
+                              const float* corr_response, int n_corr, uint8_t* selected);
+int psp_merger_wants_additions(psp_module* merger, int merged, int n_meas, int n_corr);
+int psp_merger_select_additions(psp_module* merger, const float* measurements, int dim, int n_meas, int* winners);
+
 /* LandmarkEstimatorPoseBasedSmoother{2D3D,3D3D,4D3D}: setCameraMatrix, psp_landmark_estimator_set_transforms, then the
  * batched compute over CSR measurement histories (see pslam_landmarks_smoother_update) */
 int psp_landmark_smoother_set_camera_matrix(psp_module* estimator, const float* K9);

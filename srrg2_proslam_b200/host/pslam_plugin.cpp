@@ -732,6 +732,48 @@ int LandmarkEstimatorWeightedMeanCUDA::computeBatch(int n, float* state_world, c
   return k;
 }
 
+pslam_merger_cfg MergerProjectiveCUDA::_cfg() const {
+  if (!param_projector.value()) throw std::runtime_error("MergerProjective::compute|ERROR: projector not set");  // :21-24
+  pslam_merger_cfg cfg;
+  cfg.canvas_rows = (int) param_projector->param_canvas_rows.value();
+  cfg.canvas_cols = (int) param_projector->param_canvas_cols.value();
+  cfg.number_of_row_bins = (int) param_number_of_row_bins.value();
+  cfg.number_of_col_bins = (int) param_number_of_col_bins.value();
+  cfg.maximum_distance_appearance = param_maximum_distance_appearance.value();
+  cfg.enable_binning = param_enable_binning.value() ? 1 : 0;
+  cfg.kind = _kind;
+  if (cfg.number_of_row_bins < 1 || (float) cfg.canvas_rows / (float) cfg.number_of_row_bins < 1)  // :36-41
+    throw std::runtime_error("MergerProjective::compute|ERROR: row bin width must be at least 1 pixel - reduce param_number_of_row_bins");
+  if (cfg.number_of_col_bins < 1 || (float) cfg.canvas_cols / (float) cfg.number_of_col_bins < 1)  // :42-47
+    throw std::runtime_error("MergerProjective::compute|ERROR: col bin width must be at least 1 pixel - reduce param_number_of_col_bins");
+  return cfg;
+}
+
+int MergerProjectiveCUDA::selectUpdates(const float* measurements, int dim, int n_meas, const int* corr_moving,
+                                        const float* corr_response, int n_corr, uint8_t* selected) {
+  const pslam_merger_cfg cfg = _cfg();
+  _occupied.assign((size_t) pslam_merger_occupancy_words(&cfg), 0u);
+  const int k = pslam_merger_select_updates(PslamDevice::context(), measurements, dim, n_meas, corr_moving, corr_response, n_corr, &cfg,
+                                            selected, _occupied.data());
+  PslamDevice::check(k, "MergerProjective::compute");
+  return k;
+}
+
+bool MergerProjectiveCUDA::wantsAdditions(int number_of_merged_points, int n_meas, int n_corr) const {
+  if (n_corr == 0) return true;
+  return number_of_merged_points < (int) param_target_number_of_merges.value() && number_of_merged_points < n_meas;
+}
+
+int MergerProjectiveCUDA::selectAdditions(const float* measurements, int dim, int n_meas, int* winners) {
+  if (param_enable_conservative_addition.value()) throw std::runtime_error("conservative addition is currently disabled");  // :262-264
+  const pslam_merger_cfg cfg = _cfg();
+  const bool have = _occupied.size() == (size_t) pslam_merger_occupancy_words(&cfg);
+  const int k = pslam_merger_select_additions(PslamDevice::context(), measurements, dim, n_meas, &cfg, have ? _occupied.data() : nullptr,
+                                              winners);
+  PslamDevice::check(k, "MergerProjective::_addPoints");
+  return k;
+}
+
 int LandmarkEstimatorPoseBasedSmootherCUDA::computeBatch(int n, float* state_world, int* number_of_optimizations, int n_frames,
                                                          const float* frames_sensor_in_world, const int* offsets, const int* hist_frame,
                                                          const float* hist_uv, const float* hist_point_in_camera,
@@ -940,6 +982,10 @@ template <int Kind>
 struct EstimatorK : LandmarkEstimatorEKFCUDA {
   EstimatorK() : LandmarkEstimatorEKFCUDA(Kind) {}
 };
+template <int Kind>
+struct MergerK : MergerProjectiveCUDA {
+  MergerK() : MergerProjectiveCUDA(Kind) {}
+};
 template <typename T>
 void reg(const std::string& reference_name) {
   PSLAM_REGISTER_CLASS_AS(T, reference_name);           // the unchanged .conf selects the CUDA-backed class
@@ -979,6 +1025,9 @@ void registerTypes() {
   reg<FilterK<2>>("StereoProjectivePointEKF3D");
   for (const char* dims : {"2D3D", "3D3D", "4D3D"}) reg<LandmarkEstimatorWeightedMeanCUDA>(std::string("LandmarkEstimatorWeightedMean") + dims);
   for (const char* dims : {"2D3D", "3D3D", "4D3D"}) reg<LandmarkEstimatorPoseBasedSmootherCUDA>(std::string("LandmarkEstimatorPoseBasedSmoother") + dims);
+  reg<MergerK<PSLAM_MERGER_STEREO>>("MergerRigidStereoTriangulation");  // mapping/instances.cpp:45-48
+  reg<MergerK<PSLAM_MERGER_STEREO>>("MergerRigidStereoProjectiveEKF");
+  reg<MergerK<PSLAM_MERGER_DEPTH>>("MergerProjectiveDepthEKF");
   reg<EstimatorK<0>>("LandmarkEstimatorProjectiveEKF3D");
   reg<EstimatorK<1>>("LandmarkEstimatorProjectiveDepthEKF3D");
   reg<EstimatorK<2>>("LandmarkEstimatorStereoProjectiveEKF3D");

@@ -518,6 +518,51 @@ private:
   Isometry3f _sensor_in_world, _sensor_in_local_map;
 };
 
+// ---- MergerProjective_ family (mapping/mergers/merger_projective.h:14-110, merger_projective_rigid_stereo*.h,
+// merger_projective_depth_ekf.h).  The module carries the .conf parameters and runs the BINNING of
+// compute() / _addPoints() on the device: which correspondences reach _updatePoint, which measurements become addition
+// candidates.  The landmark update itself is the linked landmark_estimator's computeBatch, the triangulation of the
+// additions pslam_triangulate -- the scene container and the statistics field stay with the caller (control plane).
+class MergerProjectiveCUDA : public Configurable {
+public:
+  explicit MergerProjectiveCUDA(int kind) : _kind(kind) {}
+  // MergerCorrespondence_ (srrg2_slam_interfaces)
+  PARAM(PropertyBool, enable_binning, "toggles point binning (distribution homogenization)", true, nullptr);
+  PARAM(PropertyUnsignedInt, target_number_of_merges,
+        "target number of points to merge, if hit no further points without correspondences will be added to moving", 100, nullptr);
+  // merger_projective.h:31-66
+  PARAM(PropertyConfigurable_<Configurable>, landmark_estimator,
+        "landmark estimator used to refine landmark positions in the map (structure-only)", nullptr, nullptr);
+  PARAM(PropertyConfigurable_<ProjectorPinhole>, projector, "pinhole projector used for projective merging",
+        std::make_shared<ProjectorPinhole>(), nullptr);
+  PARAM(PropertyFloat, maximum_distance_appearance, "maximum permitted correspondence response for merging a point", 50, nullptr);
+  PARAM(PropertyUnsignedInt, number_of_row_bins, "number of bins in row direction (feature density regulation)", 10, nullptr);
+  PARAM(PropertyUnsignedInt, number_of_col_bins, "number of bins in column direction (feature density regulation)", 30, nullptr);
+  PARAM(PropertyFloat, target_merge_ratio, "target merge ratio (#merges/#correspondences)", 0.5f, nullptr);
+  PARAM(PropertyBool, enable_conservative_addition,
+        "enables minimal addition of new points (instead all) if merge ratio is not reached", false, nullptr);
+  // merger_projective_rigid_stereo.h:24-28 / merger_projective_depth_ekf.h:27-31 (srrg2 modules outside the path: kept as links)
+  PARAM(PropertyConfigurable_<Configurable>, triangulator, "rigid stereo triangulation unit", nullptr, nullptr);
+  PARAM(PropertyConfigurable_<Configurable>, unprojector, "un-projector used to compute the points from the depth image", nullptr, nullptr);
+
+  int kind() const { return _kind; }  // PSLAM_MERGER_STEREO / PSLAM_MERGER_DEPTH
+  // update pass of compute() (merger_projective_impl.cpp:61-135): selected[c] = _updatePoint is reached; the blocked bins
+  // are kept for the addition pass.  measurements [n][dim], dim 4 (stereo) or 3 (u, v, depth).  Returns #selected.
+  int selectUpdates(const float* measurements, int dim, int n_meas, const int* corr_moving, const float* corr_response, int n_corr,
+                    uint8_t* selected);
+  // whether compute() goes on to _addPoints with `number_of_merged_points` successful updates (:158-165; always when
+  // there were no correspondences, :56-58)
+  bool wantsAdditions(int number_of_merged_points, int n_meas, int n_corr) const;
+  // binning of _addPoints (:205-253) against the bins blocked by the last selectUpdates; winners has room for n_meas
+  int selectAdditions(const float* measurements, int dim, int n_meas, int* winners);
+  void resetOccupancy() { _occupied.clear(); }
+
+private:
+  pslam_merger_cfg _cfg() const;
+  int _kind;
+  std::vector<uint32_t> _occupied;
+};
+
 // ---- LandmarkEstimatorPoseBasedSmoother_ (mapping/landmarks/landmark_estimator_pose_based_smoother.{h,cpp}) ----------
 class LandmarkEstimatorPoseBasedSmootherCUDA : public Configurable {
 public:

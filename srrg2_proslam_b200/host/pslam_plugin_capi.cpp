@@ -607,6 +607,22 @@ int psp_landmark_estimator_weighted_mean_batch(psp_module* estimator, int n, flo
   });
 }
 
+int psp_merger_select_updates(psp_module* merger, const float* measurements, int dim, int n_meas, const int* corr_moving,
+                              const float* corr_response, int n_corr, uint8_t* selected) {
+  return guard([&] {
+    return as<MergerProjectiveCUDA>(merger, "MergerProjective")
+      ->selectUpdates(measurements, dim, n_meas, corr_moving, corr_response, n_corr, selected);
+  });
+}
+
+int psp_merger_wants_additions(psp_module* merger, int merged, int n_meas, int n_corr) {
+  return guard([&] { return as<MergerProjectiveCUDA>(merger, "MergerProjective")->wantsAdditions(merged, n_meas, n_corr) ? 1 : 0; });
+}
+
+int psp_merger_select_additions(psp_module* merger, const float* measurements, int dim, int n_meas, int* winners) {
+  return guard([&] { return as<MergerProjectiveCUDA>(merger, "MergerProjective")->selectAdditions(measurements, dim, n_meas, winners); });
+}
+
 int psp_landmark_smoother_set_camera_matrix(psp_module* estimator, const float* K9) {
   return guard([&] {
     std::array<float, 9> K;

@@ -243,6 +243,24 @@ class Module:
         k = _chk(lib().psp_landmark_estimator_weighted_mean_batch(self.h, n, _p(st), _p(no), _p(ls), _p(loc), _p(inl)))
         return st, loc, inl.astype(bool), k
 
+    def merger_select_updates(self, measurements, corr_moving, corr_response):
+        """MergerProjective_::compute update pass: selected[n_corr] (the module keeps the blocked bins)"""
+        m = np.ascontiguousarray(measurements, np.float32)
+        mv = np.ascontiguousarray(corr_moving, np.int32).reshape(-1)
+        rs = np.ascontiguousarray(corr_response, np.float32).reshape(len(mv))
+        sel = np.zeros(max(len(mv), 1), np.uint8)
+        _chk(lib().psp_merger_select_updates(self.h, _p(m), m.shape[1], len(m), _p(mv), _p(rs), len(mv), _p(sel)))
+        return sel[:len(mv)].astype(bool)
+
+    def merger_wants_additions(self, merged, n_meas, n_corr):
+        return bool(_chk(lib().psp_merger_wants_additions(self.h, int(merged), int(n_meas), int(n_corr))))
+
+    def merger_select_additions(self, measurements):
+        m = np.ascontiguousarray(measurements, np.float32)
+        win = np.zeros(max(len(m), 1), np.int32)
+        k = _chk(lib().psp_merger_select_additions(self.h, _p(m), m.shape[1], len(m), _p(win)))
+        return win[:k].copy()
+
     def smoother_set_camera_matrix(self, K):
         K = np.ascontiguousarray(K, np.float32).reshape(9)
         _chk(lib().psp_landmark_smoother_set_camera_matrix(self.h, _p(K)))

@@ -76,3 +76,61 @@ def test_edges(ctx):
         ctx.merger_select_additions(cfg, outside, None)
     with pytest.raises(capi.PslamError):
         ctx.merger_select_updates(capi.merger_cfg(376, 1241, row_bins=400), meas, moving, resp)  # bin width < 1 px
+
+
+def test_conf_merger_pass_kitti_00_to_01(oracle):
+    """kitti.conf "merger_ekf" (MergerRigidStereoProjectiveEKF -> "landmark_estimator_ekf" -> "point_filter") instantiated by
+    class name: one merger pass of frame 01 into the landmarks of frame 00, chained like MergerProjective_::compute
+    (merger_projective_impl.cpp:61-171): binned update selection -> batched EKF update of the selected landmarks -> merge
+    count -> binned addition candidates -> their triangulation; every stage against the CPU restatement"""
+    import pathlib
+    from srrg2_proslam_b200 import plugin as P
+    from test_oracle_known_answers import CAM00, CAM01, K_KITTI
+    m = P.Manager(pathlib.Path(__file__).resolve().parent / "golden" / "configurations" / "kitti_hotpath.conf")
+    mg = m.get("merger_ekf")
+    assert mg.class_name == "MergerRigidStereoProjectiveEKF" and not mg.is_generic
+    pr = mg.link("projector")
+    pr.set_camera_matrix(K_KITTI)
+    pr.set("canvas_rows", 376).set("canvas_cols", 1241)
+    est = mg.link("landmark_estimator")
+    b_x = np.float32(718.856) * np.float32(0.537166)
+    est.link("filter").filter_set_camera(K_KITTI, (float(b_x), 0.0))
+    rows_bins, col_bins, gate = int(mg.get("number_of_row_bins")), int(mg.get("number_of_col_bins")), mg.get("maximum_distance_appearance")
+    assert (rows_bins, col_bins, gate) == (20, 60, 100)
+
+    c = O.extract_cfg(threshold=15, target=1000)
+    f = [O.stereo_adaptor(O.load_gray(f"kitti_city_image_left_{i}.png"), O.load_gray(f"kitti_city_image_right_{i}.png"), c,
+                          "epipolar", 100, 0.5, 100, 0) for i in (0, 1)]
+    scene, _ = O.triangulate(f[0]["uvuv"], K_KITTI, b_x, 0.0)           # landmarks: frame 00, world = camera 00
+    fixed, moving, resp = O.match_bruteforce(f[0]["desc"], f[1]["desc"], 75, 0.8)
+    meas = f[1]["uvuv"]
+    cam01_in_00 = O.pose_mul(O.pose_inverse(CAM00), CAM01).astype(np.float32)
+
+    # 1. update pass
+    g_sel = mg.merger_select_updates(meas, moving, resp)
+    o_sel, o_occ = O.merger_select_updates(meas, moving, resp, 376, 1241, rows_bins, col_bins, gate, True, "stereo")
+    assert np.array_equal(g_sel, o_sel) and 0 < g_sel.sum() < len(moving)
+    # 2. _updatePoint of the selected correspondences = the linked estimator, batched
+    state, cov = scene[fixed[g_sel]], np.tile(np.eye(3, dtype=np.float32), (int(g_sel.sum()), 1, 1))
+    est.estimator_set_transforms(cam01_in_00, cam01_in_00)
+    g = est.estimator_compute_batch(state, cov, meas[moving[g_sel]])
+    o = O.landmarks_ekf_update("stereo", K_KITTI, (float(b_x), 0.0), cam01_in_00, cam01_in_00, state, cov, meas[moving[o_sel]],
+                               min_cov=est.get("minimum_state_element_covariance"),
+                               max_cov_norm2=est.get("maximum_covariance_norm_squared"),
+                               max_dist2=est.get("maximum_distance_geometry_meters_squared"))
+    assert np.array_equal(g[3], o[3])
+    merged = int(g[3].sum())
+    assert 0 < merged <= int(g_sel.sum())
+    # 3. additions (:158-165): merge target of the file not reached -> binned candidates, then triangulated
+    assert mg.merger_wants_additions(merged, len(meas), len(moving)) == (merged < mg.get("target_number_of_merges") and merged < len(meas))
+    g_win = mg.merger_select_additions(meas)
+    o_win = O.merger_select_additions(meas, o_occ, 376, 1241, rows_bins, col_bins, True, "stereo")
+    assert np.array_equal(g_win, o_win) and len(g_win) > 0
+    from srrg2_proslam_b200 import capi
+    ctx = capi.Context(device=0, max_images=2, max_rows=376, max_cols=1241, max_features=2048, max_raw_per_bin=8192)
+    try:
+        g_xyz, g_valid, _ = ctx.triangulate(meas[g_win], K_KITTI, b_x, 0.0)
+    finally:
+        ctx.close()
+    o_xyz, _ = O.triangulate(meas[o_win], K_KITTI, b_x, 0.0)
+    assert np.array_equal(g_xyz, o_xyz) and g_valid.all()

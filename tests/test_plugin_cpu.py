@@ -40,7 +40,8 @@ HOT_CLASSES = ["IntensityFeatureExtractorBinned2D", "IntensityFeatureExtractorBi
                "LandmarkEstimatorStereoProjectiveEKF3D", "ProjectivePointEKF3D", "ProjectiveDepthPointEKF3D",
                "StereoProjectivePointEKF3D", "LandmarkEstimatorWeightedMean2D3D", "LandmarkEstimatorWeightedMean3D3D",
                "LandmarkEstimatorWeightedMean4D3D", "LandmarkEstimatorPoseBasedSmoother2D3D",
-               "LandmarkEstimatorPoseBasedSmoother3D3D", "LandmarkEstimatorPoseBasedSmoother4D3D"]
+               "LandmarkEstimatorPoseBasedSmoother3D3D", "LandmarkEstimatorPoseBasedSmoother4D3D",
+               "MergerRigidStereoTriangulation", "MergerRigidStereoProjectiveEKF", "MergerProjectiveDepthEKF"]
 HOT_CLASSES += [f"CorrespondenceFinderDescriptorBasedBruteforce{d}" for d in ("2D2D", "2D3D", "3D3D", "4D3D")]
 HOT_CLASSES += [f"CorrespondenceFinderProjective{s}{d}" for s in ("Square", "Circle", "Rhombus") for d in ("2D3D", "3D3D", "4D3D")]
 
@@ -163,8 +164,27 @@ def test_hotpath_fixtures_are_current(P, tmp_path):
     """the committed fixtures are what tools/make_golden.py derives from the unchanged files"""
     m = P.Manager(REF_CONF / "kitti.conf")
     m.write(tmp_path / "k.conf", ["adaptor_stereo_projective", "aligner", "cf_bruteforce", "clipper_stereo_projective", "landmark_estimator_ekf",
-                                 "landmark_estimator_weighted_mean", "landmark_estimator_smoother"])
+                                 "landmark_estimator_weighted_mean", "landmark_estimator_smoother", "merger_triangulation", "merger_ekf"])
     assert (tmp_path / "k.conf").read_text() == (GOLDEN / "kitti_hotpath.conf").read_text()
+
+
+def test_merger_modules_of_the_shipped_configurations(P):
+    """kitti.conf:188-230 / :552-600, icl.conf MergerProjectiveDepthEKF: parameters and links of the merger modules"""
+    m = P.Manager(GOLDEN / "kitti_hotpath.conf")
+    for name, cls, est in (("merger_triangulation", "MergerRigidStereoTriangulation", "LandmarkEstimatorPoseBasedSmoother4D3D"),
+                           ("merger_ekf", "MergerRigidStereoProjectiveEKF", "LandmarkEstimatorStereoProjectiveEKF3D")):
+        g = m.get(name)
+        assert not g.is_generic and g.class_name == cls
+        assert [g.get(k) for k in ("enable_binning", "enable_conservative_addition", "number_of_row_bins", "number_of_col_bins",
+                                   "target_merge_ratio")] == [1, 0, 20, 60, 0.5]
+        assert g.link("projector").class_name == "PointIntensityDescriptor3fProjectorPinhole"
+        assert g.link("landmark_estimator").class_name == est
+        assert g.link("triangulator").is_generic  # TriangulatorRigidStereo: control plane, kept as a generic module
+    d = [x for x in P.Manager(GOLDEN / "icl_hotpath.conf").modules() if x.class_name == "MergerProjectiveDepthEKF"][0]
+    assert not d.is_generic and d.link("landmark_estimator").class_name == "LandmarkEstimatorProjectiveDepthEKF3D"
+    fresh = P.Manager().create("MergerRigidStereoTriangulation")  # merger_projective.h:41-66 defaults
+    assert [fresh.get(k) for k in ("maximum_distance_appearance", "number_of_row_bins", "number_of_col_bins", "target_merge_ratio",
+                                   "enable_conservative_addition")] == [50, 10, 30, 0.5, 0]
 
 
 def test_errors_keep_the_reference_texts(P):

@@ -51,8 +51,9 @@ from srrg2_proslam_b200 import plugin as P  # noqa: E402
 
 CONF = pathlib.Path("/root/reference/configurations")
 HOT = {"kitti": ["adaptor_stereo_projective", "aligner", "cf_bruteforce", "clipper_stereo_projective", "landmark_estimator_ekf",
-                 "landmark_estimator_weighted_mean", "landmark_estimator_smoother"],
-       "euroc": ["adaptor_stereo_projective", "aligner", "cf_bruteforce", "clipper_stereo_projective"],
+                 "landmark_estimator_weighted_mean", "landmark_estimator_smoother", "merger_triangulation", "merger_ekf"],
+       "euroc": ["adaptor_stereo_projective", "aligner", "cf_bruteforce", "clipper_stereo_projective", "merger_triangulation",
+                 "merger_ekf"],
        "icl": ["tracker_slice_processor_projective_depth", "aligner", "cf_bruteforce_2d", "cf_bruteforce_3d"]}
 (OUT / "configurations").mkdir(exist_ok=True)
 for name, roots in HOT.items():
