@@ -160,6 +160,7 @@ def tracking_lines(ctx, capi, stream, dev):
         e, mcfg = capi.extract_cfg(15, 1, 500), capi.match_cfg(50, 0.8, 100, 0)
         meas = [small.stereo_adaptor(ld(f"kitti_city_image_left_{i}.png"), ld(f"kitti_city_image_right_{i}.png"), e, mcfg) for i in (0, 1)]
         xyz, _, _ = small.triangulate(meas[0]["uvuv"], K, float(np.float32(718.856) * np.float32(0.537166)), 0.0)
+        _, bf_moving, bf_response = small.match_bruteforce(meas[0]["desc"], meas[1]["desc"], capi.match_cfg(75, 0.8))
         # per-frame latency of the stereo adaptor (host images in, measurement cloud out: detect + describe L, R, match)
         L1, R1 = ld("kitti_city_image_left_1.png"), ld("kitti_city_image_right_1.png")
         e1k = capi.extract_cfg(15, 1, 1000)
@@ -211,6 +212,34 @@ def tracking_lines(ctx, capi, stream, dev):
         out["aligner"]["cpu_oracle_ms"] = 1e3 * float(np.median(t_cpu))
     except Exception as e:
         out["aligner"]["cpu_oracle_ms"] = repr(e)
+    # merger pass of the same frame pair (kitti.conf merger_ekf): binned update selection + binned additions, host pointers
+    try:
+        mg = m.get("merger_ekf")
+        pm = mg.link("projector")
+        pm.set_camera_matrix(K)
+        pm.set("canvas_rows", 376).set("canvas_cols", 1241)
+        mv, rs = bf_moving, bf_response  # frame 00 -> 01 correspondences (exhaustive matcher, 75 / 0.8)
+        tm = []
+        for rep in range(12):
+            t0 = time.perf_counter()
+            sel, win = mg.merger_plan(meas[1]["uvuv"], mv, rs)
+            tm.append(time.perf_counter() - t0)
+        O = oracle_lib()  # the same pass through the CPU restatement: checker + context number
+        t0 = time.perf_counter()
+        for rep in range(20):
+            osel, occ = O.merger_select_updates(meas[1]["uvuv"], mv, rs, 376, 1241, 20, 60, 100.0, True, "stereo")
+            owin = O.merger_select_additions(meas[1]["uvuv"], occ, 376, 1241, 20, 60, True, "stereo")
+        t_cpu = (time.perf_counter() - t0) / 20
+        out["merger"] = {"metric": "merger_binning_ms_per_frame", "value": 1e3 * float(np.median(tm[2:])), "unit": "ms",
+                         "cpu_oracle_ms": 1e3 * t_cpu, "measurements": int(len(meas[1]["uvuv"])), "correspondences": int(len(mv)),
+                         "updates": int(sel.sum()), "additions": int(len(win)),
+                         "parity": bool(np.array_equal(sel, osel) and np.array_equal(win, owin)),
+                         "config": "kitti.conf merger_ekf (MergerRigidStereoProjectiveEKF, 20 x 60 bins), KITTI 00 -> 01: "
+                                   "pslam_merger_plan = one upload, two launches, one download per frame; latency bound (a few "
+                                   "hundred items: the sequential CPU walk is as fast, the device version pays off inside a device-"
+                                   "resident pipeline or batched)"}
+    except Exception as e:
+        out["merger"] = {"error": repr(e)}
     # batched H,b: one launch over 2^22 correspondences
     n = 1 << 22
     rng = np.random.default_rng(0)

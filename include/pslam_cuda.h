@@ -313,6 +313,14 @@ int pslam_merger_select_updates(pslam_ctx* ctx, const float* measurements, int d
 int pslam_merger_select_additions(pslam_ctx* ctx, const float* measurements, int dim, int n_meas, const pslam_merger_cfg* cfg,
                                   const uint32_t* occupied_bins, int* winners);
 
+/* both passes in one call (one upload, two launches, one download): the addition candidates only depend on the bins the
+ * update pass blocks, not on the estimator's verdicts, so they can be computed before the caller knows whether
+ * compute() will reach _addPoints (:158-165) -- it ignores them if not.  Returns the number selected, *n_winners the
+ * number of addition candidates. */
+int pslam_merger_plan(pslam_ctx* ctx, const float* measurements, int dim, int n_meas, const int* corr_moving,
+                      const float* corr_response, int n_corr, const pslam_merger_cfg* cfg, uint8_t* selected, uint32_t* occupied_bins,
+                      int* winners, int* n_winners);
+
 /* ---- stage 2b: exhaustive Hamming matching --------------------------------------
  * Replaces CorrespondenceFinderDescriptorBasedBruteforce::compute
  *   (.../correspondence_finders/correspondence_finder_descriptor_based_bruteforce_impl.cpp:6-294).

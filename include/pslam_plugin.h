@@ -139,6 +139,9 @@ int psp_landmark_estimator_weighted_mean_batch(psp_module* estimator, int n, flo
 int psp_merger_select_updates(psp_module* merger, const float* measurements, int dim, int n_meas, const int* corr_moving,
                               const float* corr_response, int n_corr, uint8_t* selected);
 int psp_merger_wants_additions(psp_module* merger, int merged, int n_meas, int n_corr);
+/* both passes in one device round trip (pslam_merger_plan); returns #selected, *n_winners = #addition candidates */
+int psp_merger_plan(psp_module* merger, const float* measurements, int dim, int n_meas, const int* corr_moving, const float* corr_response,
+                    int n_corr, uint8_t* selected, int* winners, int* n_winners);
 int psp_merger_select_additions(psp_module* merger, const float* measurements, int dim, int n_meas, int* winners);
 
 /* LandmarkEstimatorPoseBasedSmoother{2D3D,3D3D,4D3D}: setCameraMatrix, psp_landmark_estimator_set_transforms, then the

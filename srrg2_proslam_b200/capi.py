@@ -441,6 +441,20 @@ class Context:
         assert k == int(sel.sum())
         return sel.astype(bool), occ
 
+    def merger_plan(self, cfg, measurements, corr_moving, corr_response):
+        """both passes in one call: (selected[n_corr] bool, blocked-bin words, addition winners)"""
+        m = np.ascontiguousarray(measurements, np.float32)
+        m = m.reshape(-1, m.shape[-1] if m.ndim == 2 else 4)
+        mv = np.ascontiguousarray(corr_moving, np.int32).reshape(-1)
+        rs = np.ascontiguousarray(corr_response, np.float32).reshape(len(mv))
+        sel = np.zeros(max(len(mv), 1), np.uint8)
+        occ = np.zeros(self._chk(lib().pslam_merger_occupancy_words(C.byref(cfg))), np.uint32)
+        win, nw = np.zeros(max(len(m), 1), np.int32), C.c_int(0)
+        k = self._chk(lib().pslam_merger_plan(self._h, _p(m), m.shape[1], len(m), _p(mv), _p(rs), len(mv), C.byref(cfg), _p(sel), _p(occ),
+                                              _p(win), C.byref(nw)))
+        assert k == int(sel[:len(mv)].sum())
+        return sel[:len(mv)].astype(bool), occ, win[:nw.value].copy()
+
     def merger_select_additions(self, cfg, measurements, occupied=None):
         """MergerProjective_::_addPoints binning: source measurement index of every addition candidate, in order"""
         m = np.ascontiguousarray(measurements, np.float32)

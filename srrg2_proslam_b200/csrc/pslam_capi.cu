@@ -1039,6 +1039,61 @@ int pslam_merger_select_additions(pslam_ctx* ctx, const float* measurements, int
   return h[0];
 }
 
+int pslam_merger_plan(pslam_ctx* ctx, const float* measurements, int dim, int n_meas, const int* corr_moving,
+                      const float* corr_response, int n_corr, const pslam_merger_cfg* cfg, uint8_t* selected, uint32_t* occupied_bins,
+                      int* winners, int* n_winners) {
+  if (!ctx || !merger_cfg_ok(cfg, dim) || n_meas < 0 || n_corr < 0 || !occupied_bins || !n_winners ||
+      (n_meas > 0 && (!measurements || !winners)) || (n_corr > 0 && (!corr_moving || !corr_response || !selected)))
+    return PSLAM_E_INVALID;
+  const int n_words = pslam_merger_occupancy_words(cfg);
+  auto al = [](size_t b) { return (b + 255) & ~(size_t) 255; };
+  // device block: [meas | moving | response] in, [results (4 ints) | selected | blocked bins | winners] out
+  const size_t bm = al((size_t) n_meas * dim * 4), bc = al((size_t) n_corr * 4);
+  const size_t in_bytes = bm + 2 * bc;
+  const size_t bs = al((size_t) n_corr), bw = al((size_t) n_words * 4), bi = al((size_t) n_meas * 4);
+  const size_t out_bytes = 256 + bs + bw + bi;
+  if (in_bytes + out_bytes > ctx->pinned_bytes || (size_t) n_words * 32 * 12 > 200 * 1024 ||
+      PSLAM_SOLVER_SCRATCH_OFFSET + in_bytes + out_bytes > ctx->scratch_bytes) {
+    // too large for the one-copy staging block: the two passes one after the other
+    const int k = pslam_merger_select_updates(ctx, measurements, dim, n_meas, corr_moving, corr_response, n_corr, cfg, selected, occupied_bins);
+    if (k < 0) return k;
+    const int a = pslam_merger_select_additions(ctx, measurements, dim, n_meas, cfg, occupied_bins, winners);
+    if (a < 0) return a;
+    *n_winners = a;
+    return k;
+  }
+  PSLAM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  uint8_t* d_in = ctx->d_scratch + PSLAM_SOLVER_SCRATCH_OFFSET;
+  float* d_meas = reinterpret_cast<float*>(d_in);
+  int* d_mv = reinterpret_cast<int*>(d_in + bm);
+  float* d_rs = reinterpret_cast<float*>(d_in + bm + bc);
+  uint8_t* d_out = d_in + in_bytes;
+  int* d_res = reinterpret_cast<int*>(d_out);
+  uint8_t* d_sel = d_out + 256;
+  unsigned* d_occ = reinterpret_cast<unsigned*>(d_out + 256 + bs);
+  int* d_win = reinterpret_cast<int*>(d_out + 256 + bs + bw);
+  uint8_t* h_stage = reinterpret_cast<uint8_t*>(ctx->h_pinned);
+  if (n_meas > 0) memcpy(h_stage, measurements, (size_t) n_meas * dim * 4);
+  if (n_corr > 0) {
+    memcpy(h_stage + bm, corr_moving, (size_t) n_corr * 4);
+    memcpy(h_stage + bm + bc, corr_response, (size_t) n_corr * 4);
+  }
+  if (in_bytes > 0) PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_in, h_stage, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = pslam_k_merger_select_updates(ctx, cfg, d_meas, dim, n_meas, d_mv, d_rs, n_corr, d_sel, d_occ, n_words, d_res);
+  if (rc) return rc;
+  if ((rc = pslam_k_merger_select_additions(ctx, cfg, d_meas, dim, n_meas, d_occ, d_win, d_res + 2))) return rc;
+  uint8_t* h_res = h_stage + in_bytes;
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(h_res, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  const int* h = reinterpret_cast<const int*>(h_res);
+  if (h[1] || h[3]) return pslam_set_error(ctx, PSLAM_E_INVALID, "merger: measurement outside the bin grid / correspondence index out of range", cudaSuccess);
+  if (n_corr > 0) memcpy(selected, h_res + 256, (size_t) n_corr);
+  memcpy(occupied_bins, h_res + 256 + bs, (size_t) n_words * 4);
+  if (h[2] > 0) memcpy(winners, h_res + 256 + bs + bw, (size_t) h[2] * 4);
+  *n_winners = h[2];
+  return h[0];
+}
+
 int pslam_landmarks_smoother_update(pslam_ctx* ctx, int n, float* state_world, int* number_of_optimizations, int n_frames,
                                     const float* frames_sensor_in_world, const int* offsets, const int* hist_frame,
                                     const float* hist_uv, const float* hist_point_in_camera, const pslam_smoother_cfg* cfg,

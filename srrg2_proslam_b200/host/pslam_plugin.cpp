@@ -759,6 +759,17 @@ int MergerProjectiveCUDA::selectUpdates(const float* measurements, int dim, int 
   return k;
 }
 
+int MergerProjectiveCUDA::plan(const float* measurements, int dim, int n_meas, const int* corr_moving, const float* corr_response,
+                               int n_corr, uint8_t* selected, int* winners, int* n_winners) {
+  if (param_enable_conservative_addition.value()) throw std::runtime_error("conservative addition is currently disabled");  // :262-264
+  const pslam_merger_cfg cfg = _cfg();
+  _occupied.assign((size_t) pslam_merger_occupancy_words(&cfg), 0u);
+  const int k = pslam_merger_plan(PslamDevice::context(), measurements, dim, n_meas, corr_moving, corr_response, n_corr, &cfg, selected,
+                                  _occupied.data(), winners, n_winners);
+  PslamDevice::check(k, "MergerProjective::compute");
+  return k;
+}
+
 bool MergerProjectiveCUDA::wantsAdditions(int number_of_merged_points, int n_meas, int n_corr) const {
   if (n_corr == 0) return true;
   return number_of_merged_points < (int) param_target_number_of_merges.value() && number_of_merged_points < n_meas;

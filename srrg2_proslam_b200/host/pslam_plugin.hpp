@@ -555,6 +555,10 @@ public:
   bool wantsAdditions(int number_of_merged_points, int n_meas, int n_corr) const;
   // binning of _addPoints (:205-253) against the bins blocked by the last selectUpdates; winners has room for n_meas
   int selectAdditions(const float* measurements, int dim, int n_meas, int* winners);
+  // both passes in one device round trip (the addition candidates do not depend on the estimator's verdicts, only on the
+  // bins the update pass blocks); returns #selected, *n_winners = #addition candidates
+  int plan(const float* measurements, int dim, int n_meas, const int* corr_moving, const float* corr_response, int n_corr,
+           uint8_t* selected, int* winners, int* n_winners);
   void resetOccupancy() { _occupied.clear(); }
 
 private:

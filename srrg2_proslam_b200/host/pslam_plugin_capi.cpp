@@ -615,6 +615,14 @@ int psp_merger_select_updates(psp_module* merger, const float* measurements, int
   });
 }
 
+int psp_merger_plan(psp_module* merger, const float* measurements, int dim, int n_meas, const int* corr_moving, const float* corr_response,
+                    int n_corr, uint8_t* selected, int* winners, int* n_winners) {
+  return guard([&] {
+    return as<MergerProjectiveCUDA>(merger, "MergerProjective")
+      ->plan(measurements, dim, n_meas, corr_moving, corr_response, n_corr, selected, winners, n_winners);
+  });
+}
+
 int psp_merger_wants_additions(psp_module* merger, int merged, int n_meas, int n_corr) {
   return guard([&] { return as<MergerProjectiveCUDA>(merger, "MergerProjective")->wantsAdditions(merged, n_meas, n_corr) ? 1 : 0; });
 }

@@ -252,6 +252,15 @@ class Module:
         _chk(lib().psp_merger_select_updates(self.h, _p(m), m.shape[1], len(m), _p(mv), _p(rs), len(mv), _p(sel)))
         return sel[:len(mv)].astype(bool)
 
+    def merger_plan(self, measurements, corr_moving, corr_response):
+        """both passes in one device round trip: (selected[n_corr] bool, addition winners)"""
+        m = np.ascontiguousarray(measurements, np.float32)
+        mv = np.ascontiguousarray(corr_moving, np.int32).reshape(-1)
+        rs = np.ascontiguousarray(corr_response, np.float32).reshape(len(mv))
+        sel, win, nw = np.zeros(max(len(mv), 1), np.uint8), np.zeros(max(len(m), 1), np.int32), C.c_int(0)
+        _chk(lib().psp_merger_plan(self.h, _p(m), m.shape[1], len(m), _p(mv), _p(rs), len(mv), _p(sel), _p(win), C.byref(nw)))
+        return sel[:len(mv)].astype(bool), win[:nw.value].copy()
+
     def merger_wants_additions(self, merged, n_meas, n_corr):
         return bool(_chk(lib().psp_merger_wants_additions(self.h, int(merged), int(n_meas), int(n_corr))))
 

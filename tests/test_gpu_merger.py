@@ -28,6 +28,8 @@ def both(ctx, meas, moving, resp, rows, cols, kind, row_bins=10, col_bins=30, ga
     o_win = O.merger_select_additions(meas, o_occ, rows, cols, row_bins, col_bins, binning, kind)
     g_win = ctx.merger_select_additions(cfg, meas, g_occ)
     assert np.array_equal(g_win, o_win)
+    p_sel, p_occ, p_win = ctx.merger_plan(cfg, meas, moving, resp)  # both passes in one round trip
+    assert np.array_equal(p_sel, o_sel) and np.array_equal(p_occ, o_occ) and np.array_equal(p_win, o_win)
     assert np.array_equal(ctx.merger_select_additions(cfg, meas, None),
                           O.merger_select_additions(meas, None, rows, cols, row_bins, col_bins, binning, kind))
     return g_sel, g_win
@@ -126,6 +128,8 @@ def test_conf_merger_pass_kitti_00_to_01(oracle):
     g_win = mg.merger_select_additions(meas)
     o_win = O.merger_select_additions(meas, o_occ, 376, 1241, rows_bins, col_bins, True, "stereo")
     assert np.array_equal(g_win, o_win) and len(g_win) > 0
+    p_sel, p_win = mg.merger_plan(meas, moving, resp)
+    assert np.array_equal(p_sel, o_sel) and np.array_equal(p_win, o_win)
     from srrg2_proslam_b200 import capi
     ctx = capi.Context(device=0, max_images=2, max_rows=376, max_cols=1241, max_features=2048, max_raw_per_bin=8192)
     try:
