@@ -28,6 +28,8 @@
 // K2 `bin_select_kernel`: per (region, image) gather of the region's keypoints from the row lists in
 // row-major order, then the reference's selection (keep all if fewer than quota, else unstable std::sort by
 // response and keep the first quota) replayed move-for-move (libstdcxx_sort.h).
+#include <vector>
+
 #include "libstdcxx_sort.h"
 #include "pslam_internal.cuh"
 #include "pslam_kernels.cuh"
@@ -518,40 +520,17 @@ bin_select_kernel(const int* __restrict__ row_count, const uint32_t* __restrict_
                   const uint8_t* __restrict__ mask, int mask_pitch, int mask_invert, int rows, int cols, int nh, int nv,
                   float pixel_rows_per_detector, float pixel_cols_per_detector, uint32_t* __restrict__ raw,
                   int max_raw_per_bin, int max_bins, int* __restrict__ raw_count, int* __restrict__ sel_count,
-                  unsigned long long quota, int sort_cap, int* __restrict__ flags) {
+                  unsigned long long quota, int sort_cap, int* __restrict__ flags, const int* __restrict__ bounds) {
   extern __shared__ __align__(16) uint32_t s_sort[];
   __shared__ int s_warp[33];
-  __shared__ int s_rbegin, s_rend, s_cbegin, s_cend;
+  __shared__ int s_rbegin;
   const int tid = threadIdx.x;
   const int bin = blockIdx.x, image = blockIdx.y;
-  const int rb = bin / nh;
   uint32_t* seg = raw + ((size_t) image * max_bins + bin) * max_raw_per_bin;
-  if (tid == 0) {
-    s_rbegin = rows;
-    s_rend = 0;
-    s_cbegin = cols;
-    s_cend = 0;
-  }
-  __syncthreads();
-  // rows of this region row: floor(r / pixel_rows_per_detector) == rb   (binned.cpp:84-85)
-  for (int r = tid; r < rows; r += SEL_THREADS) {
-    const float q = floorf(__fdiv_rn((float) r, pixel_rows_per_detector));
-    if ((int) q == rb) {
-      atomicMin(&s_rbegin, r);
-      atomicMax(&s_rend, r + 1);
-    }
-  }
-  // columns: (size_t)((float) row_region + (float) c / pixel_cols_per_detector) == bin (:86-88); monotone in c
-  const float row_region = __fmul_rn((float) rb, (float) nh);
-  for (int c = tid; c < cols; c += SEL_THREADS) {
-    const float f = __fadd_rn((float) (unsigned) row_region, __fdiv_rn((float) c, pixel_cols_per_detector));
-    if ((unsigned) f == (unsigned) bin) {
-      atomicMin(&s_cbegin, c);
-      atomicMax(&s_cend, c + 1);
-    }
-  }
-  __syncthreads();
-  const int rbegin = s_rbegin, rend = s_rend, cbegin = s_cbegin, cend = s_cend;
+  // pixel range of this region: the (r, c) -> region rule of binned.cpp:83-90 is the same for every image of a launch;
+  // the launcher evaluates it once (same fp32 arithmetic) instead of every CTA walking all rows and columns
+  const int4 bd = __ldg(reinterpret_cast<const int4*>(bounds) + bin);
+  const int rbegin = bd.x, rend = bd.y, cbegin = bd.z, cend = bd.w;
   // ordered gather: one thread per image row, rows in chunks of SEL_THREADS
   int running = 0;
   for (int base = rbegin; base < rend; base += SEL_THREADS) {
@@ -722,12 +701,45 @@ int pslam_k_bin_select(pslam_ctx* ctx, int n_images, int rows, int cols, int nh,
   // float arithmetic of IntensityFeatureExtractorBinned_::init (binned.cpp:49-52)
   const float pr = static_cast<float>(rows) / static_cast<float>((size_t) nv);
   const float pc = static_cast<float>(cols) / static_cast<float>((size_t) nh);
+  // region bounds (binned.cpp:83-90): rows with floor(r / pr) == rb; columns with (size_t)((float) row_region + c / pc) ==
+  // bin, monotone in c.  Same fp32 operations as the reference's LUT, evaluated once per image geometry.
+  if (ctx->sel_bounds_key[0] != rows || ctx->sel_bounds_key[1] != cols || ctx->sel_bounds_key[2] != nh || ctx->sel_bounds_key[3] != nv) {
+    std::vector<int> bd((size_t) 4 * nh * nv);
+    for (int bin = 0; bin < nh * nv; ++bin) {
+      const int rb = bin / nh;
+      int rbegin = rows, rend = 0, cbegin = cols, cend = 0;
+      for (int r = 0; r < rows; ++r)
+        if ((int) floorf((float) r / pr) == rb) {
+          rbegin = r < rbegin ? r : rbegin;
+          rend = r + 1;
+        }
+      volatile float row_region = (float) rb * (float) nh;
+      for (int c = 0; c < cols; ++c) {
+        volatile float q = (float) c / pc;
+        volatile float f = (float) (unsigned) row_region + q;
+        if ((unsigned) f == (unsigned) bin) {
+          cbegin = c < cbegin ? c : cbegin;
+          cend = c + 1;
+        }
+      }
+      bd[4 * bin] = rbegin;
+      bd[4 * bin + 1] = rend;
+      bd[4 * bin + 2] = cbegin;
+      bd[4 * bin + 3] = cend;
+    }
+    PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_sel_bounds, bd.data(), bd.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // bd is a local
+    ctx->sel_bounds_key[0] = rows;
+    ctx->sel_bounds_key[1] = cols;
+    ctx->sel_bounds_key[2] = nh;
+    ctx->sel_bounds_key[3] = nv;
+  }
   dim3 grid(nh * nv, n_images);
   const int sort_cap = ctx->lim.max_raw_per_bin < 2048 ? ctx->lim.max_raw_per_bin : 2048;
   bin_select_kernel<<<grid, SEL_THREADS, (size_t) sort_cap * 6, ctx->stream>>>(
     ctx->d_row_count, ctx->d_row_kp, ctx->map_pitch, ctx->lim.max_rows, d_mask, ctx->map_pitch, mask_invert, rows, cols, nh, nv, pr,
     pc, ctx->d_raw, ctx->lim.max_raw_per_bin, ctx->lim.max_bins, ctx->d_raw_count, ctx->d_sel_count, quota, sort_cap,
-    ctx->d_flags);
+    ctx->d_flags, ctx->d_sel_bounds);
   PSLAM_LAUNCH_CHECK(ctx, "bin_select_kernel");
   return PSLAM_OK;
 }

@@ -256,6 +256,7 @@ int pslam_create(int device, const pslam_limits* lim, pslam_ctx** out) {
   PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_ep_dist, NP * MF));
   PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_ep_count, NP));
   PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_flags, 4));
+  PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_sel_bounds, 4 * (size_t) lim->max_bins));
   PSLAM_CUDA_TRY(ctx, cudaMemset(ctx->d_flags, 0, 4 * sizeof(int)));
   PSLAM_CUDA_TRY(ctx, cudaMemset(ctx->d_count, 0, NI * sizeof(int)));
   // scratch: matcher / solver temporaries, and the packed (CSR) stereo result of a whole batch
@@ -279,7 +280,7 @@ void pslam_destroy(pslam_ctx* ctx) {
                   ctx->d_sel_count, ctx->d_xy, ctx->d_resp, ctx->d_inten, ctx->d_desc, ctx->d_count,
                   ctx->d_st_uvuv, ctx->d_st_left, ctx->d_st_right, ctx->d_st_dist, ctx->d_st_count,
                   ctx->d_ep_fixed, ctx->d_ep_moving, ctx->d_ep_dist, ctx->d_ep_count, ctx->d_flags,
-                  ctx->d_scratch};
+                  ctx->d_sel_bounds, ctx->d_scratch};
   for (void* b : bufs)
     if (b) cudaFree(b);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);

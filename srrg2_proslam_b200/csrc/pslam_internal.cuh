@@ -41,6 +41,8 @@ struct pslam_ctx {
   uint32_t* d_row_kp;
   int* d_row_count;
   size_t k1_smem_set;
+  int* d_sel_bounds;      // K2: per region (row begin, row end, col begin, col end), valid for sel_bounds_key
+  int sel_bounds_key[4];  // rows, cols, nh, nv the table was built for
   uint8_t* d_blur;
   CUtensorMap blur_tmap;  // TMA view of the blur maps: u8 [work_images][max_rows][map_pitch], box {32, 31, 1}
   uint8_t* d_mask;  // [max_rows][map_pitch], single image (host entry point only)

@@ -143,3 +143,24 @@ def test_batch_matcher_shared_memory_layouts(oracle, max_rows):
         check_batch(ctx, imgs, ctx.download_stereo_batch(n, 4096 * n), O.extract_cfg(15, 1, 4000))
     finally:
         ctx.close()
+
+
+def test_batch_euroc_shaped_synthetic(oracle):
+    """EuRoC-shaped synthetic (752x480 pairs), euroc.conf parameters: FAST threshold 10, target
+    1000 per image, epipolar matcher max distance 75, ratio 0.5, disparities up to 200 px"""
+    from srrg2_proslam_b200 import capi, synth
+    n = 5
+    imgs = synth.stereo_pairs(n, rows=480, cols=752, seed=0, device="cuda", max_disp=200).cpu().numpy()
+    match = dict(max_dist=75.0, ratio=0.5, max_disp=200, thickness=0)
+    ctx = capi.Context(max_images=2 * n, max_rows=480, max_cols=752, max_features=2048, max_raw_per_bin=8192, work_images=4)
+    try:
+        ctx.stereo_frontend_batch(imgs, n, 480, 752, 752, 480 * 752, capi.extract_cfg(10, 1, 1000), capi.match_cfg(**match))
+        res = ctx.download_stereo_batch(n, 2048 * n)
+        counts, chk = O.stereo_frontend_batch(imgs, O.extract_cfg(10, 1, 1000), threads=4, **match)
+        off = res["offsets"]
+        assert np.array_equal(np.diff(off), counts) and res["n"] > 20 * n
+        for p in range(n):
+            a, b = off[p], off[p + 1]
+            assert O.fnv1a_points(res["uvuv"][a:b], res["intensity"][a:b], res["desc"][a:b]) == chk[p], p
+    finally:
+        ctx.close()
