@@ -169,7 +169,8 @@ int pslam_k_merger_select_updates(pslam_ctx* ctx, const pslam_merger_cfg* cfg, c
                                   const int* d_corr_moving, const float* d_corr_response, int n_corr, unsigned char* d_selected,
                                   unsigned* d_occupied, int n_words, int* d_result) {
   const size_t smem = (size_t) (cfg->number_of_row_bins + 1) * (cfg->number_of_col_bins + 1) * sizeof(int);
-  PSLAM_CUDA_TRY(ctx, cudaFuncSetAttribute(merger_select_updates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  if (smem > 48 * 1024)  // the shipped configurations (<= 21 x 61 bins) stay far below the default limit
+    PSLAM_CUDA_TRY(ctx, cudaFuncSetAttribute(merger_select_updates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   merger_select_updates_kernel<<<1, MG_THREADS, smem, ctx->stream>>>(merger_params(cfg, dim), d_meas, n_meas, d_corr_moving,
                                                                       d_corr_response, n_corr, d_selected, d_occupied, n_words, d_result);
   PSLAM_LAUNCH_CHECK(ctx, "merger_select_updates_kernel");
@@ -179,7 +180,8 @@ int pslam_k_merger_select_updates(pslam_ctx* ctx, const pslam_merger_cfg* cfg, c
 int pslam_k_merger_select_additions(pslam_ctx* ctx, const pslam_merger_cfg* cfg, const float* d_meas, int dim, int n_meas,
                                     const unsigned* d_occupied, int* d_winners, int* d_result) {
   const size_t smem = (size_t) (cfg->number_of_row_bins + 1) * (cfg->number_of_col_bins + 1) * (sizeof(unsigned long long) + sizeof(int));
-  PSLAM_CUDA_TRY(ctx, cudaFuncSetAttribute(merger_select_additions_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  if (smem > 48 * 1024)
+    PSLAM_CUDA_TRY(ctx, cudaFuncSetAttribute(merger_select_additions_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   merger_select_additions_kernel<<<1, MG_THREADS, smem, ctx->stream>>>(merger_params(cfg, dim), d_meas, n_meas, d_occupied, d_winners,
                                                                         d_result);
   PSLAM_LAUNCH_CHECK(ctx, "merger_select_additions_kernel");
