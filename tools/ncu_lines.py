@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Attribute ncu per-SASS-instruction counts to CUDA source lines.
-  python tools/ncu_lines.py <report.ncu-rep> <kernel-substring> <cubin> [top]
+  python tools/ncu_lines.py <report.ncu-rep> <kernel-substring> <cubin> [top] [mangled-substring]
+(the last argument picks one template instance in the cubin, e.g. epipolar_kernelILb0ELb1EE)
 Uses `ncu --page source --csv` (SASS view: executed instructions + stall samples per instruction) and
 `nvdisasm -g -c` (line info) on the cubin that holds the kernel; both list the function's instructions in order.
 """
@@ -13,6 +14,7 @@ import sys
 
 rep, kname, cubin = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+cname = sys.argv[5] if len(sys.argv) > 5 else kname
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 # sections: "Kernel Name",<name> / header / rows ...
@@ -30,7 +32,7 @@ while i < len(rows):
     else:
         i += 1
 dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout.splitlines()
-start = [k for k, l in enumerate(dis) if l.startswith(".text.") and kname in l][0]
+start = [k for k, l in enumerate(dis) if l.startswith(".text.") and cname in l][0]
 lines = []
 cur = None
 for l in dis[start + 1:]:
@@ -42,7 +44,7 @@ for l in dis[start + 1:]:
         continue
     if re.match(r"\s+/\*[0-9a-f]{4,}\*/", l):
         lines.append(cur)
-    if l.startswith("\t.section") or (l.startswith(".text.") and kname not in l):
+    if l.startswith("\t.section") or (l.startswith(".text.") and cname not in l):
         break
 n = min(len(lines), len(sass))
 agg = collections.defaultdict(lambda: [0, 0])
