@@ -217,3 +217,26 @@ def test_no_cpu_fallback(P):
     m = P.Manager(GOLDEN / "kitti_hotpath.conf")
     with pytest.raises(P.PluginError, match="no usable CUDA device"):
         m.get("adaptor_stereo_projective").stereo_adaptor(np.zeros((376, 1241), np.uint8), np.zeros((376, 1241), np.uint8))
+
+
+def test_merger_configuration_errors_keep_the_reference_texts(P):
+    """merger_projective_impl.cpp:21-47: the checks of compute() fire before any device work, with the reference's texts"""
+    m = P.Manager()
+    g = m.create("MergerRigidStereoTriangulation", "g")
+    pr = g.link("projector")
+    pr.set("canvas_rows", 376).set("canvas_cols", 1241)
+    meas = np.array([[10, 10, 5, 10]], np.float32)
+    g.set("number_of_row_bins", 1000)
+    with pytest.raises(P.PluginError, match="row bin width must be at least 1 pixel"):
+        g.merger_select_updates(meas, [0], [10.0])
+    g.set("number_of_row_bins", 10).set("number_of_col_bins", 5000)
+    with pytest.raises(P.PluginError, match="col bin width must be at least 1 pixel"):
+        g.merger_select_additions(meas)
+    g.set("number_of_col_bins", 30).set("enable_conservative_addition", 1)
+    with pytest.raises(P.PluginError, match="conservative addition is currently disabled"):
+        g.merger_select_additions(meas)
+    g.set("enable_conservative_addition", 0).set("projector", None)
+    with pytest.raises(P.PluginError, match="projector not set"):
+        g.merger_plan(meas, [0], [10.0])
+    assert g.merger_wants_additions(5, 100, 0) and g.merger_wants_additions(5, 100, 50)      # :56-58, :158-165
+    assert not g.merger_wants_additions(100, 300, 150) and not g.merger_wants_additions(40, 40, 40)
