@@ -12,6 +12,11 @@
 // Gauss-Jordan elimination of the symmetric positive definite innovation covariance) and is pinned through the
 // scenarios of tests/test_{projective,projective_depth,stereo_projective}_point_ekf.cpp (tests/test_oracle_ekf.py).
 // The filter runs in double like the reference ("we locally operate in double precision", landmark_estimator_ekf.h:21).
+//   LandmarkEstimatorPoseBasedSmoother_::compute .../mapping/landmarks/landmark_estimator_pose_based_smoother_impl.cpp:6-148
+//     (pinned through the scenario of tests/test_landmark_estimators.cpp:210-258, tests/test_oracle_ekf.py)
+//   MergerProjective_::compute / _addPoints binning .../mapping/mergers/merger_projective_impl.cpp:61-135,205-253
+//     (the sequential map-of-maps walk; pinned on the reference's constant tests/test_mergers.cpp:337 -- ICL 00 -> 01 grows
+//     the scene from 321 to 337 points -- and :286-287, tests/test_oracle_merger.py)
 #pragma once
 #include <cmath>
 #include <cstring>
