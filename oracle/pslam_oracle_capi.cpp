@@ -654,6 +654,30 @@ int orc_linearize_f64(const double* lcfg18, const double* pose12, int n_moving,
   return 0;
 }
 
+// as orc_linearize_f64, plus: prior48 (12 doubles predicted pose + 36 doubles information; NULL = no prior
+// factor) summed into H, b (its chi goes to stats5[4], not into the slice's chi), and the per-correspondence
+// factor status (0 inlier, 1 kernelized, 2 suppressed; NULL = not wanted)
+int orc_linearize_ex_f64(const double* lcfg18, const double* pose12, int n_moving,
+                         const double* moving_xyz, int n_fixed, const double* fixed_meas,
+                         int fixed_dim, int n_corr, const int* cf, const int* cm,
+                         const double* info_diag, const double* prior48, uint8_t* status,
+                         double* H36, double* b6, double* stats5) {
+  (void) n_moving;
+  (void) n_fixed;
+  LinearSystem<double> sys;
+  const Pose<double> X = pose_from(pose12);
+  linearize(make_lcfg<double>(lcfg18), X, moving_xyz, fixed_meas, fixed_dim, cf, cm, n_corr,
+            info_diag, sys, status);
+  stats5[4] = prior48 ? pose_prior_accumulate(pose_from(prior48), prior48 + 12, X, sys) : 0.0;
+  std::memcpy(H36, sys.H, sizeof(sys.H));
+  std::memcpy(b6, sys.b, sizeof(sys.b));
+  stats5[0] = sys.chi_total;
+  stats5[1] = sys.inliers;
+  stats5[2] = sys.outliers;
+  stats5[3] = sys.suppressed;
+  return 0;
+}
+
 // the reference's own precision (fp32 accumulate), for reporting the fp32-vs-fp64 gap
 int orc_linearize_f32(const double* lcfg18, const double* pose12, int n_moving,
                       const double* moving_xyz, int n_fixed, const double* fixed_meas,

@@ -480,6 +480,9 @@ struct ProjectiveFinder {
 // -----------------------------------------------------------------------------
 enum FactorKind { FACTOR_STEREO = 0, FACTOR_DEPTH = 1, FACTOR_MONO = 2 };
 enum RobustifierKind { ROBUST_NONE = 0, ROBUST_SATURATED = 1, ROBUST_CLAMP = 2 };
+// per-factor outcome of one linearisation (srrg2_solver FactorStats::Status analogue): what the aligner's
+// inlier-only runs / keep_only_inlier_correspondences read (configurations/icl.conf:55-58)
+enum FactorStatus { FACTOR_INLIER = 0, FACTOR_KERNELIZED = 1, FACTOR_SUPPRESSED = 2 };
 
 template <typename S>
 struct LinearizeConfig {
@@ -578,7 +581,7 @@ template <typename S>
 static inline void linearize(const LinearizeConfig<S>& c, const Pose<S>& X, const S* moving_xyz,
                              const S* fixed_meas, int fixed_dim, const int* corr_fixed,
                              const int* corr_moving, int n_corr, const S* info_diag,
-                             LinearSystem<S>& sys) {
+                             LinearSystem<S>& sys, uint8_t* status = nullptr) {
   sys.clear();
   const int edim = (c.kind == FACTOR_MONO) ? 2 : 3;
   for (int k = 0; k < n_corr; ++k) {
@@ -586,6 +589,7 @@ static inline void linearize(const LinearizeConfig<S>& c, const Pose<S>& X, cons
     S e[3], J[18];
     if (!error_and_jacobian(c, X, moving_xyz + 3 * mi, fixed_meas + fixed_dim * fi, e, J)) {
       ++sys.suppressed;
+      if (status) status[k] = FACTOR_SUPPRESSED;
       continue;
     }
     S om[3] = {info_diag[3 * fi], info_diag[3 * fi + 1], info_diag[3 * fi + 2]};
@@ -595,8 +599,10 @@ static inline void linearize(const LinearizeConfig<S>& c, const Pose<S>& X, cons
     if (c.robustifier != ROBUST_NONE && chi > c.chi_threshold) {
       ++sys.outliers;
       scale = (c.robustifier == ROBUST_SATURATED) ? c.chi_threshold / chi : S(0);
+      if (status) status[k] = FACTOR_KERNELIZED;
     } else {
       ++sys.inliers;
+      if (status) status[k] = FACTOR_INLIER;
     }
     sys.chi_total += chi * scale;
     for (int i = 0; i < edim; ++i) {
@@ -608,6 +614,57 @@ static inline void linearize(const LinearizeConfig<S>& c, const Pose<S>& X, cons
       }
     }
   }
+}
+
+// SE3 pose-prior factor = the second slice of the shipped aligners, AlignerSliceMotionModel3D
+// (configurations/kitti.conf:747-772, icl.conf:268-293, euroc.conf:94-119: fixed and moving slice
+// "trajectory_chunk", a MotionModelConstantVelocity3D, no robustifier).  [upstream, srrg2_slam_interfaces +
+// srrg2_solver, not verifiable here]  The motion model predicts the estimate Z; the factor's error is the
+// 6-vector chart of the deviation, e = t2tnq(Z^-1 X), with a constant information matrix, summed into the
+// same 6x6 system before the solve.  For the right perturbation X <- X v2t(dx),
+// E = Z^-1 X = (R_E, t_E), q_E = (w, v) with w >= 0:
+//   d e_t / d dt = R_E      d e_t / d dq = 0      d e_q / d dt = 0      d e_q / d dq = w I + [v]x
+// (first order in dq: q_E (x) (1, dq) has vector part w dq + v x dq + v).  Returns chi = e' Omega e.
+template <typename S>
+static inline S pose_prior_accumulate(const Pose<S>& Z, const S* Omega36, const Pose<S>& X,
+                                      LinearSystem<S>& sys) {
+  const Pose<S> E = Z.inverse() * X;
+  S e[6];
+  t2tnq(E, e);
+  const S n2 = e[3] * e[3] + e[4] * e[4] + e[5] * e[5];
+  const S w = std::sqrt(n2 < S(1) ? S(1) - n2 : S(0));
+  S J[36];
+  for (S& v : J) v = 0;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) J[6 * i + j] = E.R[3 * i + j];
+  const S vx = e[3], vy = e[4], vz = e[5];
+  const S Q[9] = {w, -vz, vy, vz, w, -vx, -vy, vx, w};
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) J[6 * (3 + i) + 3 + j] = Q[3 * i + j];
+  S OJ[36], Oe[6];
+  for (int i = 0; i < 6; ++i) {
+    S s = 0;
+    for (int k = 0; k < 6; ++k) s += Omega36[6 * i + k] * e[k];
+    Oe[i] = s;
+    for (int j = 0; j < 6; ++j) {
+      S a = 0;
+      for (int k = 0; k < 6; ++k) a += Omega36[6 * i + k] * J[6 * k + j];
+      OJ[6 * i + j] = a;
+    }
+  }
+  S chi = 0;
+  for (int i = 0; i < 6; ++i) chi += e[i] * Oe[i];
+  for (int a = 0; a < 6; ++a) {
+    S bs = 0;
+    for (int k = 0; k < 6; ++k) bs += J[6 * k + a] * Oe[k];
+    sys.b[a] += bs;
+    for (int c = 0; c < 6; ++c) {
+      S hs = 0;
+      for (int k = 0; k < 6; ++k) hs += J[6 * k + a] * OJ[6 * k + c];
+      sys.H[6 * a + c] += hs;
+    }
+  }
+  return chi;
 }
 
 // (H + lambda I) dx = -b by Cholesky; X <- X * v2t(dx).  Returns false if not SPD.

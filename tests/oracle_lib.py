@@ -451,7 +451,10 @@ def linearize_cfg(kind, K, cols, rows, baseline=(0, 0, 0), mean_disparity=0.0,
                                                               chi_threshold]]).astype(np.float64)
 
 
-def linearize(lcfg, pose12, moving_xyz, fixed_meas, corr_fixed, corr_moving, info_diag, fp32=False):
+def linearize(lcfg, pose12, moving_xyz, fixed_meas, corr_fixed, corr_moving, info_diag, fp32=False, prior=None,
+              want_status=False):
+    """prior = (predicted pose12, information 6x6): the motion-model slice's pose-prior factor, summed into H, b.
+    want_status: the returned dict carries "status" (per correspondence: 0 inlier, 1 kernelized, 2 suppressed)."""
     pose12 = np.ascontiguousarray(pose12, np.float64).reshape(12)
     moving_xyz = np.ascontiguousarray(moving_xyz, np.float64).reshape(-1, 3)
     fixed_meas = np.ascontiguousarray(fixed_meas, np.float64)
@@ -461,12 +464,22 @@ def linearize(lcfg, pose12, moving_xyz, fixed_meas, corr_fixed, corr_moving, inf
     assert len(info) == len(fixed_meas)
     H = np.zeros(36, np.float64)
     b = np.zeros(6, np.float64)
-    st = np.zeros(4, np.float64)
-    fn = lib().orc_linearize_f32 if fp32 else lib().orc_linearize_f64
-    fn(_p(lcfg), _p(pose12), len(moving_xyz), _p(moving_xyz), len(fixed_meas), _p(fixed_meas),
-       fixed_meas.shape[1], len(cf), _p(cf), _p(cm), _p(info), _p(H), _p(b), _p(st))
-    return H.reshape(6, 6), b, dict(chi=st[0], inliers=int(st[1]), outliers=int(st[2]),
-                                    suppressed=int(st[3]))
+    st = np.zeros(5, np.float64)
+    if fp32:
+        assert prior is None and not want_status
+        lib().orc_linearize_f32(_p(lcfg), _p(pose12), len(moving_xyz), _p(moving_xyz), len(fixed_meas), _p(fixed_meas),
+                                fixed_meas.shape[1], len(cf), _p(cf), _p(cm), _p(info), _p(H), _p(b), _p(st))
+        status = None
+    else:
+        pr = None if prior is None else np.concatenate([np.asarray(prior[0], np.float64).reshape(12),
+                                                        np.asarray(prior[1], np.float64).reshape(36)])
+        status = np.zeros(max(len(cf), 1), np.uint8) if want_status else None
+        lib().orc_linearize_ex_f64(_p(lcfg), _p(pose12), len(moving_xyz), _p(moving_xyz), len(fixed_meas), _p(fixed_meas),
+                                   fixed_meas.shape[1], len(cf), _p(cf), _p(cm), _p(info), _p(pr), _p(status), _p(H), _p(b), _p(st))
+    out = dict(chi=st[0], inliers=int(st[1]), outliers=int(st[2]), suppressed=int(st[3]), prior_chi=st[4])
+    if want_status:
+        out["status"] = status[:len(cf)].copy()
+    return H.reshape(6, 6), b, out
 
 
 def gn_step(H, b, damping, pose12):
@@ -515,10 +528,54 @@ def mean_disparity_f32(fixed):
     return float(np.float32(acc / np.float32(len(fixed)))) if len(fixed) else 0.0
 
 
+class BruteforceFinder:
+    """CorrespondenceFinderDescriptorBasedBruteforce as an aligner's finder: the match does not depend on the estimate
+    and is recomputed only when a cloud changed (change flags, bruteforce_impl.cpp:13-15,233-235)."""
+
+    def __init__(self, max_dist=50.0, ratio=0.9):
+        self.max_dist, self.ratio = max_dist, ratio
+        self._f = self._m = self._result = None
+
+    def set_fixed(self, coords, desc):
+        self._f, self._result = np.ascontiguousarray(desc, np.uint8), None
+
+    def set_moving(self, xyz, desc):
+        self._m, self._result = np.ascontiguousarray(desc, np.uint8), None
+
+    def set_estimate(self, pose12):
+        pass
+
+    def compute(self):
+        if self._result is None:
+            self._result = match_bruteforce(self._f, self._m, self.max_dist, self.ratio)
+        return self._result
+
+
+def constant_velocity_prediction(trajectory_chunk):
+    """[upstream] MotionModelConstantVelocity3D over the aligner's "trajectory_chunk" slice (robot poses in the local map,
+    oldest first): the last relative motion is applied once more.  Returns the predicted moving_in_fixed (local map in
+    sensor) = (P_n * P_{n-1}^-1 * P_n)^-1; fewer than two poses: no motion (identity for an empty chunk)."""
+    if len(trajectory_chunk) == 0:
+        return np.eye(3, 4).reshape(12)
+    last = np.asarray(trajectory_chunk[-1], np.float64).reshape(12)
+    if len(trajectory_chunk) == 1:
+        return pose_inverse(last)
+    prev = np.asarray(trajectory_chunk[-2], np.float64).reshape(12)
+    motion = pose_mul(pose_inverse(prev), last)
+    return pose_inverse(pose_mul(last, motion))
+
+
 def align(pf, kind, K, rows, cols, fixed, moving_xyz, diag, init_pose=None, n_opt=None, baseline=(0, 0, 0),
           inverse_depth_weighting=False, robustifier="saturated", chi_threshold=25.0, max_iterations=100,
-          damping=0.0, min_num_inliers=6, min_num_correspondences=0):
-    """pf: an O.ProjectiveFinder with fixed / moving already set.  Returns dict(status, pose, stats, corr)."""
+          damping=0.0, min_num_inliers=6, min_num_correspondences=0, prior=None, enable_inlier_only_runs=False,
+          keep_only_inlier_correspondences=False):
+    """pf: a finder (O.ProjectiveFinder or O.BruteforceFinder) with fixed / moving already set.
+    prior: (predicted moving_in_fixed pose12, 6x6 information) of the motion-model slice, or None.
+    enable_inlier_only_runs / keep_only_inlier_correspondences (configurations/icl.conf:55-58) [upstream, restated as]:
+    after a successful main loop the correspondences whose factor was an inlier in the last linearisation are frozen and,
+    if at least min_num_inliers remain, `max_iterations` further GN iterations run on them alone (the finder is not
+    consulted again); keep_only leaves exactly those correspondences in the result.
+    Returns dict(status, pose, stats, corr[, inlier_run_stats])."""
     fixed = np.ascontiguousarray(fixed, np.float32)
     moving_xyz = np.ascontiguousarray(moving_xyz, np.float32).reshape(-1, 3)
     pose = np.eye(3, 4, dtype=np.float64).reshape(12) if init_pose is None else \
@@ -529,6 +586,17 @@ def align(pf, kind, K, rows, cols, fixed, moving_xyz, diag, init_pose=None, n_op
     diag = np.asarray(diag, np.float32)
     d3 = np.zeros(3, np.float32)
     d3[:len(diag)] = diag
+
+    def information(fi, mi):
+        info = np.zeros((len(fixed), 3), np.float64)
+        for f, m in zip(fi, mi):
+            d = d3.copy()
+            n = 0 if n_opt is None else int(n_opt[m])
+            if n > 2:
+                d = (d * np.float32(1 + np.log(float(n)))).astype(np.float32)
+            info[f] = d
+        return info
+
     stats, corr, enough = [], (np.zeros(0, np.int32),) * 2 + (np.zeros(0, np.float32),), True
     last = None
     for it in range(max_iterations):
@@ -539,14 +607,7 @@ def align(pf, kind, K, rows, cols, fixed, moving_xyz, diag, init_pose=None, n_op
             stats.append((len(fi), 0, 0, 0.0))
             enough = False
             break
-        info = np.zeros((len(fixed), 3), np.float64)
-        for f, m in zip(fi, mi):
-            d = d3.copy()
-            n = 0 if n_opt is None else int(n_opt[m])
-            if n > 2:
-                d = (d * np.float32(1 + np.log(float(n)))).astype(np.float32)
-            info[f] = d
-        H, b, st = linearize(lcfg, pose, moving_xyz, fixed, fi, mi, info)
+        H, b, st = linearize(lcfg, pose, moving_xyz, fixed, fi, mi, information(fi, mi), prior=prior, want_status=True)
         rc, new_pose, _ = gn_step(H, b, damping, pose)
         last = st
         stats.append((len(fi), st["inliers"], st["outliers"], st["chi"]))
@@ -557,4 +618,25 @@ def align(pf, kind, K, rows, cols, fixed, moving_xyz, diag, init_pose=None, n_op
         status = ALIGNER_STATUS["NotEnoughCorrespondences"]
     else:
         status = ALIGNER_STATUS["Success"] if last and last["inliers"] >= min_num_inliers else ALIGNER_STATUS["NotEnoughInliers"]
-    return {"status": status, "pose": pose, "stats": np.asarray(stats, np.float64).reshape(-1, 4), "corr": corr}
+    out = {"status": status, "pose": pose, "stats": np.asarray(stats, np.float64).reshape(-1, 4), "corr": corr}
+    if status == ALIGNER_STATUS["Success"] and (enable_inlier_only_runs or keep_only_inlier_correspondences):
+        keep = last["status"] == 0
+        inl = tuple(np.ascontiguousarray(a[keep]) for a in corr)
+        if enable_inlier_only_runs and int(keep.sum()) >= min_num_inliers:
+            fi, mi, _ = inl
+            info, rstats = information(fi, mi), []
+            for it in range(max_iterations):
+                H, b, st = linearize(lcfg, pose, moving_xyz, fixed, fi, mi, info, prior=prior, want_status=True)
+                rc, new_pose, _ = gn_step(H, b, damping, pose)
+                rstats.append((len(fi), st["inliers"], st["outliers"], st["chi"]))
+                if rc != 0:
+                    break
+                pose = new_pose
+                last = st
+            out["pose"], out["inlier_run_stats"] = pose, np.asarray(rstats, np.float64).reshape(-1, 4)
+            if keep_only_inlier_correspondences:  # inliers of the LAST linearisation of the inlier-only run
+                k2 = last["status"] == 0
+                inl = tuple(np.ascontiguousarray(a[k2]) for a in inl)
+        if keep_only_inlier_correspondences:
+            out["corr"] = inl
+    return out
