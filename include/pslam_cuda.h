@@ -361,6 +361,11 @@ int pslam_projective_set_fixed(pslam_ctx* ctx, int n_fixed, const float* fixed_c
                                const uint8_t* desc_fixed);
 int pslam_projective_set_moving(pslam_ctx* ctx, int n_moving, const float* moving_xyz,
                                 const uint8_t* desc_moving);
+/* The cached clouds live in an allocation of their own (no other entry point touches it).  Every set_fixed / set_moving
+ * stamps the cache with a process-unique, never-zero epoch: a caller that shares the context with other finder instances
+ * (or whose context was re-created) compares the epochs with the ones it saw after its own uploads and uploads again
+ * when they differ -- the host finder mirror does exactly that. */
+int pslam_projective_cache_epochs(const pslam_ctx* ctx, unsigned long long* fixed_epoch, unsigned long long* moving_epoch);
 int pslam_projective_match(pslam_ctx* ctx, int n_fixed, int n_moving, const float* local_map_in_sensor12,
                            const pslam_projective_cfg* cfg, int capacity, int* fixed_idx,
                            int* moving_idx, float* distance, int* n_projected);
@@ -390,6 +395,20 @@ typedef struct {
   double chi_threshold;
 } pslam_linearize_cfg;
 
+/* SE3 pose-prior factor summed into the same 6x6 system before the solve: the second slice of the shipped aligners,
+ * AlignerSliceMotionModel3D (configurations/kitti.conf:747-772, icl.conf:268-293, euroc.conf:94-119; srrg2_slam_interfaces).
+ * e = t2tnq(prediction^-1 * X), constant 6x6 information (row-major); evaluated on the device in every fused iteration. */
+typedef struct {
+  double prediction[12];  /* predicted moving_in_fixed, row-major 3x4 */
+  double information[36];
+} pslam_pose_prior;
+
+/* per-correspondence outcome of a linearisation (srrg2_solver FactorStats status): what MultiAligner's
+ * enable_inlier_only_runs / keep_only_inlier_correspondences read (configurations/icl.conf:55-58) */
+#define PSLAM_FACTOR_INLIER 0
+#define PSLAM_FACTOR_KERNELIZED 1
+#define PSLAM_FACTOR_SUPPRESSED 2
+
 int pslam_linearize_se3(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, const double* pose12,
                         int n_moving, const double* moving_xyz, int n_fixed, const double* fixed_meas,
                         int fixed_dim, int n_corr, const int* corr_fixed, const int* corr_moving,
@@ -410,6 +429,23 @@ int pslam_gn_iterate(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, int n_itera
                      int n_moving, const double* moving_xyz, int n_fixed, const double* fixed_meas, int fixed_dim,
                      int n_corr, const int* corr_fixed, const int* corr_moving, const double* info_diag,
                      double* poses12, double* stats4, int* iterations_done);
+/* The same two calls on fp32 clouds -- the reference's own cloud scalar (PointIntensityDescriptor_<D, float>): 40 B per
+ * correspondence travel and stay in HBM (3 + 4 + 3 floats), the widening to fp64 happens in registers (exact), nothing is
+ * converted on the host.  prior (may be NULL): pose-prior factor added to H, b (stats5[4] / not part of stats4's chi).
+ * factor_status (may be NULL): n_corr bytes, PSLAM_FACTOR_* of the (last) linearisation. */
+int pslam_linearize_se3_f32(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, const double* pose12, int n_moving,
+                            const float* moving_xyz, int n_fixed, const float* fixed_meas, int fixed_dim, int n_corr,
+                            const int* corr_fixed, const int* corr_moving, const float* info_diag,
+                            const pslam_pose_prior* prior, uint8_t* factor_status, double* H36, double* b6, double* stats5);
+int pslam_linearize_se3_timed_f32(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, const double* pose12, int n_moving,
+                                  const float* moving_xyz, int n_fixed, const float* fixed_meas, int fixed_dim, int n_corr,
+                                  const int* corr_fixed, const int* corr_moving, const float* info_diag, int reps,
+                                  double* ms_per_call);
+int pslam_gn_iterate_f32(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, int n_iterations, double damping, double* pose12,
+                         int n_moving, const float* moving_xyz, int n_fixed, const float* fixed_meas, int fixed_dim,
+                         int n_corr, const int* corr_fixed, const int* corr_moving, const float* info_diag,
+                         const pslam_pose_prior* prior, double* poses12, double* stats4, uint8_t* factor_status,
+                         int* iterations_done);
 /* (H + damping I) dx = -b, pose <- pose * v2t(dx) on the device (one thread, fp64 Cholesky) */
 int pslam_gn_step(pslam_ctx* ctx, const double* H36, const double* b6, double damping, double* pose12,
                   double* dx6);

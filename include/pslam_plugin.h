@@ -57,6 +57,10 @@ int psp_module_set_link(psp_module* c, const char* param, psp_module* target_or_
 psp_module* psp_module_get_link(psp_module* c, const char* param);
 
 /* ---- IntensityFeatureExtractorBinned{2D,3D}: setFeatures + compute(image) -------------------- */
+/* IntensityFeatureExtractorSelective_: the tracking detection mask (rows x cols bytes, 1 inside the rectangles) painted
+ * around `n` projections for a detection radius (intensity_feature_extractor_selective.cpp:63-144).  Host-side. */
+int psp_extractor_paint_tracking_mask(psp_module* extractor, int rows, int cols, int n, int dim, const float* coords, int radius,
+                                      uint8_t* mask);
 int psp_extractor_compute(psp_module* extractor, const uint8_t* image, int rows, int cols, int stride,
                           const uint8_t* mask_or_null, int capacity, float* xy, float* intensity, uint8_t* desc);
 
@@ -104,6 +108,15 @@ int psp_aligner_compute(psp_module* aligner, double* moving_in_fixed12, int* ite
                         int* num_inliers, double* chi);
 /* per-iteration stats of the last compute: rows of (num_correspondences, num_inliers, num_outliers, chi) */
 int psp_aligner_iteration_stats(psp_module* aligner, int capacity, double* rows4);
+/* aligner->param_slice_processors.setValue(index, slice) (tests/test_aligners.cpp:901) / .size() */
+int psp_aligner_set_slice_processor(psp_module* aligner, int index, psp_module* slice);
+int psp_aligner_num_slice_processors(psp_module* aligner);
+/* the "trajectory_chunk" slice of the fixed / moving scene (robot poses in the local map, oldest first; n may be 0) read by
+ * the aligner's AlignerSliceMotionModel3D, and the constant information matrix of its pose-prior factor (default identity) */
+int psp_aligner_set_trajectory_chunk(psp_module* aligner, int n, const float* poses12);
+int psp_aligner_set_prior_information(psp_module* aligner, const double* information36);
+/* rows of the additional inlier-only run (enable_inlier_only_runs, configurations/icl.conf:55); returns their number */
+int psp_aligner_inlier_run_stats(psp_module* aligner, int capacity, double* rows4);
 /* correspondences of the projective slice after the last compute */
 int psp_aligner_correspondences(psp_module* aligner, int capacity, int* fixed_idx, int* moving_idx, float* response);
 

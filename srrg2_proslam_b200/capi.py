@@ -129,6 +129,10 @@ class LinearizeCfg(C.Structure):
                 ("robustifier", C.c_int), ("chi_threshold", C.c_double)]
 
 
+class PosePrior(C.Structure):
+    _fields_ = [("prediction", C.c_double * 12), ("information", C.c_double * 36)]
+
+
 class FrameCfg(C.Structure):
     """pslam_frame_cfg: parameters of the batched projective + linearise stage"""
     _fields_ = [("K", C.c_float * 9), ("baseline_x_pixels", C.c_float), ("range_min", C.c_float),
@@ -577,6 +581,69 @@ class Context:
         if rc != PSLAM_E_NOT_SPD:
             self._chk(rc)
         return pose, poses[:done.value], stats[:done.value], done.value, rc != PSLAM_E_NOT_SPD
+
+    @staticmethod
+    def _prior(prior):
+        if prior is None:
+            return None
+        pr = PosePrior()
+        pr.prediction[:] = [float(v) for v in np.asarray(prior[0], np.float64).reshape(12)]
+        pr.information[:] = [float(v) for v in np.asarray(prior[1], np.float64).reshape(36)]
+        return pr
+
+    def linearize_f32(self, cfg, pose12, moving_xyz, fixed_meas, corr_fixed, corr_moving, info_diag, prior=None):
+        """fp32 clouds (the reference's scalar), optional pose prior (prediction pose12, information 6x6);
+        returns H, b, stats incl. per-correspondence factor status and the prior's chi"""
+        pose12 = np.ascontiguousarray(pose12, np.float64).reshape(12)
+        moving_xyz = np.ascontiguousarray(moving_xyz, np.float32).reshape(-1, 3)
+        fixed_meas = np.ascontiguousarray(fixed_meas, np.float32)
+        cf = np.ascontiguousarray(corr_fixed, np.int32)
+        cm = np.ascontiguousarray(corr_moving, np.int32)
+        info = np.ascontiguousarray(info_diag, np.float32).reshape(-1, 3)
+        assert len(info) == len(fixed_meas)
+        H, b, st = np.zeros(36, np.float64), np.zeros(6, np.float64), np.zeros(5, np.float64)
+        status = np.full(max(len(cf), 1), 255, np.uint8)
+        pr = self._prior(prior)
+        self._chk(lib().pslam_linearize_se3_f32(self._h, C.byref(cfg), _p(pose12), len(moving_xyz), _p(moving_xyz),
+                                                len(fixed_meas), _p(fixed_meas), fixed_meas.shape[1], len(cf), _p(cf), _p(cm),
+                                                _p(info), C.byref(pr) if pr is not None else None, _p(status), _p(H), _p(b), _p(st)))
+        return H.reshape(6, 6), b, dict(chi=st[0], inliers=int(st[1]), outliers=int(st[2]), suppressed=int(st[3]),
+                                        prior_chi=st[4], status=status[:len(cf)].copy())
+
+    def linearize_timed_f32(self, cfg, pose12, moving_xyz, fixed_meas, corr_fixed, corr_moving, info_diag, reps=10):
+        pose12 = np.ascontiguousarray(pose12, np.float64).reshape(12)
+        moving_xyz = np.ascontiguousarray(moving_xyz, np.float32).reshape(-1, 3)
+        fixed_meas = np.ascontiguousarray(fixed_meas, np.float32)
+        cf = np.ascontiguousarray(corr_fixed, np.int32)
+        cm = np.ascontiguousarray(corr_moving, np.int32)
+        info = np.ascontiguousarray(info_diag, np.float32).reshape(-1, 3)
+        ms = C.c_double(0)
+        self._chk(lib().pslam_linearize_se3_timed_f32(self._h, C.byref(cfg), _p(pose12), len(moving_xyz), _p(moving_xyz),
+                                                      len(fixed_meas), _p(fixed_meas), fixed_meas.shape[1], len(cf), _p(cf),
+                                                      _p(cm), _p(info), int(reps), C.byref(ms)))
+        return ms.value
+
+    def gn_iterate_f32(self, cfg, n_iterations, damping, pose12, moving_xyz, fixed_meas, corr_fixed, corr_moving, info_diag,
+                       prior=None):
+        """as gn_iterate on fp32 clouds with the optional pose prior; returns (pose, poses, stats, done, spd_ok, status)"""
+        pose = np.ascontiguousarray(pose12, np.float64).reshape(12).copy()
+        moving_xyz = np.ascontiguousarray(moving_xyz, np.float32).reshape(-1, 3)
+        fixed_meas = np.ascontiguousarray(fixed_meas, np.float32)
+        cf = np.ascontiguousarray(corr_fixed, np.int32)
+        cm = np.ascontiguousarray(corr_moving, np.int32)
+        info = np.ascontiguousarray(info_diag, np.float32).reshape(-1, 3)
+        poses = np.zeros((max(n_iterations, 1), 12), np.float64)
+        stats = np.zeros((max(n_iterations, 1), 4), np.float64)
+        status = np.full(max(len(cf), 1), 255, np.uint8)
+        done = C.c_int(0)
+        pr = self._prior(prior)
+        rc = lib().pslam_gn_iterate_f32(self._h, C.byref(cfg), int(n_iterations), C.c_double(damping), _p(pose), len(moving_xyz),
+                                        _p(moving_xyz), len(fixed_meas), _p(fixed_meas), fixed_meas.shape[1], len(cf), _p(cf),
+                                        _p(cm), _p(info), C.byref(pr) if pr is not None else None, _p(poses), _p(stats),
+                                        _p(status), C.byref(done))
+        if rc != PSLAM_E_NOT_SPD:
+            self._chk(rc)
+        return pose, poses[:done.value], stats[:done.value], done.value, rc != PSLAM_E_NOT_SPD, status[:len(cf)].copy()
 
     def gn_step(self, H, b, damping, pose12):
         H = np.ascontiguousarray(H, np.float64).reshape(36)

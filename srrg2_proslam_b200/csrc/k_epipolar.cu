@@ -557,14 +557,17 @@ static size_t ep_smem_bytes(int M, bool general, bool lean) {
 int pslam_k_epipolar(pslam_ctx* ctx, int n_pairs, const pslam_match_cfg* cfg, int general, int pair_base) {
   const int M = ctx->lim.max_features;
   if (ctx->lim.max_rows > EP_ROWS) general = 1;
-  const bool lean = !general && cfg->epipolar_line_thickness_pixels == 0 && ctx->lim.max_rows <= EP_ROWS_LEAN - 2;
+  // a negative thickness still runs the offset-0 pass in the reference (epipolar_impl.cpp:72-79: the offset list starts
+  // with 0, the +-k entries are appended in a loop that does not execute)
+  const int thickness = cfg->epipolar_line_thickness_pixels < 0 ? 0 : cfg->epipolar_line_thickness_pixels;
+  const bool lean = !general && thickness == 0 && ctx->lim.max_rows <= EP_ROWS_LEAN - 2;
   const size_t smem = ep_smem_bytes(M, general != 0, lean);
   auto kernel = general ? epipolar_kernel<true, false> : (lean ? epipolar_kernel<false, true> : epipolar_kernel<false, false>);
   if (smem > 48 * 1024) PSLAM_CUDA_TRY(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   kernel<<<n_pairs, EP_THREADS, smem, ctx->stream>>>(
     ctx->d_xy, ctx->d_desc, ctx->d_count, M, cfg->maximum_descriptor_distance,
     cfg->maximum_distance_ratio_to_second_best, cfg->maximum_disparity_pixels,
-    cfg->epipolar_line_thickness_pixels, ctx->d_ep_fixed, ctx->d_ep_moving, ctx->d_ep_dist,
+    thickness, ctx->d_ep_fixed, ctx->d_ep_moving, ctx->d_ep_dist,
     ctx->d_ep_count, ctx->d_st_uvuv, ctx->d_st_left, ctx->d_st_right, ctx->d_st_dist,
     ctx->d_st_count, pair_base);
   PSLAM_LAUNCH_CHECK(ctx, "epipolar_kernel");

@@ -102,27 +102,35 @@ __device__ __forceinline__ bool error_and_jacobian(const LinParams& c, const dou
   return true;
 }
 
-// accumulate one correspondence into the thread's partial sums (FactorCorrespondenceDriven_::compute analogue)
-__device__ __forceinline__ void accumulate_correspondence(const LinParams& c, int edim, const double* __restrict__ moving_xyz,
-                                                          const double* __restrict__ fixed_meas, int fixed_dim, int fi, int mi,
-                                                          const double* __restrict__ info_diag, double* acc) {
-  double pm[3] = {moving_xyz[3 * (size_t) mi], moving_xyz[3 * (size_t) mi + 1], moving_xyz[3 * (size_t) mi + 2]};
+// accumulate one correspondence into the thread's partial sums (FactorCorrespondenceDriven_::compute analogue).
+// T = scalar type of the clouds in HBM: float (the reference's own cloud type: 40 B per correspondence, widened to
+// fp64 in registers -- exact) or double.  status (may be nullptr): 0 inlier, 1 kernelized, 2 suppressed.
+template <typename T>
+__device__ __forceinline__ void accumulate_correspondence(const LinParams& c, int edim, const T* __restrict__ moving_xyz,
+                                                          const T* __restrict__ fixed_meas, int fixed_dim, int fi, int mi,
+                                                          const T* __restrict__ info_diag, double* acc, uint8_t* status) {
+  double pm[3] = {(double) moving_xyz[3 * (size_t) mi], (double) moving_xyz[3 * (size_t) mi + 1],
+                  (double) moving_xyz[3 * (size_t) mi + 2]};
   double z[3] = {0, 0, 0};
-  for (int i = 0; i < 3 && i < fixed_dim; ++i) z[i] = fixed_meas[(size_t) fixed_dim * fi + i];
+  for (int i = 0; i < 3 && i < fixed_dim; ++i) z[i] = (double) fixed_meas[(size_t) fixed_dim * fi + i];
   double e[3], J[18];
   if (!error_and_jacobian(c, pm, z, e, J)) {
     acc[30] += 1;
+    if (status) *status = 2;
     return;
   }
-  const double om[3] = {info_diag[3 * (size_t) fi], info_diag[3 * (size_t) fi + 1], info_diag[3 * (size_t) fi + 2]};
+  const double om[3] = {(double) info_diag[3 * (size_t) fi], (double) info_diag[3 * (size_t) fi + 1],
+                        (double) info_diag[3 * (size_t) fi + 2]};
   double chi = 0;
   for (int i = 0; i < edim; ++i) chi = __dadd_rn(chi, __dmul_rn(__dmul_rn(e[i], om[i]), e[i]));
   double scale = 1;
   if (c.robustifier != 0 && chi > c.chi_threshold) {
     acc[29] += 1;
     scale = (c.robustifier == 1) ? __ddiv_rn(c.chi_threshold, chi) : 0.0;
+    if (status) *status = 1;
   } else {
     acc[28] += 1;
+    if (status) *status = 0;
   }
   acc[27] += __dmul_rn(chi, scale);
   for (int i = 0; i < edim; ++i) {
@@ -138,18 +146,20 @@ __device__ __forceinline__ void accumulate_correspondence(const LinParams& c, in
   }
 }
 
+template <typename T>
 __global__ void __launch_bounds__(LZ_THREADS, 2)
-linearize_kernel(LinParams c, const double* __restrict__ moving_xyz,
-                 const double* __restrict__ fixed_meas, int fixed_dim, int n_corr,
+linearize_kernel(LinParams c, const T* __restrict__ moving_xyz,
+                 const T* __restrict__ fixed_meas, int fixed_dim, int n_corr,
                  const int* __restrict__ corr_fixed, const int* __restrict__ corr_moving,
-                 const double* __restrict__ info_diag, double* __restrict__ partials) {
+                 const T* __restrict__ info_diag, double* __restrict__ partials, uint8_t* __restrict__ status) {
   __shared__ double s_part[LZ_THREADS / 32][LZ_NACC];
   double acc[LZ_NACC];
 #pragma unroll
   for (int i = 0; i < LZ_NACC; ++i) acc[i] = 0;
   const int edim = (c.kind == 2) ? 2 : 3;
   for (int k = blockIdx.x * LZ_THREADS + threadIdx.x; k < n_corr; k += gridDim.x * LZ_THREADS)
-    accumulate_correspondence(c, edim, moving_xyz, fixed_meas, fixed_dim, corr_fixed[k], corr_moving[k], info_diag, acc);
+    accumulate_correspondence(c, edim, moving_xyz, fixed_meas, fixed_dim, corr_fixed[k], corr_moving[k], info_diag, acc,
+                              status ? status + k : nullptr);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
   for (int i = 0; i < LZ_NACC - 1; ++i) {
@@ -279,17 +289,113 @@ __global__ void gn_step_kernel(double* __restrict__ io) {
   io[61] = 0;
 }
 
-// ---- fused solver iterations: n_iters x { linearise all correspondences -> H, b -> Cholesky -> pose update } in ONE
-// launch, one CTA per problem.  This is what the aligner runs between two re-projections of the correspondence
+// ---- SE3 pose-prior factor (the shipped aligners' second slice, AlignerSliceMotionModel3D: configurations/kitti.conf:747-772,
+// icl.conf:268-293; srrg2_slam_interfaces / srrg2_solver, restated in oracle/pslam_oracle_solver.hpp::pose_prior_accumulate):
+// e = t2tnq(Z^-1 X), d e_t / d dt = R_E, d e_q / d dq = w I + [v]x, constant information; summed into H, b before the solve.
+struct PriorParams {
+  int enabled;
+  double Zi_R[9], Zi_t[3];  // Z^-1
+  double Omega[36];
+};
+
+__device__ __forceinline__ void t2tnq_dev(const double* R, const double* t, double* v6) {
+  v6[0] = t[0];
+  v6[1] = t[1];
+  v6[2] = t[2];
+  double w, x, y, z;
+  const double tr = R[0] + R[4] + R[8];
+  if (tr > 0) {
+    const double s = sqrt(tr + 1.0) * 2;
+    w = 0.25 * s;
+    x = (R[7] - R[5]) / s;
+    y = (R[2] - R[6]) / s;
+    z = (R[3] - R[1]) / s;
+  } else if (R[0] > R[4] && R[0] > R[8]) {
+    const double s = sqrt(1.0 + R[0] - R[4] - R[8]) * 2;
+    w = (R[7] - R[5]) / s;
+    x = 0.25 * s;
+    y = (R[1] + R[3]) / s;
+    z = (R[2] + R[6]) / s;
+  } else if (R[4] > R[8]) {
+    const double s = sqrt(1.0 + R[4] - R[0] - R[8]) * 2;
+    w = (R[2] - R[6]) / s;
+    x = (R[1] + R[3]) / s;
+    y = 0.25 * s;
+    z = (R[5] + R[7]) / s;
+  } else {
+    const double s = sqrt(1.0 + R[8] - R[0] - R[4]) * 2;
+    w = (R[3] - R[1]) / s;
+    x = (R[2] + R[6]) / s;
+    y = (R[5] + R[7]) / s;
+    z = 0.25 * s;
+  }
+  const double n = sqrt(w * w + x * x + y * y + z * z);
+  const double sgn = (w < 0) ? -1.0 : 1.0;
+  v6[3] = sgn * x / n;
+  v6[4] = sgn * y / n;
+  v6[5] = sgn * z / n;
+}
+
+// H (full 6x6), b += prior; returns chi.  One thread.
+__device__ __noinline__ double pose_prior_accumulate_dev(const PriorParams& pr, const double* R, const double* t, double* H,
+                                                         double* bvec) {
+  double ER[9], Et[3];
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j)
+      ER[3 * i + j] = (pr.Zi_R[3 * i] * R[j] + pr.Zi_R[3 * i + 1] * R[3 + j]) + pr.Zi_R[3 * i + 2] * R[6 + j];
+    Et[i] = ((pr.Zi_R[3 * i] * t[0] + pr.Zi_R[3 * i + 1] * t[1]) + pr.Zi_R[3 * i + 2] * t[2]) + pr.Zi_t[i];
+  }
+  double e[6];
+  t2tnq_dev(ER, Et, e);
+  const double n2 = e[3] * e[3] + e[4] * e[4] + e[5] * e[5];
+  const double w = sqrt(n2 < 1.0 ? 1.0 - n2 : 0.0);
+  double J[36];
+  for (int i = 0; i < 36; ++i) J[i] = 0;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) J[6 * i + j] = ER[3 * i + j];
+  const double vx = e[3], vy = e[4], vz = e[5];
+  const double Q[9] = {w, -vz, vy, vz, w, -vx, -vy, vx, w};
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) J[6 * (3 + i) + 3 + j] = Q[3 * i + j];
+  double OJ[36], Oe[6];
+  for (int i = 0; i < 6; ++i) {
+    double sum = 0;
+    for (int k = 0; k < 6; ++k) sum += pr.Omega[6 * i + k] * e[k];
+    Oe[i] = sum;
+    for (int j = 0; j < 6; ++j) {
+      double a = 0;
+      for (int k = 0; k < 6; ++k) a += pr.Omega[6 * i + k] * J[6 * k + j];
+      OJ[6 * i + j] = a;
+    }
+  }
+  double chi = 0;
+  for (int i = 0; i < 6; ++i) chi += e[i] * Oe[i];
+  for (int a = 0; a < 6; ++a) {
+    double bs = 0;
+    for (int k = 0; k < 6; ++k) bs += J[6 * k + a] * Oe[k];
+    bvec[a] += bs;
+    for (int c = 0; c < 6; ++c) {
+      double hs = 0;
+      for (int k = 0; k < 6; ++k) hs += J[6 * k + a] * OJ[6 * k + c];
+      H[6 * a + c] += hs;
+    }
+  }
+  return chi;
+}
+
+// ---- fused solver iterations: n_iters x { linearise all correspondences -> H, b (+ pose prior) -> Cholesky -> pose update }
+// in ONE launch, one CTA per problem.  This is what the aligner runs between two re-projections of the correspondence
 // finder (the correspondences, hence the information matrices, do not change in between: SURVEY App. E.6), instead
 // of 2 launches + 2 host round trips per iteration.  out (per iteration): 12 pose (after the update) + chi, inliers,
-// outliers, suppressed.  iters_done: iterations completed (stops early when H + damping I is not SPD).
+// outliers, suppressed.  iters_done: iterations completed (stops early when H + damping I is not SPD).  status (may be
+// nullptr): per-correspondence factor status of the LAST linearised iteration (inlier-only runs, icl.conf:55-58).
 constexpr int GN_OUT = 16;
+template <typename T>
 __global__ void __launch_bounds__(LZ_THREADS)
-gn_iterate_kernel(LinParams c0, double damping, int n_iters, const double* __restrict__ moving_xyz,
-                  const double* __restrict__ fixed_meas, int fixed_dim, int n_corr, const int* __restrict__ corr_fixed,
-                  const int* __restrict__ corr_moving, const double* __restrict__ info_diag, double* __restrict__ out,
-                  int* __restrict__ iters_done) {
+gn_iterate_kernel(LinParams c0, PriorParams prior, double damping, int n_iters, const T* __restrict__ moving_xyz,
+                  const T* __restrict__ fixed_meas, int fixed_dim, int n_corr, const int* __restrict__ corr_fixed,
+                  const int* __restrict__ corr_moving, const T* __restrict__ info_diag, double* __restrict__ out,
+                  int* __restrict__ iters_done, uint8_t* __restrict__ status) {
   __shared__ double s_part[LZ_THREADS / 32][LZ_NACC];
   __shared__ double s_sum[LZ_NACC];
   __shared__ double s_R[9], s_t[3];
@@ -311,7 +417,8 @@ gn_iterate_kernel(LinParams c0, double damping, int n_iters, const double* __res
 #pragma unroll
     for (int i = 0; i < LZ_NACC; ++i) acc[i] = 0;
     for (int k = threadIdx.x; k < n_corr; k += LZ_THREADS)
-      accumulate_correspondence(c, edim, moving_xyz, fixed_meas, fixed_dim, corr_fixed[k], corr_moving[k], info_diag, acc);
+      accumulate_correspondence(c, edim, moving_xyz, fixed_meas, fixed_dim, corr_fixed[k], corr_moving[k], info_diag, acc,
+                                status ? status + k : nullptr);
 #pragma unroll
     for (int i = 0; i < LZ_NACC - 1; ++i) {
       const double s = warp_sum(acc[i]);
@@ -336,6 +443,7 @@ gn_iterate_kernel(LinParams c0, double damping, int n_iters, const double* __res
       for (int a = 0; a < 6; ++a) bvec[a] = s_sum[21 + a];
       for (int i = 0; i < 9; ++i) R[i] = s_R[i];
       for (int i = 0; i < 3; ++i) t[i] = s_t[i];
+      if (prior.enabled) pose_prior_accumulate_dev(prior, R, t, H, bvec);
       const bool ok = gn_solve_update(H, bvec, damping, R, t, dx);
       double* o = out + (size_t) it * GN_OUT;
       if (ok) {
@@ -362,15 +470,18 @@ gn_iterate_kernel(LinParams c0, double damping, int n_iters, const double* __res
   }
 }
 
-}  // namespace
+// single linearisation with the optional prior folded in on the device: out46 as linearize_finish_kernel, [46] prior chi
+__global__ void prior_add_kernel(PriorParams prior, LinParams c, double* __restrict__ out) {
+  if (threadIdx.x != 0 || !prior.enabled) return;
+  double H[36], b[6];
+  for (int i = 0; i < 36; ++i) H[i] = out[i];
+  for (int i = 0; i < 6; ++i) b[i] = out[36 + i];
+  out[46] = pose_prior_accumulate_dev(prior, c.R, c.t, H, b);
+  for (int i = 0; i < 36; ++i) out[i] = H[i];
+  for (int i = 0; i < 6; ++i) out[36 + i] = b[i];
+}
 
-int pslam_k_linearize(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, const double* pose12,
-                      int n_moving, const double* d_moving_xyz, int n_fixed,
-                      const double* d_fixed_meas, int fixed_dim, int n_corr, const int* d_corr_fixed,
-                      const int* d_corr_moving, const double* d_info_diag, double* h_H36,
-                      double* h_b6, double* h_stats4) {
-  (void) n_moving;
-  (void) n_fixed;
+LinParams make_params(const pslam_linearize_cfg* cfg, const double* pose12) {
   LinParams c;
   c.kind = cfg->kind;
   c.robustifier = cfg->robustifier;
@@ -384,6 +495,31 @@ int pslam_k_linearize(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, const doub
     for (int j = 0; j < 3; ++j) c.R[3 * i + j] = pose12[4 * i + j];
     c.t[i] = pose12[4 * i + 3];
   }
+  return c;
+}
+
+PriorParams make_prior(const pslam_pose_prior* prior) {
+  PriorParams p;
+  memset(&p, 0, sizeof(p));
+  if (!prior) return p;
+  p.enabled = 1;
+  const double* Z = prior->prediction;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) p.Zi_R[3 * i + j] = Z[4 * j + i];
+  for (int i = 0; i < 3; ++i)
+    p.Zi_t[i] = -((p.Zi_R[3 * i] * Z[3] + p.Zi_R[3 * i + 1] * Z[7]) + p.Zi_R[3 * i + 2] * Z[11]);
+  for (int i = 0; i < 36; ++i) p.Omega[i] = prior->information[i];
+  return p;
+}
+
+}  // namespace
+
+template <typename T>
+int pslam_k_linearize_t(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, const double* pose12, const T* d_moving_xyz,
+                        const T* d_fixed_meas, int fixed_dim, int n_corr, const int* d_corr_fixed,
+                        const int* d_corr_moving, const T* d_info_diag, const pslam_pose_prior* prior, uint8_t* d_status,
+                        double* h_H36, double* h_b6, double* h_stats5) {
+  const LinParams c = make_params(cfg, pose12);
   int blocks = (n_corr + LZ_THREADS - 1) / LZ_THREADS;
   if (blocks < 1) blocks = 1;
   if (blocks > 592) blocks = 592;  // 4 CTAs per SM on 148 SMs
@@ -392,20 +528,30 @@ int pslam_k_linearize(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, const doub
   if (need > ctx->scratch_bytes) return pslam_set_error(ctx, PSLAM_E_CAPACITY, "linearize: scratch too small", cudaSuccess);
   double* partials = reinterpret_cast<double*>(ctx->d_scratch + ctx->scratch_bytes - need);
   double* out = partials + (size_t) blocks * LZ_NACC;
-  linearize_kernel<<<blocks, LZ_THREADS, 0, ctx->stream>>>(c, d_moving_xyz, d_fixed_meas, fixed_dim,
-                                                           n_corr, d_corr_fixed, d_corr_moving,
-                                                           d_info_diag, partials);
+  linearize_kernel<T><<<blocks, LZ_THREADS, 0, ctx->stream>>>(c, d_moving_xyz, d_fixed_meas, fixed_dim, n_corr, d_corr_fixed,
+                                                              d_corr_moving, d_info_diag, partials, d_status);
   PSLAM_LAUNCH_CHECK(ctx, "linearize_kernel");
   linearize_finish_kernel<<<1, 32, 0, ctx->stream>>>(partials, blocks, out);
   PSLAM_LAUNCH_CHECK(ctx, "linearize_finish_kernel");
+  if (prior) {
+    prior_add_kernel<<<1, 32, 0, ctx->stream>>>(make_prior(prior), c, out);
+    PSLAM_LAUNCH_CHECK(ctx, "prior_add_kernel");
+  }
   double* h = reinterpret_cast<double*>(ctx->h_pinned);
-  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(h, out, sizeof(double) * 46, cudaMemcpyDeviceToHost, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(h, out, sizeof(double) * 47, cudaMemcpyDeviceToHost, ctx->stream));
   PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   memcpy(h_H36, h, sizeof(double) * 36);
   memcpy(h_b6, h + 36, sizeof(double) * 6);
-  memcpy(h_stats4, h + 42, sizeof(double) * 4);
+  memcpy(h_stats5, h + 42, sizeof(double) * 4);
+  h_stats5[4] = prior ? h[46] : 0.0;
   return PSLAM_OK;
 }
+template int pslam_k_linearize_t<double>(pslam_ctx*, const pslam_linearize_cfg*, const double*, const double*, const double*, int, int,
+                                         const int*, const int*, const double*, const pslam_pose_prior*, uint8_t*, double*, double*,
+                                         double*);
+template int pslam_k_linearize_t<float>(pslam_ctx*, const pslam_linearize_cfg*, const double*, const float*, const float*, int, int,
+                                        const int*, const int*, const float*, const pslam_pose_prior*, uint8_t*, double*, double*,
+                                        double*);
 
 int pslam_k_gn_step(pslam_ctx* ctx, const double* H36, const double* b6, double damping,
                     double* pose12, double* dx6) {
@@ -426,61 +572,51 @@ int pslam_k_gn_step(pslam_ctx* ctx, const double* H36, const double* b6, double 
   return PSLAM_OK;
 }
 
-int pslam_k_gn_iterate(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, int n_iters, double damping, double* pose12,
-                       int n_moving, const double* h_moving_xyz, int n_fixed, const double* h_fixed_meas, int fixed_dim,
-                       int n_corr, const int* h_corr_fixed, const int* h_corr_moving, const double* h_info_diag,
-                       double* h_out16, int* h_iters_done, int* h_spd) {
-  LinParams c;
-  c.kind = cfg->kind;
-  c.robustifier = cfg->robustifier;
-  for (int i = 0; i < 9; ++i) c.K[i] = cfg->K[i];
-  c.cols = cfg->image_cols;
-  c.rows = cfg->image_rows;
-  for (int i = 0; i < 3; ++i) c.baseline[i] = cfg->baseline[i];
-  c.mean_disparity = cfg->mean_disparity;
-  c.chi_threshold = cfg->chi_threshold;
-  for (int i = 0; i < 3; ++i) {
-    for (int j = 0; j < 3; ++j) c.R[3 * i + j] = pose12[4 * i + j];
-    c.t[i] = pose12[4 * i + 3];
-  }
+// host clouds of scalar type T (float = the reference's cloud type, no widening anywhere; double = legacy entry point)
+template <typename T>
+int pslam_k_gn_iterate_t(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, int n_iters, double damping, double* pose12,
+                         int n_moving, const T* h_moving_xyz, int n_fixed, const T* h_fixed_meas, int fixed_dim,
+                         int n_corr, const int* h_corr_fixed, const int* h_corr_moving, const T* h_info_diag,
+                         const pslam_pose_prior* prior, double* h_out16, uint8_t* h_status, int* h_iters_done, int* h_spd) {
+  const LinParams c = make_params(cfg, pose12);
   auto al = [](size_t x) { return (x + 255) & ~(size_t) 255; };
-  const size_t b_mov = al(24 * (size_t) n_moving), b_fix = al(8 * (size_t) fixed_dim * n_fixed), b_cf = al(4 * (size_t) n_corr),
-               b_info = al(24 * (size_t) n_fixed), b_out = al(8 * (size_t) GN_OUT * n_iters);
-  if (b_mov + b_fix + 2 * b_cf + b_info + b_out + 256 > ctx->scratch_bytes)
-    return pslam_set_error(ctx, PSLAM_E_CAPACITY, "gn_iterate: problem exceeds the scratch buffer", cudaSuccess);
-  if (PSLAM_SOLVER_SCRATCH_OFFSET + b_mov + b_fix + 2 * b_cf + b_info + b_out + 256 > ctx->scratch_bytes)
+  const size_t b_mov = al(3 * sizeof(T) * (size_t) n_moving), b_fix = al(sizeof(T) * (size_t) fixed_dim * n_fixed),
+               b_cf = al(4 * (size_t) n_corr), b_info = al(3 * sizeof(T) * (size_t) n_fixed), b_out = al(8 * (size_t) GN_OUT * n_iters),
+               b_status = h_status ? al((size_t) n_corr) : 0;
+  if (PSLAM_SOLVER_SCRATCH_OFFSET + b_mov + b_fix + 2 * b_cf + b_info + b_out + b_status + 256 > ctx->scratch_bytes)
     return pslam_set_error(ctx, PSLAM_E_CAPACITY, "gn_iterate: problem exceeds the scratch buffer", cudaSuccess);
   uint8_t* p = ctx->d_scratch + PSLAM_SOLVER_SCRATCH_OFFSET;
   uint8_t* const d_in = p;
-  double* d_mov = (double*) p; p += b_mov;
-  double* d_fix = (double*) p; p += b_fix;
+  T* d_mov = (T*) p; p += b_mov;
+  T* d_fix = (T*) p; p += b_fix;
   int* d_cf = (int*) p; p += b_cf;
   int* d_cm = (int*) p; p += b_cf;
-  double* d_info = (double*) p; p += b_info;
+  T* d_info = (T*) p; p += b_info;
   const size_t in_bytes = (size_t) (p - d_in);
   int* d_done = (int*) p; p += 256;  // [iterations done, spd flag], directly in front of the per-iteration rows: one download
-  double* d_out = (double*) p;
-  const size_t out_bytes = 256 + 8 * (size_t) GN_OUT * n_iters;
+  double* d_out = (double*) p; p += b_out;
+  uint8_t* d_status = h_status ? p : nullptr;  // directly behind the rows: still one download
+  const size_t out_bytes = 256 + b_out + b_status;
   // per frame this is called ~20 times on a few hundred points: the call is bound by copy / launch latencies.  The five
   // inputs are packed into the pinned staging block and travel as ONE copy, the results come back as ONE copy.
   uint8_t* h_stage = reinterpret_cast<uint8_t*>(ctx->h_pinned);
   const bool packed = in_bytes + out_bytes <= ctx->pinned_bytes;
   if (packed) {
-    memcpy(h_stage + ((uint8_t*) d_mov - d_in), h_moving_xyz, 24 * (size_t) n_moving);
-    memcpy(h_stage + ((uint8_t*) d_fix - d_in), h_fixed_meas, 8 * (size_t) fixed_dim * n_fixed);
+    memcpy(h_stage + ((uint8_t*) d_mov - d_in), h_moving_xyz, 3 * sizeof(T) * (size_t) n_moving);
+    memcpy(h_stage + ((uint8_t*) d_fix - d_in), h_fixed_meas, sizeof(T) * (size_t) fixed_dim * n_fixed);
     memcpy(h_stage + ((uint8_t*) d_cf - d_in), h_corr_fixed, 4 * (size_t) n_corr);
     memcpy(h_stage + ((uint8_t*) d_cm - d_in), h_corr_moving, 4 * (size_t) n_corr);
-    memcpy(h_stage + ((uint8_t*) d_info - d_in), h_info_diag, 24 * (size_t) n_fixed);
+    memcpy(h_stage + ((uint8_t*) d_info - d_in), h_info_diag, 3 * sizeof(T) * (size_t) n_fixed);
     PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_in, h_stage, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
   } else {
-    PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_mov, h_moving_xyz, 24 * (size_t) n_moving, cudaMemcpyHostToDevice, ctx->stream));
-    PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_fix, h_fixed_meas, 8 * (size_t) fixed_dim * n_fixed, cudaMemcpyHostToDevice, ctx->stream));
+    PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_mov, h_moving_xyz, 3 * sizeof(T) * (size_t) n_moving, cudaMemcpyHostToDevice, ctx->stream));
+    PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_fix, h_fixed_meas, sizeof(T) * (size_t) fixed_dim * n_fixed, cudaMemcpyHostToDevice, ctx->stream));
     PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_cf, h_corr_fixed, 4 * (size_t) n_corr, cudaMemcpyHostToDevice, ctx->stream));
     PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_cm, h_corr_moving, 4 * (size_t) n_corr, cudaMemcpyHostToDevice, ctx->stream));
-    PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_info, h_info_diag, 24 * (size_t) n_fixed, cudaMemcpyHostToDevice, ctx->stream));
+    PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_info, h_info_diag, 3 * sizeof(T) * (size_t) n_fixed, cudaMemcpyHostToDevice, ctx->stream));
   }
-  gn_iterate_kernel<<<1, LZ_THREADS, 0, ctx->stream>>>(c, damping, n_iters, d_mov, d_fix, fixed_dim, n_corr, d_cf, d_cm, d_info,
-                                                      d_out, d_done);
+  gn_iterate_kernel<T><<<1, LZ_THREADS, 0, ctx->stream>>>(c, make_prior(prior), damping, n_iters, d_mov, d_fix, fixed_dim, n_corr,
+                                                         d_cf, d_cm, d_info, d_out, d_done, d_status);
   PSLAM_LAUNCH_CHECK(ctx, "gn_iterate_kernel");
   int h_small[2];
   const int* h = h_small;
@@ -490,9 +626,11 @@ int pslam_k_gn_iterate(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, int n_ite
     PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     h = reinterpret_cast<const int*>(h_res);
     memcpy(h_out16, h_res + 256, 8 * (size_t) GN_OUT * n_iters);
+    if (h_status) memcpy(h_status, h_res + 256 + b_out, (size_t) n_corr);
   } else {
     PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(h_small, d_done, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(h_out16, d_out, 8 * (size_t) GN_OUT * n_iters, cudaMemcpyDeviceToHost, ctx->stream));
+    if (h_status) PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(h_status, d_status, (size_t) n_corr, cudaMemcpyDeviceToHost, ctx->stream));
     PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   }
   const int done = h[0];
@@ -501,3 +639,9 @@ int pslam_k_gn_iterate(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, int n_ite
   if (done > 0) memcpy(pose12, h_out16 + (size_t) (done - 1) * GN_OUT, sizeof(double) * 12);
   return PSLAM_OK;
 }
+template int pslam_k_gn_iterate_t<double>(pslam_ctx*, const pslam_linearize_cfg*, int, double, double*, int, const double*, int,
+                                          const double*, int, int, const int*, const int*, const double*, const pslam_pose_prior*,
+                                          double*, uint8_t*, int*, int*);
+template int pslam_k_gn_iterate_t<float>(pslam_ctx*, const pslam_linearize_cfg*, int, double, double*, int, const float*, int,
+                                         const float*, int, int, const int*, const int*, const float*, const pslam_pose_prior*,
+                                         double*, uint8_t*, int*, int*);

@@ -14,6 +14,7 @@
 // which equals the reference's sequential best / second-best update with "first wins" ties.
 #include <float.h>
 
+#include <atomic>
 #include <unordered_map>
 #include <vector>
 
@@ -255,11 +256,17 @@ struct ProjState {
   int* d_nproj;
 };
 
+static std::atomic<unsigned long long> g_proj_epoch{0};  // process-wide: epochs of different contexts never coincide
+
 static int proj_layout(pslam_ctx* ctx, ProjState& st, int n_fixed, int dim, int n_moving) {
-  uint8_t* p = ctx->d_scratch;
   const int M = PSLAM_MAX_FEATURES_HARD * 2;  // generous fixed-size regions so that set_* calls are independent
   if (n_fixed > M || n_moving > 65536)
     return pslam_set_error(ctx, PSLAM_E_CAPACITY, "projective: too many points", cudaSuccess);
+  if (!ctx->d_proj) {  // the cache lives in its own allocation: nothing else carves from it
+    ctx->proj_bytes = PSLAM_SOLVER_SCRATCH_OFFSET;
+    PSLAM_CUDA_TRY(ctx, cudaMalloc(&ctx->d_proj, ctx->proj_bytes));
+  }
+  uint8_t* p = ctx->d_proj;
   st.d_fixed = (float*) p; p += al256(sizeof(float) * 4 * (size_t) M);
   st.d_desc_fixed = (uint32_t*) p; p += al256(32 * (size_t) M);
   st.d_lattice = (unsigned long long*) p; p += al256(8 * (size_t) M);
@@ -271,8 +278,8 @@ static int proj_layout(pslam_ctx* ctx, ProjState& st, int n_fixed, int dim, int 
   st.d_moving = (float*) p; p += al256(sizeof(float) * 3 * (size_t) 65536);
   st.d_desc_moving = (uint32_t*) p; p += al256(32 * (size_t) 65536);
   st.d_cand = (int*) p; p += al256(16 * (size_t) 65536);
-  if ((size_t) (p - ctx->d_scratch) > PSLAM_SOLVER_SCRATCH_OFFSET || PSLAM_SOLVER_SCRATCH_OFFSET > ctx->scratch_bytes)
-    return pslam_set_error(ctx, PSLAM_E_CAPACITY, "projective: scratch too small", cudaSuccess);
+  if ((size_t) (p - ctx->d_proj) > ctx->proj_bytes)
+    return pslam_set_error(ctx, PSLAM_E_CAPACITY, "projective: cache allocation too small", cudaSuccess);
   st.n_fixed = n_fixed;
   st.fixed_dim = dim;
   st.n_moving = n_moving;
@@ -284,6 +291,7 @@ int pslam_k_projective_set_fixed(pslam_ctx* ctx, int n_fixed, const float* h_coo
   ProjState st;
   int rc = proj_layout(ctx, st, n_fixed, dim, 0);
   if (rc) return rc;
+  ctx->proj_fixed_epoch = ++g_proj_epoch;
   if (n_fixed == 0) return PSLAM_OK;
   if (n_fixed >= 32767)
     return pslam_set_error(ctx, PSLAM_E_INVALID, "projective: int16 lattice needs < 32767 fixed points", cudaSuccess);
@@ -302,6 +310,7 @@ int pslam_k_projective_set_moving(pslam_ctx* ctx, int n_moving, const float* h_x
   ProjState st;
   int rc = proj_layout(ctx, st, 0, 2, n_moving);
   if (rc) return rc;
+  ctx->proj_moving_epoch = ++g_proj_epoch;
   if (n_moving == 0) return PSLAM_OK;
   PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(st.d_moving, h_xyz, sizeof(float) * 3 * (size_t) n_moving, cudaMemcpyHostToDevice, ctx->stream));
   PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(st.d_desc_moving, h_desc, 32 * (size_t) n_moving, cudaMemcpyHostToDevice, ctx->stream));
@@ -336,7 +345,7 @@ int pslam_k_projective_match(pslam_ctx* ctx, int n_fixed, int n_moving, const fl
   projective_search_kernel<<<(n_moving + PJ_WARPS - 1) / PJ_WARPS, PJ_WARPS * 32, smem, ctx->stream>>>(
     pp, st.d_moving, n_moving, st.d_desc_moving, st.d_lattice, n_fixed, st.d_desc_fixed, st.d_cand, nullptr);
   PSLAM_LAUNCH_CHECK(ctx, "projective_search_kernel");
-  // one filter launch, one download (see filter_fused_kernel); the result block lives above the finder's cache partition
+  // one filter launch, one download (see filter_fused_kernel); the result block is transient: generic scratch
   const size_t n_words = 1 + 2 * (size_t) n_fixed + 4 * (size_t) n_moving;
   if (PSLAM_SOLVER_SCRATCH_OFFSET + 4 * n_words > ctx->scratch_bytes)
     return pslam_set_error(ctx, PSLAM_E_CAPACITY, "projective: scratch too small for the result block", cudaSuccess);

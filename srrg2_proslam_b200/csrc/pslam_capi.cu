@@ -216,6 +216,9 @@ int pslam_create(int device, const pslam_limits* lim, pslam_ctx** out) {
   memset(ctx, 0, sizeof(*ctx));
   ctx->device = device;
   ctx->lim = *lim;
+  // per-image capacities are strides of 16-bit / 32-bit shared-memory arrays in the matchers (k_epipolar.cu): an odd
+  // capacity would misalign them.  The capacity is an upper bound, so it is rounded up (8 <= PSLAM_MAX_FEATURES_HARD's grain)
+  ctx->lim.max_features = (lim->max_features + 7) & ~7;
   *out = ctx;  // returned even on failure so that pslam_last_error is readable; caller destroys
   PSLAM_CUDA_TRY(ctx, cudaSetDevice(device));
   PSLAM_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
@@ -231,7 +234,7 @@ int pslam_create(int device, const pslam_limits* lim, pslam_ctx** out) {
   ctx->map_pitch = round_up(lim->max_cols, 128);
   ctx->img_slot = (size_t) ctx->img_pitch * lim->max_rows;
   ctx->map_slot = (size_t) ctx->map_pitch * lim->max_rows;
-  const size_t NI = lim->max_images, MF = lim->max_features, NP = (lim->max_images + 1) / 2;
+  const size_t NI = lim->max_images, MF = ctx->lim.max_features, NP = (lim->max_images + 1) / 2;
   const size_t NW = ctx->work_images;
   PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_images, 2 * NW * ctx->img_slot));
   PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_row_kp, NW * lim->max_rows * (size_t) ctx->map_pitch));
@@ -280,7 +283,7 @@ void pslam_destroy(pslam_ctx* ctx) {
                   ctx->d_sel_count, ctx->d_xy, ctx->d_resp, ctx->d_inten, ctx->d_desc, ctx->d_count,
                   ctx->d_st_uvuv, ctx->d_st_left, ctx->d_st_right, ctx->d_st_dist, ctx->d_st_count,
                   ctx->d_ep_fixed, ctx->d_ep_moving, ctx->d_ep_dist, ctx->d_ep_count, ctx->d_flags,
-                  ctx->d_sel_bounds, ctx->d_scratch};
+                  ctx->d_sel_bounds, ctx->d_scratch, ctx->d_proj};
   for (void* b : bufs)
     if (b) cudaFree(b);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
@@ -514,6 +517,17 @@ int pslam_match_epipolar(pslam_ctx* ctx, int n_fixed, const float* xy_fixed, con
                          const pslam_match_cfg* cfg, int capacity, int* fixed_idx, int* moving_idx,
                          float* distance) {
   if (!ctx || !cfg || n_fixed < 0 || n_moving < 0 || ctx->lim.max_images < 2) return PSLAM_E_INVALID;
+  // Feature{int32 row, col} (epipolar_impl.cpp:8-20) travels as a packed sort key with 16-bit columns and 15-bit rows:
+  // coordinates outside [0, 65536) x [0, 32768) would order differently from the reference's signed std::sort -- refuse
+  auto in_range = [](int n, const float* xy) {
+    for (int i = 0; i < n; ++i) {
+      const float x = xy[2 * (size_t) i], y = xy[2 * (size_t) i + 1];
+      if (!(x >= 0.f && x < 65536.f && y >= 0.f && y < 32768.f)) return false;
+    }
+    return true;
+  };
+  if (!in_range(n_fixed, xy_fixed) || !in_range(n_moving, xy_moving))
+    return pslam_set_error(ctx, PSLAM_E_INVALID, "match_epipolar: coordinates outside [0, 65536) x [0, 32768)", cudaSuccess);
   PSLAM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   int rc;
   if ((rc = upload_cloud(ctx, 0, n_fixed, xy_fixed, desc_fixed))) return rc;
@@ -1247,10 +1261,18 @@ int pslam_projective_set_moving(pslam_ctx* ctx, int n_moving, const float* xyz, 
   PSLAM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   return pslam_k_projective_set_moving(ctx, n_moving, xyz, desc);
 }
+int pslam_projective_cache_epochs(const pslam_ctx* ctx, unsigned long long* fixed_epoch, unsigned long long* moving_epoch) {
+  if (!ctx) return PSLAM_E_INVALID;
+  if (fixed_epoch) *fixed_epoch = ctx->proj_fixed_epoch;
+  if (moving_epoch) *moving_epoch = ctx->proj_moving_epoch;
+  return PSLAM_OK;
+}
 int pslam_projective_match(pslam_ctx* ctx, int n_fixed, int n_moving, const float* pose12,
                            const pslam_projective_cfg* cfg, int capacity, int* fixed_idx,
                            int* moving_idx, float* distance, int* n_projected) {
   if (!ctx || !cfg || !pose12) return PSLAM_E_INVALID;
+  if (ctx->proj_fixed_epoch == 0 || ctx->proj_moving_epoch == 0)
+    return pslam_set_error(ctx, PSLAM_E_INVALID, "projective_match: set_fixed / set_moving have not been called on this context", cudaSuccess);
   PSLAM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   return pslam_k_projective_match(ctx, n_fixed, n_moving, pose12, cfg, capacity, fixed_idx, moving_idx, distance, n_projected);
 }
@@ -1266,10 +1288,13 @@ int pslam_match_projective(pslam_ctx* ctx, int n_fixed, const float* fixed_coord
 }
 
 // ---- stages 3 + 4 -------------------------------------------------------------------------------
-int pslam_linearize_se3(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, const double* pose12,
-                        int n_moving, const double* moving_xyz, int n_fixed, const double* fixed_meas,
-                        int fixed_dim, int n_corr, const int* corr_fixed, const int* corr_moving,
-                        const double* info_diag, double* H36, double* b6, double* stats4) {
+}  // extern "C"
+namespace {
+template <typename T>
+int linearize_host(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, const double* pose12, int n_moving, const T* moving_xyz,
+                   int n_fixed, const T* fixed_meas, int fixed_dim, int n_corr, const int* corr_fixed, const int* corr_moving,
+                   const T* info_diag, const pslam_pose_prior* prior, uint8_t* factor_status, double* H36, double* b6,
+                   double* stats5) {
   if (!ctx || !cfg || !pose12 || n_corr < 0 || fixed_dim < 2 || fixed_dim > 4) return PSLAM_E_INVALID;
   if (cfg->kind < 0 || cfg->kind > 2 || cfg->robustifier < 0 || cfg->robustifier > 2) return PSLAM_E_INVALID;
   PSLAM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -1283,34 +1308,40 @@ int pslam_linearize_se3(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, const do
     p += (bytes + 255) & ~(size_t) 255;
     return r;
   };
-  double* d_mv = (double*) carve(sizeof(double) * 3 * (size_t) n_moving);
-  double* d_fx = (double*) carve(sizeof(double) * fixed_dim * (size_t) n_fixed);
-  double* d_info = (double*) carve(sizeof(double) * 3 * (size_t) n_fixed);
+  T* d_mv = (T*) carve(sizeof(T) * 3 * (size_t) n_moving);
+  T* d_fx = (T*) carve(sizeof(T) * fixed_dim * (size_t) n_fixed);
+  T* d_info = (T*) carve(sizeof(T) * 3 * (size_t) n_fixed);
   int* d_cf = (int*) carve(sizeof(int) * (size_t) n_corr);
   int* d_cm = (int*) carve(sizeof(int) * (size_t) n_corr);
+  uint8_t* d_status = factor_status ? carve((size_t) n_corr) : nullptr;
   if ((size_t) (p - ctx->d_scratch) + (1 << 20) > ctx->scratch_bytes)
     return pslam_set_error(ctx, PSLAM_E_CAPACITY, "linearize: scratch too small", cudaSuccess);
-  if (n_moving) PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_mv, moving_xyz, sizeof(double) * 3 * (size_t) n_moving, cudaMemcpyHostToDevice, ctx->stream));
+  if (n_moving) PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_mv, moving_xyz, sizeof(T) * 3 * (size_t) n_moving, cudaMemcpyHostToDevice, ctx->stream));
   if (n_fixed) {
-    PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_fx, fixed_meas, sizeof(double) * fixed_dim * (size_t) n_fixed, cudaMemcpyHostToDevice, ctx->stream));
-    PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_info, info_diag, sizeof(double) * 3 * (size_t) n_fixed, cudaMemcpyHostToDevice, ctx->stream));
+    PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_fx, fixed_meas, sizeof(T) * fixed_dim * (size_t) n_fixed, cudaMemcpyHostToDevice, ctx->stream));
+    PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_info, info_diag, sizeof(T) * 3 * (size_t) n_fixed, cudaMemcpyHostToDevice, ctx->stream));
   }
   if (n_corr) {
     PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_cf, corr_fixed, sizeof(int) * (size_t) n_corr, cudaMemcpyHostToDevice, ctx->stream));
     PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_cm, corr_moving, sizeof(int) * (size_t) n_corr, cudaMemcpyHostToDevice, ctx->stream));
   }
-  return pslam_k_linearize(ctx, cfg, pose12, n_moving, d_mv, n_fixed, d_fx, fixed_dim, n_corr, d_cf, d_cm, d_info, H36, b6, stats4);
+  int rc = pslam_k_linearize_t<T>(ctx, cfg, pose12, d_mv, d_fx, fixed_dim, n_corr, d_cf, d_cm, d_info, prior, d_status, H36, b6, stats5);
+  if (rc == PSLAM_OK && factor_status && n_corr) {
+    PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(factor_status, d_status, (size_t) n_corr, cudaMemcpyDeviceToHost, ctx->stream));
+    PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return rc;
 }
 
 // bench.py's H,b throughput line: inputs uploaded once into temporary device buffers (a batched synthetic does not fit
 // the context scratch), `reps` linearise + reduce passes timed with CUDA events on the context's stream
-int pslam_linearize_se3_timed(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, const double* pose12, int n_moving,
-                              const double* moving_xyz, int n_fixed, const double* fixed_meas, int fixed_dim, int n_corr,
-                              const int* corr_fixed, const int* corr_moving, const double* info_diag, int reps,
-                              double* ms_per_call) {
+template <typename T>
+int linearize_timed_host(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, const double* pose12, int n_moving, const T* moving_xyz,
+                         int n_fixed, const T* fixed_meas, int fixed_dim, int n_corr, const int* corr_fixed, const int* corr_moving,
+                         const T* info_diag, int reps, double* ms_per_call) {
   if (!ctx || !cfg || !pose12 || !ms_per_call || n_corr <= 0 || reps <= 0 || fixed_dim < 2 || fixed_dim > 4) return PSLAM_E_INVALID;
   PSLAM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  double *d_mv = nullptr, *d_fx = nullptr, *d_info = nullptr;
+  T *d_mv = nullptr, *d_fx = nullptr, *d_info = nullptr;
   int *d_cf = nullptr, *d_cm = nullptr;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   int rc = PSLAM_OK;
@@ -1331,25 +1362,25 @@ int pslam_linearize_se3_timed(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, co
       return pslam_set_error(ctx, PSLAM_E_CUDA, #call, e__);                   \
     }                                                                          \
   } while (0)
-  TIMED_TRY(cudaMalloc(&d_mv, sizeof(double) * 3 * (size_t) n_moving));
-  TIMED_TRY(cudaMalloc(&d_fx, sizeof(double) * fixed_dim * (size_t) n_fixed));
-  TIMED_TRY(cudaMalloc(&d_info, sizeof(double) * 3 * (size_t) n_fixed));
+  TIMED_TRY(cudaMalloc(&d_mv, sizeof(T) * 3 * (size_t) n_moving));
+  TIMED_TRY(cudaMalloc(&d_fx, sizeof(T) * fixed_dim * (size_t) n_fixed));
+  TIMED_TRY(cudaMalloc(&d_info, sizeof(T) * 3 * (size_t) n_fixed));
   TIMED_TRY(cudaMalloc(&d_cf, sizeof(int) * (size_t) n_corr));
   TIMED_TRY(cudaMalloc(&d_cm, sizeof(int) * (size_t) n_corr));
-  TIMED_TRY(cudaMemcpyAsync(d_mv, moving_xyz, sizeof(double) * 3 * (size_t) n_moving, cudaMemcpyHostToDevice, ctx->stream));
-  TIMED_TRY(cudaMemcpyAsync(d_fx, fixed_meas, sizeof(double) * fixed_dim * (size_t) n_fixed, cudaMemcpyHostToDevice, ctx->stream));
-  TIMED_TRY(cudaMemcpyAsync(d_info, info_diag, sizeof(double) * 3 * (size_t) n_fixed, cudaMemcpyHostToDevice, ctx->stream));
+  TIMED_TRY(cudaMemcpyAsync(d_mv, moving_xyz, sizeof(T) * 3 * (size_t) n_moving, cudaMemcpyHostToDevice, ctx->stream));
+  TIMED_TRY(cudaMemcpyAsync(d_fx, fixed_meas, sizeof(T) * fixed_dim * (size_t) n_fixed, cudaMemcpyHostToDevice, ctx->stream));
+  TIMED_TRY(cudaMemcpyAsync(d_info, info_diag, sizeof(T) * 3 * (size_t) n_fixed, cudaMemcpyHostToDevice, ctx->stream));
   TIMED_TRY(cudaMemcpyAsync(d_cf, corr_fixed, sizeof(int) * (size_t) n_corr, cudaMemcpyHostToDevice, ctx->stream));
   TIMED_TRY(cudaMemcpyAsync(d_cm, corr_moving, sizeof(int) * (size_t) n_corr, cudaMemcpyHostToDevice, ctx->stream));
   TIMED_TRY(cudaEventCreate(&e0));
   TIMED_TRY(cudaEventCreate(&e1));
-  double H[36], b[6], st[4];
+  double H[36], b[6], st[5];
   for (int w = 0; w < 2 && rc == PSLAM_OK; ++w)
-    rc = pslam_k_linearize(ctx, cfg, pose12, n_moving, d_mv, n_fixed, d_fx, fixed_dim, n_corr, d_cf, d_cm, d_info, H, b, st);
+    rc = pslam_k_linearize_t<T>(ctx, cfg, pose12, d_mv, d_fx, fixed_dim, n_corr, d_cf, d_cm, d_info, nullptr, nullptr, H, b, st);
   if (rc == PSLAM_OK) {
     TIMED_TRY(cudaEventRecord(e0, ctx->stream));
     for (int r = 0; r < reps && rc == PSLAM_OK; ++r)
-      rc = pslam_k_linearize(ctx, cfg, pose12, n_moving, d_mv, n_fixed, d_fx, fixed_dim, n_corr, d_cf, d_cm, d_info, H, b, st);
+      rc = pslam_k_linearize_t<T>(ctx, cfg, pose12, d_mv, d_fx, fixed_dim, n_corr, d_cf, d_cm, d_info, nullptr, nullptr, H, b, st);
     TIMED_TRY(cudaEventRecord(e1, ctx->stream));
     TIMED_TRY(cudaEventSynchronize(e1));
     float ms = 0;
@@ -1361,10 +1392,11 @@ int pslam_linearize_se3_timed(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, co
   return rc;
 }
 
-int pslam_gn_iterate(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, int n_iterations, double damping, double* pose12,
-                     int n_moving, const double* moving_xyz, int n_fixed, const double* fixed_meas, int fixed_dim,
-                     int n_corr, const int* corr_fixed, const int* corr_moving, const double* info_diag,
-                     double* poses12, double* stats4, int* iterations_done) {
+template <typename T>
+int gn_iterate_host(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, int n_iterations, double damping, double* pose12, int n_moving,
+                    const T* moving_xyz, int n_fixed, const T* fixed_meas, int fixed_dim, int n_corr, const int* corr_fixed,
+                    const int* corr_moving, const T* info_diag, const pslam_pose_prior* prior, double* poses12, double* stats4,
+                    uint8_t* factor_status, int* iterations_done) {
   if (iterations_done) *iterations_done = 0;
   if (!ctx || !cfg || !pose12 || n_corr < 0 || n_iterations < 0 || fixed_dim < 2 || fixed_dim > 4) return PSLAM_E_INVALID;
   if (cfg->kind < 0 || cfg->kind > 2 || cfg->robustifier < 0 || cfg->robustifier > 2) return PSLAM_E_INVALID;
@@ -1376,8 +1408,8 @@ int pslam_gn_iterate(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, int n_itera
       return pslam_set_error(ctx, PSLAM_E_INVALID, "gn_iterate: correspondence index out of range", cudaSuccess);
   std::vector<double> out(16 * (size_t) n_iterations);
   int done = 0, spd = 1;
-  int rc = pslam_k_gn_iterate(ctx, cfg, n_iterations, damping, pose12, n_moving, moving_xyz, n_fixed, fixed_meas, fixed_dim, n_corr,
-                              corr_fixed, corr_moving, info_diag, out.data(), &done, &spd);
+  int rc = pslam_k_gn_iterate_t<T>(ctx, cfg, n_iterations, damping, pose12, n_moving, moving_xyz, n_fixed, fixed_meas, fixed_dim,
+                                   n_corr, corr_fixed, corr_moving, info_diag, prior, out.data(), factor_status, &done, &spd);
   if (rc) return rc;
   for (int i = 0; i < done; ++i) {
     if (poses12) memcpy(poses12 + 12 * (size_t) i, out.data() + 16 * (size_t) i, sizeof(double) * 12);
@@ -1386,6 +1418,55 @@ int pslam_gn_iterate(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, int n_itera
   if (iterations_done) *iterations_done = done;
   if (!spd) return pslam_set_error(ctx, PSLAM_E_NOT_SPD, "gn_iterate: H + damping*I is not positive definite", cudaSuccess);
   return PSLAM_OK;
+}
+}  // namespace
+extern "C" {
+
+int pslam_linearize_se3(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, const double* pose12,
+                        int n_moving, const double* moving_xyz, int n_fixed, const double* fixed_meas,
+                        int fixed_dim, int n_corr, const int* corr_fixed, const int* corr_moving,
+                        const double* info_diag, double* H36, double* b6, double* stats4) {
+  double st[5];
+  const int rc = linearize_host<double>(ctx, cfg, pose12, n_moving, moving_xyz, n_fixed, fixed_meas, fixed_dim, n_corr, corr_fixed,
+                                        corr_moving, info_diag, nullptr, nullptr, H36, b6, st);
+  if (rc == PSLAM_OK) memcpy(stats4, st, sizeof(double) * 4);
+  return rc;
+}
+int pslam_linearize_se3_f32(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, const double* pose12, int n_moving,
+                            const float* moving_xyz, int n_fixed, const float* fixed_meas, int fixed_dim, int n_corr,
+                            const int* corr_fixed, const int* corr_moving, const float* info_diag,
+                            const pslam_pose_prior* prior, uint8_t* factor_status, double* H36, double* b6, double* stats5) {
+  return linearize_host<float>(ctx, cfg, pose12, n_moving, moving_xyz, n_fixed, fixed_meas, fixed_dim, n_corr, corr_fixed,
+                               corr_moving, info_diag, prior, factor_status, H36, b6, stats5);
+}
+int pslam_linearize_se3_timed(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, const double* pose12, int n_moving,
+                              const double* moving_xyz, int n_fixed, const double* fixed_meas, int fixed_dim, int n_corr,
+                              const int* corr_fixed, const int* corr_moving, const double* info_diag, int reps,
+                              double* ms_per_call) {
+  return linearize_timed_host<double>(ctx, cfg, pose12, n_moving, moving_xyz, n_fixed, fixed_meas, fixed_dim, n_corr, corr_fixed,
+                                      corr_moving, info_diag, reps, ms_per_call);
+}
+int pslam_linearize_se3_timed_f32(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, const double* pose12, int n_moving,
+                                  const float* moving_xyz, int n_fixed, const float* fixed_meas, int fixed_dim, int n_corr,
+                                  const int* corr_fixed, const int* corr_moving, const float* info_diag, int reps,
+                                  double* ms_per_call) {
+  return linearize_timed_host<float>(ctx, cfg, pose12, n_moving, moving_xyz, n_fixed, fixed_meas, fixed_dim, n_corr, corr_fixed,
+                                     corr_moving, info_diag, reps, ms_per_call);
+}
+int pslam_gn_iterate(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, int n_iterations, double damping, double* pose12,
+                     int n_moving, const double* moving_xyz, int n_fixed, const double* fixed_meas, int fixed_dim,
+                     int n_corr, const int* corr_fixed, const int* corr_moving, const double* info_diag,
+                     double* poses12, double* stats4, int* iterations_done) {
+  return gn_iterate_host<double>(ctx, cfg, n_iterations, damping, pose12, n_moving, moving_xyz, n_fixed, fixed_meas, fixed_dim,
+                                 n_corr, corr_fixed, corr_moving, info_diag, nullptr, poses12, stats4, nullptr, iterations_done);
+}
+int pslam_gn_iterate_f32(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, int n_iterations, double damping, double* pose12,
+                         int n_moving, const float* moving_xyz, int n_fixed, const float* fixed_meas, int fixed_dim,
+                         int n_corr, const int* corr_fixed, const int* corr_moving, const float* info_diag,
+                         const pslam_pose_prior* prior, double* poses12, double* stats4, uint8_t* factor_status,
+                         int* iterations_done) {
+  return gn_iterate_host<float>(ctx, cfg, n_iterations, damping, pose12, n_moving, moving_xyz, n_fixed, fixed_meas, fixed_dim,
+                                n_corr, corr_fixed, corr_moving, info_diag, prior, poses12, stats4, factor_status, iterations_done);
 }
 
 int pslam_gn_step(pslam_ctx* ctx, const double* H36, const double* b6, double damping, double* pose12,

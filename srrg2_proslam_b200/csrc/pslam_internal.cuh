@@ -71,6 +71,12 @@ struct pslam_ctx {
   size_t scratch_bytes;
   void* h_pinned;  // small pinned staging (counts, flags, H/b)
   size_t pinned_bytes;
+  // projective finder cache (fixed cloud + row-sorted lattice, moving cloud): its OWN allocation (made on first use), so
+  // that no other entry point's scratch use can clobber it; the epochs change with every upload and are unique per
+  // process, so a caller can tell whether the cache still holds what IT uploaded (pslam_projective_cache_epochs)
+  uint8_t* d_proj;
+  size_t proj_bytes;
+  unsigned long long proj_fixed_epoch, proj_moving_epoch;
   // geometry of the last batch
   int rows, cols, n_images;
   // optional per-kernel device timing (pslam_profile_*): one CUDA event after every launch; the interval

@@ -51,16 +51,17 @@ int pslam_k_projective_match(pslam_ctx* ctx, int n_fixed, int n_moving, const fl
                              const pslam_projective_cfg* cfg, int capacity, int* h_fixed,
                              int* h_moving, float* h_dist, int* n_projected);
 
-// k_linearize.cu
-int pslam_k_linearize(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, const double* pose12,
-                      int n_moving, const double* d_moving_xyz, int n_fixed,
-                      const double* d_fixed_meas, int fixed_dim, int n_corr, const int* d_corr_fixed,
-                      const int* d_corr_moving, const double* d_info_diag, double* h_H36,
-                      double* h_b6, double* h_stats4);
-int pslam_k_gn_iterate(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, int n_iters, double damping, double* pose12,
-                       int n_moving, const double* h_moving_xyz, int n_fixed, const double* h_fixed_meas, int fixed_dim,
-                       int n_corr, const int* h_corr_fixed, const int* h_corr_moving, const double* h_info_diag,
-                       double* h_out16, int* h_iters_done, int* h_spd);
+// k_linearize.cu  (T = float | double: scalar type of the clouds)
+template <typename T>
+int pslam_k_linearize_t(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, const double* pose12, const T* d_moving_xyz,
+                        const T* d_fixed_meas, int fixed_dim, int n_corr, const int* d_corr_fixed,
+                        const int* d_corr_moving, const T* d_info_diag, const pslam_pose_prior* prior, uint8_t* d_status,
+                        double* h_H36, double* h_b6, double* h_stats5);
+template <typename T>
+int pslam_k_gn_iterate_t(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, int n_iters, double damping, double* pose12,
+                         int n_moving, const T* h_moving_xyz, int n_fixed, const T* h_fixed_meas, int fixed_dim,
+                         int n_corr, const int* h_corr_fixed, const int* h_corr_moving, const T* h_info_diag,
+                         const pslam_pose_prior* prior, double* h_out16, uint8_t* h_status, int* h_iters_done, int* h_spd);
 int pslam_k_gn_step(pslam_ctx* ctx, const double* H36, const double* b6, double damping,
                     double* pose12, double* dx6);
 

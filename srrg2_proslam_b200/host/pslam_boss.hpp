@@ -262,6 +262,13 @@ public:
     _value.push_back(std::move(v));
     touch();
   }
+  size_t size() const { return _value.size(); }
+  // srrg2_core PropertyConfigurableVector_::setValue(index, pointer) (tests/test_aligners.cpp:901)
+  void setValue(size_t index, std::shared_ptr<T> v) {
+    if (index >= _value.size()) throw std::runtime_error("property '" + _name + "': index out of range");
+    _value[index] = std::move(v);
+    touch();
+  }
   void fromConf(const ConfValue& v, const Resolver& resolve) override {
     if (v.kind != ConfValue::Array) throw std::runtime_error("property '" + _name + "': array of #pointer expected");
     _value.clear();

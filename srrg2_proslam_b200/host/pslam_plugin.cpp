@@ -230,6 +230,43 @@ void IntensityFeatureExtractorSelectiveCUDA::init() {
   _config_changed = false;
 }
 
+// detection_mask_tracking of selective.cpp:63-144: one rectangle per projection, half-size = radius + base_radius (10),
+// clipped at the top / left border, its extent cut at the bottom / right border; four variants (full bars to the left /
+// right image border).  Host-side integer work; pinned through the reference's own constants (94 seeds -> 719 / 581 /
+// 294 / 237 candidates, tests/test_feature_extractors.cpp:182-213) in tests/test_plugin_cpu.py.
+void IntensityFeatureExtractorSelectiveCUDA::paintTrackingMask(int rows, int cols, const PointIntensityDescriptorCloud& projections,
+                                                               int projection_detection_radius, std::vector<uint8_t>& mask) const {
+  constexpr int16_t base_radius = 10;
+  const int16_t radius_pixels = (int16_t) (projection_detection_radius + base_radius);
+  const int16_t radius_x2 = 2 * radius_pixels;
+  mask.assign((size_t) rows * cols, 0);
+  const bool to_left = param_enable_full_distance_to_left.value(), to_right = param_enable_full_distance_to_right.value();
+  for (size_t k = 0; k < projections.size(); ++k) {
+    const float* c = projections.point(k);
+    const int16_t row = (int16_t) std::round(c[1]), col = (int16_t) std::round(c[0]);
+    const int16_t tl_row = std::max<int>(row - radius_pixels, 0);
+    const int16_t height = std::min<int16_t>(radius_x2, (int16_t) (rows - tl_row));
+    int x0, w;
+    if (to_left && to_right) {
+      x0 = 0;
+      w = cols;
+    } else if (to_left) {
+      x0 = 0;
+      w = col;
+    } else if (to_right) {
+      x0 = col;
+      w = (int16_t) (cols - col);
+    } else {
+      const int16_t tl_col = std::max<int>(col - radius_pixels, 0);
+      x0 = tl_col;
+      w = std::min<int16_t>(radius_x2, (int16_t) (cols - tl_col));
+    }
+    // cv::Mat(rect).setTo(1); a rectangle reaching outside the image asserts in the reference
+    for (int r = tl_row; r < tl_row + height && r < rows; ++r)
+      for (int x = std::max(x0, 0); x < x0 + w && x < cols; ++x) mask[(size_t) r * cols + x] = 1;
+  }
+}
+
 int IntensityFeatureExtractorSelectiveCUDA::extract(pslam_ctx* ctx, const ImageView& image, int capacity, float* xy,
                                                     float* response, float* intensity, uint8_t* desc) {
   const pslam_extract_cfg cfg = cudaConfig();
@@ -237,35 +274,7 @@ int IntensityFeatureExtractorSelectiveCUDA::extract(pslam_ctx* ctx, const ImageV
   if (_projections && !_projections->empty()) {
     // tracking phase (selective.cpp:63-178): rectangles of half-size radius + 10 around the projections
     const int rows = image.rows, cols = image.cols;
-    constexpr int16_t base_radius = 10;
-    const int16_t radius_pixels = (int16_t) (_projection_detection_radius + base_radius);
-    const int16_t radius_x2 = 2 * radius_pixels;
-    _tracking_mask.assign((size_t) rows * cols, 0);
-    const bool to_left = param_enable_full_distance_to_left.value(), to_right = param_enable_full_distance_to_right.value();
-    for (size_t k = 0; k < _projections->size(); ++k) {
-      const float* c = _projections->point(k);
-      const int16_t row = (int16_t) std::round(c[1]), col = (int16_t) std::round(c[0]);
-      const int16_t tl_row = std::max<int>(row - radius_pixels, 0);
-      const int16_t height = std::min<int16_t>(radius_x2, (int16_t) (rows - tl_row));
-      int x0, w;
-      if (to_left && to_right) {
-        x0 = 0;
-        w = cols;
-      } else if (to_left) {
-        x0 = 0;
-        w = col;
-      } else if (to_right) {
-        x0 = col;
-        w = (int16_t) (cols - col);
-      } else {
-        const int16_t tl_col = std::max<int>(col - radius_pixels, 0);
-        x0 = tl_col;
-        w = std::min<int16_t>(radius_x2, (int16_t) (cols - tl_col));
-      }
-      // cv::Mat(rect).setTo(1); a rectangle reaching outside the image asserts in the reference
-      for (int r = tl_row; r < tl_row + height && r < rows; ++r)
-        for (int x = std::max(x0, 0); x < x0 + w && x < cols; ++x) _tracking_mask[(size_t) r * cols + x] = 1;
-    }
+    paintTrackingMask(rows, cols, *_projections, _projection_detection_radius, _tracking_mask);
     int n_tracking = 0;
     const int n = pslam_extract_selective(ctx, image.data, rows, cols, image.stride, &cfg, _tracking_mask.data(),
                                           param_enable_seeding_when_tracking.value() ? 1 : 0, capacity, xy, response, intensity,
@@ -370,8 +379,24 @@ void CorrespondenceFinderDescriptorBasedEpipolarCUDA::compute() {
 void CorrespondenceFinderProjectiveCUDA::compute() {
   _preCompute();
   pslam_ctx* ctx = PslamDevice::context();
+  // the device cache is shared by every finder instance of the process (and dropped when the context is re-created):
+  // upload again when it no longer carries the stamps of OUR uploads
+  unsigned long long fixed_epoch = 0, moving_epoch = 0;
+  pslam_projective_cache_epochs(ctx, &fixed_epoch, &moving_epoch);
+  const bool fixed_stale = fixed_epoch != _device_fixed_epoch, moving_stale = moving_epoch != _device_moving_epoch;
+  if (!(_fixed_changed_flag || _moving_changed_flag || _config_changed) && (fixed_stale || moving_stale)) {
+    if (fixed_stale)
+      PslamDevice::check(pslam_projective_set_fixed(ctx, (int) _fixed->size(), _fixed->coordinates.data(), _fixed->dim,
+                                                    _fixed->descriptor.data()),
+                         "CorrespondenceFinderProjective::compute");
+    if (moving_stale)
+      PslamDevice::check(pslam_projective_set_moving(ctx, (int) _moving->size(), _moving->coordinates.data(),
+                                                     _moving->descriptor.data()),
+                         "CorrespondenceFinderProjective::compute");
+    pslam_projective_cache_epochs(ctx, &_device_fixed_epoch, &_device_moving_epoch);
+  }
   if (_fixed_changed_flag || _moving_changed_flag || _config_changed) {
-    const bool fixed_changed = _fixed_changed_flag, moving_changed = _moving_changed_flag;
+    const bool fixed_changed = _fixed_changed_flag || fixed_stale, moving_changed = _moving_changed_flag || moving_stale;
     _fixed_changed_flag = false;
     _moving_changed_flag = false;
     if ((_search_radius_pixels == 0 && _descriptor_distance == 0) || _config_changed) {
@@ -395,6 +420,7 @@ void CorrespondenceFinderProjectiveCUDA::compute() {
                                                      _moving->descriptor.data()),
                          "CorrespondenceFinderProjective::compute");
     }
+    pslam_projective_cache_epochs(ctx, &_device_fixed_epoch, &_device_moving_epoch);
     _config_changed = false;
   }
   if (_has_converged) {  // correspondences are not touched (:137-141)
@@ -881,9 +907,38 @@ AlignerSliceProcessorProjectiveCUDA* MultiAligner3DQRCUDA::projectiveSlice() con
   return nullptr;
 }
 
+AlignerSliceMotionModel3DCUDA* MultiAligner3DQRCUDA::motionModelSlice() const {
+  for (const auto& s : param_slice_processors.value())
+    if (auto p = std::dynamic_pointer_cast<AlignerSliceMotionModel3DCUDA>(s)) return p.get();
+  return nullptr;
+}
+
+Isometry3f MotionModelConstantVelocity3D::predict(const std::vector<Isometry3f>& chunk) const {
+  if (chunk.empty()) return Isometry3f::Identity();  // no history: no motion
+  const Isometry3f& last = chunk.back();
+  if (chunk.size() == 1) return last.inverse();
+  const Isometry3f motion = chunk[chunk.size() - 2].inverse() * last;  // last relative motion, applied once more
+  return (last * motion).inverse();
+}
+
+AlignerSliceMotionModel3DCUDA::AlignerSliceMotionModel3DCUDA() {
+  for (int i = 0; i < 36; ++i) _information[i] = (i % 7 == 0) ? 1.0 : 0.0;
+}
+
+pslam_pose_prior AlignerSliceMotionModel3DCUDA::prior() const {
+  pslam_pose_prior p;
+  const MotionModelConstantVelocity3D fallback;
+  const MotionModelConstantVelocity3D* mm = param_motion_model.value() ? param_motion_model.value().get() : &fallback;
+  const Isometry3f Z = mm->predict(_chunk);
+  for (int i = 0; i < 12; ++i) p.prediction[i] = Z.m[i];
+  for (int i = 0; i < 36; ++i) p.information[i] = _information[i];
+  return p;
+}
+
 void MultiAligner3DQRCUDA::compute() {
   _status = Fail;
   _stats.clear();
+  _inlier_run_stats.clear();
   AlignerSliceProcessorProjectiveCUDA* slice = projectiveSlice();
   if (!slice) throw std::runtime_error("MultiAligner::compute|ERROR: no projective slice processor configured");
   if (!_fixed || !_moving) throw std::runtime_error("MultiAligner::compute|ERROR: fixed / moving not set");
@@ -899,15 +954,45 @@ void MultiAligner3DQRCUDA::compute() {
   finder.setMoving(_moving);
   finder.setCorrespondences(&slice->correspondences());
   const double damping = param_solver->damping();
+  // second slice: the motion model seeds the estimate and adds its pose-prior factor to every iteration
+  pslam_pose_prior prior_storage;
+  const pslam_pose_prior* prior = nullptr;
+  if (AlignerSliceMotionModel3DCUDA* mm = motionModelSlice()) {
+    prior_storage = mm->prior();
+    prior = &prior_storage;
+    for (int i = 0; i < 12; ++i) _estimate[i] = prior_storage.prediction[i];
+  }
 
-  // device inputs of the factor (fp64): moving points and fixed measurements do not change over the iterations
-  std::vector<double> moving_xyz(_moving->coordinates.begin(), _moving->coordinates.end());
-  std::vector<double> fixed_meas(_fixed->coordinates.begin(), _fixed->coordinates.end());
+  // the factor reads the clouds as they are (fp32, the reference's scalar): no widening on the host, 40 B / correspondence
+  const float* moving_xyz = _moving->coordinates.data();
+  const float* fixed_meas = _fixed->coordinates.data();
   std::vector<int> cf, cm;
   std::vector<double> poses, stats;
+  std::vector<uint8_t> factor_status;
   AlignerIterationStats last;
   bool enough = true;
   const int max_iterations = param_max_iterations.value();
+  auto push_stats = [&](std::vector<AlignerIterationStats>& dst, int it, int done, int n_corr) {
+    for (int j = 0; j < done; ++j) {
+      AlignerIterationStats st;
+      st.iteration = it + j;
+      st.num_correspondences = n_corr;
+      st.chi = stats[4 * (size_t) j];
+      st.num_inliers = (int) stats[4 * (size_t) j + 1];
+      st.num_outliers = (int) stats[4 * (size_t) j + 2];
+      st.num_suppressed = (int) stats[4 * (size_t) j + 3];
+      dst.push_back(st);
+      last = st;
+    }
+  };
+  auto split = [&](const CorrespondenceVector& corr) {
+    cf.resize(corr.size());
+    cm.resize(corr.size());
+    for (size_t k = 0; k < corr.size(); ++k) {
+      cf[k] = corr[k].fixed_idx;
+      cm[k] = corr[k].moving_idx;
+    }
+  };
   for (int it = 0; it < max_iterations;) {
     Isometry3f X;
     for (int i = 0; i < 12; ++i) X.m[i] = (float) _estimate[i];
@@ -923,33 +1008,20 @@ void MultiAligner3DQRCUDA::compute() {
       break;
     }
     slice->setupFactor();
-    cf.resize(corr.size());
-    cm.resize(corr.size());
-    for (size_t k = 0; k < corr.size(); ++k) {
-      cf[k] = corr[k].fixed_idx;
-      cm[k] = corr[k].moving_idx;
-    }
+    split(corr);
     // The finder keeps these correspondences for its next `quiet` calls (it only re-projects every N-th solver
     // iteration, correspondence_finder_projective_base_impl.cpp:162-178): run this iteration and those in ONE launch.
     const int quiet = finder.callsWithoutNewCorrespondences();
     const int n_fused = std::min(max_iterations - it, quiet >= max_iterations ? max_iterations : quiet + 1);
     poses.resize(12 * (size_t) n_fused);
     stats.resize(4 * (size_t) n_fused);
+    factor_status.resize(corr.size());
     int done = 0;
-    const int rc = pslam_gn_iterate(ctx, &slice->factorConfig(), n_fused, damping, _estimate.data(), (int) _moving->size(),
-                                    moving_xyz.data(), (int) _fixed->size(), fixed_meas.data(), _fixed->dim, (int) corr.size(),
-                                    cf.data(), cm.data(), slice->informationDiagonals().data(), poses.data(), stats.data(), &done);
-    for (int j = 0; j < done; ++j) {
-      AlignerIterationStats st;
-      st.iteration = it + j;
-      st.num_correspondences = (int) corr.size();
-      st.chi = stats[4 * (size_t) j];
-      st.num_inliers = (int) stats[4 * (size_t) j + 1];
-      st.num_outliers = (int) stats[4 * (size_t) j + 2];
-      st.num_suppressed = (int) stats[4 * (size_t) j + 3];
-      _stats.push_back(st);
-      last = st;
-    }
+    const int rc = pslam_gn_iterate_f32(ctx, &slice->factorConfig(), n_fused, damping, _estimate.data(), (int) _moving->size(),
+                                        moving_xyz, (int) _fixed->size(), fixed_meas, _fixed->dim, (int) corr.size(), cf.data(),
+                                        cm.data(), slice->informationDiagonals().data(), prior, poses.data(), stats.data(),
+                                        factor_status.data(), &done);
+    push_stats(_stats, it, done, (int) corr.size());
     if (rc == PSLAM_E_NOT_SPD) break;  // degenerate system: keep the last estimate
     PslamDevice::check(rc, "MultiAligner::compute");
     // the finder's own bookkeeping for the fused iterations (iteration counter, previous estimate): host only
@@ -965,6 +1037,40 @@ void MultiAligner3DQRCUDA::compute() {
     return;
   }
   _status = last.num_inliers >= param_min_num_inliers.value() ? Success : NotEnoughInliers;
+  if (_status != Success) return;
+  // configurations/icl.conf:55-58 [upstream, restated in oracle_lib.align]: the correspondences whose factor was an inlier
+  // in the last linearisation are frozen; with enough of them max_iterations further GN iterations run on them alone (ONE
+  // launch, the finder is not consulted); keep_only_inlier_correspondences leaves exactly those in the slice
+  const bool inlier_runs = param_enable_inlier_only_runs.value(), keep_only = param_keep_only_inlier_correspondences.value();
+  if (!inlier_runs && !keep_only) return;
+  CorrespondenceVector& corr = slice->correspondences();
+  auto keep_inliers = [&]() {
+    CorrespondenceVector kept;
+    for (size_t k = 0; k < corr.size(); ++k)
+      if (factor_status[k] == PSLAM_FACTOR_INLIER) kept.push_back(corr[k]);
+    return kept;
+  };
+  CorrespondenceVector inliers = keep_inliers();
+  if (inlier_runs && (int) inliers.size() >= param_min_num_inliers.value()) {
+    const CorrespondenceVector all = corr;
+    corr = inliers;
+    slice->setupFactor();
+    split(corr);
+    poses.resize(12 * (size_t) max_iterations);
+    stats.resize(4 * (size_t) max_iterations);
+    factor_status.resize(corr.size());
+    int done = 0;
+    const int rc = pslam_gn_iterate_f32(ctx, &slice->factorConfig(), max_iterations, damping, _estimate.data(), (int) _moving->size(),
+                                        moving_xyz, (int) _fixed->size(), fixed_meas, _fixed->dim, (int) corr.size(), cf.data(),
+                                        cm.data(), slice->informationDiagonals().data(), prior, poses.data(), stats.data(),
+                                        factor_status.data(), &done);
+    push_stats(_inlier_run_stats, 0, done, (int) corr.size());
+    if (rc != PSLAM_E_NOT_SPD) PslamDevice::check(rc, "MultiAligner::compute (inlier-only run)");
+    if (keep_only) corr = keep_inliers();
+    else corr = all;
+  } else if (keep_only) {
+    corr = inliers;
+  }
 }
 
 // ---- registration -----------------------------------------------------------------------------------------------
@@ -1030,6 +1136,8 @@ void registerTypes() {
   reg<SliceK<0>>("AlignerSliceProcessorProjectiveStereo");
   reg<SliceK<0>>("AlignerSliceProcessorProjectiveStereoWithSensor");  // kitti_in_baselink.conf
   reg<MultiAligner3DQRCUDA>("MultiAligner3DQR");
+  reg<AlignerSliceMotionModel3DCUDA>("AlignerSliceMotionModel3D");  // srrg2_slam_interfaces; second slice of the shipped aligners
+  PSLAM_REGISTER_CLASS_AS(MotionModelConstantVelocity3D, "MotionModelConstantVelocity3D");
   reg<SceneClipperProjective3DCUDA>("SceneClipperProjective3D");  // mapping/instances.cpp
   reg<FilterK<0>>("ProjectivePointEKF3D");
   reg<FilterK<1>>("ProjectiveDepthPointEKF3D");

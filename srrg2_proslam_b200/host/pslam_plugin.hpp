@@ -188,6 +188,9 @@ public:
   PARAM(PropertyBool, enable_seeding_when_tracking, "enables new point seeding when in tracking mode", true, &_config_changed);
   void init() override;  // selective.cpp:6-46
   size_t numberOfTrackingKeypoints() const { return _n_tracking; }
+  // selective.cpp:63-144 (host-side, no device needed)
+  void paintTrackingMask(int rows, int cols, const PointIntensityDescriptorCloud& projections, int projection_detection_radius,
+                         std::vector<uint8_t>& mask) const;
 
 protected:
   int extract(pslam_ctx* ctx, const ImageView& image, int capacity, float* xy, float* response, float* intensity,
@@ -285,6 +288,7 @@ private:
   bool _has_converged = false;
   size_t _current_iteration = 0;
   int _number_of_searches = 0;
+  unsigned long long _device_fixed_epoch = 0, _device_moving_epoch = 0;  // stamps of OUR uploads into the shared device cache
 };
 
 // ---- measurement adaptors (sensor_processing/raw_data_preprocessor_{stereo_projective,monocular_depth}.{h,cpp}) --
@@ -375,7 +379,7 @@ public:
   void setupFactor();  // K, image dim, per-correspondence information (.cpp:27-73), stereo extras (:91-112)
   CorrespondenceVector& correspondences() { return _correspondences; }
   const pslam_linearize_cfg& factorConfig() const { return _factor; }
-  const std::vector<double>& informationDiagonals() const { return _fixed_information_diagonals; }
+  const std::vector<float>& informationDiagonals() const { return _fixed_information_diagonals; }
   float meanDisparity() const { return _mean_disparity; }
   const PointIntensityDescriptorCloud* fixedSlice() const { return _fixed_slice; }
   const PointIntensityDescriptorCloud* movingSlice() const { return _moving_slice; }
@@ -385,12 +389,44 @@ private:
   const PointIntensityDescriptorCloud* _fixed_slice = nullptr;
   const PointIntensityDescriptorCloud* _moving_slice = nullptr;
   CorrespondenceVector _correspondences;
-  std::vector<double> _fixed_information_diagonals;  // 3 per fixed point
+  std::vector<float> _fixed_information_diagonals;  // 3 per fixed point (fp32 like the reference's InformationMatrixVector)
   pslam_linearize_cfg _factor{};
   float _mean_disparity = 0;
   float _t_left_in_right[3] = {0, 0, 0};
   float _baseline_left_in_right_pixelsmeters[3] = {0, 0, 0};
   bool _baseline_set = false;
+};
+
+// ---- the shipped aligners' second slice (srrg2_slam_interfaces, external): AlignerSliceMotionModel3D over the
+//      "trajectory_chunk" slice with a MotionModelConstantVelocity3D (configurations/kitti.conf:747-772,257-260;
+//      icl.conf:268-293,660-663; euroc.conf:94-119,456-459).  [upstream, restated]: the motion model predicts the
+//      estimate from the last relative motion of the chunk; the slice seeds the aligner's estimate with the prediction
+//      (what tests/test_aligners.cpp:1083,1096-1102 requires) and contributes an SE3 pose-prior factor with a constant
+//      information matrix to every iteration's H, b -- evaluated on the device inside the fused launch.
+class MotionModelConstantVelocity3D : public Configurable {
+public:
+  // robot poses in the local map, oldest first -> predicted moving_in_fixed (= predicted robot_in_local_map^-1)
+  Isometry3f predict(const std::vector<Isometry3f>& trajectory_chunk) const;
+};
+class AlignerSliceMotionModel3DCUDA : public Configurable {
+public:
+  AlignerSliceMotionModel3DCUDA();
+  PARAM(PropertyString, base_frame_id, "name of the base frame in the tf tree", "", nullptr);
+  PARAM(PropertyString, frame_id, "name of the sensor's frame in the tf tree", "", nullptr);
+  PARAM(PropertyString, fixed_slice_name, "name of the slice in the fixed scene", "trajectory_chunk", nullptr);
+  PARAM(PropertyString, moving_slice_name, "name of the slice in the moving scene", "trajectory_chunk", nullptr);
+  PARAM(PropertyConfigurable_<MotionModelConstantVelocity3D>, motion_model, "model used to estimate inter-frame motion",
+        std::make_shared<MotionModelConstantVelocity3D>(), nullptr);
+  PARAM(PropertyConfigurable_<RobustifierBase>, robustifier, "robustifier used on this slice", nullptr, nullptr);
+  void setTrajectoryChunk(const std::vector<Isometry3f>& chunk) { _chunk = chunk; }
+  void setInformationMatrix(const double information36[36]) {
+    for (int i = 0; i < 36; ++i) _information[i] = information36[i];
+  }
+  pslam_pose_prior prior() const;  // prediction of the motion model + the information matrix
+
+private:
+  std::vector<Isometry3f> _chunk;
+  double _information[36];
 };
 
 // ---- MultiAligner3DQR (srrg2_slam_interfaces, external; iteration structure: SURVEY App. E.6) ------------------
@@ -416,14 +452,17 @@ public:
   Status status() const { return _status; }
   void compute();
   const std::vector<AlignerIterationStats>& iterationStats() const { return _stats; }
+  // iterations of the additional inlier-only run (enable_inlier_only_runs, configurations/icl.conf:55)
+  const std::vector<AlignerIterationStats>& inlierRunStats() const { return _inlier_run_stats; }
   AlignerSliceProcessorProjectiveCUDA* projectiveSlice() const;
+  AlignerSliceMotionModel3DCUDA* motionModelSlice() const;
 
 private:
   const PointIntensityDescriptorCloud* _fixed = nullptr;
   const PointIntensityDescriptorCloud* _moving = nullptr;
   std::array<double, 12> _estimate{{1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0}};
   Status _status = Fail;
-  std::vector<AlignerIterationStats> _stats;
+  std::vector<AlignerIterationStats> _stats, _inlier_run_stats;
 };
 
 // ---- SceneClipperProjective3D (mapping/scene_clipper_projective_3d.{h,cpp}) -----------------------

@@ -267,6 +267,20 @@ psp_module* psp_module_get_link(psp_module* c, const char* param) {
   return handle(p->pointer().get());
 }
 
+int psp_extractor_paint_tracking_mask(psp_module* extractor, int rows, int cols, int n, int dim, const float* coords, int radius,
+                                      uint8_t* mask) {
+  return guard([&] {
+    auto* ex = as<IntensityFeatureExtractorSelectiveCUDA>(extractor, "IntensityFeatureExtractorSelective");
+    PointIntensityDescriptorCloud proj(dim);
+    proj.resize((size_t) n);
+    if (n > 0) std::memcpy(proj.coordinates.data(), coords, sizeof(float) * (size_t) n * dim);
+    std::vector<uint8_t> m;
+    ex->paintTrackingMask(rows, cols, proj, radius, m);
+    std::memcpy(mask, m.data(), m.size());
+    return 0;
+  });
+}
+
 int psp_extractor_compute(psp_module* extractor, const uint8_t* image, int rows, int cols, int stride,
                           const uint8_t* mask, int capacity, float* xy, float* intensity, uint8_t* desc) {
   return guard([&] {
@@ -478,6 +492,55 @@ int psp_aligner_compute(psp_module* aligner, double* moving_in_fixed12, int* ite
       if (chi) *chi = st.back().chi;
     }
     return (int) a->status();
+  });
+}
+
+int psp_aligner_set_slice_processor(psp_module* aligner, int index, psp_module* slice) {
+  return guard([&] {
+    auto* a = as<MultiAligner3DQRCUDA>(aligner, "MultiAligner3DQR");
+    if (!slice) throw std::runtime_error("MultiAligner|ERROR: null slice processor");
+    a->param_slice_processors.setValue((size_t) index, mod(slice)->shared_from_this());
+    return 0;
+  });
+}
+
+int psp_aligner_num_slice_processors(psp_module* aligner) {
+  return guard([&] { return (int) as<MultiAligner3DQRCUDA>(aligner, "MultiAligner3DQR")->param_slice_processors.size(); });
+}
+
+int psp_aligner_set_trajectory_chunk(psp_module* aligner, int n, const float* poses12) {
+  return guard([&] {
+    auto* a = as<MultiAligner3DQRCUDA>(aligner, "MultiAligner3DQR");
+    AlignerSliceMotionModel3DCUDA* s = a->motionModelSlice();
+    if (!s) throw std::runtime_error("MultiAligner|ERROR: no motion model slice configured");
+    std::vector<Isometry3f> chunk((size_t) n);
+    for (int i = 0; i < n; ++i) std::memcpy(chunk[i].m, poses12 + 12 * (size_t) i, sizeof(float) * 12);
+    s->setTrajectoryChunk(chunk);
+    return 0;
+  });
+}
+
+int psp_aligner_set_prior_information(psp_module* aligner, const double* information36) {
+  return guard([&] {
+    auto* a = as<MultiAligner3DQRCUDA>(aligner, "MultiAligner3DQR");
+    AlignerSliceMotionModel3DCUDA* s = a->motionModelSlice();
+    if (!s) throw std::runtime_error("MultiAligner|ERROR: no motion model slice configured");
+    s->setInformationMatrix(information36);
+    return 0;
+  });
+}
+
+int psp_aligner_inlier_run_stats(psp_module* aligner, int capacity, double* rows4) {
+  return guard([&] {
+    auto* a = as<MultiAligner3DQRCUDA>(aligner, "MultiAligner3DQR");
+    const auto& st = a->inlierRunStats();
+    for (int i = 0; i < (int) st.size() && i < capacity; ++i) {
+      rows4[4 * i] = st[i].num_correspondences;
+      rows4[4 * i + 1] = st[i].num_inliers;
+      rows4[4 * i + 2] = st[i].num_outliers;
+      rows4[4 * i + 3] = st[i].chi;
+    }
+    return (int) st.size();
   });
 }
 

@@ -106,6 +106,12 @@ class Module:
         coords = np.ascontiguousarray(coords, np.float32)
         _chk(lib().psp_extractor_set_projections(self.h, len(coords), coords.shape[1], _p(coords), int(radius)))
 
+    def paint_tracking_mask(self, rows, cols, coords, radius):
+        coords = np.ascontiguousarray(coords, np.float32)
+        mask = np.zeros((rows, cols), np.uint8)
+        _chk(lib().psp_extractor_paint_tracking_mask(self.h, rows, cols, len(coords), coords.shape[1], _p(coords), int(radius), _p(mask)))
+        return mask
+
     def number_of_tracking_keypoints(self):
         return _chk(lib().psp_extractor_number_of_tracking_keypoints(self.h))
 
@@ -296,6 +302,20 @@ class Module:
         t3 = np.ascontiguousarray(t3, np.float32).reshape(3)
         _chk(lib().psp_aligner_set_left_camera_in_right(self.h, _p(t3)))
 
+    def aligner_set_slice_processor(self, index, slice_module):
+        _chk(lib().psp_aligner_set_slice_processor(self.h, int(index), slice_module.h))
+
+    def aligner_num_slice_processors(self):
+        return _chk(lib().psp_aligner_num_slice_processors(self.h))
+
+    def aligner_set_trajectory_chunk(self, poses):
+        poses = np.ascontiguousarray(poses, np.float32).reshape(-1, 12)
+        _chk(lib().psp_aligner_set_trajectory_chunk(self.h, len(poses), _p(poses)))
+
+    def aligner_set_prior_information(self, information):
+        information = np.ascontiguousarray(information, np.float64).reshape(36)
+        _chk(lib().psp_aligner_set_prior_information(self.h, _p(information)))
+
     def aligner_compute(self):
         pose = np.zeros(12, np.float64)
         it, nc, ni = C.c_int(), C.c_int(), C.c_int()
@@ -307,8 +327,10 @@ class Module:
         m = np.zeros(16384, np.int32)
         d = np.zeros(16384, np.float32)
         n = _chk(lib().psp_aligner_correspondences(self.h, 16384, _p(f), _p(m), _p(d)))
+        rrows = np.zeros((4096, 4), np.float64)
+        nr = _chk(lib().psp_aligner_inlier_run_stats(self.h, len(rrows), _p(rrows)))
         return {"status": status, "pose": pose, "iterations": it.value, "num_correspondences": nc.value,
-                "num_inliers": ni.value, "chi": chi.value, "stats": rows[:it.value],
+                "num_inliers": ni.value, "chi": chi.value, "stats": rows[:it.value], "inlier_run_stats": rrows[:nr].copy(),
                 "corr": (f[:n].copy(), m[:n].copy(), d[:n].copy())}
 
 

@@ -199,3 +199,38 @@ def test_triangulate(ctx):  # mapping/triangulator_rigid_stereo.cpp:7-85 (SURVEY
         assert n_valid == len(uvuv) - n_inv == int(valid.sum())
         assert (min_disp == 0.0) == bool(valid[3]) and (min_disp == 0.0) == bool(valid[5])
     assert ctx.triangulate(np.zeros((0, 4), np.float32), K_KITTI, b_x)[2] == 0
+
+
+def test_odd_feature_capacity(oracle):
+    """a context created with an odd max_features (the capacity is a stride of 16 / 32-bit shared-memory arrays in the
+    stereo matcher): whole stereo adaptor on the lean path (thickness 0) and with thickness 1"""
+    from srrg2_proslam_b200 import capi
+    L, R = O.load_gray("kitti_city_image_left_0.png"), O.load_gray("kitti_city_image_right_0.png")
+    for mf in (1001, 1003, 999):
+        c = capi.Context(max_images=2, max_rows=376, max_cols=1241, max_features=mf, max_raw_per_bin=8192)
+        try:
+            for thickness in (0, 1):
+                g = c.stereo_adaptor(L, R, capi.extract_cfg(15, 1, 1000), capi.match_cfg(100, 0.5, 100, thickness))
+                o = O.stereo_adaptor(L, R, O.extract_cfg(15, 1, 1000), "epipolar", 100, 0.5, 100, thickness)
+                assert len(g["uvuv"]) > 100 and np.array_equal(g["uvuv"], o["uvuv"]) and np.array_equal(g["desc"], o["desc"])
+        finally:
+            c.close()
+
+
+def test_epipolar_argument_checks(ctx, feats):
+    """negative line thickness = the offset-0 pass only (epipolar_impl.cpp:72-79); coordinates that do not fit the packed
+    (row, col) sort key are refused instead of silently ordered differently from the reference"""
+    from srrg2_proslam_b200 import capi
+    a, b = feats["L0"], feats["R0"]
+    g0 = ctx.match_epipolar(a["xy"], a["desc"], b["xy"], b["desc"], capi.match_cfg(50, 0.9, 100, 0))
+    gn = ctx.match_epipolar(a["xy"], a["desc"], b["xy"], b["desc"], capi.match_cfg(50, 0.9, 100, -3))
+    assert len(g0[0]) > 50 and same_corr(g0, gn)
+    bad = a["xy"].copy()
+    bad[3, 0] = 70000.0
+    with pytest.raises(capi.PslamError) as e:
+        ctx.match_epipolar(bad, a["desc"], b["xy"], b["desc"], capi.match_cfg(50, 0.9, 100, 0))
+    assert e.value.code == capi.PSLAM_E_INVALID
+    bad = a["xy"].copy()
+    bad[0, 1] = -1.0
+    with pytest.raises(capi.PslamError):
+        ctx.match_epipolar(a["xy"], a["desc"], bad, b["desc"], capi.match_cfg(50, 0.9, 100, 0))

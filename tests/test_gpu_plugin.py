@@ -172,6 +172,48 @@ def test_projective_finder_state_machine(P):
     assert al.class_name == "MultiAligner3DQR"
 
 
+def test_projective_finders_share_the_device_cache(P):
+    """Two projective finder instances and other modules share the process-wide device context.  Each finder's cached
+    clouds / lattice must survive (or be restored after) the other's uploads, a brute-force match, a triangulation and a
+    stereo adaptor call in between -- the finders only set their changed-flags once, like the reference's callers."""
+    m = P.Manager()
+    meas, xyz, cam01_in_00 = kitti_chain()
+    pose = O.pose_inverse(cam01_in_00).astype(np.float32)
+    finders, oracles = [], []
+    for shape, radius in (("Circle", 30), ("Square", 12)):
+        pr = m.create("PointIntensityDescriptor3fProjectorPinhole")
+        pr.set_camera_matrix(K_KITTI)
+        pr.set("canvas_rows", 376).set("canvas_cols", 1241).set("range_min", 0.1).set("range_max", 1000.0)
+        f = m.create(f"CorrespondenceFinderProjective{shape}4D3D")
+        f.set("projector", pr).set("maximum_search_radius_pixels", radius).set("minimum_search_radius_pixels", radius)
+        f.set("minimum_descriptor_distance", 60).set("maximum_descriptor_distance", 60).set("minimum_matching_ratio", 0.0)
+        f.set("number_of_solver_iterations_per_projection", 1)
+        o = O.ProjectiveFinder(K_KITTI, 376, 1241, shape.lower(), max_desc_dist=60, ratio=f.get("maximum_distance_ratio_to_second_best"),
+                               min_matching_ratio=0.0, min_desc_dist=60, max_radius=radius, min_radius=radius, iters_per_projection=1)
+        finders.append(f)
+        oracles.append(o)
+    # finder 0 matches frame 1 against the map, finder 1 matches frame 0 against itself: different clouds in the same cache
+    clouds = [(meas[1]["uvuv"], meas[1]["desc"], pose), (meas[0]["uvuv"], meas[0]["desc"], np.eye(3, 4, dtype=np.float32).reshape(12))]
+    for f, o, (fx, fd, _) in zip(finders, oracles, clouds):
+        for x in (f, o):
+            x.set_fixed(fx, fd)
+            x.set_moving(xyz, meas[0]["desc"])
+    bf = m.create("CorrespondenceFinderDescriptorBasedBruteforce4D3D")
+    ad = m.create("RawDataPreprocessorStereoProjective", "adaptor")
+    for rnd in range(3):
+        for f, o, (_, _, T) in zip(finders, oracles, clouds):
+            f.set_local_map_in_sensor(T)
+            o.set_estimate(T)
+            g, w = f.compute(), o.compute()
+            assert len(g[0]) > 20 and all(np.array_equal(a, b) for a, b in zip(g, w)), rnd
+            # other users of the context between two finder calls
+            bf.set_fixed(meas[1]["uvuv"], meas[1]["desc"])
+            bf.set_moving(xyz, meas[0]["desc"])
+            assert len(bf.compute()[0]) > 10
+            if rnd == 1:
+                assert len(ad.stereo_adaptor(*kitti_pair(2))["uvuv"]) > 50
+
+
 def manifold_error(estimate, cam01_in_00):
     return O.t2tnq(O.pose_mul(estimate, cam01_in_00))
 
@@ -200,7 +242,8 @@ def test_kitti_conf_aligner(P):
     base = (K_KITTI.reshape(3, 3) @ np.array([-BASELINE_M, 0, 0], np.float32)).astype(np.float32)
     o = O.align(of, "stereo", K_KITTI, 376, 1241, meas[1]["uvuv"], xyz, [1, 2, 1], baseline=base,
                 inverse_depth_weighting=True, chi_threshold=25.0, max_iterations=100, damping=1.0,
-                min_num_inliers=6, min_num_correspondences=10)
+                min_num_inliers=6, min_num_correspondences=10,
+                prior=(np.eye(3, 4).reshape(12), np.eye(6)))  # slice 2 of the conf: motion model, empty trajectory chunk
     assert g["status"] == o["status"] == O.ALIGNER_STATUS["Success"]
     assert g["iterations"] == len(o["stats"]) == 100
     assert np.array_equal(g["stats"][:, :3], o["stats"][:, :3])  # correspondences / inliers / outliers per iteration
@@ -256,9 +299,14 @@ def test_icl_conf_aligner(P):
     o = O.align(of, "depth", K_ICL, 480, 640, meas[1]["uvz"], xyz, sl.get_numbers("diagonal_info_matrix"),
                 chi_threshold=sl.link("robustifier").get("chi_threshold"), max_iterations=int(al.get("max_iterations")),
                 damping=al.link("solver").link("algorithm").get("damping"), min_num_inliers=int(al.get("min_num_inliers")),
-                min_num_correspondences=int(sl.get("min_num_correspondences")))
+                min_num_correspondences=int(sl.get("min_num_correspondences")),
+                prior=(np.eye(3, 4).reshape(12), np.eye(6)),  # slice 2 of the conf: motion model, empty trajectory chunk
+                enable_inlier_only_runs=bool(al.get("enable_inlier_only_runs")),
+                keep_only_inlier_correspondences=bool(al.get("keep_only_inlier_correspondences")))
+    assert al.get("enable_inlier_only_runs") == 1 and al.get("keep_only_inlier_correspondences") == 1  # icl.conf:55-58
     assert g["status"] == o["status"] == O.ALIGNER_STATUS["Success"]
     assert np.array_equal(g["stats"][:, :3], o["stats"][:, :3])
+    assert np.array_equal(g["inlier_run_stats"][:, :3], o["inlier_run_stats"][:, :3]) and len(g["inlier_run_stats"]) > 0
     assert all(np.array_equal(a, b) for a, b in zip(g["corr"], o["corr"]))
     d = O.t2tnq(O.pose_mul(O.pose_inverse(o["pose"]), g["pose"]))
     assert np.abs(d).max() < 1e-6, d

@@ -120,3 +120,58 @@ def test_gn_iterate_not_spd(ctx):
     # no correspondences: H = 0, not positive definite without damping; the first iteration is linearised, not solved
     pg, poses, stats, done, ok = ctx.gn_iterate(gcfg, 5, 0.0, pose, xyz, meas, cf[:0], cm[:0], info)
     assert done == 1 and not ok and np.array_equal(pg, pose) and stats[0, 1] == 0
+
+
+def rand_prior(seed):
+    rng = np.random.default_rng(seed)
+    v = np.concatenate([rng.normal(0, 0.3, 3), rng.normal(0, 0.05, 3)])
+    _, Z, _ = O.gn_step(np.eye(6), -v, 0.0, np.eye(3, 4).reshape(12))
+    M = rng.normal(size=(6, 6))
+    return Z, 50.0 * (M @ M.T + np.eye(6))
+
+
+@pytest.mark.parametrize("kind", ["stereo", "depth", "mono"])
+@pytest.mark.parametrize("n", [0, 5, 300, 20000])
+@pytest.mark.parametrize("with_prior", [False, True])
+def test_linearize_f32_prior_status(ctx, kind, n, with_prior):
+    """pslam_linearize_se3_f32: fp32 clouds in HBM (widened in registers), pose-prior factor summed on the device,
+    per-correspondence factor status -- against the oracle on the SAME fp32 values"""
+    xyz, meas, cf, cm, info, pose = synth(max(n, 1), kind, 31 + n)
+    xyz, meas, info = xyz.astype(np.float32), meas.astype(np.float32), info.astype(np.float32)
+    cf, cm = cf[:n], cm[:n]
+    prior = rand_prior(n) if with_prior else None
+    ocfg = O.linearize_cfg(kind, K, 1241, 376, (-386.1448, 0, 0), 0.0, "saturated", 25.0)
+    gcfg = ctx.linearize_cfg(kind, K, 1241, 376, (-386.1448, 0, 0), 0.0, "saturated", 25.0)
+    Ho, bo, so = O.linearize(ocfg, pose, xyz, meas, cf, cm, info, prior=prior, want_status=True)
+    Hg, bg, sg = ctx.linearize_f32(gcfg, pose, xyz, meas, cf, cm, info, prior=prior)
+    assert (sg["inliers"], sg["outliers"], sg["suppressed"]) == (so["inliers"], so["outliers"], so["suppressed"])
+    assert np.array_equal(sg["status"], so["status"])
+    assert np.abs(Hg - Ho).max() <= RTOL * max(np.abs(Ho).max(), 1e-300)
+    assert np.abs(bg - bo).max() <= RTOL * max(np.abs(bo).max(), 1e-300)
+    assert abs(sg["chi"] - so["chi"]) <= RTOL * max(abs(so["chi"]), 1e-300)
+    assert abs(sg["prior_chi"] - so["prior_chi"]) <= RTOL * max(abs(so["prior_chi"]), 1e-300)
+
+
+@pytest.mark.parametrize("kind,damping,n", [("stereo", 1.0, 400), ("depth", 0.1, 37), ("mono", 0.0, 3000)])
+def test_gn_iterate_f32_with_prior(ctx, kind, damping, n):
+    """the fused launch with the motion-model slice's factor inside == K x (linearise + prior + GN step) of the oracle"""
+    xyz, meas, cf, cm, info, pose = synth(n, kind, 5 + n, outlier_frac=0.05)
+    xyz, meas, info = xyz.astype(np.float32), meas.astype(np.float32), info.astype(np.float32)
+    prior = rand_prior(n)
+    ocfg = O.linearize_cfg(kind, K, 1241, 376, (-386.1448, 0, 0), 0.0, "saturated", 25.0)
+    gcfg = ctx.linearize_cfg(kind, K, 1241, 376, (-386.1448, 0, 0), 0.0, "saturated", 25.0)
+    iters = 12
+    pg, poses, stats, done, ok, status = ctx.gn_iterate_f32(gcfg, iters, damping, pose, xyz, meas, cf, cm, info, prior=prior)
+    assert done == iters and ok
+    po = pose.copy()
+    for it in range(iters):
+        Ho, bo, so = O.linearize(ocfg, po, xyz, meas, cf, cm, info, prior=prior, want_status=True)
+        rc, po, _ = O.gn_step(Ho, bo, damping, po)
+        assert rc == 0
+        assert np.abs(poses[it] - po).max() < 1e-9
+        assert (int(stats[it, 1]), int(stats[it, 2]), int(stats[it, 3])) == (so["inliers"], so["outliers"], so["suppressed"])
+    assert np.array_equal(status, so["status"])  # status of the LAST linearised iteration
+    # a strong prior dominates: the estimate ends at the prediction
+    strong = (prior[0], 1e12 * np.eye(6))
+    pg2, *_ = ctx.gn_iterate_f32(gcfg, 20, 0.0, pose, xyz, meas, cf, cm, info, prior=strong)
+    assert np.abs(O.t2tnq(O.pose_mul(O.pose_inverse(prior[0]), pg2))).max() < 1e-4

@@ -240,3 +240,47 @@ def test_merger_configuration_errors_keep_the_reference_texts(P):
         g.merger_plan(meas, [0], [10.0])
     assert g.merger_wants_additions(5, 100, 0) and g.merger_wants_additions(5, 100, 50)      # :56-58, :158-165
     assert not g.merger_wants_additions(100, 300, 150) and not g.merger_wants_additions(40, 40, 40)
+
+
+def test_selective_extractor_known_answers(P):
+    """Row a5, tests/test_feature_extractors.cpp:168-213 (KITTI, IntensityFeatureExtractorSelective_GFFT_ORB256).  That test
+    runs the selective extractor with detector_type "GFTT" in BOTH phases (the "TRACKING with FAST" comments are stale:
+    _keypoint_detector is the GFTT detector re-created with target 1000), so its constants pin the extractor's own logic --
+    the tracking rectangles of intensity_feature_extractor_selective.cpp:63-144 -- and ORB's 31-pixel border drop, not a
+    corner detector of the hot path.  cv2's GFTTDetector stands in for cv::GFTTDetector (test side only, parameters of
+    intensity_feature_extractor_base.cpp:107-116: quality 0.01, minimum distance = target_bin_width_pixels = 10); the mask
+    is painted by the plugin class IntensityFeatureExtractorSelective2D itself (host-side code of the product)."""
+    import cv2
+    import sys
+    sys.path.insert(0, str(ROOT / "tests"))
+    import oracle_lib as O
+    img = O.load_gray("kitti_city_image_left_0.png")
+    rows, cols = img.shape
+
+    def gftt(target, mask=None):
+        kps = cv2.GFTTDetector_create(target, 0.01, 10).detect(img, mask)
+        pts = np.array([k.pt for k in kps], np.float32).reshape(-1, 2)
+        keep = (pts[:, 0] >= 31) & (pts[:, 0] < cols - 31) & (pts[:, 1] >= 31) & (pts[:, 1] < rows - 31)  # ORB::compute
+        return pts[keep]
+
+    m = P.Manager()
+    ex = m.create("IntensityFeatureExtractorSelective2D", "selective")
+    ex.set("enable_seeding_when_tracking", 0)
+    seeds = gftt(100)
+    assert len(seeds) == 94  # :182
+    for radius, expected in ((100, 719), (50, 581), (10, 294), (5, 237)):  # :191,198,205,212
+        mask = ex.paint_tracking_mask(rows, cols, seeds, radius)
+        assert len(gftt(1000, mask)) == expected, radius
+    # the three "full bar" variants (selective.cpp:80-128) against a direct restatement
+    rng = np.random.default_rng(1)
+    proj = np.stack([rng.uniform(0, cols - 1, 30), rng.uniform(0, rows - 1, 30)], 1).astype(np.float32)
+    for to_left, to_right in ((1, 0), (0, 1), (1, 1)):
+        ex.set("enable_full_distance_to_left", to_left).set("enable_full_distance_to_right", to_right)
+        want = np.zeros((rows, cols), np.uint8)
+        for x, y in proj:
+            r, c = int(np.round(y)), int(np.round(x))
+            t = max(r - 22, 0)
+            h = min(44, rows - t)
+            x0, w = (0, cols) if (to_left and to_right) else ((0, c) if to_left else (c, cols - c))
+            want[t:t + h, x0:x0 + w] = 1
+        assert np.array_equal(ex.paint_tracking_mask(rows, cols, proj, 12), want)
