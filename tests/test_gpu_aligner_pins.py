@@ -97,4 +97,4 @@ def test_constant_velocity_prior_seeds_and_pulls(P):
     al.aligner_set_prior_information(1e12 * np.eye(6))
     g = al.aligner_compute()
     assert np.abs(O.t2tnq(O.pose_mul(O.pose_inverse(pred), g["pose"]))).max() < 1e-4
-    assert np.abs(pred - O.pose_mul(step, step)).max() < 1e-6  # two steps of the same motion
+    assert np.abs(pred - O.pose_mul(step, step)).max() < 1e-5  # two steps of the same motion (the chunk travels as fp32)

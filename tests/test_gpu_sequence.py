@@ -1,7 +1,10 @@
 """The whole hot path chained over the reference's KITTI snippet (test_data/kitti/city frames 0..4, the frames of
 tests/test_trackers.cpp:260-365 "KITTI 00To04_Tracker_ProjectiveBF_NoMerges"): per frame
   stereo adaptor (kitti.conf extractor + epipolar finder) -> rigid-stereo triangulation of the previous frame ->
-  conf-driven aligner (projective circle finder + stereo factor + GN, 100 iterations) -> pose chain.
+  conf-driven aligner (projective circle finder + stereo factor + motion-model slice + GN, 100 iterations) -> pose chain.
+The aligner's second slice (AlignerSliceMotionModel3D, configurations/kitti.conf:747-772) gets the trajectory chunk a
+tracker would hand it: the previous frame-to-frame motion, so that the constant-velocity prediction seeds every
+alignment and its pose-prior factor is summed into H, b inside the fused launch.
 The tracker / merger / clipper control plane is NOT part of the path; the test chains
 frame-to-frame alignments itself, once through the CUDA-backed plugin modules and once through the CPU oracle, and
 checks the north_star's pose criteria: every per-frame pose within 1e-6 m / 1e-6 rad of the CPU path, trajectory
@@ -65,6 +68,7 @@ def test_kitti_00_to_04_odometry(oracle):
                             min_desc_dist=25, desc_step=5, max_radius=50, min_radius=10, radius_step=10,
                             min_iterations=5, max_change_norm=0.01, iters_per_projection=5)
     g_prev = o_prev = None
+    chunk = np.eye(3, 4, dtype=np.float32).reshape(1, 12)  # first alignment: one pose, no motion yet
     g_00_in_k = np.eye(3, 4).reshape(12)  # camera 00 expressed in camera k (= moving_in_fixed chained)
     o_00_in_k = np.eye(3, 4).reshape(12)
     g_traj, o_traj = [np.eye(3, 4).reshape(12)], [np.eye(3, 4).reshape(12)]
@@ -80,12 +84,17 @@ def test_kitti_00_to_04_odometry(oracle):
             al.aligner_set_fixed(g_meas["uvuv"], g_meas["desc"])
             al.aligner_set_moving(xyz, g_prev["desc"])
             al.aligner_set_moving_in_fixed(np.eye(3, 4, dtype=np.float32))
+            # robot poses in the local map (= the previous camera frame), oldest first: camera k-2, then camera k-1 itself
+            al.aligner_set_trajectory_chunk(chunk)
             g = al.aligner_compute()
             of.set_fixed(o_meas["uvuv"], o_meas["desc"])
             of.set_moving(xyz, o_prev["desc"])
+            pred = O.constant_velocity_prediction(list(chunk))
             o = O.align(of, "stereo", K_KITTI, 376, 1241, o_meas["uvuv"], xyz, [1, 2, 1], baseline=base,
                         inverse_depth_weighting=True, chi_threshold=25.0, max_iterations=100, damping=1.0,
-                        min_num_inliers=6, min_num_correspondences=10)
+                        min_num_inliers=6, min_num_correspondences=10, init_pose=pred, prior=(pred, np.eye(6)))
+            if k > 1:  # the prediction (last motion repeated) starts within a few centimetres of the solution
+                assert np.abs(O.t2tnq(O.pose_mul(O.pose_inverse(pred), g["pose"]))[:3]).max() < 0.1
             assert g["status"] == o["status"] == O.ALIGNER_STATUS["Success"], k
             assert np.array_equal(g["stats"][:, :3], o["stats"][:, :3]), k
             assert all(np.array_equal(a, b) for a, b in zip(g["corr"], o["corr"])), k
@@ -95,6 +104,7 @@ def test_kitti_00_to_04_odometry(oracle):
             o_00_in_k = O.pose_mul(o["pose"], o_00_in_k)
             g_traj.append(O.pose_inverse(g_00_in_k))
             o_traj.append(O.pose_inverse(o_00_in_k))
+            chunk = np.stack([g["pose"], np.eye(3, 4).reshape(12)]).astype(np.float32)
         g_prev, o_prev = g_meas, o_meas
 
     w_in_00 = O.pose_inverse(CAM_IN_WORLD[0])
