@@ -23,33 +23,55 @@
 namespace {
 
 constexpr int BF_THREADS = 128;
-constexpr int BF_QPT = 2;                       // queries per thread
-constexpr int BF_QTILE = BF_THREADS * BF_QPT;   // 256 queries per CTA
+constexpr int BF_QPT_MAX = 4;                   // queries per thread (template parameter: 2 or 4)
 constexpr int BF_TTILE = 256;                   // train descriptors per smem stage (8 KB)
+constexpr int BF_MAX_SLICE = 65536;             // the packed best-2 key carries the train index within the slice in 16 bits
 
 struct Best2 {
   int best, second, idx;
 };
 
-__device__ __forceinline__ void best2_update(Best2& b, int d, int m) {
-  if (d < b.best) {
-    b.second = b.best;
-    b.best = d;
-    b.idx = m;
-  } else if (d < b.second) {
-    b.second = d;
-  }
+__device__ __forceinline__ unsigned lop3_xor3(unsigned a, unsigned b, unsigned c) {
+  unsigned r;
+  asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+__device__ __forceinline__ unsigned lop3_maj(unsigned a, unsigned b, unsigned c) {
+  unsigned r;
+  asm("lop3.b32 %0, %1, %2, %3, 0xe8;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
 }
 
-// MODE 0: best/second/argmin (+ per (query, slice) candidate counts if cand_count != nullptr)
+// 256-bit Hamming distance with a two-level carry-save reduction of the eight XOR words:
+//   (x0,x1,x2) -> (s0,c0)   (x3,x4,x5) -> (s1,c1)   (s0,s1,x6) -> (s2,c2)
+//   d = popc(s2) + popc(x7) + 2 (popc(c0) + popc(c1) + popc(c2))
+// 5 POPC + 14 LOP3 instead of 8 POPC + 8 LOP3.  Measured pipe rates on B200 (profiles/int_peaks.json): POPC 16 / clk / SM
+// (XU pipe), LOP3 / IADD3 64 / clk / SM (ALU pipe).  The plain form is XU-bound at 8 / 16 = 0.5 clk per pair (ncu: XU 94 %,
+// ALU 49 %, profiles/r04b_bf_sweep_ncu.txt); this form balances the two pipes at ~0.31 clk per pair.  The full Harley-Seal
+// tree (4 POPC, 22 LOP3) would be ALU-bound at 0.39 -- worse.
+__device__ __forceinline__ int hamming256_csa(const uint4 a0, const uint4 a1, const uint4 b0, const uint4 b1) {
+  const unsigned x0 = a0.x ^ b0.x, x1 = a0.y ^ b0.y, x2 = a0.z ^ b0.z, x3 = a0.w ^ b0.w;
+  const unsigned x4 = a1.x ^ b1.x, x5 = a1.y ^ b1.y, x6 = a1.z ^ b1.z, x7 = a1.w ^ b1.w;
+  const unsigned s0 = lop3_xor3(x0, x1, x2), c0 = lop3_maj(x0, x1, x2);
+  const unsigned s1 = lop3_xor3(x3, x4, x5), c1 = lop3_maj(x3, x4, x5);
+  const unsigned s2 = lop3_xor3(s0, s1, x6), c2 = lop3_maj(s0, s1, x6);
+  return __popc(s2) + __popc(x7) + 2 * (__popc(c0) + __popc(c1) + __popc(c2));
+}
+
+// MODE 0: best / second / argmin per (query, slice)
+// MODE 2: MODE 0 + the number of candidates (d < max_dist_i) per (query, slice)
 // MODE 1: write candidates (d < max_dist_i) at cand_offset[query * n_slices + slice] in m order
-template <int MODE>
+// Best-2 bookkeeping (MODE 0 / 2) on packed keys (distance << 16 | train index within the slice): k1 = smallest,
+// k2 = second smallest key -- min / max only, and "first index wins ties" (the reference's sequential scan,
+// bruteforce_impl.cpp:36-66) is the key order itself.
+template <int MODE, int BF_QPT>
 __global__ void __launch_bounds__(BF_THREADS)
 bf_sweep_kernel(const uint4* __restrict__ q, int nq, const uint4* __restrict__ t, int nt,
                 int slice_len, int n_slices, int max_dist_i, int* __restrict__ part_best,
                 int* __restrict__ part_second, int* __restrict__ part_idx,
                 int* __restrict__ cand_count, const int* __restrict__ cand_offset,
                 unsigned long long* __restrict__ cand, int cand_capacity) {
+  constexpr int BF_QTILE = BF_THREADS * BF_QPT;
   __shared__ uint4 s_t[2][BF_TTILE * 2];
   const int tid = threadIdx.x;
   const int qtile = blockIdx.x, slice = blockIdx.y;
@@ -58,7 +80,7 @@ bf_sweep_kernel(const uint4* __restrict__ q, int nq, const uint4* __restrict__ t
 
   uint4 qa[BF_QPT][2];
   int qi[BF_QPT];
-  Best2 b[BF_QPT];
+  unsigned k1[BF_QPT], k2[BF_QPT];
   int cnt[BF_QPT];
   int wpos[BF_QPT];
 #pragma unroll
@@ -67,9 +89,8 @@ bf_sweep_kernel(const uint4* __restrict__ q, int nq, const uint4* __restrict__ t
     const int src = min(qi[k], nq - 1);
     qa[k][0] = __ldg(q + 2 * (size_t) src);
     qa[k][1] = __ldg(q + 2 * (size_t) src + 1);
-    b[k].best = INT_MAX;
-    b[k].second = INT_MAX;
-    b[k].idx = -1;
+    k1[k] = 0xffffffffu;
+    k2[k] = 0xffffffffu;
     cnt[k] = 0;
     wpos[k] = 0;
     if (MODE == 1 && qi[k] < nq) wpos[k] = cand_offset[(size_t) qi[k] * n_slices + slice];
@@ -92,15 +113,18 @@ bf_sweep_kernel(const uint4* __restrict__ q, int nq, const uint4* __restrict__ t
     if (stage + 1 < n_stages) load_stage(stage + 1, buf ^ 1);
     const int base = t_begin + stage * BF_TTILE;
     const int lim = min(BF_TTILE, t_end - base);
+    unsigned jj = (unsigned) (stage * BF_TTILE);  // index within the slice
 #pragma unroll 4
-    for (int j = 0; j < lim; ++j) {
+    for (int j = 0; j < lim; ++j, ++jj) {
       const uint4 t0 = s_t[buf][2 * j], t1 = s_t[buf][2 * j + 1];
 #pragma unroll
       for (int k = 0; k < BF_QPT; ++k) {
-        const int d = hamming256(qa[k][0], qa[k][1], t0, t1);
-        if (MODE == 0) {
-          best2_update(b[k], d, base + j);
-          cnt[k] += (d < max_dist_i) ? 1 : 0;
+        const int d = hamming256_csa(qa[k][0], qa[k][1], t0, t1);
+        if (MODE != 1) {
+          const unsigned key = ((unsigned) d << 16) | jj;
+          k2[k] = min(k2[k], max(k1[k], key));
+          k1[k] = min(k1[k], key);
+          if (MODE == 2) cnt[k] += (d < max_dist_i) ? 1 : 0;
         } else {
           if (d < max_dist_i && qi[k] < nq) {
             if (wpos[k] < cand_capacity)
@@ -113,15 +137,15 @@ bf_sweep_kernel(const uint4* __restrict__ q, int nq, const uint4* __restrict__ t
     }
     __syncthreads();
   }
-  if (MODE == 0) {
+  if (MODE != 1) {
 #pragma unroll
     for (int k = 0; k < BF_QPT; ++k) {
       if (qi[k] < nq) {
         const size_t o = (size_t) slice * nq + qi[k];
-        part_best[o] = b[k].best;
-        part_second[o] = b[k].second;
-        part_idx[o] = b[k].idx;
-        if (cand_count) cand_count[(size_t) qi[k] * n_slices + slice] = cnt[k];
+        part_best[o] = (k1[k] != 0xffffffffu) ? (int) (k1[k] >> 16) : INT_MAX;
+        part_second[o] = (k2[k] != 0xffffffffu) ? (int) (k2[k] >> 16) : INT_MAX;
+        part_idx[o] = (k1[k] != 0xffffffffu) ? t_begin + (int) (k1[k] & 0xffffu) : -1;
+        if (MODE == 2) cand_count[(size_t) qi[k] * n_slices + slice] = cnt[k];
       }
     }
   }
@@ -306,13 +330,24 @@ bf_resolve_kernel(const unsigned long long* __restrict__ cand, int n, const unsi
   if (tid == 0) *out_n = n_out;
 }
 
+int bf_qpt() {  // queries per thread: 4 measured best on B200 (PSLAM_BF_QPT=2 selects the narrower variant for tuning runs)
+  static const int v = [] {
+    const char* e = getenv("PSLAM_BF_QPT");
+    return (e && atoi(e) == 2) ? 2 : 4;
+  }();
+  return v;
+}
+
 int choose_slices(int nq, int nt, int sm_count) {
+  const int BF_QTILE = BF_THREADS * bf_qpt();
   const int qtiles = (nq + BF_QTILE - 1) / BF_QTILE;
   int s = (sm_count * 8 + qtiles - 1) / qtiles;
   const int max_s = (nt + 1023) / 1024;
   if (s > max_s) s = max_s;
   if (s < 1) s = 1;
   if (s > 64) s = 64;
+  const int min_s = (nt + BF_MAX_SLICE - 1) / BF_MAX_SLICE;  // 16-bit train index within a slice (packed best-2 keys)
+  if (s < min_s) s = min_s;
   return s;
 }
 
@@ -342,8 +377,10 @@ int pslam_k_bf_best2(pslam_ctx* ctx, int nq, const uint32_t* d_q, int nt, const 
   int* pb = reinterpret_cast<int*>(ctx->d_scratch);
   int* ps = reinterpret_cast<int*>(ctx->d_scratch + part);
   int* pi = reinterpret_cast<int*>(ctx->d_scratch + 2 * part);
+  const int BF_QTILE = BF_THREADS * bf_qpt();
   dim3 grid((nq + BF_QTILE - 1) / BF_QTILE, n_slices);
-  bf_sweep_kernel<0><<<grid, BF_THREADS, 0, ctx->stream>>>(
+  auto sweep = bf_qpt() == 4 ? bf_sweep_kernel<0, 4> : bf_sweep_kernel<0, 2>;
+  sweep<<<grid, BF_THREADS, 0, ctx->stream>>>(
     reinterpret_cast<const uint4*>(d_q), nq, reinterpret_cast<const uint4*>(d_t), nt, slice_len,
     n_slices, 0, pb, ps, pi, nullptr, nullptr, nullptr, 0);
   PSLAM_LAUNCH_CHECK(ctx, "bf_sweep_kernel<0>");
@@ -399,11 +436,14 @@ int pslam_k_bf_match(pslam_ctx* ctx, int nf, const uint32_t* d_f, int nm, const 
   const int cand_cap = cand_cap_sz > 0x7fffffff ? 0x7fffffff : (int) cand_cap_sz;
 
   PSLAM_CUDA_TRY(ctx, cudaMemsetAsync(bm_f, 0, (size_t) (zero_end - (uint8_t*) bm_f), ctx->stream));
+  const int BF_QTILE = BF_THREADS * bf_qpt();
   dim3 grid((nf + BF_QTILE - 1) / BF_QTILE, n_slices);
-  bf_sweep_kernel<0><<<grid, BF_THREADS, 0, ctx->stream>>>(
+  auto sweep2 = bf_qpt() == 4 ? bf_sweep_kernel<2, 4> : bf_sweep_kernel<2, 2>;
+  auto sweep1 = bf_qpt() == 4 ? bf_sweep_kernel<1, 4> : bf_sweep_kernel<1, 2>;
+  sweep2<<<grid, BF_THREADS, 0, ctx->stream>>>(
     reinterpret_cast<const uint4*>(d_f), nf, reinterpret_cast<const uint4*>(d_m), nm, slice_len,
     n_slices, max_dist_i, pb, ps, pi, cnt, nullptr, nullptr, 0);
-  PSLAM_LAUNCH_CHECK(ctx, "bf_sweep_kernel<0>");
+  PSLAM_LAUNCH_CHECK(ctx, "bf_sweep_kernel<2>");
   bf_scan_kernel<<<1, 1024, 0, ctx->stream>>>(cnt, offs, nf * n_slices, total);
   PSLAM_LAUNCH_CHECK(ctx, "bf_scan_kernel");
   int* h = reinterpret_cast<int*>(ctx->h_pinned);
@@ -413,7 +453,7 @@ int pslam_k_bf_match(pslam_ctx* ctx, int nf, const uint32_t* d_f, int nm, const 
   if (n_cand == 0) return 0;
   if (n_cand > cand_cap)
     return pslam_set_error(ctx, PSLAM_E_CAPACITY, "bf_match: candidate buffer too small", cudaSuccess);
-  bf_sweep_kernel<1><<<grid, BF_THREADS, 0, ctx->stream>>>(
+  sweep1<<<grid, BF_THREADS, 0, ctx->stream>>>(
     reinterpret_cast<const uint4*>(d_f), nf, reinterpret_cast<const uint4*>(d_m), nm, slice_len,
     n_slices, max_dist_i, nullptr, nullptr, nullptr, nullptr, offs, cand, cand_cap);
   PSLAM_LAUNCH_CHECK(ctx, "bf_sweep_kernel<1>");
