@@ -93,22 +93,38 @@ static const int FAST_DX[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -
 static const int FAST_DY[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
 
 // s = max over the 16 contiguous 9-arcs of min(d_k) and of min(-d_k); corner iff s > thr.
-static inline int fast_arc_strength(const uint8_t* p, int stride) {
-  int d[25];
+// min over 9 consecutive = min of three mins over 3 consecutive (k, k+3, k+6): 5 instead of 16 operations per arc.
+// want_dark / want_bright: polarities worth evaluating (the other one contributes <= 0 when the compass pre-test
+// excluded it: a 9-arc always contains two adjacent compass points); both = the full definition.
+static inline int fast_arc_strength(const uint8_t* p, int stride, bool want_dark = true, bool want_bright = true) {
+  int d[16 + 8];
   const int v = p[0];
   for (int k = 0; k < 16; ++k) d[k] = v - p[FAST_DY[k] * stride + FAST_DX[k]];
-  for (int k = 16; k < 25; ++k) d[k] = d[k - 16];
+  for (int k = 0; k < 8; ++k) d[16 + k] = d[k];
   int s = -1000;
-  for (int k = 0; k < 16; ++k) {
-    int mn = d[k], mx = d[k];
-    for (int j = 1; j < 9; ++j) {
-      mn = std::min(mn, d[k + j]);
-      mx = std::max(mx, d[k + j]);
-    }
-    s = std::max(s, mn);   // ring darker than centre by at least mn on the whole arc
-    s = std::max(s, -mx);  // ring brighter than centre by at least -mx on the whole arc
+  if (want_dark) {  // ring darker than the centre by at least min(d) on the whole arc
+    int m3[16 + 6];
+    for (int k = 0; k < 22; ++k) m3[k] = std::min(d[k], std::min(d[k + 1], d[k + 2]));
+    for (int k = 0; k < 16; ++k) s = std::max(s, std::min(m3[k], std::min(m3[k + 3], m3[k + 6])));
+  }
+  if (want_bright) {  // ring brighter than the centre by at least -max(d) on the whole arc
+    int m3[16 + 6];
+    for (int k = 0; k < 22; ++k) m3[k] = std::max(d[k], std::max(d[k + 1], d[k + 2]));
+    for (int k = 0; k < 16; ++k) s = std::max(s, -std::max(m3[k], std::max(m3[k + 3], m3[k + 6])));
   }
   return s;
+}
+
+// compass pre-test of 32 pixels at once (GCC vector extensions, bytes): ring > v + thr  <=>  sat(ring - v) > thr
+typedef uint8_t vu8x32 __attribute__((vector_size(32)));
+static inline vu8x32 vld32(const uint8_t* p) {
+  vu8x32 v;
+  std::memcpy(&v, p, 32);
+  return v;
+}
+static inline vu8x32 vsatsub(vu8x32 a, vu8x32 b) {
+  const vu8x32 m = a > b ? a : b;
+  return m - b;
 }
 
 // score map: 0 for non-corners, s-1 (>= thr) for corners; interior pixels only.
@@ -116,19 +132,36 @@ static inline void fast_score_map(const uint8_t* img, int rows, int cols, int st
                                   std::vector<int>& score) {
   score.assign((size_t) rows * cols, 0);
   thr = std::min(std::max(thr, 0), 255);
+  std::vector<uint8_t> flag((size_t) cols + 32, 0);
+  vu8x32 T, one, two;
+  for (int i = 0; i < 32; ++i) {
+    T[i] = (uint8_t) thr;
+    one[i] = 1;
+    two[i] = 2;
+  }
   for (int y = 3; y < rows - 3; ++y) {
-    for (int x = 3; x < cols - 3; ++x) {
-      const uint8_t* p = img + (size_t) y * stride + x;
-      // cheap reject: a 9-arc always contains two adjacent compass points
-      const int v = p[0];
-      const int c0 = p[3 * stride], c4 = p[3], c8 = p[-3 * stride], c12 = p[-3];
+    const uint8_t* row = img + (size_t) y * stride;
+    const uint8_t *rn = row + 3 * stride, *rs = row - 3 * stride;
+    // cheap reject: a 9-arc always contains two adjacent compass points -> (N | S) & (E | W) per polarity
+    int x = 3;
+    for (; x + 32 <= cols - 3; x += 32) {
+      const vu8x32 v = vld32(row + x), n = vld32(rn + x), so = vld32(rs + x), e = vld32(row + x + 3), w = vld32(row + x - 3);
+      const vu8x32 bright = (vu8x32) (((vsatsub(n, v) > T) | (vsatsub(so, v) > T)) & ((vsatsub(e, v) > T) | (vsatsub(w, v) > T)));
+      const vu8x32 dark = (vu8x32) (((vsatsub(v, n) > T) | (vsatsub(v, so) > T)) & ((vsatsub(v, e) > T) | (vsatsub(v, w) > T)));
+      const vu8x32 f = (bright & one) | (dark & two);
+      std::memcpy(flag.data() + x, &f, 32);
+    }
+    for (; x < cols - 3; ++x) {
+      const int v = row[x];
+      const int c0 = rn[x], c4 = row[x + 3], c8 = rs[x], c12 = row[x - 3];
       const int hi = v + thr, lo = v - thr;
-      const bool b0 = c0 > hi, b4 = c4 > hi, b8 = c8 > hi, b12 = c12 > hi;
-      const bool d0 = c0 < lo, d4 = c4 < lo, d8 = c8 < lo, d12 = c12 < lo;
-      const bool bright = (b0 && b4) || (b4 && b8) || (b8 && b12) || (b12 && b0);
-      const bool dark   = (d0 && d4) || (d4 && d8) || (d8 && d12) || (d12 && d0);
-      if (!bright && !dark) continue;
-      const int s = fast_arc_strength(p, stride);
+      const int bright = ((c0 > hi) | (c8 > hi)) & ((c4 > hi) | (c12 > hi));
+      const int dark = ((c0 < lo) | (c8 < lo)) & ((c4 < lo) | (c12 < lo));
+      flag[x] = (uint8_t) (bright | (dark << 1));
+    }
+    for (x = 3; x < cols - 3; ++x) {
+      if (!flag[x]) continue;
+      const int s = fast_arc_strength(row + x, stride, (flag[x] & 2) != 0, (flag[x] & 1) != 0);
       if (s > thr) score[(size_t) y * cols + x] = s - 1;
     }
   }
@@ -242,24 +275,34 @@ static inline int reflect101(int i, int n) {
 static inline void blur7(const uint8_t* img, int rows, int cols, int stride,
                          std::vector<uint8_t>& out) {
   out.assign((size_t) rows * cols, 0);
-  std::vector<int> h((size_t) rows * cols);
-  for (int y = 0; y < rows; ++y)
+  // horizontal pass (h <= 257 * 255 = 65535 fits 16 bits); the interior runs without the border reflection
+  std::vector<uint16_t> h((size_t) rows * cols);
+  for (int y = 0; y < rows; ++y) {
+    const uint8_t* r = img + (size_t) y * stride;
+    uint16_t* hr = h.data() + (size_t) y * cols;
     for (int x = 0; x < cols; ++x) {
+      if (x == 3 && cols > 6) {
+        for (; x < cols - 3; ++x)
+          hr[x] = (uint16_t) (18 * (r[x - 3] + r[x + 3]) + 34 * (r[x - 2] + r[x + 2]) + 49 * (r[x - 1] + r[x + 1]) + 55 * r[x]);
+        if (x >= cols) break;
+      }
       int acc = 0;
-      for (int j = -3; j <= 3; ++j)
-        acc += BLUR_TAPS[j + 3] * img[(size_t) y * stride + reflect101(x + j, cols)];
-      h[(size_t) y * cols + x] = acc;
+      for (int j = -3; j <= 3; ++j) acc += BLUR_TAPS[j + 3] * r[reflect101(x + j, cols)];
+      hr[x] = (uint16_t) acc;
     }
-  for (int y = 0; y < rows; ++y)
+  }
+  // vertical pass, x innermost (contiguous)
+  for (int y = 0; y < rows; ++y) {
+    const uint16_t* hp[7];
+    for (int j = -3; j <= 3; ++j) hp[j + 3] = h.data() + (size_t) reflect101(y + j, rows) * cols;
+    uint8_t* o = out.data() + (size_t) y * cols;
     for (int x = 0; x < cols; ++x) {
-      int acc = 0;
-      for (int j = -3; j <= 3; ++j)
-        acc += BLUR_TAPS[j + 3] * h[(size_t) reflect101(y + j, rows) * cols + x];
-      out[(size_t) y * cols + x] = (uint8_t) std::min(255, (acc + 32768) >> 16);
+      const int acc = 18 * (hp[0][x] + hp[6][x]) + 34 * (hp[1][x] + hp[5][x]) + 49 * (hp[2][x] + hp[4][x]) + 55 * hp[3][x];
+      o[x] = (uint8_t) std::min(255, (acc + 32768) >> 16);
     }
+  }
 }
 
-// cv::KeyPointsFilter::runByImageBorder(kps, size, 31): keep 31 <= x < cols-31 etc.
 static inline void orb_border_filter(int rows, int cols, std::vector<KeyPoint>& kps) {
   std::vector<KeyPoint> kept;
   kept.reserve(kps.size());
