@@ -428,11 +428,53 @@ def main():
     t0 = time.perf_counter()
     for _ in range(args.steps):
         res = step_e2e()
+    ctx.synchronize()
+    e2e_local_s = time.perf_counter() - t0  # this rank alone (download_stereo_batch has synchronised already)
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = world * E * args.steps / float(e2e_s.item())
+
+    # ---- the end-to-end leg's own roofline: raw pinned host -> device copy rate of THIS box with all N ranks copying at
+    # the same time, same source buffer, same chunk size as the pipeline's uploads (work_images images per cudaMemcpyAsync)
+    def h2d_probe():
+        chunk = min(h_images.numel(), args.work_images * img_bytes)
+        src = h_images.view(-1)
+        n_chunks = max(1, min(8, src.numel() // chunk))
+        dst = torch.empty(chunk, dtype=torch.uint8, device=dev)
+        side = torch.cuda.Stream(device=dev)
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        best = None
+        for rep in range(3):  # first repetition = warm-up
+            barrier()
+            with torch.cuda.stream(side):
+                p0.record(side)
+                for i in range(n_chunks):
+                    dst.copy_(src[i * chunk:(i + 1) * chunk], non_blocking=True)
+                p1.record(side)
+            side.synchronize()
+            ms_ = torch.tensor([p0.elapsed_time(p1)], device=dev, dtype=torch.float64)
+            mine = float(ms_.item())
+            if world > 1:
+                dist.all_reduce(ms_, op=dist.ReduceOp.MAX)
+            if rep > 0 and (best is None or float(ms_.item()) < best[0]):
+                best = (float(ms_.item()), mine)
+        del dst
+        agg = world * n_chunks * chunk / (best[0] * 1e-3) / 1e9
+        return agg, n_chunks * chunk / (best[1] * 1e-3) / 1e9, chunk
+
+    try:
+        h2d_peak_gbs, h2d_rank_gbs, h2d_chunk = h2d_probe()
+    except Exception as e:  # the probe must never cost the headline
+        h2d_peak_gbs, h2d_rank_gbs, h2d_chunk = None, None, repr(e)
+    # per-rank view of the end-to-end leg (explains spreads between runs at the same N: which rank / PCIe slot was slow)
+    props = torch.cuda.get_device_properties(local)
+    mine = torch.tensor([e2e_local_s, h2d_rank_gbs or 0.0, float(getattr(props, "pci_bus_id", -1))], device=dev, dtype=torch.float64)
+    per_rank = [mine.clone() for _ in range(world)]
+    if world > 1:
+        dist.all_gather(per_rank, mine)
+    per_rank = [[float(v) for v in t.tolist()] for t in per_rank]
     stop.set()
     sampler.join(timeout=3)
     n_pts = int(res["n"])
@@ -504,7 +546,14 @@ def main():
             "config": workload_config(args, P),
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "pairs_per_gpu_per_step": E,
-                    "api": "pslam_stereo_frontend_batch + pslam_download_stereo_batch (host pointers)"},
+                    "api": "pslam_stereo_frontend_batch + pslam_download_stereo_batch (host pointers)",
+                    "roofline": None if h2d_peak_gbs is None else {
+                        "bound": "pcie-h2d", "achieved_gbs": e2e_value * h2d / E / 1e9, "peak_gbs": h2d_peak_gbs,
+                        "frac": (e2e_value * h2d / E / 1e9) / h2d_peak_gbs, "unit": "GB/s",
+                        "peak_source": f"measured in this job: {world} rank(s) copying concurrently from pinned host memory, "
+                                       f"{h2d_chunk >> 20} MiB per cudaMemcpyAsync (the pipeline's chunk), max over ranks"},
+                    "per_rank": [{"rank": i, "e2e_s": r_[0], "frames_per_s": E * args.steps / r_[0] if r_[0] > 0 else None,
+                                  "h2d_probe_gbs": r_[1], "pci_bus_id": int(r_[2])} for i, r_ in enumerate(per_rank)]},
             "gpu_launches": int(gpu_launches), "roofline": roofline, "kernels": kernels,
             "clocks": summarise_clocks(clk_lines),
             "mean_features_per_image": mean_feat, "mean_stereo_points_per_frame": float(counts.mean())}

@@ -96,22 +96,33 @@ static const int FAST_DY[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1,
 // min over 9 consecutive = min of three mins over 3 consecutive (k, k+3, k+6): 5 instead of 16 operations per arc.
 // want_dark / want_bright: polarities worth evaluating (the other one contributes <= 0 when the compass pre-test
 // excluded it: a 9-arc always contains two adjacent compass points); both = the full definition.
+// Evaluated on the 16 ring pixels as one 16-byte vector (GCC vector extensions): saturating differences (a negative
+// difference clips to 0, which cannot change a strength that exceeds a threshold >= 0 -- callers only compare the
+// result with thr >= 0 or 0), min over 3 consecutive ring positions, then over three of those (9-arc), horizontal max.
+typedef uint8_t vu8x16 __attribute__((vector_size(16)));
+static inline vu8x16 vmin16(vu8x16 a, vu8x16 b) { return a < b ? a : b; }
+static inline vu8x16 vmax16(vu8x16 a, vu8x16 b) { return a > b ? a : b; }
+static inline int fast_arc_min9_max(vu8x16 d) {
+  const vu8x16 r1 = __builtin_shufflevector(d, d, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 0);
+  const vu8x16 r2 = __builtin_shufflevector(d, d, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 0, 1);
+  const vu8x16 m3 = vmin16(d, vmin16(r1, r2));
+  const vu8x16 s3 = __builtin_shufflevector(m3, m3, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 0, 1, 2);
+  const vu8x16 s6 = __builtin_shufflevector(m3, m3, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 0, 1, 2, 3, 4, 5);
+  vu8x16 m = vmin16(m3, vmin16(s3, s6));  // m[k] = min over ring positions k .. k + 8
+  m = vmax16(m, __builtin_shufflevector(m, m, 8, 9, 10, 11, 12, 13, 14, 15, 0, 1, 2, 3, 4, 5, 6, 7));
+  m = vmax16(m, __builtin_shufflevector(m, m, 4, 5, 6, 7, 0, 1, 2, 3, 4, 5, 6, 7, 0, 1, 2, 3));
+  m = vmax16(m, __builtin_shufflevector(m, m, 2, 3, 0, 1, 2, 3, 0, 1, 2, 3, 0, 1, 2, 3, 0, 1));
+  return std::max(m[0], m[1]);
+}
 static inline int fast_arc_strength(const uint8_t* p, int stride, bool want_dark = true, bool want_bright = true) {
-  int d[16 + 8];
-  const int v = p[0];
-  for (int k = 0; k < 16; ++k) d[k] = v - p[FAST_DY[k] * stride + FAST_DX[k]];
-  for (int k = 0; k < 8; ++k) d[16 + k] = d[k];
-  int s = -1000;
-  if (want_dark) {  // ring darker than the centre by at least min(d) on the whole arc
-    int m3[16 + 6];
-    for (int k = 0; k < 22; ++k) m3[k] = std::min(d[k], std::min(d[k + 1], d[k + 2]));
-    for (int k = 0; k < 16; ++k) s = std::max(s, std::min(m3[k], std::min(m3[k + 3], m3[k + 6])));
+  vu8x16 ring, c;
+  for (int k = 0; k < 16; ++k) {
+    ring[k] = p[FAST_DY[k] * stride + FAST_DX[k]];
+    c[k] = p[0];
   }
-  if (want_bright) {  // ring brighter than the centre by at least -max(d) on the whole arc
-    int m3[16 + 6];
-    for (int k = 0; k < 22; ++k) m3[k] = std::max(d[k], std::max(d[k + 1], d[k + 2]));
-    for (int k = 0; k < 16; ++k) s = std::max(s, -std::max(m3[k], std::max(m3[k + 3], m3[k + 6])));
-  }
+  int s = 0;
+  if (want_dark) s = std::max(s, fast_arc_min9_max(vmax16(c, ring) - ring));      // sat(c - ring)
+  if (want_bright) s = std::max(s, fast_arc_min9_max(vmax16(ring, c) - c));       // sat(ring - c)
   return s;
 }
 
