@@ -99,7 +99,7 @@ int run_extract_chunk(pslam_ctx* ctx, const uint8_t* d_images, long long image_p
   const SelectPlan plan = make_plan(cfg, d_mask != nullptr);
   if ((rc = pslam_k_bin_select(ctx, n_images, rows, cols, plan.nh, plan.nv, plan.quota, d_mask, 0))) return rc;
   if ((rc = pslam_k_assemble(ctx, d_images, image_pitch, stride, n_images, rows, cols, plan.nh * plan.nv, 31, slot_base))) return rc;
-  if ((rc = pslam_k_describe(ctx, n_images, slot_base))) return rc;
+  if ((rc = pslam_k_describe(ctx, n_images, rows, cols, slot_base))) return rc;
   return PSLAM_OK;
 }
 
@@ -249,6 +249,9 @@ int pslam_create(int device, const pslam_limits* lim, pslam_ctx** out) {
   PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_inten, NI * MF));
   PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_desc, NI * MF * 8));
   PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_count, NI));
+  ctx->tile_cap = pslam_k_orb_tile_cap(lim->max_rows, lim->max_cols);
+  PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_tile_start, NI * ((size_t) ctx->tile_cap + 1)));
+  PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_tile_order, NI * MF));
   PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_st_uvuv, NP * MF));
   PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_st_left, NP * MF));
   PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_st_right, NP * MF));
@@ -283,7 +286,7 @@ void pslam_destroy(pslam_ctx* ctx) {
                   ctx->d_sel_count, ctx->d_xy, ctx->d_resp, ctx->d_inten, ctx->d_desc, ctx->d_count,
                   ctx->d_st_uvuv, ctx->d_st_left, ctx->d_st_right, ctx->d_st_dist, ctx->d_st_count,
                   ctx->d_ep_fixed, ctx->d_ep_moving, ctx->d_ep_dist, ctx->d_ep_count, ctx->d_flags,
-                  ctx->d_sel_bounds, ctx->d_scratch, ctx->d_proj};
+                  ctx->d_sel_bounds, ctx->d_scratch, ctx->d_proj, ctx->d_tile_start, ctx->d_tile_order};
   for (void* b : bufs)
     if (b) cudaFree(b);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
@@ -436,7 +439,7 @@ int pslam_extract_selective(pslam_ctx* ctx, const uint8_t* image, int rows, int 
   for (int pass = 0; pass < passes; ++pass) {
     if ((rc = pslam_k_bin_select(ctx, 1, rows, cols, 1, 1, ~0ULL, ctx->d_mask, pass))) return rc;
     if ((rc = pslam_k_assemble(ctx, ctx->d_images, (long long) ctx->img_slot, ctx->img_pitch, 1, rows, cols, 1, 31, pass))) return rc;
-    if ((rc = pslam_k_describe(ctx, 1, pass))) return rc;
+    if ((rc = pslam_k_describe(ctx, 1, rows, cols, pass))) return rc;
   }
   const int n0 = pslam_download_features(ctx, 0, capacity, xy, response, intensity, desc);
   if (n0 < 0) return n0;

@@ -44,7 +44,11 @@ struct pslam_ctx {
   int* d_sel_bounds;      // K2: per region (row begin, row end, col begin, col end), valid for sel_bounds_key
   int sel_bounds_key[4];  // rows, cols, nh, nv the table was built for
   uint8_t* d_blur;
-  CUtensorMap blur_tmap;  // TMA view of the blur maps: u8 [work_images][max_rows][map_pitch], box {32, 31, 1}
+  CUtensorMap blur_tmap;  // TMA view of the blur maps: u8 [work_images][max_rows][map_pitch], box = one description tile (k_detect.cu)
+  // keypoints bucketed by description tile (written by assemble_features_kernel, read by orb_describe_tiles_kernel)
+  int tile_cap;                   // tiles of a max_rows x max_cols image
+  int* d_tile_start;              // [max_images][tile_cap + 1]
+  uint32_t* d_tile_order;         // [max_images][max_features] (keypoint index | x in tile << 13 | y in tile << 20), grouped by tile
   uint8_t* d_mask;  // [max_rows][map_pitch], single image (host entry point only)
   uint32_t* d_raw;
   int* d_raw_count;
