@@ -9,7 +9,7 @@
 //   bucket + std::sort + quota of IntensityFeatureExtractorBinned_::computeKeypoints (binned.cpp:164-200)
 //
 // K1 `fast_blur_rows_kernel` -- "marching" design.  A CTA owns a band of bh image rows over the whole image
-// width; a warp owns a 256-pixel strip, a lane 8 adjacent pixels (two 32-bit words).  The CTA walks down
+// width; a warp owns a 256-pixel strip, a lane 8 adjacent pixels (two 32-bit words).  The warp walks down
 // the band one row per step and keeps a 7-row window of (a) the raw pixels and (b) the horizontally
 // filtered rows in REGISTERS, so every pixel is loaded from HBM/L2 once and the inner loops are word-wide:
 //   * blur: horizontal 7-tap as 2 x dp4a on byte quads, vertical 7-tap as 7 x dp2a on packed u16 pairs
@@ -18,9 +18,15 @@
 //     a 9-arc always contains two adjacent compass points, so (N|S) & (E|W) per polarity is necessary;
 //   * candidates go to a per-warp shared-memory queue and are scored 32 at a time, one per lane, with only
 //     the polarity the pre-test saw (a pixel cannot be a bright AND a dark 9-arc corner: 9 + 9 > 16);
-//     score = max over the 16 arcs of min over the arc, written to a band-sized score tile in shared memory;
-//   * after the band: 3x3 NMS over the score tile and ordered emission of (col, response + 1) into per-row
-//     keypoint lists (row-major = the order cv::FAST emits), no dense NMS map ever goes to HBM.
+//     score = max over the 16 arcs of min over the arc, written to the warp's own 16-row score RING;
+//   * ROLLING 3x3 NMS inside the march: a fixed number of rows behind the scoring front the warp takes the three
+//     ring rows it needs, computes the 8-neighbour maximum of its 8 pixels per lane with byte-SIMD max / compare,
+//     and appends the survivors (col, response + 1) to the row's keypoint list in column order.
+// Strips start every 252 pixels and cover 256: the 2 pixels of overlap on either side make a strip's NMS
+// self-contained, so the warps of a CTA never synchronise, no score tile of the whole band exists (it capped the
+// band height at ~29 rows = 28 % of re-marched halo rows and the CTAs at four per SM) and the band height is free.
+// Every (row, strip) has its own 256-entry keypoint list; row-major order = rows, then strips, then entries = the
+// order cv::FAST emits.  No dense NMS map ever goes to HBM.
 // Blur values closer than 3 px to the image border are NOT the reflect-101 values (nothing on the path reads
 // them: ORB only describes keypoints >= 31 px from the border and samples <= 13 px + the 3 px filter reach);
 // `blur_border_kernel` patches them for the stage-level entry point pslam_blur7.
@@ -36,13 +42,16 @@
 
 namespace {
 
-constexpr int BH_MAX = 32;        // rows per band (upper limit; the launcher picks bh <= BH_MAX, see pslam_k_fast_blur)
 constexpr int QCAP = 1024;        // per-warp candidate ring (16-bit entries = 2 KB); one push phase adds <= 512
+constexpr int STRIP_STRIDE = 252; // strips start every 252 px and cover 256 (emit: strip columns 2 .. 253; strip 0 from column 0)
+constexpr int STRIP_LIST = 256;   // keypoint list entries per (row, strip)
+constexpr int RING = 16;          // rows of the per-warp score ring (power of two)
+constexpr int WARP_SMEM = RING * 256 + QCAP * 2 + RING * 4;  // score ring | candidate queue | queue tail after each row
 constexpr unsigned FULL = 0xffffffffu;
 constexpr unsigned M16 = 0x00ff00ffu;
 constexpr unsigned K9 = 0x02000200u;  // bit 9 of both 16-bit lanes
 
-__host__ __device__ inline int score_pitch(int cols) { return (cols + 8 + 3) & ~3; }  // bytes per score-tile row: pixel column c at byte c + 4
+__host__ __device__ inline int k1_strips(int cols) { return cols <= 256 ? 1 : (cols - 2 + STRIP_STRIDE - 1) / STRIP_STRIDE; }
 
 // ---- row load: every lane fetches ONE naturally aligned 8-byte chunk ------------------------------------------
 // Image rows start at any byte (KITTI: 1241-byte pitch).  With a = row + warp * 256 + lane * 8 and d = a & 7 (the same
@@ -202,13 +211,13 @@ struct K1Args {
   const uint8_t* images;
   long long image_pitch;
   int rows, cols, stride, thr, nms;
-  int bh;              // rows per band (<= BH_MAX), chosen by the launcher (shared-memory budget)
+  int bh;              // rows per band, chosen by the launcher
   uint8_t* blur;
   int map_pitch;
   long long map_slot;
-  int* row_count;      // [images][max_rows]
-  uint32_t* row_kp;    // [images][max_rows][row_cap]  (col << 8) | (response + 1)
-  int row_cap, max_rows;
+  int* row_count;      // [images][max_rows][strips_cap]
+  uint32_t* row_kp;    // [images][max_rows][strips_cap][STRIP_LIST]  (col << 8) | (response + 1)
+  int strips_cap, max_rows;
 };
 
 // Candidate queue: push this lane's candidates (mask bits 0-7 bright, 8-15 dark pixels x0..x0+7 of tile row
@@ -217,33 +226,107 @@ struct K1Args {
 // (ncu: stall_no_instruction was the top stall reason).  Returns the new (head, tail) packed in 64 bits.
 // Entries are 16 bits, see score_entry.
 struct ScoreCtx {
-  const uint8_t* img;
-  uint8_t* s_score;
-  unsigned* s_bits;
-  int stride, by, thr, SP, BW, xw;
+  const uint8_t* img;   // first pixel of the strip (image + strip * STRIP_STRIDE)
+  uint8_t* s_score;     // the warp's score ring: [RING][256], strip column k at byte k
+  int stride, thr, row_lo;
 };
 __device__ __forceinline__ void score_entry(const ScoreCtx& c, unsigned entry) {
-  // entry = [tile row of the pair : 6][lane : 5][bit index i : 5], i = [second row : 1][dark : 1][pixel : 3] -- the push
-  // loop (one or two active lanes per iteration) only adds i, the decoding happens here with all 32 lanes busy
+  // entry = [ring row of the pair's first row : 4][lane : 5][bit index i : 5], i = [second row : 1][dark : 1][pixel : 3] -- the
+  // push loop (one or two active lanes per iteration) only adds i, the decoding happens here with all 32 lanes busy.
+  // Pending entries belong to rows row_lo .. row_lo + RING - 1: the ring row identifies the image row.
   const unsigned i = entry & 31u;
-  const int col = c.xw + ((entry >> 2) & 0xf8u) + (i & 7u), trow = (entry >> 10) + (i >> 4);
+  const int col = (int) ((entry >> 2) & 0xf8u) + (int) (i & 7u);
+  const int rr = (int) ((entry >> 10) + (i >> 4)) & (RING - 1);
   const bool bright = (i & 8u) == 0u;
-  const int y = c.by - 1 + trow;
+  const int y = c.row_lo + ((rr - c.row_lo) & (RING - 1));
   const int s = fast_score_polar(c.img + (size_t) y * c.stride + col, c.stride, bright);
-  if (s > c.thr) {
-    const int ci = col + 4;
-    c.s_score[trow * c.SP + ci] = (uint8_t) s;  // 1..255; response = s - 1
-    atomicOr(&c.s_bits[trow * c.BW + (ci >> 5)], 1u << (ci & 31));
+  if (s > c.thr) c.s_score[rr * 256 + col] = (uint8_t) s;  // 1..255; response = s - 1
+}
+// One call per PAIR of rows (A, A + 1), three jobs (deliberately NOT inlined: inlining it into the marching loop makes
+// the kernel overflow the instruction cache and its registers spill):
+//  1. push: this lane's candidates (mask bits 0-15 row A, 16-31 row A + 1; per row bits 0-7 bright, 8-15 dark pixels
+//     x0 .. x0+7) go to the warp's queue in lane order;
+//  2. drain: full batches of 32 candidates are scored, one per lane;
+//  3. rolling NMS: the row pair three pairs behind, (A - 5, A - 4), is suppressed and emitted -- it needs the rows up to
+//     A - 3 scored, i.e. the queue head past the tail recorded two calls ago (s_tail); in the rare case it is not (fewer
+//     than 32 candidates in several rows) the partial batch is scored now.  `final`: everything is scored and the last
+//     three pairs are emitted.
+// Returns the new (head, tail) packed in 64 bits.
+struct NmsOut {
+  uint32_t* row_kp;  // list of (row 0, this strip); a row's lists are row_stride entries apart
+  int* row_count;
+  int row_stride;    // strips_cap
+};
+__device__ __forceinline__ void nms_emit_pair(const uint8_t* s_score, int t, int nms, unsigned emit_mask, int col0, int row_end,
+                                              const NmsOut& o) {
+  // rows t and t + 1 of the strip: 3x3 strict maximum over the score ring with byte-SIMD max / compare (8 pixels per lane),
+  // then ordered emission into the (row, strip) keypoint lists
+  const int lane = threadIdx.x & 31;
+  const uint2 r0 = *reinterpret_cast<const uint2*>(s_score + ((t - 1) & (RING - 1)) * 256 + lane * 8);
+  const uint2 r1 = *reinterpret_cast<const uint2*>(s_score + (t & (RING - 1)) * 256 + lane * 8);
+  const uint2 r2 = *reinterpret_cast<const uint2*>(s_score + ((t + 1) & (RING - 1)) * 256 + lane * 8);
+  const uint2 r3 = *reinterpret_cast<const uint2*>(s_score + ((t + 2) & (RING - 1)) * 256 + lane * 8);
+  unsigned bits[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const uint2 u = h ? r1 : r0, c = h ? r2 : r1, d = h ? r3 : r2;
+    unsigned keep_lo, keep_hi;
+    if (nms) {
+      const unsigned v_lo = __vmaxu4(u.x, d.x), v_hi = __vmaxu4(u.y, d.y);       // rows above / below, same column
+      const unsigned a_lo = __vmaxu4(v_lo, c.x), a_hi = __vmaxu4(v_hi, c.y);     // all three rows
+      unsigned left = __shfl_up_sync(FULL, a_hi, 1), right = __shfl_down_sync(FULL, a_lo, 1);
+      if (lane == 0) left = 0u;    // strip column -1 / 256: never next to an emitted column
+      if (lane == 31) right = 0u;
+      // byte j of l_* = column j - 1, of r_* = column j + 1 (of the 3-row maxima)
+      const unsigned l_lo = __funnelshift_l(left, a_lo, 8), l_hi = __funnelshift_l(a_lo, a_hi, 8);
+      const unsigned r_lo = __funnelshift_r(a_lo, a_hi, 8), r_hi = __funnelshift_r(a_hi, right, 8);
+      // response s - 1 strictly greater than every neighbour's (0 for non-corners): s > max(neighbours, 1)
+      const unsigned m_lo = __vmaxu4(__vmaxu4(__vmaxu4(l_lo, r_lo), v_lo), 0x01010101u);
+      const unsigned m_hi = __vmaxu4(__vmaxu4(__vmaxu4(l_hi, r_hi), v_hi), 0x01010101u);
+      keep_lo = __vcmpgtu4(c.x, m_lo);
+      keep_hi = __vcmpgtu4(c.y, m_hi);
+    } else {
+      keep_lo = __vcmpgtu4(c.x, 0u);
+      keep_hi = __vcmpgtu4(c.y, 0u);
+    }
+    // 0xff / 0x00 per byte -> one bit per pixel
+    bits[h] = ((((keep_lo & 0x01010101u) * 0x01020408u) >> 24) | ((((keep_hi & 0x01010101u) * 0x01020408u) >> 24) << 4)) & emit_mask;
+  }
+  // one prefix scan for both rows (counts packed in 16-bit halves)
+  const int cnt = __popc(bits[0]) | (__popc(bits[1]) << 16);
+  int incl = cnt;
+#pragma unroll
+  for (int o2 = 1; o2 < 32; o2 <<= 1) {
+    const int tt = __shfl_up_sync(FULL, incl, o2);
+    if (lane >= o2) incl += tt;
+  }
+  const int excl = incl - cnt;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int row = t + h;
+    if (row >= row_end) break;
+    const uint2 c = h ? r2 : r1;
+    uint32_t* out = o.row_kp + (size_t) row * o.row_stride * STRIP_LIST;
+    int pos = (excl >> (16 * h)) & 0xffff;
+    unsigned b = bits[h];
+    while (b) {
+      const int j = __ffs(b) - 1;
+      b &= b - 1;
+      const unsigned sv = ((j < 4 ? c.x : c.y) >> (8 * (j & 3))) & 0xffu;
+      out[pos++] = ((unsigned) (col0 + j) << 8) | (nms ? sv : 1u);  // without NMS the response is 0
+    }
+    if (lane == 31) o.row_count[(size_t) row * o.row_stride] = (incl >> (16 * h)) & 0xffff;
   }
 }
-__device__ __noinline__ unsigned long long push_and_drain(const uint8_t* img, uint8_t* s_score, unsigned* s_bits,
-                                                          unsigned short* s_queue, int stride, int by, int thr, int SP,
-                                                          int BW, unsigned mask, unsigned ebase, unsigned q_head,
-                                                          unsigned q_tail, bool flush) {
-  // `mask`: candidates of TWO consecutive tile rows (bits 0-15 row trow, bits 16-31 row trow + 1; per row bits 0-7
-  // bright, 8-15 dark pixels x0 .. x0+7); ebase = trow << 10.  Pushing two rows per call halves the scans.
+
+__device__ __noinline__ unsigned long long push_drain_nms(const uint8_t* img, uint8_t* s_score, unsigned short* s_queue,
+                                                          unsigned* s_tail, int stride, int thr, int nms, unsigned mask, int row_a,
+                                                          int by, int row_end, NmsOut out, unsigned q_head, unsigned q_tail,
+                                                          bool final) {
   const int lane = threadIdx.x & 31;
-  ScoreCtx c{img, s_score, s_bits, stride, by, thr, SP, BW, (int) (threadIdx.x >> 5) * 256};
+  // pending candidates belong to rows row_a - 8 .. row_a + 1: the ring row identifies the image row
+  ScoreCtx c{img, s_score, stride, thr, row_a - 8};
+  const unsigned ebase = (unsigned) (row_a & (RING - 1)) << 10;
   unsigned rest = 0u;
   bool more;
   do {
@@ -287,39 +370,59 @@ __device__ __noinline__ unsigned long long push_and_drain(const uint8_t* img, ui
     mask = rest;
     rest = 0u;
   } while (more);
-  if (flush && q_tail != q_head) {  // end of the band: what is left (< 32 entries)
+  // ---- rolling NMS ----
+  const unsigned need = final ? q_tail : s_tail[1];  // tail after the pair (row_a - 4, row_a - 3) was pushed
+  if ((int) (need - q_head) > 0) {                   // rows the NMS is about to read still have unscored candidates
     if ((unsigned) lane < q_tail - q_head) score_entry(c, s_queue[(q_head + lane) & (QCAP - 1)]);
     q_head = q_tail;
   }
   __syncwarp();
+  if (lane == 0) {
+    s_tail[1] = s_tail[0];
+    s_tail[0] = q_tail;
+  }
+  // emit range of this strip: columns 2 .. 253 (strip 0: from 0); the overlap columns belong to the neighbour strips
+  unsigned emit_mask = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = lane * 8 + j;
+    if ((k >= 2 || threadIdx.x < 32) && k < STRIP_STRIDE + 2) emit_mask |= 1u << j;
+  }
+  const int col0 = (int) (threadIdx.x >> 5) * STRIP_STRIDE + lane * 8;
+  const int n_pairs = final ? 3 : 1;
+  for (int p = 0; p < n_pairs; ++p) {
+    const int t = row_a - 5 + 2 * p;
+    if (t >= by && t < row_end) {
+      nms_emit_pair(s_score, t, nms, emit_mask, col0, row_end, out);
+      // rows t - 1 and t are not needed any more: their ring slots are reused RING rows later
+      *reinterpret_cast<uint2*>(s_score + ((t - 1) & (RING - 1)) * 256 + lane * 8) = make_uint2(0u, 0u);
+      *reinterpret_cast<uint2*>(s_score + (t & (RING - 1)) * 256 + lane * 8) = make_uint2(0u, 0u);
+    }
+    __syncwarp();
+  }
   return ((unsigned long long) q_tail << 32) | q_head;
 }
 
-__host__ __device__ inline int bits_pitch(int cols) { return (score_pitch(cols) + 31) / 32; }  // words / tile row
-
-// 96 registers (no spills): 4 CTAs of 5 warps per SM at KITTI width, and the launcher sizes the band so that four CTAs'
-// shared memory fits as well (20 resident warps instead of 15: -3.5 % kernel time).  An earlier, fatter version of the
-// kernel (107-119 registers) spilled at this limit and thrashed the small L1 that 4 x 54 KB of shared memory leave
-// (hit rate 71 % -> 42 %); the aligned-chunk row loads and the SIMD scorer brought the footprint down.
+// 96 registers: 4 CTAs of 5 warps per SM at KITTI width.  Shared memory is 6.1 KB per warp (score ring, candidate queue).
 __global__ void __maxnreg__(96)
 fast_blur_rows_kernel(const K1Args a) {
   extern __shared__ __align__(16) uint8_t smem[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_strips = blockDim.x >> 5;
-  const int rows = a.rows, cols = a.cols, stride = a.stride, thr = a.thr, BH = a.bh;
-  const int SP = score_pitch(cols), BW = bits_pitch(cols);
-  // shared memory: score tile | corner bitmap | per-warp 2 KB: candidate ring (march) / corner list (NMS phase)
-  uint8_t* s_score = smem;                                                     // [BH + 2][SP], pixel column c at byte c + 4
-  unsigned* s_bits = reinterpret_cast<unsigned*>(smem + (size_t) (BH + 2) * SP);  // [BH + 2][BW], bit = byte index in the row
-  unsigned short* s_queue = reinterpret_cast<unsigned short*>(s_bits + (BH + 2) * BW) + warp * QCAP;
-  unsigned short* s_list = s_queue;  // the ring is dead once the band has been scored
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rows = a.rows, cols = a.cols, stride = a.stride, thr = a.thr, BH = a.bh;  // BH is even
+  uint8_t* s_score = smem + (size_t) warp * WARP_SMEM;                                   // [RING][256]
+  unsigned short* s_queue = reinterpret_cast<unsigned short*>(s_score + RING * 256);     // [QCAP]
+  unsigned* s_tail = reinterpret_cast<unsigned*>(s_score + RING * 256 + QCAP * 2);        // queue tails after the last two pushes
   const int by = blockIdx.x * BH, image = blockIdx.y;
+  const int band_end = min(by + BH, rows);
   const uint8_t* img = a.images + (size_t) image * a.image_pitch;
   uint8_t* blur = a.blur + (size_t) image * a.map_slot;
-  const int x0 = warp * 256 + lane * 8;
+  const int xs = warp * STRIP_STRIDE;     // first column of the strip
+  const int x0 = xs + lane * 8;
   const bool has_left = warp > 0;  // lane 0 of strip 0 has no left halo (columns < 0)
 
-  for (int i = tid; i < ((BH + 2) * SP + (BH + 2) * BW * 4) / 4; i += blockDim.x) reinterpret_cast<unsigned*>(smem)[i] = 0u;
-  __syncthreads();
+  for (int i = lane; i < RING * 256 / 4; i += 32) reinterpret_cast<unsigned*>(s_score)[i] = 0u;
+  if (lane < RING) s_tail[lane] = 0u;
+  __syncwarp();
 
   // FAST centres: 3 <= x <= cols - 4
   unsigned colmask = 0;
@@ -328,9 +431,12 @@ fast_blur_rows_kernel(const K1Args a) {
     if (x0 + j >= 3 && x0 + j <= cols - 4) colmask |= 1u << j;
   colmask |= colmask << 8;  // bright bits 0-7, dark bits 8-15
   const unsigned t1 = (unsigned) (thr + 1) * 0x00010001u;
-  const bool store_ok = x0 < a.map_pitch;
-  unsigned q_head = 0, q_tail = 0, pend = 0u, pend_base = 0u;
-  bool have_pend = false;
+  const bool store_lo = x0 < a.map_pitch, store_hi = x0 + 4 < a.map_pitch;
+  unsigned q_head = 0, q_tail = 0, pend = 0u;
+  NmsOut out;
+  out.row_stride = a.strips_cap;
+  out.row_kp = a.row_kp + ((size_t) image * a.max_rows * a.strips_cap + warp) * STRIP_LIST;
+  out.row_count = a.row_count + (size_t) image * a.max_rows * a.strips_cap + warp;
 
   RowRegs R[7];
   unsigned H[7][4];
@@ -364,7 +470,7 @@ fast_blur_rows_kernel(const K1Args a) {
     }
     RowRegs& cur = R[6];
     {
-      const unsigned d = (unsigned) (uintptr_t) (row_ptr(r) + x0) & 7u;  // uniform over the CTA
+      const unsigned d = (unsigned) (uintptr_t) (row_ptr(r) + x0) & 7u;  // uniform over the warp
       const bool hi = d >= 4u;
       const unsigned sh = (d & 3u) * 8u;
       uint2 qn;
@@ -382,93 +488,31 @@ fast_blur_rows_kernel(const K1Args a) {
     if (step + 1 < n_steps) nx = loadq_issue(row_ptr(r + 1), x0, lane, has_left, cols);
     hblur8(cur, H[6]);
     const int rc = r - 3;  // blur output row and FAST centre row
-    if (rc >= by && rc < by + BH && rc < rows && store_ok) {
+    if (rc >= by && rc < band_end) {
       unsigned o[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) o[k] = vblur_pair(H[0][k], H[1][k], H[2][k], H[3][k], H[4][k], H[5][k], H[6][k]);
-      uint2 w;
-      w.x = __byte_perm(o[0], o[1], 0x5410);
-      w.y = __byte_perm(o[2], o[3], 0x5410);
-      *reinterpret_cast<uint2*>(blur + (size_t) rc * a.map_pitch + x0) = w;
+      // x0 is a multiple of 4 (strips start every 252 pixels): two 4-byte stores
+      unsigned* bo = reinterpret_cast<unsigned*>(blur + (size_t) rc * a.map_pitch + x0);
+      if (store_lo) bo[0] = __byte_perm(o[0], o[1], 0x5410);
+      if (store_hi) bo[1] = __byte_perm(o[2], o[3], 0x5410);
     }
-    if (rc >= by - 1 && rc <= by + BH && rc >= 3 && rc < rows - 3) {
-      unsigned mb, md;
-      pretest8(R[0], R[3], cur, t1, mb, md);
-      const unsigned m16 = (mb | (md << 8)) & colmask;
-      if (!have_pend) {  // rows are pushed in pairs (the executed centre rows of a band are consecutive)
+    if (rc >= by - 1) {  // rows by - 1 .. by + BH: BH + 2 rows = BH / 2 + 1 pairs (A, A + 1), A = by - 1, by + 1, ...
+      unsigned m16 = 0u;
+      if (rc >= 3 && rc < rows - 3) {
+        unsigned mb, md;
+        pretest8(R[0], R[3], cur, t1, mb, md);
+        m16 = (mb | (md << 8)) & colmask;
+      }
+      if (((rc - by) & 1) != 0) {  // first row of a pair
         pend = m16;
-        pend_base = (unsigned) (rc - (by - 1)) << 10;
-        have_pend = true;
       } else {
-        const unsigned long long q = push_and_drain(img, s_score, s_bits, s_queue, stride, by, thr, SP, BW,
-                                                    pend | (m16 << 16), pend_base, q_head, q_tail, false);
+        const unsigned long long q = push_drain_nms(img + xs, s_score, s_queue, s_tail, stride, thr, a.nms, pend | (m16 << 16),
+                                                    rc - 1, by, band_end, out, q_head, q_tail, step + 1 == n_steps);
         q_head = (unsigned) q;
         q_tail = (unsigned) (q >> 32);
-        have_pend = false;
-        pend = 0u;
       }
     }
-  }
-  // the unpaired last row (if any) and what is left in the queue (< 32 entries)
-  push_and_drain(img, s_score, s_bits, s_queue, stride, by, thr, SP, BW, pend, pend_base, q_head, q_tail, true);
-  __syncthreads();
-
-  // ---- 3x3 NMS + ordered emission into the per-row keypoint lists ----
-  // per tile row, in groups of 32 bitmap words: (A) ordered compaction of the corner bits into a list of byte
-  // indices, (B) one corner per lane: compare with the 8 neighbours in the score tile, ballot, append survivors
-  // in column order.
-  for (int t = 1 + warp; t <= BH; t += n_strips) {
-    const int y = by - 1 + t;
-    if (y >= rows) break;
-    uint32_t* out = a.row_kp + ((size_t) image * a.max_rows + y) * a.row_cap;
-    int count = 0;
-    for (int g = 0; g < BW; g += 32) {
-      const int j = g + lane;
-      unsigned w = j < BW ? s_bits[t * BW + j] : 0u;
-      const int cnt = __popc(w);
-      int incl = cnt;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int tt = __shfl_up_sync(FULL, incl, o);
-        if (lane >= o) incl += tt;
-      }
-      const int n_list = __shfl_sync(FULL, incl, 31);
-      if (n_list == 0) continue;
-      int pos = incl - cnt;
-      while (w) {
-        const int b = __ffs(w) - 1;
-        w &= w - 1;
-        s_list[pos++] = (unsigned short) (32 * j + b);
-      }
-      __syncwarp();
-      for (int k0 = 0; k0 < n_list; k0 += 32) {
-        const int k = k0 + lane;
-        bool keep = false;
-        unsigned entry = 0;
-        if (k < n_list) {
-          const int ci = s_list[k];
-          const uint8_t* sc = s_score + (size_t) t * SP + ci;
-          const int sv = sc[0];
-          keep = true;
-          int val = 1;  // without NMS the response is 0
-          if (a.nms) {
-            int m = max(max(sc[-SP - 1], sc[-SP]), max(sc[-SP + 1], sc[-1]));
-            m = max(m, max(max(sc[1], sc[SP - 1]), max(sc[SP], sc[SP + 1])));
-            keep = m > 0 ? sv > m : sv >= 2;  // response s-1 strictly greater than every neighbour's (0 for non-corners)
-            val = sv;
-          }
-          entry = ((unsigned) (ci - 4) << 8) | (unsigned) val;
-        }
-        const unsigned bal = __ballot_sync(FULL, keep);
-        if (keep) {
-          const int pos2 = count + __popc(bal & ((1u << lane) - 1u));
-          if (pos2 < a.row_cap) out[pos2] = entry;
-        }
-        count += __popc(bal);
-      }
-      __syncwarp();
-    }
-    if (lane == 0) a.row_count[(size_t) image * a.max_rows + y] = count < a.row_cap ? count : a.row_cap;
   }
 }
 
@@ -516,7 +560,7 @@ struct RespGreater {
 };
 
 __global__ void __launch_bounds__(SEL_THREADS)
-bin_select_kernel(const int* __restrict__ row_count, const uint32_t* __restrict__ row_kp, int row_cap, int max_rows,
+bin_select_kernel(const int* __restrict__ row_count, const uint32_t* __restrict__ row_kp, int strips_cap, int max_rows,
                   const uint8_t* __restrict__ mask, int mask_pitch, int mask_invert, int rows, int cols, int nh, int nv,
                   float pixel_rows_per_detector, float pixel_cols_per_detector, uint32_t* __restrict__ raw,
                   int max_raw_per_bin, int max_bins, int* __restrict__ raw_count, int* __restrict__ sel_count,
@@ -531,39 +575,40 @@ bin_select_kernel(const int* __restrict__ row_count, const uint32_t* __restrict_
   // the launcher evaluates it once (same fp32 arithmetic) instead of every CTA walking all rows and columns
   const int4 bd = __ldg(reinterpret_cast<const int4*>(bounds) + bin);
   const int rbegin = bd.x, rend = bd.y, cbegin = bd.z, cend = bd.w;
-  // ordered gather: one thread per image row, rows in chunks of SEL_THREADS
+  // ordered gather: one thread per image row, rows in chunks of SEL_THREADS.  A row's keypoints come as one list per
+  // 252-pixel strip (K1), strips in column order: only the strips that overlap the region's columns are walked.
+  const int s_first = cbegin < STRIP_STRIDE + 2 ? 0 : (cbegin - 2) / STRIP_STRIDE;
+  const int s_last = cend - 1 < STRIP_STRIDE + 2 ? 0 : (cend - 1 - 2) / STRIP_STRIDE;
   int running = 0;
   for (int base = rbegin; base < rend; base += SEL_THREADS) {
     const int r = base + tid;
-    int cnt = 0, first = 0, n_r = 0;
-    const uint32_t* src = nullptr;
+    int cnt = 0;
     if (r < rend) {
-      n_r = row_count[(size_t) image * max_rows + r];
-      src = row_kp + ((size_t) image * max_rows + r) * row_cap;
-      // four list entries per load (rows are 16-byte aligned and row_cap is a multiple of 4): the walk is a chain of
-      // dependent L2 accesses, a quarter as many now
-      bool done = false;
-      for (int k0 = 0; k0 < n_r && !done; k0 += 4) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + k0));
-        const uint32_t e4[4] = {v.x, v.y, v.z, v.w};
+      for (int st = s_first; st <= s_last; ++st) {
+        const size_t o = ((size_t) image * max_rows + r) * strips_cap + st;
+        const int n_r = row_count[o];
+        const uint32_t* src = row_kp + o * STRIP_LIST;
+        // four list entries per load (lists are 16-byte aligned): the walk is a chain of dependent L2 accesses
+        bool done = false;
+        for (int k0 = 0; k0 < n_r && !done; k0 += 4) {
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + k0));
+          const uint32_t e4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int k = k0 + u;
-          if (done || k >= n_r) {
-            done = true;
-            continue;
+          for (int u = 0; u < 4; ++u) {
+            const int k = k0 + u;
+            if (done || k >= n_r) {
+              done = true;
+              continue;
+            }
+            const int c = (int) (e4[u] >> 8);
+            if (c < cbegin) continue;
+            if (c >= cend) {
+              done = true;
+              continue;
+            }
+            if (mask && ((mask[(size_t) r * mask_pitch + c] == 0) != (mask_invert != 0))) continue;
+            ++cnt;
           }
-          const int c = (int) (e4[u] >> 8);
-          if (c < cbegin) {
-            first = k + 1;
-            continue;
-          }
-          if (c >= cend) {
-            done = true;
-            continue;
-          }
-          if (mask && ((mask[(size_t) r * mask_pitch + c] == 0) != (mask_invert != 0))) continue;
-          ++cnt;
         }
       }
     }
@@ -571,27 +616,32 @@ bin_select_kernel(const int* __restrict__ row_count, const uint32_t* __restrict_
     const int off = block_exclusive_scan<SEL_THREADS>(cnt, s_warp, &total);
     if (cnt) {
       int o = running + off;
-      bool done = false;
-      for (int k0 = first & ~3; k0 < n_r && !done; k0 += 4) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + k0));
-        const uint32_t e4[4] = {v.x, v.y, v.z, v.w};
+      for (int st = s_first; st <= s_last; ++st) {
+        const size_t ol = ((size_t) image * max_rows + r) * strips_cap + st;
+        const int n_r = row_count[ol];
+        const uint32_t* src = row_kp + ol * STRIP_LIST;
+        bool done = false;
+        for (int k0 = 0; k0 < n_r && !done; k0 += 4) {
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + k0));
+          const uint32_t e4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int k = k0 + u;
-          if (k < first) continue;
-          if (done || k >= n_r) {
-            done = true;
-            continue;
+          for (int u = 0; u < 4; ++u) {
+            const int k = k0 + u;
+            if (done || k >= n_r) {
+              done = true;
+              continue;
+            }
+            const uint32_t e = e4[u];
+            const int c = (int) (e >> 8);
+            if (c < cbegin) continue;
+            if (c >= cend) {
+              done = true;
+              continue;
+            }
+            if (mask && ((mask[(size_t) r * mask_pitch + c] == 0) != (mask_invert != 0))) continue;
+            if (o < max_raw_per_bin) seg[o] = ((uint32_t) (r * cols + c) << 8) | (e & 0xffu);
+            ++o;
           }
-          const uint32_t e = e4[u];
-          const int c = (int) (e >> 8);
-          if (c >= cend) {
-            done = true;
-            continue;
-          }
-          if (mask && ((mask[(size_t) r * mask_pitch + c] == 0) != (mask_invert != 0))) continue;
-          if (o < max_raw_per_bin) seg[o] = ((uint32_t) (r * cols + c) << 8) | (e & 0xffu);
-          ++o;
         }
       }
     }
@@ -633,10 +683,13 @@ bin_select_kernel(const int* __restrict__ row_count, const uint32_t* __restrict_
 }  // namespace
 
 // ---- host-side launchers -----------------------------------------------------------------------------------
+int pslam_k_strips_cap(int max_cols) { return k1_strips(max_cols); }
+
 int pslam_k_fast_blur(pslam_ctx* ctx, const uint8_t* d_images, long long image_pitch, int n_images,
                       int rows, int cols, int stride, int thr, int nms) {
-  const int n_strips = (cols + 255) / 256;
-  if (n_strips > 16) return pslam_set_error(ctx, PSLAM_E_CAPACITY, "images wider than 4096 pixels are not supported", cudaSuccess);
+  const int n_strips = k1_strips(cols);
+  if (n_strips > 16 || n_strips > ctx->strips_cap)
+    return pslam_set_error(ctx, PSLAM_E_CAPACITY, "images wider than 4032 pixels (or than pslam_limits.max_cols) are not supported", cudaSuccess);
   thr = thr < 0 ? 0 : (thr > 255 ? 255 : thr);
   K1Args a;
   a.images = d_images;
@@ -651,34 +704,32 @@ int pslam_k_fast_blur(pslam_ctx* ctx, const uint8_t* d_images, long long image_p
   a.map_slot = (long long) ctx->map_slot;
   a.row_count = ctx->d_row_count;
   a.row_kp = ctx->d_row_kp;
-  a.row_cap = ctx->map_pitch;
+  a.strips_cap = ctx->strips_cap;
   a.max_rows = ctx->lim.max_rows;
-  // band height: the largest bh <= BH_MAX for which the score tile + corner bitmap + 2 KB per warp stay below a quarter
-  // of the SM's shared memory (leaves L1 for the scorer, see the kernel), then evened out over the bands; very wide
-  // images fall back to BH_MAX and one CTA's limit
-  const size_t per_row = (size_t) score_pitch(cols) + (size_t) bits_pitch(cols) * 4, fixed = (size_t) n_strips * QCAP * 2;
-  const size_t budget = (227 * 1024 - 4 * 1024) / 4;
-  int bh_max = BH_MAX;
-  if (budget > fixed + 10 * per_row) {
-    const int fit = (int) ((budget - fixed) / per_row) - 2;
-    if (fit < bh_max) bh_max = fit;
-  }
-  int n_bands = (rows + bh_max - 1) / bh_max;
-  a.bh = (rows + n_bands - 1) / n_bands;
-  // latency mode: a launch over one or two images (the per-frame adaptor) would occupy a fraction of the SMs with long
-  // serial marches; shorter bands (>= 8 rows; each band re-computes 8 halo rows) put about one CTA on every SM instead
+  // band height: every band re-marches 8 halo rows, so taller bands waste less; the grid still has to fill the GPU
+  // (4 CTAs per SM resident) several times over for the tail to stay small.  Throughput mode: ~48-row bands
+  // (PSLAM_K1_BH overrides, for tuning runs).
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+  static const int bh_env = [] {
+    const char* e = getenv("PSLAM_K1_BH");
+    return e ? atoi(e) : 0;
+  }();
+  const int bh_target = bh_env > 0 ? bh_env : 48;
+  int n_bands = (rows + bh_target - 1) / bh_target;
+  a.bh = ((rows + n_bands - 1) / n_bands + 1) & ~1;  // even: the rows by - 1 .. by + bh are processed in pairs
+  // latency mode: a launch over one or two images (the per-frame adaptor) would occupy a fraction of the SMs with long
+  // serial marches; shorter bands (>= 8 rows) put about one CTA on every SM instead
   if ((long long) n_images * n_bands < sms) {
     const int want = (sms + n_images - 1) / n_images;
-    int bh = (rows + want - 1) / want;
+    int bh = ((rows + want - 1) / want + 1) & ~1;
     if (bh < 8) bh = 8;
     if (bh < a.bh) {
       a.bh = bh;
       n_bands = (rows + bh - 1) / bh;
     }
   }
-  const size_t smem = (size_t) (a.bh + 2) * per_row + fixed;
+  const size_t smem = (size_t) n_strips * WARP_SMEM;
   if (smem > ctx->k1_smem_set) {
     PSLAM_CUDA_TRY(ctx, cudaFuncSetAttribute(fast_blur_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     ctx->k1_smem_set = smem;
@@ -737,7 +788,7 @@ int pslam_k_bin_select(pslam_ctx* ctx, int n_images, int rows, int cols, int nh,
   dim3 grid(nh * nv, n_images);
   const int sort_cap = ctx->lim.max_raw_per_bin < 2048 ? ctx->lim.max_raw_per_bin : 2048;
   bin_select_kernel<<<grid, SEL_THREADS, (size_t) sort_cap * 6, ctx->stream>>>(
-    ctx->d_row_count, ctx->d_row_kp, ctx->map_pitch, ctx->lim.max_rows, d_mask, ctx->map_pitch, mask_invert, rows, cols, nh, nv, pr,
+    ctx->d_row_count, ctx->d_row_kp, ctx->strips_cap, ctx->lim.max_rows, d_mask, ctx->map_pitch, mask_invert, rows, cols, nh, nv, pr,
     pc, ctx->d_raw, ctx->lim.max_raw_per_bin, ctx->lim.max_bins, ctx->d_raw_count, ctx->d_sel_count, quota, sort_cap,
     ctx->d_flags, ctx->d_sel_bounds);
   PSLAM_LAUNCH_CHECK(ctx, "bin_select_kernel");

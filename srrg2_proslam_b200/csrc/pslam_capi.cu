@@ -66,8 +66,8 @@ int validate_extract(pslam_ctx* ctx, int n_images, int rows, int cols, const psl
     return pslam_set_error(ctx, PSLAM_E_CAPACITY, "more detection regions than pslam_limits.max_bins", cudaSuccess);
   if (rows < 8 || cols < 8)
     return pslam_set_error(ctx, PSLAM_E_INVALID, "image smaller than 8x8", cudaSuccess);
-  if ((long long) rows * cols >= (1LL << 24) || cols > 4096)
-    return pslam_set_error(ctx, PSLAM_E_CAPACITY, "image larger than 2^24 pixels or wider than 4096", cudaSuccess);
+  if ((long long) rows * cols >= (1LL << 24) || cols > 4032)
+    return pslam_set_error(ctx, PSLAM_E_CAPACITY, "image larger than 2^24 pixels or wider than 4032", cudaSuccess);
   return PSLAM_OK;
 }
 
@@ -237,8 +237,9 @@ int pslam_create(int device, const pslam_limits* lim, pslam_ctx** out) {
   const size_t NI = lim->max_images, MF = ctx->lim.max_features, NP = (lim->max_images + 1) / 2;
   const size_t NW = ctx->work_images;
   PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_images, 2 * NW * ctx->img_slot));
-  PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_row_kp, NW * lim->max_rows * (size_t) ctx->map_pitch));
-  PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_row_count, NW * lim->max_rows));
+  ctx->strips_cap = pslam_k_strips_cap(lim->max_cols);
+  PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_row_kp, NW * lim->max_rows * (size_t) ctx->strips_cap * 256));
+  PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_row_count, NW * lim->max_rows * (size_t) ctx->strips_cap));
   PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_blur, NW * ctx->map_slot));
   PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_mask, ctx->map_slot));
   PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_raw, NW * lim->max_bins * (size_t) lim->max_raw_per_bin));

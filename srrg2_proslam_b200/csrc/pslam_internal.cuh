@@ -38,8 +38,9 @@ struct pslam_ctx {
   int img_pitch, map_pitch;
   size_t img_slot, map_slot;  // bytes per image slot
   uint8_t* d_images;
-  uint32_t* d_row_kp;
-  int* d_row_count;
+  uint32_t* d_row_kp;      // K1 -> K2: [work_images][max_rows][strips_cap][256] keypoints after NMS, (col << 8) | response + 1
+  int* d_row_count;        // [work_images][max_rows][strips_cap]
+  int strips_cap;          // 252-pixel strips of a max_cols wide image (k_fast.cu)
   size_t k1_smem_set;
   int* d_sel_bounds;      // K2: per region (row begin, row end, col begin, col end), valid for sel_bounds_key
   int sel_bounds_key[4];  // rows, cols, nh, nv the table was built for

@@ -13,7 +13,8 @@ int pslam_k_bin_select(pslam_ctx* ctx, int n_images, int rows, int cols, int nh,
 int pslam_k_assemble(pslam_ctx* ctx, const uint8_t* d_images, long long image_pitch, int stride,
                      int n_images, int rows, int cols, int nbins, int border, int slot_base);
 int pslam_k_describe(pslam_ctx* ctx, int n_images, int rows, int cols, int slot_base);
-int pslam_k_orb_tile_cap(int max_rows, int max_cols);  // description tiles of the largest image
+int pslam_k_orb_tile_cap(int max_rows, int max_cols);
+int pslam_k_strips_cap(int max_cols);  // K1 strips of the widest image  // description tiles of the largest image
 int pslam_k_make_blur_tmap(pslam_ctx* ctx, int work_images);
 int pslam_k_mono_depth(pslam_ctx* ctx, const void* d_depth, int depth_type, int depth_rows, int depth_cols,
                        int depth_stride, float scale, int slot, float* d_uvz, float* d_inten, uint32_t* d_desc,
