@@ -217,7 +217,7 @@ struct K1Args {
   long long map_slot;
   int* row_count;      // [images][max_rows][strips_cap]
   uint32_t* row_kp;    // [images][max_rows][strips_cap][STRIP_LIST]  (col << 8) | (response + 1)
-  int strips_cap, max_rows;
+  int strips_cap, max_rows, n_strips;
 };
 
 // Candidate queue: push this lane's candidates (mask bits 0-7 bright, 8-15 dark pixels x0..x0+7 of tile row
@@ -256,6 +256,7 @@ struct NmsOut {
   uint32_t* row_kp;  // list of (row 0, this strip); a row's lists are row_stride entries apart
   int* row_count;
   int row_stride;    // strips_cap
+  int strip;
 };
 __device__ __forceinline__ void nms_emit_pair(const uint8_t* s_score, int t, int nms, unsigned emit_mask, int col0, int row_end,
                                               const NmsOut& o) {
@@ -386,9 +387,9 @@ __device__ __noinline__ unsigned long long push_drain_nms(const uint8_t* img, ui
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int k = lane * 8 + j;
-    if ((k >= 2 || threadIdx.x < 32) && k < STRIP_STRIDE + 2) emit_mask |= 1u << j;
+    if ((k >= 2 || out.strip == 0) && k < STRIP_STRIDE + 2) emit_mask |= 1u << j;
   }
-  const int col0 = (int) (threadIdx.x >> 5) * STRIP_STRIDE + lane * 8;
+  const int col0 = out.strip * STRIP_STRIDE + lane * 8;
   const int n_pairs = final ? 3 : 1;
   for (int p = 0; p < n_pairs; ++p) {
     const int t = row_a - 5 + 2 * p;
@@ -407,9 +408,11 @@ __device__ __noinline__ unsigned long long push_drain_nms(const uint8_t* img, ui
 __global__ void __maxnreg__(96)
 fast_blur_rows_kernel(const K1Args a) {
   extern __shared__ __align__(16) uint8_t smem[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = blockIdx.z * (blockDim.x >> 5) + (tid >> 5);  // strip index (the strips of a band are independent)
   const int rows = a.rows, cols = a.cols, stride = a.stride, thr = a.thr, BH = a.bh;  // BH is even
-  uint8_t* s_score = smem + (size_t) warp * WARP_SMEM;                                   // [RING][256]
+  if (warp >= a.n_strips) return;
+  uint8_t* s_score = smem + (size_t) (tid >> 5) * WARP_SMEM;                             // [RING][256]
   unsigned short* s_queue = reinterpret_cast<unsigned short*>(s_score + RING * 256);     // [QCAP]
   unsigned* s_tail = reinterpret_cast<unsigned*>(s_score + RING * 256 + QCAP * 2);        // queue tails after the last two pushes
   const int by = blockIdx.x * BH, image = blockIdx.y;
@@ -435,6 +438,7 @@ fast_blur_rows_kernel(const K1Args a) {
   unsigned q_head = 0, q_tail = 0, pend = 0u;
   NmsOut out;
   out.row_stride = a.strips_cap;
+  out.strip = warp;
   out.row_kp = a.row_kp + ((size_t) image * a.max_rows * a.strips_cap + warp) * STRIP_LIST;
   out.row_count = a.row_count + (size_t) image * a.max_rows * a.strips_cap + warp;
 
@@ -706,6 +710,7 @@ int pslam_k_fast_blur(pslam_ctx* ctx, const uint8_t* d_images, long long image_p
   a.row_kp = ctx->d_row_kp;
   a.strips_cap = ctx->strips_cap;
   a.max_rows = ctx->lim.max_rows;
+  a.n_strips = n_strips;
   // band height: every band re-marches 8 halo rows, so taller bands waste less; the grid still has to fill the GPU
   // (4 CTAs per SM resident) several times over for the tail to stay small.  Throughput mode: ~48-row bands
   // (PSLAM_K1_BH overrides, for tuning runs).
@@ -715,7 +720,11 @@ int pslam_k_fast_blur(pslam_ctx* ctx, const uint8_t* d_images, long long image_p
     const char* e = getenv("PSLAM_K1_BH");
     return e ? atoi(e) : 0;
   }();
-  const int bh_target = bh_env > 0 ? bh_env : 48;
+  static const int wpc_env = [] {
+    const char* e = getenv("PSLAM_K1_WPC");
+    return e ? atoi(e) : 0;
+  }();
+  const int bh_target = bh_env > 0 ? bh_env : 94;
   int n_bands = (rows + bh_target - 1) / bh_target;
   a.bh = ((rows + n_bands - 1) / n_bands + 1) & ~1;  // even: the rows by - 1 .. by + bh are processed in pairs
   // latency mode: a launch over one or two images (the per-frame adaptor) would occupy a fraction of the SMs with long
@@ -729,13 +738,17 @@ int pslam_k_fast_blur(pslam_ctx* ctx, const uint8_t* d_images, long long image_p
       n_bands = (rows + bh - 1) / bh;
     }
   }
-  const size_t smem = (size_t) n_strips * WARP_SMEM;
+  // the strips of a band never synchronise: warps per CTA is a scheduling choice.  Measured at KITTI width (5 strips):
+  // 5 warps per CTA 2.04, 1 warp per CTA 2.15, 2 warps per CTA 2.49 us / image
+  int wpc = wpc_env > 0 ? wpc_env : n_strips;
+  if (wpc > n_strips) wpc = n_strips;
+  const size_t smem = (size_t) wpc * WARP_SMEM;
   if (smem > ctx->k1_smem_set) {
     PSLAM_CUDA_TRY(ctx, cudaFuncSetAttribute(fast_blur_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     ctx->k1_smem_set = smem;
   }
-  dim3 grid(n_bands, n_images);
-  fast_blur_rows_kernel<<<grid, 32 * n_strips, smem, ctx->stream>>>(a);
+  dim3 grid(n_bands, n_images, (n_strips + wpc - 1) / wpc);
+  fast_blur_rows_kernel<<<grid, 32 * wpc, smem, ctx->stream>>>(a);
   PSLAM_LAUNCH_CHECK(ctx, "fast_blur_rows_kernel");
   return PSLAM_OK;
 }
