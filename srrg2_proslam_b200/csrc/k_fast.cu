@@ -107,12 +107,13 @@ __device__ __forceinline__ int fast_score_polar(const uint8_t* __restrict__ p, i
   r[13] = __ldg(pp1 - 3);
   r[14] = __ldg(pp2 - 2);
   r[15] = __ldg(pp3 - 1);
-  // bright: d = r - c, dark: d = c - r; + 256 per half (no borrow between the halves: every half stays in 1 .. 511)
-  const unsigned kb = (bright ? 256u - c : 256u + c) * 0x00010001u;
-  const unsigned sg = bright ? 1u : 0xffffffffu;
+  // bright: d = r - c, dark: d = c - r = (255 - r) - (255 - c); + 256 per half (every half stays in 1 .. 511, no borrow
+  // between the halves).  The polarity is one XOR on the packed ring pairs instead of a multiply / negate per pair.
+  const unsigned px = bright ? 0u : 0x00ff00ffu;
+  const unsigned kb = (256u - (c ^ (px & 0xffu))) * 0x00010001u;
   unsigned d[10];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) d[k] = kb + sg * (r[k] | (r[k + 8] << 16));
+  for (int k = 0; k < 8; ++k) d[k] = kb + (__byte_perm(r[k], r[k + 8], 0x5410) ^ px);
   d[8] = swap16(d[0]);
   d[9] = swap16(d[1]);
   unsigned lo3[14];
@@ -267,31 +268,52 @@ __device__ __forceinline__ void nms_emit_pair(const uint8_t* s_score, int t, int
   const uint2 r1 = *reinterpret_cast<const uint2*>(s_score + (t & (RING - 1)) * 256 + lane * 8);
   const uint2 r2 = *reinterpret_cast<const uint2*>(s_score + ((t + 1) & (RING - 1)) * 256 + lane * 8);
   const uint2 r3 = *reinterpret_cast<const uint2*>(s_score + ((t + 2) & (RING - 1)) * 256 + lane * 8);
+  // 16-bit SIMD (VIMNMX3.U16x2 is native, byte-wide max / compare are ~7-instruction emulations): every row is split into
+  // pixel pairs E0 = (p0, p2), O0 = (p1, p3), E1 = (p4, p6), O1 = (p5, p7), one score per 16-bit half
+  unsigned rw[4][4];
+  {
+    const uint2 rr[4] = {r0, r1, r2, r3};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      rw[q][0] = rr[q].x & M16;
+      rw[q][1] = __byte_perm(rr[q].x, 0u, 0x4341);
+      rw[q][2] = rr[q].y & M16;
+      rw[q][3] = __byte_perm(rr[q].y, 0u, 0x4341);
+    }
+  }
   unsigned bits[2];
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
-    const uint2 u = h ? r1 : r0, c = h ? r2 : r1, d = h ? r3 : r2;
-    unsigned keep_lo, keep_hi;
+    unsigned t[4];
     if (nms) {
-      const unsigned v_lo = __vmaxu4(u.x, d.x), v_hi = __vmaxu4(u.y, d.y);       // rows above / below, same column
-      const unsigned a_lo = __vmaxu4(v_lo, c.x), a_hi = __vmaxu4(v_hi, c.y);     // all three rows
-      unsigned left = __shfl_up_sync(FULL, a_hi, 1), right = __shfl_down_sync(FULL, a_lo, 1);
-      if (lane == 0) left = 0u;    // strip column -1 / 256: never next to an emitted column
-      if (lane == 31) right = 0u;
-      // byte j of l_* = column j - 1, of r_* = column j + 1 (of the 3-row maxima)
-      const unsigned l_lo = __funnelshift_l(left, a_lo, 8), l_hi = __funnelshift_l(a_lo, a_hi, 8);
-      const unsigned r_lo = __funnelshift_r(a_lo, a_hi, 8), r_hi = __funnelshift_r(a_hi, right, 8);
       // response s - 1 strictly greater than every neighbour's (0 for non-corners): s > max(neighbours, 1)
-      const unsigned m_lo = __vmaxu4(__vmaxu4(__vmaxu4(l_lo, r_lo), v_lo), 0x01010101u);
-      const unsigned m_hi = __vmaxu4(__vmaxu4(__vmaxu4(l_hi, r_hi), v_hi), 0x01010101u);
-      keep_lo = __vcmpgtu4(c.x, m_lo);
-      keep_hi = __vcmpgtu4(c.y, m_hi);
+      unsigned v[4], a[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        v[k] = __vimax3_u16x2(rw[h][k], rw[h + 2][k], 0x00010001u);  // rows above / below, same column (and the floor 1)
+        a[k] = __vmaxu2(v[k], rw[h + 1][k]);                         // all three rows
+      }
+      unsigned prev = __shfl_up_sync(FULL, a[3], 1), next = __shfl_down_sync(FULL, a[0], 1);
+      if (lane == 0) prev = 0u;   // strip column -1 / 256: never next to an emitted column
+      if (lane == 31) next = 0u;
+      // left / right neighbour columns of the 3-row maxima, per pixel pair
+      const unsigned l_e0 = __byte_perm(prev, a[1], 0x5432) /*(p-1, p1)*/, r_e0 = a[1] /*(p1, p3)*/;
+      const unsigned l_o0 = a[0] /*(p0, p2)*/, r_o0 = __byte_perm(a[0], a[2], 0x5432) /*(p2, p4)*/;
+      const unsigned l_e1 = __byte_perm(a[1], a[3], 0x5432) /*(p3, p5)*/, r_e1 = a[3] /*(p5, p7)*/;
+      const unsigned l_o1 = a[2] /*(p4, p6)*/, r_o1 = __byte_perm(a[2], next, 0x5432) /*(p6, p8)*/;
+      // bit 15 of a half: neighbour maximum >= centre (halves stay in 0x7f01 .. 0x80ff: no borrow across)
+      t[0] = __vimax3_u16x2(l_e0, r_e0, v[0]) + 0x80008000u - rw[h + 1][0];
+      t[1] = __vimax3_u16x2(l_o0, r_o0, v[1]) + 0x80008000u - rw[h + 1][1];
+      t[2] = __vimax3_u16x2(l_e1, r_e1, v[2]) + 0x80008000u - rw[h + 1][2];
+      t[3] = __vimax3_u16x2(l_o1, r_o1, v[3]) + 0x80008000u - rw[h + 1][3];
     } else {
-      keep_lo = __vcmpgtu4(c.x, 0u);
-      keep_hi = __vcmpgtu4(c.y, 0u);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) t[k] = 0x80008000u - rw[h + 1][k];  // bit 15: not a corner
     }
-    // 0xff / 0x00 per byte -> one bit per pixel
-    bits[h] = ((((keep_lo & 0x01010101u) * 0x01020408u) >> 24) | ((((keep_hi & 0x01010101u) * 0x01020408u) >> 24) << 4)) & emit_mask;
+    // bit 15 -> pixel (0|1|4|5), bit 31 -> pixel (2|3|6|7)
+    const unsigned w = ((t[0] >> 15) & 0x00010001u) | ((t[1] >> 14) & 0x00020002u) | ((t[2] >> 11) & 0x00100010u) |
+                       ((t[3] >> 10) & 0x00200020u);
+    bits[h] = ~(w | (w >> 14)) & emit_mask;  // emit_mask has bits 0-7 only
   }
   // one prefix scan for both rows (counts packed in 16-bit halves)
   const int cnt = __popc(bits[0]) | (__popc(bits[1]) << 16);
