@@ -64,21 +64,56 @@ __host__ __device__ inline int k1_strips(int cols) { return cols <= 256 ? 1 : (c
 struct RawQ {
   uint2 q, e0, e1;
 };
-__device__ __forceinline__ RawQ loadq_issue(const uint8_t* __restrict__ row, int xw, int lane, bool has_left, int cols) {
-  const uint8_t* a = row + xw;
-  const uint8_t* c = a - ((uintptr_t) a & 7u);
+// per-lane byte offsets of the chunks relative to (the strip's first aligned chunk - 8): constant over the march
+struct LaneOffs {
+  unsigned q, e0, e1;
+  bool p_e0, p_e1;
+};
+__device__ __forceinline__ LaneOffs lane_offs(int lane, bool has_left) {
+  LaneOffs o;
+  o.q = 8u + 8u * (unsigned) lane;
+  o.e0 = lane == 31 ? 8u + 256u : 0u;  // lane 0: the chunk before its own; lane 31: the chunk after
+  o.e1 = 8u + 264u;
+  o.p_e0 = (lane == 0 && has_left) || lane == 31;
+  o.p_e1 = lane == 31;
+  return o;
+}
+__device__ __forceinline__ RawQ loadq_issue(const uint8_t* __restrict__ row, int xs, const LaneOffs& lo, int cols) {
+  // uniform over the warp: the aligned chunk that holds the strip's first pixel (minus one chunk) and the offset of the
+  // chunk that holds the row's last pixel
+  const uint8_t* a = row + xs;
+  const uint8_t* base = a - ((uintptr_t) a & 7u) - 8;
   const uint8_t* last = row + (cols - 1);
   last -= (uintptr_t) last & 7u;
+  const unsigned last_off = (unsigned) (last - base);
   RawQ r;
   r.e0 = r.e1 = make_uint2(0u, 0u);
-  const uint8_t* cc = c < last ? c : last;
-  r.q = __ldg(reinterpret_cast<const uint2*>(cc));
-  if (lane == 0 && has_left) r.e0 = __ldg(reinterpret_cast<const uint2*>(cc - 8));
-  if (lane == 31) {
-    r.e0 = __ldg(reinterpret_cast<const uint2*>(c + 8 < last ? c + 8 : last));
-    r.e1 = __ldg(reinterpret_cast<const uint2*>(c + 16 < last ? c + 16 : last));
-  }
+  r.q = __ldg(reinterpret_cast<const uint2*>(base + min(lo.q, last_off)));
+  if (lo.p_e0) r.e0 = __ldg(reinterpret_cast<const uint2*>(base + min(lo.e0, last_off)));
+  if (lo.p_e1) r.e1 = __ldg(reinterpret_cast<const uint2*>(base + min(lo.e1, last_off)));
   return r;
+}
+// the 16-pixel window of a lane (4 px left halo | 8 own | 4 px right halo) from the chunks; d = address of the strip's first
+// pixel & 7 (uniform)
+struct RowRegs {
+  unsigned hl, a0, a1, hr;  // pixels x0-4..x0-1 | x0..x0+3 | x0+4..x0+7 | x0+8..x0+11
+};
+__device__ __forceinline__ RowRegs assemble_row(const RawQ& nx, unsigned d, int lane) {
+  const bool hi = d >= 4u;
+  const unsigned sh = (d & 3u) * 8u;
+  uint2 qn;
+  qn.x = __shfl_down_sync(FULL, nx.q.x, 1);
+  qn.y = __shfl_down_sync(FULL, nx.q.y, 1);
+  if (lane == 31) qn = nx.e0;
+  const unsigned w0 = hi ? nx.q.y : nx.q.x, w1 = hi ? qn.x : nx.q.y, w2 = hi ? qn.y : qn.x;
+  RowRegs cur;
+  cur.a0 = __funnelshift_r(w0, w1, sh);
+  cur.a1 = __funnelshift_r(w1, w2, sh);
+  cur.hl = __shfl_up_sync(FULL, cur.a1, 1);
+  cur.hr = __shfl_down_sync(FULL, cur.a0, 1);
+  if (lane == 0) cur.hl = hi ? __funnelshift_r(nx.q.x, nx.q.y, sh) : __funnelshift_r(nx.e0.y, nx.q.x, sh);
+  if (lane == 31) cur.hr = hi ? __funnelshift_r(nx.e0.y, nx.e1.x, sh) : __funnelshift_r(nx.e0.x, nx.e0.y, sh);
+  return cur;
 }
 
 // ---- FAST score of one candidate, one polarity (bright: ring brighter than the centre) ---------------------
@@ -131,12 +166,8 @@ __device__ __forceinline__ int fast_score_polar(const uint8_t* __restrict__ p, i
   return (int) max(m & 0xffffu, m >> 16) - 256;
 }
 
-struct RowRegs {
-  unsigned hl, a0, a1, hr;  // pixels x0-4..x0-1 | x0..x0+3 | x0+4..x0+7 | x0+8..x0+11
-};
-
-// horizontal 7-tap of the 8 own pixels -> 4 words of packed u16 pairs
-__device__ __forceinline__ void hblur8(const RowRegs& r, unsigned h[4]) {
+// horizontal 7-tap of the 8 own pixels -> 8 sums (<= 257 * 255 = 65535 each)
+__device__ __forceinline__ void hblur8(const RowRegs& r, unsigned h[8]) {
   const unsigned KA = 18u | (34u << 8) | (49u << 16) | (55u << 24);  // taps -3..0
   const unsigned KB = 49u | (34u << 8) | (18u << 16);                // taps +1..+3
   // byte quads of the 16-byte window at offsets 1..12 (offset o = pixel x0 - 4 + o)
@@ -146,35 +177,41 @@ __device__ __forceinline__ void hblur8(const RowRegs& r, unsigned h[4]) {
                  q7 = __byte_perm(r.a0, r.a1, 0x6543), q8 = r.a1;
   const unsigned q9 = __byte_perm(r.a1, r.hr, 0x4321), q10 = __byte_perm(r.a1, r.hr, 0x5432),
                  q11 = __byte_perm(r.a1, r.hr, 0x6543), q12 = r.hr;
-  const unsigned h0 = __dp4a(q1, KA, __dp4a(q5, KB, 0u)), h1 = __dp4a(q2, KA, __dp4a(q6, KB, 0u));
-  const unsigned h2 = __dp4a(q3, KA, __dp4a(q7, KB, 0u)), h3 = __dp4a(q4, KA, __dp4a(q8, KB, 0u));
-  const unsigned h4 = __dp4a(q5, KA, __dp4a(q9, KB, 0u)), h5 = __dp4a(q6, KA, __dp4a(q10, KB, 0u));
-  const unsigned h6 = __dp4a(q7, KA, __dp4a(q11, KB, 0u)), h7 = __dp4a(q8, KA, __dp4a(q12, KB, 0u));
-  h[0] = h0 | (h1 << 16);  // <= 257 * 255 = 65535 each
-  h[1] = h2 | (h3 << 16);
-  h[2] = h4 | (h5 << 16);
-  h[3] = h6 | (h7 << 16);
+  h[0] = __dp4a(q1, KA, __dp4a(q5, KB, 0u));
+  h[1] = __dp4a(q2, KA, __dp4a(q6, KB, 0u));
+  h[2] = __dp4a(q3, KA, __dp4a(q7, KB, 0u));
+  h[3] = __dp4a(q4, KA, __dp4a(q8, KB, 0u));
+  h[4] = __dp4a(q5, KA, __dp4a(q9, KB, 0u));
+  h[5] = __dp4a(q6, KA, __dp4a(q10, KB, 0u));
+  h[6] = __dp4a(q7, KA, __dp4a(q11, KB, 0u));
+  h[7] = __dp4a(q8, KA, __dp4a(q12, KB, 0u));
 }
 
-// vertical 7-tap over the window (rows r-6 .. r as hm6 .. h0) for one packed pair -> two output bytes in bits 0-7 / 8-15
-__device__ __forceinline__ unsigned vblur_pair(unsigned hm6, unsigned hm5, unsigned hm4, unsigned hm3, unsigned hm2,
-                                               unsigned hm1, unsigned h0) {
-  const unsigned T18 = 18u | (18u << 24), T34 = 34u | (34u << 24), T49 = 49u | (49u << 24), T55 = 55u | (55u << 24);
-  unsigned lo = 32768u, hi = 32768u;
-  lo = __dp2a_lo(hm6, T18, lo); hi = __dp2a_hi(hm6, T18, hi);
-  lo = __dp2a_lo(hm5, T34, lo); hi = __dp2a_hi(hm5, T34, hi);
-  lo = __dp2a_lo(hm4, T49, lo); hi = __dp2a_hi(hm4, T49, hi);
-  lo = __dp2a_lo(hm3, T55, lo); hi = __dp2a_hi(hm3, T55, hi);
-  lo = __dp2a_lo(hm2, T49, lo); hi = __dp2a_hi(hm2, T49, hi);
-  lo = __dp2a_lo(hm1, T34, lo); hi = __dp2a_hi(hm1, T34, hi);
-  lo = __dp2a_lo(h0, T18, lo);  hi = __dp2a_hi(h0, T18, hi);
-  lo = min(lo, 0x00ffffffu);
-  hi = min(hi, 0x00ffffffu);
-  return __byte_perm(lo, hi, 0x0062);  // (lo >> 16) | ((hi >> 16) << 8)
+// vertical 7-tap on ROW-PAIR packed words: p_k = h(row 2k, x) | h(row 2k + 1, x) << 16 for the four row pairs of the 8-row
+// window (rows w .. w + 7).  One dp2a = two taps: 4 instead of 7 multiply-accumulates per output pixel.
+//   first  output row (centre w + 3, rows w .. w + 6):     taps (18,34) (49,55) (49,34) (18, 0)  = the low bytes of T0..T3
+//   second output row (centre w + 4, rows w + 1 .. w + 7): taps ( 0,18) (34,49) (55,49) (34,18)  = the high bytes
+// exact: the sum is <= 257 * 65535 + 2^15 < 2^25; (v + 2^15) >> 16, saturated to 255 (byte 2 after min with 0xffffff)
+__device__ __forceinline__ void vblur_pairs(unsigned p0, unsigned p1, unsigned p2, unsigned p3, unsigned& first, unsigned& second) {
+  const unsigned T0 = 18u | (34u << 8) | (0u << 16) | (18u << 24), T1 = 49u | (55u << 8) | (34u << 16) | (49u << 24);
+  const unsigned T2 = 49u | (34u << 8) | (55u << 16) | (49u << 24), T3 = 18u | (0u << 8) | (34u << 16) | (18u << 24);
+  unsigned f = __dp2a_lo(p0, T0, 32768u), g = __dp2a_hi(p0, T0, 32768u);
+  f = __dp2a_lo(p1, T1, f); g = __dp2a_hi(p1, T1, g);
+  f = __dp2a_lo(p2, T2, f); g = __dp2a_hi(p2, T2, g);
+  f = __dp2a_lo(p3, T3, f); g = __dp2a_hi(p3, T3, g);
+  first = min(f, 0x00ffffffu);
+  second = min(g, 0x00ffffffu);
+}
+// bytes 2 of four sums -> one word of four output pixels
+__device__ __forceinline__ unsigned pack_b2(unsigned v0, unsigned v1, unsigned v2, unsigned v3) {
+  return __byte_perm(__byte_perm(v0, v1, 0x0062), __byte_perm(v2, v3, 0x0062), 0x5410);
 }
 
 // compass pre-test for the 8 own pixels of the centre row; returns 8-bit masks (bit j = pixel x0 + j)
-__device__ __forceinline__ void pretest8(const RowRegs& n, const RowRegs& c, const RowRegs& s, unsigned t1,
+struct RowOwn {
+  unsigned a0, a1;  // pixels x0..x0+3 | x0+4..x0+7
+};
+__device__ __forceinline__ void pretest8(const RowOwn& n, const RowRegs& c, const RowOwn& s, unsigned t1,
                                          unsigned& m_bright, unsigned& m_dark) {
   // centre pairs: E0 = (p0,p2) O0 = (p1,p3) E1 = (p4,p6) O1 = (p5,p7)
   const unsigned cE0 = c.a0 & M16, cO0 = __byte_perm(c.a0, 0u, 0x4341), cE1 = c.a1 & M16, cO1 = __byte_perm(c.a1, 0u, 0x4341);
@@ -457,87 +494,107 @@ fast_blur_rows_kernel(const K1Args a) {
   colmask |= colmask << 8;  // bright bits 0-7, dark bits 8-15
   const unsigned t1 = (unsigned) (thr + 1) * 0x00010001u;
   const bool store_lo = x0 < a.map_pitch, store_hi = x0 + 4 < a.map_pitch;
-  unsigned q_head = 0, q_tail = 0, pend = 0u;
+  unsigned q_head = 0, q_tail = 0;
   NmsOut out;
   out.row_stride = a.strips_cap;
   out.strip = warp;
   out.row_kp = a.row_kp + ((size_t) image * a.max_rows * a.strips_cap + warp) * STRIP_LIST;
   out.row_count = a.row_count + (size_t) image * a.max_rows * a.strips_cap + warp;
 
-  RowRegs R[7];
-  unsigned H[7][4];
+  // Register windows.  Raw rows (8: w0 .. w7 = image rows r - 6 .. r + 1): the compass pre-test of centre row c reads the
+  // own pixels of rows c - 3 / c + 3 and the full 16-pixel window of row c, so the three oldest rows keep their own
+  // pixels only.  Horizontally filtered rows: four ROW PAIRS P0 .. P3, word x = h(first row, x) | h(second row, x) << 16.
+  RowOwn w0, w1, w2;
+  RowRegs w3, w4, w5;
+  w0.a0 = w0.a1 = w1.a0 = w1.a1 = w2.a0 = w2.a1 = 0u;
+  w3.hl = w3.a0 = w3.a1 = w3.hr = 0u;
+  w4 = w3;
+  w5 = w3;
+  unsigned P0[8], P1[8], P2[8];
 #pragma unroll
-  for (int i = 0; i < 7; ++i) {
-    R[i].hl = R[i].a0 = R[i].a1 = R[i].hr = 0u;
-    H[i][0] = H[i][1] = H[i][2] = H[i][3] = 0u;
-  }
+  for (int k = 0; k < 8; ++k) P0[k] = P1[k] = P2[k] = 0u;
 
   auto row_ptr = [&](int r) {
     const int yy = r < 0 ? 0 : (r >= rows ? rows - 1 : r);
     return img + (size_t) yy * stride;
   };
-  // software pipeline: the loads of the next row are issued one marching step ahead
-  RawQ nx = loadq_issue(row_ptr(by - 4), x0, lane, has_left, cols);
+  const LaneOffs lo = lane_offs(lane, has_left);
+  // software pipeline: the loads of the next row pair are issued one iteration ahead
+  RawQ nxa = loadq_issue(row_ptr(by - 4), xs, lo, cols);
+  RawQ nxb = loadq_issue(row_ptr(by - 3), xs, lo, cols);
 
-  // one marching step per iteration: image row r enters the window at slot 6 (slot k holds row r - 6 + k).
-  // The window is rotated with register moves instead of unrolling the loop 7x: the unrolled kernel (57 KB of
-  // SASS) stalled on instruction fetch (ncu stall_no_instruction), 48 extra MOVs per row are cheaper.
-  const int n_steps = BH + 8;
+  // One iteration per ROW PAIR: image rows r, r + 1 enter the windows, the rows c0 = r - 3 and c1 = r - 2 get their blur
+  // output and their pre-test -- (c0, c1) = (by - 1 + 2j, by + 2j) is one (A, A + 1) pair of push_drain_nms.  The windows
+  // are rotated with register moves once per pair (half of what a row-at-a-time march pays; unrolling over the window
+  // period instead overflows the instruction cache).
+  const int n_iter = BH / 2 + 4;
 #pragma unroll 1
-  for (int step = 0; step < n_steps; ++step) {
-    const int r = by - 4 + step;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      R[k] = R[k + 1];
-      H[k][0] = H[k + 1][0];
-      H[k][1] = H[k + 1][1];
-      H[k][2] = H[k + 1][2];
-      H[k][3] = H[k + 1][3];
+  for (int it = 0; it < n_iter; ++it) {
+    const int r = by - 4 + 2 * it;
+    const unsigned da = (unsigned) (uintptr_t) (row_ptr(r) + xs) & 7u;      // uniform over the warp
+    const unsigned db = (unsigned) (uintptr_t) (row_ptr(r + 1) + xs) & 7u;
+    const RowRegs w6 = assemble_row(nxa, da, lane);
+    const RowRegs w7 = assemble_row(nxb, db, lane);
+    if (it + 1 < n_iter) {
+      nxa = loadq_issue(row_ptr(r + 2), xs, lo, cols);
+      nxb = loadq_issue(row_ptr(r + 3), xs, lo, cols);
     }
-    RowRegs& cur = R[6];
+    unsigned P3[8];
     {
-      const unsigned d = (unsigned) (uintptr_t) (row_ptr(r) + x0) & 7u;  // uniform over the warp
-      const bool hi = d >= 4u;
-      const unsigned sh = (d & 3u) * 8u;
-      uint2 qn;
-      qn.x = __shfl_down_sync(FULL, nx.q.x, 1);
-      qn.y = __shfl_down_sync(FULL, nx.q.y, 1);
-      if (lane == 31) qn = nx.e0;
-      const unsigned w0 = hi ? nx.q.y : nx.q.x, w1 = hi ? qn.x : nx.q.y, w2 = hi ? qn.y : qn.x;
-      cur.a0 = __funnelshift_r(w0, w1, sh);
-      cur.a1 = __funnelshift_r(w1, w2, sh);
-      cur.hl = __shfl_up_sync(FULL, cur.a1, 1);
-      cur.hr = __shfl_down_sync(FULL, cur.a0, 1);
-      if (lane == 0) cur.hl = hi ? __funnelshift_r(nx.q.x, nx.q.y, sh) : __funnelshift_r(nx.e0.y, nx.q.x, sh);
-      if (lane == 31) cur.hr = hi ? __funnelshift_r(nx.e0.y, nx.e1.x, sh) : __funnelshift_r(nx.e0.x, nx.e0.y, sh);
-    }
-    if (step + 1 < n_steps) nx = loadq_issue(row_ptr(r + 1), x0, lane, has_left, cols);
-    hblur8(cur, H[6]);
-    const int rc = r - 3;  // blur output row and FAST centre row
-    if (rc >= by && rc < band_end) {
-      unsigned o[4];
+      unsigned ha[8], hb[8];
+      hblur8(w6, ha);
+      hblur8(w7, hb);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) o[k] = vblur_pair(H[0][k], H[1][k], H[2][k], H[3][k], H[4][k], H[5][k], H[6][k]);
-      // x0 is a multiple of 4 (strips start every 252 pixels): two 4-byte stores
-      unsigned* bo = reinterpret_cast<unsigned*>(blur + (size_t) rc * a.map_pitch + x0);
-      if (store_lo) bo[0] = __byte_perm(o[0], o[1], 0x5410);
-      if (store_hi) bo[1] = __byte_perm(o[2], o[3], 0x5410);
+      for (int k = 0; k < 8; ++k) P3[k] = __byte_perm(ha[k], hb[k], 0x5410);
     }
-    if (rc >= by - 1) {  // rows by - 1 .. by + BH: BH + 2 rows = BH / 2 + 1 pairs (A, A + 1), A = by - 1, by + 1, ...
-      unsigned m16 = 0u;
-      if (rc >= 3 && rc < rows - 3) {
+    const int c0 = r - 3, c1 = r - 2;
+    if (c1 >= by && c0 < band_end) {
+      unsigned f[8], g[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) vblur_pairs(P0[k], P1[k], P2[k], P3[k], f[k], g[k]);
+      // x0 is a multiple of 4 (strips start every 252 pixels): two 4-byte stores per row
+      if (c0 >= by) {
+        unsigned* bo = reinterpret_cast<unsigned*>(blur + (size_t) c0 * a.map_pitch + x0);
+        if (store_lo) bo[0] = pack_b2(f[0], f[1], f[2], f[3]);
+        if (store_hi) bo[1] = pack_b2(f[4], f[5], f[6], f[7]);
+      }
+      if (c1 < band_end) {
+        unsigned* bo = reinterpret_cast<unsigned*>(blur + (size_t) c1 * a.map_pitch + x0);
+        if (store_lo) bo[0] = pack_b2(g[0], g[1], g[2], g[3]);
+        if (store_hi) bo[1] = pack_b2(g[4], g[5], g[6], g[7]);
+      }
+    }
+    if (c0 >= by - 1) {  // rows by - 1 .. by + BH: BH / 2 + 1 pairs
+      unsigned m0 = 0u, m1 = 0u;
+      if (c0 >= 3 && c0 < rows - 3) {
         unsigned mb, md;
-        pretest8(R[0], R[3], cur, t1, mb, md);
-        m16 = (mb | (md << 8)) & colmask;
+        const RowOwn s6{w6.a0, w6.a1};
+        pretest8(w0, w3, s6, t1, mb, md);
+        m0 = (mb | (md << 8)) & colmask;
       }
-      if (((rc - by) & 1) != 0) {  // first row of a pair
-        pend = m16;
-      } else {
-        const unsigned long long q = push_drain_nms(img + xs, s_score, s_queue, s_tail, stride, thr, a.nms, pend | (m16 << 16),
-                                                    rc - 1, by, band_end, out, q_head, q_tail, step + 1 == n_steps);
-        q_head = (unsigned) q;
-        q_tail = (unsigned) (q >> 32);
+      if (c1 >= 3 && c1 < rows - 3) {
+        unsigned mb, md;
+        const RowOwn s7{w7.a0, w7.a1};
+        pretest8(w1, w4, s7, t1, mb, md);
+        m1 = (mb | (md << 8)) & colmask;
       }
+      const unsigned long long q = push_drain_nms(img + xs, s_score, s_queue, s_tail, stride, thr, a.nms, m0 | (m1 << 16), c0, by,
+                                                  band_end, out, q_head, q_tail, it + 1 == n_iter);
+      q_head = (unsigned) q;
+      q_tail = (unsigned) (q >> 32);
+    }
+    // rotate the windows by one row pair
+    w0 = w2;
+    w1 = RowOwn{w3.a0, w3.a1};
+    w2 = RowOwn{w4.a0, w4.a1};
+    w3 = w5;
+    w4 = w6;
+    w5 = w7;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      P0[k] = P1[k];
+      P1[k] = P2[k];
+      P2[k] = P3[k];
     }
   }
 }
