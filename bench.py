@@ -319,7 +319,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pairs", type=int, default=10000, help="stereo pairs per GPU per step")
-    ap.add_argument("--work-images", type=int, default=768, help="pipeline chunk (images); measured: 512 -> 116.2 k / 56.4 k, 768 -> 118.7 k / 56.1 k, 2048 -> 123.0 k / 52.1 k frames/s (device / e2e)")
+    ap.add_argument("--work-images", type=int, default=768, help="pipeline chunk (images); two lanes: 384 -> 173.1 k, 768 -> 175.4 k, 1536 -> 178.7 k frames/s device-resident (one lane: 149.4 / 165.3 / 172.9 k)")
+    ap.add_argument("--lanes", type=int, default=2, choices=[1, 2], help="chunk lanes of the batched stage-1 calls (pslam_set_lanes)")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--e2e-pairs", type=int, default=4000, help="stereo pairs per GPU per end-to-end step (pinned host memory: 0.93 MB each)")
     ap.add_argument("--cpu-pairs", type=int, default=0, help="cpu_baseline sample (0 = auto, ~10-30 s)")
@@ -367,6 +368,7 @@ def main():
     mcfg = capi.match_cfg(**MATCH)
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
 
+    ctx.set_lanes(args.lanes)
     def step_dev():
         ctx.stereo_frontend_batch_dev(images.data_ptr(), P, ROWS, COLS, COLS, img_bytes, ecfg, mcfg)
 
@@ -396,12 +398,25 @@ def main():
     barrier()
     gpu_launches = ctx.launches - launches0
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    prof = ctx.profile_read()
+    prof_timed = ctx.profile_read()
     ctx.profile_enable(False)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
     value = world * P * args.steps / (ms_total * 1e-3)
+    # Per-kernel durations.  In the timed region the chunks of a batch alternate over two streams ("lanes"), so an event
+    # interval there is the time a kernel SHARED the GPU with the other lane's kernels.  The roofline wants the kernel alone:
+    # one more pass over the same batch right after the timed region, same kernels and launch shapes, one lane.
+    ctx.set_lanes(1)
+    step_dev()
+    ctx.profile_enable(True)
+    barrier()
+    iso_steps = min(args.steps, 2)
+    for _ in range(iso_steps):
+        step_dev()
+    prof = ctx.profile_read()
+    ctx.profile_enable(False)
+    ctx.set_lanes(args.lanes)
 
     # ---- end-to-end leg: pinned host images in, packed stereo clouds out -------------------------
     # E pairs per step (bounded so that 8 ranks do not pin 75 GB of host memory); same images, same call chain
@@ -501,6 +516,8 @@ def main():
     }
     kernels = {}
     tot_kernel_ms = sum(v[0] for v in prof.values()) or 1.0
+    n_img_timed = n_img
+    n_img = n_img * iso_steps // args.steps  # images of the one-lane pass the per-kernel times come from
     for name, (kms, cnt) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
         units = n_img if name != "epipolar_kernel" else n_img / 2
         a = alg.get(name)
@@ -555,6 +572,13 @@ def main():
                     "per_rank": [{"rank": i, "e2e_s": r_[0], "frames_per_s": E * args.steps / r_[0] if r_[0] > 0 else None,
                                   "h2d_probe_gbs": r_[1], "pci_bus_id": int(r_[2])} for i, r_ in enumerate(per_rank)]},
             "gpu_launches": int(gpu_launches), "roofline": roofline, "kernels": kernels,
+            "kernels_note": f"per-kernel times: {iso_steps} step(s) of the same batch right after the timed region with ONE chunk lane "
+                            "(kernels strictly one after the other); in the timed region the chunks alternate over "
+                            f"{args.lanes} lane(s) and kernels of neighbouring chunks overlap",
+            "kernels_timed_region": {k_: {"stream_ms_total": v_[0], "launches": v_[1], "us_per_image": 1e3 * v_[0] / n_img_timed}
+                                     for k_, v_ in sorted(prof_timed.items(), key=lambda kv: -kv[1][0])},
+            "lanes": {"n": args.lanes, "sum_of_isolated_kernel_ms_per_step": tot_kernel_ms / iso_steps,
+                      "ms_per_step": ms_total / args.steps},
             "clocks": summarise_clocks(clk_lines),
             "mean_features_per_image": mean_feat, "mean_stereo_points_per_frame": float(counts.mean())}
 

@@ -77,9 +77,16 @@ const char* pslam_last_error(const pslam_ctx* ctx);
 const char* pslam_version(void);
 /* number of kernels this context has launched since creation (bench.py's gpu_launches) */
 long long pslam_launch_count(const pslam_ctx* ctx);
-/* the CUDA stream all of this context's kernels run on (cudaStream_t as void*) */
+/* the context's main CUDA stream (cudaStream_t as void*): every entry point is ordered on it -- batched stage-1 calls
+ * fan their chunks out over two internal streams ("lanes", see pslam_set_lanes) and join them back before they return */
 void* pslam_stream(const pslam_ctx* ctx);
 int pslam_synchronize(pslam_ctx* ctx);
+/* Chunk lanes of the batched stage-1 entry points (pslam_extract_binned_batch_dev, pslam_stereo_frontend_batch[_dev]):
+ * with 2 lanes (default) chunk i + 1's detection kernel overlaps chunk i's selection / description / matching kernels on a
+ * second stream with its own chunk-level intermediates (allocated by the first batch that spans more than one chunk);
+ * with 1 lane the kernels of a batch run strictly one after the other (per-kernel timing, debugging).  Results are
+ * identical.  The environment variable PSLAM_LANES sets the initial value. */
+int pslam_set_lanes(pslam_ctx* ctx, int n_lanes);
 
 /* Per-kernel device timing for bench.py's roofline line (the reference's counterpart is srrg2_core's
  * Profiler / PROFILE_TIME scopes, e.g. .../feature_extractors/intensity_feature_extractor_binned.cpp:119,140,165).

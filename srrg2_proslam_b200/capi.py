@@ -215,6 +215,10 @@ class Context:
     def synchronize(self):
         self._chk(lib().pslam_synchronize(self._h))
 
+    def set_lanes(self, n):
+        """1 = the chunks of a batch run one after the other on one stream, 2 = alternate over two streams (default)"""
+        self._chk(lib().pslam_set_lanes(self._h, int(n)))
+
     def profile_enable(self, on=True):
         self._chk(lib().pslam_profile_enable(self._h, int(bool(on))))
 

@@ -15,24 +15,78 @@ void pslam_prof_mark(pslam_ctx* ctx, const char* name) {
     const int cap = ctx->prof_cap ? 2 * ctx->prof_cap : 1024;
     cudaEvent_t* ev = (cudaEvent_t*) realloc(ctx->prof_ev, sizeof(cudaEvent_t) * cap);
     const char** nm = (const char**) realloc(ctx->prof_name, sizeof(char*) * cap);
-    if (!ev || !nm) {
+    int* ln = (int*) realloc(ctx->prof_lane, sizeof(int) * cap);
+    if (!ev || !nm || !ln) {
       if (ev) ctx->prof_ev = ev;
       if (nm) ctx->prof_name = nm;
+      if (ln) ctx->prof_lane = ln;
       return;
     }
     ctx->prof_ev = ev;
     ctx->prof_name = nm;
+    ctx->prof_lane = ln;
     for (int i = ctx->prof_cap; i < cap; ++i) cudaEventCreate(&ctx->prof_ev[i]);
     ctx->prof_cap = cap;
   }
   cudaEventRecord(ctx->prof_ev[ctx->prof_n], ctx->stream);
   ctx->prof_name[ctx->prof_n] = name;
+  ctx->prof_lane[ctx->prof_n] = ctx->cur_lane;
   ctx->prof_n++;
 }
 
 namespace {
 
 int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+template <typename T>
+cudaError_t dmalloc_t(T** p, size_t n) { return cudaMalloc((void**) p, n * sizeof(T)); }
+
+// chunk-level intermediates + stream of lane `i` (lane 0: pslam_create; lane 1: the first multi-chunk batch)
+int alloc_lane(pslam_ctx* ctx, int i) {
+  pslam_lane& L = ctx->lane[i];
+  const size_t NW = ctx->work_images;
+  const pslam_limits& lim = ctx->lim;
+  PSLAM_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+  PSLAM_CUDA_TRY(ctx, cudaEventCreateWithFlags(&L.ev_done, cudaEventDisableTiming));
+  PSLAM_CUDA_TRY(ctx, dmalloc_t(&L.d_row_kp, NW * lim.max_rows * (size_t) ctx->strips_cap * 256));
+  PSLAM_CUDA_TRY(ctx, dmalloc_t(&L.d_row_count, NW * lim.max_rows * (size_t) ctx->strips_cap));
+  PSLAM_CUDA_TRY(ctx, dmalloc_t(&L.d_blur, NW * ctx->map_slot));
+  PSLAM_CUDA_TRY(ctx, dmalloc_t(&L.d_raw, NW * lim.max_bins * (size_t) lim.max_raw_per_bin));
+  PSLAM_CUDA_TRY(ctx, dmalloc_t(&L.d_raw_count, NW * lim.max_bins));
+  PSLAM_CUDA_TRY(ctx, dmalloc_t(&L.d_sel_count, NW * lim.max_bins));
+  const int back = ctx->cur_lane;
+  if (i + 1 > ctx->n_lanes) ctx->n_lanes = i + 1;
+  pslam_use_lane(ctx, i);
+  const int rc = pslam_k_make_blur_tmap(ctx, (int) NW);  // encodes ctx->d_blur into ctx->blur_tmap
+  L.blur_tmap = ctx->blur_tmap;
+  pslam_use_lane(ctx, back);
+  return rc;
+}
+
+// A batch that spans several chunks alternates them between the two lanes; the guard joins lane 1 back into lane 0 (the
+// context's main stream) and makes lane 0 the active one again on every exit path.
+struct LaneScope {
+  pslam_ctx* ctx;
+  bool multi;
+  LaneScope(pslam_ctx* c, int n_images) : ctx(c), multi(false) {
+    if (n_images <= c->work_images || c->lanes_wanted < 2 || (c->work_images & 1)) return;
+    if (c->n_lanes < 2 && alloc_lane(c, 1) != PSLAM_OK) return;  // out of memory: stay on one lane
+    // lane 1 starts after everything already queued on the main stream
+    if (cudaEventRecord(c->lane[0].ev_done, c->lane[0].stream) != cudaSuccess ||
+        cudaStreamWaitEvent(c->lane[1].stream, c->lane[0].ev_done, 0) != cudaSuccess)
+      return;
+    multi = true;
+  }
+  void use(int chunk) {
+    if (multi) pslam_use_lane(ctx, chunk & 1);
+  }
+  ~LaneScope() {
+    if (!multi) return;
+    cudaEventRecord(ctx->lane[1].ev_done, ctx->lane[1].stream);
+    pslam_use_lane(ctx, 0);
+    cudaStreamWaitEvent(ctx->lane[0].stream, ctx->lane[1].ev_done, 0);
+  }
+};
 
 template <typename T>
 cudaError_t dmalloc(T** p, size_t n) {
@@ -111,8 +165,11 @@ int run_extract(pslam_ctx* ctx, const uint8_t* d_images, long long image_pitch, 
   ctx->rows = rows;
   ctx->cols = cols;
   ctx->n_images = n_images;
-  for (int base = 0; base < n_images; base += ctx->work_images) {
+  LaneScope lanes(ctx, n_images);
+  int chunk = 0;
+  for (int base = 0; base < n_images; base += ctx->work_images, ++chunk) {
     const int n = n_images - base < ctx->work_images ? n_images - base : ctx->work_images;
+    lanes.use(chunk);
     int rc = run_extract_chunk(ctx, d_images + (size_t) base * image_pitch, image_pitch, n, rows, cols, stride, cfg, d_mask, base);
     if (rc) return rc;
     if (mcfg && n / 2 > 0 && (rc = pslam_k_epipolar(ctx, n / 2, mcfg, 0, base / 2))) return rc;
@@ -131,10 +188,12 @@ int run_extract_host(pslam_ctx* ctx, const uint8_t* h_images, long long image_pi
   // the staging buffers may still be read by kernels of an earlier call: order the uploads after them
   PSLAM_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_free[0], ctx->stream));
   PSLAM_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[0], 0));
+  LaneScope lanes(ctx, n_images);
   int chunk = 0;
   for (int base = 0; base < n_images; base += ctx->work_images, ++chunk) {
     const int n = n_images - base < ctx->work_images ? n_images - base : ctx->work_images;
     const int buf = chunk & 1;
+    lanes.use(chunk);
     uint8_t* stage = ctx->d_images + buf * half;
     if (chunk >= 2) PSLAM_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[buf], 0));
     const uint8_t* src = h_images + (size_t) base * image_pitch;
@@ -221,8 +280,11 @@ int pslam_create(int device, const pslam_limits* lim, pslam_ctx** out) {
   ctx->lim.max_features = (lim->max_features + 7) & ~7;
   *out = ctx;  // returned even on failure so that pslam_last_error is readable; caller destroys
   PSLAM_CUDA_TRY(ctx, cudaSetDevice(device));
-  PSLAM_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   PSLAM_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  {
+    const char* e = getenv("PSLAM_LANES");  // 1 = chunks strictly one after the other on one stream (tuning / debugging)
+    ctx->lanes_wanted = e ? atoi(e) : 2;
+  }
   for (int i = 0; i < 2; ++i) {
     PSLAM_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_ready[i], cudaEventDisableTiming));
     PSLAM_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_free[i], cudaEventDisableTiming));
@@ -238,13 +300,7 @@ int pslam_create(int device, const pslam_limits* lim, pslam_ctx** out) {
   const size_t NW = ctx->work_images;
   PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_images, 2 * NW * ctx->img_slot));
   ctx->strips_cap = pslam_k_strips_cap(lim->max_cols);
-  PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_row_kp, NW * lim->max_rows * (size_t) ctx->strips_cap * 256));
-  PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_row_count, NW * lim->max_rows * (size_t) ctx->strips_cap));
-  PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_blur, NW * ctx->map_slot));
   PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_mask, ctx->map_slot));
-  PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_raw, NW * lim->max_bins * (size_t) lim->max_raw_per_bin));
-  PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_raw_count, NW * lim->max_bins));
-  PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_sel_count, NW * lim->max_bins));
   PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_xy, NI * MF));
   PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_resp, NI * MF));
   PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_inten, NI * MF));
@@ -264,8 +320,6 @@ int pslam_create(int device, const pslam_limits* lim, pslam_ctx** out) {
   PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_ep_count, NP));
   PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_flags, 4));
   PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_sel_bounds, 4 * (size_t) lim->max_bins));
-  PSLAM_CUDA_TRY(ctx, cudaMemset(ctx->d_flags, 0, 4 * sizeof(int)));
-  PSLAM_CUDA_TRY(ctx, cudaMemset(ctx->d_count, 0, NI * sizeof(int)));
   // scratch: matcher / solver temporaries, and the packed (CSR) stereo result of a whole batch
   ctx->scratch_bytes = (size_t) 64 << 20;
   const size_t pack_bytes = NP * MF * 64 + NP * 8 + (1 << 20);
@@ -273,18 +327,29 @@ int pslam_create(int device, const pslam_limits* lim, pslam_ctx** out) {
   PSLAM_CUDA_TRY(ctx, dmalloc(&ctx->d_scratch, ctx->scratch_bytes));
   ctx->pinned_bytes = 1 << 20;
   PSLAM_CUDA_TRY(ctx, cudaMallocHost(&ctx->h_pinned, ctx->pinned_bytes));
-  int rc = pslam_k_upload_pattern(ctx);
+  int rc = alloc_lane(ctx, 0);  // the main stream and the chunk-level intermediates
   if (rc) return rc;
-  if ((rc = pslam_k_make_blur_tmap(ctx, (int) NW))) return rc;
+  pslam_use_lane(ctx, 0);
+  PSLAM_CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_flags, 0, 4 * sizeof(int), ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_count, 0, NI * sizeof(int), ctx->stream));
+  if ((rc = pslam_k_upload_pattern(ctx))) return rc;
+  PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return PSLAM_OK;
 }
 
 void pslam_destroy(pslam_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  void* bufs[] = {ctx->d_images, ctx->d_row_kp, ctx->d_row_count, ctx->d_blur, ctx->d_mask, ctx->d_raw, ctx->d_raw_count,
-                  ctx->d_sel_count, ctx->d_xy, ctx->d_resp, ctx->d_inten, ctx->d_desc, ctx->d_count,
+  for (int l = 0; l < 2; ++l) {
+    pslam_lane& L = ctx->lane[l];
+    if (L.stream) cudaStreamSynchronize(L.stream);
+    void* lb[] = {L.d_row_kp, L.d_row_count, L.d_blur, L.d_raw, L.d_raw_count, L.d_sel_count};
+    for (void* b : lb)
+      if (b) cudaFree(b);
+    if (L.ev_done) cudaEventDestroy(L.ev_done);
+    if (L.stream) cudaStreamDestroy(L.stream);
+  }
+  void* bufs[] = {ctx->d_images, ctx->d_mask, ctx->d_xy, ctx->d_resp, ctx->d_inten, ctx->d_desc, ctx->d_count,
                   ctx->d_st_uvuv, ctx->d_st_left, ctx->d_st_right, ctx->d_st_dist, ctx->d_st_count,
                   ctx->d_ep_fixed, ctx->d_ep_moving, ctx->d_ep_dist, ctx->d_ep_count, ctx->d_flags,
                   ctx->d_sel_bounds, ctx->d_scratch, ctx->d_proj, ctx->d_tile_start, ctx->d_tile_order};
@@ -294,7 +359,7 @@ void pslam_destroy(pslam_ctx* ctx) {
   for (int i = 0; i < ctx->prof_cap; ++i) cudaEventDestroy(ctx->prof_ev[i]);
   free(ctx->prof_ev);
   free(ctx->prof_name);
-  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  free(ctx->prof_lane);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   for (int i = 0; i < 2; ++i) {
     if (ctx->ev_ready[i]) cudaEventDestroy(ctx->ev_ready[i]);
@@ -305,7 +370,12 @@ void pslam_destroy(pslam_ctx* ctx) {
 
 const char* pslam_last_error(const pslam_ctx* ctx) { return ctx ? ctx->err : "null context"; }
 long long pslam_launch_count(const pslam_ctx* ctx) { return ctx ? ctx->launches : 0; }
-void* pslam_stream(const pslam_ctx* ctx) { return ctx ? (void*) ctx->stream : nullptr; }
+void* pslam_stream(const pslam_ctx* ctx) { return ctx ? (void*) ctx->lane[0].stream : nullptr; }
+int pslam_set_lanes(pslam_ctx* ctx, int n_lanes) {
+  if (!ctx || n_lanes < 1 || n_lanes > 2) return PSLAM_E_INVALID;
+  ctx->lanes_wanted = n_lanes;
+  return PSLAM_OK;
+}
 int pslam_synchronize(pslam_ctx* ctx) {
   if (!ctx) return PSLAM_E_INVALID;
   PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -330,14 +400,19 @@ int pslam_profile_mark(pslam_ctx* ctx) {
 int pslam_profile_read(pslam_ctx* ctx, int capacity, char* names, int name_len, double* total_ms,
                        long long* launches) {
   if (!ctx || capacity <= 0 || !names || name_len <= 1 || !total_ms || !launches) return PSLAM_E_INVALID;
-  PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int l = 0; l < ctx->n_lanes; ++l) PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->lane[l].stream));
   int n_names = 0;
   std::vector<const char*> seen;
-  for (int i = 1; i < ctx->prof_n; ++i) {
+  int prev_of_lane[2] = {-1, -1};
+  for (int i = 0; i < ctx->prof_n; ++i) {
+    // the interval between consecutive events of the SAME lane (in-order stream) belongs to the kernel that ends it; when two
+    // lanes overlap, a kernel's interval includes the time it shared the GPU with the other lane's kernels
+    const int prev = prev_of_lane[ctx->prof_lane[i]];
+    prev_of_lane[ctx->prof_lane[i]] = i;
     const char* nm = ctx->prof_name[i];
-    if (!nm) continue;  // interval ending at a marker: host gap / copies, not a kernel
+    if (!nm || prev < 0) continue;  // interval ending at a marker: host gap / copies, not a kernel
     float ms = 0.0f;
-    if (cudaEventElapsedTime(&ms, ctx->prof_ev[i - 1], ctx->prof_ev[i]) != cudaSuccess) {
+    if (cudaEventElapsedTime(&ms, ctx->prof_ev[prev], ctx->prof_ev[i]) != cudaSuccess) {
       cudaGetLastError();
       continue;
     }

@@ -26,9 +26,26 @@
 //   features SoA [max_images][max_features]: xy float2, response f32, intensity f32, desc 8 x u32
 //   stereo   SoA [max_images/2][max_features]: uvuv float4, left/right feature index, distance
 // map_pitch and img_pitch are multiples of 128 so every row starts on a 128 B line.
+// One LANE = the chunk-level intermediates of the stage-1 pipeline plus the stream they are produced / consumed on.  A batch
+// alternates its chunks between two lanes: chunk i + 1's detection kernel (issue bound, long CTAs) runs while chunk i's
+// selection / description / matching kernels (latency / L2 bound, short CTAs) drain, so no SM idles in a kernel's tail.
+struct pslam_lane {
+  cudaStream_t stream;
+  uint32_t* d_row_kp;
+  int* d_row_count;
+  uint8_t* d_blur;
+  CUtensorMap blur_tmap;
+  uint32_t* d_raw;
+  int* d_raw_count;
+  int* d_sel_count;
+  cudaEvent_t ev_done;
+};
+
 struct pslam_ctx {
   int device;
-  cudaStream_t stream;       // all kernels
+  cudaStream_t stream;       // the ACTIVE lane's stream: every launcher enqueues here (lane 0 outside batched stage 1)
+  pslam_lane lane[2];        // lane 1 is allocated by the first batch that spans more than one chunk
+  int n_lanes, cur_lane, lanes_wanted;
   cudaStream_t copy_stream;  // host->device image uploads of the batched host entry point
   cudaEvent_t ev_ready[2], ev_free[2];  // double-buffered staging hand-shake
   int work_images;           // chunk size (images) of the stage-1 pipeline
@@ -89,8 +106,23 @@ struct pslam_ctx {
   int prof_enabled;
   cudaEvent_t* prof_ev;
   const char** prof_name;
+  int* prof_lane;
   int prof_n, prof_cap;
 };
+
+// make lane `i` the active one: its stream and chunk-level buffers become the ones the launchers see
+static inline void pslam_use_lane(pslam_ctx* ctx, int i) {
+  pslam_lane& L = ctx->lane[i];
+  ctx->cur_lane = i;
+  ctx->stream = L.stream;
+  ctx->d_row_kp = L.d_row_kp;
+  ctx->d_row_count = L.d_row_count;
+  ctx->d_blur = L.d_blur;
+  ctx->blur_tmap = L.blur_tmap;
+  ctx->d_raw = L.d_raw;
+  ctx->d_raw_count = L.d_raw_count;
+  ctx->d_sel_count = L.d_sel_count;
+}
 
 void pslam_prof_mark(pslam_ctx* ctx, const char* name);  // pslam_capi.cu
 
