@@ -224,18 +224,34 @@ __device__ __forceinline__ bool lowes_list(const unsigned* bm, int list_size, in
   return __fdiv_rn((float) d, (float) second) < ratio;
 }
 
-__global__ void __launch_bounds__(32)
-bf_sort_kernel(unsigned long long* __restrict__ cand, int n, int smem_cap) {
+// Candidate sort = the reference's unstable std::sort by response (bruteforce_impl.cpp:89-92), replayed move for move
+// (libstdcxx_sort.h): warp 0 runs the introsort partitioning with ballots, then all 1024 threads place every element at its
+// final-insertion-sort position.  Candidates that fit shared memory are sorted there, larger sets in place in global memory.
+constexpr int BS_THREADS = 1024;
+__global__ void __launch_bounds__(BS_THREADS)
+bf_sort_kernel(unsigned long long* __restrict__ cand, unsigned long long* __restrict__ sorted, unsigned* __restrict__ g_rpos, int n,
+               int smem_cap) {
   extern __shared__ __align__(16) unsigned long long s_c[];
-  const int lane = threadIdx.x;
+  __shared__ int s_end;
+  const int tid = threadIdx.x;
   if (n <= smem_cap) {
-    for (int i = lane; i < n; i += 32) s_c[i] = cand[i];
-    __syncwarp();
-    if (lane == 0) pslam_sort::std_sort(s_c, n, CandLess());
-    __syncwarp();
-    for (int i = lane; i < n; i += 32) cand[i] = s_c[i];
-  } else if (lane == 0) {
-    pslam_sort::std_sort(cand, n, CandLess());
+    unsigned short* s_rpos = reinterpret_cast<unsigned short*>(s_c + smem_cap);
+    for (int i = tid; i < n; i += BS_THREADS) s_c[i] = cand[i];
+    __syncthreads();
+    if (tid < 32) {
+      const int se = pslam_sort::warp_std_sort_prefix(s_c, s_rpos, n, n, CandLess());
+      if (tid == 0) s_end = se;
+    }
+    __syncthreads();
+    pslam_sort::block_final_positions<BS_THREADS>(s_c, s_end, n, sorted, CandLess());
+  } else {
+    if (tid < 32) {
+      const int se = pslam_sort::warp_std_sort_prefix(cand, g_rpos, n, n, CandLess());
+      if (tid == 0) s_end = se;
+    }
+    __threadfence_block();
+    __syncthreads();
+    pslam_sort::block_final_positions<BS_THREADS>(cand, s_end, n, sorted, CandLess());
   }
 }
 
@@ -431,9 +447,12 @@ int pslam_k_bf_match(pslam_ctx* ctx, int nf, const uint32_t* d_f, int nm, const 
   uint8_t* zero_end = p;
   if ((size_t) (p - ctx->d_scratch) + 4096 > ctx->scratch_bytes)
     return pslam_set_error(ctx, PSLAM_E_CAPACITY, "bf_match: scratch too small", cudaSuccess);
-  unsigned long long* cand = (unsigned long long*) p;
-  const size_t cand_cap_sz = (ctx->scratch_bytes - (size_t) (p - ctx->d_scratch)) / 8;
+  // candidates | sorted candidates | right-stopper positions of the partition replay
+  const size_t cand_cap_sz = (ctx->scratch_bytes - (size_t) (p - ctx->d_scratch) - 1024) / 20;
   const int cand_cap = cand_cap_sz > 0x7fffffff ? 0x7fffffff : (int) cand_cap_sz;
+  unsigned long long* cand = (unsigned long long*) p; p += align256(8 * (size_t) cand_cap);
+  unsigned long long* sorted = (unsigned long long*) p; p += align256(8 * (size_t) cand_cap);
+  unsigned* g_rpos = (unsigned*) p;
 
   PSLAM_CUDA_TRY(ctx, cudaMemsetAsync(bm_f, 0, (size_t) (zero_end - (uint8_t*) bm_f), ctx->stream));
   const int BF_QTILE = BF_THREADS * bf_qpt();
@@ -459,15 +478,19 @@ int pslam_k_bf_match(pslam_ctx* ctx, int nf, const uint32_t* d_f, int nm, const 
   PSLAM_LAUNCH_CHECK(ctx, "bf_sweep_kernel<1>");
   bf_bitmap_kernel<<<(n_cand + 255) / 256, 256, 0, ctx->stream>>>(cand, n_cand, bm_f, cnt_f, bm_m, cnt_m);
   PSLAM_LAUNCH_CHECK(ctx, "bf_bitmap_kernel");
+  const unsigned long long* resolve_in = cand;
   if (n_cand > 1) {
-    const int smem_cap = 24 * 1024;  // 192 KB of candidates in shared memory
-    const size_t smem = (size_t) (n_cand < smem_cap ? n_cand : smem_cap) * 8;
+    // 10 B per candidate in shared memory (8 B key + 2 B stopper position): up to 20 k candidates; larger sets in place
+    int smem_cap = n_cand <= 4096 ? 4096 : 20 * 1024;
+    if (n_cand > smem_cap) smem_cap = 0;
+    const size_t smem = (size_t) smem_cap * 10;
     if (smem > 48 * 1024)
       PSLAM_CUDA_TRY(ctx, cudaFuncSetAttribute(bf_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    bf_sort_kernel<<<1, 32, smem, ctx->stream>>>(cand, n_cand, smem_cap);
+    bf_sort_kernel<<<1, BS_THREADS, smem, ctx->stream>>>(cand, sorted, g_rpos, n_cand, smem_cap);
     PSLAM_LAUNCH_CHECK(ctx, "bf_sort_kernel");
+    resolve_in = sorted;
   }
-  bf_resolve_kernel<<<1, 1024, 0, ctx->stream>>>(cand, n_cand, bm_f, cnt_f, bm_m, cnt_m, reg_f, reg_m,
+  bf_resolve_kernel<<<1, 1024, 0, ctx->stream>>>(resolve_in, n_cand, bm_f, cnt_f, bm_m, cnt_m, reg_f, reg_m,
                                                  pool_f, pool_m, max_ratio, out_f, out_m, out_d, total);
   PSLAM_LAUNCH_CHECK(ctx, "bf_resolve_kernel");
   PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(h, total, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));

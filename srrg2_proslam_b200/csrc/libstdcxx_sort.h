@@ -214,10 +214,11 @@ PSLAM_HD void std_sort(T* a, int n, Comp comp) {
 // Control flow (introsort loop, pruning to the first `need` outputs, depth limit) is executed uniformly by the warp;
 // median-of-3 and the heap-sort fallback stay on lane 0.  tools/../tests: tests/test_gpu_stage1.py compares the
 // selected keypoints with the oracle (which calls the real std::sort) on every golden image.
-// a: shared memory, n <= 65535.  rpos: shared scratch of n uint16.  Must be called by all 32 lanes of one warp.
+// a: shared or global memory.  rpos: scratch of n indices (uint16 for n <= 65536, else uint32), same address space rules.
+// Must be called by all 32 lanes of one warp.
 // Returns sorted_end (see std_sort_prefix); the caller finishes with block_final_positions().
-template <typename T, typename Comp>
-__device__ __forceinline__ int warp_partition_(T* a, unsigned short* rpos, int first, int last, int pivot, Comp comp) {
+template <typename T, typename RP, typename Comp>
+__device__ __forceinline__ int warp_partition_(T* a, RP* rpos, int first, int last, int pivot, Comp comp) {
   const unsigned FULLM = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
@@ -227,7 +228,7 @@ __device__ __forceinline__ int warp_partition_(T* a, unsigned short* rpos, int f
     const int i = base - 1 - lane;
     const bool f = i >= first && !comp(p, a[i]);
     const unsigned bal = __ballot_sync(FULLM, f);
-    if (f) rpos[nR + __popc(bal & lt)] = (unsigned short) i;
+    if (f) rpos[nR + __popc(bal & lt)] = (RP) i;
     nR += __popc(bal);
   }
   __syncwarp();
@@ -264,8 +265,8 @@ __device__ __forceinline__ int warp_partition_(T* a, unsigned short* rpos, int f
   return lnext;
 }
 
-template <typename T, typename Comp>
-__device__ __forceinline__ int warp_std_sort_prefix(T* a, unsigned short* rpos, int n, int need, Comp comp) {
+template <typename T, typename RP, typename Comp>
+__device__ __forceinline__ int warp_std_sort_prefix(T* a, RP* rpos, int n, int need, Comp comp) {
   const int threshold = 16;
   const int lane = threadIdx.x & 31;
   if (n <= threshold) return n;

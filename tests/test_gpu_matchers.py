@@ -122,7 +122,7 @@ def test_bruteforce_collisions(ctx):
         d ^= (flip * (1 << rng.integers(0, 8, d.shape))).astype(np.uint8)
         return d
 
-    for nf, nm in ((300, 280), (1, 50), (50, 1), (1, 1), (513, 1025)):
+    for nf, nm in ((300, 280), (1, 50), (50, 1), (1, 1), (513, 1025), (1500, 1700)):  # last: > 20 k candidates, sorted in global memory
         f, m = cloud(nf), cloud(nm)
         g = ctx.match_bruteforce(f, m, capi.match_cfg(50, 0.9))
         o = O.match_bruteforce(f, m, 50, 0.9)
