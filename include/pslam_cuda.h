@@ -351,7 +351,11 @@ int pslam_bf_best2_dev(pslam_ctx* ctx, int n_fixed, const uint32_t* d_desc_fixed
  *   (.../correspondence_finders/correspondence_finder_projective_base_impl.cpp:39-102,165-208,
  *    ..._square_impl.cpp:7-118, ..._circle_impl.cpp:7-94, ..._rhombus_impl.cpp:7-93).
  * The adaptive state machine (:104-293) stays in the host wrapper.  Output is in the order the
- * reference's std::unordered_map iteration yields.  shape: 0 square, 1 circle, 2 rhombus. */
+ * reference's std::unordered_map iteration yields.  shape: 0 square, 1 circle, 2 rhombus,
+ * 3 = CorrespondenceFinderProjectiveKDTree::_findNearestNeighbors (..._kdtree_impl.cpp:28-79) as the EXACT radius query:
+ * every fixed point whose squared fp32 distance to the projection is < radius^2, best initialised to
+ * maximum_descriptor_distance, only the best candidate recorded.  The reference takes its candidates from srrg2_core's
+ * approximate KDTree (the query's leaf cluster only): the exact query returns a superset, parity for shape 3 is unpinned. */
 typedef struct {
   float K[9];
   int canvas_rows, canvas_cols;
@@ -360,6 +364,7 @@ typedef struct {
   int search_radius_pixels;
   float descriptor_distance;                   /* current (adaptive) threshold */
   float maximum_distance_ratio_to_second_best;
+  float maximum_descriptor_distance;           /* shape 3 only: PARAM maximum_descriptor_distance (bruteforce.h:23-27) */
 } pslam_projective_cfg;
 
 /* setFixed (+ _initializeDatabase, cached until the next call) / setMoving / one search.  The

@@ -214,7 +214,7 @@ static inline void triangulate_rectified(const Cloud& stereo, const float* K, fl
 //   .../correspondence_finders/correspondence_finder_projective_base_impl.cpp:39-293
 //   ..._square_impl.cpp:7-118, ..._circle_impl.cpp:7-94, ..._rhombus_impl.cpp:7-93
 // -----------------------------------------------------------------------------
-enum WindowShape { WINDOW_SQUARE = 0, WINDOW_CIRCLE = 1, WINDOW_RHOMBUS = 2 };
+enum WindowShape { WINDOW_SQUARE = 0, WINDOW_CIRCLE = 1, WINDOW_RHOMBUS = 2, WINDOW_KDTREE = 3 };
 
 struct ProjectiveFinderConfig {
   // inherited from the bruteforce base (bruteforce.h:23-37)
@@ -296,8 +296,42 @@ struct ProjectiveFinder {
               [](const LatticeElement& a, const LatticeElement& b) { return a.row < b.row; });
   }
 
+  // CorrespondenceFinderProjectiveKDTree::_findNearestNeighbors (..._kdtree_impl.cpp:28-79).  PARITY UNPINNED for this
+  // variant: the candidates come from srrg2_core's KDTree<float, 2>::findNeighbors (external, approximate: it only visits
+  // the leaf cluster of the query), in an order that tree defines.  Restated here as the EXACT radius query -- every fixed
+  // point with squared fp32 distance < radius^2 to the projection, the superset of what the tree returns -- visited in
+  // lattice order; everything after the candidate list follows the file: best initialised to maximum_descriptor_distance
+  // (the PARAM, not the adaptive threshold), strict "<" updates, ONLY the best candidate is recorded (:72-78).
+  CandidatePair findNearestNeighborsKDTree(const Feature2& query, int query_index) const {
+    CandidatePair out;
+    out.moving_idx = query_index;
+    const float maximum_distance_squared = (float) (search_radius_pixels * search_radius_pixels);  // :41-42
+    size_t index_best = 0;
+    float best = cfg.maximum_descriptor_distance;
+    float second = std::numeric_limits<float>::max();
+    for (const LatticeElement& e : database_fixed) {
+      const Feature2& f = (*fixed)[e.index];
+      const float dx = f.x - query.x, dy = f.y - query.y;
+      if (!(dx * dx + dy * dy < maximum_distance_squared)) continue;
+      const float d = hamming256(f.desc, query.desc);
+      if (d < best) {  // :61-68
+        second = best;
+        best = d;
+        index_best = e.index;
+      } else if (d < second) {
+        second = d;
+      }
+    }
+    if (best < cfg.maximum_descriptor_distance) {  // :72-78
+      out.fixed_best = (int) index_best;
+      out.dist_best = best;
+    }
+    return out;
+  }
+
   // one query against the row-sorted lattice; returns best/second with fixed indices
   CandidatePair findNearestNeighbors(const Feature2& query, int query_index) const {
+    if (cfg.shape == WINDOW_KDTREE) return findNearestNeighborsKDTree(query, query_index);
     CandidatePair out;
     out.moving_idx = query_index;
     const int16_t row = std::round(query.y);

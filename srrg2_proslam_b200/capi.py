@@ -44,7 +44,7 @@ class ProjectiveCfg(C.Structure):
     _fields_ = [("K", C.c_float * 9), ("canvas_rows", C.c_int), ("canvas_cols", C.c_int),
                 ("range_min", C.c_float), ("range_max", C.c_float), ("shape", C.c_int),
                 ("search_radius_pixels", C.c_int), ("descriptor_distance", C.c_float),
-                ("maximum_distance_ratio_to_second_best", C.c_float)]
+                ("maximum_distance_ratio_to_second_best", C.c_float), ("maximum_descriptor_distance", C.c_float)]
 
 
 class ClipCfg(C.Structure):
@@ -142,7 +142,7 @@ class FrameCfg(C.Structure):
                 ("inverse_depth_weighting", C.c_int), ("minimum_disparity_pixels", C.c_float)]
 
 
-SHAPES = {"square": 0, "circle": 1, "rhombus": 2}
+SHAPES = {"square": 0, "circle": 1, "rhombus": 2, "kdtree": 3}
 FACTORS = {"stereo": 0, "depth": 1, "mono": 2}
 ROBUST = {"none": 0, "saturated": 1, "clamp": 2}
 
@@ -508,7 +508,7 @@ class Context:
         self._chk(lib().pslam_projective_set_moving(self._h, len(xyz), _p(xyz), _p(desc)))
 
     def projective_match(self, pose12, K, rows, cols, shape="circle", radius=10, descriptor_distance=50.0,
-                         ratio=0.9, range_min=0.1, range_max=1000.0):
+                         ratio=0.9, range_min=0.1, range_max=1000.0, max_descriptor_distance=50.0):
         cfg = ProjectiveCfg()
         cfg.K[:] = [float(v) for v in np.asarray(K, np.float32).reshape(9)]
         cfg.canvas_rows, cfg.canvas_cols = int(rows), int(cols)
@@ -517,6 +517,7 @@ class Context:
         cfg.search_radius_pixels = int(radius)
         cfg.descriptor_distance = float(descriptor_distance)
         cfg.maximum_distance_ratio_to_second_best = float(ratio)
+        cfg.maximum_descriptor_distance = float(max_descriptor_distance)
         pose12 = np.ascontiguousarray(pose12, np.float32).reshape(12)
         cap = max(self._n_fixed, 1)
         fi, mi, d = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap, np.float32)

@@ -64,6 +64,7 @@ struct ProjParams {
   float R[9], t[3], K[9];
   float canvas_cols, canvas_rows, range_min, range_max;
   int shape, radius;
+  float max_desc_dist;  // shape 3
 };
 
 // cand[4*m + {0,1,2,3}] = {fixed_best, dist_best, fixed_second, dist_second}, -1 where absent.
@@ -74,7 +75,7 @@ projective_search_kernel(ProjParams pp, const float* __restrict__ moving_xyz, in
                          const uint32_t* __restrict__ desc_moving,
                          const unsigned long long* __restrict__ lattice, int n_fixed,
                          const uint32_t* __restrict__ desc_fixed, int* __restrict__ cand,
-                         int* __restrict__ n_projected) {
+                         int* __restrict__ n_projected, const float* __restrict__ fixed_coords, int fixed_dim) {
   extern __shared__ int s_width[];  // circle: width per |height| (0..radius)
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (pp.shape == 1) {
@@ -115,8 +116,14 @@ projective_search_kernel(ProjParams pp, const float* __restrict__ moving_xyz, in
   if (lane == 0 && n_projected) atomicAdd(n_projected, 1);
   const int row = (short) roundf(v), col = (short) roundf(u);  // std::round -> int16
   const int r = pp.radius;
-  const int row_min = (short) (row - r), row_max = (short) (row + r + 1);
+  int row_min = (short) (row - r), row_max = (short) (row + r + 1);
   const int col_min = (short) (col - r - 1), col_max = (short) (col + r + 1);
+  const float r2f = (float) ((size_t) r * (size_t) r);  // kdtree_impl.cpp:41-42
+  if (pp.shape == 3) {
+    // exact radius query: the lattice rows are int16(y) of the fixed points; |y - v| < r  =>  row in [floor(v - r), floor(v + r)]
+    row_min = (int) floorf(v - (float) r) - 1;
+    row_max = (int) floorf(v + (float) r) + 2;
+  }
   // first lattice position with row >= row_min
   int lo = 0, hi = n_fixed;
   while (lo < hi) {
@@ -135,7 +142,11 @@ projective_search_kernel(ProjParams pp, const float* __restrict__ moving_xyz, in
       if (erow < row_max) {
         more = true;
         bool in_window;
-        if (pp.shape == 0) {
+        if (pp.shape == 3) {
+          const int fi = (int) (e & 0xffffu);
+          const float dx = __fsub_rn(fixed_coords[(size_t) fixed_dim * fi], u), dy = __fsub_rn(fixed_coords[(size_t) fixed_dim * fi + 1], v);
+          in_window = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < r2f;
+        } else if (pp.shape == 0) {
           in_window = ecol > col_min && ecol < col_max;
         } else if (pp.shape == 1) {
           const int height = erow - row;
@@ -166,10 +177,18 @@ projective_search_kernel(ProjParams pp, const float* __restrict__ moving_xyz, in
     top2_insert(k1, k2, a2);
   }
   if (lane == 0) {
-    out[0] = (k1 != 0xffffffffu) ? (int) (lattice[k1 & 0xffffu] & 0xffffu) : -1;
-    out[1] = (int) (k1 >> 16);
-    out[2] = (k2 != 0xffffffffu) ? (int) (lattice[k2 & 0xffffu] & 0xffffu) : -1;
-    out[3] = (int) (k2 >> 16);
+    if (pp.shape == 3) {  // best must beat maximum_descriptor_distance (strict); no second candidate (kdtree_impl.cpp:55-78)
+      const bool ok = k1 != 0xffffffffu && (float) (k1 >> 16) < pp.max_desc_dist;
+      out[0] = ok ? (int) (lattice[k1 & 0xffffu] & 0xffffu) : -1;
+      out[1] = ok ? (int) (k1 >> 16) : 0;
+      out[2] = -1;
+      out[3] = 0;
+    } else {
+      out[0] = (k1 != 0xffffffffu) ? (int) (lattice[k1 & 0xffffu] & 0xffffu) : -1;
+      out[1] = (int) (k1 >> 16);
+      out[2] = (k2 != 0xffffffffu) ? (int) (lattice[k2 & 0xffffu] & 0xffffu) : -1;
+      out[3] = (int) (k2 >> 16);
+    }
   }
 }
 
@@ -292,6 +311,7 @@ int pslam_k_projective_set_fixed(pslam_ctx* ctx, int n_fixed, const float* h_coo
   int rc = proj_layout(ctx, st, n_fixed, dim, 0);
   if (rc) return rc;
   ctx->proj_fixed_epoch = ++g_proj_epoch;
+  ctx->proj_fixed_dim = dim;
   if (n_fixed == 0) return PSLAM_OK;
   if (n_fixed >= 32767)
     return pslam_set_error(ctx, PSLAM_E_INVALID, "projective: int16 lattice needs < 32767 fixed points", cudaSuccess);
@@ -337,13 +357,16 @@ int pslam_k_projective_match(pslam_ctx* ctx, int n_fixed, int n_moving, const fl
   pp.range_max = cfg->range_max;
   pp.shape = cfg->shape;
   pp.radius = cfg->search_radius_pixels;
+  pp.max_desc_dist = cfg->maximum_descriptor_distance;
+  if (pp.shape < 0 || pp.shape > 3) return pslam_set_error(ctx, PSLAM_E_INVALID, "projective: unknown window shape", cudaSuccess);
   if (pp.radius < 0 || pp.radius > 16000)
     return pslam_set_error(ctx, PSLAM_E_INVALID, "projective: bad search radius", cudaSuccess);
   const size_t smem = sizeof(int) * (size_t) (pp.radius + 1);
   if (smem > 48 * 1024)
     PSLAM_CUDA_TRY(ctx, cudaFuncSetAttribute(projective_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   projective_search_kernel<<<(n_moving + PJ_WARPS - 1) / PJ_WARPS, PJ_WARPS * 32, smem, ctx->stream>>>(
-    pp, st.d_moving, n_moving, st.d_desc_moving, st.d_lattice, n_fixed, st.d_desc_fixed, st.d_cand, nullptr);
+    pp, st.d_moving, n_moving, st.d_desc_moving, st.d_lattice, n_fixed, st.d_desc_fixed, st.d_cand, nullptr, st.d_fixed,
+    ctx->proj_fixed_dim);
   PSLAM_LAUNCH_CHECK(ctx, "projective_search_kernel");
   // one filter launch, one download (see filter_fused_kernel); the result block is transient: generic scratch
   const size_t n_words = 1 + 2 * (size_t) n_fixed + 4 * (size_t) n_moving;

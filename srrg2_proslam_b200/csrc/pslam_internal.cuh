@@ -99,6 +99,7 @@ struct pslam_ctx {
   uint8_t* d_proj;
   size_t proj_bytes;
   unsigned long long proj_fixed_epoch, proj_moving_epoch;
+  int proj_fixed_dim;  // floats per fixed point of the cached cloud
   // geometry of the last batch
   int rows, cols, n_images;
   // optional per-kernel device timing (pslam_profile_*): one CUDA event after every launch; the interval

@@ -455,6 +455,7 @@ void CorrespondenceFinderProjectiveCUDA::compute() {
   cfg.search_radius_pixels = (int) _search_radius_pixels;
   cfg.descriptor_distance = _descriptor_distance;
   cfg.maximum_distance_ratio_to_second_best = param_maximum_distance_ratio_to_second_best.value();
+  cfg.maximum_descriptor_distance = param_maximum_descriptor_distance.value();
   const int cap = (int) _fixed->size() + 1;
   std::vector<int> f(cap), m(cap);
   std::vector<float> d(cap);
@@ -1087,6 +1088,12 @@ template <int Shape>
 struct ProjectiveS : CorrespondenceFinderProjectiveCUDA {
   ProjectiveS() : CorrespondenceFinderProjectiveCUDA(Shape) {}
 };
+// correspondence_finder_projective_kdtree.h:24-28: the cluster size only shapes the reference's (approximate) tree; the
+// device search is the exact radius query (pslam_cuda.h, shape 3)
+struct ProjectiveKD : CorrespondenceFinderProjectiveCUDA {
+  ProjectiveKD() : CorrespondenceFinderProjectiveCUDA(3) {}
+  PARAM(PropertyUnsignedInt, minimum_number_of_points_per_cluster, "minimum number of points in the clusters", 10, nullptr);
+};
 template <int Kind>
 struct SliceK : AlignerSliceProcessorProjectiveCUDA {
   SliceK() : AlignerSliceProcessorProjectiveCUDA(Kind) {}
@@ -1130,6 +1137,7 @@ void registerTypes() {
     reg<ProjectiveS<0>>(std::string("CorrespondenceFinderProjectiveSquare") + dims);
     reg<ProjectiveS<1>>(std::string("CorrespondenceFinderProjectiveCircle") + dims);
     reg<ProjectiveS<2>>(std::string("CorrespondenceFinderProjectiveRhombus") + dims);
+    reg<ProjectiveKD>(std::string("CorrespondenceFinderProjectiveKDTree") + dims);
   }
   reg<SliceK<2>>("AlignerSliceProcessorProjective");
   reg<SliceK<1>>("AlignerSliceProcessorProjectiveDepth");

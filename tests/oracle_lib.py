@@ -367,7 +367,7 @@ def merger_select_additions(measurements, occupied, canvas_rows, canvas_cols, ro
     return win[:k].copy()
 
 
-SHAPES = {"square": 0, "circle": 1, "rhombus": 2}
+SHAPES = {"square": 0, "circle": 1, "rhombus": 2, "kdtree": 3}
 
 
 class ProjectiveFinder:

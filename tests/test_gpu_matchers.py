@@ -186,6 +186,36 @@ def test_projective(ctx, feats, shape, radius, dd, ratio):
     assert same_corr((gf, gm, gd), o)  # including the unordered_map output order
 
 
+@pytest.mark.parametrize("radius,dd,maxd,ratio", [(10, 50, 50, 0.9), (25, 25, 75, 0.8), (100, 25, 40, 0.8), (3, 100, 100, 0.99)])
+def test_projective_kdtree(ctx, feats, radius, dd, maxd, ratio):
+    """CorrespondenceFinderProjectiveKDTree (..._kdtree_impl.cpp:28-79) as the exact radius query (shape 3): GPU vs the CPU
+    restatement, bit for bit incl. the unordered_map output order.  Parity with the reference itself is UNPINNED for this
+    variant (approximate external KDTree); the exact query is its superset."""
+    from test_oracle_known_answers import CAM00, CAM01
+    m0, xyz = kitti_chain()
+    f1 = feats["L1"]
+    pose = O.pose_inverse(O.pose_mul(O.pose_inverse(CAM00), CAM01))
+    pf = O.ProjectiveFinder(K_KITTI, 376, 1241, shape="kdtree", max_desc_dist=maxd, ratio=ratio, min_desc_dist=dd,
+                            max_radius=radius, min_radius=radius, min_matching_ratio=0.0)
+    pf.set_fixed(f1["xy"], f1["desc"])
+    pf.set_moving(xyz, m0["desc"])
+    pf.set_estimate(pose)
+    o = pf.compute()
+    ctx.projective_set_fixed(f1["xy"], f1["desc"])
+    ctx.projective_set_moving(xyz, m0["desc"])
+    g = ctx.projective_match(pose, K_KITTI, 376, 1241, shape="kdtree", radius=radius, descriptor_distance=dd, ratio=ratio,
+                             max_descriptor_distance=maxd)
+    assert g[3] == pf.state()["n_projected"]
+    assert len(g[0]) == len(o[0]) and (radius < 10 or len(g[0]) > 10)
+    assert same_corr(g[:3], o)
+    # geometry: every match lies strictly inside the search radius of its projection (fp32 arithmetic of the query)
+    uvz, idx = O.project(xyz, pose, K_KITTI, 376, 1241, 0.1, 1000.0)
+    uv = np.full((len(xyz), 2), np.nan, np.float32)
+    uv[idx] = uvz[:, :2]
+    d2 = ((f1["xy"][g[0]] - uv[g[1]]) ** 2).sum(1)
+    assert (d2 < radius * radius).all() and (g[2] < min(dd, maxd)).all()
+
+
 def test_triangulate(ctx):  # mapping/triangulator_rigid_stereo.cpp:7-85 (SURVEY 8f N1)
     m0, _ = kitti_chain()
     b_x = float(np.float32(718.856) * np.float32(0.537166))

@@ -172,6 +172,46 @@ def test_projective_finder_state_machine(P):
     assert al.class_name == "MultiAligner3DQR"
 
 
+def test_projective_kdtree_finder_state_machine(P):
+    """CorrespondenceFinderProjectiveKDTree4D3D with kitti.conf's "cf_projective_kd" parameters (configurations/kitti.conf:
+    679-695) through the plugin mirror: the same adaptive state machine over the exact radius query (shape 3); every call
+    equals the CPU restatement.  Parity with the reference's approximate KDTree is unpinned."""
+    m = P.Manager()
+    pf = m.create("CorrespondenceFinderProjectiveKDTree4D3D", "cf_projective_kd")
+    assert pf.get("minimum_number_of_points_per_cluster") == 10  # correspondence_finder_projective_kdtree.h:24-28
+    pf.set("maximum_descriptor_distance", 75).set("maximum_distance_ratio_to_second_best", 0.8)
+    pf.set("minimum_matching_ratio", 0.1).set("minimum_descriptor_distance", 25).set("descriptor_distance_step_size_pixels", 5)
+    pf.set("maximum_search_radius_pixels", 50).set("minimum_search_radius_pixels", 10).set("search_radius_step_size_pixels", 10)
+    pf.set("minimum_number_of_iterations", 5).set("maximum_estimate_change_norm_for_convergence", 0.01)
+    pf.set("number_of_solver_iterations_per_projection", 5)
+    pr = m.create("PointIntensityDescriptor3fProjectorPinhole", "kd_projector")
+    pr.set_camera_matrix(K_KITTI)
+    pr.set("canvas_rows", 376).set("canvas_cols", 1241).set("range_min", 0.1).set("range_max", 1000.0)
+    pf.set("projector", pr)
+    meas, xyz, cam01_in_00 = kitti_chain()
+    of = O.ProjectiveFinder(K_KITTI, 376, 1241, "kdtree", max_desc_dist=75, ratio=0.8, min_matching_ratio=0.1,
+                            min_desc_dist=25, desc_step=5, max_radius=50, min_radius=10, radius_step=10,
+                            min_iterations=5, max_change_norm=0.01, iters_per_projection=5)
+    target = O.pose_inverse(cam01_in_00)
+    pf.set_fixed(meas[1]["uvuv"], meas[1]["desc"])
+    pf.set_moving(xyz, meas[0]["desc"])
+    of.set_fixed(meas[1]["uvuv"], meas[1]["desc"])
+    of.set_moving(xyz, meas[0]["desc"])
+    n_last = 0
+    for k in range(40):
+        t = min(1.0, k / 20.0)
+        pose = (np.eye(3, 4).reshape(12) * (1 - t) + target * t).astype(np.float32)
+        pf.set_local_map_in_sensor(pose)
+        of.set_estimate(pose)
+        g, o = pf.compute(), of.compute()
+        assert all(np.array_equal(a, b) for a, b in zip(g, o)), k
+        gs, os_ = pf.projective_state(), of.state()
+        for key in ("radius", "descriptor_distance", "iteration", "converged"):
+            assert gs[key] == os_[key], (k, key, gs, os_)
+        n_last = len(g[0])
+    assert pf.projective_state()["converged"] and n_last > 30
+
+
 def test_projective_finders_share_the_device_cache(P):
     """Two projective finder instances and other modules share the process-wide device context.  Each finder's cached
     clouds / lattice must survive (or be restored after) the other's uploads, a brute-force match, a triangulation and a

@@ -43,7 +43,7 @@ HOT_CLASSES = ["IntensityFeatureExtractorBinned2D", "IntensityFeatureExtractorBi
                "LandmarkEstimatorPoseBasedSmoother3D3D", "LandmarkEstimatorPoseBasedSmoother4D3D",
                "MergerRigidStereoTriangulation", "MergerRigidStereoProjectiveEKF", "MergerProjectiveDepthEKF"]
 HOT_CLASSES += [f"CorrespondenceFinderDescriptorBasedBruteforce{d}" for d in ("2D2D", "2D3D", "3D3D", "4D3D")]
-HOT_CLASSES += [f"CorrespondenceFinderProjective{s}{d}" for s in ("Square", "Circle", "Rhombus") for d in ("2D3D", "3D3D", "4D3D")]
+HOT_CLASSES += [f"CorrespondenceFinderProjective{s}{d}" for s in ("Square", "Circle", "Rhombus", "KDTree") for d in ("2D3D", "3D3D", "4D3D")]
 
 
 @pytest.mark.parametrize("name", HOT_CLASSES)
