@@ -586,22 +586,23 @@ def main():
     # query rows sharded by rank, train set replicated; the per-row (best, second, argmin) table is assembled on
     # every rank by ONE all-gather (NCCL over NVLink) inside the timed region -> strong scaling
     if not args.no_hamming:
-        from srrg2_proslam_b200 import sharding
         nq = nt = 65536
         q, t = synth.hamming_sets(nq, nt, seed=args.seed)
-        qb, qe = sharding.query_rows(nq, rank, world)
-        rows_local = qe - qb
-        dq, dt_ = torch.from_numpy(q[qb:qe].copy()).to(dev), torch.from_numpy(t).to(dev)
-        ob = torch.empty((3, max(rows_local, 1)), dtype=torch.int32, device=dev)
-        table = None
+        # N > 1: the C ABI's own multi-GPU entry point (pslam_bf_best2_sharded_dev): its NCCL communicator is created through
+        # the ABI as well (the 128-byte id travels over torch.distributed), the all-gather runs on the context's stream
+        dq, dt_ = torch.from_numpy(q).to(dev), torch.from_numpy(t).to(dev)
+        table = torch.empty((3, nq), dtype=torch.int32, device=dev)
+        comm = None
+        if world > 1:
+            ids = [ctx.nccl_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(ids, src=0)
+            comm = ctx.nccl_comm_create(ids[0], rank, world)
         def sweep():
-            nonlocal table
-            if rows_local:
-                ctx.bf_best2_dev(rows_local, dq.data_ptr(), nt, dt_.data_ptr(), ob[0].data_ptr(), ob[1].data_ptr(), ob[2].data_ptr())
             if world > 1:
-                torch.cuda.current_stream().wait_stream(stream)
-                table = sharding.allgather_best2(ob[:, :rows_local], nq)
-                stream.wait_stream(torch.cuda.current_stream())
+                ctx.bf_best2_sharded_dev(comm, rank, world, nq, dq.data_ptr(), nt, dt_.data_ptr(), table[0].data_ptr(),
+                                         table[1].data_ptr(), table[2].data_ptr())
+            else:
+                ctx.bf_best2_dev(nq, dq.data_ptr(), nt, dt_.data_ptr(), table[0].data_ptr(), table[1].data_ptr(), table[2].data_ptr())
         for _ in range(3):
             sweep()
         barrier()
@@ -616,6 +617,8 @@ def main():
         if world > 1:
             dist.all_reduce(hms, op=dist.ReduceOp.MAX)
         gpairs = nq * nt * reps / (float(hms.item()) * 1e-3) / 1e9
+        if comm is not None:
+            ctx.nccl_comm_destroy(comm)
         sm_mhz = line["clocks"]["sm_mhz"] or 1965.0
         # Roofline of the sweep = the busier of the two integer pipes for the kernel's instruction mix per 256-bit pair
         # (SASS of bf_sweep_kernel<0>: 5 POPC on the XU pipe; 15 LOP3 + 1 IADD3 + 3 VIMNMX on the ALU pipe), with the pipe
@@ -633,7 +636,8 @@ def main():
         plain_peak = 148 * popc_rate / 8 * sm_mhz * 1e6 / 1e9 * world
         line["hamming"] = {"metric": "hamming_best2_gpairs_per_s", "value": gpairs, "unit": "GPair/s", "scaling": "strong",
                            "config": {"workload": "64k x 64k 256-bit descriptors (BASELINE config 5): query rows sharded "
-                                                  f"over {world} GPU(s), train set replicated, all-gather of (best, second, argmin)"},
+                                                  f"over {world} GPU(s), train set replicated, all-gather of (best, second, argmin)",
+                                      "api": "pslam_bf_best2_dev" if world == 1 else "pslam_bf_best2_sharded_dev (ncclAllGather on the context stream)"},
                            "ms_per_sweep": float(hms.item()) / reps,
                            "roofline": {"bound": "int (XU popc + ALU lop3, balanced)", "achieved": gpairs, "peak": int_peak, "unit": "GPair/s",
                                         "frac": gpairs / int_peak,

@@ -344,6 +344,26 @@ int pslam_bf_best2_dev(pslam_ctx* ctx, int n_fixed, const uint32_t* d_desc_fixed
                        const uint32_t* d_desc_moving, int32_t* d_best, int32_t* d_second,
                        int32_t* d_best_idx);
 
+/* ---- multi-GPU: one process per GPU ---------------------------------
+ * Frames of the stage-1 / stereo pipeline are independent: every rank runs the batched entry points on its own frame
+ * range (pslam_shard_frames), no collective.  The exhaustive Hamming sweep shards its QUERY rows with the train set
+ * replicated -- the pair loop of CorrespondenceFinderDescriptorBasedBruteforce::compute
+ * (.../correspondence_finder_descriptor_based_bruteforce_impl.cpp:32-74) is a per-row reduction -- and ends with ONE
+ * ncclAllGather of (best, second, argmin) on the context's stream.  libnccl is resolved at run time (the copy the host
+ * process already loaded, else the system's); nccl_comm is an ncclComm_t.  A host that has no communicator yet creates
+ * one with the two helpers below: rank 0 draws the id, the application broadcasts its 128 bytes, every rank calls create. */
+typedef struct { char internal[128]; } PslamNcclId;  /* = ncclUniqueId */
+int pslam_shard_frames(int n_frames, int rank, int world, int* begin, int* end);
+/* rows [begin, end) of `rank`; returns the shard size ceil(n / world) rounded up to `align` (256 = one sweep CTA) */
+int pslam_shard_rows(int n_rows, int rank, int world, int align, int* begin, int* end);
+int pslam_nccl_unique_id(pslam_ctx* ctx, PslamNcclId* id);
+int pslam_nccl_comm_create(pslam_ctx* ctx, const PslamNcclId* id, int rank, int world, void** nccl_comm);
+int pslam_nccl_comm_destroy(pslam_ctx* ctx, void* nccl_comm);
+/* every rank passes the SAME full descriptor sets (device pointers) and receives the full tables [n_fixed] */
+int pslam_bf_best2_sharded_dev(pslam_ctx* ctx, void* nccl_comm, int rank, int world, int n_fixed,
+                               const uint32_t* d_desc_fixed, int n_moving, const uint32_t* d_desc_moving,
+                               int32_t* d_best, int32_t* d_second, int32_t* d_best_idx);
+
 /* ---- stage 2c: projective window matching ---------------------------------------
  * Replaces the device-worthy part of CorrespondenceFinderProjective{Square,Circle,Rhombus}:
  * PointProjectorPinhole_::compute + _initializeDatabase + _findNearestNeighbors +

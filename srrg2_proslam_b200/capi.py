@@ -142,6 +142,23 @@ class FrameCfg(C.Structure):
                 ("inverse_depth_weighting", C.c_int), ("minimum_disparity_pixels", C.c_float)]
 
 
+def shard_rows(n, rank, world, align=256):
+    """pslam_shard_rows: (begin, end, rows per padded shard)"""
+    b, e = C.c_int(0), C.c_int(0)
+    per = lib().pslam_shard_rows(int(n), int(rank), int(world), int(align), C.byref(b), C.byref(e))
+    if per < 0:
+        raise PslamError(per, "pslam_shard_rows")
+    return b.value, e.value, per
+
+
+def shard_frames(n, rank, world):
+    b, e = C.c_int(0), C.c_int(0)
+    rc = lib().pslam_shard_frames(int(n), int(rank), int(world), C.byref(b), C.byref(e))
+    if rc < 0:
+        raise PslamError(rc, "pslam_shard_frames")
+    return b.value, e.value
+
+
 SHAPES = {"square": 0, "circle": 1, "rhombus": 2, "kdtree": 3}
 FACTORS = {"stereo": 0, "depth": 1, "mono": 2}
 ROBUST = {"none": 0, "saturated": 1, "clamp": 2}
@@ -484,6 +501,26 @@ class Context:
     def bf_best2_dev(self, nq, d_q, nt, d_t, d_best, d_second, d_idx):
         self._chk(lib().pslam_bf_best2_dev(self._h, int(nq), C.c_void_p(d_q), int(nt), C.c_void_p(d_t),
                                            C.c_void_p(d_best), C.c_void_p(d_second), C.c_void_p(d_idx)))
+
+    # ---- multi-GPU (one process per GPU): NCCL communicator helpers + the query-row sharded sweep ---------------
+    def nccl_unique_id(self):
+        """128 bytes drawn by ONE rank (ncclGetUniqueId); the application broadcasts them to the others"""
+        buf = C.create_string_buffer(128)
+        self._chk(lib().pslam_nccl_unique_id(self._h, buf))
+        return buf.raw
+
+    def nccl_comm_create(self, unique_id, rank, world):
+        comm = C.c_void_p(0)
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._chk(lib().pslam_nccl_comm_create(self._h, buf, int(rank), int(world), C.byref(comm)))
+        return comm
+
+    def nccl_comm_destroy(self, comm):
+        self._chk(lib().pslam_nccl_comm_destroy(self._h, comm))
+
+    def bf_best2_sharded_dev(self, comm, rank, world, nq, d_q, nt, d_t, d_best, d_second, d_idx):
+        self._chk(lib().pslam_bf_best2_sharded_dev(self._h, comm, int(rank), int(world), int(nq), C.c_void_p(d_q), int(nt),
+                                                   C.c_void_p(d_t), C.c_void_p(d_best), C.c_void_p(d_second), C.c_void_p(d_idx)))
 
     def match_bruteforce(self, desc_f, desc_m, cfg):
         desc_f = np.ascontiguousarray(desc_f, np.uint8).reshape(-1, 32)

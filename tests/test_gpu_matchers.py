@@ -142,6 +142,29 @@ def test_bf_best2(ctx, nf, nm):
     assert np.array_equal(gb, ob) and np.array_equal(gs, os_) and np.array_equal(gi, oi)
 
 
+def test_bf_best2_sharded_single_rank_through_nccl(ctx):
+    """pslam_bf_best2_sharded_dev with a one-rank NCCL communicator created through the C ABI: shard -> sweep ->
+    ncclAllGather on the context's stream -> unshard == the plain sweep (the 2- and 8-GPU runs: tools/sharded_check.py)"""
+    import torch
+    rng = np.random.default_rng(9)
+    nq, nt = 1500, 2100
+    q = rng.integers(0, 256, (nq, 32), dtype=np.uint8)
+    t = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
+    comm = ctx.nccl_comm_create(ctx.nccl_unique_id(), 0, 1)
+    try:
+        dq, dt_ = torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda()
+        out = torch.full((3, nq), -7, dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+        ctx.bf_best2_sharded_dev(comm, 0, 1, nq, dq.data_ptr(), nt, dt_.data_ptr(), out[0].data_ptr(), out[1].data_ptr(),
+                                 out[2].data_ptr())
+        ctx.synchronize()
+    finally:
+        ctx.nccl_comm_destroy(comm)
+    ob, os_, oi = O.bf_best2(q, t)
+    g = out.cpu().numpy()
+    assert np.array_equal(g[0], ob) and np.array_equal(g[1], os_) and np.array_equal(g[2], oi)
+
+
 def test_adaptors_known_answers(ctx):  # tests/test_measurement_adaptors.cpp:51,130
     from srrg2_proslam_b200 import capi
     e = capi.extract_cfg(5, 1, 500)

@@ -25,6 +25,20 @@ def test_ranges_partition_exactly():
             assert all(b % 256 == 0 for b, e in qr if e > b)
 
 
+def test_c_abi_shard_ranges_equal_the_python_ones():
+    """pslam_shard_rows / pslam_shard_frames (pure functions of the C ABI, include/pslam_cuda.h) give the same ranges as
+    the torch.distributed harness"""
+    from srrg2_proslam_b200 import capi
+    for n in (0, 1, 255, 256, 257, 700, 10000, 65536, 65537):
+        for world in (1, 2, 3, 4, 8):
+            for r in range(world):
+                b, e, per = capi.shard_rows(n, r, world)
+                assert (b, e) == sharding.query_rows(n, r, world) and per % 256 == 0 and per * world >= n
+                assert capi.shard_frames(n, r, world) == sharding.frame_range(n, r, world)
+    with pytest.raises(capi.PslamError):
+        capi.shard_rows(10, 2, 2)
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
