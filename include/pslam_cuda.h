@@ -240,7 +240,12 @@ int pslam_scene_clip_dev(pslam_ctx* ctx, long long n, const float* d_xyz, const 
  * state_world [n][3] and covariance [n][9] are the landmark statistics (state(), covariance()): updated IN PLACE for
  * the landmarks the estimator accepts (what addOptimizationResult stores, :74-75); coords_in_local_map [n][3] receives
  * their new local coordinates (:79-80), inlier[n] = statistics().isInlier().  measurements: [n][E], E = 2 / 3 / 4.
- * Returns the number of inliers. */
+ * Returns the number of inliers.
+ * CALLER'S PART of addOptimizationResult: the reference also counts one optimisation per accepted landmark
+ * (statistics().numberOfOptimizations(), read by the aligner's 1 + log(n) weighting, aligner_slice_processor_projective.cpp:
+ * 41-57, and by the weighted mean).  The EKF and weighted-mean entry points take that counter read-only or not at all:
+ * the owner of the statistics increments it for every landmark with inlier[i] != 0 (the smoother entry point updates it
+ * itself, like its reference code does).  tests/test_gpu_tracker_sequence.py chains five frames this way. */
 typedef struct pslam_ekf_cfg {
   int kind;                                        /* 0 projective (u,v) | 1 projective depth (u,v,z) | 2 rectified stereo (uL,vL,uR,vR) */
   float K[9];                                      /* filter->setCameraMatrix */
