@@ -27,6 +27,9 @@ typedef struct psp_module psp_module;   /* a Configurable owned by its manager *
 
 const char* psp_last_error(void);
 int psp_set_device(int device);
+/* pslam_profile_enable / pslam_profile_read (pslam_cuda.h) on the process-wide device context the modules share */
+int psp_profile_enable(int enable);
+int psp_profile_read(int capacity, char* names, int name_len, double* total_ms, long long* launches);
 
 /* ---- ConfigurableManager: srrg2_core::ConfigurableManager::read / getByName / create ---------- */
 psp_manager* psp_manager_create(void);

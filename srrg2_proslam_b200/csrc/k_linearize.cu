@@ -105,22 +105,33 @@ __device__ __forceinline__ bool error_and_jacobian(const LinParams& c, const dou
 // accumulate one correspondence into the thread's partial sums (FactorCorrespondenceDriven_::compute analogue).
 // T = scalar type of the clouds in HBM: float (the reference's own cloud type: 40 B per correspondence, widened to
 // fp64 in registers -- exact) or double.  status (may be nullptr): 0 inlier, 1 kernelized, 2 suppressed.
+// one correspondence as the factor reads it: moving point, fixed measurement, information diagonal -- widened to fp64 (exact)
+struct CorrData {
+  double pm[3], z[3], om[3];
+};
 template <typename T>
-__device__ __forceinline__ void accumulate_correspondence(const LinParams& c, int edim, const T* __restrict__ moving_xyz,
-                                                          const T* __restrict__ fixed_meas, int fixed_dim, int fi, int mi,
-                                                          const T* __restrict__ info_diag, double* acc, uint8_t* status) {
-  double pm[3] = {(double) moving_xyz[3 * (size_t) mi], (double) moving_xyz[3 * (size_t) mi + 1],
-                  (double) moving_xyz[3 * (size_t) mi + 2]};
-  double z[3] = {0, 0, 0};
-  for (int i = 0; i < 3 && i < fixed_dim; ++i) z[i] = (double) fixed_meas[(size_t) fixed_dim * fi + i];
+__device__ __forceinline__ CorrData load_correspondence(const T* __restrict__ moving_xyz, const T* __restrict__ fixed_meas,
+                                                        int fixed_dim, int fi, int mi, const T* __restrict__ info_diag) {
+  CorrData d;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    d.pm[i] = (double) moving_xyz[3 * (size_t) mi + i];
+    d.z[i] = i < fixed_dim ? (double) fixed_meas[(size_t) fixed_dim * fi + i] : 0.0;
+    d.om[i] = (double) info_diag[3 * (size_t) fi + i];
+  }
+  return d;
+}
+
+// accumulate one correspondence into the thread's partial sums (FactorCorrespondenceDriven_::compute analogue).
+// status (may be nullptr): 0 inlier, 1 kernelized, 2 suppressed.
+__device__ __forceinline__ void accumulate_loaded(const LinParams& c, int edim, const CorrData& d, double* acc, uint8_t* status) {
   double e[3], J[18];
-  if (!error_and_jacobian(c, pm, z, e, J)) {
+  if (!error_and_jacobian(c, d.pm, d.z, e, J)) {
     acc[30] += 1;
     if (status) *status = 2;
     return;
   }
-  const double om[3] = {(double) info_diag[3 * (size_t) fi], (double) info_diag[3 * (size_t) fi + 1],
-                        (double) info_diag[3 * (size_t) fi + 2]};
+  const double* om = d.om;
   double chi = 0;
   for (int i = 0; i < edim; ++i) chi = __dadd_rn(chi, __dmul_rn(__dmul_rn(e[i], om[i]), e[i]));
   double scale = 1;
@@ -144,6 +155,16 @@ __device__ __forceinline__ void accumulate_correspondence(const LinParams& c, in
       for (int b = a; b < 6; ++b) acc[h++] += __dmul_rn(Jw, J[6 * i + b]);
     }
   }
+}
+
+// T = scalar type of the clouds in HBM: float (the reference's own cloud type: 40 B per correspondence, widened to
+// fp64 in registers -- exact) or double.
+template <typename T>
+__device__ __forceinline__ void accumulate_correspondence(const LinParams& c, int edim, const T* __restrict__ moving_xyz,
+                                                          const T* __restrict__ fixed_meas, int fixed_dim, int fi, int mi,
+                                                          const T* __restrict__ info_diag, double* acc, uint8_t* status) {
+  const CorrData d = load_correspondence(moving_xyz, fixed_meas, fixed_dim, fi, mi, info_diag);
+  accumulate_loaded(c, edim, d, acc, status);
 }
 
 template <typename T>
@@ -383,12 +404,183 @@ __device__ __noinline__ double pose_prior_accumulate_dev(const PriorParams& pr, 
   return chi;
 }
 
+// ---- the same two steps spread over the lanes of ONE warp ------------------------------------------------------------------
+// Inside the fused loop the pose-prior factor and the 6x6 solve were ~6 of the ~9 us of an iteration when one thread ran them
+// (dependent fp64 chains, arrays in local memory).  Here every matrix element is evaluated by its own lane with exactly the
+// operation sequence of the serial functions above (same sums in the same order: identical bits), intermediate matrices live
+// in shared memory, the Cholesky advances one column per step, the triangular solves one unknown per step.
+struct GnWork {
+  double H[36], b[6], L[36], dx[6], R[9], t[3];
+  double ER[9], Et[3], e6[6], J[36], OJ[36], Oe[6], D[9], q[4];
+};
+
+__device__ __forceinline__ void pose_prior_accumulate_warp(const PriorParams& pr, GnWork& S, int lane) {
+  if (lane < 9) {
+    const int i = lane / 3, j = lane % 3;
+    S.ER[lane] = (pr.Zi_R[3 * i] * S.R[j] + pr.Zi_R[3 * i + 1] * S.R[3 + j]) + pr.Zi_R[3 * i + 2] * S.R[6 + j];
+  } else if (lane < 12) {
+    const int i = lane - 9;
+    S.Et[i] = ((pr.Zi_R[3 * i] * S.t[0] + pr.Zi_R[3 * i + 1] * S.t[1]) + pr.Zi_R[3 * i + 2] * S.t[2]) + pr.Zi_t[i];
+  }
+  __syncwarp();
+  if (lane == 0) {
+    t2tnq_dev(S.ER, S.Et, S.e6);
+    const double n2 = S.e6[3] * S.e6[3] + S.e6[4] * S.e6[4] + S.e6[5] * S.e6[5];
+    S.q[0] = sqrt(n2 < 1.0 ? 1.0 - n2 : 0.0);
+  }
+  __syncwarp();
+  for (int el = lane; el < 36; el += 32) {  // J = blockdiag(R_E, w I + [v]x)
+    const int k = el / 6, j = el % 6;
+    double v = 0;
+    if (k < 3 && j < 3) {
+      v = S.ER[3 * k + j];
+    } else if (k >= 3 && j >= 3) {
+      const double w = S.q[0], vx = S.e6[3], vy = S.e6[4], vz = S.e6[5];
+      const double Q[9] = {w, -vz, vy, vz, w, -vx, -vy, vx, w};
+      v = Q[3 * (k - 3) + (j - 3)];
+    }
+    S.J[el] = v;
+  }
+  __syncwarp();
+  for (int el = lane; el < 36; el += 32) {
+    const int i = el / 6, j = el % 6;
+    double a = 0;
+    for (int k = 0; k < 6; ++k) a += pr.Omega[6 * i + k] * S.J[6 * k + j];
+    S.OJ[el] = a;
+  }
+  if (lane < 6) {
+    double sum = 0;
+    for (int k = 0; k < 6; ++k) sum += pr.Omega[6 * lane + k] * S.e6[k];
+    S.Oe[lane] = sum;
+  }
+  __syncwarp();
+  if (lane < 6) {
+    double bs = 0;
+    for (int k = 0; k < 6; ++k) bs += S.J[6 * k + lane] * S.Oe[k];
+    S.b[lane] += bs;
+  }
+  for (int el = lane; el < 36; el += 32) {
+    const int a = el / 6, c = el % 6;
+    double hs = 0;
+    for (int k = 0; k < 6; ++k) hs += S.J[6 * k + a] * S.OJ[6 * k + c];
+    S.H[el] += hs;
+  }
+  __syncwarp();
+}
+
+// (H + damping I) dx = -b by Cholesky, pose <- pose * v2t(dx); S.H, S.b, S.R, S.t in, S.R, S.t, S.dx out.  All 32 lanes call it.
+__device__ __forceinline__ bool gn_solve_update_warp(GnWork& S, double damping, int lane) {
+  const unsigned FULLM = 0xffffffffu;
+  const bool row = lane < 6;
+  double Ai[6], Li[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    Ai[j] = row ? S.H[6 * lane + j] : 0.0;
+    if (row && j == lane) Ai[j] += damping;
+    Li[j] = 0;
+  }
+  // Latency is a chain of fp64 sqrt / divide sequences (~260 cycles each on this part): ONE reciprocal square root per
+  // column replaces sqrt + divide, and the triangular solves multiply by it.  Differs from the divide form in the last bit
+  // of an element (parity with the fp64 oracle is 1e-9 relative, tests/test_gpu_solver.py).
+  double ri = 0;  // 1 / L[i][i] of this lane's row
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {  // column j: every row i >= j at once
+    double s = 1.0;
+    if (row && lane >= j) {
+      s = Ai[j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) s = __dsub_rn(s, __dmul_rn(Li[k], S.L[6 * j + k]));
+    }
+    const double d = __shfl_sync(FULLM, s, j);
+    if (!(d > 0)) return false;  // uniform
+    const double r = rsqrt(d);
+    if (row && lane >= j) {
+      Li[j] = __dmul_rn(s, r);  // row j: d / sqrt(d) = L[j][j]
+      if (lane == j) ri = r;
+      S.L[6 * lane + j] = Li[j];
+    }
+    __syncwarp();
+  }
+  // forward substitution: one unknown per step, the rows below fold it in right away (same order of terms per row)
+  double si = row ? -S.b[lane] : 0.0, yi = 0;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const double yk = __dmul_rn(__shfl_sync(FULLM, si, k), __shfl_sync(FULLM, ri, k));
+    if (lane == k) yi = yk;
+    if (row && lane > k) si = __dsub_rn(si, __dmul_rn(Li[k], yk));
+  }
+  // backward substitution: dx[i] = (y[i] - sum_{k > i, ascending} L[k][i] dx[k]) / L[i][i]
+#pragma unroll
+  for (int i = 5; i >= 0; --i) {
+    if (lane == i) {
+      double s = yi;
+      for (int k = i + 1; k < 6; ++k) s = __dsub_rn(s, __dmul_rn(S.L[6 * k + i], S.dx[k]));
+      S.dx[i] = __dmul_rn(s, ri);
+    }
+    __syncwarp();
+  }
+  // v2t(dx)
+  if (lane == 0) {
+    double x = S.dx[3], yq = S.dx[4], z = S.dx[5];
+    const double n2 = __dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(yq, yq)), __dmul_rn(z, z));
+    double w;
+    if (n2 < 1.0) {
+      w = sqrt(__dsub_rn(1.0, n2));
+    } else {
+      const double n = sqrt(n2);
+      x = __ddiv_rn(x, n);
+      yq = __ddiv_rn(yq, n);
+      z = __ddiv_rn(z, n);
+      w = 0;
+    }
+    S.q[0] = x;
+    S.q[1] = yq;
+    S.q[2] = z;
+    S.q[3] = w;
+  }
+  __syncwarp();
+  if (lane < 9) {
+    const double x = S.q[0], yq = S.q[1], z = S.q[2], w = S.q[3];
+    double v;
+    switch (lane) {
+      case 0: v = __dsub_rn(1.0, __dmul_rn(2.0, __dadd_rn(__dmul_rn(yq, yq), __dmul_rn(z, z)))); break;
+      case 1: v = __dmul_rn(2.0, __dsub_rn(__dmul_rn(x, yq), __dmul_rn(z, w))); break;
+      case 2: v = __dmul_rn(2.0, __dadd_rn(__dmul_rn(x, z), __dmul_rn(yq, w))); break;
+      case 3: v = __dmul_rn(2.0, __dadd_rn(__dmul_rn(x, yq), __dmul_rn(z, w))); break;
+      case 4: v = __dsub_rn(1.0, __dmul_rn(2.0, __dadd_rn(__dmul_rn(x, x), __dmul_rn(z, z)))); break;
+      case 5: v = __dmul_rn(2.0, __dsub_rn(__dmul_rn(yq, z), __dmul_rn(x, w))); break;
+      case 6: v = __dmul_rn(2.0, __dsub_rn(__dmul_rn(x, z), __dmul_rn(yq, w))); break;
+      case 7: v = __dmul_rn(2.0, __dadd_rn(__dmul_rn(yq, z), __dmul_rn(x, w))); break;
+      default: v = __dsub_rn(1.0, __dmul_rn(2.0, __dadd_rn(__dmul_rn(x, x), __dmul_rn(yq, yq)))); break;
+    }
+    S.D[lane] = v;
+  }
+  __syncwarp();
+  double nv = 0;
+  if (lane < 9) {
+    const int i = lane / 3, j = lane % 3;
+    nv = __dadd_rn(__dadd_rn(__dmul_rn(S.R[3 * i], S.D[j]), __dmul_rn(S.R[3 * i + 1], S.D[3 + j])), __dmul_rn(S.R[3 * i + 2], S.D[6 + j]));
+  } else if (lane < 12) {
+    const int i = lane - 9;
+    nv = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(S.R[3 * i], S.dx[0]), __dmul_rn(S.R[3 * i + 1], S.dx[1])),
+                             __dmul_rn(S.R[3 * i + 2], S.dx[2])), S.t[i]);
+  }
+  __syncwarp();
+  if (lane < 9) S.R[lane] = nv;
+  else if (lane < 12) S.t[lane - 9] = nv;
+  __syncwarp();
+  return true;
+}
+
 // ---- fused solver iterations: n_iters x { linearise all correspondences -> H, b (+ pose prior) -> Cholesky -> pose update }
 // in ONE launch, one CTA per problem.  This is what the aligner runs between two re-projections of the correspondence
 // finder (the correspondences, hence the information matrices, do not change in between: SURVEY App. E.6), instead
 // of 2 launches + 2 host round trips per iteration.  out (per iteration): 12 pose (after the update) + chi, inliers,
 // outliers, suppressed.  iters_done: iterations completed (stops early when H + damping I is not SPD).  status (may be
 // nullptr): per-correspondence factor status of the LAST linearised iteration (inlier-only runs, icl.conf:55-58).
+// Latency is what counts here (a frame runs ~100 dependent iterations on a few dozen correspondences): a thread keeps its
+// correspondence in registers across the iterations when there is at most one per thread, warps without correspondences
+// skip the shuffle reduction, and warp 0 runs the prior + solve lane-parallel (gn_solve_update_warp).
 constexpr int GN_OUT = 16;
 template <typename T>
 __global__ void __launch_bounds__(LZ_THREADS)
@@ -398,31 +590,44 @@ gn_iterate_kernel(LinParams c0, PriorParams prior, double damping, int n_iters, 
                   int* __restrict__ iters_done, uint8_t* __restrict__ status) {
   __shared__ double s_part[LZ_THREADS / 32][LZ_NACC];
   __shared__ double s_sum[LZ_NACC];
-  __shared__ double s_R[9], s_t[3];
+  __shared__ GnWork S;
   __shared__ int s_ok;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (threadIdx.x < 9) s_R[threadIdx.x] = c0.R[threadIdx.x];
-  if (threadIdx.x < 3) s_t[threadIdx.x] = c0.t[threadIdx.x];
+  if (threadIdx.x < 9) S.R[threadIdx.x] = c0.R[threadIdx.x];
+  if (threadIdx.x < 3) S.t[threadIdx.x] = c0.t[threadIdx.x];
   if (threadIdx.x == 0) s_ok = 1;
   __syncthreads();
   const int edim = (c0.kind == 2) ? 2 : 3;
   LinParams c = c0;
+  const bool resident = n_corr <= LZ_THREADS;  // at most one correspondence per thread: it stays in registers
+  const bool warp_has_work = wid * 32 < n_corr;
+  CorrData mine;
+  if (resident && (int) threadIdx.x < n_corr)
+    mine = load_correspondence(moving_xyz, fixed_meas, fixed_dim, corr_fixed[threadIdx.x], corr_moving[threadIdx.x], info_diag);
   int done = 0;
   for (int it = 0; it < n_iters; ++it) {
 #pragma unroll
-    for (int i = 0; i < 9; ++i) c.R[i] = s_R[i];
+    for (int i = 0; i < 9; ++i) c.R[i] = S.R[i];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) c.t[i] = s_t[i];
-    double acc[LZ_NACC];
+    for (int i = 0; i < 3; ++i) c.t[i] = S.t[i];
+    if (warp_has_work || !resident) {
+      double acc[LZ_NACC];
 #pragma unroll
-    for (int i = 0; i < LZ_NACC; ++i) acc[i] = 0;
-    for (int k = threadIdx.x; k < n_corr; k += LZ_THREADS)
-      accumulate_correspondence(c, edim, moving_xyz, fixed_meas, fixed_dim, corr_fixed[k], corr_moving[k], info_diag, acc,
-                                status ? status + k : nullptr);
+      for (int i = 0; i < LZ_NACC; ++i) acc[i] = 0;
+      if (resident) {
+        if ((int) threadIdx.x < n_corr) accumulate_loaded(c, edim, mine, acc, status ? status + threadIdx.x : nullptr);
+      } else {
+        for (int k = threadIdx.x; k < n_corr; k += LZ_THREADS)
+          accumulate_correspondence(c, edim, moving_xyz, fixed_meas, fixed_dim, corr_fixed[k], corr_moving[k], info_diag, acc,
+                                    status ? status + k : nullptr);
+      }
 #pragma unroll
-    for (int i = 0; i < LZ_NACC - 1; ++i) {
-      const double s = warp_sum(acc[i]);
-      if (lane == 0) s_part[wid][i] = s;
+      for (int i = 0; i < LZ_NACC - 1; ++i) {
+        const double s = warp_sum(acc[i]);
+        if (lane == 0) s_part[wid][i] = s;
+      }
+    } else if (lane < LZ_NACC - 1) {
+      s_part[wid][lane] = 0.0;
     }
     __syncthreads();
     if (threadIdx.x < LZ_NACC - 1) {
@@ -431,34 +636,19 @@ gn_iterate_kernel(LinParams c0, PriorParams prior, double damping, int n_iters, 
       s_sum[threadIdx.x] = s;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      double H[36], bvec[6], R[9], t[3], dx[6];
-      int h = 0;
-      for (int a = 0; a < 6; ++a)
-        for (int b = a; b < 6; ++b) {
-          H[6 * a + b] = s_sum[h];
-          H[6 * b + a] = s_sum[h];
-          ++h;
-        }
-      for (int a = 0; a < 6; ++a) bvec[a] = s_sum[21 + a];
-      for (int i = 0; i < 9; ++i) R[i] = s_R[i];
-      for (int i = 0; i < 3; ++i) t[i] = s_t[i];
-      if (prior.enabled) pose_prior_accumulate_dev(prior, R, t, H, bvec);
-      const bool ok = gn_solve_update(H, bvec, damping, R, t, dx);
+    if (wid == 0) {
+      for (int el = lane; el < 36; el += 32) {  // full symmetric H from the 21 upper-triangle sums
+        const int a = el / 6, b = el % 6, lo = a < b ? a : b, hi = a < b ? b : a;
+        S.H[el] = s_sum[lo * 6 - lo * (lo - 1) / 2 + (hi - lo)];
+      }
+      if (lane < 6) S.b[lane] = s_sum[21 + lane];
+      __syncwarp();
+      if (prior.enabled) pose_prior_accumulate_warp(prior, S, lane);
+      const bool ok = gn_solve_update_warp(S, damping, lane);  // leaves the pose untouched when H + damping I is not SPD
       double* o = out + (size_t) it * GN_OUT;
-      if (ok) {
-        for (int i = 0; i < 9; ++i) s_R[i] = R[i];
-        for (int i = 0; i < 3; ++i) s_t[i] = t[i];
-      }
-      for (int i = 0; i < 3; ++i) {
-        for (int j = 0; j < 3; ++j) o[4 * i + j] = s_R[3 * i + j];
-        o[4 * i + 3] = s_t[i];
-      }
-      o[12] = s_sum[27];
-      o[13] = s_sum[28];
-      o[14] = s_sum[29];
-      o[15] = s_sum[30];
-      s_ok = ok ? 1 : 0;
+      if (lane < 12) o[lane] = (lane & 3) == 3 ? S.t[lane >> 2] : S.R[3 * (lane >> 2) + (lane & 3)];
+      else if (lane < 16) o[lane] = s_sum[27 + (lane - 12)];
+      if (lane == 0) s_ok = ok ? 1 : 0;
     }
     __syncthreads();
     ++done;  // the iteration was linearised (its stats are valid) even when the solve failed

@@ -32,23 +32,35 @@ struct RowLess {  // [](a, b) { return a.row < b.row; }   (square_impl.cpp:27-29
 };
 
 // lattice element = (row << 32) | (col << 16) | index   (Element{int16 row, col, index}, square.h:37-47)
-__global__ void __launch_bounds__(32)
-lattice_build_kernel(const float* __restrict__ coords, int dim, int n,
-                     unsigned long long* __restrict__ lattice, int smem_cap) {
+// The unstable std::sort by row is replayed move for move (libstdcxx_sort.h): warp 0 runs the introsort partitioning with
+// ballots, then the whole CTA places every element at its final-insertion-sort position (113 -> ~10 us per fixed cloud:
+// the lattice is rebuilt for every frame).  `tmp` / `g_rpos`: global scratch for clouds that do not fit shared memory.
+constexpr int LB_THREADS = 1024;
+__global__ void __launch_bounds__(LB_THREADS)
+lattice_build_kernel(const float* __restrict__ coords, int dim, int n, unsigned long long* __restrict__ lattice, int smem_cap,
+                     unsigned long long* __restrict__ tmp, unsigned* __restrict__ g_rpos) {
   extern __shared__ __align__(16) unsigned long long s_l[];
-  const int lane = threadIdx.x;
-  unsigned long long* a = (n <= smem_cap) ? s_l : lattice;
-  for (int i = lane; i < n; i += 32) {
+  __shared__ int s_end;
+  const int tid = threadIdx.x;
+  const bool in_smem = n <= smem_cap;
+  unsigned long long* a = in_smem ? s_l : tmp;
+  for (int i = tid; i < n; i += LB_THREADS) {
     const short row = (short) coords[(size_t) dim * i + 1];  // int16(coordinates(1))
     const short col = (short) coords[(size_t) dim * i + 0];
     a[i] = ((unsigned long long) (unsigned) (int) row << 32) |
            ((unsigned long long) (unsigned short) col << 16) | (unsigned long long) (unsigned short) i;
   }
-  __syncwarp();
-  if (lane == 0) pslam_sort::std_sort(a, n, RowLess());
-  __syncwarp();
-  if (a != lattice)
-    for (int i = lane; i < n; i += 32) lattice[i] = a[i];
+  __threadfence_block();
+  __syncthreads();
+  if (tid < 32) {
+    int se;
+    if (in_smem) se = pslam_sort::warp_std_sort_prefix(a, reinterpret_cast<unsigned short*>(s_l + smem_cap), n, n, RowLess());
+    else se = pslam_sort::warp_std_sort_prefix(a, g_rpos, n, n, RowLess());
+    if (tid == 0) s_end = se;
+  }
+  __threadfence_block();
+  __syncthreads();
+  pslam_sort::block_final_positions<LB_THREADS>(a, s_end, n, lattice, RowLess());
 }
 
 __device__ __forceinline__ void top2_insert(unsigned& k1, unsigned& k2, unsigned k) {
@@ -317,11 +329,14 @@ int pslam_k_projective_set_fixed(pslam_ctx* ctx, int n_fixed, const float* h_coo
     return pslam_set_error(ctx, PSLAM_E_INVALID, "projective: int16 lattice needs < 32767 fixed points", cudaSuccess);
   PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(st.d_fixed, h_coords, sizeof(float) * dim * (size_t) n_fixed, cudaMemcpyHostToDevice, ctx->stream));
   PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(st.d_desc_fixed, h_desc, 32 * (size_t) n_fixed, cudaMemcpyHostToDevice, ctx->stream));
-  const int smem_cap = 16384;
-  const size_t smem = 8 * (size_t) (n_fixed < smem_cap ? n_fixed : smem_cap);
+  // 10 B per element in shared memory (key + stopper position); clouds above the cap sort in global memory (key1 / key2 of
+  // the finder cache are free until the next match)
+  const int smem_cap = n_fixed <= 4096 ? 4096 : (n_fixed <= 16384 ? 16384 : 0);
+  const size_t smem = 10 * (size_t) smem_cap;
   if (smem > 48 * 1024)
     PSLAM_CUDA_TRY(ctx, cudaFuncSetAttribute(lattice_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-  lattice_build_kernel<<<1, 32, smem, ctx->stream>>>(st.d_fixed, dim, n_fixed, st.d_lattice, smem_cap);
+  lattice_build_kernel<<<1, LB_THREADS, smem, ctx->stream>>>(st.d_fixed, dim, n_fixed, st.d_lattice, smem_cap, st.d_key1,
+                                                             reinterpret_cast<unsigned*>(st.d_key2));
   PSLAM_LAUNCH_CHECK(ctx, "lattice_build_kernel");
   return PSLAM_OK;
 }

@@ -99,6 +99,14 @@ int psp_set_device(int device) {
   });
 }
 
+// per-kernel device timing of the process-wide context (pslam_profile_*): tools/aligner_probe.py, bench.py
+int psp_profile_enable(int enable) {
+  return guard([&] { return pslam_profile_enable(PslamDevice::context(), enable); });
+}
+int psp_profile_read(int capacity, char* names, int name_len, double* total_ms, long long* launches) {
+  return guard([&] { return pslam_profile_read(PslamDevice::context(), capacity, names, name_len, total_ms, launches); });
+}
+
 psp_manager* psp_manager_create(void) {
   registerTypes();
   return new psp_manager();
