@@ -411,9 +411,13 @@ __device__ __noinline__ double pose_prior_accumulate_dev(const PriorParams& pr, 
 // in shared memory, the Cholesky advances one column per step, the triangular solves one unknown per step.
 struct GnWork {
   double H[36], b[6], L[36], dx[6], R[9], t[3];
-  double ER[9], Et[3], e6[6], J[36], OJ[36], Oe[6], D[9], q[4];
+  double ER[9], Et[3], e6[6], J[36], OJ[36], Oe[6], pw;  // pose-prior scratch (its own warp)
+  double Hp[36], bp[6];                                    // the prior's contribution to H, b for the current pose
+  double D[9], q[4];
 };
 
+// writes the prior's terms for the pose S.R, S.t into S.Hp, S.bp (the caller adds them to H, b: the same two additions
+// pose_prior_accumulate_dev makes)
 __device__ __forceinline__ void pose_prior_accumulate_warp(const PriorParams& pr, GnWork& S, int lane) {
   if (lane < 9) {
     const int i = lane / 3, j = lane % 3;
@@ -426,7 +430,7 @@ __device__ __forceinline__ void pose_prior_accumulate_warp(const PriorParams& pr
   if (lane == 0) {
     t2tnq_dev(S.ER, S.Et, S.e6);
     const double n2 = S.e6[3] * S.e6[3] + S.e6[4] * S.e6[4] + S.e6[5] * S.e6[5];
-    S.q[0] = sqrt(n2 < 1.0 ? 1.0 - n2 : 0.0);
+    S.pw = sqrt(n2 < 1.0 ? 1.0 - n2 : 0.0);
   }
   __syncwarp();
   for (int el = lane; el < 36; el += 32) {  // J = blockdiag(R_E, w I + [v]x)
@@ -435,7 +439,7 @@ __device__ __forceinline__ void pose_prior_accumulate_warp(const PriorParams& pr
     if (k < 3 && j < 3) {
       v = S.ER[3 * k + j];
     } else if (k >= 3 && j >= 3) {
-      const double w = S.q[0], vx = S.e6[3], vy = S.e6[4], vz = S.e6[5];
+      const double w = S.pw, vx = S.e6[3], vy = S.e6[4], vz = S.e6[5];
       const double Q[9] = {w, -vz, vy, vz, w, -vx, -vy, vx, w};
       v = Q[3 * (k - 3) + (j - 3)];
     }
@@ -457,13 +461,13 @@ __device__ __forceinline__ void pose_prior_accumulate_warp(const PriorParams& pr
   if (lane < 6) {
     double bs = 0;
     for (int k = 0; k < 6; ++k) bs += S.J[6 * k + lane] * S.Oe[k];
-    S.b[lane] += bs;
+    S.bp[lane] = bs;
   }
   for (int el = lane; el < 36; el += 32) {
     const int a = el / 6, c = el % 6;
     double hs = 0;
     for (int k = 0; k < 6; ++k) hs += S.J[6 * k + a] * S.OJ[6 * k + c];
-    S.H[el] += hs;
+    S.Hp[el] = hs;
   }
   __syncwarp();
 }
@@ -610,6 +614,8 @@ gn_iterate_kernel(LinParams c0, PriorParams prior, double damping, int n_iters, 
     for (int i = 0; i < 9; ++i) c.R[i] = S.R[i];
 #pragma unroll
     for (int i = 0; i < 3; ++i) c.t[i] = S.t[i];
+    // the prior only depends on the pose: the last warp evaluates it while the others linearise the correspondences
+    if (prior.enabled && wid == LZ_THREADS / 32 - 1) pose_prior_accumulate_warp(prior, S, lane);
     if (warp_has_work || !resident) {
       double acc[LZ_NACC];
 #pragma unroll
@@ -642,8 +648,11 @@ gn_iterate_kernel(LinParams c0, PriorParams prior, double damping, int n_iters, 
         S.H[el] = s_sum[lo * 6 - lo * (lo - 1) / 2 + (hi - lo)];
       }
       if (lane < 6) S.b[lane] = s_sum[21 + lane];
+      if (prior.enabled) {
+        for (int el = lane; el < 36; el += 32) S.H[el] += S.Hp[el];
+        if (lane < 6) S.b[lane] += S.bp[lane];
+      }
       __syncwarp();
-      if (prior.enabled) pose_prior_accumulate_warp(prior, S, lane);
       const bool ok = gn_solve_update_warp(S, damping, lane);  // leaves the pose untouched when H + damping I is not SPD
       double* o = out + (size_t) it * GN_OUT;
       if (lane < 12) o[lane] = (lane & 3) == 3 ? S.t[lane >> 2] : S.R[3 * (lane >> 2) + (lane & 3)];
