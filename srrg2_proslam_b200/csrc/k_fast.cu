@@ -822,9 +822,13 @@ int pslam_k_fast_blur(pslam_ctx* ctx, const uint8_t* d_images, long long image_p
   int wpc = wpc_env > 0 ? wpc_env : n_strips;
   if (wpc > n_strips) wpc = n_strips;
   const size_t smem = (size_t) wpc * WARP_SMEM;
-  if (smem > ctx->k1_smem_set) {
+  // the limit is a property of the FUNCTION (per device), shared by every context of the process: it is only ever raised --
+  // a per-context cache would let one context lower it under another one's launches ("invalid argument")
+  static size_t k1_smem_limit[64] = {0};
+  const int dev_slot = ctx->device & 63;
+  if (smem > 48 * 1024 && smem > k1_smem_limit[dev_slot]) {
     PSLAM_CUDA_TRY(ctx, cudaFuncSetAttribute(fast_blur_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    ctx->k1_smem_set = smem;
+    k1_smem_limit[dev_slot] = smem;
   }
   dim3 grid(n_bands, n_images, (n_strips + wpc - 1) / wpc);
   fast_blur_rows_kernel<<<grid, 32 * wpc, smem, ctx->stream>>>(a);

@@ -356,6 +356,7 @@ void pslam_destroy(pslam_ctx* ctx) {
   for (void* b : bufs)
     if (b) cudaFree(b);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  if (ctx->h_frame_stage) cudaFreeHost(ctx->h_frame_stage);
   for (int i = 0; i < ctx->prof_cap; ++i) cudaEventDestroy(ctx->prof_ev[i]);
   free(ctx->prof_ev);
   free(ctx->prof_name);
@@ -723,25 +724,61 @@ int pslam_stereo_adaptor(pslam_ctx* ctx, const uint8_t* left, const uint8_t* rig
   int rc = validate_extract(ctx, 2, rows, cols, ecfg);
   if (rc) return rc;
   PSLAM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  int d_stride = 0, d_stride_r = 0;
-  if ((rc = upload_one(ctx, 0, left, rows, cols, stride, &d_stride))) return rc;
-  if ((rc = upload_one(ctx, 1, right, rows, cols, stride, &d_stride_r))) return rc;  // same stride, same decision
+  // Per-frame latency path (one call per stereo frame of a sequence).  The images go through a pinned staging buffer so
+  // that the copy of the left image is on the wire while the host stages the right one (a pageable cudaMemcpyAsync blocks
+  // the host for its whole duration); the result comes back as the packed block of the batch path -- measurement
+  // coordinates, left-feature intensity and descriptor gathered on the device -- with the capacity flags in ONE
+  // synchronisation instead of six.
+  const size_t M = ctx->lim.max_features;
+  const size_t img_bytes = (size_t) (rows - 1) * stride + cols;
+  const bool linear = stride >= cols && img_bytes <= ctx->img_slot;
+  const size_t res_bytes = 512 + (sizeof(float4) + 32 + sizeof(float)) * M + 3 * 256;
+  const size_t need = 2 * ctx->img_slot + res_bytes;
+  if (!ctx->h_frame_stage || ctx->frame_stage_bytes < need) {
+    if (ctx->h_frame_stage) cudaFreeHost(ctx->h_frame_stage);
+    ctx->h_frame_stage = nullptr;
+    PSLAM_CUDA_TRY(ctx, cudaMallocHost((void**) &ctx->h_frame_stage, need));
+    ctx->frame_stage_bytes = need;
+  }
+  int d_stride = ctx->img_pitch;
+  if (linear) {
+    uint8_t* hs = ctx->h_frame_stage;
+    memcpy(hs, left, img_bytes);
+    PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_images, hs, img_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    memcpy(hs + ctx->img_slot, right, img_bytes);
+    PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_images + ctx->img_slot, hs + ctx->img_slot, img_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    d_stride = stride;
+  } else {
+    int d_stride_r = 0;
+    if ((rc = upload_one(ctx, 0, left, rows, cols, stride, &d_stride))) return rc;
+    if ((rc = upload_one(ctx, 1, right, rows, cols, stride, &d_stride_r))) return rc;  // same stride, same decision
+  }
   if ((rc = run_extract(ctx, ctx->d_images, (long long) ctx->img_slot, 2, rows, cols, d_stride, ecfg, nullptr))) return rc;
   if ((rc = pslam_k_epipolar(ctx, 1, mcfg, 0))) return rc;
-  std::vector<int> li((size_t) ctx->lim.max_features);
-  const int n = pslam_download_stereo_points(ctx, 0, capacity, uvuv, li.data(), nullptr, nullptr);
-  if (n < 0) return n;
+  pslam_packed_stereo pk;
+  if ((rc = pslam_k_pack_stereo(ctx, 1, &pk))) return rc;
+  // [flags | offsets] [uvuv] [desc] [intensity]: the three regions are carved back to back by pslam_k_pack_stereo
+  uint8_t* hr = ctx->h_frame_stage + 2 * ctx->img_slot;
+  const size_t blk = (size_t) ((uint8_t*) pk.d_left - (uint8_t*) pk.d_uvuv);  // uvuv + desc + intensity regions (256-aligned)
+  if (256 + 256 + blk > res_bytes) return pslam_set_error(ctx, PSLAM_E_CAPACITY, "stereo_adaptor: result staging too small", cudaSuccess);
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(hr, ctx->d_flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(hr + 256, pk.d_offsets, 2 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(hr + 512, pk.d_uvuv, blk, cudaMemcpyDeviceToHost, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  const int flags = *reinterpret_cast<const int*>(hr);
+  if (flags) {
+    char msg[160];
+    snprintf(msg, sizeof(msg), "capacity exceeded (flags=%d: 1 max_raw_per_bin, 2 max_features, 4 candidates)", flags);
+    PSLAM_CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_flags, 0, sizeof(int), ctx->stream));
+    return pslam_set_error(ctx, PSLAM_E_CAPACITY, msg, cudaSuccess);
+  }
+  const int n = (int) reinterpret_cast<const long long*>(hr + 256)[1];
   const int m = n < capacity ? n : capacity;
-  if (m > 0 && (intensity || desc)) {
-    // descriptor + intensity of the LEFT feature (stereo_projective.cpp:114-116): gather on the host
-    std::vector<float> inten((size_t) ctx->lim.max_features);
-    std::vector<uint8_t> d(32 * (size_t) ctx->lim.max_features);
-    const int nl = pslam_download_features(ctx, 0, ctx->lim.max_features, nullptr, nullptr, inten.data(), d.data());
-    if (nl < 0) return nl;
-    for (int i = 0; i < m; ++i) {
-      if (intensity) intensity[i] = inten[li[i]];
-      if (desc) memcpy(desc + 32 * (size_t) i, d.data() + 32 * (size_t) li[i], 32);
-    }
+  if (m > 0) {
+    const uint8_t* base = hr + 512;
+    if (uvuv) memcpy(uvuv, base, sizeof(float4) * (size_t) m);
+    if (desc) memcpy(desc, base + ((uint8_t*) pk.d_desc - (uint8_t*) pk.d_uvuv), 32 * (size_t) m);
+    if (intensity) memcpy(intensity, base + ((uint8_t*) pk.d_intensity - (uint8_t*) pk.d_uvuv), sizeof(float) * (size_t) m);
   }
   return n;
 }

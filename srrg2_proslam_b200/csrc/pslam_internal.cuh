@@ -93,6 +93,8 @@ struct pslam_ctx {
   size_t scratch_bytes;
   void* h_pinned;  // small pinned staging (counts, flags, H/b)
   size_t pinned_bytes;
+  uint8_t* h_frame_stage;  // per-frame adaptor: pinned staging of the two images + the packed result (allocated on first use)
+  size_t frame_stage_bytes;
   // projective finder cache (fixed cloud + row-sorted lattice, moving cloud): its OWN allocation (made on first use), so
   // that no other entry point's scratch use can clobber it; the epochs change with every upload and are unique per
   // process, so a caller can tell whether the cache still holds what IT uploaded (pslam_projective_cache_epochs)
