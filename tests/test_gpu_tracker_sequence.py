@@ -237,3 +237,139 @@ def test_kitti_00_to_04_tracker_with_merger(oracle, variant):
     assert abs(e[0]) < bound_x and abs(e[1]) < 0.2 and abs(e[2]) < 0.7 and np.all(np.abs(e[3:]) < 0.01), e
     assert len(S["xyz"]) > 150 and n_updates > 40
     print(f"KITTI 00->04 tracker + merger ({variant}): final error {np.round(e, 4)}, scene {len(S['xyz'])} landmarks, {n_updates} merges")
+
+
+def test_icl_00_to_50_tracker(oracle):
+    """tests/test_trackers.cpp:90-161 (ICL 00To50_Tracker_ProjectiveBruteforce): icl.conf's tracker as shipped -- RGB-D adaptor
+    (depth scale 1.0 "test only"), SceneClipperProjective3D, the conf's aligner (depth slice + ProjectiveCircle3D3D finder +
+    motion-model slice, inlier-only runs), MergerProjectiveDepthEKF with the depth EKF -- over frames 00, 01 and 50, same
+    restated per-frame chain and lock-step comparison with the CPU path as above.  Bounds of the reference test:
+    |t| < 0.02 m, |q| < 0.01 on t2tnq(robotInLocalMap^-1 * camera_50_in_00)."""
+    from srrg2_proslam_b200 import plugin as P
+    from aligner_fixtures import icl as icl_fixture
+    from scene_fixtures import K_ICL, unproject
+    R_, C_ = 480, 640
+    m = P.Manager(GOLDEN / "configurations" / "icl_hotpath.conf")
+    al = m.get("aligner")
+    sl = m.get("aligner_slice_processor_projective_depth")
+    finder = sl.link("finder")
+    assert finder.class_name == "CorrespondenceFinderProjectiveCircle3D3D"
+    pr = sl.link("projector")
+    pr.set_camera_matrix(K_ICL)
+    pr.set("canvas_rows", R_).set("canvas_cols", C_)
+    rmin, rmax = pr.get("range_min"), pr.get("range_max")
+    ad = [x for x in m.modules() if x.class_name == "RawDataPreprocessorMonocularDepth"][0]
+    ad.set("depth_scaling_factor_to_meters", 1.0)  # :112
+    clipper = m.get("clipper_projective_depth")
+    cpr = clipper.link("projector")
+    cpr.set_camera_matrix(K_ICL)
+    cpr.set("canvas_rows", R_).set("canvas_cols", C_)
+    mg = [x for x in m.modules() if x.class_name == "MergerProjectiveDepthEKF"][0]
+    mpr = mg.link("projector")
+    mpr.set_camera_matrix(K_ICL)
+    mpr.set("canvas_rows", R_).set("canvas_cols", C_)
+    est = mg.link("landmark_estimator")
+    est.link("filter").filter_set_camera(K_ICL)
+    row_bins, col_bins = int(mg.get("number_of_row_bins")), int(mg.get("number_of_col_bins"))
+    gate, max_d2 = float(mg.get("maximum_distance_appearance")), float(est.get("maximum_distance_geometry_meters_squared"))
+    rob = sl.link("robustifier")
+    diag = [float(v) for v in sl.get_numbers("diagonal_info_matrix")]
+    solver = al.link("solver")
+    of = O.ProjectiveFinder(K_ICL, R_, C_, "circle", max_desc_dist=finder.get("maximum_descriptor_distance"),
+                            ratio=finder.get("maximum_distance_ratio_to_second_best"),
+                            min_matching_ratio=finder.get("minimum_matching_ratio"),
+                            min_desc_dist=finder.get("minimum_descriptor_distance"),
+                            desc_step=finder.get("descriptor_distance_step_size_pixels"),
+                            max_radius=int(finder.get("maximum_search_radius_pixels")),
+                            min_radius=int(finder.get("minimum_search_radius_pixels")),
+                            radius_step=int(finder.get("search_radius_step_size_pixels")),
+                            min_iterations=int(finder.get("minimum_number_of_iterations")),
+                            max_change_norm=finder.get("maximum_estimate_change_norm_for_convergence"),
+                            iters_per_projection=int(finder.get("number_of_solver_iterations_per_projection")),
+                            range_min=rmin, range_max=rmax)
+    ecfg = O.extract_cfg(threshold=5, target=500)  # icl.conf extractor of the adaptor (fixture values, tests/fixtures.hpp:567-571)
+    ident = np.eye(3, 4, dtype=np.float32).reshape(12)
+    S = {"xyz": np.zeros((0, 3), np.float32), "state": np.zeros((0, 3), np.float32), "desc": np.zeros((0, 32), np.uint8),
+         "n_opt": np.zeros(0, np.int32), "cov": np.zeros((0, 3, 3), np.float32)}
+    T = []
+
+    def add_points(meas, winners, T_k):  # MergerProjectiveDepthEKF::_adaptFromMeasurementToScene = the unprojector
+        p = unproject(meas["uvz"][winners], K_ICL)
+        in_scene = transform(T_k, p)
+        n = len(p)
+        S["xyz"] = np.concatenate([S["xyz"], in_scene])
+        S["state"] = np.concatenate([S["state"], in_scene])
+        S["desc"] = np.concatenate([S["desc"], meas["desc"][winners]])
+        S["n_opt"] = np.concatenate([S["n_opt"], np.zeros(n, np.int32)])
+        S["cov"] = np.concatenate([S["cov"], np.tile(np.eye(3, dtype=np.float32), (n, 1, 1))])
+
+    for k, frame in enumerate((0, 1, 50)):
+        depth = (O.load_depth(f"icl_image_depth_{frame}.png").astype(np.float32) * np.float32(1e-3)).astype(np.float32)
+        img = O.load_gray(f"icl_image_rgb_{frame}.png")
+        meas = ad.mono_depth_adaptor(img, depth)
+        o_meas = O.mono_depth_adaptor(img, depth, O.extract_cfg(threshold=int(ad.link("feature_extractor").get("detector_threshold")),
+                                                               target=int(ad.link("feature_extractor").get("target_number_of_keypoints"))), 1.0)
+        assert np.array_equal(meas["uvz"], o_meas["uvd"]) and np.array_equal(meas["desc"], o_meas["desc"]) and len(meas["uvz"]) > 100
+        uvz = meas["uvz"]
+        if k == 0:
+            sel, win = mg.merger_plan(uvz, np.zeros(0, np.int32), np.zeros(0, np.float32))
+            o_win = O.merger_select_additions(uvz, None, R_, C_, row_bins, col_bins, True, "depth")
+            assert np.array_equal(win, o_win) and len(win) > 50
+            T.append(ident.astype(np.float64))
+            add_points(meas, win, T[0])
+            continue
+        last = T[-1]
+        clipper.clipper_set_full_scene(S["xyz"], S["desc"])
+        clipper.clipper_set_robot_in_local_map(last)
+        clipper.clipper_set_sensor_in_robot(ident)
+        clip = clipper.clipper_compute()
+        o_clip = O.scene_clip(S["xyz"], np.asarray(last, np.float32), K_ICL, R_, C_, cpr.get("range_min"), cpr.get("range_max"),
+                              sensor_in_robot=ident)
+        assert np.array_equal(clip["index"], o_clip[2]) and np.array_equal(clip["xyz"], o_clip[0]) and len(clip["index"]) > 30
+        chunk = ident.reshape(1, 12) if k == 1 else np.stack([O.pose_mul(O.pose_inverse(last), T[-2]), ident]).astype(np.float32)
+        pred = O.constant_velocity_prediction(list(chunk))
+        n_opt_clip = S["n_opt"][clip["index"]]
+        al.aligner_set_fixed(uvz, meas["desc"])
+        al.aligner_set_moving(clip["xyz"], clip["desc"], n_opt_clip)
+        al.aligner_set_moving_in_fixed(ident)
+        al.aligner_set_trajectory_chunk(chunk)
+        g = al.aligner_compute()
+        of.set_fixed(uvz, meas["desc"])
+        of.set_moving(clip["xyz"], clip["desc"])
+        o = O.align(of, "depth", K_ICL, R_, C_, uvz, clip["xyz"], diag, n_opt=n_opt_clip, chi_threshold=rob.get("chi_threshold"),
+                    max_iterations=int(al.get("max_iterations")), damping=0.1, min_num_inliers=int(al.get("min_num_inliers")),
+                    min_num_correspondences=int(sl.get("min_num_correspondences")), init_pose=pred, prior=(pred, np.eye(6)),
+                    enable_inlier_only_runs=bool(al.get("enable_inlier_only_runs")),
+                    keep_only_inlier_correspondences=bool(al.get("keep_only_inlier_correspondences")))
+        assert g["status"] == o["status"] == O.ALIGNER_STATUS["Success"], (k, g["status"], o["status"])
+        assert np.array_equal(g["stats"][:, :3], o["stats"][:, :3]), k
+        assert all(np.array_equal(a, b) for a, b in zip(g["corr"], o["corr"])), k
+        d = O.t2tnq(O.pose_mul(O.pose_inverse(o["pose"]), g["pose"]))
+        assert np.abs(d).max() < 1e-6, (k, d)
+        T_k = O.pose_mul(last, O.pose_inverse(g["pose"]))
+        T.append(T_k)
+        T32 = np.asarray(T_k, np.float32)
+        c_meas, c_scene, c_resp = g["corr"][0], clip["index"][g["corr"][1]], g["corr"][2]
+        sel, win = mg.merger_plan(uvz, c_meas, c_resp)
+        o_sel, o_occ = O.merger_select_updates(uvz, c_meas, c_resp, R_, C_, row_bins, col_bins, gate, True, "depth")
+        o_win = O.merger_select_additions(uvz, o_occ, R_, C_, row_bins, col_bins, True, "depth")
+        assert np.array_equal(sel, o_sel) and np.array_equal(win, o_win) and sel.sum() > 5
+        si, mi = c_scene[sel], c_meas[sel]
+        est.estimator_set_transforms(T32, T32)
+        gs, gc, gl, gin, _ = est.estimator_compute_batch(S["state"][si], S["cov"][si], uvz[mi])
+        os_, oc, ol, oin = O.landmarks_ekf_update("projective_depth", K_ICL, (0.0, 0.0), T32, T32, S["state"][si], S["cov"][si], uvz[mi],
+                                                  min_cov=est.get("minimum_state_element_covariance"),
+                                                  max_cov_norm2=est.get("maximum_covariance_norm_squared"), max_dist2=max_d2)
+        assert np.array_equal(gin, oin)
+        assert np.allclose(gs[gin], os_[oin], rtol=2e-6, atol=2e-6) and np.allclose(gc[gin], oc[oin], rtol=1e-4, atol=1e-6)
+        S["cov"][si[gin]] = gc[gin]
+        S["n_opt"][si[gin]] += 1
+        S["state"][si[gin]] = gs[gin]
+        S["xyz"][si[gin]] = gl[gin]
+        S["desc"][si[gin]] = meas["desc"][mi[gin]]
+        merged = int(gin.sum())
+        if mg.merger_wants_additions(merged, len(uvz), len(c_meas)):
+            add_points(meas, win, T32)
+    e = O.t2tnq(O.pose_mul(O.pose_inverse(T[2]), icl_fixture()["cam_50_in_00"]))
+    assert np.all(np.abs(e[:3]) < 0.02) and np.all(np.abs(e[3:]) < 0.01), e
+    print(f"ICL 00->01->50 tracker + MergerProjectiveDepthEKF: final error {np.round(e, 4)}, scene {len(S['xyz'])} landmarks")
