@@ -416,6 +416,46 @@ struct GnWork {
   double D[9], q[4];
 };
 
+// t2tnq with reciprocal square roots in place of the sqrt + divide pairs (the prior sits on the iteration's critical path
+// next to the linearisation: two fp64 divide sequences less).  Last-bit differences to t2tnq_dev; parity contract 1e-9.
+__device__ __forceinline__ void t2tnq_fast(const double* R, const double* t, double* v6) {
+  v6[0] = t[0];
+  v6[1] = t[1];
+  v6[2] = t[2];
+  double w, x, y, z;
+  const double tr = R[0] + R[4] + R[8];
+  if (tr > 0) {
+    const double a = tr + 1.0, r = rsqrt(a), h = 0.5 * r;  // s = 2 sqrt(a): 0.25 s = 0.5 a r, 1 / s = 0.5 r
+    w = 0.5 * a * r;
+    x = (R[7] - R[5]) * h;
+    y = (R[2] - R[6]) * h;
+    z = (R[3] - R[1]) * h;
+  } else if (R[0] > R[4] && R[0] > R[8]) {
+    const double a = 1.0 + R[0] - R[4] - R[8], r = rsqrt(a), h = 0.5 * r;
+    w = (R[7] - R[5]) * h;
+    x = 0.5 * a * r;
+    y = (R[1] + R[3]) * h;
+    z = (R[2] + R[6]) * h;
+  } else if (R[4] > R[8]) {
+    const double a = 1.0 + R[4] - R[0] - R[8], r = rsqrt(a), h = 0.5 * r;
+    w = (R[2] - R[6]) * h;
+    x = (R[1] + R[3]) * h;
+    y = 0.5 * a * r;
+    z = (R[5] + R[7]) * h;
+  } else {
+    const double a = 1.0 + R[8] - R[0] - R[4], r = rsqrt(a), h = 0.5 * r;
+    w = (R[3] - R[1]) * h;
+    x = (R[2] + R[6]) * h;
+    y = (R[5] + R[7]) * h;
+    z = 0.5 * a * r;
+  }
+  const double rn = rsqrt(w * w + x * x + y * y + z * z);
+  const double sgn = (w < 0) ? -rn : rn;
+  v6[3] = sgn * x;
+  v6[4] = sgn * y;
+  v6[5] = sgn * z;
+}
+
 // writes the prior's terms for the pose S.R, S.t into S.Hp, S.bp (the caller adds them to H, b: the same two additions
 // pose_prior_accumulate_dev makes)
 __device__ __forceinline__ void pose_prior_accumulate_warp(const PriorParams& pr, GnWork& S, int lane) {
@@ -428,7 +468,7 @@ __device__ __forceinline__ void pose_prior_accumulate_warp(const PriorParams& pr
   }
   __syncwarp();
   if (lane == 0) {
-    t2tnq_dev(S.ER, S.Et, S.e6);
+    t2tnq_fast(S.ER, S.Et, S.e6);
     const double n2 = S.e6[3] * S.e6[3] + S.e6[4] * S.e6[4] + S.e6[5] * S.e6[5];
     S.pw = sqrt(n2 < 1.0 ? 1.0 - n2 : 0.0);
   }
@@ -475,12 +515,14 @@ __device__ __forceinline__ void pose_prior_accumulate_warp(const PriorParams& pr
 // (H + damping I) dx = -b by Cholesky, pose <- pose * v2t(dx); S.H, S.b, S.R, S.t in, S.R, S.t, S.dx out.  All 32 lanes call it.
 __device__ __forceinline__ bool gn_solve_update_warp(GnWork& S, double damping, int lane) {
   const unsigned FULLM = 0xffffffffu;
-  const bool row = lane < 6;
+  // rows 0..5 = A = H + damping I; "row" 6 = -b: factorising the augmented matrix leaves y (L y = -b) in that row, column by
+  // column with the same terms in the same order as a separate forward substitution -- which is thereby off the chain
+  const bool row = lane < 7;
   double Ai[6], Li[6];
 #pragma unroll
   for (int j = 0; j < 6; ++j) {
-    Ai[j] = row ? S.H[6 * lane + j] : 0.0;
-    if (row && j == lane) Ai[j] += damping;
+    Ai[j] = lane < 6 ? S.H[6 * lane + j] : (lane == 6 ? -S.b[j] : 0.0);
+    if (lane < 6 && j == lane) Ai[j] += damping;
     Li[j] = 0;
   }
   // Latency is a chain of fp64 sqrt / divide sequences (~260 cycles each on this part): ONE reciprocal square root per
@@ -499,19 +541,18 @@ __device__ __forceinline__ bool gn_solve_update_warp(GnWork& S, double damping, 
     if (!(d > 0)) return false;  // uniform
     const double r = rsqrt(d);
     if (row && lane >= j) {
-      Li[j] = __dmul_rn(s, r);  // row j: d / sqrt(d) = L[j][j]
+      Li[j] = __dmul_rn(s, r);  // row j: d / sqrt(d) = L[j][j]; row 6: y[j]
       if (lane == j) ri = r;
-      S.L[6 * lane + j] = Li[j];
+      if (lane < 6) S.L[6 * lane + j] = Li[j];
     }
     __syncwarp();
   }
-  // forward substitution: one unknown per step, the rows below fold it in right away (same order of terms per row)
-  double si = row ? -S.b[lane] : 0.0, yi = 0;
+  // y[i] sits in lane 6's Li[i]
+  double yi = 0;
 #pragma unroll
   for (int k = 0; k < 6; ++k) {
-    const double yk = __dmul_rn(__shfl_sync(FULLM, si, k), __shfl_sync(FULLM, ri, k));
+    const double yk = __shfl_sync(FULLM, Li[k], 6);
     if (lane == k) yi = yk;
-    if (row && lane > k) si = __dsub_rn(si, __dmul_rn(Li[k], yk));
   }
   // backward substitution: dx[i] = (y[i] - sum_{k > i, ascending} L[k][i] dx[k]) / L[i][i]
 #pragma unroll
@@ -544,20 +585,20 @@ __device__ __forceinline__ bool gn_solve_update_warp(GnWork& S, double damping, 
   }
   __syncwarp();
   if (lane < 9) {
-    const double x = S.q[0], yq = S.q[1], z = S.q[2], w = S.q[3];
-    double v;
-    switch (lane) {
-      case 0: v = __dsub_rn(1.0, __dmul_rn(2.0, __dadd_rn(__dmul_rn(yq, yq), __dmul_rn(z, z)))); break;
-      case 1: v = __dmul_rn(2.0, __dsub_rn(__dmul_rn(x, yq), __dmul_rn(z, w))); break;
-      case 2: v = __dmul_rn(2.0, __dadd_rn(__dmul_rn(x, z), __dmul_rn(yq, w))); break;
-      case 3: v = __dmul_rn(2.0, __dadd_rn(__dmul_rn(x, yq), __dmul_rn(z, w))); break;
-      case 4: v = __dsub_rn(1.0, __dmul_rn(2.0, __dadd_rn(__dmul_rn(x, x), __dmul_rn(z, z)))); break;
-      case 5: v = __dmul_rn(2.0, __dsub_rn(__dmul_rn(yq, z), __dmul_rn(x, w))); break;
-      case 6: v = __dmul_rn(2.0, __dsub_rn(__dmul_rn(x, z), __dmul_rn(yq, w))); break;
-      case 7: v = __dmul_rn(2.0, __dadd_rn(__dmul_rn(yq, z), __dmul_rn(x, w))); break;
-      default: v = __dsub_rn(1.0, __dmul_rn(2.0, __dadd_rn(__dmul_rn(x, x), __dmul_rn(yq, yq)))); break;
-    }
-    S.D[lane] = v;
+    // D = v2t rotation, one element per lane WITHOUT a nine-way branch (it serialised ~1 k cycles per iteration): every
+    // element is base - 2 (A B + C E) with operands picked from (x, y, z, w) by table; for the off-diagonal elements
+    // 0 - 2 ((-p) q + (s r) w) rounds exactly like the serial 2 (p q - s r w) (negation and doubling are exact)
+    //                          D00      D01      D02      D10      D11      D12      D20      D21      D22
+    const signed char iA[9] = {1, 0, 0, 0, 0, 1, 0, 1, 0};
+    const signed char iB[9] = {1, 1, 2, 1, 0, 2, 2, 2, 0};
+    const signed char iC[9] = {2, 2, 1, 2, 2, 0, 1, 0, 1};
+    const signed char iE[9] = {2, 3, 3, 3, 2, 3, 3, 3, 1};
+    const signed char sA[9] = {1, -1, -1, -1, 1, -1, -1, -1, 1};   // sign of A
+    const signed char sC[9] = {1, 1, -1, -1, 1, 1, 1, -1, 1};      // sign of C: +z w in D01 = 2 (xy - zw) means C = +z, ...
+    const double base = (lane == 0 || lane == 4 || lane == 8) ? 1.0 : 0.0;
+    const double A = sA[lane] < 0 ? -S.q[iA[lane]] : S.q[iA[lane]], B = S.q[iB[lane]];
+    const double C = sC[lane] < 0 ? -S.q[iC[lane]] : S.q[iC[lane]], E = S.q[iE[lane]];
+    S.D[lane] = __dsub_rn(base, __dmul_rn(2.0, __dadd_rn(__dmul_rn(A, B), __dmul_rn(C, E))));
   }
   __syncwarp();
   double nv = 0;
@@ -596,6 +637,10 @@ gn_iterate_kernel(LinParams c0, PriorParams prior, double damping, int n_iters, 
   __shared__ double s_sum[LZ_NACC];
   __shared__ GnWork S;
   __shared__ int s_ok;
+  // small problems (the per-frame case): the 31 partial sums of every thread go through shared memory, four threads per sum
+  // add them up -- ~0.5 k cycles instead of the ~1.9 k of a 5-level fp64 shuffle butterfly over 31 values plus the cross-warp pass
+  constexpr int RED_CAP = 96, RED_PITCH = RED_CAP + 1;
+  __shared__ double s_acc[(LZ_NACC - 1) * RED_PITCH];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (threadIdx.x < 9) S.R[threadIdx.x] = c0.R[threadIdx.x];
   if (threadIdx.x < 3) S.t[threadIdx.x] = c0.t[threadIdx.x];
@@ -605,6 +650,7 @@ gn_iterate_kernel(LinParams c0, PriorParams prior, double damping, int n_iters, 
   LinParams c = c0;
   const bool resident = n_corr <= LZ_THREADS;  // at most one correspondence per thread: it stays in registers
   const bool warp_has_work = wid * 32 < n_corr;
+  const bool small = n_corr <= RED_CAP;
   CorrData mine;
   if (resident && (int) threadIdx.x < n_corr)
     mine = load_correspondence(moving_xyz, fixed_meas, fixed_dim, corr_fixed[threadIdx.x], corr_moving[threadIdx.x], info_diag);
@@ -616,7 +662,27 @@ gn_iterate_kernel(LinParams c0, PriorParams prior, double damping, int n_iters, 
     for (int i = 0; i < 3; ++i) c.t[i] = S.t[i];
     // the prior only depends on the pose: the last warp evaluates it while the others linearise the correspondences
     if (prior.enabled && wid == LZ_THREADS / 32 - 1) pose_prior_accumulate_warp(prior, S, lane);
-    if (warp_has_work || !resident) {
+    if (small) {
+      if ((int) threadIdx.x < n_corr) {
+        double acc[LZ_NACC];
+#pragma unroll
+        for (int i = 0; i < LZ_NACC; ++i) acc[i] = 0;
+        accumulate_loaded(c, edim, mine, acc, status ? status + threadIdx.x : nullptr);
+#pragma unroll
+        for (int i = 0; i < LZ_NACC - 1; ++i) s_acc[i * RED_PITCH + threadIdx.x] = acc[i];
+      }
+      if (wid < 4) {  // correspondences (<= 96) and the 31 x 4 adders live in warps 0..3: a barrier of their own, the prior
+                      // warp is only waited for at the block barrier below
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int v = threadIdx.x >> 2, part = threadIdx.x & 3;
+        double sum = 0;
+        if (v < LZ_NACC - 1)
+          for (int t = part; t < n_corr; t += 4) sum += s_acc[v * RED_PITCH + t];
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        if (part == 0 && v < LZ_NACC - 1) s_sum[v] = sum;
+      }
+    } else if (warp_has_work || !resident) {
       double acc[LZ_NACC];
 #pragma unroll
       for (int i = 0; i < LZ_NACC; ++i) acc[i] = 0;
@@ -636,12 +702,12 @@ gn_iterate_kernel(LinParams c0, PriorParams prior, double damping, int n_iters, 
       s_part[wid][lane] = 0.0;
     }
     __syncthreads();
-    if (threadIdx.x < LZ_NACC - 1) {
+    if (!small && threadIdx.x < LZ_NACC - 1) {
       double s = 0;
       for (int w = 0; w < LZ_THREADS / 32; ++w) s += s_part[w][threadIdx.x];
       s_sum[threadIdx.x] = s;
     }
-    __syncthreads();
+    if (!small) __syncthreads();
     if (wid == 0) {
       for (int el = lane; el < 36; el += 32) {  // full symmetric H from the 21 upper-triangle sums
         const int a = el / 6, b = el % 6, lo = a < b ? a : b, hi = a < b ? b : a;
