@@ -487,6 +487,33 @@ int pslam_gn_iterate_f32(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, int n_i
 int pslam_gn_step(pslam_ctx* ctx, const double* H36, const double* b6, double damping, double* pose12,
                   double* dx6);
 
+/* One finder phase of an aligner loop in ONE device round trip: the search + filter of pslam_projective_match and, on the
+ * correspondences it finds, `n_iterations` fused solver iterations (pslam_gn_iterate_f32) -- the reference's loop calls
+ * finder->compute() and then linearises / solves until the finder re-projects (MultiAligner3DQR, SURVEY App. E.6;
+ * correspondence_finder_projective_base_impl.cpp:162-178).  Both clouds are the finder's cached fp32 clouds; the
+ * information of a correspondence is diagonal_info x information_scale[moving index] (setupFactor's 1 + log(n_opt) weighting,
+ * aligner_slice_processor_projective.cpp:41-57; pslam_projective_set_moving_weights uploads the table once per moving cloud,
+ * without it every scale is 1).  The solver visits the correspondences in ascending fixed index; factor_status comes back in
+ * the order of the returned correspondences.  A caller that then rejects the correspondences (too few, low matching ratio)
+ * simply ignores the solver outputs. */
+typedef struct pslam_fused_gn {
+  const pslam_linearize_cfg* factor;
+  float diagonal_info[3];
+  int n_iterations;
+  double damping;
+  double pose12[12];             /* in: estimate (moving in fixed); out: after the last completed iteration */
+  const pslam_pose_prior* prior; /* or NULL */
+  double* poses12;               /* out [n_iterations][12], may be NULL */
+  double* stats4;                /* out [n_iterations][4]: chi, inliers, outliers, suppressed; may be NULL */
+  unsigned char* factor_status;  /* out [capacity], may be NULL */
+  int iterations_done;           /* out */
+  int spd;                       /* out: 0 when H + damping I was not positive definite in the last iteration */
+} pslam_fused_gn;
+int pslam_projective_set_moving_weights(pslam_ctx* ctx, int n_moving, const float* information_scale);
+int pslam_projective_match_gn(pslam_ctx* ctx, int n_fixed, int n_moving, const float* local_map_in_sensor12,
+                              const pslam_projective_cfg* cfg, int capacity, int* fixed_idx, int* moving_idx,
+                              float* distance, int* n_projected, pslam_fused_gn* gn);
+
 #ifdef __cplusplus
 }
 #endif

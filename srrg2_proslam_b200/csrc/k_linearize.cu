@@ -632,7 +632,8 @@ __global__ void __launch_bounds__(LZ_THREADS)
 gn_iterate_kernel(LinParams c0, PriorParams prior, double damping, int n_iters, const T* __restrict__ moving_xyz,
                   const T* __restrict__ fixed_meas, int fixed_dim, int n_corr, const int* __restrict__ corr_fixed,
                   const int* __restrict__ corr_moving, const T* __restrict__ info_diag, double* __restrict__ out,
-                  int* __restrict__ iters_done, uint8_t* __restrict__ status) {
+                  int* __restrict__ iters_done, uint8_t* __restrict__ status, const int* __restrict__ n_corr_dev) {
+  if (n_corr_dev) n_corr = *n_corr_dev;  // correspondences produced on the device by the launch before (pslam_projective_match_gn)
   __shared__ double s_part[LZ_THREADS / 32][LZ_NACC];
   __shared__ double s_sum[LZ_NACC];
   __shared__ GnWork S;
@@ -881,7 +882,7 @@ int pslam_k_gn_iterate_t(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, int n_i
     PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_info, h_info_diag, 3 * sizeof(T) * (size_t) n_fixed, cudaMemcpyHostToDevice, ctx->stream));
   }
   gn_iterate_kernel<T><<<1, LZ_THREADS, 0, ctx->stream>>>(c, make_prior(prior), damping, n_iters, d_mov, d_fix, fixed_dim, n_corr,
-                                                         d_cf, d_cm, d_info, d_out, d_done, d_status);
+                                                         d_cf, d_cm, d_info, d_out, d_done, d_status, nullptr);
   PSLAM_LAUNCH_CHECK(ctx, "gn_iterate_kernel");
   int h_small[2];
   const int* h = h_small;
@@ -904,6 +905,20 @@ int pslam_k_gn_iterate_t(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, int n_i
   if (done > 0) memcpy(pose12, h_out16 + (size_t) (done - 1) * GN_OUT, sizeof(double) * 12);
   return PSLAM_OK;
 }
+// everything already on the device (fp32 clouds of the projective finder's cache, correspondences + count written by the
+// launch before): launch only.  d_out: n_iters x 16 doubles, d_done: 2 ints, d_status: one byte per correspondence.
+int pslam_k_gn_iterate_dev(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, int n_iters, double damping, const double* pose12,
+                           const float* d_moving_xyz, const float* d_fixed_meas, int fixed_dim, const int* d_n_corr,
+                           const int* d_corr_fixed, const int* d_corr_moving, const float* d_info_diag,
+                           const pslam_pose_prior* prior, double* d_out, int* d_done, uint8_t* d_status) {
+  const LinParams c = make_params(cfg, pose12);
+  gn_iterate_kernel<float><<<1, LZ_THREADS, 0, ctx->stream>>>(c, make_prior(prior), damping, n_iters, d_moving_xyz, d_fixed_meas,
+                                                             fixed_dim, 0, d_corr_fixed, d_corr_moving, d_info_diag, d_out, d_done,
+                                                             d_status, d_n_corr);
+  PSLAM_LAUNCH_CHECK(ctx, "gn_iterate_kernel");
+  return PSLAM_OK;
+}
+
 template int pslam_k_gn_iterate_t<double>(pslam_ctx*, const pslam_linearize_cfg*, int, double, double*, int, const double*, int,
                                           const double*, int, int, const int*, const int*, const double*, const pslam_pose_prior*,
                                           double*, uint8_t*, int*, int*);

@@ -267,6 +267,31 @@ filter_fused_kernel(const int* __restrict__ cand, int n_moving, int n_fixed, uns
   for (int i = tid; i < 4 * n_moving; i += FF_THREADS) cand_out[i] = cand[i];
 }
 
+// correspondences of the filter's result in ascending fixed index + their information diagonals, for the fused solver:
+// acc_moving[f] >= 0  ->  (f, acc_moving[f]); info[3 f + k] = diag[k] * scale[moving]  (setupFactor, fp32 like the host)
+__global__ void __launch_bounds__(FF_THREADS)
+corr_compact_kernel(const int* __restrict__ acc_moving, int n_fixed, const float* __restrict__ scale, float d0, float d1, float d2,
+                    int* __restrict__ cf, int* __restrict__ cm, float* __restrict__ info, int* __restrict__ n_corr) {
+  __shared__ int s_warp[33];
+  int running = 0;
+  for (int base = 0; base < n_fixed; base += FF_THREADS) {
+    const int f = base + threadIdx.x;
+    const int m = f < n_fixed ? acc_moving[f] : -1;
+    int total;
+    const int off = block_exclusive_scan<FF_THREADS>(m >= 0 ? 1 : 0, s_warp, &total);
+    if (m >= 0) {
+      cf[running + off] = f;
+      cm[running + off] = m;
+      const float s = scale ? scale[m] : 1.0f;
+      info[3 * (size_t) f] = __fmul_rn(d0, s);
+      info[3 * (size_t) f + 1] = __fmul_rn(d1, s);
+      info[3 * (size_t) f + 2] = __fmul_rn(d2, s);
+    }
+    running += total;
+  }
+  if (threadIdx.x == 0) *n_corr = running;
+}
+
 }  // namespace
 
 static inline size_t al256(size_t x) { return (x + 255) & ~(size_t) 255; }
@@ -285,6 +310,10 @@ struct ProjState {
   int* d_acc_m;
   float* d_acc_d;
   int* d_nproj;
+  float* d_mscale;            // information scale per moving point (pslam_projective_set_moving_weights)
+  int *d_gn_cf, *d_gn_cm;     // correspondences of the last search in ascending fixed index (fused solver)
+  float* d_gn_info;           // information diagonal per FIXED point
+  int* d_gn_ncorr;
 };
 
 static std::atomic<unsigned long long> g_proj_epoch{0};  // process-wide: epochs of different contexts never coincide
@@ -309,6 +338,11 @@ static int proj_layout(pslam_ctx* ctx, ProjState& st, int n_fixed, int dim, int 
   st.d_moving = (float*) p; p += al256(sizeof(float) * 3 * (size_t) 65536);
   st.d_desc_moving = (uint32_t*) p; p += al256(32 * (size_t) 65536);
   st.d_cand = (int*) p; p += al256(16 * (size_t) 65536);
+  st.d_mscale = (float*) p; p += al256(4 * (size_t) 65536);
+  st.d_gn_cf = (int*) p; p += al256(4 * (size_t) M);
+  st.d_gn_cm = (int*) p; p += al256(4 * (size_t) M);
+  st.d_gn_info = (float*) p; p += al256(12 * (size_t) M);
+  st.d_gn_ncorr = (int*) p; p += 256;
   if ((size_t) (p - ctx->d_proj) > ctx->proj_bytes)
     return pslam_set_error(ctx, PSLAM_E_CAPACITY, "projective: cache allocation too small", cudaSuccess);
   st.n_fixed = n_fixed;
@@ -352,9 +386,19 @@ int pslam_k_projective_set_moving(pslam_ctx* ctx, int n_moving, const float* h_x
   return PSLAM_OK;
 }
 
+int pslam_k_projective_set_moving_weights(pslam_ctx* ctx, int n_moving, const float* h_scale) {
+  ProjState st;
+  int rc = proj_layout(ctx, st, 0, 2, n_moving);
+  if (rc) return rc;
+  if (n_moving > 0)
+    PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(st.d_mscale, h_scale, sizeof(float) * (size_t) n_moving, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->proj_weights_epoch = ctx->proj_moving_epoch;  // (a pageable source is staged before cudaMemcpyAsync returns)
+  return PSLAM_OK;
+}
+
 int pslam_k_projective_match(pslam_ctx* ctx, int n_fixed, int n_moving, const float* pose12,
                              const pslam_projective_cfg* cfg, int capacity, int* h_fixed, int* h_moving,
-                             float* h_dist, int* n_projected) {
+                             float* h_dist, int* n_projected, pslam_fused_gn* gn) {
   ProjState st;
   int rc = proj_layout(ctx, st, n_fixed, 2, n_moving);
   if (rc) return rc;
@@ -391,13 +435,35 @@ int pslam_k_projective_match(pslam_ctx* ctx, int n_fixed, int n_moving, const fl
   filter_fused_kernel<<<1, FF_THREADS, 0, ctx->stream>>>(st.d_cand, n_moving, n_fixed, st.d_key1, st.d_key2, cfg->descriptor_distance,
                                                          cfg->maximum_distance_ratio_to_second_best, d_out);
   PSLAM_LAUNCH_CHECK(ctx, "filter_fused_kernel");
+  // fused solver iterations on the correspondences just found: their block sits directly behind the filter's, ONE download
+  size_t gn_words = 0;  // 4-byte words: [done, spd | pad to 8 B][n_iters x 16 doubles][status bytes, padded]
+  const size_t gn_off = (n_words + 1) & ~(size_t) 1;  // 8-byte aligned
+  int n_gn_iters = 0;
+  if (gn) {
+    if (!gn->factor || gn->n_iterations < 0) return pslam_set_error(ctx, PSLAM_E_INVALID, "match_gn: factor configuration missing", cudaSuccess);
+    n_gn_iters = gn->n_iterations;
+    gn_words = 2 + 32 * (size_t) n_gn_iters + ((size_t) n_fixed + 3) / 4;
+    if (PSLAM_SOLVER_SCRATCH_OFFSET + 4 * (gn_off + gn_words) > ctx->scratch_bytes)
+      return pslam_set_error(ctx, PSLAM_E_CAPACITY, "match_gn: scratch too small", cudaSuccess);
+    const float* scale = ctx->proj_weights_epoch == ctx->proj_moving_epoch ? st.d_mscale : nullptr;
+    corr_compact_kernel<<<1, FF_THREADS, 0, ctx->stream>>>(d_out + 1, n_fixed, scale, gn->diagonal_info[0], gn->diagonal_info[1],
+                                                           gn->diagonal_info[2], st.d_gn_cf, st.d_gn_cm, st.d_gn_info, st.d_gn_ncorr);
+    PSLAM_LAUNCH_CHECK(ctx, "corr_compact_kernel");
+    int* d_done = d_out + gn_off;
+    double* d_gn_out = reinterpret_cast<double*>(d_done + 2);
+    uint8_t* d_status = reinterpret_cast<uint8_t*>(d_gn_out + 16 * (size_t) n_gn_iters);
+    if ((rc = pslam_k_gn_iterate_dev(ctx, gn->factor, n_gn_iters, gn->damping, gn->pose12, st.d_moving, st.d_fixed, ctx->proj_fixed_dim,
+                                     st.d_gn_ncorr, st.d_gn_cf, st.d_gn_cm, st.d_gn_info, gn->prior, d_gn_out, d_done, d_status)))
+      return rc;
+  }
+  const size_t all_words = gn ? gn_off + gn_words : n_words;
   std::vector<int> pageable;
   int* h_out = reinterpret_cast<int*>(ctx->h_pinned);
-  if (4 * n_words > ctx->pinned_bytes) {
-    pageable.resize(n_words);
+  if (4 * all_words > ctx->pinned_bytes) {
+    pageable.resize(all_words);
     h_out = pageable.data();
   }
-  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(h_out, d_out, 4 * n_words, cudaMemcpyDeviceToHost, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(h_out, d_out, 4 * all_words, cudaMemcpyDeviceToHost, ctx->stream));
   PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   const int nproj = h_out[0];
   const int* acc_m = h_out + 1;
@@ -416,6 +482,17 @@ int pslam_k_projective_match(pslam_ctx* ctx, int n_fixed, int n_moving, const fl
       if (fs >= 0) by_fixed.emplace((size_t) fs, 0);
     }
   }
+  // fused solver block: the device list is in ascending fixed index
+  const int* h_gn = gn ? h_out + gn_off : nullptr;
+  const double* h_gn_out = gn ? reinterpret_cast<const double*>(h_gn + 2) : nullptr;
+  const uint8_t* h_status = gn ? reinterpret_cast<const uint8_t*>(h_gn_out + 16 * (size_t) n_gn_iters) : nullptr;
+  std::vector<int> rank_of_fixed;
+  if (gn && gn->factor_status) {
+    rank_of_fixed.assign((size_t) n_fixed, -1);
+    int r = 0;
+    for (int f = 0; f < n_fixed; ++f)
+      if (acc_m[f] >= 0) rank_of_fixed[f] = r++;
+  }
   int n_out = 0;
   for (const auto& kv : by_fixed) {
     const int f = (int) kv.first;
@@ -424,8 +501,19 @@ int pslam_k_projective_match(pslam_ctx* ctx, int n_fixed, int n_moving, const fl
       h_fixed[n_out] = f;
       h_moving[n_out] = acc_m[f];
       h_dist[n_out] = acc_d[f];
+      if (gn && gn->factor_status) gn->factor_status[n_out] = h_status[rank_of_fixed[f]];
     }
     ++n_out;
+  }
+  if (gn) {
+    const int done = h_gn[0];
+    gn->iterations_done = done;
+    gn->spd = h_gn[1];
+    for (int i = 0; i < done; ++i) {
+      if (gn->poses12) memcpy(gn->poses12 + 12 * (size_t) i, h_gn_out + 16 * (size_t) i, sizeof(double) * 12);
+      if (gn->stats4) memcpy(gn->stats4 + 4 * (size_t) i, h_gn_out + 16 * (size_t) i + 12, sizeof(double) * 4);
+    }
+    if (done > 0) memcpy(gn->pose12, h_gn_out + 16 * (size_t) (done - 1), sizeof(double) * 12);
   }
   return n_out;
 }

@@ -1392,6 +1392,19 @@ int pslam_projective_match(pslam_ctx* ctx, int n_fixed, int n_moving, const floa
   PSLAM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   return pslam_k_projective_match(ctx, n_fixed, n_moving, pose12, cfg, capacity, fixed_idx, moving_idx, distance, n_projected);
 }
+int pslam_projective_set_moving_weights(pslam_ctx* ctx, int n_moving, const float* information_scale) {
+  if (!ctx || n_moving < 0 || (n_moving > 0 && !information_scale)) return PSLAM_E_INVALID;
+  PSLAM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  return pslam_k_projective_set_moving_weights(ctx, n_moving, information_scale);
+}
+int pslam_projective_match_gn(pslam_ctx* ctx, int n_fixed, int n_moving, const float* pose12, const pslam_projective_cfg* cfg,
+                              int capacity, int* fixed_idx, int* moving_idx, float* distance, int* n_projected, pslam_fused_gn* gn) {
+  if (!ctx || !pose12 || !cfg || !gn || capacity < 0) return PSLAM_E_INVALID;
+  PSLAM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  gn->iterations_done = 0;
+  gn->spd = 1;
+  return pslam_k_projective_match(ctx, n_fixed, n_moving, pose12, cfg, capacity, fixed_idx, moving_idx, distance, n_projected, gn);
+}
 int pslam_match_projective(pslam_ctx* ctx, int n_fixed, const float* fixed_coords, int fixed_dim,
                            const uint8_t* desc_fixed, int n_moving, const float* moving_xyz,
                            const uint8_t* desc_moving, const float* pose12,

@@ -102,6 +102,7 @@ struct pslam_ctx {
   size_t proj_bytes;
   unsigned long long proj_fixed_epoch, proj_moving_epoch;
   int proj_fixed_dim;  // floats per fixed point of the cached cloud
+  unsigned long long proj_weights_epoch;  // == proj_moving_epoch while the information-scale table belongs to the cached moving cloud
   // geometry of the last batch
   int rows, cols, n_images;
   // optional per-kernel device timing (pslam_profile_*): one CUDA event after every launch; the interval

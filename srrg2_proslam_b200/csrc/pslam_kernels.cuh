@@ -49,9 +49,14 @@ int pslam_k_bf_match(pslam_ctx* ctx, int n_fixed, const uint32_t* d_desc_fixed, 
 int pslam_k_projective_set_fixed(pslam_ctx* ctx, int n_fixed, const float* h_coords, int dim,
                                  const uint8_t* h_desc);
 int pslam_k_projective_set_moving(pslam_ctx* ctx, int n_moving, const float* h_xyz, const uint8_t* h_desc);
+int pslam_k_projective_set_moving_weights(pslam_ctx* ctx, int n_moving, const float* h_scale);
 int pslam_k_projective_match(pslam_ctx* ctx, int n_fixed, int n_moving, const float* pose12,
                              const pslam_projective_cfg* cfg, int capacity, int* h_fixed,
-                             int* h_moving, float* h_dist, int* n_projected);
+                             int* h_moving, float* h_dist, int* n_projected, pslam_fused_gn* gn = nullptr);
+int pslam_k_gn_iterate_dev(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, int n_iters, double damping, const double* pose12,
+                           const float* d_moving_xyz, const float* d_fixed_meas, int fixed_dim, const int* d_n_corr,
+                           const int* d_corr_fixed, const int* d_corr_moving, const float* d_info_diag,
+                           const pslam_pose_prior* prior, double* d_out, int* d_done, uint8_t* d_status);
 
 // k_linearize.cu  (T = float | double: scalar type of the clouds)
 template <typename T>

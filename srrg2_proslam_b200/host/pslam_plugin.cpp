@@ -460,9 +460,55 @@ void CorrespondenceFinderProjectiveCUDA::compute() {
   std::vector<int> f(cap), m(cap);
   std::vector<float> d(cap);
   int n_projected = 0;
-  const int n = pslam_projective_match(ctx, (int) _fixed->size(), (int) _moving->size(), _local_map_in_sensor.m, &cfg, cap,
-                                       f.data(), m.data(), d.data(), &n_projected);
-  PslamDevice::check(n, "CorrespondenceFinderProjective::compute");
+  int n;
+  if (_fused && _fused->factor && _fused->max_fused > 0) {
+    // the aligner runs this iteration and the following "quiet" ones (calls that keep these correspondences, :162-178) in the
+    // same device round trip as the search.  State AFTER this call, as the lines below will set it:
+    const bool converged_after = estimate_change_norm < param_maximum_estimate_change_norm_for_convergence.value() &&
+                                 _current_iteration > param_minimum_number_of_iterations.value();
+    int quiet = 0;
+    if (converged_after) {
+      quiet = 1 << 30;
+    } else {
+      const size_t N = param_number_of_solver_iterations_per_projection.value();
+      for (size_t it = _current_iteration + 1; !(it % N == 0 || it == 1); ++it) ++quiet;
+    }
+    const int n_fused = quiet >= _fused->max_fused ? _fused->max_fused : quiet + 1;
+    if (_fused->moving_scale) {
+      unsigned long long fe = 0, me = 0;
+      pslam_projective_cache_epochs(ctx, &fe, &me);
+      if (_device_weights_of != _fused->moving_scale || _device_weights_epoch != me) {
+        PslamDevice::check(pslam_projective_set_moving_weights(ctx, (int) _moving->size(), _fused->moving_scale),
+                           "CorrespondenceFinderProjective::compute");
+        _device_weights_of = _fused->moving_scale;
+        _device_weights_epoch = me;
+      }
+    }
+    pslam_fused_gn g{};
+    g.factor = _fused->factor;
+    for (int i = 0; i < 3; ++i) g.diagonal_info[i] = _fused->diagonal_info[i];
+    g.n_iterations = n_fused;
+    g.damping = _fused->damping;
+    for (int i = 0; i < 12; ++i) g.pose12[i] = _fused->estimate[i];
+    g.prior = _fused->prior;
+    _fused->poses.resize(12 * (size_t) n_fused);
+    _fused->stats.resize(4 * (size_t) n_fused);
+    _fused->status.assign((size_t) cap, 0);
+    g.poses12 = _fused->poses.data();
+    g.stats4 = _fused->stats.data();
+    g.factor_status = _fused->status.data();
+    n = pslam_projective_match_gn(ctx, (int) _fixed->size(), (int) _moving->size(), _local_map_in_sensor.m, &cfg, cap, f.data(),
+                                  m.data(), d.data(), &n_projected, &g);
+    PslamDevice::check(n, "CorrespondenceFinderProjective::compute");
+    _fused->executed = true;
+    _fused->done = g.iterations_done;
+    _fused->spd = g.spd != 0;
+    _fused->status.resize((size_t) std::max(n, 0));
+  } else {
+    n = pslam_projective_match(ctx, (int) _fixed->size(), (int) _moving->size(), _local_map_in_sensor.m, &cfg, cap, f.data(),
+                               m.data(), d.data(), &n_projected);
+    PslamDevice::check(n, "CorrespondenceFinderProjective::compute");
+  }
   ++_number_of_searches;
   if (n_projected == 0) std::cerr << "CorrespondenceFinderProjective::compute|WARNING: all projections failed" << std::endl;
 
@@ -483,6 +529,7 @@ void CorrespondenceFinderProjectiveCUDA::compute() {
       } else {
         ++_current_iteration;
       }
+      if (_fused) _fused->executed = false;  // those solver iterations ran on rejected correspondences
       return compute();  // recursion terminates as soon as the thresholds are saturated
     }
   }
@@ -857,7 +904,15 @@ void AlignerSliceProcessorProjectiveCUDA::bindFixed() {
   }
 }
 
-void AlignerSliceProcessorProjectiveCUDA::setupFactor() {
+void AlignerSliceProcessorProjectiveCUDA::diagonalInfo(float d[3]) const {
+  const std::vector<float>& diag = param_diagonal_info_matrix.value();
+  if ((int) diag.size() != (_kind == 2 ? 2 : 3)) throw std::runtime_error("AlignerSliceProjective_|diagonal_info_matrix has the wrong dimension");
+  d[0] = diag[0];
+  d[1] = diag[1];
+  d[2] = diag.size() > 2 ? diag[2] : 0.f;
+}
+
+void AlignerSliceProcessorProjectiveCUDA::setupFactorConfig() {
   if (!_fixed_slice || !_moving_slice) throw std::runtime_error("AlignerSliceProjective_|fixed / moving slice not set");
   if (!param_projector.value()) throw std::runtime_error("AlignerSliceProjective_|projector not set");
   const ProjectorPinhole& projector = *param_projector.value();
@@ -865,20 +920,6 @@ void AlignerSliceProcessorProjectiveCUDA::setupFactor() {
   for (int i = 0; i < 9; ++i) _factor.K[i] = projector.cameraMatrix()[i];
   _factor.image_cols = projector.param_canvas_cols.value();
   _factor.image_rows = projector.param_canvas_rows.value();
-  const std::vector<float>& diag = param_diagonal_info_matrix.value();
-  if ((int) diag.size() != (_kind == 2 ? 2 : 3)) throw std::runtime_error("AlignerSliceProjective_|diagonal_info_matrix has the wrong dimension");
-  // per-correspondence information, indexed by the FIXED index (.cpp:41-57)
-  _fixed_information_diagonals.resize(3 * _fixed_slice->size());
-  constexpr size_t minimum_number_of_updates = 2;
-  for (const Correspondence& c : _correspondences) {
-    float d[3] = {diag[0], diag[1], diag.size() > 2 ? diag[2] : 0.f};
-    const int n_opt = _moving_slice->number_of_optimizations.empty() ? 0 : _moving_slice->number_of_optimizations[c.moving_idx];
-    if ((size_t) n_opt > minimum_number_of_updates) {
-      const float s = (float) (1 + std::log((double) n_opt));  // Vector3f *= (1 + std::log(size_t)): double, then Scalar
-      for (float& x : d) x *= s;
-    }
-    for (int k = 0; k < 3; ++k) _fixed_information_diagonals[3 * (size_t) c.fixed_idx + k] = d[k];
-  }
   RobustifierBase* rob = param_robustifier.value().get();
   _factor.robustifier = rob ? rob->kind() : 0;
   _factor.chi_threshold = rob ? rob->param_chi_threshold.value() : 0.0;
@@ -894,6 +935,24 @@ void AlignerSliceProcessorProjectiveCUDA::setupFactor() {
     }
     for (int i = 0; i < 3; ++i) _factor.baseline[i] = _baseline_left_in_right_pixelsmeters[i];
     if (param_enable_inverse_depth_weighting.value()) _factor.mean_disparity = _mean_disparity;  // (.cpp:107-112)
+  }
+}
+
+void AlignerSliceProcessorProjectiveCUDA::setupFactor() {
+  setupFactorConfig();
+  float diag[3];
+  diagonalInfo(diag);
+  // per-correspondence information, indexed by the FIXED index (.cpp:41-57)
+  _fixed_information_diagonals.resize(3 * _fixed_slice->size());
+  constexpr size_t minimum_number_of_updates = 2;
+  for (const Correspondence& c : _correspondences) {
+    float d[3] = {diag[0], diag[1], diag[2]};
+    const int n_opt = _moving_slice->number_of_optimizations.empty() ? 0 : _moving_slice->number_of_optimizations[c.moving_idx];
+    if ((size_t) n_opt > minimum_number_of_updates) {
+      const float s = (float) (1 + std::log((double) n_opt));  // Vector3f *= (1 + std::log(size_t)): double, then Scalar
+      for (float& x : d) x *= s;
+    }
+    for (int k = 0; k < 3; ++k) _fixed_information_diagonals[3 * (size_t) c.fixed_idx + k] = d[k];
   }
 }
 
@@ -994,11 +1053,38 @@ void MultiAligner3DQRCUDA::compute() {
       cm[k] = corr[k].moving_idx;
     }
   };
+  // When the finder is one of the projective ones, the solver iterations that follow a search run in the SAME device round
+  // trip as the search (pslam_projective_match_gn): the finder's cached fp32 clouds are the factor's clouds, the information
+  // of a correspondence is diagonal x the per-point scale below (setupFactor's 1 + log(n_opt) weighting).
+  FusedSolveRequest fused;
+  std::vector<float> moving_scale;
+  const bool can_fuse = dynamic_cast<CorrespondenceFinderProjectiveCUDA*>(&finder) != nullptr;
+  if (can_fuse) {
+    slice->setupFactorConfig();
+    fused.factor = &slice->factorConfig();
+    slice->diagonalInfo(fused.diagonal_info);
+    fused.damping = damping;
+    fused.prior = prior;
+    moving_scale.assign(_moving->size(), 1.0f);
+    if (!_moving->number_of_optimizations.empty())
+      for (size_t i = 0; i < _moving->size(); ++i) {
+        const int n_opt = _moving->number_of_optimizations[i];
+        if (n_opt > 2) moving_scale[i] = (float) (1 + std::log((double) n_opt));
+      }
+    fused.moving_scale = moving_scale.data();
+  }
   for (int it = 0; it < max_iterations;) {
     Isometry3f X;
     for (int i = 0; i < 12; ++i) X.m[i] = (float) _estimate[i];
     finder.setLocalMapInSensor(X);
+    if (can_fuse) {
+      fused.executed = false;
+      fused.max_fused = max_iterations - it;
+      for (int i = 0; i < 12; ++i) fused.estimate[i] = _estimate[i];
+      finder.setFusedSolve(&fused);
+    }
     finder.compute();
+    finder.setFusedSolve(nullptr);
     const CorrespondenceVector& corr = slice->correspondences();
     if ((int) corr.size() < std::max(slice->param_min_num_correspondences.value(), 1)) {
       AlignerIterationStats st;
@@ -1008,20 +1094,30 @@ void MultiAligner3DQRCUDA::compute() {
       _stats.push_back(st);
       break;
     }
-    slice->setupFactor();
-    split(corr);
-    // The finder keeps these correspondences for its next `quiet` calls (it only re-projects every N-th solver
-    // iteration, correspondence_finder_projective_base_impl.cpp:162-178): run this iteration and those in ONE launch.
-    const int quiet = finder.callsWithoutNewCorrespondences();
-    const int n_fused = std::min(max_iterations - it, quiet >= max_iterations ? max_iterations : quiet + 1);
-    poses.resize(12 * (size_t) n_fused);
-    stats.resize(4 * (size_t) n_fused);
-    factor_status.resize(corr.size());
-    int done = 0;
-    const int rc = pslam_gn_iterate_f32(ctx, &slice->factorConfig(), n_fused, damping, _estimate.data(), (int) _moving->size(),
-                                        moving_xyz, (int) _fixed->size(), fixed_meas, _fixed->dim, (int) corr.size(), cf.data(),
-                                        cm.data(), slice->informationDiagonals().data(), prior, poses.data(), stats.data(),
-                                        factor_status.data(), &done);
+    int done = 0, rc = PSLAM_OK;
+    if (can_fuse && fused.executed) {
+      done = fused.done;
+      poses = fused.poses;
+      stats = fused.stats;
+      factor_status = fused.status;
+      if (done > 0)
+        for (int i = 0; i < 12; ++i) _estimate[i] = poses[12 * (size_t) (done - 1) + i];
+      if (!fused.spd) rc = PSLAM_E_NOT_SPD;
+    } else {
+      slice->setupFactor();
+      split(corr);
+      // The finder keeps these correspondences for its next `quiet` calls (it only re-projects every N-th solver
+      // iteration, correspondence_finder_projective_base_impl.cpp:162-178): run this iteration and those in ONE launch.
+      const int quiet = finder.callsWithoutNewCorrespondences();
+      const int n_fused = std::min(max_iterations - it, quiet >= max_iterations ? max_iterations : quiet + 1);
+      poses.resize(12 * (size_t) n_fused);
+      stats.resize(4 * (size_t) n_fused);
+      factor_status.resize(corr.size());
+      rc = pslam_gn_iterate_f32(ctx, &slice->factorConfig(), n_fused, damping, _estimate.data(), (int) _moving->size(),
+                                moving_xyz, (int) _fixed->size(), fixed_meas, _fixed->dim, (int) corr.size(), cf.data(),
+                                cm.data(), slice->informationDiagonals().data(), prior, poses.data(), stats.data(),
+                                factor_status.data(), &done);
+    }
     push_stats(_stats, it, done, (int) corr.size());
     if (rc == PSLAM_E_NOT_SPD) break;  // degenerate system: keep the last estimate
     PslamDevice::check(rc, "MultiAligner::compute");

@@ -200,8 +200,29 @@ protected:
 };
 
 // ---- descriptor-based finders (registration/correspondence_finders/correspondence_finder_descriptor_based_*.h) --
+// Request of the aligner loop to run its next solver iterations inside the finder's device round trip
+// (pslam_projective_match_gn): filled by MultiAligner3DQRCUDA before finder->compute(), honoured by the projective finders
+// when that call searches; every other finder (and every call that keeps its correspondences) leaves `executed` false and
+// the aligner runs the iterations with its own launch.
+struct FusedSolveRequest {
+  const pslam_linearize_cfg* factor = nullptr;
+  float diagonal_info[3] = {0, 0, 0};
+  double damping = 0;
+  double estimate[12] = {0};
+  const pslam_pose_prior* prior = nullptr;
+  int max_fused = 0;                  // iterations left in the aligner loop
+  const float* moving_scale = nullptr;  // per moving point: 1 + log(n_opt) weighting of setupFactor (or 1)
+  // results
+  bool executed = false;
+  bool spd = true;
+  int done = 0;
+  std::vector<double> poses, stats;
+  std::vector<uint8_t> status;
+};
+
 class CorrespondenceFinderBase : public Configurable {
 public:
+  virtual void setFusedSolve(FusedSolveRequest* r) { (void) r; }
   void setFixed(const PointIntensityDescriptorCloud* fixed) {
     _fixed = fixed;
     _fixed_changed_flag = true;
@@ -277,6 +298,7 @@ public:
   size_t currentIteration() const { return _current_iteration; }
   int numberOfSearches() const { return _number_of_searches; }
   int callsWithoutNewCorrespondences() const override;
+  void setFusedSolve(FusedSolveRequest* r) override { _fused = r; }
   int shape() const { return _shape; }
 
 private:
@@ -289,6 +311,9 @@ private:
   size_t _current_iteration = 0;
   int _number_of_searches = 0;
   unsigned long long _device_fixed_epoch = 0, _device_moving_epoch = 0;  // stamps of OUR uploads into the shared device cache
+  FusedSolveRequest* _fused = nullptr;
+  const float* _device_weights_of = nullptr;        // scale table uploaded for ...
+  unsigned long long _device_weights_epoch = 0;     // ... this moving-cloud epoch
 };
 
 // ---- measurement adaptors (sensor_processing/raw_data_preprocessor_{stereo_projective,monocular_depth}.{h,cpp}) --
@@ -377,6 +402,8 @@ public:
   void setMoving(const PointIntensityDescriptorCloud* m) { _moving_slice = m; }
   void bindFixed();    // stereo: mean disparity (.cpp:75-89)
   void setupFactor();  // K, image dim, per-correspondence information (.cpp:27-73), stereo extras (:91-112)
+  void setupFactorConfig();  // the part of setupFactor that does not depend on the correspondences
+  void diagonalInfo(float d[3]) const;
   CorrespondenceVector& correspondences() { return _correspondences; }
   const pslam_linearize_cfg& factorConfig() const { return _factor; }
   const std::vector<float>& informationDiagonals() const { return _fixed_information_diagonals; }
