@@ -47,6 +47,14 @@ class ProjectiveCfg(C.Structure):
                 ("maximum_distance_ratio_to_second_best", C.c_float), ("maximum_descriptor_distance", C.c_float)]
 
 
+class FusedGn(C.Structure):
+    """pslam_fused_gn"""
+    _fields_ = [("factor", C.c_void_p), ("diagonal_info", C.c_float * 3), ("n_iterations", C.c_int), ("damping", C.c_double),
+                ("pose12", C.c_double * 12), ("prior", C.c_void_p), ("poses12", C.POINTER(C.c_double)),
+                ("stats4", C.POINTER(C.c_double)), ("factor_status", C.POINTER(C.c_ubyte)), ("iterations_done", C.c_int),
+                ("spd", C.c_int)]
+
+
 class ClipCfg(C.Structure):
     """pslam_clip_cfg"""
     _fields_ = [("K", C.c_float * 9), ("canvas_rows", C.c_int), ("canvas_cols", C.c_int), ("range_min", C.c_float),
@@ -562,6 +570,45 @@ class Context:
         n = self._chk(lib().pslam_projective_match(self._h, self._n_fixed, self._n_moving, _p(pose12),
                                                    C.byref(cfg), cap, _p(fi), _p(mi), _p(d), C.byref(nproj)))
         return fi[:n].copy(), mi[:n].copy(), d[:n].copy(), nproj.value
+
+    def projective_set_moving_weights(self, scale):
+        scale = np.ascontiguousarray(scale, np.float32).reshape(-1)
+        self._chk(lib().pslam_projective_set_moving_weights(self._h, len(scale), _p(scale)))
+
+    def projective_match_gn(self, pose12, K, rows, cols, lcfg, diagonal_info, n_iterations, damping, estimate12, shape="circle",
+                            radius=10, descriptor_distance=50.0, ratio=0.9, range_min=0.1, range_max=1000.0, prior=None):
+        """pslam_projective_match_gn: (fixed, moving, distance, n_projected, dict(pose, poses, stats, status, done, spd))"""
+        cfg = ProjectiveCfg()
+        cfg.K[:] = [float(v) for v in np.asarray(K, np.float32).reshape(9)]
+        cfg.canvas_rows, cfg.canvas_cols = int(rows), int(cols)
+        cfg.range_min, cfg.range_max = float(range_min), float(range_max)
+        cfg.shape = SHAPES[shape]
+        cfg.search_radius_pixels = int(radius)
+        cfg.descriptor_distance = float(descriptor_distance)
+        cfg.maximum_distance_ratio_to_second_best = float(ratio)
+        cfg.maximum_descriptor_distance = float(descriptor_distance)
+        pose12 = np.ascontiguousarray(pose12, np.float32).reshape(12)
+        cap = max(self._n_fixed, 1)
+        fi, mi, d = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap, np.float32)
+        poses, stats = np.zeros((max(n_iterations, 1), 12), np.float64), np.zeros((max(n_iterations, 1), 4), np.float64)
+        status = np.zeros(cap, np.uint8)
+        g = FusedGn()
+        g.factor = C.cast(C.pointer(lcfg), C.c_void_p)
+        g.diagonal_info[:] = [float(v) for v in (list(diagonal_info) + [0.0, 0.0, 0.0])[:3]]
+        g.n_iterations, g.damping = int(n_iterations), float(damping)
+        g.pose12[:] = [float(v) for v in np.asarray(estimate12, np.float64).reshape(12)]
+        pr = self._prior(prior)
+        g.prior = C.cast(C.pointer(pr), C.c_void_p) if pr is not None else None
+        g.poses12 = poses.ctypes.data_as(C.POINTER(C.c_double))
+        g.stats4 = stats.ctypes.data_as(C.POINTER(C.c_double))
+        g.factor_status = status.ctypes.data_as(C.POINTER(C.c_ubyte))
+        nproj = C.c_int(0)
+        n = self._chk(lib().pslam_projective_match_gn(self._h, self._n_fixed, self._n_moving, _p(pose12), C.byref(cfg), cap, _p(fi),
+                                                      _p(mi), _p(d), C.byref(nproj), C.byref(g)))
+        done = g.iterations_done
+        return fi[:n].copy(), mi[:n].copy(), d[:n].copy(), nproj.value, dict(
+            pose=np.array(g.pose12[:], np.float64), poses=poses[:done], stats=stats[:done], status=status[:n].copy(), done=done,
+            spd=bool(g.spd))
 
     # ---- stages 3 + 4 -------------------------------------------------------------------------
     @staticmethod

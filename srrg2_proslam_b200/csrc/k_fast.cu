@@ -34,6 +34,7 @@
 // K2 `bin_select_kernel`: per (region, image) gather of the region's keypoints from the row lists in
 // row-major order, then the reference's selection (keep all if fewer than quota, else unstable std::sort by
 // response and keep the first quota) replayed move-for-move (libstdcxx_sort.h).
+#include <mutex>
 #include <vector>
 
 #include "libstdcxx_sort.h"
@@ -825,10 +826,14 @@ int pslam_k_fast_blur(pslam_ctx* ctx, const uint8_t* d_images, long long image_p
   // the limit is a property of the FUNCTION (per device), shared by every context of the process: it is only ever raised --
   // a per-context cache would let one context lower it under another one's launches ("invalid argument")
   static size_t k1_smem_limit[64] = {0};
+  static std::mutex k1_smem_mutex;  // contexts of different host threads may launch on the same device
   const int dev_slot = ctx->device & 63;
-  if (smem > 48 * 1024 && smem > k1_smem_limit[dev_slot]) {
-    PSLAM_CUDA_TRY(ctx, cudaFuncSetAttribute(fast_blur_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    k1_smem_limit[dev_slot] = smem;
+  if (smem > 48 * 1024) {
+    std::lock_guard<std::mutex> lock(k1_smem_mutex);
+    if (smem > k1_smem_limit[dev_slot]) {
+      PSLAM_CUDA_TRY(ctx, cudaFuncSetAttribute(fast_blur_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+      k1_smem_limit[dev_slot] = smem;
+    }
   }
   dim3 grid(n_bands, n_images, (n_strips + wpc - 1) / wpc);
   fast_blur_rows_kernel<<<grid, 32 * wpc, smem, ctx->stream>>>(a);

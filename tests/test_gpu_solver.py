@@ -175,3 +175,44 @@ def test_gn_iterate_f32_with_prior(ctx, kind, damping, n):
     strong = (prior[0], 1e12 * np.eye(6))
     pg2, *_ = ctx.gn_iterate_f32(gcfg, 20, 0.0, pose, xyz, meas, cf, cm, info, prior=strong)
     assert np.abs(O.t2tnq(O.pose_mul(O.pose_inverse(prior[0]), pg2))).max() < 1e-4
+
+
+@pytest.mark.parametrize("with_prior,weights", [(False, False), (True, True)])
+def test_projective_match_gn_equals_match_then_iterate(oracle, with_prior, weights):
+    """pslam_projective_match_gn (search + filter + K fused solver iterations in one device round trip) == pslam_projective_match
+    followed by pslam_gn_iterate_f32 on the same correspondences in ascending fixed index, with the information the aligner
+    slice would set up (diagonal x per-point scale); factor status comes back in the order of the returned correspondences"""
+    from srrg2_proslam_b200 import capi
+    from test_oracle_known_answers import CAM00, CAM01, K_KITTI
+    c = capi.Context(max_images=2, max_rows=376, max_cols=1241, max_features=2048, max_raw_per_bin=8192)
+    try:
+        e = O.extract_cfg(threshold=15, target=500)
+        m = [O.stereo_adaptor(O.load_gray(f"kitti_city_image_left_{i}.png"), O.load_gray(f"kitti_city_image_right_{i}.png"), e,
+                              "epipolar", 50, 0.8) for i in (0, 1)]
+        xyz, _ = O.triangulate(m[0]["uvuv"], K_KITTI, np.float32(718.856) * np.float32(0.537166), 0.0)
+        pose = O.pose_inverse(O.pose_mul(O.pose_inverse(CAM00), CAM01))
+        guess = np.eye(3, 4).reshape(12)
+        base = (K_KITTI.reshape(3, 3) @ np.array([-0.537166, 0, 0], np.float32)).astype(np.float64)
+        lcfg = c.linearize_cfg("stereo", K_KITTI.astype(np.float64), 1241, 376, base, 0.0, "saturated", 1000.0)
+        diag = np.array([1, 2, 1], np.float32)
+        rng = np.random.default_rng(4)
+        scale = (1 + rng.integers(0, 3, len(xyz))).astype(np.float32) if weights else np.ones(len(xyz), np.float32)
+        prior = rand_prior(8) if with_prior else None
+        c.projective_set_fixed(m[1]["uvuv"], m[1]["desc"])
+        c.projective_set_moving(xyz, m[0]["desc"])
+        if weights:
+            c.projective_set_moving_weights(scale)
+        f0, m0, d0, np0 = c.projective_match(pose, K_KITTI, 376, 1241, "circle", 30, 75.0, 0.8)
+        f1, m1, d1, np1, g = c.projective_match_gn(pose, K_KITTI, 376, 1241, lcfg, diag, 7, 1.0, guess, "circle", 30, 75.0, 0.8,
+                                                   prior=prior)
+        assert np1 == np0 and np.array_equal(f0, f1) and np.array_equal(m0, m1) and np.array_equal(d0, d1) and len(f0) > 20
+        order = np.argsort(f0)
+        info = np.zeros((len(m[1]["uvuv"]), 3), np.float32)
+        info[f0] = diag[None, :] * scale[m0][:, None]
+        pg, poses, stats, done, ok, status = c.gn_iterate_f32(lcfg, 7, 1.0, guess, xyz, m[1]["uvuv"], f0[order], m0[order], info,
+                                                             prior=prior)
+        assert g["done"] == done == 7 and g["spd"] and ok
+        assert np.array_equal(g["poses"], poses) and np.array_equal(g["stats"], stats) and np.array_equal(g["pose"], pg)
+        assert np.array_equal(g["status"][order], status)
+    finally:
+        c.close()
