@@ -164,3 +164,31 @@ def test_batch_euroc_shaped_synthetic(oracle):
             assert O.fnv1a_points(res["uvuv"][a:b], res["intensity"][a:b], res["desc"][a:b]) == chk[p], p
     finally:
         ctx.close()
+
+
+def test_chunk_lanes_give_identical_results(oracle):
+    """pslam_set_lanes: a batch that spans several chunks produces the same stereo clouds whether its chunks alternate over
+    two streams with their own intermediates (default) or run one after the other on one stream"""
+    import torch
+    from srrg2_proslam_b200 import capi, synth
+    n_pairs = 9  # 18 images, chunks of 4: five chunks, the last one short
+    imgs = synth.stereo_pairs(n_pairs, 120, 320, seed=21, device="cuda")
+    ctx = capi.Context(max_images=2 * n_pairs, max_rows=120, max_cols=320, max_features=1024, max_raw_per_bin=4096, work_images=4)
+    try:
+        ecfg, mcfg = capi.extract_cfg(15, 1, 400), capi.match_cfg(100, 0.5, 100, 0)
+        outs = []
+        for lanes in (2, 1, 2):
+            ctx.set_lanes(lanes)
+            ctx.stereo_frontend_batch_dev(imgs.data_ptr(), n_pairs, 120, 320, 320, 120 * 320, ecfg, mcfg)
+            ctx.synchronize()
+            counts = ctx.stereo_counts(n_pairs)
+            outs.append((counts.copy(), [ctx.download_stereo_points(p)["uvuv"] for p in range(n_pairs)]))
+        assert outs[0][0].sum() > 50
+        for o in outs[1:]:
+            assert np.array_equal(o[0], outs[0][0])
+            assert all(np.array_equal(a, b) for a, b in zip(o[1], outs[0][1]))
+        h = imgs.cpu().numpy()
+        ref = O.stereo_adaptor(h[3, 0], h[3, 1], O.extract_cfg(15, 1, 400), "epipolar", 100, 0.5, 100, 0)
+        assert np.array_equal(outs[0][1][3], ref["uvuv"])
+    finally:
+        ctx.close()
