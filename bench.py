@@ -595,13 +595,29 @@ def main():
         # the ABI as well (the 128-byte id travels over torch.distributed), the all-gather runs on the context's stream
         dq, dt_ = torch.from_numpy(q).to(dev), torch.from_numpy(t).to(dev)
         table = torch.empty((3, nq), dtype=torch.int32, device=dev)
-        comm = None
+        comm, p2p = None, False
         if world > 1:
-            ids = [ctx.nccl_unique_id() if rank == 0 else None]
-            dist.broadcast_object_list(ids, src=0)
-            comm = ctx.nccl_comm_create(ids[0], rank, world)
+            # preferred: exchange fused into the merge kernel (peer tables over CUDA IPC + NVLink, no collective); fallback: the
+            # NCCL all-gather entry point
+            try:
+                handles = [None] * world
+                dist.all_gather_object(handles, ctx.p2p_table_export(nq))
+                ctx.p2p_table_import(rank, world, handles)
+                p2p = True
+            except Exception as e_:  # e.g. IPC not permitted in this container
+                print(f"[bench] p2p tables unavailable ({e_!r}), using the NCCL entry point", file=sys.stderr)
+            flag = torch.tensor([int(p2p)], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            p2p = bool(flag.item())
+            if not p2p:
+                ids = [ctx.nccl_unique_id() if rank == 0 else None]
+                dist.broadcast_object_list(ids, src=0)
+                comm = ctx.nccl_comm_create(ids[0], rank, world)
         def sweep():
-            if world > 1:
+            if p2p:
+                ctx.bf_best2_sharded_p2p_dev(nq, dq.data_ptr(), nt, dt_.data_ptr(), table[0].data_ptr(), table[1].data_ptr(),
+                                             table[2].data_ptr())
+            elif world > 1:
                 ctx.bf_best2_sharded_dev(comm, rank, world, nq, dq.data_ptr(), nt, dt_.data_ptr(), table[0].data_ptr(),
                                          table[1].data_ptr(), table[2].data_ptr())
             else:
@@ -622,6 +638,9 @@ def main():
         gpairs = nq * nt * reps / (float(hms.item()) * 1e-3) / 1e9
         if comm is not None:
             ctx.nccl_comm_destroy(comm)
+        if p2p:
+            barrier()
+            ctx.p2p_table_release()
         sm_mhz = line["clocks"]["sm_mhz"] or 1965.0
         # Roofline of the sweep = the busier of the two integer pipes for the kernel's instruction mix per 256-bit pair
         # (SASS of bf_sweep_kernel<0>: 5 POPC on the XU pipe; 15 LOP3 + 1 IADD3 + 3 VIMNMX on the ALU pipe), with the pipe
@@ -639,8 +658,10 @@ def main():
         plain_peak = 148 * popc_rate / 8 * sm_mhz * 1e6 / 1e9 * world
         line["hamming"] = {"metric": "hamming_best2_gpairs_per_s", "value": gpairs, "unit": "GPair/s", "scaling": "strong",
                            "config": {"workload": "64k x 64k 256-bit descriptors (BASELINE config 5): query rows sharded "
-                                                  f"over {world} GPU(s), train set replicated, all-gather of (best, second, argmin)",
-                                      "api": "pslam_bf_best2_dev" if world == 1 else "pslam_bf_best2_sharded_dev (ncclAllGather on the context stream)"},
+                                                  f"over {world} GPU(s), train set replicated, every rank ends with the full (best, second, argmin) table",
+                                      "api": "pslam_bf_best2_dev" if world == 1 else (
+                                          "pslam_bf_best2_sharded_p2p_dev (merge kernel stores into every rank's table over NVLink, flags; no collective)"
+                                          if p2p else "pslam_bf_best2_sharded_dev (ncclAllGather on the context stream)")},
                            "ms_per_sweep": float(hms.item()) / reps,
                            "roofline": {"bound": "int (XU popc + ALU lop3, balanced)", "achieved": gpairs, "peak": int_peak, "unit": "GPair/s",
                                         "frac": gpairs / int_peak,

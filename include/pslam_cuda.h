@@ -364,6 +364,18 @@ int pslam_shard_rows(int n_rows, int rank, int world, int align, int* begin, int
 int pslam_nccl_unique_id(pslam_ctx* ctx, PslamNcclId* id);
 int pslam_nccl_comm_create(pslam_ctx* ctx, const PslamNcclId* id, int rank, int world, void** nccl_comm);
 int pslam_nccl_comm_destroy(pslam_ctx* ctx, void* nccl_comm);
+/* The same sweep with the exchange step FUSED into the merge kernel, no collective: every rank exports one result table of
+ * its HBM through CUDA IPC (pslam_p2p_table_export), the application distributes the 64-byte handles like it distributes the
+ * NCCL id, every rank maps its peers' tables (pslam_p2p_table_import); the merge kernel of pslam_bf_best2_sharded_p2p_dev
+ * then stores every row's (best, second, argmin) straight into ALL ranks' tables -- coalesced stores over NVLink / NVSwitch --
+ * followed by one flag per source rank; a rank hands its table out as soon as all flags of the call's epoch are up.  All
+ * ranks must issue the same sequence of p2p calls. */
+typedef struct { char internal[64]; } PslamIpcHandle;  /* = cudaIpcMemHandle_t */
+int pslam_p2p_table_export(pslam_ctx* ctx, int max_rows, PslamIpcHandle* mine);
+int pslam_p2p_table_import(pslam_ctx* ctx, int rank, int world, const PslamIpcHandle* handles_of_all_ranks);
+int pslam_p2p_table_release(pslam_ctx* ctx);
+int pslam_bf_best2_sharded_p2p_dev(pslam_ctx* ctx, int n_fixed, const uint32_t* d_desc_fixed, int n_moving,
+                                   const uint32_t* d_desc_moving, int32_t* d_best, int32_t* d_second, int32_t* d_best_idx);
 /* every rank passes the SAME full descriptor sets (device pointers) and receives the full tables [n_fixed] */
 int pslam_bf_best2_sharded_dev(pslam_ctx* ctx, void* nccl_comm, int rank, int world, int n_fixed,
                                const uint32_t* d_desc_fixed, int n_moving, const uint32_t* d_desc_moving,

@@ -530,6 +530,23 @@ class Context:
         self._chk(lib().pslam_bf_best2_sharded_dev(self._h, comm, int(rank), int(world), int(nq), C.c_void_p(d_q), int(nt),
                                                    C.c_void_p(d_t), C.c_void_p(d_best), C.c_void_p(d_second), C.c_void_p(d_idx)))
 
+    # peer-to-peer tables: exchange step fused into the merge kernel (no collective)
+    def p2p_table_export(self, max_rows):
+        buf = C.create_string_buffer(64)
+        self._chk(lib().pslam_p2p_table_export(self._h, int(max_rows), buf))
+        return buf.raw
+
+    def p2p_table_import(self, rank, world, handles):
+        buf = C.create_string_buffer(b"".join(bytes(h) for h in handles), 64 * int(world))
+        self._chk(lib().pslam_p2p_table_import(self._h, int(rank), int(world), buf))
+
+    def p2p_table_release(self):
+        self._chk(lib().pslam_p2p_table_release(self._h))
+
+    def bf_best2_sharded_p2p_dev(self, nq, d_q, nt, d_t, d_best, d_second, d_idx):
+        self._chk(lib().pslam_bf_best2_sharded_p2p_dev(self._h, int(nq), C.c_void_p(d_q), int(nt), C.c_void_p(d_t), C.c_void_p(d_best),
+                                                       C.c_void_p(d_second), C.c_void_p(d_idx)))
+
     def match_bruteforce(self, desc_f, desc_m, cfg):
         desc_f = np.ascontiguousarray(desc_f, np.uint8).reshape(-1, 32)
         desc_m = np.ascontiguousarray(desc_m, np.uint8).reshape(-1, 32)

@@ -173,6 +173,35 @@ __global__ void bf_merge_kernel(int nq, int n_slices, const int* __restrict__ pa
   idx[i] = b.idx;
 }
 
+// The same merge, fused with the exchange step of the sharded sweep: every row's result is stored straight into the result
+// table of EVERY rank (peer HBM mapped through CUDA IPC: plain coalesced stores that travel over NVLink / NVSwitch), so no
+// collective follows -- only a flag per source rank (k_sharded.cu).  peers[r] = table base of rank r: [2][3][cap_rows] ints.
+__global__ void bf_merge_p2p_kernel(int nq, int n_slices, const int* __restrict__ part_best, const int* __restrict__ part_second,
+                                    const int* __restrict__ part_idx, int row_offset, int cap_rows, int parity, int world,
+                                    int* const* __restrict__ peers) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  Best2 b{INT_MAX, INT_MAX, -1};
+  for (int s = 0; s < n_slices; ++s) {
+    const size_t o = (size_t) s * nq + i;
+    const int pb = part_best[o], ps = part_second[o];
+    if (pb < b.best) {
+      b.second = min(b.best, ps);
+      b.best = pb;
+      b.idx = part_idx[o];
+    } else {
+      b.second = min(b.second, pb);
+    }
+  }
+  const size_t base = (size_t) parity * 3 * cap_rows + row_offset + i;
+  for (int r = 0; r < world; ++r) {
+    int* t = peers[r];
+    t[base] = b.best;
+    t[base + cap_rows] = b.second;
+    t[base + 2 * (size_t) cap_rows] = b.idx;
+  }
+}
+
 // exclusive scan of `n` ints by a single CTA (n up to a few million); writes total to *total
 __global__ void __launch_bounds__(1024)
 bf_scan_kernel(const int* __restrict__ in, int* __restrict__ out, int n, int* __restrict__ total) {
@@ -403,6 +432,33 @@ int pslam_k_bf_best2(pslam_ctx* ctx, int nq, const uint32_t* d_q, int nt, const 
   bf_merge_kernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(nq, n_slices, pb, ps, pi, d_best,
                                                              d_second, d_idx);
   PSLAM_LAUNCH_CHECK(ctx, "bf_merge_kernel");
+  return PSLAM_OK;
+}
+
+int pslam_k_bf_best2_p2p(pslam_ctx* ctx, int nq, const uint32_t* d_q, int nt, const uint32_t* d_t, int row_offset, int cap_rows,
+                         int parity, int world, int* const* d_peers) {
+  if (nq <= 0) return PSLAM_OK;
+  if (nt <= 0) return pslam_set_error(ctx, PSLAM_E_INVALID, "bf_best2_p2p: empty train set", cudaSuccess);
+  int sm_count = 148;
+  cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, ctx->device);
+  const int S = choose_slices(nq, nt, sm_count);
+  int slice_len = (nt + S - 1) / S;
+  slice_len = (slice_len + BF_TTILE - 1) / BF_TTILE * BF_TTILE;
+  const int n_slices = (nt + slice_len - 1) / slice_len;
+  const size_t part = align256(sizeof(int) * (size_t) n_slices * nq);
+  if (3 * part > ctx->scratch_bytes) return pslam_set_error(ctx, PSLAM_E_CAPACITY, "bf_best2: scratch too small", cudaSuccess);
+  int* pb = reinterpret_cast<int*>(ctx->d_scratch);
+  int* ps = reinterpret_cast<int*>(ctx->d_scratch + part);
+  int* pi = reinterpret_cast<int*>(ctx->d_scratch + 2 * part);
+  const int BF_QTILE = BF_THREADS * bf_qpt();
+  dim3 grid((nq + BF_QTILE - 1) / BF_QTILE, n_slices);
+  auto sweep = bf_qpt() == 4 ? bf_sweep_kernel<0, 4> : bf_sweep_kernel<0, 2>;
+  sweep<<<grid, BF_THREADS, 0, ctx->stream>>>(
+    reinterpret_cast<const uint4*>(d_q), nq, reinterpret_cast<const uint4*>(d_t), nt, slice_len,
+    n_slices, 0, pb, ps, pi, nullptr, nullptr, nullptr, 0);
+  PSLAM_LAUNCH_CHECK(ctx, "bf_sweep_kernel<0>");
+  bf_merge_p2p_kernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(nq, n_slices, pb, ps, pi, row_offset, cap_rows, parity, world, d_peers);
+  PSLAM_LAUNCH_CHECK(ctx, "bf_merge_p2p_kernel");
   return PSLAM_OK;
 }
 

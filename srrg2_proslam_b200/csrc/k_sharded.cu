@@ -73,9 +73,118 @@ __global__ void unshard_best2_kernel(const int* __restrict__ gathered, int world
   idx[i] = src[2 * per + j];
 }
 
+// ---- exchange step without a collective: peer-to-peer tables ---------------------------------------------------------------
+constexpr int P2P_FLAGS = 64;
+// after the merge kernel of this stream has completed (its stores to the peers' tables are performed): tell every peer
+__global__ void p2p_signal_kernel(int* const* __restrict__ peers, int world, int rank, size_t flags_offset, int epoch) {
+  __threadfence_system();
+  if ((int) threadIdx.x < world) {
+    volatile int* f = peers[threadIdx.x] + flags_offset;
+    f[rank] = epoch;
+  }
+}
+// wait until every source rank has written this epoch into OUR table, then hand the table out
+__global__ void p2p_wait_copy_kernel(const int* __restrict__ table, size_t flags_offset, int world, int epoch, int cap_rows, int parity,
+                                     int n, int* __restrict__ best, int* __restrict__ second, int* __restrict__ idx) {
+  if ((int) threadIdx.x < world) {
+    const volatile int* f = table + flags_offset;
+    while (f[threadIdx.x] < epoch) {
+    }
+  }
+  __syncthreads();
+  __threadfence_system();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const size_t base = (size_t) parity * 3 * cap_rows + i;
+  best[i] = __ldcv(table + base);
+  second[i] = __ldcv(table + base + cap_rows);
+  idx[i] = __ldcv(table + base + 2 * (size_t) cap_rows);
+}
+
 }  // namespace
 
 extern "C" {
+
+int pslam_p2p_table_export(pslam_ctx* ctx, int max_rows, PslamIpcHandle* mine) {
+  if (!ctx || max_rows <= 0 || !mine) return PSLAM_E_INVALID;
+  static_assert(sizeof(PslamIpcHandle) == sizeof(cudaIpcMemHandle_t), "PslamIpcHandle must be a cudaIpcMemHandle_t");
+  PSLAM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (ctx->d_p2p_table) return pslam_set_error(ctx, PSLAM_E_INVALID, "p2p table already exported (release it first)", cudaSuccess);
+  const int cap = (max_rows + 255) / 256 * 256;
+  const size_t words = 2 * 3 * (size_t) cap + P2P_FLAGS;
+  PSLAM_CUDA_TRY(ctx, cudaMalloc((void**) &ctx->d_p2p_table, words * sizeof(int)));
+  PSLAM_CUDA_TRY(ctx, cudaMemset(ctx->d_p2p_table, 0, words * sizeof(int)));
+  ctx->p2p_cap_rows = cap;
+  ctx->p2p_epoch = 0;
+  cudaIpcMemHandle_t h;
+  PSLAM_CUDA_TRY(ctx, cudaIpcGetMemHandle(&h, ctx->d_p2p_table));
+  memcpy(mine, &h, sizeof(h));
+  return PSLAM_OK;
+}
+
+int pslam_p2p_table_import(pslam_ctx* ctx, int rank, int world, const PslamIpcHandle* all) {
+  if (!ctx || !all || world <= 0 || world > P2P_FLAGS || rank < 0 || rank >= world) return PSLAM_E_INVALID;
+  if (!ctx->d_p2p_table) return pslam_set_error(ctx, PSLAM_E_INVALID, "p2p: export this rank's table first", cudaSuccess);
+  PSLAM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) {
+      ctx->p2p_peer[r] = ctx->d_p2p_table;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, all + r, sizeof(h));
+    void* p = nullptr;
+    PSLAM_CUDA_TRY(ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->p2p_peer[r] = (int*) p;
+  }
+  PSLAM_CUDA_TRY(ctx, cudaMalloc((void**) &ctx->d_p2p_peers, sizeof(int*) * P2P_FLAGS));
+  PSLAM_CUDA_TRY(ctx, cudaMemcpy(ctx->d_p2p_peers, ctx->p2p_peer, sizeof(int*) * (size_t) world, cudaMemcpyHostToDevice));
+  ctx->p2p_world = world;
+  ctx->p2p_rank = rank;
+  return PSLAM_OK;
+}
+
+int pslam_p2p_table_release(pslam_ctx* ctx) {
+  if (!ctx) return PSLAM_E_INVALID;
+  if (!ctx->d_p2p_table) return PSLAM_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (int r = 0; r < ctx->p2p_world; ++r)
+    if (r != ctx->p2p_rank && ctx->p2p_peer[r]) cudaIpcCloseMemHandle(ctx->p2p_peer[r]);
+  if (ctx->d_p2p_peers) cudaFree(ctx->d_p2p_peers);
+  cudaFree(ctx->d_p2p_table);
+  ctx->d_p2p_table = nullptr;
+  ctx->d_p2p_peers = nullptr;
+  ctx->p2p_world = 0;
+  memset(ctx->p2p_peer, 0, sizeof(ctx->p2p_peer));
+  return PSLAM_OK;
+}
+
+int pslam_bf_best2_sharded_p2p_dev(pslam_ctx* ctx, int n_fixed, const uint32_t* d_desc_fixed, int n_moving,
+                                   const uint32_t* d_desc_moving, int32_t* d_best, int32_t* d_second, int32_t* d_best_idx) {
+  if (!ctx || n_fixed < 0 || n_moving <= 0) return PSLAM_E_INVALID;
+  if (!ctx->d_p2p_peers || ctx->p2p_world <= 0)
+    return pslam_set_error(ctx, PSLAM_E_INVALID, "p2p: pslam_p2p_table_export / _import first", cudaSuccess);
+  if (n_fixed > ctx->p2p_cap_rows) return pslam_set_error(ctx, PSLAM_E_CAPACITY, "p2p: more rows than the exported table holds", cudaSuccess);
+  if (n_fixed == 0) return PSLAM_OK;
+  PSLAM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const int rank = ctx->p2p_rank, world = ctx->p2p_world;
+  int b = 0, e = 0;
+  pslam_shard_rows(n_fixed, rank, world, 256, &b, &e);
+  // Every rank runs the same sequence of calls, so `epoch` advances in lock step.  Tables are double-buffered by epoch parity: a
+  // peer can only write epoch e + 1 after it has seen OUR flag of epoch e, which we raise after having copied epoch e - 1 out.
+  const int epoch = ++ctx->p2p_epoch, parity = epoch & 1;
+  const size_t flags_offset = 2 * 3 * (size_t) ctx->p2p_cap_rows;
+  const int rc = pslam_k_bf_best2_p2p(ctx, e - b, d_desc_fixed + 8 * (size_t) b, n_moving, d_desc_moving, b, ctx->p2p_cap_rows, parity,
+                                      world, ctx->d_p2p_peers);
+  if (rc) return rc;
+  p2p_signal_kernel<<<1, P2P_FLAGS, 0, ctx->stream>>>(ctx->d_p2p_peers, world, rank, flags_offset, epoch);
+  PSLAM_LAUNCH_CHECK(ctx, "p2p_signal_kernel");
+  p2p_wait_copy_kernel<<<(n_fixed + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_p2p_table, flags_offset, world, epoch, ctx->p2p_cap_rows,
+                                                                     parity, n_fixed, d_best, d_second, d_best_idx);
+  PSLAM_LAUNCH_CHECK(ctx, "p2p_wait_copy_kernel");
+  return PSLAM_OK;
+}
 
 int pslam_shard_frames(int n_frames, int rank, int world, int* begin, int* end) {
   if (n_frames < 0 || world <= 0 || rank < 0 || rank >= world || !begin || !end) return PSLAM_E_INVALID;

@@ -355,6 +355,7 @@ void pslam_destroy(pslam_ctx* ctx) {
                   ctx->d_sel_bounds, ctx->d_scratch, ctx->d_proj, ctx->d_tile_start, ctx->d_tile_order};
   for (void* b : bufs)
     if (b) cudaFree(b);
+  pslam_p2p_table_release(ctx);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   if (ctx->h_frame_stage) cudaFreeHost(ctx->h_frame_stage);
   for (int i = 0; i < ctx->prof_cap; ++i) cudaEventDestroy(ctx->prof_ev[i]);

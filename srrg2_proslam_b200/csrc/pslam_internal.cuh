@@ -103,6 +103,13 @@ struct pslam_ctx {
   unsigned long long proj_fixed_epoch, proj_moving_epoch;
   int proj_fixed_dim;  // floats per fixed point of the cached cloud
   unsigned long long proj_weights_epoch;  // == proj_moving_epoch while the information-scale table belongs to the cached moving cloud
+  // peer-to-peer result tables of the sharded Hamming sweep (k_sharded.cu): every rank owns one table in its HBM, exported
+  // through CUDA IPC; the ranks' merge kernels store their rows straight into every peer's table over NVLink
+  int* d_p2p_table;        // [2 parities][3][p2p_cap_rows] ints + 64 flags (epoch of the last complete write, per source rank)
+  int p2p_cap_rows, p2p_world, p2p_rank;
+  int* p2p_peer[64];       // table base of every rank as seen from this device (own pointer for p2p_rank)
+  int** d_p2p_peers;       // the same array on the device
+  int p2p_epoch;
   // geometry of the last batch
   int rows, cols, n_images;
   // optional per-kernel device timing (pslam_profile_*): one CUDA event after every launch; the interval

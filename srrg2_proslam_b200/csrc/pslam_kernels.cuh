@@ -38,6 +38,9 @@ int pslam_k_triangulate(pslam_ctx* ctx, const float4* d_uvuv, long long n, const
                         float infinity_depth, float* d_xyz, unsigned char* d_valid);
 
 // k_bruteforce.cu
+// sweep of this rank's rows + merge that stores (best, second, argmin) into table[3][cap_rows] of every peer at row_offset
+int pslam_k_bf_best2_p2p(pslam_ctx* ctx, int n_q, const uint32_t* d_q, int n_t, const uint32_t* d_t, int row_offset, int cap_rows,
+                         int parity, int world, int* const* d_peers);
 int pslam_k_bf_best2(pslam_ctx* ctx, int n_fixed, const uint32_t* d_desc_fixed, int n_moving,
                      const uint32_t* d_desc_moving, int32_t* d_best, int32_t* d_second,
                      int32_t* d_best_idx);

@@ -165,6 +165,29 @@ def test_bf_best2_sharded_single_rank_through_nccl(ctx):
     assert np.array_equal(g[0], ob) and np.array_equal(g[1], os_) and np.array_equal(g[2], oi)
 
 
+def test_bf_best2_sharded_p2p_single_rank(ctx):
+    """pslam_bf_best2_sharded_p2p_dev with a one-rank world: export / import of the result table, merge kernel storing into
+    it, flag + wait + hand-out, two consecutive epochs (both table parities) == the plain sweep (N ranks: tools/sharded_check.py)"""
+    import torch
+    rng = np.random.default_rng(19)
+    nq, nt = 1300, 900
+    t = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
+    ctx.p2p_table_import(0, 1, [ctx.p2p_table_export(nq)])
+    try:
+        for rep in range(3):
+            q = rng.integers(0, 256, (nq, 32), dtype=np.uint8)
+            dq, dt_ = torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda()
+            out = torch.full((3, nq), -7, dtype=torch.int32, device="cuda")
+            torch.cuda.synchronize()
+            ctx.bf_best2_sharded_p2p_dev(nq, dq.data_ptr(), nt, dt_.data_ptr(), out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr())
+            ctx.synchronize()
+            ob, os_, oi = O.bf_best2(q, t)
+            g = out.cpu().numpy()
+            assert np.array_equal(g[0], ob) and np.array_equal(g[1], os_) and np.array_equal(g[2], oi), rep
+    finally:
+        ctx.p2p_table_release()
+
+
 def test_adaptors_known_answers(ctx):  # tests/test_measurement_adaptors.cpp:51,130
     from srrg2_proslam_b200 import capi
     e = capi.extract_cfg(5, 1, 500)

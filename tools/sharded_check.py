@@ -34,8 +34,20 @@ def main():
     out = torch.full((3, n), -1, dtype=torch.int32, device=dev)
     ctx.bf_best2_dev(n, dq.data_ptr(), n, dt_.data_ptr(), ref[0].data_ptr(), ref[1].data_ptr(), ref[2].data_ptr())
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
-    run = lambda: ctx.bf_best2_sharded_dev(comm, rank, world, n, dq.data_ptr(), n, dt_.data_ptr(), out[0].data_ptr(),
-                                           out[1].data_ptr(), out[2].data_ptr())
+    mode = sys.argv[2] if len(sys.argv) > 2 else "nccl"
+    if mode == "p2p":  # exchange fused into the merge kernel: peer tables mapped through CUDA IPC, no collective
+        handles = [None] * world
+        mine = ctx.p2p_table_export(n)
+        if world > 1:
+            dist.all_gather_object(handles, mine)
+        else:
+            handles = [mine]
+        ctx.p2p_table_import(rank, world, handles)
+        run = lambda: ctx.bf_best2_sharded_p2p_dev(n, dq.data_ptr(), n, dt_.data_ptr(), out[0].data_ptr(), out[1].data_ptr(),
+                                                   out[2].data_ptr())
+    else:
+        run = lambda: ctx.bf_best2_sharded_dev(comm, rank, world, n, dq.data_ptr(), n, dt_.data_ptr(), out[0].data_ptr(),
+                                               out[1].data_ptr(), out[2].data_ptr())
     for _ in range(3):
         run()
     ctx.synchronize()
@@ -54,9 +66,15 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print(json.dumps({"metric": "hamming_best2_gpairs_per_s", "api": "pslam_bf_best2_sharded_dev (C ABI, ncclAllGather on the context stream)",
+        print(json.dumps({"metric": "hamming_best2_gpairs_per_s", "api": "pslam_bf_best2_sharded_p2p_dev (C ABI, merge kernel stores into every peer's table over NVLink, flags, no collective)"
+                          if mode == "p2p" else "pslam_bf_best2_sharded_dev (C ABI, ncclAllGather on the context stream)",
                           "n_gpus": world, "n": n, "ms_per_sweep": float(ms.item()), "value": n * n / (float(ms.item()) * 1e-3) / 1e9,
                           "unit": "GPair/s", "parity_with_single_gpu_sweep": bool(ok.item())}))
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    if mode == "p2p":
+        ctx.p2p_table_release()
     ctx.nccl_comm_destroy(comm)
     ctx.close()
     dist.destroy_process_group()
