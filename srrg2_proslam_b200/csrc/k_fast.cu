@@ -635,7 +635,8 @@ __global__ void blur_border_kernel(const uint8_t* __restrict__ img, int rows, in
 // -------------------------------------------------------------------------------------------------------------
 // K2: gather + select.  grid (regions, images), one CTA of SEL_THREADS threads.
 // -------------------------------------------------------------------------------------------------------------
-constexpr int SEL_THREADS = 64;
+constexpr int SEL_THREADS = 64;       // throughput launches (many images): small CTAs, several per SM
+constexpr int SEL_THREADS_WIDE = 256;  // latency launches (one or two images): the gather walks all rows of a region at once
 
 struct RespGreater {
   __device__ __forceinline__ bool operator()(const uint32_t& x, const uint32_t& y) const {
@@ -643,7 +644,8 @@ struct RespGreater {
   }
 };
 
-__global__ void __launch_bounds__(SEL_THREADS)
+template <int NT>
+__global__ void __launch_bounds__(NT)
 bin_select_kernel(const int* __restrict__ row_count, const uint32_t* __restrict__ row_kp, int strips_cap, int max_rows,
                   const uint8_t* __restrict__ mask, int mask_pitch, int mask_invert, int rows, int cols, int nh, int nv,
                   float pixel_rows_per_detector, float pixel_cols_per_detector, uint32_t* __restrict__ raw,
@@ -659,12 +661,12 @@ bin_select_kernel(const int* __restrict__ row_count, const uint32_t* __restrict_
   // the launcher evaluates it once (same fp32 arithmetic) instead of every CTA walking all rows and columns
   const int4 bd = __ldg(reinterpret_cast<const int4*>(bounds) + bin);
   const int rbegin = bd.x, rend = bd.y, cbegin = bd.z, cend = bd.w;
-  // ordered gather: one thread per image row, rows in chunks of SEL_THREADS.  A row's keypoints come as one list per
+  // ordered gather: one thread per image row, rows in chunks of NT.  A row's keypoints come as one list per
   // 252-pixel strip (K1), strips in column order: only the strips that overlap the region's columns are walked.
   const int s_first = cbegin < STRIP_STRIDE + 2 ? 0 : (cbegin - 2) / STRIP_STRIDE;
   const int s_last = cend - 1 < STRIP_STRIDE + 2 ? 0 : (cend - 1 - 2) / STRIP_STRIDE;
   int running = 0;
-  for (int base = rbegin; base < rend; base += SEL_THREADS) {
+  for (int base = rbegin; base < rend; base += NT) {
     const int r = base + tid;
     int cnt = 0;
     if (r < rend) {
@@ -697,7 +699,7 @@ bin_select_kernel(const int* __restrict__ row_count, const uint32_t* __restrict_
       }
     }
     int total;
-    const int off = block_exclusive_scan<SEL_THREADS>(cnt, s_warp, &total);
+    const int off = block_exclusive_scan<NT>(cnt, s_warp, &total);
     if (cnt) {
       int o = running + off;
       for (int st = s_first; st <= s_last; ++st) {
@@ -745,14 +747,14 @@ bin_select_kernel(const int* __restrict__ row_count, const uint32_t* __restrict_
     if (kept > 0) {
       if (n <= sort_cap) {
         unsigned short* s_rpos = reinterpret_cast<unsigned short*>(s_sort + sort_cap);
-        for (int i = tid; i < n; i += SEL_THREADS) s_sort[i] = seg[i];
+        for (int i = tid; i < n; i += NT) s_sort[i] = seg[i];
         __syncthreads();
         if (tid < 32) {
           const int se = pslam_sort::warp_std_sort_prefix(s_sort, s_rpos, n, kept, RespGreater());
           if (tid == 0) s_rbegin = se;
         }
         __syncthreads();
-        pslam_sort::block_final_positions<SEL_THREADS>(s_sort, s_rbegin, kept, seg, RespGreater());
+        pslam_sort::block_final_positions<NT>(s_sort, s_rbegin, kept, seg, RespGreater());
       } else if (tid == 0) {
         pslam_sort::std_sort_prefix(seg, n, kept, RespGreater());
       }
@@ -888,7 +890,10 @@ int pslam_k_bin_select(pslam_ctx* ctx, int n_images, int rows, int cols, int nh,
   }
   dim3 grid(nh * nv, n_images);
   const int sort_cap = ctx->lim.max_raw_per_bin < 2048 ? ctx->lim.max_raw_per_bin : 2048;
-  bin_select_kernel<<<grid, SEL_THREADS, (size_t) sort_cap * 6, ctx->stream>>>(
+  // one or two images (the per-frame adaptor): 9-18 CTAs cannot fill the GPU, so each gets four times the threads
+  const bool wide = (long long) nh * nv * n_images <= 64;
+  auto kernel = wide ? bin_select_kernel<SEL_THREADS_WIDE> : bin_select_kernel<SEL_THREADS>;
+  kernel<<<grid, wide ? SEL_THREADS_WIDE : SEL_THREADS, (size_t) sort_cap * 6, ctx->stream>>>(
     ctx->d_row_count, ctx->d_row_kp, ctx->strips_cap, ctx->lim.max_rows, d_mask, ctx->map_pitch, mask_invert, rows, cols, nh, nv, pr,
     pc, ctx->d_raw, ctx->lim.max_raw_per_bin, ctx->lim.max_bins, ctx->d_raw_count, ctx->d_sel_count, quota, sort_cap,
     ctx->d_flags, ctx->d_sel_bounds);
