@@ -23,11 +23,12 @@ constexpr int EP_ROWS_LEAN = 512;   // lean variant: image rows <= 510 (KITTI 37
 constexpr int EP_ROWS = 4096;  // counting-sort path: 0 <= row < EP_ROWS (the device pipeline: row < max_rows)
 
 // ---- (row, col) sort, general path: shared-memory bitonic sort of 64-bit keys (any 32-bit row, 16-bit col) ----
+template <int NT>
 __device__ __forceinline__ void ep_sort_side(const float2* __restrict__ xy, int n, int P,
                                              unsigned long long* keys, short* row, short* col,
                                              short* idx) {
   const int tid = threadIdx.x;
-  for (int i = tid; i < P; i += EP_THREADS) {
+  for (int i = tid; i < P; i += NT) {
     unsigned long long k = ~0ULL;
     if (i < n) {
       const float2 p = xy[i];
@@ -40,7 +41,7 @@ __device__ __forceinline__ void ep_sort_side(const float2* __restrict__ xy, int 
   __syncthreads();
   for (int k = 2; k <= P; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = tid; i < P; i += EP_THREADS) {
+      for (int i = tid; i < P; i += NT) {
         const int ixj = i ^ j;
         if (ixj > i) {
           const unsigned long long a = keys[i], b = keys[ixj];
@@ -54,7 +55,7 @@ __device__ __forceinline__ void ep_sort_side(const float2* __restrict__ xy, int 
       __syncthreads();
     }
   }
-  for (int i = tid; i < n; i += EP_THREADS) {
+  for (int i = tid; i < n; i += NT) {
     const unsigned long long k = keys[i];
     row[i] = (short) (k >> 32);
     col[i] = (short) ((k >> 16) & 0xffffu);
@@ -66,22 +67,22 @@ __device__ __forceinline__ void ep_sort_side(const float2* __restrict__ xy, int 
 // ---- (row, col) sort, pipeline path: counting sort by row + per-row insertion sort by column.  Keys are unique,
 // so the result is the order std::sort gives the reference (epipolar_impl.cpp:36-41).
 // hist / cursor: ROWS + 1 unsigned shorts each; tmp: n uint32 ((col << 16) | idx)
-template <int ROWS>
+template <int ROWS, int NT>
 __device__ __forceinline__ void ep_count_sort_side(const float2* __restrict__ xy, int n, unsigned short* hist,
                                                    unsigned short* cursor, uint32_t* tmp, short* row, short* col,
                                                    short* idx, int* s_warp) {
   const int tid = threadIdx.x;
-  for (int r = tid; r <= ROWS; r += EP_THREADS) hist[r] = 0;
+  for (int r = tid; r <= ROWS; r += NT) hist[r] = 0;
   __syncthreads();
   // 16-bit shared atomics do not exist: count into the aligned 32-bit word that holds the pair
   unsigned* hist32 = reinterpret_cast<unsigned*>(hist);
-  for (int i = tid; i < n; i += EP_THREADS) {
+  for (int i = tid; i < n; i += NT) {
     const int r = (int) xy[i].y;
     atomicAdd(&hist32[r >> 1], (r & 1) ? 0x10000u : 1u);
   }
   __syncthreads();
-  // exclusive scan over rows: EP_ROWS / EP_THREADS consecutive rows per thread
-  constexpr int PER = ROWS / EP_THREADS;
+  // exclusive scan over rows: EP_ROWS / NT consecutive rows per thread
+  constexpr int PER = ROWS / NT;
   int local[PER], sum = 0;
 #pragma unroll
   for (int k = 0; k < PER; ++k) {
@@ -89,7 +90,7 @@ __device__ __forceinline__ void ep_count_sort_side(const float2* __restrict__ xy
     sum += hist[tid * PER + k];
   }
   int total;
-  const int base = block_exclusive_scan<EP_THREADS>(sum, s_warp, &total);
+  const int base = block_exclusive_scan<NT>(sum, s_warp, &total);
 #pragma unroll
   for (int k = 0; k < PER; ++k) {
     hist[tid * PER + k] = (unsigned short) (base + local[k]);  // start of row
@@ -98,7 +99,7 @@ __device__ __forceinline__ void ep_count_sort_side(const float2* __restrict__ xy
   if (tid == 0) hist[ROWS] = (unsigned short) total;
   __syncthreads();
   unsigned* cur32 = reinterpret_cast<unsigned*>(cursor);
-  for (int i = tid; i < n; i += EP_THREADS) {
+  for (int i = tid; i < n; i += NT) {
     const float2 p = xy[i];
     const int r = (int) p.y, c = (int) p.x;
     const unsigned old = atomicAdd(&cur32[r >> 1], (r & 1) ? 0x10000u : 1u);
@@ -108,7 +109,7 @@ __device__ __forceinline__ void ep_count_sort_side(const float2* __restrict__ xy
   }
   __syncthreads();
   // order inside a row: rank of (col, idx) among the row's entries (unique values), one thread per feature
-  for (int i = tid; i < n; i += EP_THREADS) {
+  for (int i = tid; i < n; i += NT) {
     const int r = row[i];
     const int b = hist[r], e = hist[r + 1];
     const uint32_t v = tmp[i];
@@ -121,15 +122,16 @@ __device__ __forceinline__ void ep_count_sort_side(const float2* __restrict__ xy
 }
 
 // ordered in-place removal of flagged entries from (row, col, idx); tmp >= 3*n shorts
+template <int NT>
 __device__ __forceinline__ int ep_compact(short* row, short* col, short* idx, int n,
                                           const unsigned char* removed, short* tmp, int* s_warp) {
   const int tid = threadIdx.x;
   int running = 0;
-  for (int base = 0; base < n; base += EP_THREADS) {
+  for (int base = 0; base < n; base += NT) {
     const int i = base + tid;
     const int keep = (i < n && !removed[i]) ? 1 : 0;
     int total;
-    const int off = block_exclusive_scan<EP_THREADS>(keep, s_warp, &total);
+    const int off = block_exclusive_scan<NT>(keep, s_warp, &total);
     if (keep) {
       const int o = running + off;
       tmp[3 * o] = row[i];
@@ -139,7 +141,7 @@ __device__ __forceinline__ int ep_compact(short* row, short* col, short* idx, in
     running += total;
   }
   __syncthreads();
-  for (int i = tid; i < running; i += EP_THREADS) {
+  for (int i = tid; i < running; i += NT) {
     row[i] = tmp[3 * i];
     col[i] = tmp[3 * i + 1];
     idx[i] = tmp[3 * i + 2];
@@ -159,8 +161,8 @@ __device__ __forceinline__ int ep_compact(short* row, short* col, short* idx, in
 // LEAN (pipeline path, thickness 0, image rows <= EP_ROWS_LEAN - 2): one pass, so nothing is ever removed -- no used
 // flags, no row array of the right side after its sort, run starts bounded by the image height, and a histogram of
 // EP_ROWS_LEAN instead of EP_ROWS rows: 16 instead of 26 bytes of shared memory per feature, 3 instead of 2 CTAs per SM.
-template <bool GENERAL, bool LEAN>
-__global__ void __launch_bounds__(EP_THREADS)
+template <bool GENERAL, bool LEAN, int NT>
+__global__ void __launch_bounds__(NT)
 epipolar_kernel(const float2* __restrict__ xy, const uint32_t* __restrict__ desc,
                 const int* __restrict__ count, int M, float max_dist, float max_ratio, int max_disp,
                 int thickness, int* __restrict__ ep_fixed, int* __restrict__ ep_moving,
@@ -208,14 +210,14 @@ epipolar_kernel(const float2* __restrict__ xy, const uint32_t* __restrict__ desc
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem);
     int P = 1;
     while (P < max(nL, nR)) P <<= 1;
-    ep_sort_side(xyL, nL, P, keys, rowL, colL, idxL);
-    ep_sort_side(xyR, nR, P, keys, rowR, colR, idxR);
+    ep_sort_side<NT>(xyL, nL, P, keys, rowL, colL, idxL);
+    ep_sort_side<NT>(xyR, nR, P, keys, rowR, colR, idxR);
   } else {
     unsigned short* hist = reinterpret_cast<unsigned short*>(smem);
     unsigned short* cursor = hist + ROWS + 2;
     uint32_t* tmp = reinterpret_cast<uint32_t*>(match);  // match + dist = 4 M bytes, not in use yet
-    ep_count_sort_side<ROWS>(xyL, nL, hist, cursor, tmp, rowL, colL, idxL, s_warp);
-    ep_count_sort_side<ROWS>(xyR, nR, hist, cursor, tmp, rowR, colR, idxR, s_warp);
+    ep_count_sort_side<ROWS, NT>(xyL, nL, hist, cursor, tmp, rowL, colL, idxL, s_warp);
+    ep_count_sort_side<ROWS, NT>(xyR, nR, hist, cursor, tmp, rowR, colR, idxR, s_warp);
   }
 
   int* o_fixed = ep_fixed + (size_t) pair * M;
@@ -227,19 +229,19 @@ epipolar_kernel(const float2* __restrict__ xy, const uint32_t* __restrict__ desc
   for (int oi = 0; oi < n_offsets; ++oi) {
     // row offsets 0, +1, -1, +2, -2, ...  (epipolar_impl.cpp:72-79)
     const int off = (oi == 0) ? 0 : ((oi & 1) ? (oi + 1) / 2 : -(oi / 2));
-    for (int i = tid; i < nL; i += EP_THREADS) {
+    for (int i = tid; i < nL; i += NT) {
       match[i] = -1;
       if (!LEAN) usedL[i] = 0;
     }
     if (!LEAN)
-      for (int i = tid; i < nR; i += EP_THREADS) usedR[i] = 0;
+      for (int i = tid; i < nR; i += NT) usedR[i] = 0;
     // ordered list of the left row-run starts
     int n_runs = 0;
-    for (int base = 0; base < nL; base += EP_THREADS) {
+    for (int base = 0; base < nL; base += NT) {
       const int i = base + tid;
       const int is_start = (i < nL && (i == 0 || rowL[i] != rowL[i - 1])) ? 1 : 0;
       int total;
-      const int o = block_exclusive_scan<EP_THREADS>(is_start, s_warp, &total);
+      const int o = block_exclusive_scan<NT>(is_start, s_warp, &total);
       if (is_start) runs[n_runs + o] = (short) i;
       n_runs += total;
     }
@@ -381,11 +383,11 @@ epipolar_kernel(const float2* __restrict__ xy, const uint32_t* __restrict__ desc
     }
     __syncthreads();
     // emit this pass's matches in scan order
-    for (int base = 0; base < nL; base += EP_THREADS) {
+    for (int base = 0; base < nL; base += NT) {
       const int i = base + tid;
       const int has = (i < nL && match[i] >= 0) ? 1 : 0;
       int total;
-      const int o = block_exclusive_scan<EP_THREADS>(has, s_warp, &total);
+      const int o = block_exclusive_scan<NT>(has, s_warp, &total);
       if (has) {
         const int k = n_out + o;
         if (k < M) {
@@ -399,8 +401,8 @@ epipolar_kernel(const float2* __restrict__ xy, const uint32_t* __restrict__ desc
     if (!LEAN && oi + 1 < n_offsets) {  // prune matched candidates, keeping the order (:189-205)
       __syncthreads();
       short* ctmp = reinterpret_cast<short*>(smem);  // the sort scratch holds >= 3 * M shorts (ep_smem_bytes)
-      nL = ep_compact(rowL, colL, idxL, nL, usedL, ctmp, s_warp);
-      nR = ep_compact(rowR, colR, idxR, nR, usedR, ctmp, s_warp);
+      nL = ep_compact<NT>(rowL, colL, idxL, nL, usedL, ctmp, s_warp);
+      nR = ep_compact<NT>(rowR, colR, idxR, nR, usedR, ctmp, s_warp);
     }
   }
   if (n_out > M) n_out = M;
@@ -415,7 +417,7 @@ epipolar_kernel(const float2* __restrict__ xy, const uint32_t* __restrict__ desc
   int* s_r = st_right + (size_t) pair * M;
   float* s_d = st_dist + (size_t) pair * M;
   int n_st = 0;
-  for (int base = 0; base < n_out; base += EP_THREADS) {
+  for (int base = 0; base < n_out; base += NT) {
     const int k = base + tid;
     int keep = 0, f = 0, m = 0;
     float4 p = make_float4(0, 0, 0, 0);
@@ -427,7 +429,7 @@ epipolar_kernel(const float2* __restrict__ xy, const uint32_t* __restrict__ desc
       keep = !((l.x - r.x) < 0.0f || (l.y - r.y) < 0.0f);
     }
     int total;
-    const int o = block_exclusive_scan<EP_THREADS>(keep, s_warp, &total);
+    const int o = block_exclusive_scan<NT>(keep, s_warp, &total);
     if (keep) {
       s_uvuv[n_st + o] = p;
       s_l[n_st + o] = f;
@@ -562,9 +564,14 @@ int pslam_k_epipolar(pslam_ctx* ctx, int n_pairs, const pslam_match_cfg* cfg, in
   const int thickness = cfg->epipolar_line_thickness_pixels < 0 ? 0 : cfg->epipolar_line_thickness_pixels;
   const bool lean = !general && thickness == 0 && ctx->lim.max_rows <= EP_ROWS_LEAN - 2;
   const size_t smem = ep_smem_bytes(M, general != 0, lean);
-  auto kernel = general ? epipolar_kernel<true, false> : (lean ? epipolar_kernel<false, true> : epipolar_kernel<false, false>);
+  // a handful of pairs (the per-frame adaptor: ONE) cannot fill the GPU with one CTA each: twice the warps per CTA take the
+  // dynamically handed-out row runs in half the time (61 -> 40 us for one KITTI pair)
+  const bool wide = lean && n_pairs <= 32;
+  auto kernel = general ? epipolar_kernel<true, false, EP_THREADS>
+                        : (lean ? (wide ? epipolar_kernel<false, true, 2 * EP_THREADS> : epipolar_kernel<false, true, EP_THREADS>)
+                                : epipolar_kernel<false, false, EP_THREADS>);
   if (smem > 48 * 1024) PSLAM_CUDA_TRY(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-  kernel<<<n_pairs, EP_THREADS, smem, ctx->stream>>>(
+  kernel<<<n_pairs, wide ? 2 * EP_THREADS : EP_THREADS, smem, ctx->stream>>>(
     ctx->d_xy, ctx->d_desc, ctx->d_count, M, cfg->maximum_descriptor_distance,
     cfg->maximum_distance_ratio_to_second_best, cfg->maximum_disparity_pixels,
     thickness, ctx->d_ep_fixed, ctx->d_ep_moving, ctx->d_ep_dist,
