@@ -91,7 +91,9 @@ def test_gn_not_spd(ctx):
     assert e.value.code == capi.PSLAM_E_NOT_SPD
 
 
-@pytest.mark.parametrize("kind,damping,n", [("stereo", 1.0, 400), ("depth", 0.1, 37), ("mono", 0.0, 3000)])
+# sizes on both sides of the kernel's regimes: <= 96 shared-memory reduction, <= 256 one correspondence per thread, above: grid-stride
+@pytest.mark.parametrize("kind,damping,n", [("stereo", 1.0, 400), ("depth", 0.1, 37), ("mono", 0.0, 3000), ("depth", 0.1, 96),
+                                            ("stereo", 1.0, 97), ("stereo", 1.0, 150), ("mono", 0.0, 256), ("depth", 1.0, 257)])
 def test_gn_iterate_fused(ctx, kind, damping, n):
     """pslam_gn_iterate: K solver iterations in one launch == K x (linearise + GN step) of the oracle"""
     xyz, meas, cf, cm, info, pose = synth(n, kind, 5 + n, outlier_frac=0.05)
@@ -152,7 +154,8 @@ def test_linearize_f32_prior_status(ctx, kind, n, with_prior):
     assert abs(sg["prior_chi"] - so["prior_chi"]) <= RTOL * max(abs(so["prior_chi"]), 1e-300)
 
 
-@pytest.mark.parametrize("kind,damping,n", [("stereo", 1.0, 400), ("depth", 0.1, 37), ("mono", 0.0, 3000)])
+@pytest.mark.parametrize("kind,damping,n", [("stereo", 1.0, 400), ("depth", 0.1, 37), ("mono", 0.0, 3000), ("stereo", 1.0, 96),
+                                            ("depth", 0.1, 97), ("stereo", 1.0, 256)])
 def test_gn_iterate_f32_with_prior(ctx, kind, damping, n):
     """the fused launch with the motion-model slice's factor inside == K x (linearise + prior + GN step) of the oracle"""
     xyz, meas, cf, cm, info, pose = synth(n, kind, 5 + n, outlier_frac=0.05)
