@@ -243,6 +243,14 @@ def tracking_lines(ctx, capi, stream, dev):
                         "correspondences": n, "fp64_tflops": flop / (ms * 1e-3) / 1e12,
                         "bytes_per_correspondence": 24 + 32 + 24 + 8,
                         "hbm_gbs": n * 88 / (ms * 1e-3) / 1e9}
+    # the reference's own scalar: fp32 clouds in HBM, widened in registers (pslam_linearize_se3_f32) -- 3 + 4 + 3 floats + 2 indices
+    try:
+        ms32 = ctx.linearize_timed_f32(cfg, np.eye(3, 4).reshape(12), xyzb.astype(np.float32), measb.astype(np.float32), idx, idx,
+                                       info.astype(np.float32), reps=10)
+        out["linearize"]["f32_clouds"] = {"value": n / (ms32 * 1e-3) / 1e9, "unit": "GCorr/s", "ms": ms32,
+                                          "bytes_per_correspondence": 12 + 16 + 12 + 8, "hbm_gbs": n * 48 / (ms32 * 1e-3) / 1e9}
+    except Exception as e:
+        out["linearize"]["f32_clouds"] = {"error": repr(e)}
     return out
 
 
