@@ -6,7 +6,8 @@
 // with RobustifierSaturated / RobustifierClamp (external code; wiring at
 // .../registration/aligner_slice_processor_projective.cpp:27-112, use at tests/test_aligners.cpp:586-638,
 // in-tree analogue of the accumulate loop: .../mapping/landmarks/landmark_estimator_pose_based_smoother_impl.cpp:48-106).
-// The arithmetic (operation order included) is that of oracle/pslam_oracle_solver.hpp.
+// The arithmetic is that of oracle/pslam_oracle_solver.hpp evaluated with fused multiply-adds (see error_and_jacobian); the
+// parity contract with the fp64 oracle is 1e-9 relative on H, b (tests/test_gpu_solver.py).
 //
 // One thread per correspondence (grid-stride), 21 + 6 + 1 fp64 partial sums and 3 counters per
 // thread, warp-shuffle tree, one partial row per CTA, a last single-CTA pass adds the rows in
@@ -34,21 +35,22 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// fp64 fused multiply-adds throughout: the fp64 pipe issues one warp instruction every two cycles, so the instruction count IS
+// the cost (batched: issue-bound; per frame: the head of every solver iteration).  Against the oracle's separately rounded
+// operations this differs in the last bits (relative 1e-15 on H, b; the parity contract is 1e-9).
 __device__ __forceinline__ bool error_and_jacobian(const LinParams& c, const double* pm,
                                                    const double* z, double* e, double* J) {
   const double* R = c.R;
   double pc[3];
 #pragma unroll
-  for (int i = 0; i < 3; ++i)
-    pc[i] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(R[3 * i], pm[0]), __dmul_rn(R[3 * i + 1], pm[1])),
-                                __dmul_rn(R[3 * i + 2], pm[2])), c.t[i]);
+  for (int i = 0; i < 3; ++i) pc[i] = fma(R[3 * i], pm[0], fma(R[3 * i + 1], pm[1], fma(R[3 * i + 2], pm[2], c.t[i])));
   if (pc[2] <= 0) return false;
   const double* K = c.K;
-  const double hx = __dadd_rn(__dadd_rn(__dmul_rn(K[0], pc[0]), __dmul_rn(K[1], pc[1])), __dmul_rn(K[2], pc[2]));
-  const double hy = __dadd_rn(__dadd_rn(__dmul_rn(K[3], pc[0]), __dmul_rn(K[4], pc[1])), __dmul_rn(K[5], pc[2]));
-  const double hz = __dadd_rn(__dadd_rn(__dmul_rn(K[6], pc[0]), __dmul_rn(K[7], pc[1])), __dmul_rn(K[8], pc[2]));
+  const double hx = fma(K[0], pc[0], fma(K[1], pc[1], K[2] * pc[2]));
+  const double hy = fma(K[3], pc[0], fma(K[4], pc[1], K[5] * pc[2]));
+  const double hz = fma(K[6], pc[0], fma(K[7], pc[1], K[8] * pc[2]));
   const double iz = __ddiv_rn(1.0, hz);
-  const double u = __dmul_rn(hx, iz), v = __dmul_rn(hy, iz);
+  const double u = hx * iz, v = hy * iz;
   if (u < 0 || u > c.cols || v < 0 || v > c.rows) return false;
   double Jx[18];
 #pragma unroll
@@ -56,42 +58,40 @@ __device__ __forceinline__ bool error_and_jacobian(const LinParams& c, const dou
     Jx[6 * i + 0] = R[3 * i + 0];
     Jx[6 * i + 1] = R[3 * i + 1];
     Jx[6 * i + 2] = R[3 * i + 2];
-    Jx[6 * i + 3] = __dmul_rn(-2.0, __dsub_rn(__dmul_rn(R[3 * i + 1], pm[2]), __dmul_rn(R[3 * i + 2], pm[1])));
-    Jx[6 * i + 4] = __dmul_rn(-2.0, __dadd_rn(__dmul_rn(-R[3 * i + 0], pm[2]), __dmul_rn(R[3 * i + 2], pm[0])));
-    Jx[6 * i + 5] = __dmul_rn(-2.0, __dsub_rn(__dmul_rn(R[3 * i + 0], pm[1]), __dmul_rn(R[3 * i + 1], pm[0])));
+    Jx[6 * i + 3] = -2.0 * fma(R[3 * i + 1], pm[2], -(R[3 * i + 2] * pm[1]));
+    Jx[6 * i + 4] = -2.0 * fma(R[3 * i + 2], pm[0], -(R[3 * i + 0] * pm[2]));
+    Jx[6 * i + 5] = -2.0 * fma(R[3 * i + 0], pm[1], -(R[3 * i + 1] * pm[0]));
   }
   double KJ[18];
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
-    for (int j = 0; j < 6; ++j)
-      KJ[6 * i + j] = __dadd_rn(__dadd_rn(__dmul_rn(K[3 * i], Jx[j]), __dmul_rn(K[3 * i + 1], Jx[6 + j])),
-                                __dmul_rn(K[3 * i + 2], Jx[12 + j]));
-  const double iz2 = __dmul_rn(iz, iz);
-  const double hx_iz2 = __dmul_rn(hx, iz2), hy_iz2 = __dmul_rn(hy, iz2);
+    for (int j = 0; j < 6; ++j) KJ[6 * i + j] = fma(K[3 * i], Jx[j], fma(K[3 * i + 1], Jx[6 + j], K[3 * i + 2] * Jx[12 + j]));
+  const double iz2 = iz * iz;
+  const double hx_iz2 = hx * iz2, hy_iz2 = hy * iz2;
 #pragma unroll
   for (int j = 0; j < 6; ++j) {
-    J[j] = __dsub_rn(__dmul_rn(KJ[j], iz), __dmul_rn(hx_iz2, KJ[12 + j]));
-    J[6 + j] = __dsub_rn(__dmul_rn(KJ[6 + j], iz), __dmul_rn(hy_iz2, KJ[12 + j]));
+    J[j] = fma(KJ[j], iz, -(hx_iz2 * KJ[12 + j]));
+    J[6 + j] = fma(KJ[6 + j], iz, -(hy_iz2 * KJ[12 + j]));
   }
-  e[0] = __dsub_rn(u, z[0]);
-  e[1] = __dsub_rn(v, z[1]);
+  e[0] = u - z[0];
+  e[1] = v - z[1];
   if (c.kind == 0) {
-    const double hxr = __dadd_rn(hx, c.baseline[0]);
-    e[2] = __dsub_rn(__dmul_rn(hxr, iz), z[2]);
-    const double hxr_iz2 = __dmul_rn(hxr, iz2);
+    const double hxr = hx + c.baseline[0];
+    e[2] = fma(hxr, iz, -z[2]);
+    const double hxr_iz2 = hxr * iz2;
 #pragma unroll
-    for (int j = 0; j < 6; ++j) J[12 + j] = __dsub_rn(__dmul_rn(KJ[j], iz), __dmul_rn(hxr_iz2, KJ[12 + j]));
+    for (int j = 0; j < 6; ++j) J[12 + j] = fma(KJ[j], iz, -(hxr_iz2 * KJ[12 + j]));
     if (c.mean_disparity > 0) {
-      double w = __dadd_rn(0.01, __ddiv_rn(__dsub_rn(z[0], z[2]), c.mean_disparity));
+      double w = 0.01 + __ddiv_rn(z[0] - z[2], c.mean_disparity);
       if (w > 1) w = 1;
 #pragma unroll
       for (int i = 0; i < 3; ++i)
 #pragma unroll
-        for (int j = 0; j < 3; ++j) J[6 * i + j] = __dmul_rn(J[6 * i + j], w);
+        for (int j = 0; j < 3; ++j) J[6 * i + j] *= w;
     }
   } else if (c.kind == 1) {
-    e[2] = __dsub_rn(pc[2], z[2]);
+    e[2] = pc[2] - z[2];
 #pragma unroll
     for (int j = 0; j < 6; ++j) J[12 + j] = Jx[12 + j];
   } else {
@@ -102,9 +102,6 @@ __device__ __forceinline__ bool error_and_jacobian(const LinParams& c, const dou
   return true;
 }
 
-// accumulate one correspondence into the thread's partial sums (FactorCorrespondenceDriven_::compute analogue).
-// T = scalar type of the clouds in HBM: float (the reference's own cloud type: 40 B per correspondence, widened to
-// fp64 in registers -- exact) or double.  status (may be nullptr): 0 inlier, 1 kernelized, 2 suppressed.
 // one correspondence as the factor reads it: moving point, fixed measurement, information diagonal -- widened to fp64 (exact)
 struct CorrData {
   double pm[3], z[3], om[3];
@@ -133,7 +130,7 @@ __device__ __forceinline__ void accumulate_loaded(const LinParams& c, int edim, 
   }
   const double* om = d.om;
   double chi = 0;
-  for (int i = 0; i < edim; ++i) chi = __dadd_rn(chi, __dmul_rn(__dmul_rn(e[i], om[i]), e[i]));
+  for (int i = 0; i < edim; ++i) chi = fma(e[i] * om[i], e[i], chi);
   double scale = 1;
   if (c.robustifier != 0 && chi > c.chi_threshold) {
     acc[29] += 1;
@@ -143,16 +140,16 @@ __device__ __forceinline__ void accumulate_loaded(const LinParams& c, int edim, 
     acc[28] += 1;
     if (status) *status = 0;
   }
-  acc[27] += __dmul_rn(chi, scale);
+  acc[27] = fma(chi, scale, acc[27]);
   for (int i = 0; i < edim; ++i) {
-    const double w = __dmul_rn(om[i], scale);
+    const double w = om[i] * scale;
     int h = 0;
 #pragma unroll
     for (int a = 0; a < 6; ++a) {
-      const double Jw = __dmul_rn(J[6 * i + a], w);
-      acc[21 + a] += __dmul_rn(Jw, e[i]);
+      const double Jw = J[6 * i + a] * w;
+      acc[21 + a] = fma(Jw, e[i], acc[21 + a]);
 #pragma unroll
-      for (int b = a; b < 6; ++b) acc[h++] += __dmul_rn(Jw, J[6 * i + b]);
+      for (int b = a; b < 6; ++b, ++h) acc[h] = fma(Jw, J[6 * i + b], acc[h]);
     }
   }
 }
