@@ -254,6 +254,53 @@ def tracking_lines(ctx, capi, stream, dev):
     return out
 
 
+def natural_images_line(capi, dev, work_images):
+    """The same device-resident stereo frontend on NATURAL images: the five KITTI pairs of tests/golden (the reference's
+    test_data) tiled to 2 000 pairs.  The synthetic batch of the headline is far richer in FAST candidates than a photograph
+    (17.7 % of the pixels pass the compass pre-test there); this line shows what the kernels do on real texture."""
+    import cv2
+    import torch
+    G = ROOT / "tests" / "golden"
+    pairs = [np.stack([cv2.imread(str(G / f"kitti_city_image_{s_}_{i}.png"), cv2.IMREAD_UNCHANGED) for s_ in ("left", "right")])
+             for i in range(5)]
+    reps, P = 400, 2000
+    batch = torch.from_numpy(np.stack(pairs)).to(dev).repeat(reps, 1, 1, 1).contiguous()  # [2000, 2, 376, 1241]
+    ctx = capi.Context(device=dev.index or 0, max_images=2 * P, max_rows=ROWS, max_cols=COLS, max_features=4096,
+                       max_raw_per_bin=8192, max_bins=9, work_images=work_images)
+    try:
+        ecfg, mcfg = capi.extract_cfg(THRESHOLD, 1, TARGET), capi.match_cfg(**MATCH)
+        stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+        run = lambda: ctx.stereo_frontend_batch_dev(batch.data_ptr(), P, ROWS, COLS, COLS, ROWS * COLS, ecfg, mcfg)
+        for _ in range(3):
+            run()
+        ctx.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(5):
+            run()
+        e1.record(stream)
+        ctx.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        counts = ctx.stereo_counts(P)
+        feats = ctx.feature_counts(2 * P) if hasattr(ctx, "feature_counts") else None
+        ctx.set_lanes(1)
+        run()
+        ctx.profile_enable(True)
+        ctx.synchronize()
+        run()
+        prof = ctx.profile_read()
+        ctx.profile_enable(False)
+        return {"metric": "frontend_stereo_frames_per_s", "value": P / (ms * 1e-3), "unit": "frames/s", "ms_per_step": ms,
+                "config": "5 KITTI stereo pairs of tests/golden (1241x376, the reference's test_data) tiled to 2 000 pairs, same detector / "
+                          "matcher parameters as the headline",
+                "mean_stereo_points_per_frame": float(counts.mean()),
+                "mean_features_per_image": None if feats is None else float(np.mean(feats)),
+                "kernels_us_per_image": {k: 1e3 * v[0] / (2 * P) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}}
+    finally:
+        ctx.close()
+        del batch
+
+
 def scene_traffic():
     tr = ROOT / "profiles" / "traffic.json"
     if tr.exists():
@@ -693,6 +740,11 @@ def main():
                 line["hamming"]["match_bruteforce"] = {"error": repr(e)}
 
     # ---- sequential stage (latency in microseconds, FP64 throughput on a batched synthetic) ------
+    if rank == 0 and not args.no_tracking:
+        try:
+            line["natural_images"] = natural_images_line(capi, dev, args.work_images)
+        except Exception as e:
+            line["natural_images"] = {"error": repr(e)}
     if rank == 0 and not args.no_tracking:
         try:
             line["tracking"] = tracking_lines(ctx, capi, stream, dev)
