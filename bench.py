@@ -654,13 +654,19 @@ def main():
         if world > 1:
             # preferred: exchange fused into the merge kernel (peer tables over CUDA IPC + NVLink, no collective); fallback: the
             # NCCL all-gather entry point
+            mine = None
             try:
-                handles = [None] * world
-                dist.all_gather_object(handles, ctx.p2p_table_export(nq))
-                ctx.p2p_table_import(rank, world, handles)
-                p2p = True
+                mine = ctx.p2p_table_export(nq)
             except Exception as e_:  # e.g. IPC not permitted in this container
-                print(f"[bench] p2p tables unavailable ({e_!r}), using the NCCL entry point", file=sys.stderr)
+                print(f"[bench] p2p table export failed ({e_!r})", file=sys.stderr)
+            handles = [None] * world
+            dist.all_gather_object(handles, mine)  # every rank takes part, whatever happened above
+            if all(h is not None for h in handles):
+                try:
+                    ctx.p2p_table_import(rank, world, handles)
+                    p2p = True
+                except Exception as e_:
+                    print(f"[bench] p2p table import failed ({e_!r}), using the NCCL entry point", file=sys.stderr)
             flag = torch.tensor([int(p2p)], device=dev)
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
             p2p = bool(flag.item())
@@ -693,9 +699,9 @@ def main():
         gpairs = nq * nt * reps / (float(hms.item()) * 1e-3) / 1e9
         if comm is not None:
             ctx.nccl_comm_destroy(comm)
-        if p2p:
+        if world > 1:
             barrier()
-            ctx.p2p_table_release()
+            ctx.p2p_table_release()  # no-op when nothing was exported
         sm_mhz = line["clocks"]["sm_mhz"] or 1965.0
         # Roofline of the sweep = the busier of the two integer pipes for the kernel's instruction mix per 256-bit pair
         # (SASS of bf_sweep_kernel<0>: 5 POPC on the XU pipe; 15 LOP3 + 1 IADD3 + 3 VIMNMX on the ALU pipe), with the pipe

@@ -12,6 +12,8 @@
 // the system's): the library itself links neither NCCL nor libcuda, and single-GPU users never touch it.
 #include <dlfcn.h>
 
+#include <mutex>
+
 #include "pslam_internal.cuh"
 #include "pslam_kernels.cuh"
 
@@ -31,9 +33,8 @@ constexpr int NCCL_INT32 = 2;  // ncclInt32
 
 NcclApi* nccl_api(pslam_ctx* ctx) {
   static NcclApi api;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
+  static std::once_flag once;
+  std::call_once(once, [] {
     const char* names[] = {"libnccl.so.2", "libnccl.so"};
     for (const char* n : names)
       if ((api.handle = dlopen(n, RTLD_NOW | RTLD_NOLOAD))) break;  // the copy the process already uses
@@ -47,7 +48,7 @@ NcclApi* nccl_api(pslam_ctx* ctx) {
       api.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t)) dlsym(api.handle, "ncclAllGather");
       api.GetErrorString = (const char* (*) (int) ) dlsym(api.handle, "ncclGetErrorString");
     }
-  }
+  });
   if (!api.handle || !api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllGather) {
     pslam_set_error(ctx, PSLAM_E_CUDA, "NCCL is not available in this process (libnccl.so.2 could not be loaded)", cudaSuccess);
     return nullptr;
@@ -84,11 +85,19 @@ __global__ void p2p_signal_kernel(int* const* __restrict__ peers, int world, int
   }
 }
 // wait until every source rank has written this epoch into OUR table, then hand the table out
+// The wait is BOUNDED (~4 s of SM clocks): a rank that never signals (crashed process, mismatched call sequence) must not
+// leave this GPU spinning forever; the caller sees PSLAM_FLAG_P2P_TIMEOUT at the next status check and a table with stale rows.
 __global__ void p2p_wait_copy_kernel(const int* __restrict__ table, size_t flags_offset, int world, int epoch, int cap_rows, int parity,
-                                     int n, int* __restrict__ best, int* __restrict__ second, int* __restrict__ idx) {
+                                     int n, int* __restrict__ best, int* __restrict__ second, int* __restrict__ idx,
+                                     int* __restrict__ status_flags) {
   if ((int) threadIdx.x < world) {
     const volatile int* f = table + flags_offset;
+    const long long t0 = clock64();
     while (f[threadIdx.x] < epoch) {
+      if (clock64() - t0 > 8000000000LL) {
+        atomicOr(status_flags, PSLAM_FLAG_P2P_TIMEOUT);
+        break;
+      }
     }
   }
   __syncthreads();
@@ -125,6 +134,7 @@ int pslam_p2p_table_export(pslam_ctx* ctx, int max_rows, PslamIpcHandle* mine) {
 int pslam_p2p_table_import(pslam_ctx* ctx, int rank, int world, const PslamIpcHandle* all) {
   if (!ctx || !all || world <= 0 || world > P2P_FLAGS || rank < 0 || rank >= world) return PSLAM_E_INVALID;
   if (!ctx->d_p2p_table) return pslam_set_error(ctx, PSLAM_E_INVALID, "p2p: export this rank's table first", cudaSuccess);
+  if (ctx->d_p2p_peers) return pslam_set_error(ctx, PSLAM_E_INVALID, "p2p: peers already imported (release the table first)", cudaSuccess);
   PSLAM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   for (int r = 0; r < world; ++r) {
     if (r == rank) {
@@ -181,7 +191,7 @@ int pslam_bf_best2_sharded_p2p_dev(pslam_ctx* ctx, int n_fixed, const uint32_t* 
   p2p_signal_kernel<<<1, P2P_FLAGS, 0, ctx->stream>>>(ctx->d_p2p_peers, world, rank, flags_offset, epoch);
   PSLAM_LAUNCH_CHECK(ctx, "p2p_signal_kernel");
   p2p_wait_copy_kernel<<<(n_fixed + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_p2p_table, flags_offset, world, epoch, ctx->p2p_cap_rows,
-                                                                     parity, n_fixed, d_best, d_second, d_best_idx);
+                                                                     parity, n_fixed, d_best, d_second, d_best_idx, ctx->d_flags);
   PSLAM_LAUNCH_CHECK(ctx, "p2p_wait_copy_kernel");
   return PSLAM_OK;
 }

@@ -99,7 +99,7 @@ int check_flags(pslam_ctx* ctx) {
   PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   if (h[0]) {
     char msg[160];
-    snprintf(msg, sizeof(msg), "capacity exceeded (flags=%d: 1 max_raw_per_bin, 2 max_features, 4 candidates)", h[0]);
+    snprintf(msg, sizeof(msg), "capacity exceeded (flags=%d: 1 max_raw_per_bin, 2 max_features, 4 candidates, 8 a peer never signalled its rows of a sharded sweep)", h[0]);
     PSLAM_CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_flags, 0, sizeof(int), ctx->stream));
     return pslam_set_error(ctx, PSLAM_E_CAPACITY, msg, cudaSuccess);
   }

@@ -140,6 +140,7 @@ void pslam_prof_mark(pslam_ctx* ctx, const char* name);  // pslam_capi.cu
 #define PSLAM_FLAG_RAW_OVERFLOW 1
 #define PSLAM_FLAG_FEATURE_OVERFLOW 2
 #define PSLAM_FLAG_CANDIDATE_OVERFLOW 4
+#define PSLAM_FLAG_P2P_TIMEOUT 8
 
 static inline int pslam_set_error(pslam_ctx* ctx, int code, const char* what, cudaError_t e) {
   if (ctx) {
