@@ -33,6 +33,22 @@ def main():
             t0 = time.perf_counter()
             fi, mi, d = ctx.match_bruteforce(q, t, capi.match_cfg(50, 0.9))
             print("matches", len(fi), "s", time.perf_counter() - t0)
+    elif what == "natural":
+        # stage 1 + stereo match on the five real KITTI pairs of tests/golden tiled to 384 pairs (one 768-image chunk)
+        import cv2
+        G = ROOT / "tests" / "golden"
+        pairs = [np.stack([cv2.imread(str(G / f"kitti_city_image_{s_}_{i}.png"), cv2.IMREAD_UNCHANGED) for s_ in ("left", "right")])
+                 for i in range(5)]
+        P = 385
+        batch = torch.from_numpy(np.stack(pairs)).to(dev).repeat(77, 1, 1, 1).contiguous()
+        big = capi.Context(device=0, max_images=2 * P, max_rows=376, max_cols=1241, max_features=4096, max_raw_per_bin=8192,
+                           max_bins=9, work_images=768)
+        for _ in range(3):
+            big.stereo_frontend_batch_dev(batch.data_ptr(), P, 376, 1241, 1241, 376 * 1241, capi.extract_cfg(15, 1, 4000),
+                                          capi.match_cfg(100.0, 0.5, 100, 0))
+        big.synchronize()
+        print("stereo points per frame", float(big.stereo_counts(P).mean()))
+        big.close()
     elif what == "linearize":
         n = 1 << 22
         K = np.array([718.856, 0, 607.193, 0, 718.856, 185.216, 0, 0, 1], np.float32)
