@@ -54,3 +54,28 @@ def test_sort_replay_matches_libstdcxx(tmp_path):
                     str(ROOT / "tests" / "native" / "sort_emul_check.cpp")], check=True)
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.startswith("OK"), r.stdout
+
+
+def _build_native_caller(tmp_path):
+    exe = tmp_path / "abi_smoke"
+    lib_dir = ROOT / "srrg2_proslam_b200"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", str(ROOT / "include"),
+                    str(ROOT / "tests" / "native" / "abi_smoke.c"), "-L", str(lib_dir), "-lpslam_cuda",
+                    f"-Wl,-rpath,{lib_dir}", "-o", str(exe)], check=True)
+    return exe
+
+
+def test_headers_are_plain_c99_and_a_native_caller_links(built, tmp_path):
+    """the drop-in boundary is a C ABI: both public headers compile as C99 (-pedantic) and a C program links against the
+    library without Python / C++ / torch; without a GPU it must be refused with PSLAM_E_CUDA (tests/native/abi_smoke.c)"""
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "pslam_cuda.h"\n#include "pslam_plugin.h"\nint main(void) { return 0; }\n')
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", str(ROOT / "include"),
+                    str(src)], check=True)
+    exe = _build_native_caller(tmp_path)
+    import torch
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    if torch.cuda.is_available():
+        assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr
+    else:
+        assert r.returncode == 3 and "NO_DEVICE" in r.stdout, r.stdout + r.stderr

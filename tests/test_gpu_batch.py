@@ -192,3 +192,12 @@ def test_chunk_lanes_give_identical_results(oracle):
         assert np.array_equal(outs[0][1][3], ref["uvuv"])
     finally:
         ctx.close()
+
+
+def test_native_c_caller(tmp_path):
+    """tests/native/abi_smoke.c: a C99 program against include/pslam_cuda.h + libpslam_cuda.so -- extraction and the stereo
+    adaptor on a synthetic pair (right = left shifted by 12 px: every stereo point has disparity 12), deterministic"""
+    from test_cpu_abi import _build_native_caller
+    import subprocess
+    r = subprocess.run([str(_build_native_caller(tmp_path))], capture_output=True, text=True)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr
