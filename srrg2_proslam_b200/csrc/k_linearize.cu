@@ -509,58 +509,60 @@ __device__ __forceinline__ void pose_prior_accumulate_warp(const PriorParams& pr
   __syncwarp();
 }
 
+// (H + damping I) dx = -b by 3x3 block elimination with closed-form (adjugate) inverses of the translation block A and of its
+// Schur complement S = C - B^T A^-1 B.  Same solution as the Cholesky of gn_solve_update (H is symmetric positive definite
+// and well conditioned under the damping the shipped solvers use; differences ~1e-12 relative on dx), but the dependent chain
+// holds TWO reciprocals instead of six reciprocal square roots + a backward substitution: every product is independent of its
+// neighbours, one thread pipelines them.  Positive definiteness = Sylvester's criterion on A and S.  Every lane computes the
+// same thing (no exchange); returns false when H + damping I is not positive definite.
+__device__ __forceinline__ bool gn_solve6_block(const double* H, const double* bvec, double lam, double* dx) {
+  const double a00 = H[0] + lam, a01 = H[1], a02 = H[2], a11 = H[7] + lam, a12 = H[8], a22 = H[14] + lam;
+  const double b00 = H[3], b01 = H[4], b02 = H[5], b10 = H[9], b11 = H[10], b12 = H[11], b20 = H[15], b21 = H[16], b22 = H[17];
+  const double c00 = H[21] + lam, c01 = H[22], c02 = H[23], c11 = H[28] + lam, c12 = H[29], c22 = H[35] + lam;
+  const double g0 = -bvec[0], g1 = -bvec[1], g2 = -bvec[2], g3 = -bvec[3], g4 = -bvec[4], g5 = -bvec[5];
+  // adj(A) (symmetric) and det(A)
+  const double A00 = fma(a11, a22, -(a12 * a12)), A01 = fma(a02, a12, -(a01 * a22)), A02 = fma(a01, a12, -(a02 * a11));
+  const double A11 = fma(a00, a22, -(a02 * a02)), A12 = fma(a01, a02, -(a00 * a12)), A22 = fma(a00, a11, -(a01 * a01));
+  const double detA = fma(a00, A00, fma(a01, A01, a02 * A02));
+  if (!(a00 > 0) || !(A22 > 0) || !(detA > 0)) return false;
+  const double rd = __ddiv_rn(1.0, detA);
+  // Y' = adj(A) B, y' = adj(A) g1 (the 1 / det(A) is applied where they are used)
+  const double Y00 = fma(A00, b00, fma(A01, b10, A02 * b20)), Y01 = fma(A00, b01, fma(A01, b11, A02 * b21)),
+               Y02 = fma(A00, b02, fma(A01, b12, A02 * b22));
+  const double Y10 = fma(A01, b00, fma(A11, b10, A12 * b20)), Y11 = fma(A01, b01, fma(A11, b11, A12 * b21)),
+               Y12 = fma(A01, b02, fma(A11, b12, A12 * b22));
+  const double Y20 = fma(A02, b00, fma(A12, b10, A22 * b20)), Y21 = fma(A02, b01, fma(A12, b11, A22 * b21)),
+               Y22 = fma(A02, b02, fma(A12, b12, A22 * b22));
+  const double y0 = fma(A00, g0, fma(A01, g1, A02 * g2)), y1 = fma(A01, g0, fma(A11, g1, A12 * g2)),
+               y2 = fma(A02, g0, fma(A12, g1, A22 * g2));
+  // S = C - B^T Y' / det(A) (upper triangle), h = g2 - B^T y' / det(A)
+  const double s00 = fma(-rd, fma(b00, Y00, fma(b10, Y10, b20 * Y20)), c00), s01 = fma(-rd, fma(b00, Y01, fma(b10, Y11, b20 * Y21)), c01),
+               s02 = fma(-rd, fma(b00, Y02, fma(b10, Y12, b20 * Y22)), c02), s11 = fma(-rd, fma(b01, Y01, fma(b11, Y11, b21 * Y21)), c11),
+               s12 = fma(-rd, fma(b01, Y02, fma(b11, Y12, b21 * Y22)), c12), s22 = fma(-rd, fma(b02, Y02, fma(b12, Y12, b22 * Y22)), c22);
+  const double h0 = fma(-rd, fma(b00, y0, fma(b10, y1, b20 * y2)), g3), h1 = fma(-rd, fma(b01, y0, fma(b11, y1, b21 * y2)), g4),
+               h2 = fma(-rd, fma(b02, y0, fma(b12, y1, b22 * y2)), g5);
+  const double S00 = fma(s11, s22, -(s12 * s12)), S01 = fma(s02, s12, -(s01 * s22)), S02 = fma(s01, s12, -(s02 * s11));
+  const double S11 = fma(s00, s22, -(s02 * s02)), S12 = fma(s01, s02, -(s00 * s12)), S22 = fma(s00, s11, -(s01 * s01));
+  const double detS = fma(s00, S00, fma(s01, S01, s02 * S02));
+  if (!(s00 > 0) || !(S22 > 0) || !(detS > 0)) return false;
+  const double rs = __ddiv_rn(1.0, detS);
+  dx[3] = rs * fma(S00, h0, fma(S01, h1, S02 * h2));
+  dx[4] = rs * fma(S01, h0, fma(S11, h1, S12 * h2));
+  dx[5] = rs * fma(S02, h0, fma(S12, h1, S22 * h2));
+  dx[0] = rd * (y0 - fma(Y00, dx[3], fma(Y01, dx[4], Y02 * dx[5])));
+  dx[1] = rd * (y1 - fma(Y10, dx[3], fma(Y11, dx[4], Y12 * dx[5])));
+  dx[2] = rd * (y2 - fma(Y20, dx[3], fma(Y21, dx[4], Y22 * dx[5])));
+  return true;
+}
+
 // (H + damping I) dx = -b by Cholesky, pose <- pose * v2t(dx); S.H, S.b, S.R, S.t in, S.R, S.t, S.dx out.  All 32 lanes call it.
 __device__ __forceinline__ bool gn_solve_update_warp(GnWork& S, double damping, int lane) {
   const unsigned FULLM = 0xffffffffu;
-  // rows 0..5 = A = H + damping I; "row" 6 = -b: factorising the augmented matrix leaves y (L y = -b) in that row, column by
-  // column with the same terms in the same order as a separate forward substitution -- which is thereby off the chain
-  const bool row = lane < 7;
-  double Ai[6], Li[6];
-#pragma unroll
-  for (int j = 0; j < 6; ++j) {
-    Ai[j] = lane < 6 ? S.H[6 * lane + j] : (lane == 6 ? -S.b[j] : 0.0);
-    if (lane < 6 && j == lane) Ai[j] += damping;
-    Li[j] = 0;
-  }
-  // Latency is a chain of fp64 sqrt / divide sequences (~260 cycles each on this part): ONE reciprocal square root per
-  // column replaces sqrt + divide, and the triangular solves multiply by it.  Differs from the divide form in the last bit
-  // of an element (parity with the fp64 oracle is 1e-9 relative, tests/test_gpu_solver.py).
-  double ri = 0;  // 1 / L[i][i] of this lane's row
-#pragma unroll
-  for (int j = 0; j < 6; ++j) {  // column j: every row i >= j at once
-    double s = 1.0;
-    if (row && lane >= j) {
-      s = Ai[j];
-#pragma unroll
-      for (int k = 0; k < j; ++k) s = __dsub_rn(s, __dmul_rn(Li[k], S.L[6 * j + k]));
-    }
-    const double d = __shfl_sync(FULLM, s, j);
-    if (!(d > 0)) return false;  // uniform
-    const double r = rsqrt(d);
-    if (row && lane >= j) {
-      Li[j] = __dmul_rn(s, r);  // row j: d / sqrt(d) = L[j][j]; row 6: y[j]
-      if (lane == j) ri = r;
-      if (lane < 6) S.L[6 * lane + j] = Li[j];
-    }
-    __syncwarp();
-  }
-  // y[i] sits in lane 6's Li[i]
-  double yi = 0;
-#pragma unroll
-  for (int k = 0; k < 6; ++k) {
-    const double yk = __shfl_sync(FULLM, Li[k], 6);
-    if (lane == k) yi = yk;
-  }
-  // backward substitution: dx[i] = (y[i] - sum_{k > i, ascending} L[k][i] dx[k]) / L[i][i]
-#pragma unroll
-  for (int i = 5; i >= 0; --i) {
-    if (lane == i) {
-      double s = yi;
-      for (int k = i + 1; k < 6; ++k) s = __dsub_rn(s, __dmul_rn(S.L[6 * k + i], S.dx[k]));
-      S.dx[i] = __dmul_rn(s, ri);
-    }
-    __syncwarp();
-  }
+  (void) FULLM;
+  double dxr[6];
+  if (!gn_solve6_block(S.H, S.b, damping, dxr)) return false;  // uniform: every lane evaluates the same values
+  if (lane < 6) S.dx[lane] = dxr[lane];
+  __syncwarp();
   // v2t(dx)
   if (lane == 0) {
     double x = S.dx[3], yq = S.dx[4], z = S.dx[5];
