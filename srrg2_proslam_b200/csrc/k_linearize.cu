@@ -35,6 +35,17 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// 1 / a for a normal, finite a: the hardware's 2^-23 seed + two Newton steps (four dependent fused multiply-adds, ~1 ulp) instead
+// of the correctly rounded __ddiv_rn sequence, which sits ~260 cycles deep on every dependent chain of the solver iterations
+__device__ __forceinline__ double rcp_fast(double a) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+  double e = fma(-a, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-a, r, 1.0);
+  return fma(r, e, r);
+}
+
 // fp64 fused multiply-adds throughout: the fp64 pipe issues one warp instruction every two cycles, so the instruction count IS
 // the cost (batched: issue-bound; per frame: the head of every solver iteration).  Against the oracle's separately rounded
 // operations this differs in the last bits (relative 1e-15 on H, b; the parity contract is 1e-9).
@@ -49,7 +60,7 @@ __device__ __forceinline__ bool error_and_jacobian(const LinParams& c, const dou
   const double hx = fma(K[0], pc[0], fma(K[1], pc[1], K[2] * pc[2]));
   const double hy = fma(K[3], pc[0], fma(K[4], pc[1], K[5] * pc[2]));
   const double hz = fma(K[6], pc[0], fma(K[7], pc[1], K[8] * pc[2]));
-  const double iz = __ddiv_rn(1.0, hz);
+  const double iz = rcp_fast(hz);
   const double u = hx * iz, v = hy * iz;
   if (u < 0 || u > c.cols || v < 0 || v > c.rows) return false;
   double Jx[18];
@@ -83,7 +94,7 @@ __device__ __forceinline__ bool error_and_jacobian(const LinParams& c, const dou
 #pragma unroll
     for (int j = 0; j < 6; ++j) J[12 + j] = fma(KJ[j], iz, -(hxr_iz2 * KJ[12 + j]));
     if (c.mean_disparity > 0) {
-      double w = 0.01 + __ddiv_rn(z[0] - z[2], c.mean_disparity);
+      double w = fma(z[0] - z[2], rcp_fast(c.mean_disparity), 0.01);
       if (w > 1) w = 1;
 #pragma unroll
       for (int i = 0; i < 3; ++i)
@@ -134,7 +145,7 @@ __device__ __forceinline__ void accumulate_loaded(const LinParams& c, int edim, 
   double scale = 1;
   if (c.robustifier != 0 && chi > c.chi_threshold) {
     acc[29] += 1;
-    scale = (c.robustifier == 1) ? __ddiv_rn(c.chi_threshold, chi) : 0.0;
+    scale = (c.robustifier == 1) ? c.chi_threshold * rcp_fast(chi) : 0.0;
     if (status) *status = 1;
   } else {
     acc[28] += 1;
@@ -515,17 +526,18 @@ __device__ __forceinline__ void pose_prior_accumulate_warp(const PriorParams& pr
 // holds TWO reciprocals instead of six reciprocal square roots + a backward substitution: every product is independent of its
 // neighbours, one thread pipelines them.  Positive definiteness = Sylvester's criterion on A and S.  Every lane computes the
 // same thing (no exchange); returns false when H + damping I is not positive definite.
-__device__ __forceinline__ bool gn_solve6_block(const double* H, const double* bvec, double lam, double* dx) {
-  const double a00 = H[0] + lam, a01 = H[1], a02 = H[2], a11 = H[7] + lam, a12 = H[8], a22 = H[14] + lam;
-  const double b00 = H[3], b01 = H[4], b02 = H[5], b10 = H[9], b11 = H[10], b12 = H[11], b20 = H[15], b21 = H[16], b22 = H[17];
-  const double c00 = H[21] + lam, c01 = H[22], c02 = H[23], c11 = H[28] + lam, c12 = H[29], c22 = H[35] + lam;
+__device__ __forceinline__ bool gn_solve6_block(const double* U, const double* bvec, double lam, double* dx) {
+  // U = upper triangle, row by row: (0,0..5) 0..5, (1,1..5) 6..10, (2,2..5) 11..14, (3,3..5) 15..17, (4,4..5) 18..19, (5,5) 20
+  const double a00 = U[0] + lam, a01 = U[1], a02 = U[2], a11 = U[6] + lam, a12 = U[7], a22 = U[11] + lam;
+  const double b00 = U[3], b01 = U[4], b02 = U[5], b10 = U[8], b11 = U[9], b12 = U[10], b20 = U[12], b21 = U[13], b22 = U[14];
+  const double c00 = U[15] + lam, c01 = U[16], c02 = U[17], c11 = U[18] + lam, c12 = U[19], c22 = U[20] + lam;
   const double g0 = -bvec[0], g1 = -bvec[1], g2 = -bvec[2], g3 = -bvec[3], g4 = -bvec[4], g5 = -bvec[5];
   // adj(A) (symmetric) and det(A)
   const double A00 = fma(a11, a22, -(a12 * a12)), A01 = fma(a02, a12, -(a01 * a22)), A02 = fma(a01, a12, -(a02 * a11));
   const double A11 = fma(a00, a22, -(a02 * a02)), A12 = fma(a01, a02, -(a00 * a12)), A22 = fma(a00, a11, -(a01 * a01));
   const double detA = fma(a00, A00, fma(a01, A01, a02 * A02));
   if (!(a00 > 0) || !(A22 > 0) || !(detA > 0)) return false;
-  const double rd = __ddiv_rn(1.0, detA);
+  const double rd = rcp_fast(detA);
   // Y' = adj(A) B, y' = adj(A) g1 (the 1 / det(A) is applied where they are used)
   const double Y00 = fma(A00, b00, fma(A01, b10, A02 * b20)), Y01 = fma(A00, b01, fma(A01, b11, A02 * b21)),
                Y02 = fma(A00, b02, fma(A01, b12, A02 * b22));
@@ -545,7 +557,7 @@ __device__ __forceinline__ bool gn_solve6_block(const double* H, const double* b
   const double S11 = fma(s00, s22, -(s02 * s02)), S12 = fma(s01, s02, -(s00 * s12)), S22 = fma(s00, s11, -(s01 * s01));
   const double detS = fma(s00, S00, fma(s01, S01, s02 * S02));
   if (!(s00 > 0) || !(S22 > 0) || !(detS > 0)) return false;
-  const double rs = __ddiv_rn(1.0, detS);
+  const double rs = rcp_fast(detS);
   dx[3] = rs * fma(S00, h0, fma(S01, h1, S02 * h2));
   dx[4] = rs * fma(S01, h0, fma(S11, h1, S12 * h2));
   dx[5] = rs * fma(S02, h0, fma(S12, h1, S22 * h2));
@@ -555,59 +567,47 @@ __device__ __forceinline__ bool gn_solve6_block(const double* H, const double* b
   return true;
 }
 
-// (H + damping I) dx = -b by Cholesky, pose <- pose * v2t(dx); S.H, S.b, S.R, S.t in, S.R, S.t, S.dx out.  All 32 lanes call it.
-__device__ __forceinline__ bool gn_solve_update_warp(GnWork& S, double damping, int lane) {
-  const unsigned FULLM = 0xffffffffu;
-  (void) FULLM;
-  double dxr[6];
-  if (!gn_solve6_block(S.H, S.b, damping, dxr)) return false;  // uniform: every lane evaluates the same values
-  if (lane < 6) S.dx[lane] = dxr[lane];
-  __syncwarp();
-  // v2t(dx)
-  if (lane == 0) {
-    double x = S.dx[3], yq = S.dx[4], z = S.dx[5];
-    const double n2 = __dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(yq, yq)), __dmul_rn(z, z));
-    double w;
-    if (n2 < 1.0) {
-      w = sqrt(__dsub_rn(1.0, n2));
-    } else {
-      const double n = sqrt(n2);
-      x = __ddiv_rn(x, n);
-      yq = __ddiv_rn(yq, n);
-      z = __ddiv_rn(z, n);
-      w = 0;
-    }
-    S.q[0] = x;
-    S.q[1] = yq;
-    S.q[2] = z;
-    S.q[3] = w;
+// (H + damping I) dx = -b, pose <- pose * v2t(dx).  sums = the 21 upper-triangle sums of H followed by the 6 of b (the
+// reduction's output, read in place: no 6x6 staging copy); the prior's S.Hp, S.bp are added when with_prior.  S.R, S.t in / out.
+// All 32 lanes call it: every lane solves the (tiny) system and forms the update rotation in its own registers -- nothing
+// is exchanged until lanes 0..11 each write one element of the new pose.
+__device__ __forceinline__ bool gn_solve_update_warp(GnWork& S, const double* sums, bool with_prior, double damping, int lane) {
+  double U[21], g[6], dx[6];
+  {
+    int h = 0;
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+      for (int b = a; b < 6; ++b, ++h) U[h] = with_prior ? sums[h] + S.Hp[6 * a + b] : sums[h];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) g[a] = with_prior ? sums[21 + a] + S.bp[a] : sums[21 + a];
   }
-  __syncwarp();
-  if (lane < 9) {
-    // D = v2t rotation, one element per lane WITHOUT a nine-way branch (it serialised ~1 k cycles per iteration): every
-    // element is base - 2 (A B + C E) with operands picked from (x, y, z, w) by table; for the off-diagonal elements
-    // 0 - 2 ((-p) q + (s r) w) rounds exactly like the serial 2 (p q - s r w) (negation and doubling are exact)
-    //                          D00      D01      D02      D10      D11      D12      D20      D21      D22
-    const signed char iA[9] = {1, 0, 0, 0, 0, 1, 0, 1, 0};
-    const signed char iB[9] = {1, 1, 2, 1, 0, 2, 2, 2, 0};
-    const signed char iC[9] = {2, 2, 1, 2, 2, 0, 1, 0, 1};
-    const signed char iE[9] = {2, 3, 3, 3, 2, 3, 3, 3, 1};
-    const signed char sA[9] = {1, -1, -1, -1, 1, -1, -1, -1, 1};   // sign of A
-    const signed char sC[9] = {1, 1, -1, -1, 1, 1, 1, -1, 1};      // sign of C: +z w in D01 = 2 (xy - zw) means C = +z, ...
-    const double base = (lane == 0 || lane == 4 || lane == 8) ? 1.0 : 0.0;
-    const double A = sA[lane] < 0 ? -S.q[iA[lane]] : S.q[iA[lane]], B = S.q[iB[lane]];
-    const double C = sC[lane] < 0 ? -S.q[iC[lane]] : S.q[iC[lane]], E = S.q[iE[lane]];
-    S.D[lane] = __dsub_rn(base, __dmul_rn(2.0, __dadd_rn(__dmul_rn(A, B), __dmul_rn(C, E))));
+  if (!gn_solve6_block(U, g, damping, dx)) return false;  // uniform: every lane evaluates the same values
+  // v2t(dx): unit quaternion (x, y, z, w) from its imaginary part, normalised when longer than 1
+  double x = dx[3], y = dx[4], z = dx[5];
+  const double n2 = fma(x, x, fma(y, y, z * z));
+  double w = 0;
+  if (n2 < 1.0) {
+    const double a = 1.0 - n2;
+    w = a * rsqrt(a);
+  } else {
+    const double rn = rsqrt(n2);
+    x *= rn;
+    y *= rn;
+    z *= rn;
   }
-  __syncwarp();
+  const double xx = x * x, yy = y * y, zz = z * z, xy = x * y, xz = x * z, yz = y * z, xw = x * w, yw = y * w, zw = z * w;
+  const double D0 = 1.0 - 2.0 * (yy + zz), D1 = 2.0 * (xy - zw), D2 = 2.0 * (xz + yw);
+  const double D3 = 2.0 * (xy + zw), D4 = 1.0 - 2.0 * (xx + zz), D5 = 2.0 * (yz - xw);
+  const double D6 = 2.0 * (xz - yw), D7 = 2.0 * (yz + xw), D8 = 1.0 - 2.0 * (xx + yy);
   double nv = 0;
-  if (lane < 9) {
-    const int i = lane / 3, j = lane % 3;
-    nv = __dadd_rn(__dadd_rn(__dmul_rn(S.R[3 * i], S.D[j]), __dmul_rn(S.R[3 * i + 1], S.D[3 + j])), __dmul_rn(S.R[3 * i + 2], S.D[6 + j]));
-  } else if (lane < 12) {
+  if (lane < 9) {  // R <- R D
+    const int i = lane / 3, j = lane - 3 * i;
+    const double d0 = j == 0 ? D0 : (j == 1 ? D1 : D2), d1 = j == 0 ? D3 : (j == 1 ? D4 : D5), d2 = j == 0 ? D6 : (j == 1 ? D7 : D8);
+    nv = fma(S.R[3 * i], d0, fma(S.R[3 * i + 1], d1, S.R[3 * i + 2] * d2));
+  } else if (lane < 12) {  // t <- R dt + t
     const int i = lane - 9;
-    nv = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(S.R[3 * i], S.dx[0]), __dmul_rn(S.R[3 * i + 1], S.dx[1])),
-                             __dmul_rn(S.R[3 * i + 2], S.dx[2])), S.t[i]);
+    nv = fma(S.R[3 * i], dx[0], fma(S.R[3 * i + 1], dx[1], fma(S.R[3 * i + 2], dx[2], S.t[i])));
   }
   __syncwarp();
   if (lane < 9) S.R[lane] = nv;
@@ -709,17 +709,7 @@ gn_iterate_kernel(LinParams c0, PriorParams prior, double damping, int n_iters, 
     }
     if (!small) __syncthreads();
     if (wid == 0) {
-      for (int el = lane; el < 36; el += 32) {  // full symmetric H from the 21 upper-triangle sums
-        const int a = el / 6, b = el % 6, lo = a < b ? a : b, hi = a < b ? b : a;
-        S.H[el] = s_sum[lo * 6 - lo * (lo - 1) / 2 + (hi - lo)];
-      }
-      if (lane < 6) S.b[lane] = s_sum[21 + lane];
-      if (prior.enabled) {
-        for (int el = lane; el < 36; el += 32) S.H[el] += S.Hp[el];
-        if (lane < 6) S.b[lane] += S.bp[lane];
-      }
-      __syncwarp();
-      const bool ok = gn_solve_update_warp(S, damping, lane);  // leaves the pose untouched when H + damping I is not SPD
+      const bool ok = gn_solve_update_warp(S, s_sum, prior.enabled != 0, damping, lane);  // pose untouched when not SPD
       double* o = out + (size_t) it * GN_OUT;
       if (lane < 12) o[lane] = (lane & 3) == 3 ? S.t[lane >> 2] : S.R[3 * (lane >> 2) + (lane & 3)];
       else if (lane < 16) o[lane] = s_sum[27 + (lane - 12)];
