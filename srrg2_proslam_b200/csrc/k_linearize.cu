@@ -414,14 +414,13 @@ __device__ __noinline__ double pose_prior_accumulate_dev(const PriorParams& pr, 
 
 // ---- the same two steps spread over the lanes of ONE warp ------------------------------------------------------------------
 // Inside the fused loop the pose-prior factor and the 6x6 solve were ~6 of the ~9 us of an iteration when one thread ran them
-// (dependent fp64 chains, arrays in local memory).  Here every matrix element is evaluated by its own lane with exactly the
-// operation sequence of the serial functions above (same sums in the same order: identical bits), intermediate matrices live
-// in shared memory, the Cholesky advances one column per step, the triangular solves one unknown per step.
+// (dependent fp64 chains, arrays in local memory).  The prior runs in a warp of its own next to the linearisation, one
+// matrix element per lane, intermediate matrices in shared memory; the solve runs in registers (gn_solve_update_warp).
 struct GnWork {
-  double H[36], b[6], L[36], dx[6], R[9], t[3];
-  double ER[9], Et[3], e6[6], J[36], OJ[36], Oe[6], pw;  // pose-prior scratch (its own warp)
-  double Hp[36], bp[6];                                    // the prior's contribution to H, b for the current pose
-  double D[9], q[4];
+  double R[9], t[3];
+  double Om[36];                               // the prior's information matrix (kernel parameters indexed per lane would serialise)
+  double ER[9], Et[3], e6[6], Q[9], OJ[36], Oe[6];  // pose-prior scratch (its own warp)
+  double Hp[36], bp[6];                        // the prior's contribution to H, b for the current pose
 };
 
 // t2tnq with reciprocal square roots in place of the sqrt + divide pairs (the prior sits on the iteration's critical path
@@ -475,47 +474,46 @@ __device__ __forceinline__ void pose_prior_accumulate_warp(const PriorParams& pr
     S.Et[i] = ((pr.Zi_R[3 * i] * S.t[0] + pr.Zi_R[3 * i + 1] * S.t[1]) + pr.Zi_R[3 * i + 2] * S.t[2]) + pr.Zi_t[i];
   }
   __syncwarp();
-  if (lane == 0) {
-    t2tnq_fast(S.ER, S.Et, S.e6);
-    const double n2 = S.e6[3] * S.e6[3] + S.e6[4] * S.e6[4] + S.e6[5] * S.e6[5];
-    S.pw = sqrt(n2 < 1.0 ? 1.0 - n2 : 0.0);
-  }
-  __syncwarp();
-  for (int el = lane; el < 36; el += 32) {  // J = blockdiag(R_E, w I + [v]x)
-    const int k = el / 6, j = el % 6;
-    double v = 0;
-    if (k < 3 && j < 3) {
-      v = S.ER[3 * k + j];
-    } else if (k >= 3 && j >= 3) {
-      const double w = S.pw, vx = S.e6[3], vy = S.e6[4], vz = S.e6[5];
-      const double Q[9] = {w, -vz, vy, vz, w, -vx, -vy, vx, w};
-      v = Q[3 * (k - 3) + (j - 3)];
+  {  // e = t2tnq(E), Q = w I + [v]x: every lane evaluates it (no exchange), lane 0 publishes
+    double e6[6];
+    t2tnq_fast(S.ER, S.Et, e6);
+    const double vx = e6[3], vy = e6[4], vz = e6[5];
+    const double a = 1.0 - (vx * vx + vy * vy + vz * vz);
+    const double w = a > 0 ? a * rsqrt(a) : 0.0;
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) S.e6[i] = e6[i];
+      S.Q[0] = w, S.Q[1] = -vz, S.Q[2] = vy;
+      S.Q[3] = vz, S.Q[4] = w, S.Q[5] = -vx;
+      S.Q[6] = -vy, S.Q[7] = vx, S.Q[8] = w;
     }
-    S.J[el] = v;
   }
   __syncwarp();
+  // J = blockdiag(R_E, Q): Omega J, J^T (Omega J) and J^T (Omega e) only touch the non-zero 3x3 blocks (three terms per element;
+  // the dropped terms are exact zeros, the sums keep their order)
   for (int el = lane; el < 36; el += 32) {
     const int i = el / 6, j = el % 6;
-    double a = 0;
-    for (int k = 0; k < 6; ++k) a += pr.Omega[6 * i + k] * S.J[6 * k + j];
-    S.OJ[el] = a;
+    const double* B = j < 3 ? S.ER + j : S.Q + (j - 3);
+    const double* O = S.Om + 6 * i + (j < 3 ? 0 : 3);
+    S.OJ[el] = (O[0] * B[0] + O[1] * B[3]) + O[2] * B[6];
   }
   if (lane < 6) {
     double sum = 0;
-    for (int k = 0; k < 6; ++k) sum += pr.Omega[6 * lane + k] * S.e6[k];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) sum += S.Om[6 * lane + k] * S.e6[k];
     S.Oe[lane] = sum;
   }
   __syncwarp();
   if (lane < 6) {
-    double bs = 0;
-    for (int k = 0; k < 6; ++k) bs += S.J[6 * k + lane] * S.Oe[k];
-    S.bp[lane] = bs;
+    const double* B = lane < 3 ? S.ER + lane : S.Q + (lane - 3);
+    const double* v = S.Oe + (lane < 3 ? 0 : 3);
+    S.bp[lane] = (B[0] * v[0] + B[3] * v[1]) + B[6] * v[2];
   }
   for (int el = lane; el < 36; el += 32) {
     const int a = el / 6, c = el % 6;
-    double hs = 0;
-    for (int k = 0; k < 6; ++k) hs += S.J[6 * k + a] * S.OJ[6 * k + c];
-    S.Hp[el] = hs;
+    const double* B = a < 3 ? S.ER + a : S.Q + (a - 3);
+    const double* M = S.OJ + c + (a < 3 ? 0 : 18);
+    S.Hp[el] = (B[0] * M[0] + B[3] * M[6]) + B[6] * M[12];
   }
   __syncwarp();
 }
@@ -645,6 +643,7 @@ gn_iterate_kernel(LinParams c0, PriorParams prior, double damping, int n_iters, 
   if (threadIdx.x < 9) S.R[threadIdx.x] = c0.R[threadIdx.x];
   if (threadIdx.x < 3) S.t[threadIdx.x] = c0.t[threadIdx.x];
   if (threadIdx.x == 0) s_ok = 1;
+  if (prior.enabled && threadIdx.x >= 64 && threadIdx.x < 100) S.Om[threadIdx.x - 64] = prior.Omega[threadIdx.x - 64];
   __syncthreads();
   const int edim = (c0.kind == 2) ? 2 : 3;
   LinParams c = c0;
@@ -676,8 +675,19 @@ gn_iterate_kernel(LinParams c0, PriorParams prior, double damping, int n_iters, 
         asm volatile("bar.sync 1, 128;" ::: "memory");
         const int v = threadIdx.x >> 2, part = threadIdx.x & 3;
         double sum = 0;
-        if (v < LZ_NACC - 1)
-          for (int t = part; t < n_corr; t += 4) sum += s_acc[v * RED_PITCH + t];
+        if (v < LZ_NACC - 1) {  // four independent chains: the loads pipeline instead of alternating with dependent adds
+          const double* a = s_acc + v * RED_PITCH;
+          double s1 = 0, s2 = 0, s3 = 0;
+          int t = part;
+          for (; t + 12 < n_corr; t += 16) {
+            sum += a[t];
+            s1 += a[t + 4];
+            s2 += a[t + 8];
+            s3 += a[t + 12];
+          }
+          for (; t < n_corr; t += 4) sum += a[t];
+          sum = (sum + s1) + (s2 + s3);
+        }
         sum += __shfl_xor_sync(0xffffffffu, sum, 2);
         sum += __shfl_xor_sync(0xffffffffu, sum, 1);
         if (part == 0 && v < LZ_NACC - 1) s_sum[v] = sum;
