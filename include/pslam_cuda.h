@@ -526,6 +526,42 @@ int pslam_projective_match_gn(pslam_ctx* ctx, int n_fixed, int n_moving, const f
                               const pslam_projective_cfg* cfg, int capacity, int* fixed_idx, int* moving_idx,
                               float* distance, int* n_projected, pslam_fused_gn* gn);
 
+/* ---- the whole registration of one frame, device resident ---------------------------------------------------------
+ * MultiAligner_::compute drives { finder.compute(); solver iterations } until max_iterations are spent; between two
+ * searches the finder only updates a handful of scalars (CorrespondenceFinderProjective_::compute,
+ * correspondence_finder_projective_base_impl.cpp:104-293: re-project every N-th call, convergence = norm of the estimate
+ * change below a threshold after a minimum of calls, then the correspondences are kept).  pslam_projective_align runs that
+ * state machine on the device: search -> filter -> decisions -> solver iterations, phase after phase, with ONE download at
+ * the end of every batch of phases instead of one host round trip per search.  Same per-iteration poses / stats and the
+ * same final correspondences as the call-by-call path.
+ * It stops and hands back to the caller's loop (the state below describes the point reached) when a decision needs the
+ * caller: stop_reason 2 = low matching ratio with room to widen the search (the finder repeats the call with its maximum
+ * radius), 3 = fewer than min_num_correspondences, 4 = H + damping I not positive definite.  The phase that stopped has
+ * changed nothing: the caller re-runs it through pslam_projective_match_gn.
+ * in / out finder state: current_iteration, has_converged, previous12 (_local_map_in_sensor_previous).
+ * gn: as pslam_projective_match_gn, n_iterations = max_iterations = rows of poses12 / stats4. */
+#define PSLAM_ALIGN_MAX_PHASES 64
+typedef struct pslam_align {
+  int max_iterations;                       /* solver iterations left in the aligner's budget */
+  int solver_iterations_per_projection;     /* finder PARAM number_of_solver_iterations_per_projection */
+  int minimum_number_of_iterations;         /* finder PARAM */
+  float maximum_estimate_change_norm_for_convergence;
+  float minimum_matching_ratio;
+  int can_widen_search;                     /* search radius below its maximum or descriptor distance above its minimum */
+  int min_num_correspondences;              /* slice PARAM (at least 1) */
+  int current_iteration;                    /* in / out */
+  int has_converged;                        /* in (must be 0) / out */
+  float previous12[12];                     /* in / out */
+  int stop_reason;                          /* out: 1 budget spent, 2 / 3 / 4 see above */
+  int iterations_done;                      /* out: solver iterations completed (rows of poses12 / stats4 that are valid) */
+  int converged_with_good_ratio;            /* out: has_converged was set in a phase whose matching ratio exceeded the minimum */
+  int n_projected;                          /* out: of the last phase */
+  int n_phases;                             /* out: searches executed */
+  int phase_log[3 * PSLAM_ALIGN_MAX_PHASES]; /* out per phase: first solver iteration, iterations done, correspondences */
+} pslam_align;
+int pslam_projective_align(pslam_ctx* ctx, int n_fixed, int n_moving, const pslam_projective_cfg* cfg, pslam_align* align,
+                           int capacity, int* fixed_idx, int* moving_idx, float* distance, pslam_fused_gn* gn);
+
 #ifdef __cplusplus
 }
 #endif

@@ -629,8 +629,21 @@ __global__ void __launch_bounds__(LZ_THREADS)
 gn_iterate_kernel(LinParams c0, PriorParams prior, double damping, int n_iters, const T* __restrict__ moving_xyz,
                   const T* __restrict__ fixed_meas, int fixed_dim, int n_corr, const int* __restrict__ corr_fixed,
                   const int* __restrict__ corr_moving, const T* __restrict__ info_diag, double* __restrict__ out,
-                  int* __restrict__ iters_done, uint8_t* __restrict__ status, const int* __restrict__ n_corr_dev) {
+                  int* __restrict__ iters_done, uint8_t* __restrict__ status, const int* __restrict__ n_corr_dev,
+                  PslamAlignState* __restrict__ state, int max_iterations) {
   if (n_corr_dev) n_corr = *n_corr_dev;  // correspondences produced on the device by the launch before (pslam_projective_match_gn)
+  if (state) {  // one phase of pslam_projective_align: budget, start estimate and output rows are the state's (uniform reads;
+                // thread 0 advances the state after the last barrier of the kernel)
+    if (state->stop) return;
+    n_iters = state->n_fused;
+    out += (size_t) state->it * GN_OUT;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) c0.R[3 * i + j] = state->estimate[4 * i + j];
+      c0.t[i] = state->estimate[4 * i + 3];
+    }
+  }
   __shared__ double s_part[LZ_THREADS / 32][LZ_NACC];
   __shared__ double s_sum[LZ_NACC];
   __shared__ GnWork S;
@@ -732,6 +745,27 @@ gn_iterate_kernel(LinParams c0, PriorParams prior, double damping, int n_iters, 
   if (threadIdx.x == 0) {
     iters_done[0] = done;
     iters_done[1] = s_ok;
+    if (state) {
+      // MultiAligner_::compute after the solver block: estimate <- last pose; the finder's bookkeeping for the `done - 1` calls
+      // that kept these correspondences (each: previous <- the pose it was given, ++iteration; none once converged; skipped
+      // when the solve failed, as the caller leaves its loop before them)
+      const int ph = state->phases - 1;
+      if (ph >= 0 && ph < PSLAM_ALIGN_MAX_PHASES) {
+        state->phase_log[3 * ph] = state->it;
+        state->phase_log[3 * ph + 1] = done;
+        state->phase_log[3 * ph + 2] = state->n_corr;
+      }
+      if (done > 0)
+        for (int i = 0; i < 12; ++i) state->estimate[i] = out[(size_t) (done - 1) * GN_OUT + i];
+      if (s_ok && !state->has_converged) {
+        if (done >= 2)
+          for (int i = 0; i < 12; ++i) state->prev[i] = (float) out[(size_t) (done - 2) * GN_OUT + i];
+        state->current_iteration += done - 1;
+      }
+      state->it += done;
+      if (!s_ok) state->stop = 4;
+      else if (state->it >= max_iterations) state->stop = 1;
+    }
   }
 }
 
@@ -881,7 +915,7 @@ int pslam_k_gn_iterate_t(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, int n_i
     PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_info, h_info_diag, 3 * sizeof(T) * (size_t) n_fixed, cudaMemcpyHostToDevice, ctx->stream));
   }
   gn_iterate_kernel<T><<<1, LZ_THREADS, 0, ctx->stream>>>(c, make_prior(prior), damping, n_iters, d_mov, d_fix, fixed_dim, n_corr,
-                                                         d_cf, d_cm, d_info, d_out, d_done, d_status, nullptr);
+                                                         d_cf, d_cm, d_info, d_out, d_done, d_status, nullptr, nullptr, 0);
   PSLAM_LAUNCH_CHECK(ctx, "gn_iterate_kernel");
   int h_small[2];
   const int* h = h_small;
@@ -909,11 +943,12 @@ int pslam_k_gn_iterate_t(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, int n_i
 int pslam_k_gn_iterate_dev(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, int n_iters, double damping, const double* pose12,
                            const float* d_moving_xyz, const float* d_fixed_meas, int fixed_dim, const int* d_n_corr,
                            const int* d_corr_fixed, const int* d_corr_moving, const float* d_info_diag,
-                           const pslam_pose_prior* prior, double* d_out, int* d_done, uint8_t* d_status) {
+                           const pslam_pose_prior* prior, double* d_out, int* d_done, uint8_t* d_status,
+                           PslamAlignState* d_state, int max_iterations) {
   const LinParams c = make_params(cfg, pose12);
   gn_iterate_kernel<float><<<1, LZ_THREADS, 0, ctx->stream>>>(c, make_prior(prior), damping, n_iters, d_moving_xyz, d_fixed_meas,
                                                              fixed_dim, 0, d_corr_fixed, d_corr_moving, d_info_diag, d_out, d_done,
-                                                             d_status, d_n_corr);
+                                                             d_status, d_n_corr, d_state, max_iterations);
   PSLAM_LAUNCH_CHECK(ctx, "gn_iterate_kernel");
   return PSLAM_OK;
 }

@@ -87,9 +87,20 @@ projective_search_kernel(ProjParams pp, const float* __restrict__ moving_xyz, in
                          const uint32_t* __restrict__ desc_moving,
                          const unsigned long long* __restrict__ lattice, int n_fixed,
                          const uint32_t* __restrict__ desc_fixed, int* __restrict__ cand,
-                         int* __restrict__ n_projected, const float* __restrict__ fixed_coords, int fixed_dim) {
+                         int* __restrict__ n_projected, const float* __restrict__ fixed_coords, int fixed_dim,
+                         const PslamAlignState* __restrict__ state) {
   extern __shared__ int s_width[];  // circle: width per |height| (0..radius)
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (state) {  // a phase of pslam_projective_align: the pose is the solver's current estimate, rounded to fp32 as the caller's
+                // finder.setLocalMapInSensor(X) does (uniform reads; the state is only written by later launches)
+    if (state->stop) return;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) pp.R[3 * i + j] = (float) state->estimate[4 * i + j];
+      pp.t[i] = (float) state->estimate[4 * i + 3];
+    }
+  }
   if (pp.shape == 1) {
     const int r2 = pp.radius * pp.radius;
     for (int h = threadIdx.x; h <= pp.radius; h += PJ_WARPS * 32)
@@ -204,6 +215,125 @@ projective_search_kernel(ProjParams pp, const float* __restrict__ moving_xyz, in
   }
 }
 
+constexpr int FF_THREADS = 1024;  // filter + compaction: one CTA
+// ---- the finder's state machine between two searches (pslam_projective_align), thread 0 after the compaction -------------
+// fp32 arithmetic of the host mirror (pslam_plugin.cpp: Isometry3f::inverse, operator*, t2tnq; separately rounded operations,
+// IEEE sqrt / divide): the decisions are bit-identical to the call-by-call path's.
+__device__ float align_estimate_change_norm(const float* X, const float* P) {
+  float I[12], E[12];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) I[4 * i + j] = X[4 * j + i];
+  for (int i = 0; i < 3; ++i)
+    I[4 * i + 3] = -__fadd_rn(__fadd_rn(__fmul_rn(I[4 * i], X[3]), __fmul_rn(I[4 * i + 1], X[7])), __fmul_rn(I[4 * i + 2], X[11]));
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j)
+      E[4 * i + j] = __fadd_rn(__fadd_rn(__fmul_rn(I[4 * i], P[j]), __fmul_rn(I[4 * i + 1], P[4 + j])), __fmul_rn(I[4 * i + 2], P[8 + j]));
+    E[4 * i + 3] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(I[4 * i], P[3]), __fmul_rn(I[4 * i + 1], P[7])), __fmul_rn(I[4 * i + 2], P[11])),
+                             I[4 * i + 3]);
+  }
+  float v6[6] = {E[3], E[7], E[11], 0, 0, 0};
+  float w, q[3];
+  float t = __fadd_rn(__fadd_rn(E[0], E[5]), E[10]);
+  if (t > 0.f) {
+    t = __fsqrt_rn(__fadd_rn(t, 1.f));
+    w = __fmul_rn(0.5f, t);
+    t = __fdiv_rn(0.5f, t);
+    q[0] = __fmul_rn(__fsub_rn(E[9], E[6]), t);
+    q[1] = __fmul_rn(__fsub_rn(E[2], E[8]), t);
+    q[2] = __fmul_rn(__fsub_rn(E[4], E[1]), t);
+  } else {
+    int i = 0;
+    if (E[5] > E[0]) i = 1;
+    if (E[10] > (i == 0 ? E[0] : E[5])) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    t = __fsqrt_rn(__fadd_rn(__fsub_rn(__fsub_rn(E[5 * i], E[5 * j]), E[5 * k]), 1.f));
+    q[i] = __fmul_rn(0.5f, t);
+    t = __fdiv_rn(0.5f, t);
+    w = __fmul_rn(__fsub_rn(E[4 * k + j], E[4 * j + k]), t);
+    q[j] = __fmul_rn(__fadd_rn(E[4 * j + i], E[4 * i + j]), t);
+    q[k] = __fmul_rn(__fadd_rn(E[4 * k + i], E[4 * i + k]), t);
+  }
+  const float n = __fsqrt_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w, w), __fmul_rn(q[0], q[0])), __fmul_rn(q[1], q[1])), __fmul_rn(q[2], q[2])));
+  const float sg = __fdiv_rn(w < 0.f ? -1.f : 1.f, n);
+  v6[3] = __fmul_rn(q[0], sg);
+  v6[4] = __fmul_rn(q[1], sg);
+  v6[5] = __fmul_rn(q[2], sg);
+  float n2 = 0;
+  for (int i = 0; i < 6; ++i) n2 = __fadd_rn(n2, __fmul_rn(v6[i], v6[i]));
+  return __fsqrt_rn(n2);
+}
+
+// CorrespondenceFinderProjective_::compute after the search (base_impl.cpp:181-183, 228-288) + the caller's choice of how
+// many solver iterations follow (the calls that keep these correspondences, :162-178)
+__device__ void align_control(PslamAlignState* s, const PslamAlignCfg& a, int n, int n_fixed, int n_projected) {
+  s->n_corr = n;
+  s->n_projected = n_projected;
+  const float ratio = __fdiv_rn((float) n, (float) n_fixed);
+  if (ratio < a.min_matching_ratio && a.can_widen) {  // the finder repeats the call with its widest search: the caller's turn
+    s->stop = 2;
+    return;
+  }
+  if (n < (a.min_corr > 1 ? a.min_corr : 1)) {
+    s->stop = 3;
+    return;
+  }
+  float X[12];
+  for (int i = 0; i < 12; ++i) X[i] = (float) s->estimate[i];
+  const float norm = align_estimate_change_norm(X, s->prev);
+  for (int i = 0; i < 12; ++i) s->prev[i] = X[i];
+  const bool converged = norm < a.max_change_norm && s->current_iteration > a.min_iterations;
+  int n_fused = a.max_iterations - s->it;
+  if (converged) {
+    s->has_converged = 1;
+    s->converged_ratio_ok = ratio > a.min_matching_ratio ? 1 : 0;
+  } else {
+    int quiet = 0;
+    for (int it = s->current_iteration + 1; !(it % a.per_projection == 0 || it == 1) && quiet < n_fused; ++it) ++quiet;
+    if (quiet + 1 < n_fused) n_fused = quiet + 1;
+  }
+  s->n_fused = n_fused;
+  s->current_iteration += 1;
+  s->phases += 1;
+}
+
+// correspondences of the filter's result in ascending fixed index + their information diagonals, for the fused solver:
+// acc_moving[f] >= 0  ->  (f, acc_moving[f]); info[3 f + k] = diag[k] * scale[moving]  (setupFactor, fp32 like the host)
+struct CompactArgs {
+  int enabled;
+  const float* scale;
+  float d0, d1, d2;
+  int *cf, *cm;
+  float* info;
+  int* n_corr;
+  PslamAlignState* state;
+  PslamAlignCfg acfg;
+};
+__device__ __forceinline__ void corr_compact(const int* __restrict__ acc_moving, int n_fixed, const float* __restrict__ scale, float d0,
+                                             float d1, float d2, int* __restrict__ cf, int* __restrict__ cm, float* __restrict__ info,
+                                             int* __restrict__ n_corr, PslamAlignState* __restrict__ state, const PslamAlignCfg& acfg) {
+  __shared__ int s_warp[33];
+  int running = 0;
+  for (int base = 0; base < n_fixed; base += FF_THREADS) {
+    const int f = base + threadIdx.x;
+    const int m = f < n_fixed ? acc_moving[f] : -1;
+    int total;
+    const int off = block_exclusive_scan<FF_THREADS>(m >= 0 ? 1 : 0, s_warp, &total);
+    if (m >= 0) {
+      cf[running + off] = f;
+      cm[running + off] = m;
+      const float s = scale ? scale[m] : 1.0f;
+      info[3 * (size_t) f] = __fmul_rn(d0, s);
+      info[3 * (size_t) f + 1] = __fmul_rn(d1, s);
+      info[3 * (size_t) f + 2] = __fmul_rn(d2, s);
+    }
+    running += total;
+  }
+  if (threadIdx.x == 0) {
+    *n_corr = running;
+    if (state) align_control(state, acfg, running, n_fixed, acc_moving[-1]);  // acc_moving[-1] = the filter's n_projected
+  }
+}
+
 // Filtering (_filterCorrespondences, projective_base_impl.cpp:39-102): per fixed point the lowest and second lowest
 // response over its candidates in insertion order (order key = 2 * moving_idx + {0 best, 1 second}; key = (dist << 32) |
 // order), Lowe's ratio + distance threshold, then bijectivity (the moving point's own best candidate is its first entry).
@@ -211,12 +341,12 @@ projective_search_kernel(ProjParams pp, const float* __restrict__ moving_xyz, in
 // CTA: per frame the finder is called ~20 times on a few hundred points, so the search is bound by launch and copy
 // latencies, not by work -- 3 memsets + 3 kernels + 4 copies became 1 kernel + 1 copy.  `out` is the contiguous block the
 // host downloads: [n_projected][acc_moving x n_fixed][acc_dist x n_fixed (float bits)][cand x 4 n_moving].
-constexpr int FF_THREADS = 1024;
 __global__ void __launch_bounds__(FF_THREADS)
 filter_fused_kernel(const int* __restrict__ cand, int n_moving, int n_fixed, unsigned long long* __restrict__ key1,
-                    unsigned long long* __restrict__ key2, float max_dist, float max_ratio, int* __restrict__ out) {
+                    unsigned long long* __restrict__ key2, float max_dist, float max_ratio, int* __restrict__ out, CompactArgs ca) {
   __shared__ int s_proj;
   const int tid = threadIdx.x;
+  if (ca.state && ca.state->stop) return;
   if (tid == 0) s_proj = 0;
   for (int f = tid; f < n_fixed; f += FF_THREADS) {
     key1[f] = ~0ULL;
@@ -265,31 +395,10 @@ filter_fused_kernel(const int* __restrict__ cand, int n_moving, int n_fixed, uns
   }
   int* cand_out = out + 1 + 2 * n_fixed;
   for (int i = tid; i < 4 * n_moving; i += FF_THREADS) cand_out[i] = cand[i];
-}
-
-// correspondences of the filter's result in ascending fixed index + their information diagonals, for the fused solver:
-// acc_moving[f] >= 0  ->  (f, acc_moving[f]); info[3 f + k] = diag[k] * scale[moving]  (setupFactor, fp32 like the host)
-__global__ void __launch_bounds__(FF_THREADS)
-corr_compact_kernel(const int* __restrict__ acc_moving, int n_fixed, const float* __restrict__ scale, float d0, float d1, float d2,
-                    int* __restrict__ cf, int* __restrict__ cm, float* __restrict__ info, int* __restrict__ n_corr) {
-  __shared__ int s_warp[33];
-  int running = 0;
-  for (int base = 0; base < n_fixed; base += FF_THREADS) {
-    const int f = base + threadIdx.x;
-    const int m = f < n_fixed ? acc_moving[f] : -1;
-    int total;
-    const int off = block_exclusive_scan<FF_THREADS>(m >= 0 ? 1 : 0, s_warp, &total);
-    if (m >= 0) {
-      cf[running + off] = f;
-      cm[running + off] = m;
-      const float s = scale ? scale[m] : 1.0f;
-      info[3 * (size_t) f] = __fmul_rn(d0, s);
-      info[3 * (size_t) f + 1] = __fmul_rn(d1, s);
-      info[3 * (size_t) f + 2] = __fmul_rn(d2, s);
-    }
-    running += total;
+  if (ca.enabled) {  // the fused solver's input (+ the finder's decisions) in the same launch: one kernel boundary less per search
+    __syncthreads();
+    corr_compact(acc_moving, n_fixed, ca.scale, ca.d0, ca.d1, ca.d2, ca.cf, ca.cm, ca.info, ca.n_corr, ca.state, ca.acfg);
   }
-  if (threadIdx.x == 0) *n_corr = running;
 }
 
 }  // namespace
@@ -396,75 +505,10 @@ int pslam_k_projective_set_moving_weights(pslam_ctx* ctx, int n_moving, const fl
   return PSLAM_OK;
 }
 
-int pslam_k_projective_match(pslam_ctx* ctx, int n_fixed, int n_moving, const float* pose12,
-                             const pslam_projective_cfg* cfg, int capacity, int* h_fixed, int* h_moving,
-                             float* h_dist, int* n_projected, pslam_fused_gn* gn) {
-  ProjState st;
-  int rc = proj_layout(ctx, st, n_fixed, 2, n_moving);
-  if (rc) return rc;
-  if (n_projected) *n_projected = 0;
-  if (n_fixed == 0 || n_moving == 0) return 0;
-  ProjParams pp;
-  for (int i = 0; i < 3; ++i) {
-    for (int j = 0; j < 3; ++j) pp.R[3 * i + j] = pose12[4 * i + j];
-    pp.t[i] = pose12[4 * i + 3];
-  }
-  for (int i = 0; i < 9; ++i) pp.K[i] = cfg->K[i];
-  pp.canvas_cols = (float) cfg->canvas_cols;
-  pp.canvas_rows = (float) cfg->canvas_rows;
-  pp.range_min = cfg->range_min;
-  pp.range_max = cfg->range_max;
-  pp.shape = cfg->shape;
-  pp.radius = cfg->search_radius_pixels;
-  pp.max_desc_dist = cfg->maximum_descriptor_distance;
-  if (pp.shape < 0 || pp.shape > 3) return pslam_set_error(ctx, PSLAM_E_INVALID, "projective: unknown window shape", cudaSuccess);
-  if (pp.radius < 0 || pp.radius > 16000)
-    return pslam_set_error(ctx, PSLAM_E_INVALID, "projective: bad search radius", cudaSuccess);
-  const size_t smem = sizeof(int) * (size_t) (pp.radius + 1);
-  if (smem > 48 * 1024)
-    PSLAM_CUDA_TRY(ctx, cudaFuncSetAttribute(projective_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-  projective_search_kernel<<<(n_moving + PJ_WARPS - 1) / PJ_WARPS, PJ_WARPS * 32, smem, ctx->stream>>>(
-    pp, st.d_moving, n_moving, st.d_desc_moving, st.d_lattice, n_fixed, st.d_desc_fixed, st.d_cand, nullptr, st.d_fixed,
-    ctx->proj_fixed_dim);
-  PSLAM_LAUNCH_CHECK(ctx, "projective_search_kernel");
-  // one filter launch, one download (see filter_fused_kernel); the result block is transient: generic scratch
-  const size_t n_words = 1 + 2 * (size_t) n_fixed + 4 * (size_t) n_moving;
-  if (PSLAM_SOLVER_SCRATCH_OFFSET + 4 * n_words > ctx->scratch_bytes)
-    return pslam_set_error(ctx, PSLAM_E_CAPACITY, "projective: scratch too small for the result block", cudaSuccess);
-  int* d_out = reinterpret_cast<int*>(ctx->d_scratch + PSLAM_SOLVER_SCRATCH_OFFSET);
-  filter_fused_kernel<<<1, FF_THREADS, 0, ctx->stream>>>(st.d_cand, n_moving, n_fixed, st.d_key1, st.d_key2, cfg->descriptor_distance,
-                                                         cfg->maximum_distance_ratio_to_second_best, d_out);
-  PSLAM_LAUNCH_CHECK(ctx, "filter_fused_kernel");
-  // fused solver iterations on the correspondences just found: their block sits directly behind the filter's, ONE download
-  size_t gn_words = 0;  // 4-byte words: [done, spd | pad to 8 B][n_iters x 16 doubles][status bytes, padded]
-  const size_t gn_off = (n_words + 1) & ~(size_t) 1;  // 8-byte aligned
-  int n_gn_iters = 0;
-  if (gn) {
-    if (!gn->factor || gn->n_iterations < 0) return pslam_set_error(ctx, PSLAM_E_INVALID, "match_gn: factor configuration missing", cudaSuccess);
-    n_gn_iters = gn->n_iterations;
-    gn_words = 2 + 32 * (size_t) n_gn_iters + ((size_t) n_fixed + 3) / 4;
-    if (PSLAM_SOLVER_SCRATCH_OFFSET + 4 * (gn_off + gn_words) > ctx->scratch_bytes)
-      return pslam_set_error(ctx, PSLAM_E_CAPACITY, "match_gn: scratch too small", cudaSuccess);
-    const float* scale = ctx->proj_weights_epoch == ctx->proj_moving_epoch ? st.d_mscale : nullptr;
-    corr_compact_kernel<<<1, FF_THREADS, 0, ctx->stream>>>(d_out + 1, n_fixed, scale, gn->diagonal_info[0], gn->diagonal_info[1],
-                                                           gn->diagonal_info[2], st.d_gn_cf, st.d_gn_cm, st.d_gn_info, st.d_gn_ncorr);
-    PSLAM_LAUNCH_CHECK(ctx, "corr_compact_kernel");
-    int* d_done = d_out + gn_off;
-    double* d_gn_out = reinterpret_cast<double*>(d_done + 2);
-    uint8_t* d_status = reinterpret_cast<uint8_t*>(d_gn_out + 16 * (size_t) n_gn_iters);
-    if ((rc = pslam_k_gn_iterate_dev(ctx, gn->factor, n_gn_iters, gn->damping, gn->pose12, st.d_moving, st.d_fixed, ctx->proj_fixed_dim,
-                                     st.d_gn_ncorr, st.d_gn_cf, st.d_gn_cm, st.d_gn_info, gn->prior, d_gn_out, d_done, d_status)))
-      return rc;
-  }
-  const size_t all_words = gn ? gn_off + gn_words : n_words;
-  std::vector<int> pageable;
-  int* h_out = reinterpret_cast<int*>(ctx->h_pinned);
-  if (4 * all_words > ctx->pinned_bytes) {
-    pageable.resize(all_words);
-    h_out = pageable.data();
-  }
-  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(h_out, d_out, 4 * all_words, cudaMemcpyDeviceToHost, ctx->stream));
-  PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+// host side of a search: the downloaded block [n_projected][acc_moving x n_fixed][acc_dist x n_fixed][cand x 4 n_moving]
+// (+ the fused solver's block at gn_off: [done, spd][rows x 16 doubles][status]) -> the caller's arrays
+static int proj_collect(const int* h_out, int n_fixed, int n_moving, int capacity, int* h_fixed, int* h_moving, float* h_dist,
+                        int* n_projected, pslam_fused_gn* gn, size_t gn_off, int gn_rows, int done, int spd) {
   const int nproj = h_out[0];
   const int* acc_m = h_out + 1;
   const float* acc_d = reinterpret_cast<const float*>(h_out + 1 + n_fixed);
@@ -485,7 +529,7 @@ int pslam_k_projective_match(pslam_ctx* ctx, int n_fixed, int n_moving, const fl
   // fused solver block: the device list is in ascending fixed index
   const int* h_gn = gn ? h_out + gn_off : nullptr;
   const double* h_gn_out = gn ? reinterpret_cast<const double*>(h_gn + 2) : nullptr;
-  const uint8_t* h_status = gn ? reinterpret_cast<const uint8_t*>(h_gn_out + 16 * (size_t) n_gn_iters) : nullptr;
+  const uint8_t* h_status = gn ? reinterpret_cast<const uint8_t*>(h_gn_out + 16 * (size_t) gn_rows) : nullptr;
   std::vector<int> rank_of_fixed;
   if (gn && gn->factor_status) {
     rank_of_fixed.assign((size_t) n_fixed, -1);
@@ -506,9 +550,12 @@ int pslam_k_projective_match(pslam_ctx* ctx, int n_fixed, int n_moving, const fl
     ++n_out;
   }
   if (gn) {
-    const int done = h_gn[0];
+    if (done < 0) {
+      done = h_gn[0];
+      spd = h_gn[1];
+    }
     gn->iterations_done = done;
-    gn->spd = h_gn[1];
+    gn->spd = spd;
     for (int i = 0; i < done; ++i) {
       if (gn->poses12) memcpy(gn->poses12 + 12 * (size_t) i, h_gn_out + 16 * (size_t) i, sizeof(double) * 12);
       if (gn->stats4) memcpy(gn->stats4 + 4 * (size_t) i, h_gn_out + 16 * (size_t) i + 12, sizeof(double) * 4);
@@ -516,4 +563,195 @@ int pslam_k_projective_match(pslam_ctx* ctx, int n_fixed, int n_moving, const fl
     if (done > 0) memcpy(gn->pose12, h_gn_out + 16 * (size_t) (done - 1), sizeof(double) * 12);
   }
   return n_out;
+}
+
+static int proj_params(pslam_ctx* ctx, const pslam_projective_cfg* cfg, const float* pose12, ProjParams& pp) {
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) pp.R[3 * i + j] = pose12 ? pose12[4 * i + j] : (i == j ? 1.f : 0.f);
+    pp.t[i] = pose12 ? pose12[4 * i + 3] : 0.f;
+  }
+  for (int i = 0; i < 9; ++i) pp.K[i] = cfg->K[i];
+  pp.canvas_cols = (float) cfg->canvas_cols;
+  pp.canvas_rows = (float) cfg->canvas_rows;
+  pp.range_min = cfg->range_min;
+  pp.range_max = cfg->range_max;
+  pp.shape = cfg->shape;
+  pp.radius = cfg->search_radius_pixels;
+  pp.max_desc_dist = cfg->maximum_descriptor_distance;
+  if (pp.shape < 0 || pp.shape > 3) return pslam_set_error(ctx, PSLAM_E_INVALID, "projective: unknown window shape", cudaSuccess);
+  if (pp.radius < 0 || pp.radius > 16000)
+    return pslam_set_error(ctx, PSLAM_E_INVALID, "projective: bad search radius", cudaSuccess);
+  const size_t smem = sizeof(int) * (size_t) (pp.radius + 1);
+  if (smem > 48 * 1024)
+    PSLAM_CUDA_TRY(ctx, cudaFuncSetAttribute(projective_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  return PSLAM_OK;
+}
+
+int pslam_k_projective_match(pslam_ctx* ctx, int n_fixed, int n_moving, const float* pose12,
+                             const pslam_projective_cfg* cfg, int capacity, int* h_fixed, int* h_moving,
+                             float* h_dist, int* n_projected, pslam_fused_gn* gn) {
+  ProjState st;
+  int rc = proj_layout(ctx, st, n_fixed, 2, n_moving);
+  if (rc) return rc;
+  if (n_projected) *n_projected = 0;
+  if (n_fixed == 0 || n_moving == 0) return 0;
+  ProjParams pp;
+  if ((rc = proj_params(ctx, cfg, pose12, pp))) return rc;
+  const size_t smem = sizeof(int) * (size_t) (pp.radius + 1);
+  projective_search_kernel<<<(n_moving + PJ_WARPS - 1) / PJ_WARPS, PJ_WARPS * 32, smem, ctx->stream>>>(
+    pp, st.d_moving, n_moving, st.d_desc_moving, st.d_lattice, n_fixed, st.d_desc_fixed, st.d_cand, nullptr, st.d_fixed,
+    ctx->proj_fixed_dim, nullptr);
+  PSLAM_LAUNCH_CHECK(ctx, "projective_search_kernel");
+  // one filter launch, one download (see filter_fused_kernel); the result block is transient: generic scratch
+  const size_t n_words = 1 + 2 * (size_t) n_fixed + 4 * (size_t) n_moving;
+  if (PSLAM_SOLVER_SCRATCH_OFFSET + 4 * n_words > ctx->scratch_bytes)
+    return pslam_set_error(ctx, PSLAM_E_CAPACITY, "projective: scratch too small for the result block", cudaSuccess);
+  int* d_out = reinterpret_cast<int*>(ctx->d_scratch + PSLAM_SOLVER_SCRATCH_OFFSET);
+  // fused solver iterations on the correspondences just found: their block sits directly behind the filter's, ONE download
+  size_t gn_words = 0;  // 4-byte words: [done, spd | pad to 8 B][n_iters x 16 doubles][status bytes, padded]
+  const size_t gn_off = (n_words + 1) & ~(size_t) 1;  // 8-byte aligned
+  int n_gn_iters = 0;
+  CompactArgs ca{};
+  if (gn) {
+    if (!gn->factor || gn->n_iterations < 0) return pslam_set_error(ctx, PSLAM_E_INVALID, "match_gn: factor configuration missing", cudaSuccess);
+    n_gn_iters = gn->n_iterations;
+    gn_words = 2 + 32 * (size_t) n_gn_iters + ((size_t) n_fixed + 3) / 4;
+    if (PSLAM_SOLVER_SCRATCH_OFFSET + 4 * (gn_off + gn_words) > ctx->scratch_bytes)
+      return pslam_set_error(ctx, PSLAM_E_CAPACITY, "match_gn: scratch too small", cudaSuccess);
+    ca = CompactArgs{1, ctx->proj_weights_epoch == ctx->proj_moving_epoch ? st.d_mscale : nullptr, gn->diagonal_info[0],
+                     gn->diagonal_info[1], gn->diagonal_info[2], st.d_gn_cf, st.d_gn_cm, st.d_gn_info, st.d_gn_ncorr, nullptr,
+                     PslamAlignCfg{}};
+  }
+  filter_fused_kernel<<<1, FF_THREADS, 0, ctx->stream>>>(st.d_cand, n_moving, n_fixed, st.d_key1, st.d_key2, cfg->descriptor_distance,
+                                                         cfg->maximum_distance_ratio_to_second_best, d_out, ca);
+  PSLAM_LAUNCH_CHECK(ctx, "filter_fused_kernel");
+  if (gn) {
+    int* d_done = d_out + gn_off;
+    double* d_gn_out = reinterpret_cast<double*>(d_done + 2);
+    uint8_t* d_status = reinterpret_cast<uint8_t*>(d_gn_out + 16 * (size_t) n_gn_iters);
+    if ((rc = pslam_k_gn_iterate_dev(ctx, gn->factor, n_gn_iters, gn->damping, gn->pose12, st.d_moving, st.d_fixed, ctx->proj_fixed_dim,
+                                     st.d_gn_ncorr, st.d_gn_cf, st.d_gn_cm, st.d_gn_info, gn->prior, d_gn_out, d_done, d_status)))
+      return rc;
+  }
+  const size_t all_words = gn ? gn_off + gn_words : n_words;
+  std::vector<int> pageable;
+  int* h_out = reinterpret_cast<int*>(ctx->h_pinned);
+  if (4 * all_words > ctx->pinned_bytes) {
+    pageable.resize(all_words);
+    h_out = pageable.data();
+  }
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(h_out, d_out, 4 * all_words, cudaMemcpyDeviceToHost, ctx->stream));
+  PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return proj_collect(h_out, n_fixed, n_moving, capacity, h_fixed, h_moving, h_dist, n_projected, gn, gn_off, n_gn_iters, -1, 0);
+}
+
+// The frame's whole registration on the device (see pslam_cuda.h): phases of { search, filter, compaction + the finder's
+// decisions, solver iterations } are queued a batch at a time; every kernel of a phase returns at once when the state says
+// the registration has stopped, so a batch costs one download whatever happens inside it.  The first batch holds exactly the
+// phases that MUST happen before the finder is allowed to converge (its iteration counter advances deterministically until
+// then) plus the first one that may; later batches hold two.
+int pslam_k_projective_align(pslam_ctx* ctx, int n_fixed, int n_moving, const pslam_projective_cfg* cfg, pslam_align* al,
+                             int capacity, int* h_fixed, int* h_moving, float* h_dist, pslam_fused_gn* gn) {
+  if (!al || !gn || !gn->factor) return pslam_set_error(ctx, PSLAM_E_INVALID, "align: configuration missing", cudaSuccess);
+  if (al->max_iterations <= 0 || gn->n_iterations < al->max_iterations || al->has_converged || al->solver_iterations_per_projection <= 0)
+    return pslam_set_error(ctx, PSLAM_E_INVALID, "align: bad iteration budget or finder state", cudaSuccess);
+  ProjState st;
+  int rc = proj_layout(ctx, st, n_fixed, 2, n_moving);
+  if (rc) return rc;
+  al->stop_reason = 0;
+  al->iterations_done = 0;
+  al->converged_with_good_ratio = 0;
+  al->n_projected = 0;
+  al->n_phases = 0;
+  gn->iterations_done = 0;
+  gn->spd = 1;
+  if (n_fixed == 0 || n_moving == 0) {
+    al->stop_reason = 3;
+    return 0;
+  }
+  ProjParams pp;
+  if ((rc = proj_params(ctx, cfg, nullptr, pp))) return rc;
+  const size_t smem = sizeof(int) * (size_t) (pp.radius + 1);
+  const int rows = al->max_iterations;
+  const size_t state_words = (sizeof(PslamAlignState) + 255) / 256 * 64;
+  const size_t n_words = 1 + 2 * (size_t) n_fixed + 4 * (size_t) n_moving;
+  const size_t gn_off = (n_words + 1) & ~(size_t) 1;
+  const size_t gn_words = 2 + 32 * (size_t) rows + ((size_t) n_fixed + 3) / 4;
+  const size_t all_words = state_words + gn_off + gn_words;
+  if (PSLAM_SOLVER_SCRATCH_OFFSET + 4 * all_words > ctx->scratch_bytes)
+    return pslam_set_error(ctx, PSLAM_E_CAPACITY, "align: scratch too small", cudaSuccess);
+  int* d_base = reinterpret_cast<int*>(ctx->d_scratch + PSLAM_SOLVER_SCRATCH_OFFSET);
+  PslamAlignState* d_state = reinterpret_cast<PslamAlignState*>(d_base);
+  int* d_out = d_base + state_words;
+  int* d_done = d_out + gn_off;
+  double* d_gn_out = reinterpret_cast<double*>(d_done + 2);
+  uint8_t* d_status = reinterpret_cast<uint8_t*>(d_gn_out + 16 * (size_t) rows);
+  std::vector<int> pageable;
+  int* h_all = reinterpret_cast<int*>(ctx->h_pinned);
+  if (4 * all_words > ctx->pinned_bytes) {
+    pageable.resize(all_words);
+    h_all = pageable.data();
+  }
+  PslamAlignState* h_state = reinterpret_cast<PslamAlignState*>(h_all);
+  memset(h_state, 0, sizeof(*h_state));
+  for (int i = 0; i < 12; ++i) {
+    h_state->estimate[i] = gn->pose12[i];
+    h_state->prev[i] = al->previous12[i];
+  }
+  h_state->current_iteration = al->current_iteration;
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_state, h_state, sizeof(*h_state), cudaMemcpyHostToDevice, ctx->stream));
+  PslamAlignCfg a;
+  a.max_iterations = al->max_iterations;
+  a.per_projection = al->solver_iterations_per_projection;
+  a.min_iterations = al->minimum_number_of_iterations;
+  a.can_widen = al->can_widen_search;
+  a.min_corr = al->min_num_correspondences;
+  a.max_change_norm = al->maximum_estimate_change_norm_for_convergence;
+  a.min_matching_ratio = al->minimum_matching_ratio;
+  const CompactArgs ca{1, ctx->proj_weights_epoch == ctx->proj_moving_epoch ? st.d_mscale : nullptr, gn->diagonal_info[0],
+                       gn->diagonal_info[1], gn->diagonal_info[2], st.d_gn_cf, st.d_gn_cm, st.d_gn_info, st.d_gn_ncorr, d_state, a};
+  int first_batch = 0;
+  for (int ci = al->current_iteration, it = 0; first_batch < 16;) {
+    ++first_batch;
+    if (ci > a.min_iterations) break;  // this phase may converge and spend the whole budget
+    int n_fused = a.max_iterations - it, quiet = 0;
+    for (int k = ci + 1; !(k % a.per_projection == 0 || k == 1) && quiet < n_fused; ++k) ++quiet;
+    if (quiet + 1 < n_fused) n_fused = quiet + 1;
+    it += n_fused;
+    ci += n_fused;
+    if (it >= a.max_iterations) break;
+  }
+  for (int queued = 0; queued < PSLAM_ALIGN_MAX_PHASES;) {
+    const int batch = queued == 0 ? first_batch : 2;
+    queued += batch;
+    for (int p = 0; p < batch; ++p) {
+      projective_search_kernel<<<(n_moving + PJ_WARPS - 1) / PJ_WARPS, PJ_WARPS * 32, smem, ctx->stream>>>(
+        pp, st.d_moving, n_moving, st.d_desc_moving, st.d_lattice, n_fixed, st.d_desc_fixed, st.d_cand, nullptr, st.d_fixed,
+        ctx->proj_fixed_dim, d_state);
+      PSLAM_LAUNCH_CHECK(ctx, "projective_search_kernel");
+      filter_fused_kernel<<<1, FF_THREADS, 0, ctx->stream>>>(st.d_cand, n_moving, n_fixed, st.d_key1, st.d_key2, cfg->descriptor_distance,
+                                                             cfg->maximum_distance_ratio_to_second_best, d_out, ca);
+      PSLAM_LAUNCH_CHECK(ctx, "filter_fused_kernel");
+      if ((rc = pslam_k_gn_iterate_dev(ctx, gn->factor, 0, gn->damping, gn->pose12, st.d_moving, st.d_fixed, ctx->proj_fixed_dim,
+                                       st.d_gn_ncorr, st.d_gn_cf, st.d_gn_cm, st.d_gn_info, gn->prior, d_gn_out, d_done, d_status,
+                                       d_state, al->max_iterations)))
+        return rc;
+    }
+    PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(h_all, d_base, 4 * all_words, cudaMemcpyDeviceToHost, ctx->stream));
+    PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (h_state->stop) break;
+  }
+  al->stop_reason = h_state->stop;
+  al->iterations_done = h_state->it;
+  al->converged_with_good_ratio = h_state->converged_ratio_ok;
+  al->n_projected = h_state->n_projected;
+  al->n_phases = h_state->phases;
+  al->current_iteration = h_state->current_iteration;
+  al->has_converged = h_state->has_converged;
+  for (int i = 0; i < 12; ++i) al->previous12[i] = h_state->prev[i];
+  memcpy(al->phase_log, h_state->phase_log, sizeof(al->phase_log));
+  for (int i = 0; i < 12; ++i) gn->pose12[i] = h_state->estimate[i];
+  if (h_state->phases == 0) return 0;  // the first phase already needs the caller: nothing to report
+  return proj_collect(h_all + state_words, n_fixed, n_moving, capacity, h_fixed, h_moving, h_dist, nullptr, gn, gn_off, rows, h_state->it,
+                      h_state->stop == 4 ? 0 : 1);
 }

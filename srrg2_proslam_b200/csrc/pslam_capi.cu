@@ -1406,6 +1406,14 @@ int pslam_projective_match_gn(pslam_ctx* ctx, int n_fixed, int n_moving, const f
   gn->spd = 1;
   return pslam_k_projective_match(ctx, n_fixed, n_moving, pose12, cfg, capacity, fixed_idx, moving_idx, distance, n_projected, gn);
 }
+int pslam_projective_align(pslam_ctx* ctx, int n_fixed, int n_moving, const pslam_projective_cfg* cfg, pslam_align* align,
+                           int capacity, int* fixed_idx, int* moving_idx, float* distance, pslam_fused_gn* gn) {
+  if (!ctx || !cfg || !align || !gn || capacity < 0) return PSLAM_E_INVALID;
+  if (ctx->proj_fixed_epoch == 0 || ctx->proj_moving_epoch == 0)
+    return pslam_set_error(ctx, PSLAM_E_INVALID, "projective_align: set_fixed / set_moving have not been called on this context", cudaSuccess);
+  PSLAM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  return pslam_k_projective_align(ctx, n_fixed, n_moving, cfg, align, capacity, fixed_idx, moving_idx, distance, gn);
+}
 int pslam_match_projective(pslam_ctx* ctx, int n_fixed, const float* fixed_coords, int fixed_dim,
                            const uint8_t* desc_fixed, int n_moving, const float* moving_xyz,
                            const uint8_t* desc_moving, const float* pose12,

@@ -56,10 +56,28 @@ int pslam_k_projective_set_moving_weights(pslam_ctx* ctx, int n_moving, const fl
 int pslam_k_projective_match(pslam_ctx* ctx, int n_fixed, int n_moving, const float* pose12,
                              const pslam_projective_cfg* cfg, int capacity, int* h_fixed,
                              int* h_moving, float* h_dist, int* n_projected, pslam_fused_gn* gn = nullptr);
+// device-resident state of one fused alignment (pslam_projective_align): the finder's state machine + the solver's estimate
+struct PslamAlignState {
+  double estimate[12];  // solver's estimate (moving in fixed), 3x4 row-major
+  float prev[12];       // finder's _local_map_in_sensor_previous
+  int current_iteration, has_converged, converged_ratio_ok;
+  int it;               // solver iterations done
+  int stop;             // 0 running, 1 budget spent, 2 low matching ratio, 3 too few correspondences, 4 not positive definite
+  int phases, n_fused, n_corr, n_projected, pad;
+  int phase_log[3 * PSLAM_ALIGN_MAX_PHASES];
+};
+struct PslamAlignCfg {
+  int max_iterations, per_projection, min_iterations, can_widen, min_corr;
+  float max_change_norm, min_matching_ratio;
+};
+// state != nullptr: iterations, start estimate and output row come from the state (left by the search phase), which is advanced
 int pslam_k_gn_iterate_dev(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, int n_iters, double damping, const double* pose12,
                            const float* d_moving_xyz, const float* d_fixed_meas, int fixed_dim, const int* d_n_corr,
                            const int* d_corr_fixed, const int* d_corr_moving, const float* d_info_diag,
-                           const pslam_pose_prior* prior, double* d_out, int* d_done, uint8_t* d_status);
+                           const pslam_pose_prior* prior, double* d_out, int* d_done, uint8_t* d_status,
+                           PslamAlignState* d_state = nullptr, int max_iterations = 0);
+int pslam_k_projective_align(pslam_ctx* ctx, int n_fixed, int n_moving, const pslam_projective_cfg* cfg, pslam_align* align,
+                             int capacity, int* h_fixed, int* h_moving, float* h_dist, pslam_fused_gn* gn);
 
 // k_linearize.cu  (T = float | double: scalar type of the clouds)
 template <typename T>

@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <mutex>
 
 namespace pslam_host {
@@ -376,7 +377,7 @@ void CorrespondenceFinderDescriptorBasedEpipolarCUDA::compute() {
 }
 
 // ---- projective finder: host state machine (projective_base_impl.cpp:104-293), device search + filter ---------
-void CorrespondenceFinderProjectiveCUDA::compute() {
+void CorrespondenceFinderProjectiveCUDA::_prepare() {
   _preCompute();
   pslam_ctx* ctx = PslamDevice::context();
   // the device cache is shared by every finder instance of the process (and dropped when the context is re-created):
@@ -423,12 +424,120 @@ void CorrespondenceFinderProjectiveCUDA::compute() {
     pslam_projective_cache_epochs(ctx, &_device_fixed_epoch, &_device_moving_epoch);
     _config_changed = false;
   }
+}
+
+pslam_projective_cfg CorrespondenceFinderProjectiveCUDA::_deviceConfig() const {
+  const ProjectorPinhole& projector = *param_projector.value();
+  pslam_projective_cfg cfg{};
+  for (int i = 0; i < 9; ++i) cfg.K[i] = projector.cameraMatrix()[i];
+  cfg.canvas_rows = (int) projector.param_canvas_rows.value();
+  cfg.canvas_cols = (int) projector.param_canvas_cols.value();
+  cfg.range_min = projector.param_range_min.value();
+  cfg.range_max = projector.param_range_max.value();
+  cfg.shape = _shape;
+  cfg.search_radius_pixels = (int) _search_radius_pixels;
+  cfg.descriptor_distance = _descriptor_distance;
+  cfg.maximum_distance_ratio_to_second_best = param_maximum_distance_ratio_to_second_best.value();
+  cfg.maximum_descriptor_distance = param_maximum_descriptor_distance.value();
+  return cfg;
+}
+
+void CorrespondenceFinderProjectiveCUDA::_uploadWeights(pslam_ctx* ctx, const float* moving_scale) {
+  if (!moving_scale) return;
+  unsigned long long fe = 0, me = 0;
+  pslam_projective_cache_epochs(ctx, &fe, &me);
+  if (_device_weights_of != moving_scale || _device_weights_epoch != me) {
+    PslamDevice::check(pslam_projective_set_moving_weights(ctx, (int) _moving->size(), moving_scale),
+                       "CorrespondenceFinderProjective::compute");
+    _device_weights_of = moving_scale;
+    _device_weights_epoch = me;
+  }
+}
+
+void CorrespondenceFinderProjectiveCUDA::_adaptAfterConvergence() {
+  _search_radius_pixels = std::max<size_t>(_search_radius_pixels - param_search_radius_step_size_pixels.value(),
+                                           param_minimum_search_radius_pixels.value());
+  _descriptor_distance = std::min(_descriptor_distance + param_descriptor_distance_step_size_pixels.value(),
+                                  param_maximum_descriptor_distance.value());
+}
+
+bool CorrespondenceFinderProjectiveCUDA::alignFused(FusedSolveRequest& r, int min_num_correspondences) {
+  if (!_fixed || !_moving || !_correspondences || _fixed->empty() || _moving->empty()) return false;
+  if (!r.factor || r.max_fused <= 0 || !param_projector.value() || _moving->dim != 3) return false;
+  const size_t N = param_number_of_solver_iterations_per_projection.value();
+  if (N == 0 || r.max_fused > (1 << 20)) return false;
+  _prepare();
+  if (_has_converged || !(_current_iteration % N == 0 || _current_iteration == 1)) return false;
+  pslam_ctx* ctx = PslamDevice::context();
+  _uploadWeights(ctx, r.moving_scale);
+  const pslam_projective_cfg cfg = _deviceConfig();
+  pslam_align al{};
+  al.max_iterations = r.max_fused;
+  al.solver_iterations_per_projection = (int) N;
+  al.minimum_number_of_iterations = (int) param_minimum_number_of_iterations.value();
+  al.maximum_estimate_change_norm_for_convergence = param_maximum_estimate_change_norm_for_convergence.value();
+  al.minimum_matching_ratio = param_minimum_matching_ratio.value();
+  al.can_widen_search = (_search_radius_pixels < param_maximum_search_radius_pixels.value() ||
+                         _descriptor_distance > param_minimum_descriptor_distance.value()) ? 1 : 0;
+  al.min_num_correspondences = min_num_correspondences;
+  al.current_iteration = (int) _current_iteration;
+  al.has_converged = 0;
+  for (int i = 0; i < 12; ++i) al.previous12[i] = _local_map_in_sensor_previous.m[i];
+  pslam_fused_gn g{};
+  g.factor = r.factor;
+  for (int i = 0; i < 3; ++i) g.diagonal_info[i] = r.diagonal_info[i];
+  g.n_iterations = r.max_fused;
+  g.damping = r.damping;
+  for (int i = 0; i < 12; ++i) g.pose12[i] = r.estimate[i];
+  g.prior = r.prior;
+  const int cap = (int) _fixed->size() + 1;
+  r.poses.resize(12 * (size_t) r.max_fused);
+  r.stats.resize(4 * (size_t) r.max_fused);
+  r.status.assign((size_t) cap, 0);
+  g.poses12 = r.poses.data();
+  g.stats4 = r.stats.data();
+  g.factor_status = r.status.data();
+  std::vector<int> f(cap), m(cap);
+  std::vector<float> d(cap);
+  const int n = pslam_projective_align(ctx, (int) _fixed->size(), (int) _moving->size(), &cfg, &al, cap, f.data(), m.data(), d.data(), &g);
+  PslamDevice::check(n, "CorrespondenceFinderProjective::compute");
+  r.executed = true;
+  r.done = al.iterations_done;
+  r.spd = g.spd != 0;
+  r.stop_reason = al.stop_reason;
+  r.phase_log.assign(al.phase_log, al.phase_log + 3 * std::min(al.n_phases, (int) PSLAM_ALIGN_MAX_PHASES));
+  r.status.resize((size_t) std::max(n, 0));
+  if (al.n_phases == 0) return true;  // the first search already needs the caller's loop: nothing has changed
+  // the state the call-by-call loop would have left behind
+  _number_of_searches += al.n_phases;
+  _current_iteration = (size_t) al.current_iteration;
+  _has_converged = al.has_converged != 0;
+  for (int i = 0; i < 12; ++i) _local_map_in_sensor_previous.m[i] = al.previous12[i];
+  {  // _local_map_in_sensor = the pose handed to the last compute() of the loop
+    const int last = al.n_phases - 1, start = al.phase_log[3 * last], done = al.phase_log[3 * last + 1];
+    const int row = done >= 2 ? start + done - 2 : start - 1;  // pose after that solver iteration (-1: the initial estimate)
+    for (int i = 0; i < 12; ++i) _local_map_in_sensor.m[i] = (float) (row >= 0 ? r.poses[12 * (size_t) row + i] : r.estimate[i]);
+  }
+  for (int p = 0; p < al.n_phases && p < (int) PSLAM_ALIGN_MAX_PHASES; ++p) {
+    const float matching_ratio = static_cast<float>(al.phase_log[3 * p + 2]) / _fixed->size();
+    if (matching_ratio < param_minimum_matching_ratio.value())
+      std::cerr << "CorrespondenceFinderProjective::compute|low matching ratio: " << matching_ratio << " (" << al.phase_log[3 * p + 2]
+                << "/" << _fixed->size() << ") target: " << param_minimum_matching_ratio.value() << std::endl;
+  }
+  if (al.converged_with_good_ratio) _adaptAfterConvergence();
+  if (al.stop_reason != 2 && al.stop_reason != 3) fill(*_correspondences, n, f, m, d);
+  _postCompute();
+  return true;
+}
+
+void CorrespondenceFinderProjectiveCUDA::compute() {
+  _prepare();
+  pslam_ctx* ctx = PslamDevice::context();
   if (_has_converged) {  // correspondences are not touched (:137-141)
     _postCompute();
     return;
   }
   if (!param_projector.value()) throw std::runtime_error("CorrespondenceFinderProjective::compute|ERROR: projector not set");
-  const ProjectorPinhole& projector = *param_projector.value();
 
   // periodically re-project; always for iterations 0 and 1 (:162-178)
   if (!(_current_iteration % param_number_of_solver_iterations_per_projection.value() == 0 || _current_iteration == 1)) {
@@ -445,17 +554,7 @@ void CorrespondenceFinderProjectiveCUDA::compute() {
   _local_map_in_sensor_previous = _local_map_in_sensor;
 
   // projector->compute + _findNearestNeighbors + _filterCorrespondences: one device call
-  pslam_projective_cfg cfg{};
-  for (int i = 0; i < 9; ++i) cfg.K[i] = projector.cameraMatrix()[i];
-  cfg.canvas_rows = (int) projector.param_canvas_rows.value();
-  cfg.canvas_cols = (int) projector.param_canvas_cols.value();
-  cfg.range_min = projector.param_range_min.value();
-  cfg.range_max = projector.param_range_max.value();
-  cfg.shape = _shape;
-  cfg.search_radius_pixels = (int) _search_radius_pixels;
-  cfg.descriptor_distance = _descriptor_distance;
-  cfg.maximum_distance_ratio_to_second_best = param_maximum_distance_ratio_to_second_best.value();
-  cfg.maximum_descriptor_distance = param_maximum_descriptor_distance.value();
+  const pslam_projective_cfg cfg = _deviceConfig();
   const int cap = (int) _fixed->size() + 1;
   std::vector<int> f(cap), m(cap);
   std::vector<float> d(cap);
@@ -474,16 +573,7 @@ void CorrespondenceFinderProjectiveCUDA::compute() {
       for (size_t it = _current_iteration + 1; !(it % N == 0 || it == 1); ++it) ++quiet;
     }
     const int n_fused = quiet >= _fused->max_fused ? _fused->max_fused : quiet + 1;
-    if (_fused->moving_scale) {
-      unsigned long long fe = 0, me = 0;
-      pslam_projective_cache_epochs(ctx, &fe, &me);
-      if (_device_weights_of != _fused->moving_scale || _device_weights_epoch != me) {
-        PslamDevice::check(pslam_projective_set_moving_weights(ctx, (int) _moving->size(), _fused->moving_scale),
-                           "CorrespondenceFinderProjective::compute");
-        _device_weights_of = _fused->moving_scale;
-        _device_weights_epoch = me;
-      }
-    }
+    _uploadWeights(ctx, _fused->moving_scale);
     pslam_fused_gn g{};
     g.factor = _fused->factor;
     for (int i = 0; i < 3; ++i) g.diagonal_info[i] = _fused->diagonal_info[i];
@@ -537,12 +627,7 @@ void CorrespondenceFinderProjectiveCUDA::compute() {
   if (estimate_change_norm < param_maximum_estimate_change_norm_for_convergence.value() &&
       _current_iteration > param_minimum_number_of_iterations.value()) {
     _has_converged = true;
-    if (matching_ratio > param_minimum_matching_ratio.value()) {
-      _search_radius_pixels = std::max<size_t>(_search_radius_pixels - param_search_radius_step_size_pixels.value(),
-                                               param_minimum_search_radius_pixels.value());
-      _descriptor_distance = std::min(_descriptor_distance + param_descriptor_distance_step_size_pixels.value(),
-                                      param_maximum_descriptor_distance.value());
-    }
+    if (matching_ratio > param_minimum_matching_ratio.value()) _adaptAfterConvergence();
   }
   ++_current_iteration;
   _postCompute();
@@ -1073,7 +1158,30 @@ void MultiAligner3DQRCUDA::compute() {
       }
     fused.moving_scale = moving_scale.data();
   }
-  for (int it = 0; it < max_iterations;) {
+  int it = 0;
+  bool solve_failed = false;
+  // The whole loop below, device resident (pslam_projective_align): the finder's state machine runs between the searches on
+  // the device, one download per batch of search phases.  It hands back with `it` iterations done wherever a decision needs
+  // this loop (repeat with a wider search, too few correspondences); PSLAM_ALIGN_DEVICE=0 keeps the call-by-call path.
+  const char* align_env = std::getenv("PSLAM_ALIGN_DEVICE");
+  if (can_fuse && !(align_env && align_env[0] == '0')) {
+    fused.executed = false;
+    fused.max_fused = max_iterations;
+    for (int i = 0; i < 12; ++i) fused.estimate[i] = _estimate[i];
+    if (finder.alignFused(fused, std::max(slice->param_min_num_correspondences.value(), 1)) && fused.executed) {
+      for (size_t p = 0; 3 * p + 2 < fused.phase_log.size(); ++p) {
+        const int start = fused.phase_log[3 * p], done = fused.phase_log[3 * p + 1];
+        stats.assign(fused.stats.begin() + 4 * (size_t) start, fused.stats.begin() + 4 * (size_t) (start + done));
+        push_stats(_stats, start, done, fused.phase_log[3 * p + 2]);
+      }
+      if (fused.done > 0)
+        for (int i = 0; i < 12; ++i) _estimate[i] = fused.poses[12 * (size_t) (fused.done - 1) + i];
+      factor_status = fused.status;
+      it = fused.done;
+      solve_failed = fused.stop_reason == 4;
+    }
+  }
+  for (; it < max_iterations && !solve_failed;) {
     Isometry3f X;
     for (int i = 0; i < 12; ++i) X.m[i] = (float) _estimate[i];
     finder.setLocalMapInSensor(X);

@@ -218,11 +218,24 @@ struct FusedSolveRequest {
   int done = 0;
   std::vector<double> poses, stats;
   std::vector<uint8_t> status;
+  // alignFused only: why the device-resident registration handed back (pslam_align.stop_reason) and, per search phase,
+  // (first solver iteration, iterations done, correspondences)
+  int stop_reason = 0;
+  std::vector<int> phase_log;
 };
 
 class CorrespondenceFinderBase : public Configurable {
 public:
   virtual void setFusedSolve(FusedSolveRequest* r) { (void) r; }
+  // The aligner's whole loop { compute(); solver iterations } from the current estimate, as far as this finder can take it on
+  // the device (pslam_projective_align).  false: nothing done, the caller runs its loop.  true: r.done iterations were
+  // executed (r.poses / r.stats / r.phase_log), the finder is in the state the call-by-call loop would have left it in, and
+  // r.stop_reason tells whether the caller's loop has anything left to do.
+  virtual bool alignFused(FusedSolveRequest& r, int min_num_correspondences) {
+    (void) r;
+    (void) min_num_correspondences;
+    return false;
+  }
   void setFixed(const PointIntensityDescriptorCloud* fixed) {
     _fixed = fixed;
     _fixed_changed_flag = true;
@@ -299,9 +312,14 @@ public:
   int numberOfSearches() const { return _number_of_searches; }
   int callsWithoutNewCorrespondences() const override;
   void setFusedSolve(FusedSolveRequest* r) override { _fused = r; }
+  bool alignFused(FusedSolveRequest& r, int min_num_correspondences) override;
   int shape() const { return _shape; }
 
 private:
+  void _prepare();                                            // :104-160: checks, device uploads, state reset on new clouds
+  pslam_projective_cfg _deviceConfig() const;                 // projector + current thresholds
+  void _uploadWeights(pslam_ctx* ctx, const float* moving_scale);
+  void _adaptAfterConvergence();                              // :272-283
   int _shape;
   bool _config_changed = true;
   size_t _search_radius_pixels = 0;

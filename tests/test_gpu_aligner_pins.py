@@ -58,6 +58,7 @@ def configure(P, name):
             finder.set("minimum_search_radius_pixels", 10).set("maximum_search_radius_pixels", 50)
             finder.set("number_of_solver_iterations_per_projection", 5)
     sl.set("finder", finder).set("projector", projector)
+    al.fixture_finder = finder
     sl.set("diagonal_info_matrix", sc["diag"])
     al.aligner_set_fixed(fixed, fdesc)
     al.aligner_set_moving(xyz, mdesc)
@@ -98,3 +99,31 @@ def test_constant_velocity_prior_seeds_and_pulls(P):
     g = al.aligner_compute()
     assert np.abs(O.t2tnq(O.pose_mul(O.pose_inverse(pred), g["pose"]))).max() < 1e-4
     assert np.abs(pred - O.pose_mul(step, step)).max() < 1e-5  # two steps of the same motion (the chunk travels as fp32)
+
+
+@pytest.mark.parametrize("name", sorted(n for n in A.SCENARIOS if A.SCENARIOS[n]["finder"][0] != "bruteforce"))
+def test_device_resident_alignment_equals_call_by_call(P, name, monkeypatch):
+    """pslam_projective_align (the finder's state machine on the device, one download per batch of search phases) against the
+    call-by-call loop (one pslam_projective_match_gn per search): bit-identical poses, per-iteration stats, correspondences
+    and finder state -- on a frame and on the frame after it (the finder carries radius / descriptor distance over)."""
+    def run(env):
+        monkeypatch.setenv("PSLAM_ALIGN_DEVICE", env)
+        al, gt = configure(P, name)
+        out = []
+        for _ in range(2):
+            sc, d, fixed, fdesc, xyz, mdesc, gt_, init = A.scenario_inputs(name)
+            al.aligner_set_fixed(fixed, fdesc)
+            al.aligner_set_moving(xyz, mdesc)
+            al.aligner_set_moving_in_fixed(init.astype(np.float32))
+            g = al.aligner_compute()
+            g["finder"] = al.fixture_finder.projective_state()
+            out.append(g)
+        return out
+    a, b = run("1"), run("0")
+    for ga, gb in zip(a, b):
+        assert ga["status"] == gb["status"] and ga["iterations"] == gb["iterations"]
+        assert np.array_equal(ga["pose"], gb["pose"])
+        assert np.array_equal(ga["stats"], gb["stats"])
+        assert all(np.array_equal(x, y) for x, y in zip(ga["corr"], gb["corr"]))
+        assert np.array_equal(ga["inlier_run_stats"], gb["inlier_run_stats"])
+        assert ga["finder"] == gb["finder"]
