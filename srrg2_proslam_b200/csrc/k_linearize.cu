@@ -421,6 +421,7 @@ struct GnWork {
   double Om[36];                               // the prior's information matrix (kernel parameters indexed per lane would serialise)
   double ER[9], Et[3], e6[6], Q[9], OJ[36], Oe[6];  // pose-prior scratch (its own warp)
   double Hp[36], bp[6];                        // the prior's contribution to H, b for the current pose
+  double Rp[9], tp[3];                         // the pose before the last update (= after the iteration before the last)
 };
 
 // t2tnq with reciprocal square roots in place of the sqrt + divide pairs (the prior sits on the iteration's critical path
@@ -569,7 +570,14 @@ __device__ __forceinline__ bool gn_solve6_block(const double* U, const double* b
 // reduction's output, read in place: no 6x6 staging copy); the prior's S.Hp, S.bp are added when with_prior.  S.R, S.t in / out.
 // All 32 lanes call it: every lane solves the (tiny) system and forms the update rotation in its own registers -- nothing
 // is exchanged until lanes 0..11 each write one element of the new pose.
-__device__ __forceinline__ bool gn_solve_update_warp(GnWork& S, const double* sums, bool with_prior, double damping, int lane) {
+// row (shared memory, 12 doubles): the pose after this iteration in 3x4 row-major order (the unchanged pose when the solve
+// fails); S.Rp, S.tp <- the pose before the update.  Both straight from the lanes' registers.
+__device__ __forceinline__ bool gn_solve_update_warp(GnWork& S, const double* sums, bool with_prior, double damping, int lane,
+                                                     double* row) {
+  const int pos = lane < 9 ? 4 * (lane / 3) + lane % 3 : 4 * (lane - 9) + 3;  // lane's element of the pose in the row
+  double old = 0;
+  if (lane < 9) old = S.R[lane];
+  else if (lane < 12) old = S.t[lane - 9];
   double U[21], g[6], dx[6];
   {
     int h = 0;
@@ -580,7 +588,10 @@ __device__ __forceinline__ bool gn_solve_update_warp(GnWork& S, const double* su
 #pragma unroll
     for (int a = 0; a < 6; ++a) g[a] = with_prior ? sums[21 + a] + S.bp[a] : sums[21 + a];
   }
-  if (!gn_solve6_block(U, g, damping, dx)) return false;  // uniform: every lane evaluates the same values
+  if (!gn_solve6_block(U, g, damping, dx)) {  // uniform: every lane evaluates the same values
+    if (lane < 12) row[pos] = old;
+    return false;
+  }
   // v2t(dx): unit quaternion (x, y, z, w) from its imaginary part, normalised when longer than 1
   double x = dx[3], y = dx[4], z = dx[5];
   const double n2 = fma(x, x, fma(y, y, z * z));
@@ -608,8 +619,9 @@ __device__ __forceinline__ bool gn_solve_update_warp(GnWork& S, const double* su
     nv = fma(S.R[3 * i], dx[0], fma(S.R[3 * i + 1], dx[1], fma(S.R[3 * i + 2], dx[2], S.t[i])));
   }
   __syncwarp();
-  if (lane < 9) S.R[lane] = nv;
-  else if (lane < 12) S.t[lane - 9] = nv;
+  if (lane < 9) S.R[lane] = nv, S.Rp[lane] = old;
+  else if (lane < 12) S.t[lane - 9] = nv, S.tp[lane - 9] = old;
+  if (lane < 12) row[pos] = nv;
   __syncwarp();
   return true;
 }
@@ -648,10 +660,11 @@ gn_iterate_kernel(LinParams c0, PriorParams prior, double damping, int n_iters, 
   __shared__ double s_sum[LZ_NACC];
   __shared__ GnWork S;
   __shared__ int s_ok;
-  // small problems (the per-frame case): the 31 partial sums of every thread go through shared memory, four threads per sum
-  // add them up -- ~0.5 k cycles instead of the ~1.9 k of a 5-level fp64 shuffle butterfly over 31 values plus the cross-warp pass
+  // small problems (the per-frame case): the 31 partial sums of every thread go through shared memory, eight threads per PAIR
+  // of sums add them up (instead of a 5-level fp64 shuffle butterfly over 31 values plus the cross-warp pass: ~1.9 k cycles).
+  // 128-bit stores: the barrier that follows drains the stores in flight at tens of cycles apiece, so their NUMBER is the cost.
   constexpr int RED_CAP = 96, RED_PITCH = RED_CAP + 1;
-  __shared__ double s_acc[(LZ_NACC - 1) * RED_PITCH];
+  __shared__ double2 s_acc[(LZ_NACC / 2) * RED_PITCH];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (threadIdx.x < 9) S.R[threadIdx.x] = c0.R[threadIdx.x];
   if (threadIdx.x < 3) S.t[threadIdx.x] = c0.t[threadIdx.x];
@@ -664,6 +677,12 @@ gn_iterate_kernel(LinParams c0, PriorParams prior, double damping, int n_iters, 
   const bool warp_has_work = wid * 32 < n_corr;
   const bool small = n_corr <= RED_CAP;
   CorrData mine;
+  uint8_t my_status = 255;  // resident correspondences: the status stays in a register, ONE global store after the loop
+  // The barriers below order the block's global stores as well: every store in flight at a barrier is waited for (an HBM
+  // round trip per iteration when the loop stored its outputs as it went).  The per-iteration rows therefore collect in
+  // shared memory and leave in bursts of OUT_RING iterations.
+  constexpr int OUT_RING = 32;
+  __shared__ double s_out[OUT_RING * GN_OUT];
   if (resident && (int) threadIdx.x < n_corr)
     mine = load_correspondence(moving_xyz, fixed_meas, fixed_dim, corr_fixed[threadIdx.x], corr_moving[threadIdx.x], info_diag);
   int done = 0;
@@ -679,38 +698,46 @@ gn_iterate_kernel(LinParams c0, PriorParams prior, double damping, int n_iters, 
         double acc[LZ_NACC];
 #pragma unroll
         for (int i = 0; i < LZ_NACC; ++i) acc[i] = 0;
-        accumulate_loaded(c, edim, mine, acc, status ? status + threadIdx.x : nullptr);
+        accumulate_loaded(c, edim, mine, acc, &my_status);
 #pragma unroll
-        for (int i = 0; i < LZ_NACC - 1; ++i) s_acc[i * RED_PITCH + threadIdx.x] = acc[i];
+        for (int i = 0; i < LZ_NACC / 2; ++i) s_acc[i * RED_PITCH + threadIdx.x] = make_double2(acc[2 * i], acc[2 * i + 1]);
       }
       if (wid < 4) {  // correspondences (<= 96) and the 31 x 4 adders live in warps 0..3: a barrier of their own, the prior
                       // warp is only waited for at the block barrier below
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        const int v = threadIdx.x >> 2, part = threadIdx.x & 3;
-        double sum = 0;
-        if (v < LZ_NACC - 1) {  // four independent chains: the loads pipeline instead of alternating with dependent adds
-          const double* a = s_acc + v * RED_PITCH;
-          double s1 = 0, s2 = 0, s3 = 0;
-          int t = part;
-          for (; t + 12 < n_corr; t += 16) {
-            sum += a[t];
-            s1 += a[t + 4];
-            s2 += a[t + 8];
-            s3 += a[t + 12];
-          }
-          for (; t < n_corr; t += 4) sum += a[t];
-          sum = (sum + s1) + (s2 + s3);
+        const int pr = threadIdx.x >> 3, part = threadIdx.x & 7;  // 16 pairs x 8 adders = warps 0..3
+        const double2* a = s_acc + pr * RED_PITCH;
+        // at most RED_CAP / 8 = 12 entries per adder: all loads issued at once (predicated), then an add tree
+        double2 v[RED_CAP / 8];
+#pragma unroll
+        for (int k = 0; k < RED_CAP / 8; ++k) {
+          const int t = part + 8 * k;
+          v[k] = t < n_corr ? a[t] : make_double2(0.0, 0.0);
         }
-        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-        if (part == 0 && v < LZ_NACC - 1) s_sum[v] = sum;
+        static_assert(RED_CAP == 96, "the add tree below is written for 12 entries per adder");
+#pragma unroll
+        for (int k = 0; k < 6; ++k) v[k].x += v[k + 6].x, v[k].y += v[k + 6].y;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) v[k].x += v[k + 3].x, v[k].y += v[k + 3].y;
+        v[0].x += v[1].x, v[0].y += v[1].y;
+        v[0].x += v[2].x, v[0].y += v[2].y;
+        double sx = v[0].x, sy = v[0].y;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+          sx += __shfl_xor_sync(0xffffffffu, sx, o);
+          sy += __shfl_xor_sync(0xffffffffu, sy, o);
+        }
+        if (part == 0) {
+          s_sum[2 * pr] = sx;
+          s_sum[2 * pr + 1] = sy;  // [31] is padding
+        }
       }
     } else if (warp_has_work || !resident) {
       double acc[LZ_NACC];
 #pragma unroll
       for (int i = 0; i < LZ_NACC; ++i) acc[i] = 0;
       if (resident) {
-        if ((int) threadIdx.x < n_corr) accumulate_loaded(c, edim, mine, acc, status ? status + threadIdx.x : nullptr);
+        if ((int) threadIdx.x < n_corr) accumulate_loaded(c, edim, mine, acc, &my_status);
       } else {
         for (int k = threadIdx.x; k < n_corr; k += LZ_THREADS)
           accumulate_correspondence(c, edim, moving_xyz, fixed_meas, fixed_dim, corr_fixed[k], corr_moving[k], info_diag, acc,
@@ -732,16 +759,21 @@ gn_iterate_kernel(LinParams c0, PriorParams prior, double damping, int n_iters, 
     }
     if (!small) __syncthreads();
     if (wid == 0) {
-      const bool ok = gn_solve_update_warp(S, s_sum, prior.enabled != 0, damping, lane);  // pose untouched when not SPD
-      double* o = out + (size_t) it * GN_OUT;
-      if (lane < 12) o[lane] = (lane & 3) == 3 ? S.t[lane >> 2] : S.R[3 * (lane >> 2) + (lane & 3)];
-      else if (lane < 16) o[lane] = s_sum[27 + (lane - 12)];
+      const int slot = it % OUT_RING;
+      if (lane >= 12 && lane < 16) s_out[slot * GN_OUT + lane] = s_sum[27 + (lane - 12)];
+      const bool ok = gn_solve_update_warp(S, s_sum, prior.enabled != 0, damping, lane, s_out + slot * GN_OUT);  // pose untouched when not SPD
       if (lane == 0) s_ok = ok ? 1 : 0;
+      if (slot == OUT_RING - 1 || it == n_iters - 1 || !ok) {  // burst: rows it - slot .. it
+        __syncwarp();
+        double* o = out + (size_t) (it - slot) * GN_OUT;
+        for (int i = lane; i < (slot + 1) * GN_OUT; i += 32) o[i] = s_out[i];
+      }
     }
     __syncthreads();
     ++done;  // the iteration was linearised (its stats are valid) even when the solve failed
     if (!s_ok) break;
   }
+  if (status && resident && (int) threadIdx.x < n_corr && done > 0) status[threadIdx.x] = my_status;
   if (threadIdx.x == 0) {
     iters_done[0] = done;
     iters_done[1] = s_ok;
@@ -756,10 +788,10 @@ gn_iterate_kernel(LinParams c0, PriorParams prior, double damping, int n_iters, 
         state->phase_log[3 * ph + 2] = state->n_corr;
       }
       if (done > 0)
-        for (int i = 0; i < 12; ++i) state->estimate[i] = out[(size_t) (done - 1) * GN_OUT + i];
+        for (int i = 0; i < 12; ++i) state->estimate[i] = (i & 3) == 3 ? S.t[i >> 2] : S.R[3 * (i >> 2) + (i & 3)];
       if (s_ok && !state->has_converged) {
         if (done >= 2)
-          for (int i = 0; i < 12; ++i) state->prev[i] = (float) out[(size_t) (done - 2) * GN_OUT + i];
+          for (int i = 0; i < 12; ++i) state->prev[i] = (float) ((i & 3) == 3 ? S.tp[i >> 2] : S.Rp[3 * (i >> 2) + (i & 3)]);
         state->current_iteration += done - 1;
       }
       state->it += done;
