@@ -141,7 +141,9 @@ __device__ __forceinline__ void accumulate_loaded(const LinParams& c, int edim, 
   }
   const double* om = d.om;
   double chi = 0;
-  for (int i = 0; i < edim; ++i) chi = fma(e[i] * om[i], e[i], chi);
+#pragma unroll
+  for (int i = 0; i < 3; ++i)  // edim is 2 or 3: unrolled under a predicate so that e, J, om stay in registers
+    if (i < edim) chi = fma(e[i] * om[i], e[i], chi);
   double scale = 1;
   if (c.robustifier != 0 && chi > c.chi_threshold) {
     acc[29] += 1;
@@ -152,7 +154,9 @@ __device__ __forceinline__ void accumulate_loaded(const LinParams& c, int edim, 
     if (status) *status = 0;
   }
   acc[27] = fma(chi, scale, acc[27]);
-  for (int i = 0; i < edim; ++i) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    if (i >= edim) break;
     const double w = om[i] * scale;
     int h = 0;
 #pragma unroll
