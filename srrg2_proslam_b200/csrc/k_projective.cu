@@ -85,11 +85,11 @@ constexpr int PJ_WARPS = 8;
 __global__ void __launch_bounds__(PJ_WARPS * 32)
 projective_search_kernel(ProjParams pp, const float* __restrict__ moving_xyz, int n_moving,
                          const uint32_t* __restrict__ desc_moving,
-                         const unsigned long long* __restrict__ lattice, int n_fixed,
+                         const unsigned long long* lattice, int n_fixed,
                          const uint32_t* __restrict__ desc_fixed, int* __restrict__ cand,
                          int* __restrict__ n_projected, const float* __restrict__ fixed_coords, int fixed_dim,
-                         const PslamAlignState* __restrict__ state) {
-  extern __shared__ int s_width[];  // circle: width per |height| (0..radius)
+                         const PslamAlignState* __restrict__ state, int stage_lattice) {
+  extern __shared__ __align__(8) int s_width[];  // circle: width per |height| (0..radius); then the staged lattice
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (state) {  // a phase of pslam_projective_align: the pose is the solver's current estimate, rounded to fp32 as the caller's
                 // finder.setLocalMapInSensor(X) does (uniform reads; the state is only written by later launches)
@@ -105,8 +105,15 @@ projective_search_kernel(ProjParams pp, const float* __restrict__ moving_xyz, in
     const int r2 = pp.radius * pp.radius;
     for (int h = threadIdx.x; h <= pp.radius; h += PJ_WARPS * 32)
       s_width[h] = (int) sqrt((double) (r2 - h * h)) + 1;  // circle_impl.cpp:51-54
-    __syncthreads();
   }
+  // frame-sized fixed clouds: the lattice (8 B per point) is staged in shared memory once per CTA -- the binary search and the
+  // window walk below are chains of dependent loads, an L2 round trip apiece otherwise
+  if (stage_lattice) {
+    unsigned long long* s_lat = reinterpret_cast<unsigned long long*>(s_width + ((pp.radius + 2) & ~1));
+    for (int i = threadIdx.x; i < n_fixed; i += PJ_WARPS * 32) s_lat[i] = lattice[i];
+    lattice = s_lat;
+  }
+  __syncthreads();
   const int m = blockIdx.x * PJ_WARPS + wid;
   if (m >= n_moving) return;
   // ---- pinhole projection, fp32, operation order of oracle/pslam_oracle_solver.hpp::project_point
@@ -565,7 +572,12 @@ static int proj_collect(const int* h_out, int n_fixed, int n_moving, int capacit
   return n_out;
 }
 
-static int proj_params(pslam_ctx* ctx, const pslam_projective_cfg* cfg, const float* pose12, ProjParams& pp) {
+// dynamic shared memory of the search: the circle's width table (+ the lattice when the fixed cloud is frame sized)
+constexpr int PJ_STAGE_MAX = 4096;
+static size_t search_smem(int radius, int n_fixed) {
+  return sizeof(int) * (size_t) ((radius + 2) & ~1) + (n_fixed <= PJ_STAGE_MAX ? 8 * (size_t) n_fixed : 0);
+}
+static int proj_params(pslam_ctx* ctx, const pslam_projective_cfg* cfg, const float* pose12, ProjParams& pp, int n_fixed) {
   for (int i = 0; i < 3; ++i) {
     for (int j = 0; j < 3; ++j) pp.R[3 * i + j] = pose12 ? pose12[4 * i + j] : (i == j ? 1.f : 0.f);
     pp.t[i] = pose12 ? pose12[4 * i + 3] : 0.f;
@@ -581,7 +593,7 @@ static int proj_params(pslam_ctx* ctx, const pslam_projective_cfg* cfg, const fl
   if (pp.shape < 0 || pp.shape > 3) return pslam_set_error(ctx, PSLAM_E_INVALID, "projective: unknown window shape", cudaSuccess);
   if (pp.radius < 0 || pp.radius > 16000)
     return pslam_set_error(ctx, PSLAM_E_INVALID, "projective: bad search radius", cudaSuccess);
-  const size_t smem = sizeof(int) * (size_t) (pp.radius + 1);
+  const size_t smem = search_smem(pp.radius, n_fixed);
   if (smem > 48 * 1024)
     PSLAM_CUDA_TRY(ctx, cudaFuncSetAttribute(projective_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   return PSLAM_OK;
@@ -596,11 +608,11 @@ int pslam_k_projective_match(pslam_ctx* ctx, int n_fixed, int n_moving, const fl
   if (n_projected) *n_projected = 0;
   if (n_fixed == 0 || n_moving == 0) return 0;
   ProjParams pp;
-  if ((rc = proj_params(ctx, cfg, pose12, pp))) return rc;
-  const size_t smem = sizeof(int) * (size_t) (pp.radius + 1);
+  if ((rc = proj_params(ctx, cfg, pose12, pp, n_fixed))) return rc;
+  const size_t smem = search_smem(pp.radius, n_fixed);
   projective_search_kernel<<<(n_moving + PJ_WARPS - 1) / PJ_WARPS, PJ_WARPS * 32, smem, ctx->stream>>>(
     pp, st.d_moving, n_moving, st.d_desc_moving, st.d_lattice, n_fixed, st.d_desc_fixed, st.d_cand, nullptr, st.d_fixed,
-    ctx->proj_fixed_dim, nullptr);
+    ctx->proj_fixed_dim, nullptr, n_fixed <= PJ_STAGE_MAX ? 1 : 0);
   PSLAM_LAUNCH_CHECK(ctx, "projective_search_kernel");
   // one filter launch, one download (see filter_fused_kernel); the result block is transient: generic scratch
   const size_t n_words = 1 + 2 * (size_t) n_fixed + 4 * (size_t) n_moving;
@@ -670,8 +682,8 @@ int pslam_k_projective_align(pslam_ctx* ctx, int n_fixed, int n_moving, const ps
     return 0;
   }
   ProjParams pp;
-  if ((rc = proj_params(ctx, cfg, nullptr, pp))) return rc;
-  const size_t smem = sizeof(int) * (size_t) (pp.radius + 1);
+  if ((rc = proj_params(ctx, cfg, nullptr, pp, n_fixed))) return rc;
+  const size_t smem = search_smem(pp.radius, n_fixed);
   const int rows = al->max_iterations;
   const size_t state_words = (sizeof(PslamAlignState) + 255) / 256 * 64;
   const size_t n_words = 1 + 2 * (size_t) n_fixed + 4 * (size_t) n_moving;
@@ -727,7 +739,7 @@ int pslam_k_projective_align(pslam_ctx* ctx, int n_fixed, int n_moving, const ps
     for (int p = 0; p < batch; ++p) {
       projective_search_kernel<<<(n_moving + PJ_WARPS - 1) / PJ_WARPS, PJ_WARPS * 32, smem, ctx->stream>>>(
         pp, st.d_moving, n_moving, st.d_desc_moving, st.d_lattice, n_fixed, st.d_desc_fixed, st.d_cand, nullptr, st.d_fixed,
-        ctx->proj_fixed_dim, d_state);
+        ctx->proj_fixed_dim, d_state, n_fixed <= PJ_STAGE_MAX ? 1 : 0);
       PSLAM_LAUNCH_CHECK(ctx, "projective_search_kernel");
       filter_fused_kernel<<<1, FF_THREADS, 0, ctx->stream>>>(st.d_cand, n_moving, n_fixed, st.d_key1, st.d_key2, cfg->descriptor_distance,
                                                              cfg->maximum_distance_ratio_to_second_best, d_out, ca);
