@@ -186,12 +186,12 @@ def tracking_lines(ctx, capi, stream, dev):
     pr.set("canvas_rows", 376).set("canvas_cols", 1241)
     al.aligner_set_left_camera_in_right([-0.537166, 0, 0])
     times = []
-    for rep in range(7):
+    for rep in range(12):
         al.aligner_set_fixed(meas[1]["uvuv"], meas[1]["desc"])
         al.aligner_set_moving(xyz, meas[0]["desc"])
         al.aligner_set_moving_in_fixed(np.eye(3, 4, dtype=np.float32))
         t0 = time.perf_counter()
-        r = al.aligner_compute()
+        r = al.aligner_run()  # MultiAligner3DQR::compute(): uploads, searches, solver iterations, download -- host pointers in and out
         times.append(time.perf_counter() - t0)
     out["aligner"] = {"metric": "aligner_ms_per_frame", "value": 1e3 * float(np.median(times[2:])), "unit": "ms",
                       "iterations": int(r["iterations"]), "correspondences": int(r["num_correspondences"]),

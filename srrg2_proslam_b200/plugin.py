@@ -316,11 +316,23 @@ class Module:
         information = np.ascontiguousarray(information, np.float64).reshape(36)
         _chk(lib().psp_aligner_set_prior_information(self.h, _p(information)))
 
-    def aligner_compute(self):
+    def aligner_run(self):
+        """MultiAligner_::compute() alone (what a latency measurement should time); the per-iteration statistics and the
+        correspondences are read afterwards with aligner_results()"""
         pose = np.zeros(12, np.float64)
         it, nc, ni = C.c_int(), C.c_int(), C.c_int()
         chi = C.c_double()
         status = _chk(lib().psp_aligner_compute(self.h, _p(pose), C.byref(it), C.byref(nc), C.byref(ni), C.byref(chi)))
+        return {"status": status, "pose": pose, "iterations": it.value, "num_correspondences": nc.value,
+                "num_inliers": ni.value, "chi": chi.value}
+
+    def aligner_compute(self):
+        return self.aligner_results(self.aligner_run())
+
+    def aligner_results(self, run):
+        status, pose = run["status"], run["pose"]
+        it, nc, ni, chi = (C.c_int(run["iterations"]), C.c_int(run["num_correspondences"]), C.c_int(run["num_inliers"]),
+                           C.c_double(run["chi"]))
         rows = np.zeros((max(it.value, 1), 4), np.float64)
         _chk(lib().psp_aligner_iteration_stats(self.h, len(rows), _p(rows)))
         f = np.zeros(16384, np.int32)

@@ -35,7 +35,7 @@ def run():
     al.aligner_set_moving(xyz, meas[0]["desc"])
     al.aligner_set_moving_in_fixed(np.eye(3, 4, dtype=np.float32))
     t0 = time.perf_counter()
-    r = al.aligner_compute()
+    r = al.aligner_run()
     return time.perf_counter() - t0, r
 
 
