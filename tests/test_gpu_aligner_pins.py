@@ -59,6 +59,7 @@ def configure(P, name):
             finder.set("number_of_solver_iterations_per_projection", 5)
     sl.set("finder", finder).set("projector", projector)
     al.fixture_finder = finder
+    al.fixture_slice = sl
     sl.set("diagonal_info_matrix", sc["diag"])
     al.aligner_set_fixed(fixed, fdesc)
     al.aligner_set_moving(xyz, mdesc)
@@ -127,3 +128,45 @@ def test_device_resident_alignment_equals_call_by_call(P, name, monkeypatch):
         assert all(np.array_equal(x, y) for x, y in zip(ga["corr"], gb["corr"]))
         assert np.array_equal(ga["inlier_run_stats"], gb["inlier_run_stats"])
         assert ga["finder"] == gb["finder"]
+
+
+@pytest.mark.parametrize("case", ["repeat_with_wider_search", "too_few_correspondences", "single_iteration_budget"])
+def test_device_resident_alignment_hands_back(P, case, monkeypatch, capfd):
+    """the decisions pslam_projective_align leaves to the caller's loop: a low matching ratio while the search window can still
+    grow (the finder repeats the call, base_impl.cpp:228-262), fewer correspondences than the slice wants, and a budget that ends
+    inside the first phase -- same results as the call-by-call path in every case"""
+    name = "kitti_00to01_projective_circle"
+
+    def run(env):
+        monkeypatch.setenv("PSLAM_ALIGN_DEVICE", env)
+        al, gt = configure(P, name)
+        finder = al.fixture_finder
+        if case == "too_few_correspondences":
+            al.fixture_slice.set("min_num_correspondences", 1000)
+        if case == "single_iteration_budget":
+            al.set("max_iterations", 1)
+        out = []
+        for frame in range(3):
+            sc, d, fixed, fdesc, xyz, mdesc, gt_, init = A.scenario_inputs(name)
+            if case == "repeat_with_wider_search" and frame == 1:
+                finder.set("minimum_matching_ratio", 0.95)  # the shrunken window of frame 0 cannot satisfy this: internal repeat
+            al.aligner_set_fixed(fixed, fdesc)
+            al.aligner_set_moving(xyz, mdesc)
+            al.aligner_set_moving_in_fixed(init.astype(np.float32))
+            g = al.aligner_compute()
+            g["finder"] = finder.projective_state()
+            out.append(g)
+        return out
+
+    a, b = run("1"), run("0")
+    for ga, gb in zip(a, b):
+        assert ga["status"] == gb["status"] and ga["iterations"] == gb["iterations"]
+        assert np.array_equal(ga["pose"], gb["pose"])
+        assert np.array_equal(ga["stats"], gb["stats"])
+        assert all(np.array_equal(x, y) for x, y in zip(ga["corr"], gb["corr"]))
+        assert ga["finder"] == gb["finder"]
+    err = capfd.readouterr().err
+    if case == "repeat_with_wider_search":
+        assert err.count("triggering internal repeat with increased search radius") == 2  # once per path: it really happened
+    if case == "too_few_correspondences":
+        assert all(g["status"] != 1 for g in a)  # AlignerBase::NotEnoughCorrespondences
