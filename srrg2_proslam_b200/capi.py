@@ -55,6 +55,19 @@ class FusedGn(C.Structure):
                 ("spd", C.c_int)]
 
 
+ALIGN_MAX_PHASES = 64
+
+
+class Align(C.Structure):
+    """pslam_align"""
+    _fields_ = [("max_iterations", C.c_int), ("solver_iterations_per_projection", C.c_int),
+                ("minimum_number_of_iterations", C.c_int), ("maximum_estimate_change_norm_for_convergence", C.c_float),
+                ("minimum_matching_ratio", C.c_float), ("can_widen_search", C.c_int), ("min_num_correspondences", C.c_int),
+                ("current_iteration", C.c_int), ("has_converged", C.c_int), ("previous12", C.c_float * 12),
+                ("stop_reason", C.c_int), ("iterations_done", C.c_int), ("converged_with_good_ratio", C.c_int),
+                ("n_projected", C.c_int), ("n_phases", C.c_int), ("phase_log", C.c_int * (3 * ALIGN_MAX_PHASES))]
+
+
 class ClipCfg(C.Structure):
     """pslam_clip_cfg"""
     _fields_ = [("K", C.c_float * 9), ("canvas_rows", C.c_int), ("canvas_cols", C.c_int), ("range_min", C.c_float),
@@ -626,6 +639,54 @@ class Context:
         return fi[:n].copy(), mi[:n].copy(), d[:n].copy(), nproj.value, dict(
             pose=np.array(g.pose12[:], np.float64), poses=poses[:done], stats=stats[:done], status=status[:n].copy(), done=done,
             spd=bool(g.spd))
+
+    def projective_align(self, K, rows, cols, lcfg, diagonal_info, max_iterations, damping, estimate12, per_projection,
+                         minimum_iterations, max_change_norm=1e-5, minimum_matching_ratio=0.1, can_widen=0, min_corr=1,
+                         current_iteration=0, previous12=None, has_converged=0, shape="circle", radius=10,
+                         descriptor_distance=50.0, ratio=0.9, range_min=0.1, range_max=1000.0, prior=None):
+        """pslam_projective_align: the registration of one frame, device resident.  Returns (fixed, moving, distance, dict(pose,
+        poses, stats, status, done, spd, stop_reason, phases = [(first iteration, iterations, correspondences)], finder state))"""
+        cfg = ProjectiveCfg()
+        cfg.K[:] = [float(v) for v in np.asarray(K, np.float32).reshape(9)]
+        cfg.canvas_rows, cfg.canvas_cols = int(rows), int(cols)
+        cfg.range_min, cfg.range_max = float(range_min), float(range_max)
+        cfg.shape = SHAPES[shape]
+        cfg.search_radius_pixels = int(radius)
+        cfg.descriptor_distance = float(descriptor_distance)
+        cfg.maximum_distance_ratio_to_second_best = float(ratio)
+        cfg.maximum_descriptor_distance = float(descriptor_distance)
+        a = Align()
+        a.max_iterations, a.solver_iterations_per_projection = int(max_iterations), int(per_projection)
+        a.minimum_number_of_iterations = int(minimum_iterations)
+        a.maximum_estimate_change_norm_for_convergence = float(max_change_norm)
+        a.minimum_matching_ratio, a.can_widen_search = float(minimum_matching_ratio), int(can_widen)
+        a.min_num_correspondences, a.current_iteration, a.has_converged = int(min_corr), int(current_iteration), int(has_converged)
+        prev = np.eye(3, 4, dtype=np.float32).reshape(12) if previous12 is None else np.asarray(previous12, np.float32).reshape(12)
+        a.previous12[:] = [float(v) for v in prev]
+        cap = max(self._n_fixed, 1)
+        rows_n = max(int(max_iterations), 1)
+        fi, mi, d = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap, np.float32)
+        poses, stats = np.zeros((rows_n, 12), np.float64), np.zeros((rows_n, 4), np.float64)
+        status = np.zeros(cap, np.uint8)
+        g = FusedGn()
+        g.factor = C.cast(C.pointer(lcfg), C.c_void_p)
+        g.diagonal_info[:] = [float(v) for v in (list(diagonal_info) + [0.0, 0.0, 0.0])[:3]]
+        g.n_iterations, g.damping = rows_n, float(damping)
+        g.pose12[:] = [float(v) for v in np.asarray(estimate12, np.float64).reshape(12)]
+        pr = self._prior(prior)
+        g.prior = C.cast(C.pointer(pr), C.c_void_p) if pr is not None else None
+        g.poses12 = poses.ctypes.data_as(C.POINTER(C.c_double))
+        g.stats4 = stats.ctypes.data_as(C.POINTER(C.c_double))
+        g.factor_status = status.ctypes.data_as(C.POINTER(C.c_ubyte))
+        n = self._chk(lib().pslam_projective_align(self._h, self._n_fixed, self._n_moving, C.byref(cfg), C.byref(a), cap, _p(fi),
+                                                   _p(mi), _p(d), C.byref(g)))
+        done = a.iterations_done
+        phases = [tuple(a.phase_log[3 * p:3 * p + 3]) for p in range(min(a.n_phases, ALIGN_MAX_PHASES))]
+        return fi[:n].copy(), mi[:n].copy(), d[:n].copy(), dict(
+            pose=np.array(g.pose12[:], np.float64), poses=poses[:done], stats=stats[:done], status=status[:n].copy(), done=done,
+            spd=bool(g.spd), stop_reason=a.stop_reason, phases=phases, n_projected=a.n_projected,
+            current_iteration=a.current_iteration, has_converged=bool(a.has_converged),
+            converged_with_good_ratio=bool(a.converged_with_good_ratio), previous12=np.array(a.previous12[:], np.float32))
 
     # ---- stages 3 + 4 -------------------------------------------------------------------------
     @staticmethod

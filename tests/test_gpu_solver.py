@@ -219,3 +219,69 @@ def test_projective_match_gn_equals_match_then_iterate(oracle, with_prior, weigh
         assert np.array_equal(g["status"][order], status)
     finally:
         c.close()
+
+
+def test_projective_align_equals_host_driven_phases(oracle):
+    """pslam_projective_align (finder state machine on the device) == the same phases driven from the host with
+    pslam_projective_match_gn: re-project when iteration % N == 0 or == 1, converge when the fp32 norm of
+    t2tnq(X^-1 X_previous) drops below the threshold after the minimum number of calls, then spend the rest of the budget"""
+    from srrg2_proslam_b200 import capi
+    from test_oracle_known_answers import K_KITTI
+    c = capi.Context(max_images=2, max_rows=376, max_cols=1241, max_features=2048, max_raw_per_bin=8192)
+    try:
+        e = O.extract_cfg(threshold=15, target=500)
+        m = [O.stereo_adaptor(O.load_gray(f"kitti_city_image_left_{i}.png"), O.load_gray(f"kitti_city_image_right_{i}.png"), e,
+                              "epipolar", 50, 0.8) for i in (0, 1)]
+        xyz, _ = O.triangulate(m[0]["uvuv"], K_KITTI, np.float32(718.856) * np.float32(0.537166), 0.0)
+        guess = np.eye(3, 4).reshape(12)
+        base = (K_KITTI.reshape(3, 3) @ np.array([-0.537166, 0, 0], np.float32)).astype(np.float64)
+        lcfg = c.linearize_cfg("stereo", K_KITTI.astype(np.float64), 1241, 376, base, 0.0, "saturated", 1000.0)
+        diag = np.array([1, 2, 1], np.float32)
+        c.projective_set_fixed(m[1]["uvuv"], m[1]["desc"])
+        c.projective_set_moving(xyz, m[0]["desc"])
+        N, MIN_IT, BUDGET, THR = 5, 10, 60, 1e-5
+        f, mm, d, a = c.projective_align(K_KITTI, 376, 1241, lcfg, diag, BUDGET, 1.0, guess, N, MIN_IT, THR, 0.1, 0, 10,
+                                         shape="circle", radius=50, descriptor_distance=75.0, ratio=0.8)
+        assert a["stop_reason"] == 1 and a["done"] == BUDGET and a["spd"] and len(a["phases"]) >= 4
+        # host-driven replay
+        est, prev, ci, it, conv = guess.copy(), np.eye(3, 4, dtype=np.float32), 0, 0, False
+        poses, stats, phases = [], [], []
+        while it < BUDGET:
+            X = est.astype(np.float32).reshape(3, 4)
+            E = O.pose_mul(O.pose_inverse(X.reshape(12).astype(np.float64)), prev.reshape(12).astype(np.float64))
+            norm = float(np.linalg.norm(O.t2tnq(E)))
+            conv = norm < THR and ci > MIN_IT
+            quiet = 0
+            k = ci + 1
+            while not (k % N == 0 or k == 1):
+                quiet, k = quiet + 1, k + 1
+            n_fused = BUDGET - it if conv else min(BUDGET - it, quiet + 1)
+            f1, m1, d1, _, g = c.projective_match_gn(X.reshape(12), K_KITTI, 376, 1241, lcfg, diag, n_fused, 1.0, est, "circle", 50,
+                                                     75.0, 0.8)
+            assert g["done"] == n_fused
+            phases.append((it, n_fused, len(f1)))
+            poses.append(g["poses"])
+            stats.append(g["stats"])
+            prev = X  # the search call keeps the pose it was given; the n_fused - 1 calls that follow (none once converged) do too
+            if not conv and n_fused >= 2:
+                prev = g["poses"][n_fused - 2].astype(np.float32).reshape(3, 4)
+            ci += 1 if conv else n_fused
+            est, it = g["pose"], it + n_fused
+        assert a["phases"] == phases
+        assert np.array_equal(a["poses"], np.concatenate(poses)) and np.array_equal(a["stats"], np.concatenate(stats))
+        assert np.array_equal(f, f1) and np.array_equal(mm, m1) and np.array_equal(d, d1)
+        assert a["current_iteration"] == ci and a["has_converged"] == conv
+        # argument validation
+        with pytest.raises(Exception):
+            c.projective_align(K_KITTI, 376, 1241, lcfg, diag, BUDGET, 1.0, guess, N, MIN_IT, has_converged=1)
+        with pytest.raises(Exception):
+            c.projective_align(K_KITTI, 376, 1241, lcfg, diag, 0, 1.0, guess, N, MIN_IT)
+        # decisions left to the caller: nothing is applied, the state comes back as it went in
+        _, _, _, b = c.projective_align(K_KITTI, 376, 1241, lcfg, diag, BUDGET, 1.0, guess, N, MIN_IT, THR, 0.99, 1, 10, shape="circle",
+                                        radius=50, descriptor_distance=75.0, ratio=0.8)
+        assert b["stop_reason"] == 2 and b["done"] == 0 and b["phases"] == [] and b["current_iteration"] == 0
+        _, _, _, b = c.projective_align(K_KITTI, 376, 1241, lcfg, diag, BUDGET, 1.0, guess, N, MIN_IT, THR, 0.1, 0, 5000, shape="circle",
+                                        radius=50, descriptor_distance=75.0, ratio=0.8)
+        assert b["stop_reason"] == 3 and b["done"] == 0 and np.array_equal(b["pose"], guess)
+    finally:
+        c.close()
