@@ -524,6 +524,7 @@ bool CorrespondenceFinderProjectiveCUDA::alignFused(FusedSolveRequest& r, int mi
       std::cerr << "CorrespondenceFinderProjective::compute|low matching ratio: " << matching_ratio << " (" << al.phase_log[3 * p + 2]
                 << "/" << _fixed->size() << ") target: " << param_minimum_matching_ratio.value() << std::endl;
   }
+  if (al.n_projected == 0) std::cerr << "CorrespondenceFinderProjective::compute|WARNING: all projections failed" << std::endl;
   if (al.converged_with_good_ratio) _adaptAfterConvergence();
   if (al.stop_reason != 2 && al.stop_reason != 3) fill(*_correspondences, n, f, m, d);
   _postCompute();

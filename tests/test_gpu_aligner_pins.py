@@ -60,6 +60,7 @@ def configure(P, name):
     sl.set("finder", finder).set("projector", projector)
     al.fixture_finder = finder
     al.fixture_slice = sl
+    al.fixture_manager = m
     sl.set("diagonal_info_matrix", sc["diag"])
     al.aligner_set_fixed(fixed, fdesc)
     al.aligner_set_moving(xyz, mdesc)
@@ -170,3 +171,40 @@ def test_device_resident_alignment_hands_back(P, case, monkeypatch, capfd):
         assert err.count("triggering internal repeat with increased search radius") == 2  # once per path: it really happened
     if case == "too_few_correspondences":
         assert all(g["status"] != 1 for g in a)  # AlignerBase::NotEnoughCorrespondences
+
+
+@pytest.mark.parametrize("cls", ["CorrespondenceFinderProjectiveSquare4D3D", "CorrespondenceFinderProjectiveRhombus4D3D",
+                                 "CorrespondenceFinderProjectiveKDTree4D3D"])
+def test_device_resident_alignment_other_windows(P, cls, monkeypatch):
+    """the device-resident registration with the other window shapes of the projective finder family (square, rhombus, exact
+    radius query of the KD-tree variant) in place of the circle: identical to the call-by-call path"""
+    name = "kitti_00to01_projective_circle"
+
+    def run(env):
+        monkeypatch.setenv("PSLAM_ALIGN_DEVICE", env)
+        al, gt = configure(P, name)
+        m = al.fixture_manager
+        finder = m.create(cls)
+        circle = al.fixture_finder
+        finder.set("projector", circle.link("projector"))
+        for k in ("minimum_descriptor_distance", "maximum_descriptor_distance", "maximum_distance_ratio_to_second_best",
+                  "minimum_search_radius_pixels", "maximum_search_radius_pixels", "number_of_solver_iterations_per_projection"):
+            finder.set(k, circle.get(k))
+        al.fixture_slice.set("finder", finder)
+        out = []
+        for frame in range(2):
+            sc, d, fixed, fdesc, xyz, mdesc, gt_, init = A.scenario_inputs(name)
+            al.aligner_set_fixed(fixed, fdesc)
+            al.aligner_set_moving(xyz, mdesc)
+            al.aligner_set_moving_in_fixed(init.astype(np.float32))
+            g = al.aligner_compute()
+            g["finder"] = finder.projective_state()
+            out.append(g)
+        return out
+
+    a, b = run("1"), run("0")
+    for ga, gb in zip(a, b):
+        assert ga["status"] == gb["status"] == 1 and ga["iterations"] == gb["iterations"]
+        assert np.array_equal(ga["pose"], gb["pose"]) and np.array_equal(ga["stats"], gb["stats"])
+        assert all(np.array_equal(x, y) for x, y in zip(ga["corr"], gb["corr"])) and len(ga["corr"][0]) > 20
+        assert ga["finder"] == gb["finder"]
