@@ -734,7 +734,8 @@ int pslam_k_projective_align(pslam_ctx* ctx, int n_fixed, int n_moving, const ps
     if (it >= a.max_iterations) break;
   }
   for (int queued = 0; queued < PSLAM_ALIGN_MAX_PHASES;) {
-    const int batch = queued == 0 ? first_batch : 2;
+    int batch = queued == 0 ? first_batch : 2;
+    if (batch > PSLAM_ALIGN_MAX_PHASES - queued) batch = PSLAM_ALIGN_MAX_PHASES - queued;  // the phase log has that many rows
     queued += batch;
     for (int p = 0; p < batch; ++p) {
       projective_search_kernel<<<(n_moving + PJ_WARPS - 1) / PJ_WARPS, PJ_WARPS * 32, smem, ctx->stream>>>(
