@@ -131,7 +131,8 @@ def test_device_resident_alignment_equals_call_by_call(P, name, monkeypatch):
         assert ga["finder"] == gb["finder"]
 
 
-@pytest.mark.parametrize("case", ["repeat_with_wider_search", "too_few_correspondences", "single_iteration_budget"])
+@pytest.mark.parametrize("case", ["repeat_with_wider_search", "too_few_correspondences", "single_iteration_budget",
+                                  "more_phases_than_the_log"])
 def test_device_resident_alignment_hands_back(P, case, monkeypatch, capfd):
     """the decisions pslam_projective_align leaves to the caller's loop: a low matching ratio while the search window can still
     grow (the finder repeats the call, base_impl.cpp:228-262), fewer correspondences than the slice wants, and a budget that ends
@@ -146,6 +147,8 @@ def test_device_resident_alignment_hands_back(P, case, monkeypatch, capfd):
             al.fixture_slice.set("min_num_correspondences", 1000)
         if case == "single_iteration_budget":
             al.set("max_iterations", 1)
+        if case == "more_phases_than_the_log":  # a search before every solver iteration, never converged: 100 phases > 64
+            finder.set("number_of_solver_iterations_per_projection", 1).set("minimum_number_of_iterations", 1000)
         out = []
         for frame in range(3):
             sc, d, fixed, fdesc, xyz, mdesc, gt_, init = A.scenario_inputs(name)
@@ -171,6 +174,8 @@ def test_device_resident_alignment_hands_back(P, case, monkeypatch, capfd):
         assert err.count("triggering internal repeat with increased search radius") == 2  # once per path: it really happened
     if case == "too_few_correspondences":
         assert all(g["status"] != 1 for g in a)  # AlignerBase::NotEnoughCorrespondences
+    if case == "more_phases_than_the_log":
+        assert all(g["iterations"] == 100 and g["finder"]["searches"] % 100 == 0 for g in a)
 
 
 @pytest.mark.parametrize("cls", ["CorrespondenceFinderProjectiveSquare4D3D", "CorrespondenceFinderProjectiveRhombus4D3D",
