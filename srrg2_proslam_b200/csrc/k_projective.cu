@@ -305,6 +305,12 @@ __device__ void align_control(PslamAlignState* s, const PslamAlignCfg& a, int n,
 
 // correspondences of the filter's result in ascending fixed index + their information diagonals, for the fused solver:
 // acc_moving[f] >= 0  ->  (f, acc_moving[f]); info[3 f + k] = diag[k] * scale[moving]  (setupFactor, fp32 like the host)
+// start of a device-resident alignment: handed to the first phase's filter kernel by value (one upload less per frame)
+struct AlignInit {
+  double estimate[12];
+  float prev[12];
+  int current_iteration, valid;
+};
 struct CompactArgs {
   int enabled;
   const float* scale;
@@ -314,6 +320,7 @@ struct CompactArgs {
   int* n_corr;
   PslamAlignState* state;
   PslamAlignCfg acfg;
+  AlignInit init;
 };
 __device__ __forceinline__ void corr_compact(const int* __restrict__ acc_moving, int n_fixed, const float* __restrict__ scale, float d0,
                                              float d1, float d2, int* __restrict__ cf, int* __restrict__ cm, float* __restrict__ info,
@@ -353,6 +360,18 @@ filter_fused_kernel(const int* __restrict__ cand, int n_moving, int n_fixed, uns
                     unsigned long long* __restrict__ key2, float max_dist, float max_ratio, int* __restrict__ out, CompactArgs ca) {
   __shared__ int s_proj;
   const int tid = threadIdx.x;
+  if (ca.state && ca.init.valid) {  // first phase: the state starts here (the search of this phase took its pose by value too)
+    if (tid == 0) {
+      PslamAlignState* s = ca.state;
+      for (int i = 0; i < 12; ++i) {
+        s->estimate[i] = ca.init.estimate[i];
+        s->prev[i] = ca.init.prev[i];
+      }
+      s->current_iteration = ca.init.current_iteration;
+      s->has_converged = s->converged_ratio_ok = s->it = s->stop = s->phases = s->n_fused = s->n_corr = s->n_projected = s->pad = 0;
+    }
+    __syncthreads();
+  }
   if (ca.state && ca.state->stop) return;
   if (tid == 0) s_proj = 0;
   for (int f = tid; f < n_fixed; f += FF_THREADS) {
@@ -434,6 +453,19 @@ struct ProjState {
 
 static std::atomic<unsigned long long> g_proj_epoch{0};  // process-wide: epochs of different contexts never coincide
 
+// one packed upload: `a` then `b` at the next 256-byte boundary, through a buffer the thread keeps (a pageable source is staged by
+// the driver before cudaMemcpyAsync returns)
+static int proj_upload2(pslam_ctx* ctx, void* dst, const void* a, size_t a_bytes, const void* b, size_t b_bytes) {
+  static thread_local std::vector<unsigned char> pack;
+  const size_t off = al256(a_bytes), total = off + b_bytes;
+  if (pack.size() < total) pack.resize(total);
+  memcpy(pack.data(), a, a_bytes);
+  memcpy(pack.data() + off, b, b_bytes);
+  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(dst, pack.data(), total, cudaMemcpyHostToDevice, ctx->stream));
+  return PSLAM_OK;
+}
+
+// n_fixed / n_moving < 0: "as uploaded" (the set_* calls pass their own sizes after recording them in the context)
 static int proj_layout(pslam_ctx* ctx, ProjState& st, int n_fixed, int dim, int n_moving) {
   const int M = PSLAM_MAX_FEATURES_HARD * 2;  // generous fixed-size regions so that set_* calls are independent
   if (n_fixed > M || n_moving > 65536)
@@ -442,17 +474,21 @@ static int proj_layout(pslam_ctx* ctx, ProjState& st, int n_fixed, int dim, int 
     ctx->proj_bytes = PSLAM_SOLVER_SCRATCH_OFFSET;
     PSLAM_CUDA_TRY(ctx, cudaMalloc(&ctx->d_proj, ctx->proj_bytes));
   }
+  // a cloud's descriptors sit directly behind its coordinates (at the 256-byte boundary after them) inside the cloud's
+  // region: coordinates + descriptors arrive in ONE copy (an upload costs the host ~4.5 us of API time whatever its size)
   uint8_t* p = ctx->d_proj;
-  st.d_fixed = (float*) p; p += al256(sizeof(float) * 4 * (size_t) M);
-  st.d_desc_fixed = (uint32_t*) p; p += al256(32 * (size_t) M);
+  st.d_fixed = (float*) p;
+  st.d_desc_fixed = (uint32_t*) (p + al256(sizeof(float) * (size_t) ctx->proj_fixed_dim * (size_t) ctx->proj_n_fixed));
+  p += al256(sizeof(float) * 4 * (size_t) M) + al256(32 * (size_t) M);
   st.d_lattice = (unsigned long long*) p; p += al256(8 * (size_t) M);
   st.d_key1 = (unsigned long long*) p; p += al256(8 * (size_t) M);
   st.d_key2 = (unsigned long long*) p; p += al256(8 * (size_t) M);
   st.d_acc_m = (int*) p; p += al256(4 * (size_t) M);
   st.d_acc_d = (float*) p; p += al256(4 * (size_t) M);
   st.d_nproj = (int*) p; p += 256;
-  st.d_moving = (float*) p; p += al256(sizeof(float) * 3 * (size_t) 65536);
-  st.d_desc_moving = (uint32_t*) p; p += al256(32 * (size_t) 65536);
+  st.d_moving = (float*) p;
+  st.d_desc_moving = (uint32_t*) (p + al256(sizeof(float) * 3 * (size_t) ctx->proj_n_moving));
+  p += al256(sizeof(float) * 3 * (size_t) 65536) + al256(32 * (size_t) 65536);
   st.d_cand = (int*) p; p += al256(16 * (size_t) 65536);
   st.d_mscale = (float*) p; p += al256(4 * (size_t) 65536);
   st.d_gn_cf = (int*) p; p += al256(4 * (size_t) M);
@@ -469,16 +505,17 @@ static int proj_layout(pslam_ctx* ctx, ProjState& st, int n_fixed, int dim, int 
 
 int pslam_k_projective_set_fixed(pslam_ctx* ctx, int n_fixed, const float* h_coords, int dim,
                                  const uint8_t* h_desc) {
+  if (n_fixed >= 32767)
+    return pslam_set_error(ctx, PSLAM_E_INVALID, "projective: int16 lattice needs < 32767 fixed points", cudaSuccess);
+  if (n_fixed > PSLAM_MAX_FEATURES_HARD * 2) return pslam_set_error(ctx, PSLAM_E_CAPACITY, "projective: too many points", cudaSuccess);
+  ctx->proj_fixed_epoch = ++g_proj_epoch;
+  ctx->proj_fixed_dim = dim;
+  ctx->proj_n_fixed = n_fixed;
   ProjState st;
   int rc = proj_layout(ctx, st, n_fixed, dim, 0);
   if (rc) return rc;
-  ctx->proj_fixed_epoch = ++g_proj_epoch;
-  ctx->proj_fixed_dim = dim;
   if (n_fixed == 0) return PSLAM_OK;
-  if (n_fixed >= 32767)
-    return pslam_set_error(ctx, PSLAM_E_INVALID, "projective: int16 lattice needs < 32767 fixed points", cudaSuccess);
-  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(st.d_fixed, h_coords, sizeof(float) * dim * (size_t) n_fixed, cudaMemcpyHostToDevice, ctx->stream));
-  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(st.d_desc_fixed, h_desc, 32 * (size_t) n_fixed, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = proj_upload2(ctx, st.d_fixed, h_coords, sizeof(float) * dim * (size_t) n_fixed, h_desc, 32 * (size_t) n_fixed))) return rc;
   // 10 B per element in shared memory (key + stopper position); clouds above the cap sort in global memory (key1 / key2 of
   // the finder cache are free until the next match)
   const int smem_cap = n_fixed <= 4096 ? 4096 : (n_fixed <= 16384 ? 16384 : 0);
@@ -492,17 +529,19 @@ int pslam_k_projective_set_fixed(pslam_ctx* ctx, int n_fixed, const float* h_coo
 }
 
 int pslam_k_projective_set_moving(pslam_ctx* ctx, int n_moving, const float* h_xyz, const uint8_t* h_desc) {
+  if (n_moving > 65536) return pslam_set_error(ctx, PSLAM_E_CAPACITY, "projective: too many points", cudaSuccess);
+  ctx->proj_moving_epoch = ++g_proj_epoch;
+  ctx->proj_n_moving = n_moving;
   ProjState st;
   int rc = proj_layout(ctx, st, 0, 2, n_moving);
   if (rc) return rc;
-  ctx->proj_moving_epoch = ++g_proj_epoch;
   if (n_moving == 0) return PSLAM_OK;
-  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(st.d_moving, h_xyz, sizeof(float) * 3 * (size_t) n_moving, cudaMemcpyHostToDevice, ctx->stream));
-  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(st.d_desc_moving, h_desc, 32 * (size_t) n_moving, cudaMemcpyHostToDevice, ctx->stream));
-  return PSLAM_OK;
+  return proj_upload2(ctx, st.d_moving, h_xyz, sizeof(float) * 3 * (size_t) n_moving, h_desc, 32 * (size_t) n_moving);
 }
 
 int pslam_k_projective_set_moving_weights(pslam_ctx* ctx, int n_moving, const float* h_scale) {
+  if (n_moving != ctx->proj_n_moving)
+    return pslam_set_error(ctx, PSLAM_E_INVALID, "projective: one information scale per point of the uploaded moving cloud", cudaSuccess);
   ProjState st;
   int rc = proj_layout(ctx, st, 0, 2, n_moving);
   if (rc) return rc;
@@ -602,6 +641,8 @@ static int proj_params(pslam_ctx* ctx, const pslam_projective_cfg* cfg, const fl
 int pslam_k_projective_match(pslam_ctx* ctx, int n_fixed, int n_moving, const float* pose12,
                              const pslam_projective_cfg* cfg, int capacity, int* h_fixed, int* h_moving,
                              float* h_dist, int* n_projected, pslam_fused_gn* gn) {
+  if (n_fixed != ctx->proj_n_fixed || n_moving != ctx->proj_n_moving)
+    return pslam_set_error(ctx, PSLAM_E_INVALID, "projective: cloud sizes differ from the uploaded clouds", cudaSuccess);
   ProjState st;
   int rc = proj_layout(ctx, st, n_fixed, 2, n_moving);
   if (rc) return rc;
@@ -667,6 +708,8 @@ int pslam_k_projective_align(pslam_ctx* ctx, int n_fixed, int n_moving, const ps
   if (!al || !gn || !gn->factor) return pslam_set_error(ctx, PSLAM_E_INVALID, "align: configuration missing", cudaSuccess);
   if (al->max_iterations <= 0 || gn->n_iterations < al->max_iterations || al->has_converged || al->solver_iterations_per_projection <= 0)
     return pslam_set_error(ctx, PSLAM_E_INVALID, "align: bad iteration budget or finder state", cudaSuccess);
+  if (n_fixed != ctx->proj_n_fixed || n_moving != ctx->proj_n_moving)
+    return pslam_set_error(ctx, PSLAM_E_INVALID, "projective: cloud sizes differ from the uploaded clouds", cudaSuccess);
   ProjState st;
   int rc = proj_layout(ctx, st, n_fixed, 2, n_moving);
   if (rc) return rc;
@@ -705,13 +748,18 @@ int pslam_k_projective_align(pslam_ctx* ctx, int n_fixed, int n_moving, const ps
     h_all = pageable.data();
   }
   PslamAlignState* h_state = reinterpret_cast<PslamAlignState*>(h_all);
-  memset(h_state, 0, sizeof(*h_state));
+  AlignInit init;
   for (int i = 0; i < 12; ++i) {
-    h_state->estimate[i] = gn->pose12[i];
-    h_state->prev[i] = al->previous12[i];
+    init.estimate[i] = gn->pose12[i];
+    init.prev[i] = al->previous12[i];
   }
-  h_state->current_iteration = al->current_iteration;
-  PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(d_state, h_state, sizeof(*h_state), cudaMemcpyHostToDevice, ctx->stream));
+  init.current_iteration = al->current_iteration;
+  init.valid = 1;
+  ProjParams pp_first = pp;  // the first search takes the start estimate by value (fp32, as finder.setLocalMapInSensor(X) rounds it)
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) pp_first.R[3 * i + j] = (float) gn->pose12[4 * i + j];
+    pp_first.t[i] = (float) gn->pose12[4 * i + 3];
+  }
   PslamAlignCfg a;
   a.max_iterations = al->max_iterations;
   a.per_projection = al->solver_iterations_per_projection;
@@ -720,8 +768,8 @@ int pslam_k_projective_align(pslam_ctx* ctx, int n_fixed, int n_moving, const ps
   a.min_corr = al->min_num_correspondences;
   a.max_change_norm = al->maximum_estimate_change_norm_for_convergence;
   a.min_matching_ratio = al->minimum_matching_ratio;
-  const CompactArgs ca{1, ctx->proj_weights_epoch == ctx->proj_moving_epoch ? st.d_mscale : nullptr, gn->diagonal_info[0],
-                       gn->diagonal_info[1], gn->diagonal_info[2], st.d_gn_cf, st.d_gn_cm, st.d_gn_info, st.d_gn_ncorr, d_state, a};
+  CompactArgs ca{1, ctx->proj_weights_epoch == ctx->proj_moving_epoch ? st.d_mscale : nullptr, gn->diagonal_info[0],
+                 gn->diagonal_info[1], gn->diagonal_info[2], st.d_gn_cf, st.d_gn_cm, st.d_gn_info, st.d_gn_ncorr, d_state, a, init};
   int first_batch = 0;
   for (int ci = al->current_iteration, it = 0; first_batch < 16;) {
     ++first_batch;
@@ -738,9 +786,10 @@ int pslam_k_projective_align(pslam_ctx* ctx, int n_fixed, int n_moving, const ps
     if (batch > PSLAM_ALIGN_MAX_PHASES - queued) batch = PSLAM_ALIGN_MAX_PHASES - queued;  // the phase log has that many rows
     queued += batch;
     for (int p = 0; p < batch; ++p) {
+      const bool first = ca.init.valid != 0;
       projective_search_kernel<<<(n_moving + PJ_WARPS - 1) / PJ_WARPS, PJ_WARPS * 32, smem, ctx->stream>>>(
-        pp, st.d_moving, n_moving, st.d_desc_moving, st.d_lattice, n_fixed, st.d_desc_fixed, st.d_cand, nullptr, st.d_fixed,
-        ctx->proj_fixed_dim, d_state, n_fixed <= PJ_STAGE_MAX ? 1 : 0);
+        first ? pp_first : pp, st.d_moving, n_moving, st.d_desc_moving, st.d_lattice, n_fixed, st.d_desc_fixed, st.d_cand, nullptr,
+        st.d_fixed, ctx->proj_fixed_dim, first ? nullptr : d_state, n_fixed <= PJ_STAGE_MAX ? 1 : 0);
       PSLAM_LAUNCH_CHECK(ctx, "projective_search_kernel");
       filter_fused_kernel<<<1, FF_THREADS, 0, ctx->stream>>>(st.d_cand, n_moving, n_fixed, st.d_key1, st.d_key2, cfg->descriptor_distance,
                                                              cfg->maximum_distance_ratio_to_second_best, d_out, ca);
@@ -749,6 +798,7 @@ int pslam_k_projective_align(pslam_ctx* ctx, int n_fixed, int n_moving, const ps
                                        st.d_gn_ncorr, st.d_gn_cf, st.d_gn_cm, st.d_gn_info, gn->prior, d_gn_out, d_done, d_status,
                                        d_state, al->max_iterations)))
         return rc;
+      ca.init.valid = 0;
     }
     PSLAM_CUDA_TRY(ctx, cudaMemcpyAsync(h_all, d_base, 4 * all_words, cudaMemcpyDeviceToHost, ctx->stream));
     PSLAM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));

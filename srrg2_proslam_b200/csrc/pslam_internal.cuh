@@ -102,6 +102,7 @@ struct pslam_ctx {
   size_t proj_bytes;
   unsigned long long proj_fixed_epoch, proj_moving_epoch;
   int proj_fixed_dim;  // floats per fixed point of the cached cloud
+  int proj_n_fixed, proj_n_moving;  // sizes of the cached clouds: a cloud's descriptors sit directly behind its coordinates (ONE upload)
   unsigned long long proj_weights_epoch;  // == proj_moving_epoch while the information-scale table belongs to the cached moving cloud
   // peer-to-peer result tables of the sharded Hamming sweep (k_sharded.cu): every rank owns one table in its HBM, exported
   // through CUDA IPC; the ranks' merge kernels store their rows straight into every peer's table over NVLink
