@@ -647,6 +647,7 @@ gn_iterate_kernel(LinParams c0, PriorParams prior, double damping, int n_iters, 
                   const int* __restrict__ corr_moving, const T* __restrict__ info_diag, double* __restrict__ out,
                   int* __restrict__ iters_done, uint8_t* __restrict__ status, const int* __restrict__ n_corr_dev,
                   PslamAlignState* __restrict__ state, int max_iterations) {
+  pslam_pdl_enter();
   if (n_corr_dev) n_corr = *n_corr_dev;  // correspondences produced on the device by the launch before (pslam_projective_match_gn)
   if (state) {  // one phase of pslam_projective_align: budget, start estimate and output rows are the state's (uniform reads;
                 // thread 0 advances the state after the last barrier of the kernel)
@@ -982,9 +983,9 @@ int pslam_k_gn_iterate_dev(pslam_ctx* ctx, const pslam_linearize_cfg* cfg, int n
                            const pslam_pose_prior* prior, double* d_out, int* d_done, uint8_t* d_status,
                            PslamAlignState* d_state, int max_iterations) {
   const LinParams c = make_params(cfg, pose12);
-  gn_iterate_kernel<float><<<1, LZ_THREADS, 0, ctx->stream>>>(c, make_prior(prior), damping, n_iters, d_moving_xyz, d_fixed_meas,
-                                                             fixed_dim, 0, d_corr_fixed, d_corr_moving, d_info_diag, d_out, d_done,
-                                                             d_status, d_n_corr, d_state, max_iterations);
+  pslam_launch_pdl(gn_iterate_kernel<float>, dim3(1), dim3(LZ_THREADS), 0, ctx->stream, c, make_prior(prior), damping, n_iters,
+                   d_moving_xyz, d_fixed_meas, fixed_dim, 0, d_corr_fixed, d_corr_moving, d_info_diag, d_out, d_done, d_status, d_n_corr,
+                   d_state, max_iterations);
   PSLAM_LAUNCH_CHECK(ctx, "gn_iterate_kernel");
   return PSLAM_OK;
 }

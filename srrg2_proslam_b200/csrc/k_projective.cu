@@ -91,6 +91,7 @@ projective_search_kernel(ProjParams pp, const float* __restrict__ moving_xyz, in
                          const PslamAlignState* __restrict__ state, int stage_lattice) {
   extern __shared__ __align__(8) int s_width[];  // circle: width per |height| (0..radius); then the staged lattice
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  pslam_pdl_enter();
   if (state) {  // a phase of pslam_projective_align: the pose is the solver's current estimate, rounded to fp32 as the caller's
                 // finder.setLocalMapInSensor(X) does (uniform reads; the state is only written by later launches)
     if (state->stop) return;
@@ -360,6 +361,7 @@ filter_fused_kernel(const int* __restrict__ cand, int n_moving, int n_fixed, uns
                     unsigned long long* __restrict__ key2, float max_dist, float max_ratio, int* __restrict__ out, CompactArgs ca) {
   __shared__ int s_proj;
   const int tid = threadIdx.x;
+  pslam_pdl_enter();
   if (ca.state && ca.init.valid) {  // first phase: the state starts here (the search of this phase took its pose by value too)
     if (tid == 0) {
       PslamAlignState* s = ca.state;
@@ -651,9 +653,9 @@ int pslam_k_projective_match(pslam_ctx* ctx, int n_fixed, int n_moving, const fl
   ProjParams pp;
   if ((rc = proj_params(ctx, cfg, pose12, pp, n_fixed))) return rc;
   const size_t smem = search_smem(pp.radius, n_fixed);
-  projective_search_kernel<<<(n_moving + PJ_WARPS - 1) / PJ_WARPS, PJ_WARPS * 32, smem, ctx->stream>>>(
-    pp, st.d_moving, n_moving, st.d_desc_moving, st.d_lattice, n_fixed, st.d_desc_fixed, st.d_cand, nullptr, st.d_fixed,
-    ctx->proj_fixed_dim, nullptr, n_fixed <= PJ_STAGE_MAX ? 1 : 0);
+  pslam_launch_pdl(projective_search_kernel, dim3((n_moving + PJ_WARPS - 1) / PJ_WARPS), dim3(PJ_WARPS * 32), smem, ctx->stream, pp,
+                   st.d_moving, n_moving, st.d_desc_moving, st.d_lattice, n_fixed, st.d_desc_fixed, st.d_cand, nullptr, st.d_fixed,
+                   ctx->proj_fixed_dim, nullptr, n_fixed <= PJ_STAGE_MAX ? 1 : 0);
   PSLAM_LAUNCH_CHECK(ctx, "projective_search_kernel");
   // one filter launch, one download (see filter_fused_kernel); the result block is transient: generic scratch
   const size_t n_words = 1 + 2 * (size_t) n_fixed + 4 * (size_t) n_moving;
@@ -675,8 +677,8 @@ int pslam_k_projective_match(pslam_ctx* ctx, int n_fixed, int n_moving, const fl
                      gn->diagonal_info[1], gn->diagonal_info[2], st.d_gn_cf, st.d_gn_cm, st.d_gn_info, st.d_gn_ncorr, nullptr,
                      PslamAlignCfg{}};
   }
-  filter_fused_kernel<<<1, FF_THREADS, 0, ctx->stream>>>(st.d_cand, n_moving, n_fixed, st.d_key1, st.d_key2, cfg->descriptor_distance,
-                                                         cfg->maximum_distance_ratio_to_second_best, d_out, ca);
+  pslam_launch_pdl(filter_fused_kernel, dim3(1), dim3(FF_THREADS), 0, ctx->stream, st.d_cand, n_moving, n_fixed, st.d_key1, st.d_key2,
+                   cfg->descriptor_distance, cfg->maximum_distance_ratio_to_second_best, d_out, ca);
   PSLAM_LAUNCH_CHECK(ctx, "filter_fused_kernel");
   if (gn) {
     int* d_done = d_out + gn_off;
@@ -787,12 +789,12 @@ int pslam_k_projective_align(pslam_ctx* ctx, int n_fixed, int n_moving, const ps
     queued += batch;
     for (int p = 0; p < batch; ++p) {
       const bool first = ca.init.valid != 0;
-      projective_search_kernel<<<(n_moving + PJ_WARPS - 1) / PJ_WARPS, PJ_WARPS * 32, smem, ctx->stream>>>(
-        first ? pp_first : pp, st.d_moving, n_moving, st.d_desc_moving, st.d_lattice, n_fixed, st.d_desc_fixed, st.d_cand, nullptr,
-        st.d_fixed, ctx->proj_fixed_dim, first ? nullptr : d_state, n_fixed <= PJ_STAGE_MAX ? 1 : 0);
+      pslam_launch_pdl(projective_search_kernel, dim3((n_moving + PJ_WARPS - 1) / PJ_WARPS), dim3(PJ_WARPS * 32), smem, ctx->stream,
+                       first ? pp_first : pp, st.d_moving, n_moving, st.d_desc_moving, st.d_lattice, n_fixed, st.d_desc_fixed, st.d_cand,
+                       nullptr, st.d_fixed, ctx->proj_fixed_dim, first ? nullptr : d_state, n_fixed <= PJ_STAGE_MAX ? 1 : 0);
       PSLAM_LAUNCH_CHECK(ctx, "projective_search_kernel");
-      filter_fused_kernel<<<1, FF_THREADS, 0, ctx->stream>>>(st.d_cand, n_moving, n_fixed, st.d_key1, st.d_key2, cfg->descriptor_distance,
-                                                             cfg->maximum_distance_ratio_to_second_best, d_out, ca);
+      pslam_launch_pdl(filter_fused_kernel, dim3(1), dim3(FF_THREADS), 0, ctx->stream, st.d_cand, n_moving, n_fixed, st.d_key1, st.d_key2,
+                       cfg->descriptor_distance, cfg->maximum_distance_ratio_to_second_best, d_out, ca);
       PSLAM_LAUNCH_CHECK(ctx, "filter_fused_kernel");
       if ((rc = pslam_k_gn_iterate_dev(ctx, gn->factor, 0, gn->damping, gn->pose12, st.d_moving, st.d_fixed, ctx->proj_fixed_dim,
                                        st.d_gn_ncorr, st.d_gn_cf, st.d_gn_cm, st.d_gn_info, gn->prior, d_gn_out, d_done, d_status,

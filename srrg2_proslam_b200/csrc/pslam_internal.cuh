@@ -168,6 +168,31 @@ static inline int pslam_set_error(pslam_ctx* ctx, int code, const char* what, cu
   } while (0)
 
 #ifdef __CUDACC__
+// ---- programmatic dependent launch --------------------------------------------------------------
+// The per-frame paths are chains of short dependent kernels on one stream; between two of them the GPU idles for the launch
+// latency of the second (~2 us).  Launched with pslam_launch_pdl, a kernel is scheduled while its predecessor still runs
+// and parks in pslam_pdl_enter() -- its first statement -- until the predecessor has completed and its writes are visible;
+// only the launch overlaps, never the work.  (A kernel launched the ordinary way passes through pslam_pdl_enter() at once.)
+__device__ __forceinline__ void pslam_pdl_enter() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t pslam_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                           Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- device helpers ---------------------------------------------------------------------------
 __device__ __forceinline__ int reflect101(int i, int n) {
   // single reflection is enough: |overhang| <= 4 << n
