@@ -671,10 +671,19 @@ gn_iterate_kernel(LinParams c0, PriorParams prior, double damping, int n_iters, 
   constexpr int RED_CAP = 96, RED_PITCH = RED_CAP + 1;
   __shared__ double2 s_acc[(LZ_NACC / 2) * RED_PITCH];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (threadIdx.x < 9) S.R[threadIdx.x] = c0.R[threadIdx.x];
-  if (threadIdx.x < 3) S.t[threadIdx.x] = c0.t[threadIdx.x];
-  if (threadIdx.x == 0) s_ok = 1;
-  if (prior.enabled && threadIdx.x >= 64 && threadIdx.x < 100) S.Om[threadIdx.x - 64] = prior.Omega[threadIdx.x - 64];
+  // kernel parameters are copied with compile-time indices, one thread per array (a per-thread index into the parameter
+  // space serialises the constant loads and makes the compiler spill the struct to local memory first)
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) S.R[i] = c0.R[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) S.t[i] = c0.t[i];
+    s_ok = 1;
+  }
+  if (prior.enabled && threadIdx.x == 64) {
+#pragma unroll
+    for (int i = 0; i < 36; ++i) S.Om[i] = prior.Omega[i];
+  }
   __syncthreads();
   const int edim = (c0.kind == 2) ? 2 : 3;
   LinParams c = c0;
