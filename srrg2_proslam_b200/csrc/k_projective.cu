@@ -323,9 +323,10 @@ struct CompactArgs {
   PslamAlignCfg acfg;
   AlignInit init;
 };
-__device__ __forceinline__ void corr_compact(const int* __restrict__ acc_moving, int n_fixed, const float* __restrict__ scale, float d0,
+__device__ __forceinline__ void corr_compact(const int* acc_moving, int n_fixed, const float* __restrict__ scale, float d0,
                                              float d1, float d2, int* __restrict__ cf, int* __restrict__ cm, float* __restrict__ info,
-                                             int* __restrict__ n_corr, PslamAlignState* __restrict__ state, const PslamAlignCfg& acfg) {
+                                             int* __restrict__ n_corr, PslamAlignState* __restrict__ state, const PslamAlignCfg& acfg,
+                                             int n_projected) {
   __shared__ int s_warp[33];
   int running = 0;
   for (int base = 0; base < n_fixed; base += FF_THREADS) {
@@ -345,7 +346,7 @@ __device__ __forceinline__ void corr_compact(const int* __restrict__ acc_moving,
   }
   if (threadIdx.x == 0) {
     *n_corr = running;
-    if (state) align_control(state, acfg, running, n_fixed, acc_moving[-1]);  // acc_moving[-1] = the filter's n_projected
+    if (state) align_control(state, acfg, running, n_fixed, n_projected);
   }
 }
 
@@ -356,10 +357,18 @@ __device__ __forceinline__ void corr_compact(const int* __restrict__ acc_moving,
 // CTA: per frame the finder is called ~20 times on a few hundred points, so the search is bound by launch and copy
 // latencies, not by work -- 3 memsets + 3 kernels + 4 copies became 1 kernel + 1 copy.  `out` is the contiguous block the
 // host downloads: [n_projected][acc_moving x n_fixed][acc_dist x n_fixed (float bits)][cand x 4 n_moving].
+// SMEM: frame-sized fixed clouds (<= FF_SMEM_FIXED points) keep the two key arrays and the accepted moving index in shared
+// memory -- the passes below stop being L2 round trips.
+constexpr int FF_SMEM_FIXED = 2048;
+template <bool SMEM>
 __global__ void __launch_bounds__(FF_THREADS)
-filter_fused_kernel(const int* __restrict__ cand, int n_moving, int n_fixed, unsigned long long* __restrict__ key1,
-                    unsigned long long* __restrict__ key2, float max_dist, float max_ratio, int* __restrict__ out, CompactArgs ca) {
+filter_fused_kernel(const int* __restrict__ cand, int n_moving, int n_fixed, unsigned long long* __restrict__ g_key1,
+                    unsigned long long* __restrict__ g_key2, float max_dist, float max_ratio, int* __restrict__ out, CompactArgs ca) {
   __shared__ int s_proj;
+  __shared__ unsigned long long s_key1[SMEM ? FF_SMEM_FIXED : 1], s_key2[SMEM ? FF_SMEM_FIXED : 1];
+  __shared__ int s_res[SMEM ? FF_SMEM_FIXED : 1];
+  unsigned long long* key1 = SMEM ? s_key1 : g_key1;
+  unsigned long long* key2 = SMEM ? s_key2 : g_key2;
   const int tid = threadIdx.x;
   pslam_pdl_enter();
   if (ca.state && ca.init.valid) {  // first phase: the state starts here (the search of this phase took its pose by value too)
@@ -420,12 +429,14 @@ filter_fused_kernel(const int* __restrict__ cand, int n_moving, int n_fixed, uns
     }
     acc_moving[f] = res;
     acc_dist[f] = __float_as_int(dist);
+    if (SMEM) s_res[f] = res;
   }
   int* cand_out = out + 1 + 2 * n_fixed;
   for (int i = tid; i < 4 * n_moving; i += FF_THREADS) cand_out[i] = cand[i];
   if (ca.enabled) {  // the fused solver's input (+ the finder's decisions) in the same launch: one kernel boundary less per search
     __syncthreads();
-    corr_compact(acc_moving, n_fixed, ca.scale, ca.d0, ca.d1, ca.d2, ca.cf, ca.cm, ca.info, ca.n_corr, ca.state, ca.acfg);
+    corr_compact(SMEM ? s_res : acc_moving, n_fixed, ca.scale, ca.d0, ca.d1, ca.d2, ca.cf, ca.cm, ca.info, ca.n_corr, ca.state, ca.acfg,
+                 s_proj);
   }
 }
 
@@ -677,8 +688,9 @@ int pslam_k_projective_match(pslam_ctx* ctx, int n_fixed, int n_moving, const fl
                      gn->diagonal_info[1], gn->diagonal_info[2], st.d_gn_cf, st.d_gn_cm, st.d_gn_info, st.d_gn_ncorr, nullptr,
                      PslamAlignCfg{}};
   }
-  pslam_launch_pdl(filter_fused_kernel, dim3(1), dim3(FF_THREADS), 0, ctx->stream, st.d_cand, n_moving, n_fixed, st.d_key1, st.d_key2,
-                   cfg->descriptor_distance, cfg->maximum_distance_ratio_to_second_best, d_out, ca);
+  pslam_launch_pdl(n_fixed <= FF_SMEM_FIXED ? filter_fused_kernel<true> : filter_fused_kernel<false>, dim3(1), dim3(FF_THREADS), 0,
+                   ctx->stream, st.d_cand, n_moving, n_fixed, st.d_key1, st.d_key2, cfg->descriptor_distance,
+                   cfg->maximum_distance_ratio_to_second_best, d_out, ca);
   PSLAM_LAUNCH_CHECK(ctx, "filter_fused_kernel");
   if (gn) {
     int* d_done = d_out + gn_off;
@@ -793,8 +805,9 @@ int pslam_k_projective_align(pslam_ctx* ctx, int n_fixed, int n_moving, const ps
                        first ? pp_first : pp, st.d_moving, n_moving, st.d_desc_moving, st.d_lattice, n_fixed, st.d_desc_fixed, st.d_cand,
                        nullptr, st.d_fixed, ctx->proj_fixed_dim, first ? nullptr : d_state, n_fixed <= PJ_STAGE_MAX ? 1 : 0);
       PSLAM_LAUNCH_CHECK(ctx, "projective_search_kernel");
-      pslam_launch_pdl(filter_fused_kernel, dim3(1), dim3(FF_THREADS), 0, ctx->stream, st.d_cand, n_moving, n_fixed, st.d_key1, st.d_key2,
-                       cfg->descriptor_distance, cfg->maximum_distance_ratio_to_second_best, d_out, ca);
+      pslam_launch_pdl(n_fixed <= FF_SMEM_FIXED ? filter_fused_kernel<true> : filter_fused_kernel<false>, dim3(1), dim3(FF_THREADS), 0,
+                       ctx->stream, st.d_cand, n_moving, n_fixed, st.d_key1, st.d_key2, cfg->descriptor_distance,
+                       cfg->maximum_distance_ratio_to_second_best, d_out, ca);
       PSLAM_LAUNCH_CHECK(ctx, "filter_fused_kernel");
       if ((rc = pslam_k_gn_iterate_dev(ctx, gn->factor, 0, gn->damping, gn->pose12, st.d_moving, st.d_fixed, ctx->proj_fixed_dim,
                                        st.d_gn_ncorr, st.d_gn_cf, st.d_gn_cm, st.d_gn_info, gn->prior, d_gn_out, d_done, d_status,
