@@ -312,6 +312,67 @@ __device__ __forceinline__ int warp_std_sort_prefix(T* a, RP* rpos, int n, int n
   return sorted_end;
 }
 
+// The same replay with the partitions of one recursion level spread over the warps of the block (full sort, need == n).
+// The introsort recursion is a binary tree whose nodes touch disjoint ranges: [first, cut) and [cut, last) both continue with
+// the decremented depth limit, so the order in which the nodes of a level are processed does not matter.  Level by level:
+// every warp takes segments of the current list, partitions them exactly as warp_std_sort_prefix does and appends the
+// children longer than the insertion-sort threshold to the next list (at most n / 17 segments are alive at a time).
+// s_seg: 2 x SEG_CAP x 3 ints, s_cnt: 2 ints (shared memory).  rpos: n entries; a segment uses the slice of its own range.
+// Call with all NT threads; follow with __syncthreads() + block_final_positions(a, n, ...).
+template <int NT, int SEG_CAP, typename T, typename RP, typename Comp>
+__device__ __forceinline__ void block_std_sort_full(T* a, RP* rpos, int n, Comp comp, int* s_seg, int* s_cnt) {
+  const int threshold = 16;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (n <= threshold) return;
+  if (threadIdx.x == 0) {
+    s_seg[0] = 0;
+    s_seg[1] = n;
+    s_seg[2] = 2 * lg_(n);
+    s_cnt[0] = 1;
+    s_cnt[1] = 0;
+  }
+  __syncthreads();
+  int cur = 0;
+  for (;;) {
+    const int n_cur = s_cnt[cur];
+    if (n_cur == 0) break;
+    const int* seg = s_seg + cur * (3 * SEG_CAP);
+    int* nxt = s_seg + (cur ^ 1) * (3 * SEG_CAP);
+    for (int sidx = wid; sidx < n_cur; sidx += NT / 32) {
+      const int first = seg[3 * sidx], last = seg[3 * sidx + 1];
+      int depth = seg[3 * sidx + 2];
+      if (depth == 0) {
+        if (lane == 0) heap_sort_(a + first, last - first, comp);
+        __syncwarp();
+        continue;
+      }
+      --depth;
+      const int mid = first + (last - first) / 2;
+      if (lane == 0) move_median_to_first_(a, first, first + 1, mid, last - 1, comp);
+      __syncwarp();
+      const int cut = warp_partition_(a, rpos + first, first + 1, last, first, comp);
+      if (lane == 0) {
+        if (last - cut > threshold) {
+          const int k = atomicAdd(&s_cnt[cur ^ 1], 1);  // k < SEG_CAP: live segments are disjoint and longer than 16
+          nxt[3 * k] = cut;
+          nxt[3 * k + 1] = last;
+          nxt[3 * k + 2] = depth;
+        }
+        if (cut - first > threshold) {
+          const int k = atomicAdd(&s_cnt[cur ^ 1], 1);
+          nxt[3 * k] = first;
+          nxt[3 * k + 1] = cut;
+          nxt[3 * k + 2] = depth;
+        }
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_cnt[cur] = 0;
+    cur ^= 1;
+    __syncthreads();
+  }
+}
+
 // final insertion sort as a windowed stable rank; thread-parallel over the block.  out[pos] receives a[i] for the
 // positions pos < keep (the caller only needs the kept prefix).  Call after a __syncthreads().
 template <int NT, typename T, typename Comp>
