@@ -120,7 +120,7 @@ assemble_features_kernel(const uint8_t* __restrict__ images, long long image_pit
 //     in its place with one (t >> 31) & mask OR.  All per-lane constants (16 offsets, 8 multipliers, 8 masks) live in
 //     registers across the keypoints of the tile.
 // ---------------------------------------------------------------------------------------------
-constexpr int K4_WARPS = 4;
+constexpr int K4_WARPS = 2;  // measured us / image: 1 warp per tile CTA 0.461, 2 0.425, 3 0.458, 4 0.461, 8 0.604 (15.9 kB tile per CTA: 14 CTAs per SM)
 constexpr int ORB_REACH = 13;                           // bit_pattern_31_ reaches +-13 pixels (include/pslam_orb_pattern.h)
 constexpr int ORB_BOX_W = 176, ORB_BOX_H = ORB_TH + 2 * ORB_REACH, ORB_BOX_X0 = 16;  // box = [tx*128 - 16, +176) x [ty*64 - 13, +90)
 constexpr int ORB_BOX_BYTES = ORB_BOX_W * ORB_BOX_H;
