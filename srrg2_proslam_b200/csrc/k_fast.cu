@@ -750,10 +750,11 @@ bin_select_kernel(const int* __restrict__ row_count, const uint32_t* __restrict_
         unsigned short* s_rpos = reinterpret_cast<unsigned short*>(s_sort + sort_cap);
         for (int i = tid; i < n; i += NT) s_sort[i] = seg[i];
         __syncthreads();
-        if (tid < 32) {
-          const int se = pslam_sort::warp_std_sort_prefix(s_sort, s_rpos, n, kept, RespGreater());
-          if (tid == 0) s_rbegin = se;
-        }
+        // the partitions of a recursion level of the replay run on all warps of the CTA (at most sort_cap / 17 live segments)
+        constexpr int SEL_SEG_CAP = 128;
+        __shared__ int s_seg[2 * 3 * SEL_SEG_CAP], s_cnt[3];
+        const int se = pslam_sort::block_std_sort_prefix<NT, SEL_SEG_CAP>(s_sort, s_rpos, n, kept, RespGreater(), s_seg, s_cnt);
+        if (tid == 0) s_rbegin = se;
         __syncthreads();
         pslam_sort::block_final_positions<NT>(s_sort, s_rbegin, kept, seg, RespGreater());
       } else if (tid == 0) {

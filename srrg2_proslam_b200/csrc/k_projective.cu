@@ -53,7 +53,7 @@ lattice_build_kernel(const float* __restrict__ coords, int dim, int n, unsigned 
   __threadfence_block();
   __syncthreads();
   constexpr int LB_SEG_CAP = 256;  // >= 4096 / 17 live segments
-  __shared__ int s_seg[2 * 3 * LB_SEG_CAP], s_cnt[2];
+  __shared__ int s_seg[2 * 3 * LB_SEG_CAP], s_cnt[3];
   if (in_smem && n <= 4096) {
     // frame-sized clouds: the partitions of a recursion level run on all the warps of the block
     pslam_sort::block_std_sort_full<LB_THREADS, LB_SEG_CAP>(a, reinterpret_cast<unsigned short*>(s_l + smem_cap), n, RowLess(), s_seg,

@@ -317,19 +317,22 @@ __device__ __forceinline__ int warp_std_sort_prefix(T* a, RP* rpos, int n, int n
 // the decremented depth limit, so the order in which the nodes of a level are processed does not matter.  Level by level:
 // every warp takes segments of the current list, partitions them exactly as warp_std_sort_prefix does and appends the
 // children longer than the insertion-sort threshold to the next list (at most n / 17 segments are alive at a time).
-// s_seg: 2 x SEG_CAP x 3 ints, s_cnt: 2 ints (shared memory).  rpos: n entries; a segment uses the slice of its own range.
+// s_seg: 2 x SEG_CAP x 3 ints, s_cnt: 3 ints (shared memory).  rpos: n entries; a segment uses the slice of its own range.
 // Call with all NT threads; follow with __syncthreads() + block_final_positions(a, n, ...).
+// need < n: only the first `need` outputs are wanted (std_sort_prefix's pruning: a right part that starts at or beyond `need`
+// is dropped and the smallest such cut is the returned sorted_end, kept in s_cnt[2]); need == n: full sort, returns n.
 template <int NT, int SEG_CAP, typename T, typename RP, typename Comp>
-__device__ __forceinline__ void block_std_sort_full(T* a, RP* rpos, int n, Comp comp, int* s_seg, int* s_cnt) {
+__device__ __forceinline__ int block_std_sort_prefix(T* a, RP* rpos, int n, int need, Comp comp, int* s_seg, int* s_cnt) {
   const int threshold = 16;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (n <= threshold) return;
+  if (n <= threshold) return n;
   if (threadIdx.x == 0) {
     s_seg[0] = 0;
     s_seg[1] = n;
     s_seg[2] = 2 * lg_(n);
     s_cnt[0] = 1;
     s_cnt[1] = 0;
+    s_cnt[2] = n;
   }
   __syncthreads();
   int cur = 0;
@@ -352,7 +355,9 @@ __device__ __forceinline__ void block_std_sort_full(T* a, RP* rpos, int n, Comp 
       __syncwarp();
       const int cut = warp_partition_(a, rpos + first, first + 1, last, first, comp);
       if (lane == 0) {
-        if (last - cut > threshold) {
+        if (cut >= need) {
+          atomicMin(&s_cnt[2], cut);  // pruned right part: everything from `cut` on is beyond the wanted prefix
+        } else if (last - cut > threshold) {
           const int k = atomicAdd(&s_cnt[cur ^ 1], 1);  // k < SEG_CAP: live segments are disjoint and longer than 16
           nxt[3 * k] = cut;
           nxt[3 * k + 1] = last;
@@ -371,6 +376,11 @@ __device__ __forceinline__ void block_std_sort_full(T* a, RP* rpos, int n, Comp 
     cur ^= 1;
     __syncthreads();
   }
+  return s_cnt[2];
+}
+template <int NT, int SEG_CAP, typename T, typename RP, typename Comp>
+__device__ __forceinline__ void block_std_sort_full(T* a, RP* rpos, int n, Comp comp, int* s_seg, int* s_cnt) {
+  block_std_sort_prefix<NT, SEG_CAP>(a, rpos, n, n, comp, s_seg, s_cnt);
 }
 
 // final insertion sort as a windowed stable rank; thread-parallel over the block.  out[pos] receives a[i] for the
